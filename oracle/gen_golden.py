@@ -1,0 +1,164 @@
+"""Generate tests/golden/*.npz by executing the UNMODIFIED reference (this container only).
+
+    python oracle/gen_golden.py            # writes tests/golden/
+
+*** TEST INFRASTRUCTURE ONLY ***  Every fixture is (seeded input description, reference output).
+Weights are ``rsgnet_b200.models._params.synth_state_dict`` of this package's parameter
+containers loaded into the reference model with ``strict=True`` -- which also proves the
+state_dict names/shapes are drop-in compatible.  Inputs come from ``rsgnet_b200.synth`` (NumPy
+RandomState: identical bytes on any machine), so fixtures store seeds, not inputs.
+"""
+import os
+import sys
+
+import numpy as np
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+
+from oracle import ref_import  # noqa: E402
+from rsgnet_b200 import presets, synth  # noqa: E402
+from rsgnet_b200.models import _params, pose_hrnet, pose_rsgnet  # noqa: E402
+
+OUT = os.path.join(ROOT, 'tests', 'golden')
+SUB = 4099          # prime stride for sub-sampled tensors
+
+
+def subsample(t):
+    flat = t.detach().reshape(-1).numpy()
+    return flat[::SUB].copy() if flat.size > 65536 else flat.copy()
+
+
+def model_case(key, batch, seed, full):
+    cfg = presets.preset(key)
+    name = cfg.MODEL.NAME
+    ours = (pose_rsgnet if name == 'pose_rsgnet' else pose_hrnet).get_pose_net(cfg, False)
+    sd = _params.synth_state_dict(ours, seed=seed)
+    ref = ref_import.ref_model(cfg, name)
+    missing = ref.load_state_dict(sd, strict=True)
+    assert not missing.missing_keys and not missing.unexpected_keys
+    x = torch.from_numpy(synth.crops(batch, cfg.MODEL.IMAGE_SIZE, seed=seed + 11))
+    taps = {}
+    hooks = []
+    top = dict(ref.named_children())
+    for nm in ('layer1', 'stage2', 'stage3', 'stage4', 'vis_conv', 'type_conv',
+               'predict_contact_net', 'kpt_net', 'predict_net'):
+        if nm in top:
+            def hook(_m, _i, o, nm=nm):
+                if isinstance(o, (list, tuple)):
+                    for b, t in enumerate(o):
+                        taps[f'{nm}.{b}'] = t.detach().clone()
+                else:
+                    taps[nm] = o.detach().clone()
+            hooks.append(top[nm].register_forward_hook(hook))
+    with torch.no_grad():
+        out = ref(x)
+    for h in hooks:
+        h.remove()
+    rec = dict(preset=key, batch=batch, seed=seed, sub=SUB)
+    if name == 'pose_hrnet':
+        outs = dict(heatmaps=out)
+    else:
+        outs = dict(multi_kpt_scores=out[0], kpt_scores=out[1], limbs_scores=out[2],
+                    relation_scores=out[3])
+    for k, v in outs.items():
+        if full or k == 'kpt_scores' or k == 'heatmaps':
+            rec['out.' + k] = v.numpy().astype(np.float32)
+        else:
+            rec['sub.' + k] = subsample(v)
+        rec['absmax.' + k] = np.float32(v.abs().max())
+    for k, v in taps.items():
+        rec['tap.' + k] = v.numpy().astype(np.float32) if full else subsample(v)
+        rec['tapabsmax.' + k] = np.float32(v.abs().max())
+    fn = os.path.join(OUT, f'model_{key}.npz')
+    np.savez_compressed(fn, **rec)
+    print('wrote', fn, os.path.getsize(fn) // 1024, 'KiB')
+
+
+def decode_cases():
+    f = ref_import.ref_functions()
+    for tag, (k, h, w, n) in dict(small=(17, 16, 12, 24), hrnet=(17, 64, 48, 6),
+                                  rsgnet=(14, 128, 96, 3)).items():
+        hm = np.concatenate([synth.heatmaps(n, k, h, w, seed=2),
+                             synth.crafted_heatmaps(k, h, w)])
+        n_all = hm.shape[0]
+        c, s = synth.centers_scales(n_all, seed=5)
+        rec = dict(k=k, h=h, w=w, n=n, seed=2, cs_seed=5)
+        for pp in (0, 1):
+            cfg = presets.make_cfg(post_process=bool(pp))
+            preds, maxvals = f['get_final_preds'](cfg, hm.copy(), c, s)
+            rec[f'preds_pp{pp}'] = preds.astype(np.float32)
+            rec[f'maxvals_pp{pp}'] = maxvals.astype(np.float32)
+            # heat-map-space coordinates: run the reference with an identity-like affine is not
+            # possible, so recover them from get_max_preds (+ our own restated offsets, checked
+            # in tests against preds through the affine)
+        coords, mv = f['get_max_preds'](hm.copy())
+        rec['coords_raw'] = coords.astype(np.float32)
+        # flip path: reference flip_back on a fresh copy + shift + average (function.py:417-427)
+        rs = np.random.RandomState(9)
+        nb = 2 if h * w <= 3072 else 1
+        a = rs.standard_normal((nb, k, h, w)).astype(np.float32)
+        b = rs.standard_normal((nb, k, h, w)).astype(np.float32)
+        pairs = presets.flip_pairs_for(k)
+        fb = f['flip_back'](b.copy(), pairs)
+        fb = np.ascontiguousarray(fb)
+        t = torch.from_numpy(fb.copy())
+        t[:, :, :, 1:] = t.clone()[:, :, :, 0:-1]
+        avg = ((torch.from_numpy(a) + t) * 0.5).numpy()
+        rec['flip_seed'] = 9
+        rec['flip_avg'] = avg.astype(np.float32)
+        rec['flip_n'] = nb
+        if h * w <= 192:
+            rec['flip_back'] = fb.astype(np.float32)
+        fn = os.path.join(OUT, f'decode_{tag}.npz')
+        np.savez_compressed(fn, **rec)
+        print('wrote', fn, os.path.getsize(fn) // 1024, 'KiB')
+
+
+def nms_cases():
+    f = ref_import.ref_functions()
+    from oracle.nms_oracle import CROWDPOSE_SIGMAS
+    for tag, (k, sig) in dict(coco=(17, None), crowdpose=(14, CROWDPOSE_SIGMAS)).items():
+        kpts, scores, areas, off = synth.detections(300, 20, k, seed=3, ragged=True)
+        keeps, counts = [], []
+        for i in range(len(off) - 1):
+            db = [dict(keypoints=kpts[j], score=scores[j], area=areas[j])
+                  for j in range(off[i], off[i + 1])]
+            keep = f['oks_nms'](db, 0.9, sig)
+            keeps.extend(int(v) for v in keep)
+            counts.append(len(keep))
+        # a few thresholds on one bigger image
+        kb, sb, ab, _ = synth.detections(1, 150, k, seed=4)
+        big = {}
+        for th in (0.5, 0.9, 0.99):
+            db = [dict(keypoints=kb[j], score=sb[j], area=ab[j]) for j in range(len(sb))]
+            big[f'big_keep_{th}'] = np.asarray(f['oks_nms'](db, th, sig), np.int32)
+        fn = os.path.join(OUT, f'nms_{tag}.npz')
+        np.savez_compressed(fn, k=k, seed=3, n_imgs=300, per_img=20, thresh=0.9,
+                            keep=np.asarray(keeps, np.int32), counts=np.asarray(counts, np.int32),
+                            big_seed=4, big_n=150, **big)
+        print('wrote', fn, os.path.getsize(fn) // 1024, 'KiB')
+
+
+def main():
+    assert ref_import.available(), 'needs /root/reference'
+    os.makedirs(OUT, exist_ok=True)
+    torch.set_num_threads(8)
+    which = sys.argv[1:] or ['decode', 'nms', 'model']
+    if 'decode' in which:
+        decode_cases()
+    if 'nms' in which:
+        nms_cases()
+    if 'model' in which:
+        model_case('tiny', 2, 0, full=True)
+        model_case('tiny_cp_sub', 2, 1, full=True)
+        model_case('tiny_hrnet', 2, 2, full=True)
+        model_case('w32_coco', 1, 3, full=False)
+        model_case('w32_crowdpose', 1, 4, full=False)
+        model_case('hrnet_w32_coco', 1, 5, full=False)
+        model_case('w48_coco_384', 1, 6, full=False)
+
+
+if __name__ == '__main__':
+    main()

@@ -1,0 +1,91 @@
+"""CPU oracle for OKS-NMS and the evaluate()-side rescoring.   *** TEST INFRASTRUCTURE ONLY ***
+
+NumPy restatement; only ``tests/``, ``__graft_entry__.smoke()`` and ``bench.py``'s cpu_baseline /
+``--impl reference`` leg may import it.  Pinned by ``tests/golden/nms_*.npz`` produced by the
+unmodified reference's ``oks_nms`` (``oracle/gen_golden.py``).
+
+Reference lines followed (paths under /root/reference):
+  lib/nms/nms.py:75-94            oks_iou (dx,dy,squares in fp32; the rest fp64; np.sum order)
+  lib/nms/nms.py:97-124           oks_nms greedy sweep (keep oks <= thresh)
+  lib/dataset/crowdpose.py:1294-1306   rescoring: box_score * mean(maxval > in_vis_thre)
+"""
+import numpy as np
+
+COCO_SIGMAS = np.array([.26, .25, .25, .35, .35, .79, .79, .72, .72, .62, .62, 1.07, 1.07,
+                        .87, .87, .89, .89]) / 10.0
+CROWDPOSE_SIGMAS = np.array([.79, .79, .72, .72, .62, .62, 1.07, 1.07, .87, .87, .89, .89,
+                             .35, .35]) / 10.0
+
+
+def oks_iou(g, d, a_g, a_d, sigmas=None, in_vis_thre=None):
+    """nms.py:75-94.  g: f32[3K]; d: f32[M,3K]; areas fp64."""
+    if not isinstance(sigmas, np.ndarray):
+        sigmas = COCO_SIGMAS
+    var = (sigmas * 2) ** 2
+    xg, yg, vg = g[0::3], g[1::3], g[2::3]
+    ious = np.zeros(d.shape[0])
+    for i in range(d.shape[0]):
+        dx = d[i, 0::3] - xg
+        dy = d[i, 1::3] - yg
+        e = (dx ** 2 + dy ** 2) / var / ((a_g + a_d[i]) / 2 + np.spacing(1)) / 2
+        if in_vis_thre is not None:
+            # the reference evaluates `list(a) and list(b)`, i.e. the SECOND list only
+            e = e[list(d[i, 2::3] > in_vis_thre)]
+        ious[i] = np.sum(np.exp(-e)) / e.shape[0] if e.shape[0] != 0 else 0.0
+    return ious
+
+
+def oks_order(scores):
+    """Descending order used by the sweep: reverse of NumPy's ascending argsort (nms.py:112)."""
+    return np.asarray(scores).argsort()[::-1]
+
+
+def oks_nms(kpts_db, thresh, sigmas=None, in_vis_thre=None):
+    """nms.py:97-124.  Returns indices in greedy selection order."""
+    if len(kpts_db) == 0:
+        return []
+    scores = np.array([k['score'] for k in kpts_db])
+    kpts = np.array([k['keypoints'].flatten() for k in kpts_db])
+    areas = np.array([k['area'] for k in kpts_db])
+    order = oks_order(scores)
+    keep = []
+    while order.size > 0:
+        i = order[0]
+        keep.append(i)
+        ovr = oks_iou(kpts[i], kpts[order[1:]], areas[i], areas[order[1:]], sigmas, in_vis_thre)
+        order = order[np.where(ovr <= thresh)[0] + 1]
+    return keep
+
+
+def oks_nms_arrays(kpts, scores, areas, thresh, sigmas=None):
+    """Same sweep on plain arrays (kpts f32 [n,K,3]); also returns the minimum |oks-thresh|
+    margin seen, so tests can tell whether a 1-ulp exp difference could flip a decision."""
+    n = kpts.shape[0]
+    if n == 0:
+        return [], np.inf
+    flat = kpts.reshape(n, -1)
+    order = oks_order(scores)
+    keep, margin = [], np.inf
+    while order.size > 0:
+        i = order[0]
+        keep.append(int(i))
+        ovr = oks_iou(flat[i], flat[order[1:]], areas[i], areas[order[1:]], sigmas)
+        if ovr.size:
+            margin = min(margin, float(np.min(np.abs(ovr - thresh))))
+        order = order[np.where(ovr <= thresh)[0] + 1]
+    return keep, margin
+
+
+def rescore(box_score, maxvals, in_vis_thre):
+    """crowdpose.py:1294-1306 / coco.py:1249-1261 for one detection.
+    maxvals: fp32 [K]; accumulation runs in fp32 (np.float32 scalars), product with the fp64
+    box score in fp64."""
+    kpt_score = 0
+    valid = 0
+    for t in maxvals:
+        if t > in_vis_thre:
+            kpt_score = kpt_score + t
+            valid += 1
+    if valid != 0:
+        kpt_score = kpt_score / valid
+    return kpt_score * box_score

@@ -1,0 +1,97 @@
+"""Import the UNMODIFIED reference hot path from /root/reference (this container only).
+
+*** TEST INFRASTRUCTURE ONLY ***  Used by ``oracle/gen_golden.py`` (fixture generation) and by
+CPU tests that are skipped when /root/reference is absent (it does not exist on the GPU box).
+The three shims are the ones verified in SURVEY.md App. C: an empty pre-registered ``models``
+package (its __init__ imports modules that are not in the tree), dummy ``nms.cpu_nms`` /
+``nms.gpu_nms`` extension modules (never called by oks_nms), and an attribute-dict config in
+place of yacs.  No reference source is copied or modified.
+"""
+import contextlib
+import importlib
+import io
+import os
+import shutil
+import sys
+import tempfile
+import types
+
+import yaml
+
+REF = os.environ.get('RSG_REFERENCE_ROOT', '/root/reference')
+
+
+def available():
+    return os.path.isdir(os.path.join(REF, 'lib', 'models'))
+
+
+class AttrDict(dict):
+    __getattr__ = dict.__getitem__
+
+
+def to_attr(d):
+    if isinstance(d, dict):
+        return AttrDict({k: to_attr(v) for k, v in d.items()})
+    return d
+
+
+def load_yaml_cfg(relpath, **model_overrides):
+    with open(os.path.join(REF, relpath)) as f:
+        cfg = yaml.safe_load(f)
+    m = cfg['MODEL']
+    m.setdefault('UDP_POSE_ON', False)
+    m.setdefault('RELATION_SUB_SAMPLE', False)
+    m.setdefault('UP_SCALE', 1)
+    if isinstance(m.get('NUM_TYPE_VECTOR'), list):
+        m['NUM_TYPE_VECTOR'] = m['NUM_TYPE_VECTOR'][0]
+    m.update(model_overrides)
+    return to_attr(cfg)
+
+
+_installed = False
+
+
+def _install_shims():
+    global _installed
+    if _installed:
+        return
+    pkg = types.ModuleType('models')
+    pkg.__path__ = [os.path.join(REF, 'lib', 'models')]
+    sys.modules['models'] = pkg
+    for n in ('nms.cpu_nms', 'nms.gpu_nms'):
+        m = types.ModuleType(n)
+        setattr(m, n.split('.')[1], None)
+        sys.modules[n] = m
+    sys.path.insert(0, os.path.join(REF, 'lib'))
+    _installed = True
+
+
+def ref_model(cfg, name):
+    """name: 'pose_rsgnet' | 'pose_hrnet'.  Handles the CWD-relative kpt_word_embs.pkl."""
+    _install_shims()
+    mod = importlib.import_module('models.' + name)
+    cwd = os.getcwd()
+    tmp = None
+    try:
+        if name == 'pose_rsgnet':
+            k = int(cfg.MODEL.NUM_JOINTS)
+            src = os.path.join(REF, 'kpt_word_embs.pkl' if k == 17 else 'cp_kpt_word_embs.pkl')
+            tmp = tempfile.mkdtemp()
+            shutil.copy(src, os.path.join(tmp, 'kpt_word_embs.pkl'))
+            os.chdir(tmp)
+        with contextlib.redirect_stdout(io.StringIO()):
+            model = mod.get_pose_net(cfg, is_train=False)
+    finally:
+        os.chdir(cwd)
+        if tmp:
+            shutil.rmtree(tmp, ignore_errors=True)
+    return model.eval()
+
+
+def ref_functions():
+    _install_shims()
+    from core.inference import get_final_preds, get_max_preds
+    from nms.nms import oks_iou, oks_nms
+    from utils.transforms import flip_back
+    return dict(get_final_preds=get_final_preds, get_max_preds=get_max_preds,
+                oks_nms=oks_nms, oks_iou=oks_iou, flip_back=flip_back)

@@ -1,0 +1,94 @@
+"""Seeded synthetic workloads: crops, heat-maps, centres/scales, detections.
+
+NumPy's legacy ``RandomState`` streams are stable across platforms and versions, so the same
+seed gives the same bytes here, on the GPU box and in the committed golden fixtures.
+"""
+import numpy as np
+
+
+def crops(n, image_wh, seed=0):
+    """fp32 NCHW ~N(0,1) (ImageNet-normalised images look like this)."""
+    rs = np.random.RandomState(seed)
+    return rs.standard_normal((n, 3, image_wh[1], image_wh[0])).astype(np.float32)
+
+
+def centers_scales(n, seed=0):
+    rs = np.random.RandomState(seed + 1000)
+    c = rs.uniform(20, 600, (n, 2)).astype(np.float32)
+    s = rs.uniform(0.3, 4.0, (n, 2)).astype(np.float32)
+    return c, s
+
+
+def heatmaps(n, k, h, w, seed=2, dead_frac=0.15, noise=0.01):
+    """Gaussian bump (sigma 2, centre anywhere incl. borders, amplitude U(0.1,1)) + N(0,noise);
+    `dead_frac` of the maps get 2.0 subtracted so that their max <= 0."""
+    rs = np.random.RandomState(seed)
+    cx = rs.uniform(-1, w, (n, k, 1, 1)).astype(np.float32)
+    cy = rs.uniform(-1, h, (n, k, 1, 1)).astype(np.float32)
+    amp = rs.uniform(0.1, 1.0, (n, k, 1, 1)).astype(np.float32)
+    xs = np.arange(w, dtype=np.float32)[None, None, None, :]
+    ys = np.arange(h, dtype=np.float32)[None, None, :, None]
+    hm = amp * np.exp(-((xs - cx) ** 2 + (ys - cy) ** 2) / np.float32(8.0))
+    hm = hm + rs.normal(0, noise, hm.shape).astype(np.float32)
+    dead = rs.uniform(size=(n, k, 1, 1)) < dead_frac
+    hm = np.where(dead, hm - np.float32(2.0), hm)
+    return np.ascontiguousarray(hm.astype(np.float32))
+
+
+def crafted_heatmaps(k, h, w):
+    """Edge cases of App. B.1 as one [C,k,h,w] batch: constant map (tie -> index 0), all-negative,
+    all-zero, maxima at the four corners and at px in {1,2,W-3,W-2}, equal neighbours."""
+    cases = []
+
+    def blank(v=0.0):
+        return np.full((k, h, w), v, np.float32)
+    cases.append(blank(0.5))
+    cases.append(blank(-1.0))
+    cases.append(blank(0.0))
+    for (y, x) in ((0, 0), (0, w - 1), (h - 1, 0), (h - 1, w - 1)):
+        m = blank(0.01)
+        m[:, y, x] = 1.0
+        cases.append(m)
+    for x in (1, 2, w - 3, w - 2):
+        for y in (1, 2, h - 3, h - 2):
+            m = blank(0.0)
+            m[:, y, x] = 1.0
+            m[:, y, min(x + 1, w - 1)] = 0.5
+            m[:, min(y + 1, h - 1), x] = 0.25
+            cases.append(m)
+    m = blank(0.0)                       # symmetric neighbours -> sign(0) = 0
+    m[:, h // 2, w // 2] = 1.0
+    m[:, h // 2, w // 2 - 1] = m[:, h // 2, w // 2 + 1] = 0.3
+    m[:, h // 2 - 1, w // 2] = m[:, h // 2 + 1, w // 2] = 0.3
+    cases.append(m)
+    m = blank(0.0)                       # duplicated maximum -> first occurrence wins
+    m[:, 3, 5] = 0.7
+    m[:, 2, w - 4] = 0.7
+    cases.append(m)
+    return np.stack(cases).astype(np.float32)
+
+
+def detections(n_imgs, per_img, k, seed=3, ragged=False):
+    """Pose detections grouped per image: 3 pose clusters per image with jitter
+    sigma in {1,5,30} px so that NMS both keeps and suppresses; distinct scores.
+    Returns kpts f32 [N,k,3], scores f64 [N], areas f64 [N], offsets i32 [n_imgs+1]."""
+    rs = np.random.RandomState(seed)
+    counts = (rs.randint(0, 2 * per_img + 1, n_imgs) if ragged
+              else np.full(n_imgs, per_img)).astype(np.int64)
+    offsets = np.zeros(n_imgs + 1, np.int32)
+    offsets[1:] = np.cumsum(counts)
+    n = int(offsets[-1])
+    kpts = np.zeros((n, k, 3), np.float32)
+    for i in range(n_imgs):
+        c = int(counts[i])
+        if c == 0:
+            continue
+        base = rs.uniform(50, 500, (3, k, 2))
+        which = rs.randint(0, 3, c)
+        sig = np.array([1.0, 5.0, 30.0])[rs.randint(0, 3, c)]
+        pts = base[which] + rs.normal(0, 1, (c, k, 2)) * sig[:, None, None]
+        kpts[offsets[i]:offsets[i + 1], :, :2] = pts.astype(np.float32)
+    kpts[:, :, 2] = rs.uniform(0, 1, (n, k)).astype(np.float32)
+    scores = rs.permutation(n).astype(np.float64) / max(n, 1) + rs.uniform(0, 0.5 / max(n, 1), n)
+    areas = rs.uniform(2e3, 4e4, n).astype(np.float32).astype(np.float64)
+    return kpts, scores, areas, offsets

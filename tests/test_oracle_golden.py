@@ -1,0 +1,110 @@
+"""The CPU oracle (oracle/*.py) against fixtures produced by the unmodified reference
+(oracle/gen_golden.py).  This is what pins the oracle; everything GPU-side is then compared
+with the oracle."""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import decode_oracle, model_oracle, nms_oracle
+from rsgnet_b200 import presets, synth
+from rsgnet_b200.models import _params, pose_hrnet, pose_rsgnet
+
+MODEL_CASES = ['tiny', 'tiny_cp_sub', 'tiny_hrnet', 'w32_coco', 'w32_crowdpose', 'hrnet_w32_coco']
+
+
+def _load(golden_dir, name):
+    return np.load(os.path.join(golden_dir, name), allow_pickle=False)
+
+
+def ulp_diff(a, b):
+    a = np.ascontiguousarray(a, np.float32).view(np.int32).astype(np.int64)
+    b = np.ascontiguousarray(b, np.float32).view(np.int32).astype(np.int64)
+    a = np.where(a < 0, np.int64(-2 ** 31) - a, a)
+    b = np.where(b < 0, np.int64(-2 ** 31) - b, b)
+    return np.abs(a - b)
+
+
+@pytest.mark.parametrize('tag', ['small', 'hrnet', 'rsgnet'])
+def test_decode_oracle_vs_reference(golden_dir, tag):
+    g = _load(golden_dir, f'decode_{tag}.npz')
+    k, h, w, n = int(g['k']), int(g['h']), int(g['w']), int(g['n'])
+    hm = np.concatenate([synth.heatmaps(n, k, h, w, seed=int(g['seed'])),
+                         synth.crafted_heatmaps(k, h, w)])
+    c, s = synth.centers_scales(hm.shape[0], seed=int(g['cs_seed']))
+    coords, mv = decode_oracle.get_max_preds(hm)
+    assert np.array_equal(coords, g['coords_raw'])
+    for pp in (0, 1):
+        preds, maxvals = decode_oracle.get_final_preds(bool(pp), hm, c, s)
+        assert np.array_equal(maxvals, g[f'maxvals_pp{pp}'])
+        d = ulp_diff(preds, g[f'preds_pp{pp}'])
+        assert d.max() <= 1, d.max()
+        assert (d == 0).mean() > 0.95
+    # flip + shift + average is exact fp32 arithmetic
+    rs = np.random.RandomState(int(g['flip_seed']))
+    nb = int(g['flip_n'])
+    a = rs.standard_normal((nb, k, h, w)).astype(np.float32)
+    b = rs.standard_normal((nb, k, h, w)).astype(np.float32)
+    avg = decode_oracle.flip_average(a, b, presets.flip_pairs_for(k), shift=True)
+    assert np.array_equal(avg, g['flip_avg'])
+    if 'flip_back' in g:
+        assert np.array_equal(decode_oracle.flip_back(b, presets.flip_pairs_for(k)),
+                              g['flip_back'])
+
+
+@pytest.mark.parametrize('tag', ['coco', 'crowdpose'])
+def test_nms_oracle_vs_reference(golden_dir, tag):
+    g = _load(golden_dir, f'nms_{tag}.npz')
+    k = int(g['k'])
+    sig = None if tag == 'coco' else nms_oracle.CROWDPOSE_SIGMAS
+    kpts, scores, areas, off = synth.detections(int(g['n_imgs']), int(g['per_img']), k,
+                                                seed=int(g['seed']), ragged=True)
+    keeps, counts = [], []
+    for i in range(len(off) - 1):
+        keep, _ = nms_oracle.oks_nms_arrays(kpts[off[i]:off[i + 1]], scores[off[i]:off[i + 1]],
+                                            areas[off[i]:off[i + 1]], float(g['thresh']), sig)
+        keeps.extend(keep)
+        counts.append(len(keep))
+    assert counts == list(g['counts'])
+    assert keeps == list(g['keep'])
+    kb, sb, ab, _ = synth.detections(1, int(g['big_n']), k, seed=int(g['big_seed']))
+    for th in (0.5, 0.9, 0.99):
+        keep, _ = nms_oracle.oks_nms_arrays(kb, sb, ab, th, sig)
+        assert keep == list(g[f'big_keep_{th}'])
+    # dict interface
+    db = [dict(keypoints=kb[j], score=sb[j], area=ab[j]) for j in range(len(sb))]
+    assert [int(v) for v in nms_oracle.oks_nms(db, 0.9, sig)] == list(g['big_keep_0.9'])
+    assert nms_oracle.oks_nms([], 0.9) == []
+
+
+@pytest.mark.parametrize('key', MODEL_CASES)
+def test_model_oracle_vs_reference(golden_dir, key):
+    g = _load(golden_dir, f'model_{key}.npz')
+    cfg = presets.preset(key)
+    mod = pose_rsgnet if cfg.MODEL.NAME == 'pose_rsgnet' else pose_hrnet
+    net = mod.get_pose_net(cfg, False)
+    sd = _params.synth_state_dict(net, seed=int(g['seed']))
+    x = torch.from_numpy(synth.crops(int(g['batch']), cfg.MODEL.IMAGE_SIZE,
+                                     seed=int(g['seed']) + 11))
+    torch.set_num_threads(max(1, len(os.sched_getaffinity(0))))
+    stages = {}
+    out = model_oracle.forward(sd, cfg, x, stages=stages)
+    if cfg.MODEL.NAME == 'pose_hrnet':
+        outs = dict(heatmaps=out)
+    else:
+        outs = dict(zip(('multi_kpt_scores', 'kpt_scores', 'limbs_scores', 'relation_scores'),
+                        out))
+    sub = int(g['sub'])
+    for name, t in outs.items():
+        ref_absmax = float(g['absmax.' + name])
+        if 'out.' + name in g:
+            ref = g['out.' + name]
+            got = t.numpy()
+        else:
+            ref = g['sub.' + name]
+            flat = t.reshape(-1).numpy()
+            got = flat[::sub] if flat.size > 65536 else flat
+        assert got.shape == ref.shape
+        err = np.abs(got - ref).max()
+        assert err <= 2e-5 * max(ref_absmax, 1e-3), (name, err, ref_absmax)
