@@ -1,0 +1,165 @@
+/* librsg_b200 -- C ABI of the B200-native (sm_100a) RSGNet per-crop inference hot path.
+ *
+ * Every entry point takes plain pointers and sizes; `stream` is a cudaStream_t passed as void*
+ * (NULL = the legacy default stream).  Unless an entry point says "host", every data pointer is a
+ * DEVICE pointer and the call is asynchronous on `stream`.  All functions return 0 on success;
+ * otherwise a non-zero code, with a thread-local message available from rsg_last_error().
+ * There is no CPU fallback anywhere in this library.
+ *
+ * Each group cites the reference interface it replaces (paths under the reference checkout).
+ */
+#ifndef RSG_B200_H_
+#define RSG_B200_H_
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define RSG_ABI_VERSION 1
+
+int rsg_abi_version(void);
+const char* rsg_last_error(void);
+/* Device properties the host side sizes work against: out[0]=SM count, out[1]=cc major,
+ * out[2]=cc minor, out[3]=max dynamic smem per block (bytes). */
+int rsg_device_info(int* out4);
+
+/* ------------------------------------------------------------------------------------------
+ * Post-processing.
+ * ---------------------------------------------------------------------------------------- */
+
+/* Fused flip-test average + argmax decode + quarter-pixel offset + inverse crop affine.
+ * Replaces lib/core/function.py:417-427 (flip_back, 1-px shift, (a+b)*0.5),
+ * lib/core/inference.py:21-82 (get_max_preds, get_final_preds) and
+ * lib/utils/transforms.py:57-103 (transform_preds / get_affine_transform(inv=1)).
+ *   hm          f32 [N,K,H,W]  heat-maps of the un-flipped crops
+ *   hm_flipped  f32 [N,K,H,W]  RAW heat-maps of the W-flipped crops, or NULL (no flip test)
+ *   flip_perm   i32 [K]        channel permutation pi(k) of flip_back (ignored when hm_flipped==NULL)
+ *   center,scale f32 [N,2]     crop centre / scale (scale[:,1] is unused, as in the reference)
+ *   post_process            TEST.POST_PROCESS  (quarter-pixel offset)
+ *   shift                   TEST.SHIFT_HEATMAP (1-px shift of the flipped map)
+ *   preds   f32 [N,K,2]  image-space coordinates          (NULL = skip)
+ *   maxvals f32 [N,K]    value at the arg-max
+ *   coords  f32 [N,K,2]  heat-map-space coordinates incl. the +-0.25 offset (NULL = skip)
+ *   avg_out f32 [N,K,H,W] averaged heat-maps (NULL = never materialised) */
+int rsg_flip_avg_decode(void* stream, const float* hm, const float* hm_flipped,
+                        const int32_t* flip_perm, int N, int K, int H, int W,
+                        const float* center, const float* scale, int post_process, int shift,
+                        float* preds, float* maxvals, float* coords, float* avg_out);
+
+/* lib/utils/transforms.py:23-37 flip_back: out[n,k,y,x] = in[n,pi(k),y,W-1-x]. */
+int rsg_flip_back(void* stream, const float* in, float* out, const int32_t* flip_perm,
+                  int N, int K, int H, int W);
+
+/* Segmented greedy OKS-NMS, one image per CTA.  Replaces lib/nms/nms.py:75-124
+ * (oks_iou + oks_nms) for all images of an evaluate() call at once
+ * (lib/dataset/crowdpose.py:1315, lib/dataset/coco.py:1269).
+ *   kpts    f32 [n,K,3] (x,y,score);  scores f64 [n];  areas f64 [n]
+ *   img_offsets i32 [n_imgs+1]  detections of image i are [off[i], off[i+1])
+ *   sigmas  f64 [K];  thresh: suppress when oks > thresh
+ *   keep    i32 [n]   per image, at keep[off[i] ...]: kept indices RELATIVE to the image, in
+ *                     greedy selection order;  keep_counts i32 [n_imgs] */
+int rsg_oks_nms(void* stream, const float* kpts, const double* scores, const double* areas,
+                const int32_t* img_offsets, int n_imgs, int max_per_img, const double* sigmas,
+                int K, double thresh, int32_t* keep, int32_t* keep_counts);
+
+/* evaluate()-side rescoring, lib/dataset/crowdpose.py:1294-1306 / coco.py:1249-1261:
+ * score[i] = box_score[i] * mean(maxvals[i,k] for maxvals[i,k] > in_vis_thre). */
+int rsg_rescore(void* stream, const float* maxvals, const double* box_scores, int n, int K,
+                double in_vis_thre, double* scores);
+
+/* ------------------------------------------------------------------------------------------
+ * Model plan: a flat list of device ops (the folded / packed network) executed per chunk of crops.
+ * Replaces the nn.Module forward of lib/models/pose_rsgnet.py:955-1021 and
+ * lib/models/pose_hrnet.py:428-463.  The host side (rsgnet_b200/_engine.py, or any other
+ * host language) folds BatchNorm etc., packs weights into device memory, and describes the
+ * network once with the rsg_plan_add_* calls; rsg_plan_run then executes it.
+ * ---------------------------------------------------------------------------------------- */
+typedef struct rsg_plan rsg_plan;
+
+#define RSG_MAX_TAPS 16
+#define RSG_MAX_RES 4
+
+/* A pointer inside a plan is either absolute, or relative to an external per-run base:
+ * address = (ext_slot < 0 ? ptr : ext_base[ext_slot]) + offset + first_crop * crop_stride. */
+typedef struct rsg_ref {
+  void* ptr;             /* absolute device pointer (ext_slot < 0) */
+  int32_t ext_slot;      /* >= 0: index into the ext[] array given to rsg_plan_run */
+  int64_t offset;        /* bytes */
+  int64_t crop_stride;   /* bytes per crop, applied with the chunk's first crop (ext only) */
+} rsg_ref;
+
+typedef struct rsg_res {       /* residual / fuse term added in a conv epilogue */
+  rsg_ref src;                 /* bf16 NHWC */
+  int32_t cs, co;              /* channel stride / offset of the source buffer (elements) */
+  int32_t H, W;                /* source spatial size; read at (y >> shift, x >> shift) */
+  int32_t shift;
+  int32_t batch_stride0;       /* 1: the same map for every crop (broadcast) */
+} rsg_res;
+
+typedef struct rsg_conv_desc {
+  rsg_ref in;                  /* bf16 NHWC [N,Hin,Win,in_cs], channels [in_co, in_co+Cin) */
+  int32_t in_cs, in_co, Hin, Win, Cin;
+  rsg_ref w;                   /* bf16 [ntaps][CoutPad][Cin] (BN folded) */
+  rsg_ref bias;                /* f32 [CoutPad] */
+  int32_t Cout, CoutPad;
+  int32_t ntaps;
+  int8_t tap_dy[RSG_MAX_TAPS], tap_dx[RSG_MAX_TAPS];   /* input offset of each tap */
+  int32_t stride;              /* input pixel = out * stride + tap */
+  int32_t Hout, Wout;          /* iteration space */
+  rsg_ref out;                 /* bf16 NHWC or NULL */
+  int32_t out_cs, out_co, oH, oW, omul, ooy, oox;      /* out pixel = (y*omul+ooy, x*omul+oox) */
+  rsg_ref out_f32;             /* f32 NCHW [N,Cout,oH,oW] or NULL */
+  int32_t nres;
+  rsg_res res[RSG_MAX_RES];
+  int32_t relu;
+  int32_t engine;              /* 0 = auto, 1 = force mma.sync path, 2 = force tcgen05 path */
+} rsg_conv_desc;
+
+int rsg_plan_create(rsg_plan** out, int chunk);
+void rsg_plan_destroy(rsg_plan*);
+int rsg_plan_num_ops(const rsg_plan*);
+
+/* conv1 of the stem (pose_rsgnet.py:612-613,922-924): fp32 NCHW [*,3,H,W] -> bf16 NHWC
+ * [N,H/2,W/2,64], 3x3 s2 p1, BN folded, ReLU.  Forward f of a run reads crop f % n_crops,
+ * W-reversed when f >= n_crops (the flip-test second forward, function.py:401). */
+int rsg_plan_add_stem(rsg_plan*, rsg_ref x, int H, int W, rsg_ref w /*f32 [27][64]*/,
+                      rsg_ref bias /*f32[64]*/, rsg_ref out);
+int rsg_plan_add_conv(rsg_plan*, const rsg_conv_desc*);
+/* out = relu(sum_i up_i(term_i)): HighResolutionModule fuse (pose_rsgnet.py:261-270). */
+int rsg_plan_add_fuse(rsg_plan*, int nterms, const rsg_res* terms, rsg_ref out, int out_cs,
+                      int out_co, int H, int W, int C, int relu);
+/* 2x2 max-pool (association.py:286-287). */
+int rsg_plan_add_maxpool(rsg_plan*, rsg_ref in, int cs, int co, int H, int W, int C, rsg_ref out);
+/* TRP core (association.py:288-299): y[n,i,:] = sum_j sigmoid(x_i . x_j) g[n,j,:];
+ * x, g, y are bf16 [N,S,C] views with channel strides/offsets. */
+int rsg_plan_add_attention(rsg_plan*, rsg_ref x, int x_cs, int x_co, rsg_ref g, int g_cs,
+                           int g_co, rsg_ref y, int y_cs, int y_co, int S, int C);
+/* relation_scores f32 [N,S,S] = sigmoid(x x^T) (4th output of RSGNet.forward). */
+int rsg_plan_add_relation_scores(rsg_plan*, rsg_ref x, int x_cs, int x_co, int S, int C,
+                                 rsg_ref out);
+/* GroupNorm(groups, C) over [S,C] per crop (association.py:243-245). */
+int rsg_plan_add_groupnorm(rsg_plan*, rsg_ref in, int in_cs, int in_co, rsg_ref gamma,
+                           rsg_ref beta, int groups, float eps, rsg_ref out, int out_cs,
+                           int out_co, int S, int C);
+/* bilinear x2, align_corners=True (+ optional sigmoid) on f32 NCHW (pose_rsgnet.py:1009-1013). */
+int rsg_plan_add_bilinear2x(rsg_plan*, rsg_ref in, rsg_ref out, int C, int H, int W, int sigmoid);
+/* Mark ops added after this call as "aux": skipped by rsg_plan_run unless with_aux != 0. */
+int rsg_plan_begin_aux(rsg_plan*);
+
+/* Run `n_fwd` forwards in chunks.  ext[] resolves rsg_ref.ext_slot.  n_crops: see add_stem
+ * (n_fwd == n_crops: plain forward; n_fwd == 2*n_crops: flip-test batch).  use_graph: capture the
+ * whole run into a CUDA graph keyed by (n_fwd, n_crops, with_aux, ext pointers) and replay it. */
+int rsg_plan_run(rsg_plan*, void* stream, void* const* ext, int n_ext, int n_fwd, int n_crops,
+                 int with_aux, int use_graph);
+/* Kernel launches issued by the last rsg_plan_run (graph nodes when replayed). */
+int rsg_plan_last_launches(const rsg_plan*);
+
+/* Stand-alone conv launch (unit tests / micro-benchmarks): desc refs must be absolute. */
+int rsg_conv_run(void* stream, const rsg_conv_desc*, int N);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* RSG_B200_H_ */

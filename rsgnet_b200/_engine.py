@@ -1,0 +1,690 @@
+"""Host side of the model path: fold + pack the reference-named parameters, describe the network
+to librsg_b200 as a flat op list (the "plan"), and run it.
+
+What is folded at pack time (exact algebraic identities in eval mode):
+  * BatchNorm into the preceding bias-free conv (pose_rsgnet.py:38-54 etc.);
+  * the type branch  type_fc -> BN1d -> ReLU -> scores^T.T -> type_conv  into one K->C0 3x3 conv
+    (pose_rsgnet.py:966-977);
+  * the loc branch  loc_conv(loc_features)  into a constant map stored once in the loc slice of the
+    contact_conv input (pose_rsgnet.py:979-980);
+  * KTMachine(final_layer.weight) into a constant 1x1 conv (pose_rsgnet.py:592-600, 1004-1005);
+  * torch.cat by writing producers into channel slices of one buffer (pose_rsgnet.py:982, 991).
+Packing is host-side NumPy on the parameters only; every activation is computed on the device by
+the library.  Nothing here falls back to PyTorch ops for the forward.
+"""
+import ctypes as C
+import threading
+
+import numpy as np
+import torch
+
+from . import _lib
+from ._lib import ConvDesc, Ref, Res, abs_ref, ext_ref, null_ref
+from .config import KIND_RSGNET
+
+EPS = 1e-5
+EXT_X, EXT_HEAT, EXT_MULTI, EXT_LIMBS, EXT_REL = 0, 1, 2, 3, 4
+N_EXT = 5
+
+
+def _np(t):
+    return t.detach().to('cpu', torch.float64).numpy()
+
+
+def _round_up(v, m):
+    return (v + m - 1) // m * m
+
+
+def _bf16_bits(a):
+    """fp32 -> bf16 (round to nearest even) as uint16."""
+    a = np.ascontiguousarray(a, np.float32)
+    u = a.view(np.uint32).astype(np.uint64)
+    r = ((u >> 16) & 1) + 0x7FFF
+    return ((u + r) >> 16).astype(np.uint16)
+
+
+class _Params:
+    """state_dict accessor (fp64 NumPy) with prefixes."""
+
+    def __init__(self, sd, prefix=''):
+        self.sd, self.prefix = sd, prefix
+
+    def sub(self, name):
+        return _Params(self.sd, f'{self.prefix}{name}.')
+
+    def has(self, name):
+        return f'{self.prefix}{name}' in self.sd
+
+    def __getitem__(self, name):
+        return _np(self.sd[f'{self.prefix}{name}'])
+
+    def bn(self, name):
+        """(scale, shift) of an eval-mode BatchNorm."""
+        p = self.sub(name)
+        s = p['weight'] / np.sqrt(p['running_var'] + EPS)
+        return s, p['bias'] - p['running_mean'] * s
+
+
+class Buf:
+    """Symbolic activation buffer: per forward `elems` items of `itemsize` bytes."""
+
+    def __init__(self, name, H, W, C, itemsize=2, persistent=False):
+        self.name, self.H, self.W, self.C, self.itemsize = name, H, W, C, itemsize
+        self.persistent = persistent
+        self.first = self.last = None
+        self.ptr = None
+        self.tensor = None
+
+    @property
+    def bytes_per_fwd(self):
+        return self.H * self.W * self.C * self.itemsize
+
+
+class View:
+    def __init__(self, buf, co=0, C=None):
+        self.buf, self.co, self.C = buf, co, (buf.C - co if C is None else C)
+
+    @property
+    def H(self):
+        return self.buf.H
+
+    @property
+    def W(self):
+        return self.buf.W
+
+
+class _Arena:
+    """Host-side staging of packed constants -> one device tensor."""
+
+    def __init__(self):
+        self.chunks, self.size = [], 0
+
+    def add(self, arr):
+        arr = np.ascontiguousarray(arr)
+        off = self.size
+        self.chunks.append((off, arr))
+        self.size = _round_up(off + arr.nbytes, 256)
+        return off
+
+    def upload(self, device):
+        host = np.zeros(max(self.size, 256), np.uint8)
+        for off, arr in self.chunks:
+            host[off:off + arr.nbytes] = arr.view(np.uint8).reshape(-1)
+        return torch.from_numpy(host).to(device)
+
+
+class PlanBuilder:
+    def __init__(self, chunk, reuse=True):
+        self.chunk = chunk
+        self.reuse = reuse     # False: every buffer keeps its own memory (debug taps)
+        self.ops = []          # (kind, payload, reads, writes, aux)
+        self.bufs = []
+        self.arena = _Arena()
+        self.aux = False
+        self.flops_per_fwd = 0   # executed MACs*2 (after folding)
+
+    # -- buffers ---------------------------------------------------------------------------
+    def tensor_of(self, x):
+        """torch view of a Buf / View after allocate(): bf16 [chunk,H,W,C(slice)] or f32 [chunk,C,H,W]."""
+        b = x.buf if isinstance(x, View) else x
+        raw = b.tensor if b.tensor is not None else self.work[b.ptr - self.work.data_ptr():][:self.chunk * b.bytes_per_fwd]
+        if b.itemsize == 4:
+            return raw.view(torch.float32).view(self.chunk, b.C, b.H, b.W)
+        t = raw.view(torch.bfloat16).view(self.chunk, b.H, b.W, b.C)
+        return t[..., x.co:x.co + x.C] if isinstance(x, View) else t
+
+    def buf(self, name, H, W, C, itemsize=2, persistent=False):
+        b = Buf(name, H, W, C, itemsize, persistent or not self.reuse)
+        self.bufs.append(b)
+        return b
+
+    def const(self, arr):
+        return ('const', self.arena.add(arr))
+
+    # -- ops -------------------------------------------------------------------------------
+    def _add(self, kind, payload, reads, writes):
+        idx = len(self.ops)
+        for b in list(reads) + list(writes):
+            if b is None:
+                continue
+            if b.first is None:
+                b.first = idx
+            b.last = idx
+        self.ops.append((kind, payload, self.aux))
+
+    def conv(self, src, w_oihw, bias, stride=1, relu=False, dst=None, res=(), taps=None,
+             out_f32=None, omul=1, ooy=0, oox=0, out_hw=None, name='conv', cout=None):
+        """w_oihw: folded fp64 [Cout, Cin, kh, kw] (or [ntaps, Cout, Cin] with explicit taps)."""
+        if taps is None:
+            co_, ci_, kh, kw = w_oihw.shape
+            pad = kh // 2
+            taps = [(ky - pad, kx - pad) for ky in range(kh) for kx in range(kw)]
+            w_t = w_oihw.transpose(2, 3, 0, 1).reshape(kh * kw, co_, ci_)
+        else:
+            w_t = w_oihw
+            _, co_, ci_ = w_t.shape
+        assert ci_ <= src.C, (name, ci_, src.C)
+        cin = _round_up(ci_, 8)
+        assert cin <= src.buf.C - src.co
+        cin_pad = _round_up(cin, 32)
+        cout = co_ if cout is None else cout
+        cout_pad = _round_up(cout, 32)
+        wp = np.zeros((len(taps), cout_pad, cin_pad), np.float32)
+        wp[:, :co_, :ci_] = w_t
+        bp = np.zeros(cout_pad, np.float32)
+        bp[:co_] = bias
+        Hin, Win = src.H, src.W
+        Hout = (Hin - 1) // stride + 1 if out_hw is None else out_hw[0]
+        Wout = (Win - 1) // stride + 1 if out_hw is None else out_hw[1]
+        payload = dict(src=src, w=self.const(_bf16_bits(wp)), bias=self.const(bp), cin=cin,
+                       cout=cout, cout_pad=cout_pad, taps=taps, stride=stride, Hout=Hout, Wout=Wout,
+                       dst=dst, out_f32=out_f32, res=list(res), relu=relu, omul=omul, ooy=ooy,
+                       oox=oox, name=name)
+        reads = [src.buf] + [r[0].buf for r in res]
+        writes = [dst.buf if dst is not None else None,
+                  out_f32 if isinstance(out_f32, Buf) else None]
+        self._add('conv', payload, reads, writes)
+        self.flops_per_fwd += 2 * len(taps) * ci_ * co_ * Hout * Wout
+        return dst
+
+    def simple(self, kind, payload, reads, writes):
+        self._add(kind, payload, reads, writes)
+
+    # -- finalise --------------------------------------------------------------------------
+    def allocate(self, device):
+        """Lifetime-based first-fit placement of the non-persistent buffers in one arena."""
+        live = []      # (offset, size, last)
+        total = 0
+        order = sorted([b for b in self.bufs if b.first is not None and not b.persistent],
+                       key=lambda b: b.first)
+        placed = {}
+        for b in order:
+            size = _round_up(b.bytes_per_fwd * self.chunk, 1024)
+            live = [(o, s, l) for (o, s, l) in live if l >= b.first]
+            live.sort()
+            off = 0
+            for (o, s, l) in live:
+                if off + size <= o:
+                    break
+                off = max(off, o + s)
+            placed[b] = off
+            live.append((off, size, b.last))
+            total = max(total, off + size)
+        self.work = torch.zeros(max(total, 1024), dtype=torch.uint8, device=device)
+        base = self.work.data_ptr()
+        for b, off in placed.items():
+            b.ptr = base + off
+        for b in self.bufs:
+            if b.persistent:
+                b.tensor = torch.zeros(self.chunk * b.bytes_per_fwd, dtype=torch.uint8, device=device)
+                b.ptr = b.tensor.data_ptr()
+        self.consts = self.arena.upload(device)
+        self.work_bytes = total
+        return self
+
+
+def _ref(x, consts_ptr):
+    """Buf / View / ('const', off) / ('ext', slot, crop_stride) / None -> Ref."""
+    if x is None:
+        return null_ref()
+    if isinstance(x, Buf):
+        return abs_ref(x.ptr)
+    if isinstance(x, View):
+        return abs_ref(x.buf.ptr)
+    if x[0] == 'const':
+        return abs_ref(consts_ptr + x[1])
+    if x[0] == 'ext':
+        return ext_ref(x[1], 0, x[2])
+    raise TypeError(x)
+
+
+def _res(view, shift, consts_ptr, bs0=0):
+    return Res(_ref(view, consts_ptr), view.buf.C, view.co, view.buf.H, view.buf.W, shift, bs0)
+
+
+def emit(builder, plan):
+    """Second pass: translate the symbolic ops into rsg_plan_add_* calls."""
+    L = _lib.lib()
+    cp = builder.consts.data_ptr()
+    aux_started = False
+    for kind, p, aux in builder.ops:
+        if aux and not aux_started:
+            _lib.check(L.rsg_plan_begin_aux(plan))
+            aux_started = True
+        if kind == 'conv':
+            d = ConvDesc()
+            src = p['src']
+            d.inp = _ref(src, cp)
+            d.in_cs, d.in_co, d.Hin, d.Win, d.Cin = src.buf.C, src.co, src.H, src.W, p['cin']
+            d.w, d.bias = _ref(p['w'], cp), _ref(p['bias'], cp)
+            d.Cout, d.CoutPad = p['cout'], p['cout_pad']
+            d.ntaps = len(p['taps'])
+            for t, (dy, dx) in enumerate(p['taps']):
+                d.tap_dy[t], d.tap_dx[t] = dy, dx
+            d.stride, d.Hout, d.Wout = p['stride'], p['Hout'], p['Wout']
+            d.omul, d.ooy, d.oox = p['omul'], p['ooy'], p['oox']
+            d.oH, d.oW = p['Hout'] * p['omul'], p['Wout'] * p['omul']
+            dst = p['dst']
+            if dst is not None:
+                d.out = _ref(dst, cp)
+                d.out_cs, d.out_co = dst.buf.C, dst.co
+                assert (dst.buf.H, dst.buf.W) == (d.oH, d.oW), p['name']
+            else:
+                d.out = null_ref()
+            d.out_f32 = _ref(p['out_f32'], cp)
+            d.nres = len(p['res'])
+            for q, (view, shift) in enumerate(p['res']):
+                d.res[q] = _res(view, shift, cp)
+            d.relu = int(p['relu'])
+            d.engine = 0
+            _lib.check(L.rsg_plan_add_conv(plan, C.byref(d)))
+        elif kind == 'stem':
+            _lib.check(L.rsg_plan_add_stem(plan, _ref(p['x'], cp), p['H'], p['W'], _ref(p['w'], cp),
+                                           _ref(p['bias'], cp), _ref(p['out'], cp)))
+        elif kind == 'fuse':
+            terms = (Res * len(p['terms']))(*[_res(v, s, cp) for v, s in p['terms']])
+            dst = p['dst']
+            _lib.check(L.rsg_plan_add_fuse(plan, len(p['terms']), terms, _ref(dst, cp), dst.buf.C,
+                                           dst.co, dst.H, dst.W, dst.C, int(p['relu'])))
+        elif kind == 'maxpool':
+            src = p['src']
+            _lib.check(L.rsg_plan_add_maxpool(plan, _ref(src, cp), src.buf.C, src.co, src.H, src.W,
+                                              src.C, _ref(p['dst'], cp)))
+        elif kind == 'attention':
+            x, g, y = p['x'], p['g'], p['y']
+            _lib.check(L.rsg_plan_add_attention(plan, _ref(x, cp), x.buf.C, x.co, _ref(g, cp),
+                                                g.buf.C, g.co, _ref(y, cp), y.buf.C, y.co,
+                                                x.H * x.W, x.C))
+        elif kind == 'relscores':
+            x = p['x']
+            _lib.check(L.rsg_plan_add_relation_scores(plan, _ref(x, cp), x.buf.C, x.co, x.H * x.W,
+                                                      x.C, _ref(p['out'], cp)))
+        elif kind == 'groupnorm':
+            x, y = p['x'], p['y']
+            _lib.check(L.rsg_plan_add_groupnorm(plan, _ref(x, cp), x.buf.C, x.co,
+                                                _ref(p['gamma'], cp), _ref(p['beta'], cp),
+                                                p['groups'], EPS, _ref(y, cp), y.buf.C, y.co,
+                                                x.H * x.W, x.C))
+        elif kind == 'bilinear':
+            _lib.check(L.rsg_plan_add_bilinear2x(plan, _ref(p['src'], cp), _ref(p['out'], cp),
+                                                 p['C'], p['H'], p['W'], int(p['sigmoid'])))
+        else:
+            raise ValueError(kind)
+
+
+# ---------------------------------------------------------------------------------------------
+# Network description (mirrors pose_rsgnet.py:921-1021 / pose_hrnet.py:428-463)
+# ---------------------------------------------------------------------------------------------
+def _fold(w, bn):
+    s, b = bn
+    return w * s[:, None, None, None], b
+
+
+def _cbr(pb, P, src, name, stride=1, relu=True, dst=None, res=(), conv='0', bn='1'):
+    """Sequential(conv(bias=False), BN[, ReLU]) -> one fused conv op."""
+    w, b = _fold(P.sub(name)[f'{conv}.weight'] if conv else P[f'{name}.weight'], P.sub(name).bn(bn))
+    if dst is None:
+        Hout = (src.H - 1) // stride + 1
+        Wout = (src.W - 1) // stride + 1
+        dst = View(pb.buf(name, Hout, Wout, _round_up(w.shape[0], 8)))
+    return pb.conv(src, w, b, stride=stride, relu=relu, dst=dst, res=res, name=P.prefix + name)
+
+
+def _conv_bn(pb, P, conv, bn, src, stride=1, relu=False, res=(), dst=None):
+    w, b = _fold(P[f'{conv}.weight'], P.bn(bn))
+    if dst is None:
+        Hout = (src.H - 1) // stride + 1
+        Wout = (src.W - 1) // stride + 1
+        dst = View(pb.buf(P.prefix + conv, Hout, Wout, _round_up(w.shape[0], 8)))
+    return pb.conv(src, w, b, stride=stride, relu=relu, dst=dst, res=res, name=P.prefix + conv)
+
+
+def _bottleneck(pb, P, x):
+    y = _conv_bn(pb, P, 'conv1', 'bn1', x, relu=True)
+    y = _conv_bn(pb, P, 'conv2', 'bn2', y, relu=True)
+    r = _cbr(pb, P, x, 'downsample', relu=False) if P.has('downsample.0.weight') else x
+    return _conv_bn(pb, P, 'conv3', 'bn3', y, relu=True, res=[(r, 0)])
+
+
+def _basic(pb, P, x):
+    y = _conv_bn(pb, P, 'conv1', 'bn1', x, relu=True)
+    return _conv_bn(pb, P, 'conv2', 'bn2', y, relu=True, res=[(x, 0)])
+
+
+def _hr_module(pb, P, xs, n_out):
+    nb = len(xs)
+    xs = list(xs)
+    for b in range(nb):
+        i = 0
+        while P.has(f'branches.{b}.{i}.conv1.weight'):
+            xs[b] = _basic(pb, P.sub(f'branches.{b}.{i}'), xs[b])
+            i += 1
+    if nb == 1:
+        return xs
+    outs = []
+    for i in range(n_out):
+        terms = []                       # (view, up-shift)
+        for j in range(nb):
+            if j == i:
+                terms.append((xs[j], 0))
+            elif j > i:
+                t = _cbr(pb, P, xs[j], f'fuse_layers.{i}.{j}', relu=False)
+                terms.append((t, j - i))
+        down = [j for j in range(nb) if j < i]
+        # all but the last down-path produce plain tensors; the last one's final conv absorbs the
+        # whole sum + ReLU in its epilogue
+        for j in down[:-1]:
+            t = xs[j]
+            for k in range(i - j):
+                t = _cbr(pb, P, t, f'fuse_layers.{i}.{j}.{k}', stride=2, relu=(k != i - j - 1))
+            terms.append((t, 0))
+        if down:
+            j = down[-1]
+            t = xs[j]
+            for k in range(i - j - 1):
+                t = _cbr(pb, P, t, f'fuse_layers.{i}.{j}.{k}', stride=2, relu=True)
+            out = _cbr(pb, P, t, f'fuse_layers.{i}.{j}.{i - j - 1}', stride=2, relu=True, res=terms)
+        else:
+            x0 = xs[i]
+            out = View(pb.buf(P.prefix + f'fuse{i}', x0.H, x0.W, x0.buf.C))
+            pb.simple('fuse', dict(terms=terms, dst=out, relu=True),
+                      [t.buf for t, _ in terms], [out.buf])
+        outs.append(out)
+    return outs
+
+
+def _transition(pb, P, prev, n_cur):
+    n_pre = len(prev)
+    out = []
+    for i in range(n_cur):
+        if i < n_pre:
+            out.append(_cbr(pb, P, prev[i], f'{i}') if P.has(f'{i}.0.weight') else prev[i])
+        else:
+            t = prev[-1]
+            for j in range(i + 1 - n_pre):
+                t = _cbr(pb, P, t, f'{i}.{j}', stride=2)
+            out.append(t)
+    return out
+
+
+def _backbone(pb, P, spec, taps):
+    H, W = spec.image_h, spec.image_w
+    w1, b1 = _fold(P['conv1.weight'], P.bn('bn1'))
+    c1 = pb.buf('conv1', H // 2, W // 2, 64)
+    wst = np.ascontiguousarray(w1.transpose(1, 2, 3, 0).reshape(27, 64), np.float32)
+    pb.simple('stem', dict(x=('ext', EXT_X, 0), H=H, W=W, w=pb.const(wst),
+                           bias=pb.const(b1.astype(np.float32)), out=c1), [], [c1])
+    pb.flops_per_fwd += 2 * 27 * 64 * (H // 2) * (W // 2)
+    x = _conv_bn(pb, P, 'conv2', 'bn2', View(c1), stride=2, relu=True)
+    taps['stem'] = x
+    for i in range(4):
+        x = _bottleneck(pb, P.sub(f'layer1.{i}'), x)
+    taps['layer1'] = x
+    ys = [x]
+    for si, st in enumerate(spec.stages):
+        s = si + 2
+        xs = _transition(pb, P.sub(f'transition{s - 1}'), ys, st.num_branches)
+        for m in range(st.num_modules):
+            last = (si == len(spec.stages) - 1 and m == st.num_modules - 1)
+            xs = _hr_module(pb, P.sub(f'stage{s}.{m}'), xs, 1 if last else st.num_branches)
+        ys = xs
+        for b, t in enumerate(ys):
+            taps[f'stage{s}.{b}'] = t
+    return ys
+
+
+def _deconv4(pb, P, name, src, dst):
+    """Sequential(ConvTranspose2d(k4,s2,p1,bias=False), BN, ReLU) as four 2x2 phase convs."""
+    w = P[f'{name}.0.weight']                       # [Cin, Cout, 4, 4]
+    s, b = P.sub(name).bn('1')
+    if w.shape[2] != 4:
+        raise ValueError('only FINAL_DECONV_KERNEL_SIZE=4 is supported')
+    for py in (0, 1):
+        ys = [(1, 0), (3, -1)] if py == 0 else [(0, 1), (2, 0)]
+        for px in (0, 1):
+            xs = [(1, 0), (3, -1)] if px == 0 else [(0, 1), (2, 0)]
+            taps, mats = [], []
+            for ky, dy in ys:
+                for kx, dx in xs:
+                    taps.append((dy, dx))
+                    mats.append((w[:, :, ky, kx] * s[None, :]).T)      # [Cout, Cin]
+            pb.conv(src, np.stack(mats), b, relu=True, dst=dst, taps=taps, omul=2, ooy=py, oox=px,
+                    out_hw=(src.H, src.W), name=P.prefix + name + f'.p{py}{px}')
+    return dst
+
+
+def build_network(pb, sd, spec):
+    """Returns a dict describing the external outputs."""
+    P = _Params(sd)
+    taps = {}
+    ys = _backbone(pb, P, spec, taps)
+    feat = ys[0]
+    K = spec.num_joints
+    h, w = spec.feat_h, spec.feat_w
+    info = dict(K=K, heat_h=spec.heat_h, heat_w=spec.heat_w, taps=taps)
+
+    def head1x1(name, src, out_f32, cout_w=None):
+        wt, bs = P[f'{name}.weight'], P[f'{name}.bias']
+        if wt.shape[-1] != 1:
+            raise ValueError('FINAL_CONV_KERNEL must be 1')
+        return wt, bs
+
+    if spec.kind != KIND_RSGNET:
+        wt, bs = head1x1('final_layer', feat, None)
+        pb.conv(feat, wt, bs, out_f32=('ext', EXT_HEAT, K * h * w * 4), name='final_layer')
+        return info
+
+    C0 = spec.head_channels
+    L = spec.num_limbs
+    up = spec.up_scale
+    if up not in (1, 2):
+        raise ValueError('UP_SCALE must be 1 or 2')
+    # multi_final_layer -> bf16 scores (padded to a multiple of 8 channels) for the type conv
+    wm, bm = head1x1('multi_final_layer', feat, None)
+    K8 = _round_up(K, 8)
+    multi = View(pb.buf('multi_scores', h, w, K8))
+    pb.conv(feat, wm, bm, dst=multi, cout=K8, name='multi_final_layer')
+
+    # cat(vis, type, loc) lives in one persistent buffer; the loc slice is a pack-time constant
+    cat1 = pb.buf('cat_vis_type_loc', h, w, 3 * C0, persistent=True)
+    taps['vis'] = _cbr(pb, P, feat, 'vis_conv', dst=View(cat1, 0, C0))
+    tf = P['type_features'] @ P['type_fc.0.weight'].T
+    s1, b1 = P.sub('type_fc').bn('1')
+    T = np.maximum(tf * s1[None, :] + b1[None, :], 0.0)                 # [K, 600]
+    wc = P['type_conv.0.weight']                                       # [C0, 600, 3, 3]
+    wfold = np.einsum('otyx,kt->okyx', wc, T)
+    s2, b2 = P.sub('type_conv').bn('1')
+    taps['type'] = pb.conv(multi, wfold * s2[:, None, None, None], b2, relu=True,
+                           dst=View(cat1, C0, C0), name='type_conv(folded)')
+    wl = P['loc_conv.0.weight'][:, :, 0, 0]                            # [C0, 4]
+    s3, b3 = P.sub('loc_conv').bn('1')
+    loc = np.einsum('oi,iyx->oyx', wl, P['loc_features'][0]) * s3[:, None, None] + b3[:, None, None]
+    info['loc_const'] = (cat1, np.maximum(loc, 0.0).transpose(1, 2, 0).astype(np.float32), 2 * C0)
+
+    fvc = _cbr(pb, P, View(cat1), 'contact_conv')
+    cat2 = pb.buf('cat_rel_vis', h, w, 2 * C0)
+    fv = _cbr(pb, P, fvc, 'predict_contact_net', dst=View(cat2, C0, C0))
+    taps['final_vis'] = fv
+    taps['relation'] = View(cat2, 0, C0)
+
+    # ---- TRP (association.py:280-301)
+    R = P.sub('relation_head')
+    xs = fv
+    if spec.relation_sub_sample:
+        pooled = pb.buf('trp_pool', h // 2, w // 2, C0)
+        pb.simple('maxpool', dict(src=fv, dst=pooled), [fv.buf], [pooled])
+        xs = View(pooled)
+    g = View(pb.buf('trp_g', xs.H, xs.W, C0))
+    pb.conv(xs, R['g.weight'], R['g.bias'], dst=g, name='relation_head.g')
+    yv = View(pb.buf('trp_y', xs.H, xs.W, C0))
+    pb.simple('attention', dict(x=xs, g=g, y=yv), [xs.buf, g.buf], [yv.buf])
+    S = xs.H * xs.W
+    pb.flops_per_fwd += 2 * 2 * S * S * C0
+    info['S'] = S
+    info['trp_x'] = xs
+    if spec.relation_sub_sample:
+        yu = View(pb.buf('trp_up', h, w, C0))
+        _deconv4(pb, R, 'W.0', yv, yu)
+        yv, Wt = yu, R.sub('W.1')
+    else:
+        Wt = R.sub('W')
+    z = View(pb.buf('trp_z', h, w, C0))
+    pb.conv(yv, Wt['0.weight'], Wt['0.bias'], dst=z, name='relation_head.W')
+    pb.simple('groupnorm', dict(x=z, y=View(cat2, 0, C0), groups=8,
+                                gamma=pb.const(Wt['1.weight'].astype(np.float32)),
+                                beta=pb.const(Wt['1.bias'].astype(np.float32))),
+              [z.buf], [cat2])
+
+    # ---- keypoint head (pose_rsgnet.py:991-1000)
+    kf = _cbr(pb, P, View(cat2), 'kpt_net')
+    if up > 1:
+        kd = View(pb.buf('kpt_up', h * 2, w * 2, C0))
+        kf = _deconv4(pb, P, 'predict_convtranspose', kf, kd)
+    kf = _cbr(pb, P, kf, 'predict_net')
+    taps['kpt_feat'] = kf
+    wf, bf_ = head1x1('final_layer', kf, None)
+    pb.conv(kf, wf, bf_, out_f32=('ext', EXT_HEAT, K * spec.heat_h * spec.heat_w * 4),
+            name='final_layer')
+
+    # ---- auxiliary outputs (unused by the eval loop, function.py:389): multi_kpt_scores,
+    # limbs_scores (SGM, pose_rsgnet.py:1003-1013), relation_scores
+    pb.aux = True
+    if up > 1:
+        m32 = pb.buf('multi_f32', h, w, K, itemsize=4)
+        pb.conv(feat, wm, bm, out_f32=m32, name='multi_final_layer(aux)')
+        pb.simple('bilinear', dict(src=m32, out=('ext', EXT_MULTI, K * 4 * h * w * 4), C=K, H=h, W=w,
+                                   sigmoid=False), [m32], [])
+    else:
+        pb.conv(feat, wm, bm, out_f32=('ext', EXT_MULTI, K * h * w * 4), name='multi_final_layer(aux)')
+    lf = _cbr(pb, P, fv, 'limbs_net')
+    KT = P.sub('kt_machine')
+    mm = KT['matrix_limb'] * KT['real_matrix_limb']
+    t = mm @ wf.reshape(K, -1)
+    t = t @ KT['kpt_transformer.0.weight'].T + KT['kpt_transformer.0.bias']
+    t = np.where(t > 0, t, 0.02 * t)
+    t = t @ KT['kpt_transformer.2.weight'].T + KT['kpt_transformer.2.bias']
+    refine = t.reshape(L, C0, 1, 1)
+    if up > 1:
+        l32 = pb.buf('limbs_f32', h, w, L, itemsize=4)
+        pb.conv(lf, refine, np.zeros(L), out_f32=l32, name='limbs(dynamic 1x1)')
+        pb.simple('bilinear', dict(src=l32, out=('ext', EXT_LIMBS, L * 4 * h * w * 4), C=L, H=h, W=w,
+                                   sigmoid=True), [l32], [])
+    else:
+        raise ValueError('UP_SCALE=1 RSGNet heads are not supported')
+    pb.simple('relscores', dict(x=xs, out=('ext', EXT_REL, S * S * 4)), [xs.buf], [])
+    info['L'] = L
+    return info
+
+
+# ---------------------------------------------------------------------------------------------
+class Engine:
+    """Per (module, device) packed network + plan.  Rebuilt when parameters change."""
+
+    def __init__(self, module, device, chunk=32, reuse=True):
+        _lib.require_cuda()
+        self.device = torch.device(device)
+        self.spec = module.spec
+        self.chunk = chunk
+        sd = {k: v for k, v in module.state_dict().items()}
+        with torch.cuda.device(self.device):
+            pb = PlanBuilder(chunk, reuse)
+            self.info = build_network(pb, sd, self.spec)
+            pb.allocate(self.device)
+            if 'loc_const' in self.info:
+                buf, loc, co = self.info.pop('loc_const')
+                t = buf.tensor.view(torch.bfloat16).view(chunk, buf.H, buf.W, buf.C)
+                t[..., co:co + loc.shape[-1]] = torch.from_numpy(loc).to(self.device, torch.bfloat16)
+            self.pb = pb
+            handle = C.c_void_p()
+            _lib.check(_lib.lib().rsg_plan_create(C.byref(handle), chunk))
+            self.plan = handle
+            emit(pb, self.plan)
+        self.flops_per_fwd = pb.flops_per_fwd
+        self.lock = threading.Lock()
+
+    def __del__(self):
+        try:
+            if getattr(self, 'plan', None):
+                _lib.lib().rsg_plan_destroy(self.plan)
+                self.plan = None
+        except Exception:
+            pass
+
+    def out_shapes(self, n_fwd):
+        s, i = self.spec, self.info
+        shapes = {EXT_HEAT: (n_fwd, i['K'], s.heat_h, s.heat_w)}
+        if s.kind == KIND_RSGNET:
+            shapes[EXT_MULTI] = (n_fwd, i['K'], s.heat_h, s.heat_w)
+            shapes[EXT_LIMBS] = (n_fwd, i['L'], s.heat_h, s.heat_w)
+            shapes[EXT_REL] = (n_fwd, i['S'], i['S'])
+        return shapes
+
+    def run(self, x, heat, n_fwd, n_crops, aux=None, use_graph=False):
+        """x: f32 CUDA [n_crops,3,H,W] contiguous; heat: f32 CUDA [n_fwd,K,Hh,Wh]; aux: dict slot->tensor."""
+        ext = (C.c_void_p * N_EXT)()
+        ext[EXT_X] = x.data_ptr()
+        ext[EXT_HEAT] = heat.data_ptr()
+        with_aux = 0
+        if aux:
+            with_aux = 1
+            for slot, t in aux.items():
+                ext[slot] = t.data_ptr()
+        with self.lock, torch.cuda.device(self.device):
+            _lib.check(_lib.lib().rsg_plan_run(self.plan, _lib.stream_ptr(self.device), ext, N_EXT,
+                                               n_fwd, n_crops, with_aux, int(use_graph)))
+
+    def last_launches(self):
+        return _lib.lib().rsg_plan_last_launches(self.plan)
+
+
+# ---------------------------------------------------------------------------------------------
+_engines_lock = threading.Lock()
+
+
+def _param_version(module):
+    return tuple((id(t), t._version) for t in list(module.parameters()) + list(module.buffers()))
+
+
+def engine_for(module, device, chunk=None):
+    """Engine cache on the module, keyed by device; invalidated when any parameter/buffer changes
+    (load_state_dict, .to(), in-place edits)."""
+    key = str(torch.device(device))
+    with _engines_lock:
+        cache = module.__dict__.setdefault('_rsg_engines', {})
+        ver = _param_version(module)
+        chunk = chunk or getattr(module, 'chunk', 32)
+        ent = cache.get(key)
+        if ent is None or ent[0] != ver or ent[1].chunk != chunk:
+            cache[key] = ent = (ver, Engine(module, device, chunk))
+        return ent[1]
+
+
+def module_forward(module, x, relation_target=None):
+    """nn.Module.forward of the drop-in models: the reference's return convention."""
+    if module.training:
+        raise _lib.RsgError('rsgnet_b200 implements the inference path only: call model.eval() '
+                            '(training mode needs batch-statistics BatchNorm; SURVEY.md §8f-4)')
+    _lib.require_cuda()
+    dev = next(module.parameters()).device
+    if dev.type != 'cuda':
+        raise _lib.RsgError('move the model to a CUDA device first (model.cuda()); no CPU path')
+    if x.dim() != 4 or x.shape[1] != 3 or x.shape[2] != module.spec.image_h or x.shape[3] != module.spec.image_w:
+        raise ValueError(f'expected input [B,3,{module.spec.image_h},{module.spec.image_w}], got {tuple(x.shape)}')
+    x = x.to(dev, torch.float32, non_blocking=True).contiguous()
+    eng = engine_for(module, dev)
+    B = x.shape[0]
+    shapes = eng.out_shapes(B)
+    heat = torch.empty(shapes[EXT_HEAT], dtype=torch.float32, device=dev)
+    if module.spec.kind != KIND_RSGNET:
+        eng.run(x, heat, B, B)
+        return heat
+    if getattr(module, 'lazy_aux', False):
+        eng.run(x, heat, B, B)
+        return None, heat, None, None
+    aux = {s: torch.empty(shapes[s], dtype=torch.float32, device=dev)
+           for s in (EXT_MULTI, EXT_LIMBS, EXT_REL)}
+    eng.run(x, heat, B, B, aux=aux)
+    rel = aux[EXT_REL]
+    if relation_target is not None:
+        rel = ((relation_target.to(dev) - rel) ** 2).mean(dim=(1, 2))
+    return aux[EXT_MULTI], heat, aux[EXT_LIMBS], rel

@@ -1,0 +1,120 @@
+"""ctypes binding of librsg_b200.so (C ABI declared in include/rsg_b200.h).
+
+The library is the only compute path of this package: if it is missing or a call fails, the
+caller gets an exception -- there is no CPU or PyTorch fallback.
+"""
+import ctypes as C
+import os
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, 'librsg_b200.so')
+
+MAX_TAPS = 16
+MAX_RES = 4
+
+
+class Ref(C.Structure):
+    _fields_ = [('ptr', C.c_void_p), ('ext_slot', C.c_int32), ('offset', C.c_int64),
+                ('crop_stride', C.c_int64)]
+
+
+class Res(C.Structure):
+    _fields_ = [('src', Ref), ('cs', C.c_int32), ('co', C.c_int32), ('H', C.c_int32),
+                ('W', C.c_int32), ('shift', C.c_int32), ('batch_stride0', C.c_int32)]
+
+
+class ConvDesc(C.Structure):
+    _fields_ = [('inp', Ref), ('in_cs', C.c_int32), ('in_co', C.c_int32), ('Hin', C.c_int32),
+                ('Win', C.c_int32), ('Cin', C.c_int32),
+                ('w', Ref), ('bias', Ref), ('Cout', C.c_int32), ('CoutPad', C.c_int32),
+                ('ntaps', C.c_int32), ('tap_dy', C.c_int8 * MAX_TAPS), ('tap_dx', C.c_int8 * MAX_TAPS),
+                ('stride', C.c_int32), ('Hout', C.c_int32), ('Wout', C.c_int32),
+                ('out', Ref), ('out_cs', C.c_int32), ('out_co', C.c_int32), ('oH', C.c_int32),
+                ('oW', C.c_int32), ('omul', C.c_int32), ('ooy', C.c_int32), ('oox', C.c_int32),
+                ('out_f32', Ref), ('nres', C.c_int32), ('res', Res * MAX_RES),
+                ('relu', C.c_int32), ('engine', C.c_int32)]
+
+
+def null_ref():
+    return Ref(None, -1, 0, 0)
+
+
+def abs_ref(ptr):
+    return Ref(int(ptr) if ptr else None, -1, 0, 0)
+
+
+def ext_ref(slot, offset=0, crop_stride=0):
+    return Ref(None, int(slot), int(offset), int(crop_stride))
+
+
+class RsgError(RuntimeError):
+    pass
+
+
+_lib = None
+
+_SIGS = {
+    'rsg_abi_version': (C.c_int, []),
+    'rsg_last_error': (C.c_char_p, []),
+    'rsg_device_info': (C.c_int, [C.POINTER(C.c_int)]),
+    'rsg_flip_avg_decode': (C.c_int, [C.c_void_p] * 4 + [C.c_int] * 4 + [C.c_void_p] * 2 +
+                            [C.c_int] * 2 + [C.c_void_p] * 4),
+    'rsg_flip_back': (C.c_int, [C.c_void_p] * 4 + [C.c_int] * 4),
+    'rsg_oks_nms': (C.c_int, [C.c_void_p] * 5 + [C.c_int, C.c_int, C.c_void_p, C.c_int,
+                                                 C.c_double, C.c_void_p, C.c_void_p]),
+    'rsg_rescore': (C.c_int, [C.c_void_p] * 3 + [C.c_int, C.c_int, C.c_double, C.c_void_p]),
+    'rsg_plan_create': (C.c_int, [C.POINTER(C.c_void_p), C.c_int]),
+    'rsg_plan_destroy': (None, [C.c_void_p]),
+    'rsg_plan_num_ops': (C.c_int, [C.c_void_p]),
+    'rsg_plan_add_stem': (C.c_int, [C.c_void_p, Ref, C.c_int, C.c_int, Ref, Ref, Ref]),
+    'rsg_plan_add_conv': (C.c_int, [C.c_void_p, C.POINTER(ConvDesc)]),
+    'rsg_plan_add_fuse': (C.c_int, [C.c_void_p, C.c_int, C.POINTER(Res), Ref] + [C.c_int] * 6),
+    'rsg_plan_add_maxpool': (C.c_int, [C.c_void_p, Ref] + [C.c_int] * 5 + [Ref]),
+    'rsg_plan_add_attention': (C.c_int, [C.c_void_p, Ref, C.c_int, C.c_int, Ref, C.c_int, C.c_int,
+                                         Ref, C.c_int, C.c_int, C.c_int, C.c_int]),
+    'rsg_plan_add_relation_scores': (C.c_int, [C.c_void_p, Ref] + [C.c_int] * 4 + [Ref]),
+    'rsg_plan_add_groupnorm': (C.c_int, [C.c_void_p, Ref, C.c_int, C.c_int, Ref, Ref, C.c_int,
+                                         C.c_float, Ref, C.c_int, C.c_int, C.c_int, C.c_int]),
+    'rsg_plan_add_bilinear2x': (C.c_int, [C.c_void_p, Ref, Ref] + [C.c_int] * 4),
+    'rsg_plan_begin_aux': (C.c_int, [C.c_void_p]),
+    'rsg_plan_run': (C.c_int, [C.c_void_p, C.c_void_p, C.POINTER(C.c_void_p), C.c_int, C.c_int,
+                               C.c_int, C.c_int, C.c_int]),
+    'rsg_plan_last_launches': (C.c_int, [C.c_void_p]),
+    'rsg_conv_run': (C.c_int, [C.c_void_p, C.POINTER(ConvDesc), C.c_int]),
+}
+
+EXPORTS = tuple(_SIGS)
+
+
+def lib():
+    """Load librsg_b200.so (once).  Raises if it has not been built: there is no other path."""
+    global _lib
+    if _lib is None:
+        if not os.path.isfile(LIB_PATH):
+            raise RsgError(f'{LIB_PATH} is missing: build it with `python __graft_entry__.py` '
+                           '(or make -C rsgnet_b200/csrc); rsgnet_b200 has no CPU fallback')
+        handle = C.CDLL(LIB_PATH)
+        for name, (res, args) in _SIGS.items():
+            fn = getattr(handle, name)
+            fn.restype = res
+            fn.argtypes = args
+        if handle.rsg_abi_version() != 1:
+            raise RsgError('librsg_b200.so ABI version mismatch')
+        _lib = handle
+    return _lib
+
+
+def check(rc):
+    if rc != 0:
+        raise RsgError(lib().rsg_last_error().decode('utf-8', 'replace') or f'librsg_b200 error {rc}')
+
+
+def require_cuda():
+    import torch
+    if not torch.cuda.is_available():
+        raise RsgError('rsgnet_b200 needs a CUDA device (sm_100a); there is no CPU fallback')
+
+
+def stream_ptr(device=None):
+    import torch
+    return C.c_void_p(torch.cuda.current_stream(device).cuda_stream)

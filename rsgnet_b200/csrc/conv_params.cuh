@@ -1,0 +1,32 @@
+// Device-side (resolved) parameter blocks shared by the conv kernels and the plan executor.
+#pragma once
+#include "common.cuh"
+
+struct ResP {
+  const bf16* p;
+  int cs, co, H, W, shift, bs0;
+};
+
+struct ConvP {
+  const bf16* in;
+  int in_cs, in_co, Hin, Win, Cin, CinPad;
+  const bf16* w;        // [ntaps][CoutPad][CinPad]
+  const float* bias;    // [CoutPad]
+  int Cout, CoutPad;
+  int ntaps;
+  int8_t dy[16], dx[16];
+  int stride;
+  int Hout, Wout;
+  bf16* out;
+  int out_cs, out_co, oH, oW, omul, ooy, oox;
+  float* out_f32;
+  int nres;
+  ResP res[4];
+  int relu;
+  int N;
+  long long M;          // N * Hout * Wout
+};
+
+int conv_mma_launch(const ConvP& p, cudaStream_t s);
+// returns RSG_OK and sets *handled=1 when the tcgen05 kernel covers this shape
+int conv_tc5_launch(const ConvP& p, cudaStream_t s, int* handled);

@@ -1,0 +1,148 @@
+// Segmented greedy OKS-NMS (one image per CTA) and evaluate()-side rescoring.
+//
+// Replaces (paths under the reference checkout):
+//   lib/nms/nms.py:75-94    oks_iou  -- dx,dy and their squares in fp32, everything after the
+//                                       division by vars in fp64, np.sum's pairwise order
+//   lib/nms/nms.py:97-124   oks_nms  -- descending-score greedy sweep, suppress when oks > thresh
+//   lib/dataset/crowdpose.py:1294-1306, lib/dataset/coco.py:1249-1261   rescoring
+// Like the reference, OKS is evaluated lazily: only between a kept detection and the detections
+// still alive behind it in the score order.
+#include "common.cuh"
+#include "../../include/rsg_b200.h"
+
+namespace {
+
+// np.add.reduce over a contiguous fp64 vector of length n <= 128 (numpy's pairwise_sum).
+__device__ double numpy_sum(const double* a, int n) {
+  if (n < 8) {
+    double r = 0.0;
+    for (int i = 0; i < n; ++i) r = __dadd_rn(r, a[i]);
+    return r;
+  }
+  double r[8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) r[j] = a[j];
+  int i = 8;
+  for (; i < n - (n % 8); i += 8) {
+#pragma unroll
+    for (int j = 0; j < 8; ++j) r[j] = __dadd_rn(r[j], a[i + j]);
+  }
+  double res = __dadd_rn(__dadd_rn(__dadd_rn(r[0], r[1]), __dadd_rn(r[2], r[3])),
+                         __dadd_rn(__dadd_rn(r[4], r[5]), __dadd_rn(r[6], r[7])));
+  for (; i < n; ++i) res = __dadd_rn(res, a[i]);
+  return res;
+}
+
+#define RSG_NMS_MAXK 64
+
+__device__ double oks_pair(const float* __restrict__ g, const float* __restrict__ d, double a_g,
+                           double a_d, const double* __restrict__ vars, int K) {
+  double ex[RSG_NMS_MAXK];
+  const double denom = __dadd_rn(__ddiv_rn(__dadd_rn(a_g, a_d), 2.0), 2.220446049250313e-16);
+  for (int k = 0; k < K; ++k) {
+    float dx = __fsub_rn(d[3 * k], g[3 * k]);
+    float dy = __fsub_rn(d[3 * k + 1], g[3 * k + 1]);
+    float s = __fadd_rn(__fmul_rn(dx, dx), __fmul_rn(dy, dy));
+    double e = __ddiv_rn(__ddiv_rn(__ddiv_rn((double)s, vars[k]), denom), 2.0);
+    ex[k] = exp(-e);
+  }
+  return __ddiv_rn(numpy_sum(ex, K), (double)K);
+}
+
+__global__ void __launch_bounds__(128)
+oks_nms_kernel(const float* __restrict__ kpts, const double* __restrict__ scores,
+               const double* __restrict__ areas, const int32_t* __restrict__ offs,
+               const double* __restrict__ sigmas, int K, double thresh,
+               int32_t* __restrict__ keep, int32_t* __restrict__ keep_counts) {
+  extern __shared__ unsigned char smem_raw[];
+  __shared__ double vars[RSG_NMS_MAXK];
+  const int img = blockIdx.x;
+  const int beg = offs[img], n = offs[img + 1] - beg;
+  int* order = reinterpret_cast<int*>(smem_raw);          // [n] local indices, best first
+  int* dead = order + n;                                  // [n] by position in `order`
+  const int tid = threadIdx.x, nt = blockDim.x;
+  if (tid < K) {
+    double s2 = __dmul_rn(sigmas[tid], 2.0);
+    vars[tid] = __dmul_rn(s2, s2);
+  }
+  // rank = position in scores.argsort()[::-1]; ties: the later index first
+  for (int i = tid; i < n; i += nt) {
+    const double si = scores[beg + i];
+    int r = 0;
+    for (int j = 0; j < n; ++j) {
+      const double sj = scores[beg + j];
+      r += (sj > si) || (sj == si && j > i);
+    }
+    order[r] = i;
+    dead[i] = 0;
+  }
+  __syncthreads();
+  int nkeep = 0;
+  for (int p = 0; p < n; ++p) {
+    if (dead[p]) continue;                                 // uniform: smem value
+    const int i = order[p];
+    if (tid == 0) keep[beg + nkeep] = i;
+    ++nkeep;
+    const float* g = kpts + (size_t)(beg + i) * K * 3;
+    const double a_g = areas[beg + i];
+    for (int q = p + 1 + tid; q < n; q += nt) {
+      if (dead[q]) continue;
+      const int j = order[q];
+      double oks = oks_pair(g, kpts + (size_t)(beg + j) * K * 3, a_g, areas[beg + j], vars, K);
+      if (oks > thresh) dead[q] = 1;
+    }
+    __syncthreads();
+  }
+  if (tid == 0) keep_counts[img] = nkeep;
+}
+
+__global__ void rescore_kernel(const float* __restrict__ maxvals,
+                               const double* __restrict__ box, int n, int K, double thre,
+                               double* __restrict__ out) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  // np.float32 accumulation; under NumPy 2 (NEP 50) float32 > python-float compares in fp32
+  float acc = 0.f;
+  const float thre32 = (float)thre;
+  int valid = 0;
+  for (int k = 0; k < K; ++k) {
+    float t = maxvals[(size_t)i * K + k];
+    if (t > thre32) { acc = __fadd_rn(acc, t); ++valid; }
+  }
+  double s;
+  if (valid != 0) s = (double)__fdiv_rn(acc, (float)valid);
+  else s = 0.0;
+  out[i] = __dmul_rn(s, box[i]);
+}
+
+}  // namespace
+
+extern "C" int rsg_oks_nms(void* stream, const float* kpts, const double* scores,
+                           const double* areas, const int32_t* img_offsets, int n_imgs,
+                           int max_per_img, const double* sigmas, int K, double thresh,
+                           int32_t* keep, int32_t* keep_counts) {
+  RSG_REQUIRE(n_imgs >= 0 && K > 0 && K <= RSG_NMS_MAXK, "rsg_oks_nms: bad n_imgs=%d or K=%d", n_imgs, K);
+  if (n_imgs == 0) return RSG_OK;
+  RSG_REQUIRE(kpts && scores && areas && img_offsets && sigmas && keep && keep_counts,
+              "rsg_oks_nms: null pointer");
+  RSG_REQUIRE(max_per_img >= 0, "rsg_oks_nms: max_per_img < 0");
+  size_t smem = (size_t)max_per_img * 2 * sizeof(int);
+  RSG_REQUIRE(smem <= 200 * 1024, "rsg_oks_nms: more than %d detections in one image", 25600);
+  if (smem > 48 * 1024)
+    RSG_CUDA(cudaFuncSetAttribute(oks_nms_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  oks_nms_kernel<<<n_imgs, 128, smem, (cudaStream_t)stream>>>(kpts, scores, areas, img_offsets,
+                                                             sigmas, K, thresh, keep, keep_counts);
+  RSG_LAUNCH_CHECK();
+  return RSG_OK;
+}
+
+extern "C" int rsg_rescore(void* stream, const float* maxvals, const double* box_scores, int n,
+                           int K, double in_vis_thre, double* scores) {
+  RSG_REQUIRE(n >= 0 && K > 0, "rsg_rescore: bad shape");
+  if (n == 0) return RSG_OK;
+  RSG_REQUIRE(maxvals && box_scores && scores, "rsg_rescore: null pointer");
+  rescore_kernel<<<ceil_div(n, 128), 128, 0, (cudaStream_t)stream>>>(maxvals, box_scores, n, K,
+                                                                     in_vis_thre, scores);
+  RSG_LAUNCH_CHECK();
+  return RSG_OK;
+}

@@ -1,0 +1,365 @@
+// HBM-bound helper kernels of the RSGNet forward: stem conv1 (Cin=3), fuse-layer sum with
+// nearest up-sampling, 2x2 max-pool, GroupNorm, bilinear x2, relation_scores dump.
+#include "ops.cuh"
+
+namespace {
+
+// ---------------------------------------------------------------------------------------------
+// conv1: 3x3 s2 p1, 3 -> 64, fp32 NCHW in (optionally W-reversed), bf16 NHWC out, BN folded, ReLU.
+// pose_rsgnet.py:612-613, 922-924 (+ input.flip(3), function.py:401).  fp32 FMA on CUDA cores:
+// K = 27 is too thin for the tensor pipe and the op is bound by its 128 B/pixel output stream.
+// A warp covers 8 consecutive output pixels x 4 groups of 16 channels -> 1 KB contiguous stores.
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+stem_kernel(const float* __restrict__ x, int H, int W, const float* __restrict__ w,
+            const float* __restrict__ bias, bf16* __restrict__ out, int f0, int nb, int n_crops) {
+  __shared__ float sw[27 * 64];
+  __shared__ float sb[64];
+  for (int i = threadIdx.x; i < 27 * 64; i += blockDim.x) sw[i] = w[i];
+  if (threadIdx.x < 64) sb[threadIdx.x] = bias[threadIdx.x];
+  __syncthreads();
+  const int Ho = H >> 1, Wo = W >> 1;
+  const long long total = (long long)nb * Ho * Wo;
+  const long long pix = (long long)blockIdx.x * 64 + (threadIdx.x >> 2);
+  if (pix >= total) return;
+  const int cg = threadIdx.x & 3;
+  const int ox = (int)(pix % Wo);
+  const long long r = pix / Wo;
+  const int oy = (int)(r % Ho);
+  const int fl = (int)(r / Ho);
+  const int f = f0 + fl;
+  const int crop = f % n_crops;
+  const bool flip = f >= n_crops;
+  const float* xin = x + (size_t)crop * 3 * H * W;
+  float acc[16];
+#pragma unroll
+  for (int j = 0; j < 16; ++j) acc[j] = sb[cg * 16 + j];
+#pragma unroll
+  for (int ci = 0; ci < 3; ++ci) {
+#pragma unroll
+    for (int ky = 0; ky < 3; ++ky) {
+      const int iy = oy * 2 - 1 + ky;
+#pragma unroll
+      for (int kx = 0; kx < 3; ++kx) {
+        const int ix = ox * 2 - 1 + kx;
+        float v = 0.f;
+        if (iy >= 0 && iy < H && ix >= 0 && ix < W)
+          v = __ldg(xin + ((size_t)ci * H + iy) * W + (flip ? W - 1 - ix : ix));
+        const float4* wp = reinterpret_cast<const float4*>(sw + ((ci * 3 + ky) * 3 + kx) * 64 + cg * 16);
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+          float4 ww = wp[q];
+          acc[q * 4 + 0] = fmaf(v, ww.x, acc[q * 4 + 0]);
+          acc[q * 4 + 1] = fmaf(v, ww.y, acc[q * 4 + 1]);
+          acc[q * 4 + 2] = fmaf(v, ww.z, acc[q * 4 + 2]);
+          acc[q * 4 + 3] = fmaf(v, ww.w, acc[q * 4 + 3]);
+        }
+      }
+    }
+  }
+  uint32_t pk[8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    __nv_bfloat162 t;
+    t.x = __float2bfloat16_rn(fmaxf(acc[2 * j], 0.f));
+    t.y = __float2bfloat16_rn(fmaxf(acc[2 * j + 1], 0.f));
+    pk[j] = *reinterpret_cast<uint32_t*>(&t);
+  }
+  uint4* op = reinterpret_cast<uint4*>(out + ((size_t)fl * Ho * Wo + (size_t)oy * Wo + ox) * 64 + cg * 16);
+  op[0] = make_uint4(pk[0], pk[1], pk[2], pk[3]);
+  op[1] = make_uint4(pk[4], pk[5], pk[6], pk[7]);
+}
+
+// ---------------------------------------------------------------------------------------------
+// Fuse-layer sum: out = relu(sum_t term_t[y >> s_t, x >> s_t])  (pose_rsgnet.py:261-270 with
+// nn.Upsample(nearest), :213).  One thread per (pixel, 8 channels): 16-byte loads and stores.
+// ---------------------------------------------------------------------------------------------
+struct FuseP {
+  int nterms;
+  ResP t[4];
+  bf16* out;
+  int out_cs, out_co, N, H, W, C, relu;
+};
+
+__device__ __forceinline__ void add8(float* a, const uint4& v) {
+  const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&v);
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    a[2 * j] += __bfloat162float(h[j].x);
+    a[2 * j + 1] += __bfloat162float(h[j].y);
+  }
+}
+__device__ __forceinline__ uint4 pack8(const float* a) {
+  uint4 o;
+  __nv_bfloat162* h = reinterpret_cast<__nv_bfloat162*>(&o);
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    h[j].x = __float2bfloat16_rn(a[2 * j]);
+    h[j].y = __float2bfloat16_rn(a[2 * j + 1]);
+  }
+  return o;
+}
+
+__global__ void __launch_bounds__(256) fuse_kernel(const FuseP p) {
+  const int c8 = p.C >> 3;
+  const long long total = (long long)p.N * p.H * p.W * c8;
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= total) return;
+  const int c = (int)(i % c8) * 8;
+  long long r = i / c8;
+  const int x = (int)(r % p.W);
+  r /= p.W;
+  const int y = (int)(r % p.H);
+  const int n = (int)(r / p.H);
+  float a[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+#pragma unroll
+  for (int t = 0; t < 4; ++t) {
+    if (t < p.nterms) {
+      const ResP& q = p.t[t];
+      const bf16* src = q.p + ((size_t)((size_t)(q.bs0 ? 0 : n) * q.H + (y >> q.shift)) * q.W + (x >> q.shift)) * q.cs + q.co + c;
+      add8(a, __ldg(reinterpret_cast<const uint4*>(src)));
+    }
+  }
+  if (p.relu) {
+#pragma unroll
+    for (int j = 0; j < 8; ++j) a[j] = fmaxf(a[j], 0.f);
+  }
+  *reinterpret_cast<uint4*>(p.out + ((size_t)((size_t)n * p.H + y) * p.W + x) * p.out_cs + p.out_co + c) = pack8(a);
+}
+
+// 2x2 max-pool, stride 2 (association.py:254, 286-287)
+__global__ void __launch_bounds__(256)
+maxpool_kernel(const bf16* __restrict__ in, int cs, int co, int N, int H, int W, int C,
+               bf16* __restrict__ out) {
+  const int c8 = C >> 3, Ho = H >> 1, Wo = W >> 1;
+  const long long total = (long long)N * Ho * Wo * c8;
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= total) return;
+  const int c = (int)(i % c8) * 8;
+  long long r = i / c8;
+  const int x = (int)(r % Wo);
+  r /= Wo;
+  const int y = (int)(r % Ho);
+  const int n = (int)(r / Ho);
+  float m[8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) m[j] = -INFINITY;
+#pragma unroll
+  for (int dy = 0; dy < 2; ++dy)
+#pragma unroll
+    for (int dx = 0; dx < 2; ++dx) {
+      uint4 v = __ldg(reinterpret_cast<const uint4*>(
+          in + ((size_t)((size_t)n * H + 2 * y + dy) * W + 2 * x + dx) * cs + co + c));
+      const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&v);
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        m[2 * j] = fmaxf(m[2 * j], __bfloat162float(h[j].x));
+        m[2 * j + 1] = fmaxf(m[2 * j + 1], __bfloat162float(h[j].y));
+      }
+    }
+  *reinterpret_cast<uint4*>(out + ((size_t)((size_t)n * Ho + y) * Wo + x) * C + c) = pack8(m);
+}
+
+// ---------------------------------------------------------------------------------------------
+// GroupNorm(groups, C) over one crop's [S, C] map (association.py:243-245): one CTA per crop,
+// pass 1 = per-channel sum / sum of squares (deterministic two-level reduction), pass 2 (L2-hot
+// re-read) = normalise + affine, written into a channel slice of the next conv's input.
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+groupnorm_kernel(const bf16* __restrict__ in, int in_cs, int in_co, const float* __restrict__ gamma,
+                 const float* __restrict__ beta, int groups, float eps, bf16* __restrict__ out,
+                 int out_cs, int out_co, int S, int C) {
+  extern __shared__ float sm[];
+  const int c8 = C >> 3;
+  const int nthr = (blockDim.x / c8) * c8;         // threads that own a fixed 8-channel chunk
+  float* part = sm;                                // [nthr][16]
+  float* chs = sm + (size_t)nthr * 16;             // [C] sums, [C] sums of squares
+  float* gstat = chs + 2 * C;                      // [groups] mean, [groups] rstd
+  const int n = blockIdx.x, tid = threadIdx.x;
+  const bf16* src = in + (size_t)n * S * in_cs + in_co;
+  const long long total = (long long)S * c8;
+  float s[8] = {0, 0, 0, 0, 0, 0, 0, 0}, q[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+  if (tid < nthr) {
+    const int ch = tid % c8;
+    for (long long i = tid; i < total; i += nthr) {
+      const long long pix = i / c8;
+      uint4 v = __ldg(reinterpret_cast<const uint4*>(src + pix * in_cs + ch * 8));
+      const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&v);
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        float a = __bfloat162float(h[j].x), b = __bfloat162float(h[j].y);
+        s[2 * j] += a; q[2 * j] = fmaf(a, a, q[2 * j]);
+        s[2 * j + 1] += b; q[2 * j + 1] = fmaf(b, b, q[2 * j + 1]);
+      }
+    }
+#pragma unroll
+    for (int j = 0; j < 8; ++j) { part[tid * 16 + j] = s[j]; part[tid * 16 + 8 + j] = q[j]; }
+  }
+  __syncthreads();
+  for (int t = tid; t < 2 * C; t += blockDim.x) {
+    const int c = t % C, which = t / C;
+    const int ch = c >> 3, j = c & 7;
+    float a = 0.f;
+    for (int th = ch; th < nthr; th += c8) a += part[th * 16 + which * 8 + j];
+    chs[t] = a;
+  }
+  __syncthreads();
+  const int cpg = C / groups;
+  if (tid < groups) {
+    float a = 0.f, b = 0.f;
+    for (int c = tid * cpg; c < (tid + 1) * cpg; ++c) { a += chs[c]; b += chs[C + c]; }
+    const float cnt = (float)S * cpg;
+    const float mean = a / cnt;
+    const float var = fmaxf(b / cnt - mean * mean, 0.f);
+    gstat[tid] = mean;
+    gstat[groups + tid] = rsqrtf(var + eps);
+  }
+  __syncthreads();
+  bf16* dst = out + (size_t)n * S * out_cs + out_co;
+  for (long long i = tid; i < total; i += blockDim.x) {
+    const long long pix = i / c8;
+    const int ch = (int)(i - pix * c8);
+    uint4 v = __ldg(reinterpret_cast<const uint4*>(src + pix * in_cs + ch * 8));
+    const bf16* h = reinterpret_cast<const bf16*>(&v);
+    float o[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const int c = ch * 8 + j, g = c / cpg;
+      o[j] = (__bfloat162float(h[j]) - gstat[g]) * gstat[groups + g] * __ldg(gamma + c) + __ldg(beta + c);
+    }
+    *reinterpret_cast<uint4*>(dst + pix * out_cs + ch * 8) = pack8(o);
+  }
+}
+
+// bilinear x2, align_corners=True, optional sigmoid (pose_rsgnet.py:1009-1013); fp32 NCHW
+__global__ void __launch_bounds__(256)
+bilinear2x_kernel(const float* __restrict__ in, float* __restrict__ out, long long NC, int H, int W,
+                  int sig) {
+  const int Ho = 2 * H, Wo = 2 * W;
+  const long long total = NC * Ho * Wo;
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= total) return;
+  const int X = (int)(i % Wo);
+  long long r = i / Wo;
+  const int Y = (int)(r % Ho);
+  const long long nc = r / Ho;
+  const float sy = Ho > 1 ? (float)(H - 1) / (float)(Ho - 1) : 0.f;
+  const float sx = Wo > 1 ? (float)(W - 1) / (float)(Wo - 1) : 0.f;
+  const float fy = sy * Y, fx = sx * X;
+  const int y0 = (int)fy, x0 = (int)fx;
+  const int y1 = y0 + (y0 < H - 1), x1 = x0 + (x0 < W - 1);
+  const float ly = fy - y0, lx = fx - x0;
+  const float hy = 1.f - ly, hx = 1.f - lx;
+  const float* p = in + nc * H * W;
+  float v = hy * (hx * __ldg(p + y0 * W + x0) + lx * __ldg(p + y0 * W + x1)) +
+            ly * (hx * __ldg(p + y1 * W + x0) + lx * __ldg(p + y1 * W + x1));
+  if (sig) v = 1.f / (1.f + expf(-v));
+  out[i] = v;
+}
+
+// relation_scores[n,i,j] = sigmoid(x_i . x_j) in fp32 from the bf16 TRP input (association.py:
+// 294-295); only produced on request (it is S*S*4 bytes per crop and unused by the eval loop).
+__global__ void __launch_bounds__(256)
+relation_scores_kernel(const bf16* __restrict__ x, int cs, int co, int S, int C,
+                       float* __restrict__ out) {
+  extern __shared__ float sm[];
+  const int pitch = C + 1;
+  float* xi = sm;                 // [64][C+1]
+  float* xj = sm + 64 * pitch;    // [64][C+1]
+  const int n = blockIdx.z, i0 = blockIdx.y * 64, j0 = blockIdx.x * 64;
+  const bf16* base = x + (size_t)n * S * cs + co;
+  for (int t = threadIdx.x; t < 64 * C; t += blockDim.x) {
+    const int r = t / C, c = t - r * C;
+    xi[r * pitch + c] = (i0 + r < S) ? __bfloat162float(base[(size_t)(i0 + r) * cs + c]) : 0.f;
+    xj[r * pitch + c] = (j0 + r < S) ? __bfloat162float(base[(size_t)(j0 + r) * cs + c]) : 0.f;
+  }
+  __syncthreads();
+  const int tx = threadIdx.x & 15, ty = threadIdx.x >> 4;
+  float acc[4][4] = {};
+  for (int c = 0; c < C; ++c) {
+    float a[4], b[4];
+#pragma unroll
+    for (int u = 0; u < 4; ++u) { a[u] = xi[(ty + 16 * u) * pitch + c]; b[u] = xj[(tx + 16 * u) * pitch + c]; }
+#pragma unroll
+    for (int u = 0; u < 4; ++u)
+#pragma unroll
+      for (int v = 0; v < 4; ++v) acc[u][v] = fmaf(a[u], b[v], acc[u][v]);
+  }
+#pragma unroll
+  for (int u = 0; u < 4; ++u)
+#pragma unroll
+    for (int v = 0; v < 4; ++v) {
+      const int i = i0 + ty + 16 * u, j = j0 + tx + 16 * v;
+      if (i < S && j < S) out[((size_t)n * S + i) * S + j] = 1.f / (1.f + expf(-acc[u][v]));
+    }
+}
+
+}  // namespace
+
+int stem_launch(cudaStream_t s, const float* x, int H, int W, const float* w, const float* bias,
+                bf16* out, int f0, int nb, int n_crops) {
+  RSG_REQUIRE(H % 2 == 0 && W % 2 == 0, "stem: H and W must be even");
+  const long long total = (long long)nb * (H / 2) * (W / 2);
+  if (total == 0) return RSG_OK;
+  stem_kernel<<<ceil_div(total, 64), 256, 0, s>>>(x, H, W, w, bias, out, f0, nb, n_crops);
+  RSG_LAUNCH_CHECK();
+  return RSG_OK;
+}
+
+int fuse_launch(cudaStream_t s, int nterms, const ResP* terms, bf16* out, int out_cs, int out_co,
+                int N, int H, int W, int C, int relu) {
+  RSG_REQUIRE(nterms >= 1 && nterms <= 4 && C % 8 == 0, "fuse: nterms=%d C=%d", nterms, C);
+  FuseP p;
+  p.nterms = nterms;
+  for (int i = 0; i < nterms; ++i) p.t[i] = terms[i];
+  p.out = out; p.out_cs = out_cs; p.out_co = out_co; p.N = N; p.H = H; p.W = W; p.C = C; p.relu = relu;
+  const long long total = (long long)N * H * W * (C / 8);
+  if (total == 0) return RSG_OK;
+  fuse_kernel<<<ceil_div(total, 256), 256, 0, s>>>(p);
+  RSG_LAUNCH_CHECK();
+  return RSG_OK;
+}
+
+int maxpool_launch(cudaStream_t s, const bf16* in, int cs, int co, int N, int H, int W, int C,
+                   bf16* out) {
+  RSG_REQUIRE(C % 8 == 0 && H % 2 == 0 && W % 2 == 0, "maxpool: bad shape");
+  const long long total = (long long)N * (H / 2) * (W / 2) * (C / 8);
+  if (total == 0) return RSG_OK;
+  maxpool_kernel<<<ceil_div(total, 256), 256, 0, s>>>(in, cs, co, N, H, W, C, out);
+  RSG_LAUNCH_CHECK();
+  return RSG_OK;
+}
+
+int groupnorm_launch(cudaStream_t s, const bf16* in, int in_cs, int in_co, const float* gamma,
+                     const float* beta, int groups, float eps, bf16* out, int out_cs, int out_co,
+                     int N, int S, int C) {
+  RSG_REQUIRE(C % 8 == 0 && C % groups == 0 && C / 8 <= 256, "groupnorm: C=%d groups=%d", C, groups);
+  if (N == 0) return RSG_OK;
+  const int c8 = C / 8, nthr = (256 / c8) * c8;
+  size_t smem = ((size_t)nthr * 16 + 2 * C + 2 * groups) * sizeof(float);
+  groupnorm_kernel<<<N, 256, smem, s>>>(in, in_cs, in_co, gamma, beta, groups, eps, out, out_cs,
+                                        out_co, S, C);
+  RSG_LAUNCH_CHECK();
+  return RSG_OK;
+}
+
+int bilinear2x_launch(cudaStream_t s, const float* in, float* out, int NC, int H, int W, int sig) {
+  const long long total = (long long)NC * 4 * H * W;
+  if (total == 0) return RSG_OK;
+  bilinear2x_kernel<<<ceil_div(total, 256), 256, 0, s>>>(in, out, NC, H, W, sig);
+  RSG_LAUNCH_CHECK();
+  return RSG_OK;
+}
+
+int relation_scores_launch(cudaStream_t s, const bf16* x, int cs, int co, int N, int S, int C,
+                           float* out) {
+  RSG_REQUIRE(C <= 96, "relation_scores: C=%d too large", C);
+  if (N == 0) return RSG_OK;
+  dim3 grid(ceil_div(S, 64), ceil_div(S, 64), N);
+  size_t smem = (size_t)2 * 64 * (C + 1) * sizeof(float);
+  if (smem > 48 * 1024)
+    RSG_CUDA(cudaFuncSetAttribute(relation_scores_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  relation_scores_kernel<<<grid, 256, smem, s>>>(x, cs, co, S, C, out);
+  RSG_LAUNCH_CHECK();
+  return RSG_OK;
+}

@@ -1,0 +1,19 @@
+// Launchers of the non-GEMM kernels (ops.cu) and the TRP attention kernel (attention.cu).
+#pragma once
+#include "conv_params.cuh"
+
+int stem_launch(cudaStream_t s, const float* x, int H, int W, const float* w, const float* bias,
+                bf16* out, int f0, int nb, int n_crops);
+int fuse_launch(cudaStream_t s, int nterms, const ResP* terms, bf16* out, int out_cs, int out_co,
+                int N, int H, int W, int C, int relu);
+int maxpool_launch(cudaStream_t s, const bf16* in, int cs, int co, int N, int H, int W, int C,
+                   bf16* out);
+int groupnorm_launch(cudaStream_t s, const bf16* in, int in_cs, int in_co, const float* gamma,
+                     const float* beta, int groups, float eps, bf16* out, int out_cs, int out_co,
+                     int N, int S, int C);
+int bilinear2x_launch(cudaStream_t s, const float* in, float* out, int NC, int H, int W,
+                      int sigmoid);
+int relation_scores_launch(cudaStream_t s, const bf16* x, int cs, int co, int N, int S, int C,
+                           float* out);
+int attention_launch(cudaStream_t s, const bf16* x, int x_cs, int x_co, const bf16* g, int g_cs,
+                     int g_co, bf16* y, int y_cs, int y_co, int N, int S, int C);

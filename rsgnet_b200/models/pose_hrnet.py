@@ -16,7 +16,33 @@ from . import _params
 logger = logging.getLogger(__name__)
 
 
-class PoseHighResolutionNet(nn.Module):
+class EngineOwner(nn.Module):
+    """nn.Module whose packed-weight engines (rsgnet_b200._engine) are dropped whenever the
+    parameters can have changed: load_state_dict, .to()/.cuda()/.half() (``_apply``), train().
+    The cache dict is shared with DataParallel replicas (``replicate`` shallow-copies __dict__), so
+    it is cleared in place."""
+
+    chunk = 32        # crops processed per pass of the plan (activations stay L2-sized)
+
+    def _drop_engines(self):
+        cache = self.__dict__.get('_rsg_engines')
+        if cache:
+            cache.clear()
+
+    def _apply(self, fn, *a, **kw):
+        self._drop_engines()
+        return super()._apply(fn, *a, **kw)
+
+    def load_state_dict(self, *a, **kw):
+        self._drop_engines()
+        return super().load_state_dict(*a, **kw)
+
+    def train(self, mode=True):
+        self._drop_engines()
+        return super().train(mode)
+
+
+class PoseHighResolutionNet(EngineOwner):
     def __init__(self, cfg, **kwargs):
         super().__init__()
         self.spec = ModelSpec.from_cfg(cfg, KIND_HRNET)

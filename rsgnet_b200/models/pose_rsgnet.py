@@ -13,10 +13,10 @@ import torch.nn as nn
 
 from ..config import KIND_RSGNET, ModelSpec, cfg_get
 from . import _params
-from .pose_hrnet import _init_weights
+from .pose_hrnet import EngineOwner, _init_weights
 
 
-class RSGNet(nn.Module):
+class RSGNet(EngineOwner):
     def __init__(self, cfg, **kwargs):
         super().__init__()
         self.spec = ModelSpec.from_cfg(cfg, KIND_RSGNET)

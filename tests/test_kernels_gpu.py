@@ -1,0 +1,176 @@
+"""Unit parity of single kernels through the C ABI against plain PyTorch fp32 math on the same
+bf16-rounded inputs (tolerance: fp32 accumulation-order noise + one bf16 output rounding)."""
+import ctypes as C
+
+import numpy as np
+import pytest
+import torch
+import torch.nn.functional as F
+
+from rsgnet_b200 import _engine, _lib
+from rsgnet_b200._engine import PlanBuilder, View
+
+pytestmark = pytest.mark.gpu
+
+
+def _run(pb, n):
+    pb.allocate('cuda')
+    handle = C.c_void_p()
+    _lib.check(_lib.lib().rsg_plan_create(C.byref(handle), pb.chunk))
+    _engine.emit(pb, handle)
+    return handle
+
+
+def _exec(handle, n, ext=None):
+    arr = (C.c_void_p * _engine.N_EXT)()
+    for k, t in (ext or {}).items():
+        arr[k] = t.data_ptr()
+    _lib.check(_lib.lib().rsg_plan_run(handle, _lib.stream_ptr(), arr, _engine.N_EXT, n, n, 1, 0))
+    torch.cuda.synchronize()
+
+
+CASES = [
+    # Cin, Cout, k, stride, H, W, relu, residual
+    (32, 32, 3, 1, 16, 12, True, True),
+    (64, 64, 3, 1, 8, 6, True, False),
+    (256, 32, 3, 1, 16, 12, True, False),
+    (32, 64, 3, 2, 16, 12, False, False),
+    (64, 256, 1, 1, 16, 12, True, True),
+    (128, 32, 1, 1, 4, 3, False, False),
+    (96, 96, 3, 1, 16, 12, True, False),
+    (48, 48, 3, 1, 12, 10, True, True),
+    (24, 32, 3, 1, 16, 12, True, False),
+    (16, 16, 3, 1, 24, 16, True, True),
+    (256, 256, 3, 1, 8, 6, True, True),
+    (144, 48, 3, 1, 10, 8, True, False),
+]
+
+
+@pytest.mark.parametrize('cin,cout,k,stride,H,W,relu,use_res', CASES)
+def test_conv_vs_torch(cin, cout, k, stride, H, W, relu, use_res):
+    N = 5
+    g = torch.Generator().manual_seed(cin * 131 + cout)
+    x = torch.randn(N, cin, H, W, generator=g).bfloat16().float()
+    w = (torch.randn(cout, cin, k, k, generator=g) / (cin * k * k) ** 0.5).bfloat16().float()
+    b = torch.randn(cout, generator=g) * 0.1
+    Ho, Wo = (H - 1) // stride + 1, (W - 1) // stride + 1
+    r = torch.randn(N, cout, Ho, Wo, generator=g).bfloat16().float()
+    pb = PlanBuilder(8)
+    xin = pb.buf('x', H, W, cin + 8)           # channel-sliced input (offset 8)
+    rb = pb.buf('r', Ho, Wo, cout)
+    ob = pb.buf('o', Ho, Wo, cout + 16)        # channel-sliced output (offset 8)
+    pb.simple('fuse', dict(terms=[(View(xin), 0)], dst=View(xin), relu=False), [xin], [xin])  # keep x alive
+    pb.conv(View(xin, 8, cin), w.double().numpy(), b.double().numpy(), stride=stride, relu=relu,
+            dst=View(ob, 8, cout), res=[(View(rb), 0)] if use_res else ())
+    pb.ops.pop(0)
+    h = _run(pb, N)
+    pb.tensor_of(xin)[:N, ..., 8:] = x.permute(0, 2, 3, 1).cuda().bfloat16()
+    pb.tensor_of(rb)[:N] = r.permute(0, 2, 3, 1).cuda().bfloat16()
+    pb.tensor_of(ob).fill_(7.0)
+    _exec(h, N)
+    ref = F.conv2d(x, w, b, stride, k // 2)
+    if use_res:
+        ref = ref + r
+    if relu:
+        ref = F.relu(ref)
+    got = pb.tensor_of(ob)[:N, ..., 8:8 + cout].float().permute(0, 3, 1, 2).cpu()
+    err = (got - ref).abs().max().item()
+    assert err <= 2e-2 * max(ref.abs().max().item(), 1.0), err
+    # the untouched channel slices keep their sentinel
+    assert torch.all(pb.tensor_of(ob)[:N, ..., :8] == 7.0) and torch.all(pb.tensor_of(ob)[:N, ..., 8 + cout:] == 7.0)
+    _lib.lib().rsg_plan_destroy(h)
+
+
+def test_conv_fp32_nchw_output_and_upsampled_residuals():
+    N, cin, K, H, W = 3, 32, 17, 16, 12
+    g = torch.Generator().manual_seed(1)
+    x = torch.randn(N, cin, H, W, generator=g).bfloat16().float()
+    w = (torch.randn(K, cin, 1, 1, generator=g) / cin ** 0.5).bfloat16().float()
+    b = torch.randn(K, generator=g)
+    pb = PlanBuilder(4)
+    xin = pb.buf('x', H, W, cin)
+    of = pb.buf('of', H, W, K, itemsize=4)
+    pb.conv(View(xin), w.double().numpy(), b.double().numpy(), out_f32=of)
+    # second conv: 3x3 s2 with two residual terms, one of them nearest-upsampled by 2
+    w2 = (torch.randn(32, cin, 3, 3, generator=g) / (cin * 9) ** 0.5).bfloat16().float()
+    r0 = pb.buf('r0', H // 2, W // 2, 32)
+    r1 = pb.buf('r1', H // 4, W // 4, 32)
+    o2 = pb.buf('o2', H // 2, W // 2, 32)
+    pb.conv(View(xin), w2.double().numpy(), np.zeros(32), stride=2, relu=True, dst=View(o2),
+            res=[(View(r0), 0), (View(r1), 1)])
+    h = _run(pb, N)
+    pb.tensor_of(xin)[:N] = x.permute(0, 2, 3, 1).cuda().bfloat16()
+    a0 = torch.randn(N, 32, H // 2, W // 2, generator=g).bfloat16().float()
+    a1 = torch.randn(N, 32, H // 4, W // 4, generator=g).bfloat16().float()
+    pb.tensor_of(r0)[:N] = a0.permute(0, 2, 3, 1).cuda().bfloat16()
+    pb.tensor_of(r1)[:N] = a1.permute(0, 2, 3, 1).cuda().bfloat16()
+    _exec(h, N)
+    ref = F.conv2d(x, w, b)
+    got = pb.tensor_of(of)[:N].cpu()
+    assert (got - ref).abs().max().item() <= 1e-4 * max(1.0, ref.abs().max().item())
+    ref2 = F.relu(F.conv2d(x, w2, None, 2, 1) + a0 + F.interpolate(a1, scale_factor=2, mode='nearest'))
+    got2 = pb.tensor_of(o2)[:N].float().permute(0, 3, 1, 2).cpu()
+    assert (got2 - ref2).abs().max().item() <= 2e-2 * max(1.0, ref2.abs().max().item())
+    _lib.lib().rsg_plan_destroy(h)
+
+
+@pytest.mark.parametrize('C_,S_hw', [(32, (16, 12)), (16, (12, 8)), (48, (9, 7)), (64, (8, 8))])
+def test_trp_attention_vs_torch(C_, S_hw):
+    N = 3
+    H, W = S_hw
+    S = H * W
+    g = torch.Generator().manual_seed(C_)
+    x = (torch.randn(N, S, C_, generator=g) * 0.5).bfloat16().float()
+    gv = torch.randn(N, S, C_, generator=g).bfloat16().float()
+    pb = PlanBuilder(4)
+    xb = pb.buf('x', H, W, 2 * C_)
+    gb = pb.buf('g', H, W, C_)
+    yb = pb.buf('y', H, W, C_)
+    rel = pb.buf('rel', 1, 1, S * S, itemsize=4)
+    pb.simple('attention', dict(x=View(xb, C_, C_), g=View(gb), y=View(yb)), [xb, gb], [yb])
+    pb.simple('relscores', dict(x=View(xb, C_, C_), out=rel), [xb], [rel])
+    h = _run(pb, N)
+    pb.tensor_of(xb)[:N, ..., C_:] = x.view(N, H, W, C_).cuda().bfloat16()
+    pb.tensor_of(gb)[:N] = gv.view(N, H, W, C_).cuda().bfloat16()
+    _exec(h, N)
+    A = torch.sigmoid(x @ x.transpose(1, 2))
+    ref = A @ gv
+    got = pb.tensor_of(yb)[:N].float().view(N, S, C_).cpu()
+    assert (got - ref).abs().max().item() <= 2e-2 * ref.abs().max().item()
+    got_rel = pb.tensor_of(rel)[:N].view(N, S, S).cpu()
+    assert (got_rel - A).abs().max().item() <= 1e-5
+    _lib.lib().rsg_plan_destroy(h)
+
+
+def test_groupnorm_maxpool_bilinear_fuse_vs_torch():
+    N, C_, H, W = 3, 32, 12, 8
+    g = torch.Generator().manual_seed(3)
+    x = (torch.randn(N, C_, H, W, generator=g) * 2 + 0.7).bfloat16().float()
+    gamma, beta = torch.randn(C_, generator=g), torch.randn(C_, generator=g)
+    pb = PlanBuilder(4)
+    xb = pb.buf('x', H, W, C_)
+    yb = pb.buf('y', H, W, 2 * C_)
+    pool = pb.buf('p', H // 2, W // 2, C_)
+    f32 = pb.buf('f', H, W, 5, itemsize=4)
+    up = pb.buf('u', 2 * H, 2 * W, 5, itemsize=4)
+    fz = pb.buf('fz', H, W, C_)
+    pb.simple('groupnorm', dict(x=View(xb), y=View(yb, C_, C_), groups=8,
+                                gamma=pb.const(gamma.numpy()), beta=pb.const(beta.numpy())), [xb], [yb])
+    pb.simple('maxpool', dict(src=View(xb), dst=pool), [xb], [pool])
+    pb.simple('bilinear', dict(src=f32, out=up, C=5, H=H, W=W, sigmoid=True), [f32], [up])
+    pb.simple('fuse', dict(terms=[(View(xb), 0), (View(pool), 1)], dst=View(fz), relu=True), [xb, pool], [fz])
+    h = _run(pb, N)
+    pb.tensor_of(xb)[:N] = x.permute(0, 2, 3, 1).cuda().bfloat16()
+    src = torch.randn(N, 5, H, W, generator=g)
+    pb.tensor_of(f32)[:N] = src.cuda()
+    _exec(h, N)
+    ref = F.group_norm(x, 8, gamma, beta, 1e-5)
+    got = pb.tensor_of(yb)[:N, ..., C_:].float().permute(0, 3, 1, 2).cpu()
+    assert (got - ref).abs().max().item() <= 2e-2 * ref.abs().max().item()
+    refp = F.max_pool2d(x, 2)
+    assert torch.equal(pb.tensor_of(pool)[:N].float().permute(0, 3, 1, 2).cpu(), refp)
+    refu = torch.sigmoid(F.interpolate(src, scale_factor=2, mode='bilinear', align_corners=True))
+    assert (pb.tensor_of(up)[:N].cpu() - refu).abs().max().item() <= 1e-5
+    reff = F.relu(x + F.interpolate(refp, scale_factor=2, mode='nearest')).bfloat16().float()
+    assert torch.equal(pb.tensor_of(fz)[:N].float().permute(0, 3, 1, 2).cpu(), reff)
+    _lib.lib().rsg_plan_destroy(h)

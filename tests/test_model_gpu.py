@@ -1,0 +1,132 @@
+"""GPU parity of the model path (through the C ABI plan) against the CPU oracle and the
+reference-executed golden fixtures.
+
+Tolerance (stated per BASELINE.json): activations are stored in bf16 (8 bits of mantissa) with fp32
+accumulation, so each stage is compared with the fp32 oracle as  max|got-ref| <= TOL * max|ref|.
+TOL = 0.03 for backbone/head taps and final heat-maps (measured values are printed with -s)."""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import model_oracle
+from rsgnet_b200 import _engine
+from tests.gpu_util import build, crops, rel_err
+
+pytestmark = pytest.mark.gpu
+TOL = 0.03
+
+
+def _nchw(t):
+    return t.float().permute(0, 3, 1, 2).contiguous().cpu().numpy()
+
+
+@pytest.mark.parametrize('key,seed', [('tiny', 0), ('tiny_cp_sub', 1), ('tiny_hrnet', 2)])
+def test_tiny_models_per_stage(golden_dir, key, seed):
+    g = np.load(os.path.join(golden_dir, f'model_{key}.npz'))
+    cfg, net, sd = build(key, seed)
+    B = int(g['batch'])
+    x = crops(cfg, B, seed + 11)
+    stages = {}
+    ref = model_oracle.forward(sd, cfg, x, stages=stages)
+    # debug engine: every buffer keeps its own memory so that taps survive the run
+    eng = _engine.Engine(net, 'cuda', chunk=4, reuse=False)
+    shapes = eng.out_shapes(B)
+    heat = torch.empty(shapes[_engine.EXT_HEAT], device='cuda')
+    aux = {s: torch.empty(shapes[s], device='cuda') for s in shapes if s != _engine.EXT_HEAT}
+    eng.run(x.cuda(), heat, B, B, aux=aux or None)
+    torch.cuda.synchronize()
+    report = {}
+    for name, view in eng.info['taps'].items():
+        if name not in stages:
+            continue
+        got = _nchw(eng.pb.tensor_of(view)[:B])
+        report[name] = rel_err(got, stages[name].numpy())
+    if cfg.MODEL.NAME == 'pose_hrnet':
+        report['heatmaps'] = rel_err(heat.cpu().numpy(), ref.numpy())
+        gold = {'heatmaps': g['out.heatmaps']}
+        outs = {'heatmaps': heat}
+    else:
+        names = ('multi_kpt_scores', 'kpt_scores', 'limbs_scores', 'relation_scores')
+        outs = dict(zip(names, (aux[_engine.EXT_MULTI], heat, aux[_engine.EXT_LIMBS], aux[_engine.EXT_REL])))
+        for nm, r in zip(names, ref):
+            report[nm] = rel_err(outs[nm].cpu().numpy(), r.numpy())
+        gold = {nm: g['out.' + nm] for nm in names}
+    print(key, {k: f'{v:.4f}' for k, v in report.items()})
+    for name, e in report.items():
+        assert e <= TOL, (name, e)
+    for nm, ref_np in gold.items():      # the unmodified reference's outputs
+        assert rel_err(outs[nm].cpu().numpy(), ref_np) <= TOL, nm
+    # module API: same numbers through nn.Module.forward, and chunking / graph replay change nothing
+    out = net(x.cuda())
+    main = out if cfg.MODEL.NAME == 'pose_hrnet' else out[1]
+    assert torch.equal(main, heat)
+    eng2 = _engine.Engine(net, 'cuda', chunk=1)
+    h2 = torch.empty_like(heat)
+    s = torch.cuda.Stream()
+    with torch.cuda.stream(s):
+        for _ in range(3):                 # eager, capture, replay
+            h2.zero_()
+            eng2.run(x.cuda(), h2, B, B, use_graph=True)
+    s.synchronize()
+    assert torch.equal(h2, heat)
+
+
+@pytest.mark.parametrize('key,seed', [('w32_coco', 3), ('w32_crowdpose', 4), ('hrnet_w32_coco', 5),
+                                      ('w48_coco_384', 6)])
+def test_full_models_vs_reference_golden(golden_dir, key, seed):
+    g = np.load(os.path.join(golden_dir, f'model_{key}.npz'))
+    cfg, net, sd = build(key, seed)
+    x = crops(cfg, int(g['batch']), seed + 11).cuda()
+    sub = int(g['sub'])
+    out = net(x)
+    if cfg.MODEL.NAME == 'pose_hrnet':
+        outs = {'heatmaps': out}
+    else:
+        outs = dict(zip(('multi_kpt_scores', 'kpt_scores', 'limbs_scores', 'relation_scores'), out))
+    rep = {}
+    for nm, t in outs.items():
+        if 'out.' + nm in g:
+            ref, got = g['out.' + nm], t.cpu().numpy()
+        else:
+            ref = g['sub.' + nm]
+            flat = t.reshape(-1).cpu().numpy()
+            got = flat[::sub] if flat.size > 65536 else flat
+        rep[nm] = float(np.abs(got - ref).max() / float(g['absmax.' + nm]))
+    print(key, {k: f'{v:.4f}' for k, v in rep.items()})
+    for nm, e in rep.items():
+        assert e <= TOL, (nm, e)
+
+
+def test_flip_batch_equals_two_forwards():
+    """[x ; flip(x)] in one run (stem reads the second half W-reversed) == two separate forwards."""
+    cfg, net, sd = build('tiny', 0)
+    x = crops(cfg, 3, 5).cuda()
+    eng = _engine.engine_for(net, 'cuda')
+    shapes = eng.out_shapes(6)
+    heat = torch.empty(shapes[_engine.EXT_HEAT], device='cuda')
+    eng.run(x, heat, 6, 3)
+    a = net(x)[1]
+    b = net(x.flip(3))[1]
+    assert torch.equal(heat[:3], a) and torch.equal(heat[3:], b)
+
+
+def test_pipeline_matches_reference_loop_on_oracle_heatmaps():
+    """infer_crops == flip-average + decode of this implementation's own heat-maps by the oracle
+    (decode is bit-exact given identical heat-maps)."""
+    from oracle import decode_oracle
+    from rsgnet_b200 import presets, synth
+    from rsgnet_b200.pipeline import CropPipeline
+    cfg, net, sd = build('tiny', 0)
+    B = 5
+    x = crops(cfg, B, 9)
+    c, s = synth.centers_scales(B, seed=1)
+    pipe = CropPipeline(net, cfg, B, use_graph=False)
+    preds, maxvals = pipe(x, c, s)
+    hm = net(x.cuda())[1].cpu().numpy()
+    hf = net(x.cuda().flip(3))[1].cpu().numpy()
+    avg = decode_oracle.flip_average(hm, hf, presets.flip_pairs_for(17), shift=True)
+    o_preds, o_mv = decode_oracle.get_final_preds(True, avg, c, s)
+    assert np.array_equal(preds, o_preds) and np.array_equal(maxvals, o_mv)
+    assert pipe.launches_per_step() > 100
