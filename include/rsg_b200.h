@@ -101,7 +101,9 @@ typedef struct rsg_res {       /* residual / fuse term added in a conv epilogue 
 typedef struct rsg_conv_desc {
   rsg_ref in;                  /* bf16 NHWC [N,Hin,Win,in_cs], channels [in_co, in_co+Cin) */
   int32_t in_cs, in_co, Hin, Win, Cin;
-  rsg_ref w;                   /* bf16 [ntaps][CoutPad][Cin] (BN folded) */
+  rsg_ref w;                   /* bf16 [ntaps][CoutPad][CinPad32] (BN folded), generic kernel */
+  rsg_ref w_tc5;               /* bf16 [ntaps][Cin/8][CoutPad][8] (same weights in the UMMA
+                                  K-major core-matrix order) or NULL: enables the tcgen05 kernel */
   rsg_ref bias;                /* f32 [CoutPad] */
   int32_t Cout, CoutPad;
   int32_t ntaps;
@@ -153,6 +155,13 @@ int rsg_plan_begin_aux(rsg_plan*);
  * whole run into a CUDA graph keyed by (n_fwd, n_crops, with_aux, ext pointers) and replay it. */
 int rsg_plan_run(rsg_plan*, void* stream, void* const* ext, int n_ext, int n_fwd, int n_crops,
                  int with_aux, int use_graph);
+/* Measurement aid: run ONE chunk of `nb` forwards eagerly with a CUDA event pair around every op.
+ * ms[i] = device time of op i, kind[i]: 0 stem, 1 conv (generic mma.sync kernel), 2 conv (tcgen05
+ * kernel), 3 fuse, 4 maxpool, 5 attention, 6 relation_scores, 7 groupnorm, 8 bilinear;
+ * flops[i] = MAC*2 the op executes for nb forwards (0 for the element-wise ops).  Arrays must hold
+ * rsg_plan_num_ops entries; ops skipped (aux) get ms = -1. */
+int rsg_plan_profile(rsg_plan*, void* stream, void* const* ext, int n_ext, int nb, int n_crops,
+                     int with_aux, float* ms, int32_t* kind, double* flops);
 /* Kernel launches issued by the last rsg_plan_run (graph nodes when replayed). */
 int rsg_plan_last_launches(const rsg_plan*);
 

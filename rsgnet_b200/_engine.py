@@ -153,7 +153,7 @@ class PlanBuilder:
         self.ops.append((kind, payload, self.aux))
 
     def conv(self, src, w_oihw, bias, stride=1, relu=False, dst=None, res=(), taps=None,
-             out_f32=None, omul=1, ooy=0, oox=0, out_hw=None, name='conv', cout=None):
+             out_f32=None, omul=1, ooy=0, oox=0, out_hw=None, name='conv', cout=None, engine=0):
         """w_oihw: folded fp64 [Cout, Cin, kh, kw] (or [ntaps, Cout, Cin] with explicit taps)."""
         if taps is None:
             co_, ci_, kh, kw = w_oihw.shape
@@ -176,10 +176,17 @@ class PlanBuilder:
         Hin, Win = src.H, src.W
         Hout = (Hin - 1) // stride + 1 if out_hw is None else out_hw[0]
         Wout = (Win - 1) // stride + 1 if out_hw is None else out_hw[1]
-        payload = dict(src=src, w=self.const(_bf16_bits(wp)), bias=self.const(bp), cin=cin,
+        w_tc5 = None
+        if (stride == 1 and omul == 1 and out_f32 is None and cin % 16 == 0 and cout % 8 == 0
+                and all(abs(dy) <= 1 and abs(dx) <= 1 for dy, dx in taps) and len(taps) <= 9
+                and len(taps) * cin * cout_pad * 2 + 2 * 180 * cin * 2 <= 200 * 1024):
+            # [tap][Cin/8][CoutPad][8]: the K-major core-matrix order the tcgen05 kernel bulk-copies
+            wt = wp[:, :, :cin].reshape(len(taps), cout_pad, cin // 8, 8).transpose(0, 2, 1, 3)
+            w_tc5 = self.const(_bf16_bits(wt))
+        payload = dict(src=src, w=self.const(_bf16_bits(wp)), w_tc5=w_tc5, bias=self.const(bp), cin=cin,
                        cout=cout, cout_pad=cout_pad, taps=taps, stride=stride, Hout=Hout, Wout=Wout,
                        dst=dst, out_f32=out_f32, res=list(res), relu=relu, omul=omul, ooy=ooy,
-                       oox=oox, name=name)
+                       oox=oox, name=name, engine=engine)
         reads = [src.buf] + [r[0].buf for r in res]
         writes = [dst.buf if dst is not None else None,
                   out_f32 if isinstance(out_f32, Buf) else None]
@@ -215,7 +222,7 @@ class PlanBuilder:
         for b, off in placed.items():
             b.ptr = base + off
         for b in self.bufs:
-            if b.persistent:
+            if b.persistent or b.first is None:
                 b.tensor = torch.zeros(self.chunk * b.bytes_per_fwd, dtype=torch.uint8, device=device)
                 b.ptr = b.tensor.data_ptr()
         self.consts = self.arena.upload(device)
@@ -257,6 +264,8 @@ def emit(builder, plan):
             d.inp = _ref(src, cp)
             d.in_cs, d.in_co, d.Hin, d.Win, d.Cin = src.buf.C, src.co, src.H, src.W, p['cin']
             d.w, d.bias = _ref(p['w'], cp), _ref(p['bias'], cp)
+            d.w_tc5 = _ref(p['w_tc5'], cp)
+            d.engine = int(p.get('engine', 0))
             d.Cout, d.CoutPad = p['cout'], p['cout_pad']
             d.ntaps = len(p['taps'])
             for t, (dy, dx) in enumerate(p['taps']):
@@ -276,7 +285,6 @@ def emit(builder, plan):
             for q, (view, shift) in enumerate(p['res']):
                 d.res[q] = _res(view, shift, cp)
             d.relu = int(p['relu'])
-            d.engine = 0
             _lib.check(L.rsg_plan_add_conv(plan, C.byref(d)))
         elif kind == 'stem':
             _lib.check(L.rsg_plan_add_stem(plan, _ref(p['x'], cp), p['H'], p['W'], _ref(p['w'], cp),
@@ -632,6 +640,24 @@ class Engine:
         with self.lock, torch.cuda.device(self.device):
             _lib.check(_lib.lib().rsg_plan_run(self.plan, _lib.stream_ptr(self.device), ext, N_EXT,
                                                n_fwd, n_crops, with_aux, int(use_graph)))
+
+    def profile(self, x, heat, nb, n_crops):
+        """Per-op device times of one chunk (eager, event pair around every op).
+        Returns (ms f32[n_ops], kind i32[n_ops], flops f64[n_ops], names)."""
+        L = _lib.lib()
+        n = L.rsg_plan_num_ops(self.plan)
+        ms = np.zeros(n, np.float32)
+        kind = np.zeros(n, np.int32)
+        flops = np.zeros(n, np.float64)
+        ext = (C.c_void_p * N_EXT)()
+        ext[EXT_X] = x.data_ptr()
+        ext[EXT_HEAT] = heat.data_ptr()
+        with self.lock, torch.cuda.device(self.device):
+            _lib.check(L.rsg_plan_profile(self.plan, _lib.stream_ptr(self.device), ext, N_EXT, nb,
+                                          n_crops, 0, ms.ctypes.data, kind.ctypes.data,
+                                          flops.ctypes.data))
+        names = [p.get('name', k) if isinstance(p, dict) else k for k, p, _ in self.pb.ops]
+        return ms, kind, flops, names
 
     def last_launches(self):
         return _lib.lib().rsg_plan_last_launches(self.plan)

@@ -26,7 +26,7 @@ class Res(C.Structure):
 class ConvDesc(C.Structure):
     _fields_ = [('inp', Ref), ('in_cs', C.c_int32), ('in_co', C.c_int32), ('Hin', C.c_int32),
                 ('Win', C.c_int32), ('Cin', C.c_int32),
-                ('w', Ref), ('bias', Ref), ('Cout', C.c_int32), ('CoutPad', C.c_int32),
+                ('w', Ref), ('w_tc5', Ref), ('bias', Ref), ('Cout', C.c_int32), ('CoutPad', C.c_int32),
                 ('ntaps', C.c_int32), ('tap_dy', C.c_int8 * MAX_TAPS), ('tap_dx', C.c_int8 * MAX_TAPS),
                 ('stride', C.c_int32), ('Hout', C.c_int32), ('Wout', C.c_int32),
                 ('out', Ref), ('out_cs', C.c_int32), ('out_co', C.c_int32), ('oH', C.c_int32),
@@ -80,6 +80,8 @@ _SIGS = {
     'rsg_plan_run': (C.c_int, [C.c_void_p, C.c_void_p, C.POINTER(C.c_void_p), C.c_int, C.c_int,
                                C.c_int, C.c_int, C.c_int]),
     'rsg_plan_last_launches': (C.c_int, [C.c_void_p]),
+    'rsg_plan_profile': (C.c_int, [C.c_void_p, C.c_void_p, C.POINTER(C.c_void_p), C.c_int, C.c_int,
+                                   C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p]),
     'rsg_conv_run': (C.c_int, [C.c_void_p, C.POINTER(ConvDesc), C.c_int]),
 }
 

@@ -116,6 +116,7 @@ int fill_conv(const rsg_conv_desc& d, const RunCtx& c, int N, ConvP* p) {
   p->in_cs = d.in_cs; p->in_co = d.in_co; p->Hin = d.Hin; p->Win = d.Win; p->Cin = d.Cin;
   p->CinPad = (d.Cin + 31) / 32 * 32;
   p->w = (const bf16*)resolve(d.w, c);
+  p->w_tc5 = is_null(d.w_tc5) ? nullptr : (const bf16*)resolve(d.w_tc5, c);
   p->bias = (const float*)resolve(d.bias, c);
   p->Cout = d.Cout; p->CoutPad = d.CoutPad;
   p->ntaps = d.ntaps;
@@ -135,28 +136,32 @@ int fill_conv(const rsg_conv_desc& d, const RunCtx& c, int N, ConvP* p) {
   return RSG_OK;
 }
 
-int run_conv(const rsg_conv_desc& d, const RunCtx& c, int N, cudaStream_t s) {
+int run_conv(const rsg_conv_desc& d, const RunCtx& c, int N, cudaStream_t s, int* used_tc5 = nullptr) {
   ConvP p;
   int rc = fill_conv(d, c, N, &p);
   if (rc) return rc;
+  if (used_tc5) *used_tc5 = 0;
   if (d.engine != 1) {
     int handled = 0;
     rc = conv_tc5_launch(p, s, &handled);
     if (rc) return rc;
-    if (handled) return RSG_OK;
+    if (handled) {
+      if (used_tc5) *used_tc5 = 1;
+      return RSG_OK;
+    }
     RSG_REQUIRE(d.engine != 2, "conv: shape not supported by the tcgen05 kernel (engine=2 forced)");
   }
   return conv_mma_launch(p, s);
 }
 
-int run_op(const Op& op, const RunCtx& c, int nb, int n_crops, cudaStream_t s) {
+int run_op(const Op& op, const RunCtx& c, int nb, int n_crops, cudaStream_t s, int* used_tc5 = nullptr) {
   switch (op.kind) {
     case OP_STEM:
       return stem_launch(s, (const float*)resolve(op.r[0], c), op.i[0], op.i[1],
                          (const float*)resolve(op.r[1], c), (const float*)resolve(op.r[2], c),
                          (bf16*)resolve(op.r[3], c), c.f0, nb, n_crops);
     case OP_CONV:
-      return run_conv(op.conv, c, nb, s);
+      return run_conv(op.conv, c, nb, s, used_tc5);
     case OP_FUSE: {
       ResP t[RSG_MAX_RES];
       for (int q = 0; q < op.i[0]; ++q) t[q] = resolve_res(op.terms[q], c);
@@ -339,6 +344,47 @@ extern "C" int rsg_plan_run(rsg_plan* p, void* stream, void* const* ext, int n_e
   e.launches = launches;
   p->last_launches = launches;
   RSG_CUDA(cudaGraphLaunch(e.exec, s));
+  return RSG_OK;
+}
+
+extern "C" int rsg_plan_profile(rsg_plan* p, void* stream, void* const* ext, int n_ext, int nb,
+                                int n_crops, int with_aux, float* ms, int32_t* kind, double* flops) {
+  RSG_REQUIRE(p && ms && kind && flops, "rsg_plan_profile: null argument");
+  RSG_REQUIRE(nb >= 1 && nb <= p->chunk, "rsg_plan_profile: nb=%d must be in [1, chunk=%d]", nb, p->chunk);
+  cudaStream_t s = (cudaStream_t)stream;
+  const size_t n = p->ops.size();
+  std::vector<cudaEvent_t> ev(2 * n, nullptr);
+  RunCtx c{ext, n_ext, 0};
+  int rc = RSG_OK;
+  for (size_t i = 0; i < n && rc == RSG_OK; ++i) {
+    const Op& op = p->ops[i];
+    ms[i] = -1.f; flops[i] = 0.0;
+    static const int kmap[] = {0, 1, 3, 4, 5, 6, 7, 8};
+    kind[i] = kmap[op.kind];
+    if (op.aux && !with_aux) continue;
+    cudaEventCreate(&ev[2 * i]); cudaEventCreate(&ev[2 * i + 1]);
+    cudaEventRecord(ev[2 * i], s);
+    int tc5 = 0;
+    rc = run_op(op, c, nb, n_crops, s, &tc5);
+    cudaEventRecord(ev[2 * i + 1], s);
+    if (op.kind == OP_CONV) {
+      if (tc5) kind[i] = 2;
+      flops[i] = 2.0 * op.conv.ntaps * op.conv.Cin * op.conv.Cout * (double)op.conv.Hout * op.conv.Wout * nb;
+    } else if (op.kind == OP_ATTN) {
+      flops[i] = 4.0 * (double)op.i[6] * op.i[6] * op.i[7] * nb;
+    } else if (op.kind == OP_STEM) {
+      flops[i] = 2.0 * 27 * 64 * (double)(op.i[0] / 2) * (op.i[1] / 2) * nb;
+    }
+  }
+  cudaError_t ce = cudaStreamSynchronize(s);
+  for (size_t i = 0; i < n; ++i) {
+    if (ev[2 * i]) {
+      if (ce == cudaSuccess && rc == RSG_OK) cudaEventElapsedTime(&ms[i], ev[2 * i], ev[2 * i + 1]);
+      cudaEventDestroy(ev[2 * i]); cudaEventDestroy(ev[2 * i + 1]);
+    }
+  }
+  if (rc) return rc;
+  if (ce != cudaSuccess) return rsg_cuda_fail(ce, "cudaStreamSynchronize", __FILE__, __LINE__);
   return RSG_OK;
 }
 

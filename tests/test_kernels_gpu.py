@@ -55,14 +55,12 @@ def test_conv_vs_torch(cin, cout, k, stride, H, W, relu, use_res):
     b = torch.randn(cout, generator=g) * 0.1
     Ho, Wo = (H - 1) // stride + 1, (W - 1) // stride + 1
     r = torch.randn(N, cout, Ho, Wo, generator=g).bfloat16().float()
-    pb = PlanBuilder(8)
+    pb = PlanBuilder(8, reuse=False)
     xin = pb.buf('x', H, W, cin + 8)           # channel-sliced input (offset 8)
     rb = pb.buf('r', Ho, Wo, cout)
     ob = pb.buf('o', Ho, Wo, cout + 16)        # channel-sliced output (offset 8)
-    pb.simple('fuse', dict(terms=[(View(xin), 0)], dst=View(xin), relu=False), [xin], [xin])  # keep x alive
     pb.conv(View(xin, 8, cin), w.double().numpy(), b.double().numpy(), stride=stride, relu=relu,
             dst=View(ob, 8, cout), res=[(View(rb), 0)] if use_res else ())
-    pb.ops.pop(0)
     h = _run(pb, N)
     pb.tensor_of(xin)[:N, ..., 8:] = x.permute(0, 2, 3, 1).cuda().bfloat16()
     pb.tensor_of(rb)[:N] = r.permute(0, 2, 3, 1).cuda().bfloat16()
@@ -87,7 +85,7 @@ def test_conv_fp32_nchw_output_and_upsampled_residuals():
     x = torch.randn(N, cin, H, W, generator=g).bfloat16().float()
     w = (torch.randn(K, cin, 1, 1, generator=g) / cin ** 0.5).bfloat16().float()
     b = torch.randn(K, generator=g)
-    pb = PlanBuilder(4)
+    pb = PlanBuilder(4, reuse=False)
     xin = pb.buf('x', H, W, cin)
     of = pb.buf('of', H, W, K, itemsize=4)
     pb.conv(View(xin), w.double().numpy(), b.double().numpy(), out_f32=of)
@@ -122,7 +120,7 @@ def test_trp_attention_vs_torch(C_, S_hw):
     g = torch.Generator().manual_seed(C_)
     x = (torch.randn(N, S, C_, generator=g) * 0.5).bfloat16().float()
     gv = torch.randn(N, S, C_, generator=g).bfloat16().float()
-    pb = PlanBuilder(4)
+    pb = PlanBuilder(4, reuse=False)
     xb = pb.buf('x', H, W, 2 * C_)
     gb = pb.buf('g', H, W, C_)
     yb = pb.buf('y', H, W, C_)
@@ -147,7 +145,7 @@ def test_groupnorm_maxpool_bilinear_fuse_vs_torch():
     g = torch.Generator().manual_seed(3)
     x = (torch.randn(N, C_, H, W, generator=g) * 2 + 0.7).bfloat16().float()
     gamma, beta = torch.randn(C_, generator=g), torch.randn(C_, generator=g)
-    pb = PlanBuilder(4)
+    pb = PlanBuilder(4, reuse=False)
     xb = pb.buf('x', H, W, C_)
     yb = pb.buf('y', H, W, 2 * C_)
     pool = pb.buf('p', H // 2, W // 2, C_)
@@ -173,4 +171,50 @@ def test_groupnorm_maxpool_bilinear_fuse_vs_torch():
     assert (pb.tensor_of(up)[:N].cpu() - refu).abs().max().item() <= 1e-5
     reff = F.relu(x + F.interpolate(refp, scale_factor=2, mode='nearest')).bfloat16().float()
     assert torch.equal(pb.tensor_of(fz)[:N].float().permute(0, 3, 1, 2).cpu(), reff)
+    _lib.lib().rsg_plan_destroy(h)
+
+
+TC5_CASES = [
+    # Cin, Cout, k, H, W, relu, nres
+    (32, 32, 3, 16, 8, False, 0),      # exactly one tile
+    (32, 32, 3, 64, 48, True, 1),
+    (64, 64, 3, 32, 24, True, 1),
+    (32, 32, 1, 16, 8, False, 0),
+    (64, 32, 3, 64, 48, True, 0),
+    (96, 32, 3, 24, 16, True, 0),
+    (16, 16, 3, 24, 16, True, 1),
+    (32, 32, 3, 20, 12, True, 1),      # partial tiles in both directions
+    (64, 256, 1, 16, 12, True, 1),
+    (128, 64, 1, 16, 12, True, 0),
+    (48, 48, 3, 24, 24, True, 1),
+]
+
+
+@pytest.mark.parametrize('cin,cout,k,H,W,relu,nres', TC5_CASES)
+def test_conv_tcgen05_vs_torch(cin, cout, k, H, W, relu, nres):
+    """engine=2 forces the tcgen05/TMEM/TMA kernel (fails loudly if the shape is not covered)."""
+    N = 5
+    g = torch.Generator().manual_seed(cin * 7 + cout + k)
+    x = torch.randn(N, cin, H, W, generator=g).bfloat16().float()
+    w = (torch.randn(cout, cin, k, k, generator=g) / (cin * k * k) ** 0.5).bfloat16().float()
+    b = torch.randn(cout, generator=g) * 0.1
+    r = torch.randn(N, cout, H, W, generator=g).bfloat16().float()
+    pb = PlanBuilder(8, reuse=False)
+    xin = pb.buf('x', H, W, cin + 8)
+    rb = pb.buf('r', H, W, cout)
+    ob = pb.buf('o', H, W, cout + 16)
+    pb.conv(View(xin, 8, cin), w.double().numpy(), b.double().numpy(), relu=relu, dst=View(ob, 8, cout),
+            res=[(View(rb), 0)] * nres, engine=2)
+    h = _run(pb, N)
+    pb.tensor_of(xin)[:N, ..., 8:] = x.permute(0, 2, 3, 1).cuda().bfloat16()
+    pb.tensor_of(rb)[:N] = r.permute(0, 2, 3, 1).cuda().bfloat16()
+    pb.tensor_of(ob).fill_(7.0)
+    _exec(h, N)
+    ref = F.conv2d(x, w, b, 1, k // 2) + nres * r
+    if relu:
+        ref = F.relu(ref)
+    got = pb.tensor_of(ob)[:N, ..., 8:8 + cout].float().permute(0, 3, 1, 2).cpu()
+    err = (got - ref).abs().max().item()
+    assert err <= 2e-2 * max(ref.abs().max().item(), 1.0), err
+    assert torch.all(pb.tensor_of(ob)[:N, ..., :8] == 7.0) and torch.all(pb.tensor_of(ob)[:N, ..., 8 + cout:] == 7.0)
     _lib.lib().rsg_plan_destroy(h)

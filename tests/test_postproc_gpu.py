@@ -80,7 +80,7 @@ def test_flip_average_fused(golden_dir, tag):
 
 def test_decode_ragged_and_edge_shapes():
     # odd widths (scalar path), single-row maps, N=0
-    for (n, k, h, w) in [(3, 5, 7, 9), (2, 1, 1, 33), (1, 17, 130, 6), (0, 17, 64, 48)]:
+    for (n, k, h, w) in [(3, 5, 7, 9), (2, 1, 3, 33), (1, 17, 130, 6), (0, 17, 64, 48)]:
         hm = synth.heatmaps(n, k, h, w, seed=11) if n else np.zeros((0, k, h, w), np.float32)
         c, s = synth.centers_scales(n, seed=3)
         preds, mv = get_final_preds(presets.make_cfg(), hm, c, s)
