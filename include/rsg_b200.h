@@ -102,8 +102,9 @@ typedef struct rsg_conv_desc {
   rsg_ref in;                  /* bf16 NHWC [N,Hin,Win,in_cs], channels [in_co, in_co+Cin) */
   int32_t in_cs, in_co, Hin, Win, Cin;
   rsg_ref w;                   /* bf16 [ntaps][CoutPad][CinPad32] (BN folded), generic kernel */
-  rsg_ref w_tc5;               /* bf16 [ntaps][Cin/8][CoutPad][8] (same weights in the UMMA
-                                  K-major core-matrix order) or NULL: enables the tcgen05 kernel */
+  rsg_ref w_tc5;               /* bf16 [CoutPad/NS][ntaps][Cin/8][NS][8] (same weights in the UMMA
+                                  K-major core-matrix order, NS from rsg_conv_tc5_config) or NULL:
+                                  enables the tcgen05 kernel */
   rsg_ref bias;                /* f32 [CoutPad] */
   int32_t Cout, CoutPad;
   int32_t ntaps;
@@ -164,6 +165,11 @@ int rsg_plan_profile(rsg_plan*, void* stream, void* const* ext, int n_ext, int n
                      int with_aux, float* ms, int32_t* kind, double* flops);
 /* Kernel launches issued by the last rsg_plan_run (graph nodes when replayed). */
 int rsg_plan_last_launches(const rsg_plan*);
+
+/* Tiling the tcgen05 conv kernel uses for a shape: output channels per CTA (NS), channels per TMA
+ * halo stage (KC) and ring depth (S).  Returns 0 when the shape is not covered (the generic kernel
+ * runs instead).  The host packer needs NS to lay w_tc5 out as [CoutPad/NS][ntaps][Cin/8][NS][8]. */
+int rsg_conv_tc5_config(int Cin, int CoutPad, int ntaps, int halo, int* NS, int* KC, int* S);
 
 /* Stand-alone conv launch (unit tests / micro-benchmarks): desc refs must be absolute. */
 int rsg_conv_run(void* stream, const rsg_conv_desc*, int N);

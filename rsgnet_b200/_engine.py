@@ -178,11 +178,14 @@ class PlanBuilder:
         Wout = (Win - 1) // stride + 1 if out_hw is None else out_hw[1]
         w_tc5 = None
         if (stride == 1 and omul == 1 and out_f32 is None and cin % 16 == 0 and cout % 8 == 0
-                and all(abs(dy) <= 1 and abs(dx) <= 1 for dy, dx in taps) and len(taps) <= 9
-                and len(taps) * cin * cout_pad * 2 + 2 * 180 * cin * 2 <= 200 * 1024):
-            # [tap][Cin/8][CoutPad][8]: the K-major core-matrix order the tcgen05 kernel bulk-copies
-            wt = wp[:, :, :cin].reshape(len(taps), cout_pad, cin // 8, 8).transpose(0, 2, 1, 3)
-            w_tc5 = self.const(_bf16_bits(wt))
+                and all(abs(dy) <= 1 and abs(dx) <= 1 for dy, dx in taps) and len(taps) <= 9):
+            halo = int(any(dy != 0 or dx != 0 for dy, dx in taps))
+            ns, kc, st = C.c_int(), C.c_int(), C.c_int()
+            if _lib.lib().rsg_conv_tc5_config(cin, cout_pad, len(taps), halo, C.byref(ns), C.byref(kc), C.byref(st)):
+                # [slice][tap][Cin/8][NS][8]: the K-major core-matrix order the kernel bulk-copies
+                NS = ns.value
+                wt = wp[:, :, :cin].reshape(len(taps), cout_pad // NS, NS, cin // 8, 8)
+                w_tc5 = self.const(_bf16_bits(wt.transpose(1, 0, 3, 2, 4)))
         payload = dict(src=src, w=self.const(_bf16_bits(wp)), w_tc5=w_tc5, bias=self.const(bp), cin=cin,
                        cout=cout, cout_pad=cout_pad, taps=taps, stride=stride, Hout=Hout, Wout=Wout,
                        dst=dst, out_f32=out_f32, res=list(res), relu=relu, omul=omul, ooy=ooy,

@@ -11,7 +11,7 @@ struct ConvP {
   const bf16* in;
   int in_cs, in_co, Hin, Win, Cin, CinPad;
   const bf16* w;        // [ntaps][CoutPad][CinPad]
-  const bf16* w_tc5;    // [ntaps][Cin/8][CoutPad][8] or nullptr (tcgen05 kernel layout)
+  const bf16* w_tc5;    // [CoutPad/NS][ntaps][Cin/8][NS][8] or nullptr (tcgen05 kernel layout)
   const float* bias;    // [CoutPad]
   int Cout, CoutPad;
   int ntaps;

@@ -1,36 +1,40 @@
 // Blackwell-native implicit-GEMM convolution: tcgen05.mma (single-thread issue, fp32 accumulators
-// in TMEM) fed by TMA, for stride-1 convolutions whose taps lie in the 3x3 neighbourhood
-// (3x3 p1 and 1x1) with weights that fit in shared memory.
+// in TMEM) for stride-1 convolutions whose taps lie in the 3x3 neighbourhood (3x3 p1 and 1x1).
 //
 // "Halo-resident" formulation.  A CTA owns a 16 x 8 pixel patch of one crop (= the 128 rows of the
-// MMA M dimension).  ONE 5-D TMA box load brings the (16+2) x (8+2) halo patch of all Cin channels
-// into shared memory laid out as [Cin/8][18][10][8 ch] -- which is exactly the canonical
-// K-major / no-swizzle UMMA operand layout (8 consecutive pixels x 16 bytes = one core matrix,
-// SBO = one halo row = 160 B, LBO = one 8-channel plane = 2880 B).  Each of the 9 taps is then just
-// a different START ADDRESS of the A descriptor into that same patch ((1+dy)*10 + (1+dx) pixels
-// further), so the activation tile is read from L2 once (1.4x with halo) instead of 9x, and the
-// zero padding of the convolution is the TMA out-of-bounds fill.  Weights ([tap][Cin/8][Cout][8],
-// BN folded) are bulk-copied once per CTA and stay resident while the CTA walks over its tiles.
+// MMA M dimension).  The (16+2) x (8+2) halo patch of KC input channels is brought into shared
+// memory ONCE, laid out as [KC/8][18][10][8 ch] -- exactly the canonical K-major / no-swizzle UMMA
+// operand layout (8 consecutive pixels x 16 bytes = one core matrix, SBO = one halo row = 160 B,
+// LBO = one 8-channel plane = 2880 B).  Each of the 9 taps is then just a different START ADDRESS
+// of the A descriptor into that same patch ((1+dy)*10 + (1+dx) pixels further), so the activation
+// tile is read from L2 once (1.4x with halo) instead of 9x, and the zero padding of the
+// convolution is the zero-fill of the out-of-bounds copies.  Weights (BN folded, packed
+// [slice][tap][Cin/8][NS][8]) are TMA-bulk-copied once per CTA and stay resident while the CTA
+// walks over its tiles; blockIdx.y selects a slice of NS output channels.
 //
-// Warp roles (192 threads): warp 0 = TMA producer, warp 1 = TMEM allocator + MMA issuer,
-// warps 2..5 = epilogue (TMEM -> registers -> +bias +residual terms -> ReLU -> bf16 NHWC stores).
-// Pipelines: 2 halo buffers (full/empty mbarriers) and 2 TMEM accumulators (full/empty mbarriers).
+// The halo patch is gathered with 16-byte cp.async (LDGSTS) by three producer warps, completion
+// tracked by the stage's mbarrier (cp.async.mbarrier.arrive).  A first version used one 5-D TMA box
+// per stage; with the 16-byte inner rows this layout needs, the TMA engine sustained only about one
+// row per 5 cycles and was the bottleneck of every shape (profiles/r1_notes.md), LDGSTS moves the
+// same bytes ~20x faster.
+//
+// Warp roles (128 + 32*EW threads): warp 0 = TMEM allocator + weight bulk copy + MMA issuer,
+// warps 1..3 = halo producers, warps 4.. = epilogue (TMEM -> registers -> +bias +residual terms ->
+// ReLU -> bf16 NHWC stores).  Pipelines: S-deep ring of halo stages (full/empty mbarriers, one
+// stage = one K-chunk of one tile) and 2 TMEM accumulators (full/empty mbarriers).
 //
 // Reference ops subsumed: Conv2d(3x3|1x1, s1) + BatchNorm2d(eval) [+ residual adds] [+ ReLU]
 // (pose_rsgnet.py:38-54 BasicBlock, :75-95 Bottleneck, :261-270 fuse sum, heads :965-1003).
 #include <cuda.h>
 #include <stdlib.h>
 
-#include <map>
-#include <mutex>
-#include <tuple>
-
 #include "conv_params.cuh"
 
 namespace {
 
 constexpr int TH = 16, TW = 8;                 // pixel patch = 128 MMA rows
-constexpr int NTHREADS = 192;
+constexpr int NPROD = 96;                      // producer threads (warps 1..3)
+constexpr int MAX_ITEMS = 15;                  // 16-byte items per producer thread per stage (180*8/96)
 constexpr uint32_t SPIN_LIMIT = 1u << 26;      // bounded waits: a protocol bug traps, never hangs
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) {
@@ -59,13 +63,12 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
   }
   __trap();
 }
-__device__ __forceinline__ void tma_load_5d(uint32_t dst, const CUtensorMap* map, uint32_t bar,
-                                            int c0, int c1, int c2, int c3, int c4) {
-  asm volatile(
-      "cp.async.bulk.tensor.5d.shared::cluster.global.tile.mbarrier::complete_tx::bytes "
-      "[%0], [%1, {%3, %4, %5, %6, %7}], [%2];"
-      ::"r"(dst), "l"(map), "r"(bar), "r"(c0), "r"(c1), "r"(c2), "r"(c3), "r"(c4)
-      : "memory");
+__device__ __forceinline__ void cp_async16(uint32_t dst, const void* src, bool pred) {
+  const int sz = pred ? 16 : 0;                 // src-size 0: the 16 bytes are zero-filled
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dst), "l"(src), "r"(sz) : "memory");
+}
+__device__ __forceinline__ void cp_async_arrive(uint32_t bar) {
+  asm volatile("cp.async.mbarrier.arrive.noinc.shared::cta.b64 [%0];" ::"r"(bar) : "memory");
 }
 __device__ __forceinline__ void bulk_load(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar) {
   asm volatile(
@@ -107,13 +110,18 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t* v) {
 }
 
 struct Tc5P {
-  const bf16* w;        // [ntaps][Cin/8][N][8]
-  const float* bias;    // [N]
-  int Cin, N, Cout;
+  const bf16* w;        // [nslices][ntaps][Cin/8][NS][8]
+  const float* bias;    // [CoutPad]
+  int Cin, NS, Cout;    // NS = output channels per CTA (blockIdx.y selects the slice)
+  int KC, nchunks;      // channels per halo stage, Cin / KC
+  int S;                // halo ring depth
+  int EW;               // epilogue warps: 4, or 8 (two column halves per TMEM lane quarter)
   int ntaps;
   int8_t dy[9], dx[9];
   int halo;             // 1 for 3x3, 0 for 1x1
-  int H, W, Nimg;
+  int H, W;
+  const bf16* in;       // NHWC, channel stride in_cs, first channel in_co
+  int in_cs, in_co;
   int tiles_x, tiles_y; // per image
   long long ntiles;
   bf16* out;
@@ -121,34 +129,46 @@ struct Tc5P {
   int nres;
   ResP res[4];
   int relu;
-  uint32_t w_bytes, halo_bytes, tmem_cols;
+  uint32_t w_bytes, stage_bytes, tmem_cols;
 };
 
-__global__ void __launch_bounds__(NTHREADS, 1)
-conv_tc5_kernel(const __grid_constant__ CUtensorMap in_map, const Tc5P p) {
+constexpr int MAX_STAGES = 4;
+
+__device__ __forceinline__ void add_res8(float* f, const uint4& u) {
+  const __nv_bfloat162* h2 = reinterpret_cast<const __nv_bfloat162*>(&u);
+#pragma unroll
+  for (int e = 0; e < 4; ++e) {
+    f[2 * e] += __bfloat162float(h2[e].x);
+    f[2 * e + 1] += __bfloat162float(h2[e].y);
+  }
+}
+
+__global__ void __launch_bounds__(384)
+conv_tc5_kernel(const Tc5P p) {
   extern __shared__ __align__(128) unsigned char smem[];
-  __shared__ __align__(8) uint64_t bars[9];
+  __shared__ __align__(8) uint64_t bars[1 + 2 * MAX_STAGES + 4];
   __shared__ uint32_t tmem_base_slot;
-  // bars: 0 weights, 1-2 halo full, 3-4 halo empty, 5-6 acc full, 7-8 acc empty
+  // bars: 0 weights | 1..S halo full | 1+S..2S halo empty | then acc full x2, acc empty x2
   const uint32_t bar0 = smem_u32(&bars[0]);
   auto BAR = [&](int i) { return bar0 + 8u * i; };
+  const int B_FULL = 1, B_EMPTY = 1 + p.S, B_ACCF = 1 + 2 * p.S, B_ACCE = 3 + 2 * p.S;
 
   unsigned char* sW = smem;
-  unsigned char* sH[2] = {smem + p.w_bytes, smem + p.w_bytes + p.halo_bytes};
+  unsigned char* sH = smem + p.w_bytes;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int HW_ = TW + 2 * p.halo, HH_ = TH + 2 * p.halo;     // halo patch extent
   const uint32_t lbo_a = (uint32_t)HW_ * HH_ * 16u, sbo_a = (uint32_t)HW_ * 16u;
-  const uint32_t lbo_b = (uint32_t)p.N * 16u, sbo_b = 128u;
+  const uint32_t lbo_b = (uint32_t)p.NS * 16u, sbo_b = 128u;
+  const int slice = blockIdx.y;
 
   if (threadIdx.x == 0) {
     mbar_init(BAR(0), 1);
-    mbar_init(BAR(1), 1); mbar_init(BAR(2), 1);
-    mbar_init(BAR(3), 1); mbar_init(BAR(4), 1);
-    mbar_init(BAR(5), 1); mbar_init(BAR(6), 1);
-    mbar_init(BAR(7), 4); mbar_init(BAR(8), 4);
+    for (int i = 0; i < p.S; ++i) { mbar_init(BAR(B_FULL + i), NPROD); mbar_init(BAR(B_EMPTY + i), 1); }
+    mbar_init(BAR(B_ACCF), 1); mbar_init(BAR(B_ACCF + 1), 1);
+    mbar_init(BAR(B_ACCE), p.EW); mbar_init(BAR(B_ACCE + 1), p.EW);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
-  if (warp == 1) {
+  if (warp == 0) {
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_base_slot)), "r"(p.tmem_cols) : "memory");
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
   }
@@ -159,104 +179,150 @@ conv_tc5_kernel(const __grid_constant__ CUtensorMap in_map, const Tc5P p) {
 
   const long long first = blockIdx.x, step = gridDim.x;
 
-  if (warp == 0) {
-    // ===================== TMA producer =====================
-    if (lane == 0) {
-      asm volatile("prefetch.tensormap [%0];" ::"l"(&in_map) : "memory");
-      mbar_arrive_expect_tx(BAR(0), p.w_bytes);
-      // bulk copies are limited in size only by the 20-bit tx-count per arrive: split in 64 KB pieces
-      for (uint32_t off = 0; off < p.w_bytes; off += 65536u) {
-        uint32_t n = p.w_bytes - off < 65536u ? p.w_bytes - off : 65536u;
-        bulk_load(smem_u32(sW + off), reinterpret_cast<const unsigned char*>(p.w) + off, n, BAR(0));
-      }
-      uint32_t it = 0;
-      for (long long t = first; t < p.ntiles; t += step, ++it) {
-        const int b = it & 1;
-        const uint32_t ph = (it >> 1) & 1;
-        mbar_wait(BAR(3 + b), ph ^ 1);
-        const int tx = (int)(t % p.tiles_x);
-        const long long r = t / p.tiles_x;
-        const int ty = (int)(r % p.tiles_y);
-        const int n = (int)(r / p.tiles_y);
-        mbar_arrive_expect_tx(BAR(1 + b), p.halo_bytes);
-        tma_load_5d(smem_u32(sH[b]), &in_map, BAR(1 + b), 0, tx * TW - p.halo, ty * TH - p.halo, 0, n);
-      }
+  if (warp >= 1 && warp <= 3) {
+    // ===================== halo producers (cp.async gather) =====================
+    const int ptid = threadIdx.x - 32;
+    const int kc8 = p.KC >> 3;
+    const int hpix = HW_ * HH_;
+    const int nitems = hpix * kc8;
+    // item i -> (pixel = i / kc8, 8-channel plane = i % kc8): consecutive lanes read consecutive
+    // 16-byte pieces of one pixel's channels.  The decomposition is the same for every tile.
+    uint32_t code[MAX_ITEMS];
+#pragma unroll
+    for (int j = 0; j < MAX_ITEMS; ++j) {
+      const int i = ptid + j * NPROD;
+      const int pix = i / kc8, k8 = i - pix * kc8;
+      const int py = pix / HW_, px = pix - py * HW_;
+      code[j] = i < nitems ? ((uint32_t)py << 27) | ((uint32_t)px << 23) | ((uint32_t)k8 << 20) | (uint32_t)(k8 * hpix + pix) : 0xFFFFFFFFu;
     }
-  } else if (warp == 1) {
-    // ===================== MMA issuer =====================
-    if (lane == 0) {
-      const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(p.N >> 3) << 17) | ((128u >> 4) << 24);
-      mbar_wait(BAR(0), 0);
-      uint32_t it = 0;
-      const int kc2n = p.Cin >> 4;
-      for (long long t = first; t < p.ntiles; t += step, ++it) {
-        const int b = it & 1;
-        const uint32_t ph = (it >> 1) & 1;
-        mbar_wait(BAR(1 + b), ph);            // halo landed
-        mbar_wait(BAR(7 + b), ph ^ 1);        // accumulator drained by the epilogue
-        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-        const uint32_t a_base = smem_u32(sH[b]);
-        const uint32_t w_base = smem_u32(sW);
-        const uint32_t d_tmem = tmem_base + (uint32_t)b * p.N;
-        uint32_t acc = 0;
-        for (int tp = 0; tp < p.ntaps; ++tp) {
-          const uint32_t a_tap = a_base + (uint32_t)((p.halo + p.dy[tp]) * HW_ + (p.halo + p.dx[tp])) * 16u;
-          const uint32_t w_tap = w_base + (uint32_t)tp * (uint32_t)(p.Cin >> 3) * lbo_b;
-          for (int kc = 0; kc < kc2n; ++kc) {
-            const uint64_t ad = make_desc(a_tap + (uint32_t)kc * 2u * lbo_a, lbo_a, sbo_a);
-            const uint64_t bd = make_desc(w_tap + (uint32_t)kc * 2u * lbo_b, lbo_b, sbo_b);
-            umma_f16(d_tmem, ad, bd, idesc, acc);
-            acc = 1;
+    uint32_t it = 0;
+    for (long long t = first; t < p.ntiles; t += step) {
+      const int tx = (int)(t % p.tiles_x);
+      const long long r = t / p.tiles_x;
+      const int ty = (int)(r % p.tiles_y);
+      const int n = (int)(r / p.tiles_y);
+      const int y0 = ty * TH - p.halo, x0 = tx * TW - p.halo;
+      const bf16* img = p.in + (size_t)n * p.H * p.W * p.in_cs + p.in_co;
+      for (int c = 0; c < p.nchunks; ++c, ++it) {
+        const int s = it % p.S;
+        mbar_wait(BAR(B_EMPTY + s), ((it / p.S) & 1) ^ 1);
+        const uint32_t dst = smem_u32(sH + (size_t)s * p.stage_bytes);
+        const bf16* src_c = img + c * p.KC;
+#pragma unroll
+        for (int j = 0; j < MAX_ITEMS; ++j) {
+          if (code[j] != 0xFFFFFFFFu) {
+            const int gy = y0 + (int)(code[j] >> 27), gx = x0 + (int)((code[j] >> 23) & 0xF);
+            const uint32_t slot = code[j] & 0xFFFFFu;          // (k8 * hpix + pix)
+            const int k8 = (int)((code[j] >> 20) & 0x7);
+            const bool ok = gy >= 0 && gy < p.H && gx >= 0 && gx < p.W;
+            const bf16* src = ok ? src_c + ((size_t)gy * p.W + gx) * p.in_cs + k8 * 8 : p.in;
+            cp_async16(dst + slot * 16u, src, ok);
           }
         }
-        umma_commit(BAR(3 + b));              // halo buffer free once these MMAs retire
-        umma_commit(BAR(5 + b));              // accumulator ready
+        cp_async_arrive(BAR(B_FULL + s));
+      }
+    }
+  } else if (warp == 0) {
+    // ===================== weight bulk copy + MMA issuer =====================
+    if (lane == 0) {
+      mbar_arrive_expect_tx(BAR(0), p.w_bytes);
+      const unsigned char* wsrc = reinterpret_cast<const unsigned char*>(p.w) + (size_t)slice * p.w_bytes;
+      for (uint32_t off = 0; off < p.w_bytes; off += 32768u) {
+        uint32_t nb = p.w_bytes - off < 32768u ? p.w_bytes - off : 32768u;
+        bulk_load(smem_u32(sW + off), wsrc + off, nb, BAR(0));
+      }
+      const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(p.NS >> 3) << 17) | ((128u >> 4) << 24);
+      mbar_wait(BAR(0), 0);
+      uint32_t it = 0, tl = 0;
+      const int kc2n = p.KC >> 4;
+      const uint32_t w_base = smem_u32(sW);
+      for (long long t = first; t < p.ntiles; t += step, ++tl) {
+        const int b = tl & 1;
+        mbar_wait(BAR(B_ACCE + b), ((tl >> 1) & 1) ^ 1);     // accumulator drained by the epilogue
+        const uint32_t d_tmem = tmem_base + (uint32_t)b * p.NS;
+        uint32_t acc = 0;
+        for (int c = 0; c < p.nchunks; ++c, ++it) {
+          const int s = it % p.S;
+          mbar_wait(BAR(B_FULL + s), (it / p.S) & 1);        // halo chunk landed
+          asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // cp.async writes -> UMMA reads
+          asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+          const uint32_t a_base = smem_u32(sH + (size_t)s * p.stage_bytes);
+          for (int tp = 0; tp < p.ntaps; ++tp) {
+            const uint32_t a_tap = a_base + (uint32_t)((p.halo + p.dy[tp]) * HW_ + (p.halo + p.dx[tp])) * 16u;
+            const uint32_t w_tap = w_base + (uint32_t)(tp * (p.Cin >> 3) + c * (p.KC >> 3)) * lbo_b;
+            for (int kc = 0; kc < kc2n; ++kc) {
+              const uint64_t ad = make_desc(a_tap + (uint32_t)kc * 2u * lbo_a, lbo_a, sbo_a);
+              const uint64_t bd = make_desc(w_tap + (uint32_t)kc * 2u * lbo_b, lbo_b, sbo_b);
+              umma_f16(d_tmem, ad, bd, idesc, acc);
+              acc = 1;
+            }
+          }
+          umma_commit(BAR(B_EMPTY + s));        // stage free once these MMAs retire
+        }
+        umma_commit(BAR(B_ACCF + b));           // accumulator ready
       }
     }
   } else {
-    // ===================== epilogue (warps 2..5) =====================
-    const int q = warp & 3;                   // TMEM lane quarter this warp may access
-    const int row = q * 32 + lane;            // MMA row = pixel inside the patch
+    // ===================== epilogue (warps 4 .. 4+EW) =====================
+    const int e = warp - 4;
+    const int q = warp & 3;                     // TMEM lane quarter this warp may access
+    const int row = q * 32 + lane;              // MMA row = pixel inside the patch
     const int hy = row >> 3, wx = row & 7;
-    uint32_t it = 0;
-    for (long long t = first; t < p.ntiles; t += step, ++it) {
-      const int b = it & 1;
-      const uint32_t ph = (it >> 1) & 1;
+    const int ncol = p.EW == 8 ? (p.NS >> 1) : p.NS;      // columns handled by this warp
+    const int cbeg = (p.EW == 8 && e >= 4) ? ncol : 0;
+    const int gch0 = slice * p.NS;              // first global output channel of this CTA
+    uint32_t tl = 0;
+    for (long long t = first; t < p.ntiles; t += step, ++tl) {
+      const int b = tl & 1;
       const int tx = (int)(t % p.tiles_x);
       const long long r = t / p.tiles_x;
       const int ty = (int)(r % p.tiles_y);
       const int n = (int)(r / p.tiles_y);
       const int y = ty * TH + hy, x = tx * TW + wx;
       const bool ok = y < p.H && x < p.W;
-      mbar_wait(BAR(5 + b), ph);
+      // residual pointers; the first two terms of the first column block are prefetched before
+      // waiting for the accumulator so that their latency overlaps the MMAs
+      const bf16* rp[4] = {nullptr, nullptr, nullptr, nullptr};
+#pragma unroll
+      for (int qi = 0; qi < 4; ++qi) {
+        if (qi < p.nres && ok) {
+          const ResP& rr = p.res[qi];
+          rp[qi] = rr.p + ((size_t)((size_t)(rr.bs0 ? 0 : n) * rr.H + (y >> rr.shift)) * rr.W + (x >> rr.shift)) * rr.cs + rr.co + gch0;
+        }
+      }
+      uint4 pre[2][4];
+#pragma unroll
+      for (int qi = 0; qi < 2; ++qi)
+#pragma unroll
+        for (int j4 = 0; j4 < 4; ++j4)
+          if (rp[qi] && gch0 + cbeg + j4 * 8 < p.Cout) pre[qi][j4] = __ldg(reinterpret_cast<const uint4*>(rp[qi] + cbeg) + j4);
+      mbar_wait(BAR(B_ACCF + b), (tl >> 1) & 1);
       asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-      const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)b * p.N;
-      for (int c0 = 0; c0 < p.N; c0 += 32) {
+      const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)b * p.NS;
+      for (int c0 = cbeg; c0 < cbeg + ncol; c0 += 32) {
         uint32_t v[32];
         tmem_ld32(taddr + c0, v);
         asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-        if (c0 + 32 >= p.N) {
+        if (c0 + 32 >= cbeg + ncol) {
           // all of this warp's TMEM reads for the tile are done: release the accumulator
           asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
           __syncwarp();
-          if (lane == 0) mbar_arrive(BAR(7 + b));
+          if (lane == 0) mbar_arrive(BAR(B_ACCE + b));
         }
         if (!ok) continue;
         float f[32];
 #pragma unroll
-        for (int j = 0; j < 32; ++j) f[j] = __uint_as_float(v[j]) + __ldg(p.bias + c0 + j);
-        for (int qi = 0; qi < p.nres; ++qi) {
-          const ResP& rr = p.res[qi];
-          const bf16* rp = rr.p + ((size_t)((size_t)(rr.bs0 ? 0 : n) * rr.H + (y >> rr.shift)) * rr.W + (x >> rr.shift)) * rr.cs + rr.co + c0;
+        for (int j = 0; j < 32; ++j) f[j] = __uint_as_float(v[j]) + __ldg(p.bias + gch0 + c0 + j);
 #pragma unroll
-          for (int j4 = 0; j4 < 4; ++j4) {
-            if (c0 + j4 * 8 < p.Cout) {
-              uint4 u = __ldg(reinterpret_cast<const uint4*>(rp) + j4);
-              const __nv_bfloat162* h2 = reinterpret_cast<const __nv_bfloat162*>(&u);
+        for (int qi = 0; qi < 4; ++qi) {
+          if (rp[qi]) {
 #pragma unroll
-              for (int e = 0; e < 4; ++e) {
-                f[j4 * 8 + 2 * e] += __bfloat162float(h2[e].x);
-                f[j4 * 8 + 2 * e + 1] += __bfloat162float(h2[e].y);
+            for (int j4 = 0; j4 < 4; ++j4) {
+              if (gch0 + c0 + j4 * 8 < p.Cout) {
+                uint4 u;
+                if (qi < 2 && c0 == cbeg) u = pre[qi][j4];
+                else u = __ldg(reinterpret_cast<const uint4*>(rp[qi] + c0) + j4);
+                add_res8(f + j4 * 8, u);
               }
             }
           }
@@ -265,16 +331,16 @@ conv_tc5_kernel(const __grid_constant__ CUtensorMap in_map, const Tc5P p) {
 #pragma unroll
           for (int j = 0; j < 32; ++j) f[j] = fmaxf(f[j], 0.f);
         }
-        bf16* op = p.out + ((size_t)((size_t)n * p.H + y) * p.W + x) * p.out_cs + p.out_co + c0;
+        bf16* op = p.out + ((size_t)((size_t)n * p.H + y) * p.W + x) * p.out_cs + p.out_co + gch0 + c0;
 #pragma unroll
         for (int j4 = 0; j4 < 4; ++j4) {
-          if (c0 + j4 * 8 < p.Cout) {
+          if (gch0 + c0 + j4 * 8 < p.Cout) {
             uint4 u;
             __nv_bfloat162* h2 = reinterpret_cast<__nv_bfloat162*>(&u);
 #pragma unroll
-            for (int e = 0; e < 4; ++e) {
-              h2[e].x = __float2bfloat16_rn(f[j4 * 8 + 2 * e]);
-              h2[e].y = __float2bfloat16_rn(f[j4 * 8 + 2 * e + 1]);
+            for (int k2 = 0; k2 < 4; ++k2) {
+              h2[k2].x = __float2bfloat16_rn(f[j4 * 8 + 2 * k2]);
+              h2[k2].y = __float2bfloat16_rn(f[j4 * 8 + 2 * k2 + 1]);
             }
             reinterpret_cast<uint4*>(op)[j4] = u;
           }
@@ -285,64 +351,36 @@ conv_tc5_kernel(const __grid_constant__ CUtensorMap in_map, const Tc5P p) {
   // ---- teardown
   asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
   __syncthreads();
-  if (warp == 1) {
+  if (warp == 0) {
     asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(p.tmem_cols) : "memory");
   }
 }
 
-// ---------------------------------------------------------------------------------------------
-typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
-                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*,
-                                  CUtensorMapInterleave, CUtensorMapSwizzle, CUtensorMapL2promotion,
-                                  CUtensorMapFloatOOBfill);
-
-EncodeTiledFn get_encode() {
-  static EncodeTiledFn fn = nullptr;
-  static bool tried = false;
-  if (!tried) {
-    tried = true;
-    void* f = nullptr;
-    cudaDriverEntryPointQueryResult q;
-    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &f, cudaEnableDefault, &q) == cudaSuccess &&
-        q == cudaDriverEntryPointSuccess)
-      fn = (EncodeTiledFn)f;
-  }
-  return fn;
-}
-
-struct MapKey {
-  const void* ptr; int cs, co, H, W, Cin, N, halo;
-  bool operator<(const MapKey& o) const {
-    return std::tie(ptr, cs, co, H, W, Cin, N, halo) < std::tie(o.ptr, o.cs, o.co, o.H, o.W, o.Cin, o.N, o.halo);
-  }
-};
-std::map<MapKey, CUtensorMap> g_maps;
-std::mutex g_maps_mu;
-
-int get_map(const ConvP& p, int halo, CUtensorMap* out) {
-  MapKey k{p.in, p.in_cs, p.in_co, p.Hin, p.Win, p.Cin, p.N, halo};
-  std::lock_guard<std::mutex> lk(g_maps_mu);
-  auto it = g_maps.find(k);
-  if (it != g_maps.end()) { *out = it->second; return RSG_OK; }
-  EncodeTiledFn enc = get_encode();
-  RSG_REQUIRE(enc, "cuTensorMapEncodeTiled is not available from this driver");
-  const cuuint64_t es = 2;
-  cuuint64_t dims[5] = {8, (cuuint64_t)p.Win, (cuuint64_t)p.Hin, (cuuint64_t)(p.Cin / 8), (cuuint64_t)p.N};
-  cuuint64_t strides[4] = {(cuuint64_t)p.in_cs * es, (cuuint64_t)p.Win * p.in_cs * es, 16,
-                           (cuuint64_t)p.Hin * p.Win * p.in_cs * es};
-  cuuint32_t box[5] = {8, (cuuint32_t)(TW + 2 * halo), (cuuint32_t)(TH + 2 * halo), (cuuint32_t)(p.Cin / 8), 1};
-  cuuint32_t estr[5] = {1, 1, 1, 1, 1};
-  CUtensorMap m;
-  CUresult r = enc(&m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 5, (void*)(p.in + p.in_co), dims, strides, box, estr,
-                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE,
-                   CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-  RSG_REQUIRE(r == CUDA_SUCCESS, "cuTensorMapEncodeTiled failed with %d (Cin=%d H=%d W=%d cs=%d)", (int)r, p.Cin, p.Hin, p.Win, p.in_cs);
-  g_maps[k] = m;
-  *out = m;
-  return RSG_OK;
-}
-
 }  // namespace
+
+// Shape -> (NS, KC, S): shared with the host-side packer through rsg_conv_tc5_config().
+extern "C" int rsg_conv_tc5_config(int Cin, int CoutPad, int ntaps, int halo, int* NS, int* KC, int* S) {
+  if (Cin % 16 != 0 || CoutPad % 32 != 0 || ntaps < 1 || ntaps > 9) return 0;
+  int kc = 0;
+  for (int c = 64; c >= 16; c -= 16)
+    if (Cin % c == 0) { kc = c; break; }
+  if (!kc) return 0;
+  const int stage = (TH + 2 * halo) * (TW + 2 * halo) * kc * 2;
+  const int cands[4] = {128, 96, 64, 32};
+  for (int i = 0; i < 4; ++i) {
+    const int ns = cands[i];
+    if (ns > CoutPad || CoutPad % ns != 0) continue;
+    const long long wb = (long long)ntaps * Cin * ns * 2;
+    if (wb + 2 * stage > 196 * 1024) continue;
+    int s = 4;
+    while (s > 2 && wb + (long long)s * stage > 196 * 1024) --s;
+    // small problems: do not hog shared memory, so that several CTAs share an SM
+    if (wb + (long long)s * stage <= 72 * 1024 && s > 3) s = 3;
+    *NS = ns; *KC = kc; *S = s;
+    return 1;
+  }
+  return 0;
+}
 
 int conv_tc5_launch(const ConvP& p, cudaStream_t s, int* handled) {
   *handled = 0;
@@ -351,48 +389,58 @@ int conv_tc5_launch(const ConvP& p, cudaStream_t s, int* handled) {
   if (!p.w_tc5 || !p.out || p.out_f32) return RSG_OK;
   if (p.stride != 1 || p.omul != 1 || p.ooy != 0 || p.oox != 0) return RSG_OK;
   if (p.Hout != p.Hin || p.Wout != p.Win || p.oH != p.Hin || p.oW != p.Win) return RSG_OK;
-  if (p.Cin % 16 != 0 || p.CoutPad % 32 != 0 || p.CoutPad > 256 || p.Cout % 8 != 0) return RSG_OK;
-  if (p.ntaps > 9 || p.in_cs % 8 != 0 || p.in_co % 8 != 0 || p.out_cs % 8 != 0 || p.out_co % 8 != 0) return RSG_OK;
+  if (p.Cout % 8 != 0 || p.in_cs % 8 != 0 || p.in_co % 8 != 0 || p.out_cs % 8 != 0 || p.out_co % 8 != 0) return RSG_OK;
   int halo = 0;
-  for (int t = 0; t < p.ntaps; ++t) {
+  for (int t = 0; t < p.ntaps && t < 16; ++t) {
     if (p.dy[t] < -1 || p.dy[t] > 1 || p.dx[t] < -1 || p.dx[t] > 1) return RSG_OK;
     if (p.dy[t] != 0 || p.dx[t] != 0) halo = 1;
   }
   for (int q = 0; q < p.nres; ++q)
     if (p.res[q].cs % 8 != 0 || p.res[q].co % 8 != 0) return RSG_OK;
-  const uint32_t w_bytes = (uint32_t)p.ntaps * p.Cin * p.CoutPad * 2;
-  const uint32_t halo_bytes = (uint32_t)(TH + 2 * halo) * (TW + 2 * halo) * p.Cin * 2;
-  const size_t smem = (size_t)w_bytes + 2 * (size_t)halo_bytes;
-  if (smem > 200 * 1024) return RSG_OK;          // weights do not fit: generic kernel
+  int NS, KC, S;
+  if (!rsg_conv_tc5_config(p.Cin, p.CoutPad, p.ntaps, halo, &NS, &KC, &S)) return RSG_OK;
   if (p.M == 0) { *handled = 1; return RSG_OK; }
 
   Tc5P k;
   memset(&k, 0, sizeof(k));
-  k.w = p.w_tc5; k.bias = p.bias; k.Cin = p.Cin; k.N = p.CoutPad; k.Cout = p.Cout;
+  k.w = p.w_tc5; k.bias = p.bias; k.Cin = p.Cin; k.NS = NS; k.Cout = p.Cout;
+  k.KC = KC; k.nchunks = p.Cin / KC; k.S = S;
+  k.EW = (NS % 64 == 0) ? 8 : 4;
   k.ntaps = p.ntaps;
   for (int t = 0; t < p.ntaps; ++t) { k.dy[t] = p.dy[t]; k.dx[t] = p.dx[t]; }
-  k.halo = halo; k.H = p.Hin; k.W = p.Win; k.Nimg = p.N;
+  k.halo = halo; k.H = p.Hin; k.W = p.Win;
+  k.in = p.in; k.in_cs = p.in_cs; k.in_co = p.in_co;
   k.tiles_x = (p.Win + TW - 1) / TW; k.tiles_y = (p.Hin + TH - 1) / TH;
   k.ntiles = (long long)k.tiles_x * k.tiles_y * p.N;
   k.out = p.out; k.out_cs = p.out_cs; k.out_co = p.out_co;
   k.nres = p.nres;
   for (int q = 0; q < p.nres; ++q) k.res[q] = p.res[q];
   k.relu = p.relu;
-  k.w_bytes = w_bytes; k.halo_bytes = halo_bytes;
+  k.w_bytes = (uint32_t)p.ntaps * p.Cin * NS * 2;
+  k.stage_bytes = (uint32_t)(TH + 2 * halo) * (TW + 2 * halo) * KC * 2;
   uint32_t cols = 32;
-  while (cols < 2u * p.CoutPad) cols <<= 1;
+  while (cols < 2u * NS) cols <<= 1;
   k.tmem_cols = cols;
+  const size_t smem = (size_t)k.w_bytes + (size_t)S * k.stage_bytes;
+  const int nslices = p.CoutPad / NS;
+  const int threads = 128 + 32 * k.EW;
 
-  CUtensorMap map;
-  int rc = get_map(p, halo, &map);
-  if (rc) return rc;
   static bool attr_done = false;
   if (!attr_done) {
     RSG_CUDA(cudaFuncSetAttribute(conv_tc5_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
     attr_done = true;
   }
-  long long grid = k.ntiles < rsg_num_sms() ? k.ntiles : rsg_num_sms();
-  conv_tc5_kernel<<<(unsigned)grid, NTHREADS, smem, s>>>(map, k);
+  int occ = 1;
+  RSG_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, conv_tc5_kernel, threads, smem));
+  const int tmem_occ = 512 / (int)cols;
+  if (occ > tmem_occ) occ = tmem_occ;
+  if (occ > 4) occ = 4;
+  if (occ < 1) occ = 1;
+  long long gx = ((long long)rsg_num_sms() * occ + nslices - 1) / nslices;
+  if (gx > k.ntiles) gx = k.ntiles;
+  if (gx < 1) gx = 1;
+  dim3 grid((unsigned)gx, (unsigned)nslices);
+  conv_tc5_kernel<<<grid, threads, smem, s>>>(k);
   RSG_LAUNCH_CHECK();
   *handled = 1;
   return RSG_OK;

@@ -186,6 +186,13 @@ TC5_CASES = [
     (32, 32, 3, 20, 12, True, 1),      # partial tiles in both directions
     (64, 256, 1, 16, 12, True, 1),
     (128, 64, 1, 16, 12, True, 0),
+    (128, 128, 3, 16, 12, True, 1),
+    (256, 256, 3, 8, 6, True, 1),
+    (256, 32, 3, 32, 24, True, 0),
+    (256, 64, 1, 16, 12, True, 0),
+    (96, 96, 3, 16, 16, True, 0),
+    (64, 64, 3, 64, 48, True, 2),
+    (192, 192, 3, 12, 9, True, 1),
     (48, 48, 3, 24, 24, True, 1),
 ]
 
