@@ -33,9 +33,11 @@
 namespace {
 
 constexpr int TH = 16, TW = 8;                 // pixel patch = 128 MMA rows
-constexpr int NPROD = 96;                      // producer threads (warps 1..3)
-constexpr int MAX_ITEMS = 15;                  // 16-byte items per producer thread per stage (180*8/96)
-constexpr uint32_t SPIN_LIMIT = 1u << 26;      // bounded waits: a protocol bug traps, never hangs
+constexpr int NTHREADS = 512;                  // one fat persistent CTA per SM
+constexpr int NMMA = 2;                        // MMA-issuing warps (0, 1): alternate tiles
+constexpr int NPROD = 192;                     // producer threads (warps 2..7)
+constexpr int EPI_WARP0 = 8;                   // epilogue warps 8..15
+constexpr uint32_t SPIN_LIMIT = 1u << 21;      // bounded waits: a protocol bug traps, never hangs
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) {
   return (uint32_t)__cvta_generic_to_shared(p);
@@ -61,6 +63,8 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
         : "memory");
     if (done) return;
   }
+  printf("[conv_tc5] mbarrier wait timed out: smem 0x%x parity %u block (%d,%d) thread %d\n", bar, parity,
+         (int)blockIdx.x, (int)blockIdx.y, (int)threadIdx.x);
   __trap();
 }
 __device__ __forceinline__ void cp_async16(uint32_t dst, const void* src, bool pred) {
@@ -85,14 +89,33 @@ __device__ __forceinline__ uint64_t make_desc(uint32_t saddr, uint32_t lbo_bytes
   d |= (uint64_t)1 << 46;                       // descriptor version (Blackwell)
   return d;                                     // base_offset = 0, layout_type = SWIZZLE_NONE (0)
 }
+// No "memory" clobber on purpose: the descriptor-table loads of the next MMAs must be free to move
+// above this instruction (volatile keeps the MMAs ordered among themselves and with the barriers).
 __device__ __forceinline__ void umma_f16(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc,
                                          uint32_t idesc, uint32_t accumulate) {
   asm volatile(
       "{\n\t.reg .pred p;\n\t"
       "setp.ne.b32 p, %4, 0;\n\t"
       "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
-      ::"r"(d_tmem), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
-      : "memory");
+      ::"r"(d_tmem), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate));
+}
+// Launder a value through an asm so that ptxas keeps it in a register instead of re-deriving it
+// (it re-materialised shared-window addresses with S2R + LEA before every cp.async).
+__device__ __forceinline__ uint32_t opaque(uint32_t v) {
+  uint32_t r;
+  asm volatile("mov.u32 %0, %1;" : "=r"(r) : "r"(v));
+  return r;
+}
+__device__ __forceinline__ bool elect_one() {
+  uint32_t pred;
+  asm volatile("{\n\t.reg .pred p;\n\telect.sync _|p, 0xffffffff;\n\tselp.u32 %0, 1, 0, p;\n\t}" : "=r"(pred));
+  return pred != 0;
+}
+__device__ __forceinline__ uint32_t desc_lo(uint32_t saddr, uint32_t lbo_bytes) {
+  return ((saddr >> 4) & 0x3FFFu) | (((lbo_bytes >> 4) & 0x3FFFu) << 16);
+}
+__device__ __forceinline__ uint32_t desc_hi(uint32_t sbo_bytes) {
+  return ((sbo_bytes >> 4) & 0x3FFFu) | (1u << 14);     // version 1 (bit 46), SWIZZLE_NONE
 }
 __device__ __forceinline__ void umma_commit(uint32_t bar) {
   asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
@@ -109,15 +132,26 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t* v) {
       : "r"(taddr));
 }
 
+__device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t* v) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
+      "{%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
+      : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]),
+        "=r"(v[8]), "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15])
+      : "r"(taddr));
+}
+
 struct Tc5P {
   const bf16* w;        // [nslices][ntaps][Cin/8][NS][8]
   const float* bias;    // [CoutPad]
   int Cin, NS, Cout;    // NS = output channels per CTA (blockIdx.y selects the slice)
   int KC, nchunks;      // channels per halo stage, Cin / KC
   int S;                // halo ring depth
+  int NACC;             // TMEM accumulator ring depth
   int EW;               // epilogue warps: 4, or 8 (two column halves per TMEM lane quarter)
   int ntaps;
   int8_t dy[9], dx[9];
+  int tapoff[9];        // A start-address offset of each tap inside the halo patch, 16-byte units
   int halo;             // 1 for 3x3, 0 for 1x1
   int H, W;
   const bf16* in;       // NHWC, channel stride in_cs, first channel in_co
@@ -130,9 +164,13 @@ struct Tc5P {
   ResP res[4];
   int relu;
   uint32_t w_bytes, stage_bytes, tmem_cols;
+  long long* dbg;       // debug timeline (CTA 0): [tile][8] clock64 stamps, or nullptr
+  int skip;             // debug: bit0 no halo loads, bit1 no MMAs, bit2 no residual loads, bit3 no stores
 };
 
-constexpr int MAX_STAGES = 4;
+constexpr int MAX_STAGES = 8;
+constexpr int MAX_ACC = 8;
+constexpr int MAX_CHUNKS = 8;
 
 __device__ __forceinline__ void add_res8(float* f, const uint4& u) {
   const __nv_bfloat162* h2 = reinterpret_cast<const __nv_bfloat162*>(&u);
@@ -143,15 +181,16 @@ __device__ __forceinline__ void add_res8(float* f, const uint4& u) {
   }
 }
 
-__global__ void __launch_bounds__(384)
+__global__ void __launch_bounds__(NTHREADS, 1)
 conv_tc5_kernel(const Tc5P p) {
   extern __shared__ __align__(128) unsigned char smem[];
-  __shared__ __align__(8) uint64_t bars[1 + 2 * MAX_STAGES + 4];
+  __shared__ __align__(8) uint64_t bars[1 + 2 * MAX_STAGES + 2 * MAX_ACC];
   __shared__ uint32_t tmem_base_slot;
-  // bars: 0 weights | 1..S halo full | 1+S..2S halo empty | then acc full x2, acc empty x2
+  __shared__ __align__(16) float sBias[128];       // bias of this CTA's NS output channels
+  // bars: 0 weights | 1..S halo full | 1+S..2S halo empty | then acc full x NACC, acc empty x NACC
   const uint32_t bar0 = smem_u32(&bars[0]);
   auto BAR = [&](int i) { return bar0 + 8u * i; };
-  const int B_FULL = 1, B_EMPTY = 1 + p.S, B_ACCF = 1 + 2 * p.S, B_ACCE = 3 + 2 * p.S;
+  const int B_FULL = 1, B_EMPTY = 1 + p.S, B_ACCF = 1 + 2 * p.S, B_ACCE = 1 + 2 * p.S + p.NACC;
 
   unsigned char* sW = smem;
   unsigned char* sH = smem + p.w_bytes;
@@ -164,10 +203,10 @@ conv_tc5_kernel(const Tc5P p) {
   if (threadIdx.x == 0) {
     mbar_init(BAR(0), 1);
     for (int i = 0; i < p.S; ++i) { mbar_init(BAR(B_FULL + i), NPROD); mbar_init(BAR(B_EMPTY + i), 1); }
-    mbar_init(BAR(B_ACCF), 1); mbar_init(BAR(B_ACCF + 1), 1);
-    mbar_init(BAR(B_ACCE), p.EW); mbar_init(BAR(B_ACCE + 1), p.EW);
+    for (int i = 0; i < p.NACC; ++i) { mbar_init(BAR(B_ACCF + i), 1); mbar_init(BAR(B_ACCE + i), 8); }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
+  for (int i = threadIdx.x; i < p.NS; i += blockDim.x) sBias[i] = p.bias[slice * p.NS + i];
   if (warp == 0) {
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_base_slot)), "r"(p.tmem_cols) : "memory");
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
@@ -179,173 +218,212 @@ conv_tc5_kernel(const Tc5P p) {
 
   const long long first = blockIdx.x, step = gridDim.x;
 
-  if (warp >= 1 && warp <= 3) {
+  if (warp >= NMMA && warp < EPI_WARP0) {
     // ===================== halo producers (cp.async gather) =====================
-    const int ptid = threadIdx.x - 32;
+    const int ptid = threadIdx.x - 32 * NMMA;
     const int kc8 = p.KC >> 3;
     const int hpix = HW_ * HH_;
     const int nitems = hpix * kc8;
     // item i -> (pixel = i / kc8, 8-channel plane = i % kc8): consecutive lanes read consecutive
     // 16-byte pieces of one pixel's channels.  The decomposition is the same for every tile.
-    uint32_t code[MAX_ITEMS];
-#pragma unroll
-    for (int j = 0; j < MAX_ITEMS; ++j) {
-      const int i = ptid + j * NPROD;
-      const int pix = i / kc8, k8 = i - pix * kc8;
-      const int py = pix / HW_, px = pix - py * HW_;
-      code[j] = i < nitems ? ((uint32_t)py << 27) | ((uint32_t)px << 23) | ((uint32_t)k8 << 20) | (uint32_t)(k8 * hpix + pix) : 0xFFFFFFFFu;
-    }
-    uint32_t it = 0;
-    for (long long t = first; t < p.ntiles; t += step) {
-      const int tx = (int)(t % p.tiles_x);
-      const long long r = t / p.tiles_x;
-      const int ty = (int)(r % p.tiles_y);
-      const int n = (int)(r / p.tiles_y);
+    // NPROD is a multiple of KC/8, so a thread always copies the same 8-channel plane k8 and walks
+    // over pixels pix0, pix0 + PS, ...: no per-thread tables, a dozen instructions per 16 bytes.
+    const int k8 = ptid % kc8, pix0 = ptid / kc8, PS = NPROD / kc8;
+    const int nj = (hpix - pix0 + PS - 1) / PS;              // items of this thread per stage
+    const uint32_t sH_u32 = opaque(smem_u32(sH)) + (uint32_t)(k8 * hpix) * 16u;
+    const uint32_t bar_full = opaque(BAR(B_FULL)), bar_empty = opaque(BAR(B_EMPTY));
+    const int W = p.W, H = p.H, cs = p.in_cs;
+    uint32_t it = 0, tl = 0;
+    const int tiles_per_img = p.tiles_x * p.tiles_y;
+    const uint32_t S2 = (uint32_t)p.S / NMMA;          // each MMA warp owns its own ring of S/2 stages
+    for (int t = (int)first; t < (int)p.ntiles; t += (int)step, ++tl) {
+      const int n = t / tiles_per_img;
+      const int rem = t - n * tiles_per_img;
+      const int ty = rem / p.tiles_x, tx = rem - ty * p.tiles_x;
       const int y0 = ty * TH - p.halo, x0 = tx * TW - p.halo;
-      const bf16* img = p.in + (size_t)n * p.H * p.W * p.in_cs + p.in_co;
-      for (int c = 0; c < p.nchunks; ++c, ++it) {
-        const int s = it % p.S;
-        mbar_wait(BAR(B_EMPTY + s), ((it / p.S) & 1) ^ 1);
-        const uint32_t dst = smem_u32(sH + (size_t)s * p.stage_bytes);
-        const bf16* src_c = img + c * p.KC;
-#pragma unroll
-        for (int j = 0; j < MAX_ITEMS; ++j) {
-          if (code[j] != 0xFFFFFFFFu) {
-            const int gy = y0 + (int)(code[j] >> 27), gx = x0 + (int)((code[j] >> 23) & 0xF);
-            const uint32_t slot = code[j] & 0xFFFFFu;          // (k8 * hpix + pix)
-            const int k8 = (int)((code[j] >> 20) & 0x7);
-            const bool ok = gy >= 0 && gy < p.H && gx >= 0 && gx < p.W;
-            const bf16* src = ok ? src_c + ((size_t)gy * p.W + gx) * p.in_cs + k8 * 8 : p.in;
-            cp_async16(dst + slot * 16u, src, ok);
+      const bf16* tile0 = p.in + ((long long)n * H * W + (long long)y0 * W + x0) * cs + p.in_co + k8 * 8;
+      uint32_t j = (tl / NMMA) * (uint32_t)p.nchunks;  // stage counter inside the owning warp's ring
+      for (int c = 0; c < p.nchunks; ++c, ++it, ++j) {
+        const int s = (int)((j % S2) * NMMA + (tl % NMMA));
+        mbar_wait(bar_empty + 8u * s, ((j / S2) & 1) ^ 1);
+        if (p.dbg && blockIdx.x == 0 && blockIdx.y == 0 && ptid == 0 && it < 64) p.dbg[it * 8 + 0] = clock64();
+        const uint32_t dst = sH_u32 + (uint32_t)s * p.stage_bytes;
+        const bf16* src_c = tile0 + c * p.KC;
+        if (!(p.skip & 1)) {
+#pragma unroll 4
+          for (int j = 0; j < nj; ++j) {
+            const int pix = pix0 + j * PS;
+            const int py = p.halo ? (int)(((uint32_t)pix * 52429u) >> 19) : (pix >> 3);   // pix / HW_
+            const int px = pix - py * HW_;
+            const bool ok = (unsigned)(y0 + py) < (unsigned)H && (unsigned)(x0 + px) < (unsigned)W;
+            cp_async16(dst + (uint32_t)pix * 16u, ok ? src_c + (py * W + px) * cs : p.in, ok);
           }
         }
-        cp_async_arrive(BAR(B_FULL + s));
+        cp_async_arrive(bar_full + 8u * s);
+        if (p.dbg && blockIdx.x == 0 && blockIdx.y == 0 && ptid == 0 && it < 64) p.dbg[it * 8 + 1] = clock64();
       }
     }
-  } else if (warp == 0) {
-    // ===================== weight bulk copy + MMA issuer =====================
-    if (lane == 0) {
+  } else if (warp < NMMA) {
+    // ===================== weight bulk copy + MMA issuers =====================
+    // Two issuing warps, alternating tiles: one warp sustains one UTCHMMA per ~86 cycles whatever N
+    // is, two together reach the operand-fetch floor (40 / 48 / 64 cycles for N = 32 / 64 / 128;
+    // tools/umma_rate.cu, profiles/r1_notes.md).
+    // The whole warp runs this loop with warp-uniform values and only the tcgen05 instructions
+    // are predicated on one elected lane: UTCHMMA takes its descriptors from UNIFORM registers, and
+    // issuing from inside `if (lane == 0)` made the compiler wrap every MMA in a ~20-instruction
+    // R2UR "waterfall" loop (~150 cycles per MMA, profiles/r1_notes.md).
+    if (warp == 0 && elect_one()) {
       mbar_arrive_expect_tx(BAR(0), p.w_bytes);
       const unsigned char* wsrc = reinterpret_cast<const unsigned char*>(p.w) + (size_t)slice * p.w_bytes;
       for (uint32_t off = 0; off < p.w_bytes; off += 32768u) {
         uint32_t nb = p.w_bytes - off < 32768u ? p.w_bytes - off : 32768u;
         bulk_load(smem_u32(sW + off), wsrc + off, nb, BAR(0));
       }
-      const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(p.NS >> 3) << 17) | ((128u >> 4) << 24);
-      mbar_wait(BAR(0), 0);
-      uint32_t it = 0, tl = 0;
-      const int kc2n = p.KC >> 4;
-      const uint32_t w_base = smem_u32(sW);
-      for (long long t = first; t < p.ntiles; t += step, ++tl) {
-        const int b = tl & 1;
-        mbar_wait(BAR(B_ACCE + b), ((tl >> 1) & 1) ^ 1);     // accumulator drained by the epilogue
-        const uint32_t d_tmem = tmem_base + (uint32_t)b * p.NS;
-        uint32_t acc = 0;
-        for (int c = 0; c < p.nchunks; ++c, ++it) {
-          const int s = it % p.S;
-          mbar_wait(BAR(B_FULL + s), (it / p.S) & 1);        // halo chunk landed
-          asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // cp.async writes -> UMMA reads
-          asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-          const uint32_t a_base = smem_u32(sH + (size_t)s * p.stage_bytes);
-          for (int tp = 0; tp < p.ntaps; ++tp) {
-            const uint32_t a_tap = a_base + (uint32_t)((p.halo + p.dy[tp]) * HW_ + (p.halo + p.dx[tp])) * 16u;
-            const uint32_t w_tap = w_base + (uint32_t)(tp * (p.Cin >> 3) + c * (p.KC >> 3)) * lbo_b;
+    }
+    __syncwarp();
+    const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(p.NS >> 3) << 17) | ((128u >> 4) << 24);
+    mbar_wait(BAR(0), 0);
+    const int kc2n = p.KC >> 4;
+    const uint32_t hiA = desc_hi(sbo_a), hiB = desc_hi(sbo_b);
+    const uint32_t a0 = smem_u32(sH), w0 = smem_u32(sW);
+    const uint32_t a_kstep = (2u * lbo_a) >> 4, b_kstep = (2u * lbo_b) >> 4;     // per k16 step, in 16-byte units
+    const uint32_t b_tapstep = ((uint32_t)(p.Cin >> 3) * lbo_b) >> 4;
+    const uint32_t b_chunkstep = ((uint32_t)(p.KC >> 3) * lbo_b) >> 4;
+    const uint32_t lo_lbo_a = ((lbo_a >> 4) & 0x3FFFu) << 16, lo_lbo_b = ((lbo_b >> 4) & 0x3FFFu) << 16;
+    for (uint32_t tl = (uint32_t)warp; (long long)first + (long long)tl * step < p.ntiles; tl += NMMA) {
+      const int b = tl % p.NACC;
+      mbar_wait(BAR(B_ACCE + b), ((tl / p.NACC) & 1) ^ 1);  // accumulator drained by the epilogue
+      const uint32_t d_tmem = tmem_base + (uint32_t)b * p.NS;
+      if (p.dbg && blockIdx.x == 0 && blockIdx.y == 0 && lane == 0 && tl < 64) p.dbg[tl * 8 + 2] = clock64();
+      // Each issuing warp consumes its OWN ring of S/2 stages (slots warp, warp+2, ...).  With one
+      // shared ring a warp could wait for phase k+1 of a slot before phase k had completed, and an
+      // mbarrier parity wait cannot tell "not yet" from "one phase ago".
+      const uint32_t S2 = (uint32_t)p.S / NMMA;
+      uint32_t j = (tl / NMMA) * (uint32_t)p.nchunks;
+      for (int c = 0; c < p.nchunks; ++c, ++j) {
+        const int s = (int)((j % S2) * NMMA + (uint32_t)warp);
+        mbar_wait(BAR(B_FULL + s), (j / S2) & 1);          // halo chunk landed
+        if (p.dbg && blockIdx.x == 0 && blockIdx.y == 0 && lane == 0 && tl < 64) p.dbg[tl * 8 + 3] = clock64();
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // cp.async writes -> UMMA reads
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        const uint32_t a_stage = (a0 + (uint32_t)s * p.stage_bytes) >> 4;
+        const uint32_t w_chunk = (w0 >> 4) + (uint32_t)c * b_chunkstep;
+        if (elect_one()) {
+          uint32_t acc = c > 0;
+          const int ntp = (p.skip & 2) ? 1 : p.ntaps;
+          for (int tp = 0; tp < ntp; ++tp) {
+            uint32_t alo = a_stage + (uint32_t)p.tapoff[tp];
+            uint32_t blo = w_chunk + (uint32_t)tp * b_tapstep;
             for (int kc = 0; kc < kc2n; ++kc) {
-              const uint64_t ad = make_desc(a_tap + (uint32_t)kc * 2u * lbo_a, lbo_a, sbo_a);
-              const uint64_t bd = make_desc(w_tap + (uint32_t)kc * 2u * lbo_b, lbo_b, sbo_b);
+              const uint64_t ad = ((uint64_t)hiA << 32) | (alo & 0x3FFFu) | lo_lbo_a;
+              const uint64_t bd = ((uint64_t)hiB << 32) | (blo & 0x3FFFu) | lo_lbo_b;
               umma_f16(d_tmem, ad, bd, idesc, acc);
               acc = 1;
+              alo += a_kstep;
+              blo += b_kstep;
             }
           }
           umma_commit(BAR(B_EMPTY + s));        // stage free once these MMAs retire
+          if (c == p.nchunks - 1) umma_commit(BAR(B_ACCF + b));   // accumulator ready
         }
-        umma_commit(BAR(B_ACCF + b));           // accumulator ready
+        __syncwarp();
       }
+      if (p.dbg && blockIdx.x == 0 && blockIdx.y == 0 && lane == 0 && tl < 64) p.dbg[tl * 8 + 4] = clock64();
     }
   } else {
-    // ===================== epilogue (warps 4 .. 4+EW) =====================
-    const int e = warp - 4;
-    const int q = warp & 3;                     // TMEM lane quarter this warp may access
+    // ===================== epilogue (warps 8 .. 15) =====================
+    // 8 warps: TMEM lane quarter q = warp & 3 (hardware rule), column half = (warp - 4) >> 2.
+    // The kernel is bound by the instruction latency of these warps (profiles/r1_notes.md), hence
+    // 16-column blocks (few live registers -> 2 CTAs per SM) and the bias staged in shared memory.
+    const int e = warp - EPI_WARP0;
+    const int q = warp & 3;
     const int row = q * 32 + lane;              // MMA row = pixel inside the patch
     const int hy = row >> 3, wx = row & 7;
-    const int ncol = p.EW == 8 ? (p.NS >> 1) : p.NS;      // columns handled by this warp
-    const int cbeg = (p.EW == 8 && e >= 4) ? ncol : 0;
+    const int ncol = p.NS >> 1;                 // columns handled by this warp
+    const int cbeg = (e >= 4) ? ncol : 0;
     const int gch0 = slice * p.NS;              // first global output channel of this CTA
+    const int tiles_per_img = p.tiles_x * p.tiles_y;
     uint32_t tl = 0;
-    for (long long t = first; t < p.ntiles; t += step, ++tl) {
-      const int b = tl & 1;
-      const int tx = (int)(t % p.tiles_x);
-      const long long r = t / p.tiles_x;
-      const int ty = (int)(r % p.tiles_y);
-      const int n = (int)(r / p.tiles_y);
+    for (int t = (int)first; t < (int)p.ntiles; t += (int)step, ++tl) {
+      const int b = tl % p.NACC;
+      const int n = t / tiles_per_img;
+      const int rem = t - n * tiles_per_img;
+      const int ty = rem / p.tiles_x, tx = rem - ty * p.tiles_x;
       const int y = ty * TH + hy, x = tx * TW + wx;
       const bool ok = y < p.H && x < p.W;
-      // residual pointers; the first two terms of the first column block are prefetched before
-      // waiting for the accumulator so that their latency overlaps the MMAs
       const bf16* rp[4] = {nullptr, nullptr, nullptr, nullptr};
 #pragma unroll
       for (int qi = 0; qi < 4; ++qi) {
-        if (qi < p.nres && ok) {
+        if (qi < p.nres && ok && !(p.skip & 4)) {
           const ResP& rr = p.res[qi];
           rp[qi] = rr.p + ((size_t)((size_t)(rr.bs0 ? 0 : n) * rr.H + (y >> rr.shift)) * rr.W + (x >> rr.shift)) * rr.cs + rr.co + gch0;
         }
       }
-      uint4 pre[2][4];
+      // first two residual terms of the first column block: issued before waiting for the
+      // accumulator so that their latency overlaps the MMAs
+      uint4 pre[2][2];
 #pragma unroll
       for (int qi = 0; qi < 2; ++qi)
 #pragma unroll
-        for (int j4 = 0; j4 < 4; ++j4)
-          if (rp[qi] && gch0 + cbeg + j4 * 8 < p.Cout) pre[qi][j4] = __ldg(reinterpret_cast<const uint4*>(rp[qi] + cbeg) + j4);
-      mbar_wait(BAR(B_ACCF + b), (tl >> 1) & 1);
+        for (int j2 = 0; j2 < 2; ++j2)
+          if (rp[qi] && gch0 + cbeg + j2 * 8 < p.Cout) pre[qi][j2] = __ldg(reinterpret_cast<const uint4*>(rp[qi] + cbeg) + j2);
+      bf16* orow = ok ? p.out + ((size_t)((size_t)n * p.H + y) * p.W + x) * p.out_cs + p.out_co + gch0 : nullptr;
+      mbar_wait(BAR(B_ACCF + b), (tl / p.NACC) & 1);
+      if (p.dbg && blockIdx.x == 0 && blockIdx.y == 0 && threadIdx.x == 32 * EPI_WARP0 && tl < 64) p.dbg[tl * 8 + 5] = clock64();
       asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
       const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)b * p.NS;
-      for (int c0 = cbeg; c0 < cbeg + ncol; c0 += 32) {
-        uint32_t v[32];
-        tmem_ld32(taddr + c0, v);
+      for (int c0 = cbeg; c0 < cbeg + ncol; c0 += 16) {
+        uint32_t v[16];
+        tmem_ld16(taddr + c0, v);
         asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-        if (c0 + 32 >= cbeg + ncol) {
+        if (c0 + 16 >= cbeg + ncol) {
           // all of this warp's TMEM reads for the tile are done: release the accumulator
           asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
           __syncwarp();
           if (lane == 0) mbar_arrive(BAR(B_ACCE + b));
+          if (p.dbg && blockIdx.x == 0 && blockIdx.y == 0 && threadIdx.x == 32 * EPI_WARP0 && tl < 64) p.dbg[tl * 8 + 6] = clock64();
         }
         if (!ok) continue;
-        float f[32];
+        float f[16];
+        const float4* bp = reinterpret_cast<const float4*>(sBias + c0);
 #pragma unroll
-        for (int j = 0; j < 32; ++j) f[j] = __uint_as_float(v[j]) + __ldg(p.bias + gch0 + c0 + j);
+        for (int j4 = 0; j4 < 4; ++j4) {
+          const float4 bb = bp[j4];
+          f[j4 * 4 + 0] = __uint_as_float(v[j4 * 4 + 0]) + bb.x;
+          f[j4 * 4 + 1] = __uint_as_float(v[j4 * 4 + 1]) + bb.y;
+          f[j4 * 4 + 2] = __uint_as_float(v[j4 * 4 + 2]) + bb.z;
+          f[j4 * 4 + 3] = __uint_as_float(v[j4 * 4 + 3]) + bb.w;
+        }
 #pragma unroll
         for (int qi = 0; qi < 4; ++qi) {
           if (rp[qi]) {
 #pragma unroll
-            for (int j4 = 0; j4 < 4; ++j4) {
-              if (gch0 + c0 + j4 * 8 < p.Cout) {
+            for (int j2 = 0; j2 < 2; ++j2) {
+              if (gch0 + c0 + j2 * 8 < p.Cout) {
                 uint4 u;
-                if (qi < 2 && c0 == cbeg) u = pre[qi][j4];
-                else u = __ldg(reinterpret_cast<const uint4*>(rp[qi] + c0) + j4);
-                add_res8(f + j4 * 8, u);
+                if (qi < 2 && c0 == cbeg) u = pre[qi][j2];
+                else u = __ldg(reinterpret_cast<const uint4*>(rp[qi] + c0) + j2);
+                add_res8(f + j2 * 8, u);
               }
             }
           }
         }
         if (p.relu) {
 #pragma unroll
-          for (int j = 0; j < 32; ++j) f[j] = fmaxf(f[j], 0.f);
+          for (int j = 0; j < 16; ++j) f[j] = fmaxf(f[j], 0.f);
         }
-        bf16* op = p.out + ((size_t)((size_t)n * p.H + y) * p.W + x) * p.out_cs + p.out_co + gch0 + c0;
 #pragma unroll
-        for (int j4 = 0; j4 < 4; ++j4) {
-          if (gch0 + c0 + j4 * 8 < p.Cout) {
+        for (int j2 = 0; j2 < 2; ++j2) {
+          if (gch0 + c0 + j2 * 8 < p.Cout && !(p.skip & 8)) {
             uint4 u;
             __nv_bfloat162* h2 = reinterpret_cast<__nv_bfloat162*>(&u);
 #pragma unroll
-            for (int k2 = 0; k2 < 4; ++k2) {
-              h2[k2].x = __float2bfloat16_rn(f[j4 * 8 + 2 * k2]);
-              h2[k2].y = __float2bfloat16_rn(f[j4 * 8 + 2 * k2 + 1]);
-            }
-            reinterpret_cast<uint4*>(op)[j4] = u;
+            for (int k2 = 0; k2 < 4; ++k2) h2[k2] = __floats2bfloat162_rn(f[j2 * 8 + 2 * k2], f[j2 * 8 + 2 * k2 + 1]);
+            reinterpret_cast<uint4*>(orow + c0)[j2] = u;
           }
         }
       }
+      if (p.dbg && blockIdx.x == 0 && blockIdx.y == 0 && threadIdx.x == 32 * EPI_WARP0 && tl < 64) p.dbg[tl * 8 + 7] = clock64();
     }
   }
   // ---- teardown
@@ -364,7 +442,7 @@ extern "C" int rsg_conv_tc5_config(int Cin, int CoutPad, int ntaps, int halo, in
   int kc = 0;
   for (int c = 64; c >= 16; c -= 16)
     if (Cin % c == 0) { kc = c; break; }
-  if (!kc) return 0;
+  if (!kc || Cin / kc > MAX_CHUNKS) return 0;
   const int stage = (TH + 2 * halo) * (TW + 2 * halo) * kc * 2;
   const int cands[4] = {128, 96, 64, 32};
   for (int i = 0; i < 4; ++i) {
@@ -372,10 +450,8 @@ extern "C" int rsg_conv_tc5_config(int Cin, int CoutPad, int ntaps, int halo, in
     if (ns > CoutPad || CoutPad % ns != 0) continue;
     const long long wb = (long long)ntaps * Cin * ns * 2;
     if (wb + 2 * stage > 196 * 1024) continue;
-    int s = 4;
-    while (s > 2 && wb + (long long)s * stage > 196 * 1024) --s;
-    // small problems: do not hog shared memory, so that several CTAs share an SM
-    if (wb + (long long)s * stage <= 72 * 1024 && s > 3) s = 3;
+    int s = MAX_STAGES;                         // even: the two MMA warps own half of the ring each
+    while (s > 2 && wb + (long long)s * stage > 196 * 1024) s -= 2;
     *NS = ns; *KC = kc; *S = s;
     return 1;
   }
@@ -405,43 +481,78 @@ int conv_tc5_launch(const ConvP& p, cudaStream_t s, int* handled) {
   memset(&k, 0, sizeof(k));
   k.w = p.w_tc5; k.bias = p.bias; k.Cin = p.Cin; k.NS = NS; k.Cout = p.Cout;
   k.KC = KC; k.nchunks = p.Cin / KC; k.S = S;
-  k.EW = (NS % 64 == 0) ? 8 : 4;
+  k.EW = 8;
   k.ntaps = p.ntaps;
-  for (int t = 0; t < p.ntaps; ++t) { k.dy[t] = p.dy[t]; k.dx[t] = p.dx[t]; }
+  for (int t = 0; t < p.ntaps; ++t) {
+    k.dy[t] = p.dy[t]; k.dx[t] = p.dx[t];
+    k.tapoff[t] = (halo + p.dy[t]) * (TW + 2 * halo) + (halo + p.dx[t]);
+  }
   k.halo = halo; k.H = p.Hin; k.W = p.Win;
   k.in = p.in; k.in_cs = p.in_cs; k.in_co = p.in_co;
   k.tiles_x = (p.Win + TW - 1) / TW; k.tiles_y = (p.Hin + TH - 1) / TH;
   k.ntiles = (long long)k.tiles_x * k.tiles_y * p.N;
+  if (k.ntiles >= (1ll << 31)) return RSG_OK;
+  // maps much smaller than the 16x8 patch waste most MMA rows (8x6: 37%): generic kernel instead
+  if (!getenv("RSG_TC5_ANYSIZE") && (double)p.Hin * p.Win < 0.6 * 128.0 * k.tiles_x * k.tiles_y) return RSG_OK;
   k.out = p.out; k.out_cs = p.out_cs; k.out_co = p.out_co;
   k.nres = p.nres;
   for (int q = 0; q < p.nres; ++q) k.res[q] = p.res[q];
   k.relu = p.relu;
+  { const char* e = getenv("RSG_TC5_SKIP"); k.skip = e ? atoi(e) : 0; }
+  static long long* dbg_buf = nullptr;
+  if (getenv("RSG_TC5_TIMELINE")) {
+    if (!dbg_buf) { cudaMalloc(&dbg_buf, 64 * 8 * sizeof(long long)); }
+    cudaMemsetAsync(dbg_buf, 0, 64 * 8 * sizeof(long long), s);
+    k.dbg = dbg_buf;
+  }
   k.w_bytes = (uint32_t)p.ntaps * p.Cin * NS * 2;
   k.stage_bytes = (uint32_t)(TH + 2 * halo) * (TW + 2 * halo) * KC * 2;
-  uint32_t cols = 32;
-  while (cols < 2u * NS) cols <<= 1;
-  k.tmem_cols = cols;
   const size_t smem = (size_t)k.w_bytes + (size_t)S * k.stage_bytes;
+  // accumulator ring: MMA completion + barrier wake-up latency is ~1-2k cycles per tile hand-off, so
+  // two accumulators leave the tensor pipe idle (profiles/r1_notes.md); use up to 8
+  const uint32_t col_budget = 512u;                       // one CTA per SM owns all of TMEM
+  int nacc = (int)(col_budget / (uint32_t)NS);
+  if (nacc > MAX_ACC) nacc = MAX_ACC;
+  nacc &= ~1;                                             // even: tiles alternate between the two MMA warps
+  if (nacc < 2) nacc = 2;
+  { const char* e = getenv("RSG_TC5_NACC"); if (e) nacc = atoi(e); }
+  k.NACC = nacc;
+  uint32_t cols = 32;
+  while (cols < (uint32_t)(nacc * NS)) cols <<= 1;
+  k.tmem_cols = cols;
   const int nslices = p.CoutPad / NS;
-  const int threads = 128 + 32 * k.EW;
+  const int threads = NTHREADS;
 
   static bool attr_done = false;
   if (!attr_done) {
     RSG_CUDA(cudaFuncSetAttribute(conv_tc5_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+    RSG_CUDA(cudaFuncSetAttribute(conv_tc5_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
     attr_done = true;
   }
-  int occ = 1;
-  RSG_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, conv_tc5_kernel, threads, smem));
-  const int tmem_occ = 512 / (int)cols;
-  if (occ > tmem_occ) occ = tmem_occ;
-  if (occ > 4) occ = 4;
-  if (occ < 1) occ = 1;
+  const int occ = 1;
+  static const bool dbg = getenv("RSG_DEBUG") != nullptr;
+  if (dbg) fprintf(stderr, "[tc5] Cin=%d Cout=%d taps=%d NS=%d KC=%d S=%d NACC=%d smem=%zu tiles=%lld\n", p.Cin, p.CoutPad, p.ntaps, NS, KC, S, k.NACC, smem, k.ntiles);
   long long gx = ((long long)rsg_num_sms() * occ + nslices - 1) / nslices;
   if (gx > k.ntiles) gx = k.ntiles;
   if (gx < 1) gx = 1;
   dim3 grid((unsigned)gx, (unsigned)nslices);
   conv_tc5_kernel<<<grid, threads, smem, s>>>(k);
   RSG_LAUNCH_CHECK();
+  if (k.dbg) {
+    static int dumped = 0;
+    if (dumped++ == 3) {
+      long long h[64 * 8];
+      cudaStreamSynchronize(s);
+      cudaMemcpy(h, k.dbg, sizeof(h), cudaMemcpyDeviceToHost);
+      long long t0 = h[0];
+      fprintf(stderr, "[tc5 timeline] tile: prod_empty_ok prod_issued | mma_acc_ok mma_full_ok mma_committed | epi_accf_ok epi_ld_done epi_done (cycles since first stamp)\n");
+      for (int i = 0; i < 24; ++i) {
+        fprintf(stderr, "%2d:", i);
+        for (int j = 0; j < 8; ++j) fprintf(stderr, " %8lld", h[i * 8 + j] ? h[i * 8 + j] - t0 : -1);
+        fprintf(stderr, "\n");
+      }
+    }
+  }
   *handled = 1;
   return RSG_OK;
 }
