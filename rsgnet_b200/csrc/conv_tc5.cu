@@ -106,6 +106,10 @@ __device__ __forceinline__ uint32_t opaque(uint32_t v) {
   asm volatile("mov.u32 %0, %1;" : "=r"(r) : "r"(v));
   return r;
 }
+// magic = ceil(2^32 / d), or 0 for d == 1
+__device__ __forceinline__ uint32_t fastdiv(uint32_t n, uint32_t magic) {
+  return magic ? __umulhi(n, magic) : n;
+}
 __device__ __forceinline__ bool elect_one() {
   uint32_t pred;
   asm volatile("{\n\t.reg .pred p;\n\telect.sync _|p, 0xffffffff;\n\tselp.u32 %0, 1, 0, p;\n\t}" : "=r"(pred));
@@ -157,6 +161,7 @@ struct Tc5P {
   const bf16* in;       // NHWC, channel stride in_cs, first channel in_co
   int in_cs, in_co;
   int tiles_x, tiles_y; // per image
+  uint32_t tiles_per_img, magic_tpi, magic_tx;   // __umulhi(t, magic) == t / divisor (host-checked range)
   long long ntiles;
   bf16* out;
   int out_cs, out_co;
@@ -237,9 +242,9 @@ conv_tc5_kernel(const Tc5P p) {
     const int tiles_per_img = p.tiles_x * p.tiles_y;
     const uint32_t S2 = (uint32_t)p.S / NMMA;          // each MMA warp owns its own ring of S/2 stages
     for (int t = (int)first; t < (int)p.ntiles; t += (int)step, ++tl) {
-      const int n = t / tiles_per_img;
+      const int n = (int)fastdiv((uint32_t)t, p.magic_tpi);
       const int rem = t - n * tiles_per_img;
-      const int ty = rem / p.tiles_x, tx = rem - ty * p.tiles_x;
+      const int ty = (int)fastdiv((uint32_t)rem, p.magic_tx), tx = rem - ty * p.tiles_x;
       const int y0 = ty * TH - p.halo, x0 = tx * TW - p.halo;
       const bf16* tile0 = p.in + ((long long)n * H * W + (long long)y0 * W + x0) * cs + p.in_co + k8 * 8;
       uint32_t j = (tl / NMMA) * (uint32_t)p.nchunks;  // stage counter inside the owning warp's ring
@@ -332,60 +337,60 @@ conv_tc5_kernel(const Tc5P p) {
     }
   } else {
     // ===================== epilogue (warps 8 .. 15) =====================
-    // 8 warps: TMEM lane quarter q = warp & 3 (hardware rule), column half = (warp - 4) >> 2.
-    // The kernel is bound by the instruction latency of these warps (profiles/r1_notes.md), hence
-    // 16-column blocks (few live registers -> 2 CTAs per SM) and the bias staged in shared memory.
+    // 8 warps: TMEM lane quarter q = warp & 3 (hardware rule), column half = (warp - 8) >> 2.
+    // These warps are what bounds the kernel once loads and MMA issue are out of the way: every
+    // warp runs a serial ~6.6 cycles/instruction stream per tile (profiles/r1_notes.md), so the
+    // code below is written for instruction count: magic-number tile decomposition, 32-bit element
+    // offsets, 16-column blocks, packed bf16x2 ReLU, first residual term prefetched before the wait.
     const int e = warp - EPI_WARP0;
     const int q = warp & 3;
     const int row = q * 32 + lane;              // MMA row = pixel inside the patch
     const int hy = row >> 3, wx = row & 7;
     const int ncol = p.NS >> 1;                 // columns handled by this warp
     const int cbeg = (e >= 4) ? ncol : 0;
-    const int gch0 = slice * p.NS;              // first global output channel of this CTA
-    const int tiles_per_img = p.tiles_x * p.tiles_y;
+    const int gch0 = slice * p.NS + cbeg;       // first global output channel of this warp
+    const int nres = (p.skip & 4) ? 0 : p.nres;
+    const float* biasp = sBias + cbeg;
+    bf16* const outp = p.out + p.out_co + gch0;
+    const uint32_t tq = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)cbeg;
+    const uint32_t bar_accf = opaque(BAR(B_ACCF)), bar_acce = opaque(BAR(B_ACCE));
     uint32_t tl = 0;
-    for (int t = (int)first; t < (int)p.ntiles; t += (int)step, ++tl) {
-      const int b = tl % p.NACC;
-      const int n = t / tiles_per_img;
-      const int rem = t - n * tiles_per_img;
-      const int ty = rem / p.tiles_x, tx = rem - ty * p.tiles_x;
-      const int y = ty * TH + hy, x = tx * TW + wx;
+    for (uint32_t t = (uint32_t)first; t < (uint32_t)p.ntiles; t += (uint32_t)step, ++tl) {
+      const uint32_t b = tl % (uint32_t)p.NACC;
+      const uint32_t n = fastdiv(t, p.magic_tpi);                  // t / tiles_per_img
+      const uint32_t rem = t - n * p.tiles_per_img;
+      const uint32_t ty = fastdiv(rem, p.magic_tx);                // rem / tiles_x
+      const uint32_t tx = rem - ty * (uint32_t)p.tiles_x;
+      const int y = (int)ty * TH + hy, x = (int)tx * TW + wx;
       const bool ok = y < p.H && x < p.W;
-      const bf16* rp[4] = {nullptr, nullptr, nullptr, nullptr};
-#pragma unroll
-      for (int qi = 0; qi < 4; ++qi) {
-        if (qi < p.nres && ok && !(p.skip & 4)) {
-          const ResP& rr = p.res[qi];
-          rp[qi] = rr.p + ((size_t)((size_t)(rr.bs0 ? 0 : n) * rr.H + (y >> rr.shift)) * rr.W + (x >> rr.shift)) * rr.cs + rr.co + gch0;
-        }
+      const uint32_t ooff = ((n * (uint32_t)p.H + (uint32_t)y) * (uint32_t)p.W + (uint32_t)x) * (uint32_t)p.out_cs;
+      const bf16* r0p = nullptr;
+      uint4 pre0, pre1;
+      if (nres > 0 && ok && gch0 < p.Cout) {
+        const ResP& rr = p.res[0];
+        r0p = rr.p + rr.co + gch0 +
+              (((rr.bs0 ? 0u : n) * (uint32_t)rr.H + (uint32_t)(y >> rr.shift)) * (uint32_t)rr.W + (uint32_t)(x >> rr.shift)) * (uint32_t)rr.cs;
+        pre0 = __ldg(reinterpret_cast<const uint4*>(r0p));
+        pre1 = __ldg(reinterpret_cast<const uint4*>(r0p) + 1);
       }
-      // first two residual terms of the first column block: issued before waiting for the
-      // accumulator so that their latency overlaps the MMAs
-      uint4 pre[2][2];
-#pragma unroll
-      for (int qi = 0; qi < 2; ++qi)
-#pragma unroll
-        for (int j2 = 0; j2 < 2; ++j2)
-          if (rp[qi] && gch0 + cbeg + j2 * 8 < p.Cout) pre[qi][j2] = __ldg(reinterpret_cast<const uint4*>(rp[qi] + cbeg) + j2);
-      bf16* orow = ok ? p.out + ((size_t)((size_t)n * p.H + y) * p.W + x) * p.out_cs + p.out_co + gch0 : nullptr;
-      mbar_wait(BAR(B_ACCF + b), (tl / p.NACC) & 1);
+      mbar_wait(bar_accf + 8u * b, (tl / (uint32_t)p.NACC) & 1);
       if (p.dbg && blockIdx.x == 0 && blockIdx.y == 0 && threadIdx.x == 32 * EPI_WARP0 && tl < 64) p.dbg[tl * 8 + 5] = clock64();
       asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-      const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)b * p.NS;
-      for (int c0 = cbeg; c0 < cbeg + ncol; c0 += 16) {
+      const uint32_t taddr = tq + b * (uint32_t)p.NS;
+      for (int c0 = 0; c0 < ncol; c0 += 16) {
         uint32_t v[16];
         tmem_ld16(taddr + c0, v);
         asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-        if (c0 + 16 >= cbeg + ncol) {
+        if (c0 + 16 >= ncol) {
           // all of this warp's TMEM reads for the tile are done: release the accumulator
           asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
           __syncwarp();
-          if (lane == 0) mbar_arrive(BAR(B_ACCE + b));
+          if (lane == 0) mbar_arrive(bar_acce + 8u * b);
           if (p.dbg && blockIdx.x == 0 && blockIdx.y == 0 && threadIdx.x == 32 * EPI_WARP0 && tl < 64) p.dbg[tl * 8 + 6] = clock64();
         }
-        if (!ok) continue;
+        if (!ok || gch0 + c0 >= p.Cout) continue;        // padded output channels are never stored
         float f[16];
-        const float4* bp = reinterpret_cast<const float4*>(sBias + c0);
+        const float4* bp = reinterpret_cast<const float4*>(biasp + c0);
 #pragma unroll
         for (int j4 = 0; j4 < 4; ++j4) {
           const float4 bb = bp[j4];
@@ -394,33 +399,37 @@ conv_tc5_kernel(const Tc5P p) {
           f[j4 * 4 + 2] = __uint_as_float(v[j4 * 4 + 2]) + bb.z;
           f[j4 * 4 + 3] = __uint_as_float(v[j4 * 4 + 3]) + bb.w;
         }
-#pragma unroll
-        for (int qi = 0; qi < 4; ++qi) {
-          if (rp[qi]) {
-#pragma unroll
-            for (int j2 = 0; j2 < 2; ++j2) {
-              if (gch0 + c0 + j2 * 8 < p.Cout) {
-                uint4 u;
-                if (qi < 2 && c0 == cbeg) u = pre[qi][j2];
-                else u = __ldg(reinterpret_cast<const uint4*>(rp[qi] + c0) + j2);
-                add_res8(f + j2 * 8, u);
-              }
-            }
+        if (nres > 0) {
+          if (c0 == 0) { add_res8(f, pre0); add_res8(f + 8, pre1); }
+          else {
+            add_res8(f, __ldg(reinterpret_cast<const uint4*>(r0p + c0)));
+            add_res8(f + 8, __ldg(reinterpret_cast<const uint4*>(r0p + c0) + 1));
           }
+          for (int qi = 1; qi < nres; ++qi) {
+            const ResP& rr = p.res[qi];
+            const bf16* rp = rr.p + rr.co + gch0 + c0 +
+                (((rr.bs0 ? 0u : n) * (uint32_t)rr.H + (uint32_t)(y >> rr.shift)) * (uint32_t)rr.W + (uint32_t)(x >> rr.shift)) * (uint32_t)rr.cs;
+            add_res8(f, __ldg(reinterpret_cast<const uint4*>(rp)));
+            add_res8(f + 8, __ldg(reinterpret_cast<const uint4*>(rp) + 1));
+          }
+        }
+        uint4 o0, o1;
+        __nv_bfloat162* h0 = reinterpret_cast<__nv_bfloat162*>(&o0);
+        __nv_bfloat162* h1 = reinterpret_cast<__nv_bfloat162*>(&o1);
+#pragma unroll
+        for (int k2 = 0; k2 < 4; ++k2) {
+          h0[k2] = __floats2bfloat162_rn(f[2 * k2], f[2 * k2 + 1]);
+          h1[k2] = __floats2bfloat162_rn(f[8 + 2 * k2], f[8 + 2 * k2 + 1]);
         }
         if (p.relu) {
+          const __nv_bfloat162 z = __floats2bfloat162_rn(0.f, 0.f);
 #pragma unroll
-          for (int j = 0; j < 16; ++j) f[j] = fmaxf(f[j], 0.f);
+          for (int k2 = 0; k2 < 4; ++k2) { h0[k2] = __hmax2(h0[k2], z); h1[k2] = __hmax2(h1[k2], z); }
         }
-#pragma unroll
-        for (int j2 = 0; j2 < 2; ++j2) {
-          if (gch0 + c0 + j2 * 8 < p.Cout && !(p.skip & 8)) {
-            uint4 u;
-            __nv_bfloat162* h2 = reinterpret_cast<__nv_bfloat162*>(&u);
-#pragma unroll
-            for (int k2 = 0; k2 < 4; ++k2) h2[k2] = __floats2bfloat162_rn(f[j2 * 8 + 2 * k2], f[j2 * 8 + 2 * k2 + 1]);
-            reinterpret_cast<uint4*>(orow + c0)[j2] = u;
-          }
+        if (!(p.skip & 8)) {
+          uint4* op = reinterpret_cast<uint4*>(outp + ooff + c0);
+          op[0] = o0;
+          op[1] = o1;
         }
       }
       if (p.dbg && blockIdx.x == 0 && blockIdx.y == 0 && threadIdx.x == 32 * EPI_WARP0 && tl < 64) p.dbg[tl * 8 + 7] = clock64();
@@ -465,7 +474,7 @@ int conv_tc5_launch(const ConvP& p, cudaStream_t s, int* handled) {
   if (!p.w_tc5 || !p.out || p.out_f32) return RSG_OK;
   if (p.stride != 1 || p.omul != 1 || p.ooy != 0 || p.oox != 0) return RSG_OK;
   if (p.Hout != p.Hin || p.Wout != p.Win || p.oH != p.Hin || p.oW != p.Win) return RSG_OK;
-  if (p.Cout % 8 != 0 || p.in_cs % 8 != 0 || p.in_co % 8 != 0 || p.out_cs % 8 != 0 || p.out_co % 8 != 0) return RSG_OK;
+  if (p.Cout % 16 != 0 || p.in_cs % 8 != 0 || p.in_co % 8 != 0 || p.out_cs % 8 != 0 || p.out_co % 8 != 0) return RSG_OK;
   int halo = 0;
   for (int t = 0; t < p.ntaps && t < 16; ++t) {
     if (p.dy[t] < -1 || p.dy[t] > 1 || p.dx[t] < -1 || p.dx[t] > 1) return RSG_OK;
@@ -492,6 +501,11 @@ int conv_tc5_launch(const ConvP& p, cudaStream_t s, int* handled) {
   k.tiles_x = (p.Win + TW - 1) / TW; k.tiles_y = (p.Hin + TH - 1) / TH;
   k.ntiles = (long long)k.tiles_x * k.tiles_y * p.N;
   if (k.ntiles >= (1ll << 31)) return RSG_OK;
+  k.tiles_per_img = (uint32_t)(k.tiles_x * k.tiles_y);
+  // magic = ceil(2^32 / d): __umulhi(t, magic) == t / d exactly while t * d < 2^32 (d == 1 needs no division)
+  if ((unsigned long long)k.ntiles * k.tiles_per_img >= (1ull << 32)) return RSG_OK;
+  k.magic_tpi = k.tiles_per_img > 1 ? (uint32_t)(((1ull << 32) + k.tiles_per_img - 1) / k.tiles_per_img) : 0u;
+  k.magic_tx = k.tiles_x > 1 ? (uint32_t)(((1ull << 32) + k.tiles_x - 1) / k.tiles_x) : 0u;
   // maps much smaller than the 16x8 patch waste most MMA rows (8x6: 37%): generic kernel instead
   if (!getenv("RSG_TC5_ANYSIZE") && (double)p.Hin * p.Win < 0.6 * 128.0 * k.tiles_x * k.tiles_y) return RSG_OK;
   k.out = p.out; k.out_cs = p.out_cs; k.out_co = p.out_co;
