@@ -69,7 +69,7 @@ class ClockSampler:
                     self.rows.append([c.strip() for c in out.split(',')])
             except Exception:
                 pass
-            time.sleep(0.1)
+            time.sleep(0.02)
 
     def start(self):
         self.th = threading.Thread(target=self._loop, daemon=True)
@@ -139,6 +139,10 @@ def run_reference(args):
         'gpu_launches': 0}))
 
 
+# dram__bytes_read.sum + dram__bytes_write.sum per launch of the dominant kernel, from the committed
+# `ncu --set full` capture of this same command (profiles/r1_conv_tc5_ncu_details.txt, 512 forwards)
+NCU_TRAFFIC = {('conv_tcgen05', 'conv 32->32 taps9 s1 64x48'): 100.73e6 + 52.91e6}
+
 FAMILY = {0: 'stem', 1: 'conv_mma', 2: 'conv_tcgen05', 3: 'fuse', 4: 'maxpool', 5: 'trp_attention',
           6: 'relation_scores', 7: 'groupnorm', 8: 'bilinear'}
 
@@ -146,7 +150,7 @@ FAMILY = {0: 'stem', 1: 'conv_mma', 2: 'conv_tcgen05', 3: 'fuse', 4: 'maxpool', 
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument('--gpus', type=int, default=1)
-    ap.add_argument('--steps', type=int, default=10)
+    ap.add_argument('--steps', type=int, default=30)
     ap.add_argument('--warmup', type=int, default=3)
     ap.add_argument('--impl', default='ours')
     ap.add_argument('--batch', type=int, default=256, help='crops per GPU per step')
@@ -241,27 +245,32 @@ def main():
     nb = min(eng.chunk, pipe.n_fwd)
     with torch.cuda.stream(stream):
         eng.profile(pipe.x, pipe.heat, nb, B)                     # warm
-        ms_op, kind, flops, names = eng.profile(pipe.x, pipe.heat, nb, B)
-    fam = {}
-    for m, k, f in zip(ms_op, kind, flops):
+        ms_op, kind, flops, names, shapes = eng.profile(pipe.x, pipe.heat, nb, B)
+    fam, groups = {}, {}
+    for m, k, f, sh in zip(ms_op, kind, flops, shapes):
         if m < 0:
             continue
         d = fam.setdefault(FAMILY[int(k)], [0.0, 0.0, 0])
         d[0] += float(m); d[1] += float(f); d[2] += 1
+        g = groups.setdefault((FAMILY[int(k)], sh), [0.0, 0.0, 0])
+        g[0] += float(m); g[1] += float(f); g[2] += 1
     total_ms = sum(v[0] for v in fam.values())
-    dom = max(fam, key=lambda k: fam[k][0])
-    dom_ms, dom_fl, dom_n = fam[dom]
-    achieved = dom_fl / (dom_ms * 1e-3) / 1e12 if dom_ms > 0 else 0.0
-    roofline = {'bound': 'tensor', 'kernel': dom, 'achieved': achieved, 'peak': pk['tf_sus'],
-                'unit': 'TFLOP/s', 'frac': achieved / pk['tf_sus'], 'traffic': None,
+    # dominant kernel = the (kernel, shape) group with the largest share of the step
+    (dom_fam, dom_shape), (dom_ms, dom_fl, dom_n) = max(groups.items(), key=lambda kv: kv[1][0])
+    per_launch_ms = dom_ms / dom_n
+    achieved = dom_fl / dom_n / (per_launch_ms * 1e-3) / 1e12 if dom_ms > 0 else 0.0
+    traffic = NCU_TRAFFIC.get((dom_fam, dom_shape.replace(' +res', '')))
+    roofline = {'bound': 'tensor', 'kernel': f'{dom_fam}: {dom_shape} x {nb} forwards', 'achieved': achieved,
+                'peak': pk['tf_sus'], 'unit': 'TFLOP/s', 'frac': achieved / pk['tf_sus'], 'traffic': traffic,
                 'peak_source': pk['src'] + ' bf16_tflops_sustained',
-                'launches_in_chunk': dom_n, 'share_of_step': dom_ms / total_ms if total_ms else None,
+                'algorithmic_flops_per_launch': dom_fl / dom_n, 'us_per_launch': per_launch_ms * 1e3,
+                'launches_per_step': dom_n, 'share_of_step': dom_ms / total_ms if total_ms else None,
                 'families': {k: {'ms': round(v[0], 4), 'tflops': (v[1] / (v[0] * 1e-3) / 1e12 if v[0] > 0 else 0.0),
-                                 'launches': v[2]} for k, v in fam.items()}}
+                                 'launches': v[2], 'share': round(v[0] / total_ms, 4)} for k, v in fam.items()}}
     if args.dump_profile:
         with open(args.dump_profile, 'w') as f:
-            for m, k, fl, nm in zip(ms_op, kind, flops, names):
-                f.write(f'{nm}\t{FAMILY[int(k)]}\t{m:.5f}\t{fl:.0f}\n')
+            for m, k, fl, nm, sh in zip(ms_op, kind, flops, names, shapes):
+                f.write(f'{nm}\t{FAMILY[int(k)]}\t{m:.5f}\t{fl:.0f}\t{sh}\n')
 
     crops_per_step = B * world
     value = crops_per_step * args.steps / (ms_dev * 1e-3)

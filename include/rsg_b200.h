@@ -64,6 +64,11 @@ int rsg_oks_nms(void* stream, const float* kpts, const double* scores, const dou
                 const int32_t* img_offsets, int n_imgs, int max_per_img, const double* sigmas,
                 int K, double thresh, int32_t* keep, int32_t* keep_counts);
 
+/* lib/nms/nms.py:75-94 oks_iou: OKS of one detection g (f32 [K,3]) against M detections d (f32 [M,K,3]);
+ * a_g, a_d f64 areas; out f64 [M]. */
+int rsg_oks_iou(void* stream, const float* g, const float* d, double a_g, const double* a_d,
+                const double* sigmas, int K, int M, double* out);
+
 /* evaluate()-side rescoring, lib/dataset/crowdpose.py:1294-1306 / coco.py:1249-1261:
  * score[i] = box_score[i] * mean(maxvals[i,k] for maxvals[i,k] > in_vis_thre). */
 int rsg_rescore(void* stream, const float* maxvals, const double* box_scores, int n, int K,

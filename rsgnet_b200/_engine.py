@@ -659,8 +659,15 @@ class Engine:
             _lib.check(L.rsg_plan_profile(self.plan, _lib.stream_ptr(self.device), ext, N_EXT, nb,
                                           n_crops, 0, ms.ctypes.data, kind.ctypes.data,
                                           flops.ctypes.data))
-        names = [p.get('name', k) if isinstance(p, dict) else k for k, p, _ in self.pb.ops]
-        return ms, kind, flops, names
+        names, shapes = [], []
+        for k, p, _ in self.pb.ops:
+            names.append(p.get('name', k) if isinstance(p, dict) else k)
+            if k == 'conv':
+                shapes.append(f"conv {p['cin']}->{p['cout']} taps{len(p['taps'])} s{p['stride']} "
+                              f"{p['Hout']}x{p['Wout']}{' +res' * len(p['res'])}")
+            else:
+                shapes.append(k)
+        return ms, kind, flops, names, shapes
 
     def last_launches(self):
         return _lib.lib().rsg_plan_last_launches(self.plan)

@@ -96,6 +96,19 @@ oks_nms_kernel(const float* __restrict__ kpts, const double* __restrict__ scores
   if (tid == 0) keep_counts[img] = nkeep;
 }
 
+__global__ void oks_iou_kernel(const float* __restrict__ g, const float* __restrict__ d, double a_g,
+                               const double* __restrict__ a_d, const double* __restrict__ sigmas, int K,
+                               int M, double* __restrict__ out) {
+  __shared__ double vars[RSG_NMS_MAXK];
+  if (threadIdx.x < K) {
+    double s2 = __dmul_rn(sigmas[threadIdx.x], 2.0);
+    vars[threadIdx.x] = __dmul_rn(s2, s2);
+  }
+  __syncthreads();
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < M) out[i] = oks_pair(g, d + (size_t)i * K * 3, a_g, a_d[i], vars, K);
+}
+
 __global__ void rescore_kernel(const float* __restrict__ maxvals,
                                const double* __restrict__ box, int n, int K, double thre,
                                double* __restrict__ out) {
@@ -132,6 +145,16 @@ extern "C" int rsg_oks_nms(void* stream, const float* kpts, const double* scores
     RSG_CUDA(cudaFuncSetAttribute(oks_nms_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   oks_nms_kernel<<<n_imgs, 128, smem, (cudaStream_t)stream>>>(kpts, scores, areas, img_offsets,
                                                              sigmas, K, thresh, keep, keep_counts);
+  RSG_LAUNCH_CHECK();
+  return RSG_OK;
+}
+
+extern "C" int rsg_oks_iou(void* stream, const float* g, const float* d, double a_g, const double* a_d,
+                           const double* sigmas, int K, int M, double* out) {
+  RSG_REQUIRE(K > 0 && K <= RSG_NMS_MAXK && M >= 0, "rsg_oks_iou: bad K=%d or M=%d", K, M);
+  if (M == 0) return RSG_OK;
+  RSG_REQUIRE(g && d && a_d && sigmas && out, "rsg_oks_iou: null pointer");
+  oks_iou_kernel<<<ceil_div(M, 128), 128, 0, (cudaStream_t)stream>>>(g, d, a_g, a_d, sigmas, K, M, out);
   RSG_LAUNCH_CHECK();
   return RSG_OK;
 }

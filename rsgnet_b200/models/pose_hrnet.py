@@ -22,7 +22,7 @@ class EngineOwner(nn.Module):
     The cache dict is shared with DataParallel replicas (``replicate`` shallow-copies __dict__), so
     it is cleared in place."""
 
-    chunk = 32        # crops processed per pass of the plan (activations stay L2-sized)
+    chunk = 512       # forwards per pass of the plan (one pass per 256-crop flip-test step)
 
     def _drop_engines(self):
         cache = self.__dict__.get('_rsg_engines')

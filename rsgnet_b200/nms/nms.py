@@ -54,6 +54,25 @@ def oks_nms_batched(kpts, scores, areas, img_offsets, thresh, sigmas=None, devic
     return keep[:n].cpu().numpy(), counts.cpu().numpy()
 
 
+def oks_iou(g, d, a_g, a_d, sigmas=None, in_vis_thre=None):
+    """nms.py:75-94: OKS of detection g (f32 [3K]) with each row of d (f32 [M,3K]); returns f64 [M]."""
+    if in_vis_thre is not None:
+        raise NotImplementedError('oks_iou(in_vis_thre=...) is not supported (no reference caller uses it)')
+    _lib.require_cuda()
+    if not isinstance(sigmas, np.ndarray):
+        sigmas = COCO_SIGMAS
+    dev = torch.device('cuda')
+    gt = torch.from_numpy(np.ascontiguousarray(g, np.float32).reshape(-1)).to(dev)
+    dt = torch.from_numpy(np.ascontiguousarray(d, np.float32).reshape(len(d), -1)).to(dev)
+    at = torch.from_numpy(np.ascontiguousarray(a_d, np.float64).reshape(-1)).to(dev)
+    sg = torch.from_numpy(np.ascontiguousarray(sigmas, np.float64)).to(dev)
+    K, M = gt.numel() // 3, dt.shape[0]
+    assert len(sigmas) == K
+    out = torch.zeros(M, dtype=torch.float64, device=dev)
+    _lib.check(_lib.lib().rsg_oks_iou(_lib.stream_ptr(dev), _p(gt), _p(dt), float(a_g), _p(at), _p(sg), K, M, _p(out)))
+    return out.cpu().numpy()
+
+
 def oks_nms(kpts_db, thresh, sigmas=None, in_vis_thre=None):
     """nms.py:97-124.  `in_vis_thre` is never passed by any caller of the reference
     (crowdpose.py:1315, coco.py:1269); a non-None value is rejected rather than guessed at."""

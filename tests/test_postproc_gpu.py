@@ -10,7 +10,7 @@ import torch
 from oracle import decode_oracle, nms_oracle
 from rsgnet_b200 import presets, synth
 from rsgnet_b200.core.inference import decode_device, get_final_preds, get_max_preds
-from rsgnet_b200.nms.nms import oks_nms, oks_nms_batched, rescore
+from rsgnet_b200.nms.nms import oks_iou, oks_nms, oks_nms_batched, rescore
 from rsgnet_b200.utils.transforms import flip_back, flip_perm
 
 pytestmark = pytest.mark.gpu
@@ -150,3 +150,11 @@ def test_rescore_vs_oracle():
     got = rescore(mv, box, 0.2)
     ref = np.array([nms_oracle.rescore(box[i], mv[i], 0.2) for i in range(500)], np.float64)
     assert np.array_equal(got, ref)
+
+
+def test_oks_iou_vs_oracle():
+    kpts, scores, areas, off = synth.detections(1, 40, 17, seed=8)
+    flat = kpts.reshape(40, -1)
+    got = oks_iou(flat[0], flat[1:], areas[0], areas[1:])
+    ref = nms_oracle.oks_iou(flat[0], flat[1:], areas[0], areas[1:])
+    assert np.abs(got - ref).max() <= 4e-16          # fp64 exp may differ from NumPy's by an ulp
