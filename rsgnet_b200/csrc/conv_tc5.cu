@@ -12,16 +12,17 @@
 // [slice][tap][Cin/8][NS][8]) are TMA-bulk-copied once per CTA and stay resident while the CTA
 // walks over its tiles; blockIdx.y selects a slice of NS output channels.
 //
-// The halo patch is gathered with 16-byte cp.async (LDGSTS) by three producer warps, completion
-// tracked by the stage's mbarrier (cp.async.mbarrier.arrive).  A first version used one 5-D TMA box
-// per stage; with the 16-byte inner rows this layout needs, the TMA engine sustained only about one
-// row per 5 cycles and was the bottleneck of every shape (profiles/r1_notes.md), LDGSTS moves the
-// same bytes ~20x faster.
+// The halo patch is ONE 5-D TMA tensor load per stage (box 8 ch x 10 px x 18 rows x KC/8 planes x
+// 1 crop over the NHWC activation viewed as (8, W, H, C/8, N)); a cp.async (LDGSTS) gather with the
+// same layout was measured at 1.2-2 TB/s per chip against >5 TB/s for the TMA box once the other
+// bottlenecks were gone (profiles/r1_notes.md).
 //
-// Warp roles (128 + 32*EW threads): warp 0 = TMEM allocator + weight bulk copy + MMA issuer,
-// warps 1..3 = halo producers, warps 4.. = epilogue (TMEM -> registers -> +bias +residual terms ->
-// ReLU -> bf16 NHWC stores).  Pipelines: S-deep ring of halo stages (full/empty mbarriers, one
-// stage = one K-chunk of one tile) and 2 TMEM accumulators (full/empty mbarriers).
+// Warp roles (608 threads, one persistent CTA per SM): warps 0-1 = MMA issuers alternating tiles
+// (warp 0 also allocates TMEM and bulk-copies the weights), warp 2 = TMA producer (one elected
+// thread), warps 3..18 = two epilogue groups of 8 warps alternating tiles (TMEM -> registers -> +bias
+// +residual terms -> ReLU -> bf16 NHWC stores).  Pipelines: S-deep ring of halo stages (full/empty
+// mbarriers, one stage = one K-chunk of one tile, half of the ring per MMA warp) and up to 8 TMEM
+// accumulators (full/empty mbarriers).
 //
 // Reference ops subsumed: Conv2d(3x3|1x1, s1) + BatchNorm2d(eval) [+ residual adds] [+ ReLU]
 // (pose_rsgnet.py:38-54 BasicBlock, :75-95 Bottleneck, :261-270 fuse sum, heads :965-1003).
@@ -33,10 +34,10 @@
 namespace {
 
 constexpr int TH = 16, TW = 8;                 // pixel patch = 128 MMA rows
-constexpr int NTHREADS = 512;                  // one fat persistent CTA per SM
+constexpr int NTHREADS = 608;                  // one fat persistent CTA per SM (19 warps)
 constexpr int NMMA = 2;                        // MMA-issuing warps (0, 1): alternate tiles
-constexpr int NPROD = 192;                     // producer threads (warps 2..7)
-constexpr int EPI_WARP0 = 8;                   // epilogue warps 8..15
+constexpr int EPI_WARP0 = 3;                   // warp 2 = TMA producer; epilogue warps 3..18: two groups of 8
+constexpr int NEPI = 2;
 constexpr uint32_t SPIN_LIMIT = 1u << 21;      // bounded waits: a protocol bug traps, never hangs
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) {
@@ -67,12 +68,13 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
          (int)blockIdx.x, (int)blockIdx.y, (int)threadIdx.x);
   __trap();
 }
-__device__ __forceinline__ void cp_async16(uint32_t dst, const void* src, bool pred) {
-  const int sz = pred ? 16 : 0;                 // src-size 0: the 16 bytes are zero-filled
-  asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dst), "l"(src), "r"(sz) : "memory");
-}
-__device__ __forceinline__ void cp_async_arrive(uint32_t bar) {
-  asm volatile("cp.async.mbarrier.arrive.noinc.shared::cta.b64 [%0];" ::"r"(bar) : "memory");
+__device__ __forceinline__ void tma_load_5d(uint32_t dst, const CUtensorMap* map, uint32_t bar,
+                                            int c0, int c1, int c2, int c3, int c4) {
+  asm volatile(
+      "cp.async.bulk.tensor.5d.shared::cluster.global.tile.mbarrier::complete_tx::bytes "
+      "[%0], [%1, {%3, %4, %5, %6, %7}], [%2];"
+      ::"r"(dst), "l"(map), "r"(bar), "r"(c0), "r"(c1), "r"(c2), "r"(c3), "r"(c4)
+      : "memory");
 }
 __device__ __forceinline__ void bulk_load(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar) {
   asm volatile(
@@ -187,7 +189,7 @@ __device__ __forceinline__ void add_res8(float* f, const uint4& u) {
 }
 
 __global__ void __launch_bounds__(NTHREADS, 1)
-conv_tc5_kernel(const Tc5P p) {
+conv_tc5_kernel(const __grid_constant__ CUtensorMap in_map, const Tc5P p) {
   extern __shared__ __align__(128) unsigned char smem[];
   __shared__ __align__(8) uint64_t bars[1 + 2 * MAX_STAGES + 2 * MAX_ACC];
   __shared__ uint32_t tmem_base_slot;
@@ -207,7 +209,7 @@ conv_tc5_kernel(const Tc5P p) {
 
   if (threadIdx.x == 0) {
     mbar_init(BAR(0), 1);
-    for (int i = 0; i < p.S; ++i) { mbar_init(BAR(B_FULL + i), NPROD); mbar_init(BAR(B_EMPTY + i), 1); }
+    for (int i = 0; i < p.S; ++i) { mbar_init(BAR(B_FULL + i), 1); mbar_init(BAR(B_EMPTY + i), 1); }
     for (int i = 0; i < p.NACC; ++i) { mbar_init(BAR(B_ACCF + i), 1); mbar_init(BAR(B_ACCE + i), 8); }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
@@ -224,48 +226,33 @@ conv_tc5_kernel(const Tc5P p) {
   const long long first = blockIdx.x, step = gridDim.x;
 
   if (warp >= NMMA && warp < EPI_WARP0) {
-    // ===================== halo producers (cp.async gather) =====================
+    // ===================== halo producer (TMA) =====================
     const int ptid = threadIdx.x - 32 * NMMA;
-    const int kc8 = p.KC >> 3;
-    const int hpix = HW_ * HH_;
-    const int nitems = hpix * kc8;
-    // item i -> (pixel = i / kc8, 8-channel plane = i % kc8): consecutive lanes read consecutive
-    // 16-byte pieces of one pixel's channels.  The decomposition is the same for every tile.
-    // NPROD is a multiple of KC/8, so a thread always copies the same 8-channel plane k8 and walks
-    // over pixels pix0, pix0 + PS, ...: no per-thread tables, a dozen instructions per 16 bytes.
-    const int k8 = ptid % kc8, pix0 = ptid / kc8, PS = NPROD / kc8;
-    const int nj = (hpix - pix0 + PS - 1) / PS;              // items of this thread per stage
-    const uint32_t sH_u32 = opaque(smem_u32(sH)) + (uint32_t)(k8 * hpix) * 16u;
-    const uint32_t bar_full = opaque(BAR(B_FULL)), bar_empty = opaque(BAR(B_EMPTY));
-    const int W = p.W, H = p.H, cs = p.in_cs;
-    uint32_t it = 0, tl = 0;
-    const int tiles_per_img = p.tiles_x * p.tiles_y;
-    const uint32_t S2 = (uint32_t)p.S / NMMA;          // each MMA warp owns its own ring of S/2 stages
-    for (int t = (int)first; t < (int)p.ntiles; t += (int)step, ++tl) {
-      const int n = (int)fastdiv((uint32_t)t, p.magic_tpi);
-      const int rem = t - n * tiles_per_img;
-      const int ty = (int)fastdiv((uint32_t)rem, p.magic_tx), tx = rem - ty * p.tiles_x;
-      const int y0 = ty * TH - p.halo, x0 = tx * TW - p.halo;
-      const bf16* tile0 = p.in + ((long long)n * H * W + (long long)y0 * W + x0) * cs + p.in_co + k8 * 8;
-      uint32_t j = (tl / NMMA) * (uint32_t)p.nchunks;  // stage counter inside the owning warp's ring
-      for (int c = 0; c < p.nchunks; ++c, ++it, ++j) {
-        const int s = (int)((j % S2) * NMMA + (tl % NMMA));
-        mbar_wait(bar_empty + 8u * s, ((j / S2) & 1) ^ 1);
-        if (p.dbg && blockIdx.x == 0 && blockIdx.y == 0 && ptid == 0 && it < 64) p.dbg[it * 8 + 0] = clock64();
-        const uint32_t dst = sH_u32 + (uint32_t)s * p.stage_bytes;
-        const bf16* src_c = tile0 + c * p.KC;
-        if (!(p.skip & 1)) {
-#pragma unroll 4
-          for (int j = 0; j < nj; ++j) {
-            const int pix = pix0 + j * PS;
-            const int py = p.halo ? (int)(((uint32_t)pix * 52429u) >> 19) : (pix >> 3);   // pix / HW_
-            const int px = pix - py * HW_;
-            const bool ok = (unsigned)(y0 + py) < (unsigned)H && (unsigned)(x0 + px) < (unsigned)W;
-            cp_async16(dst + (uint32_t)pix * 16u, ok ? src_c + (py * W + px) * cs : p.in, ok);
+    // One elected thread issues one 5-D TMA box per stage: (8 ch, 10 px, 18 rows, KC/8 planes, 1 crop)
+    // lands in shared memory as [KC/8][18][10][8ch]; out-of-bounds coordinates are zero-filled, which
+    // is the convolution's zero padding.
+    if (ptid == 0) {
+      asm volatile("prefetch.tensormap [%0];" ::"l"(&in_map) : "memory");
+      const uint32_t S2 = (uint32_t)p.S / NMMA;          // each MMA warp owns its own ring of S/2 stages
+      uint32_t tl = 0, it = 0;
+      for (int t = (int)first; t < (int)p.ntiles; t += (int)step, ++tl) {
+        const int n = (int)fastdiv((uint32_t)t, p.magic_tpi);
+        const int rem = t - n * (p.tiles_x * p.tiles_y);
+        const int ty = (int)fastdiv((uint32_t)rem, p.magic_tx), tx = rem - ty * p.tiles_x;
+        uint32_t j = (tl / NMMA) * (uint32_t)p.nchunks;  // stage counter inside the owning warp's ring
+        for (int c = 0; c < p.nchunks; ++c, ++j, ++it) {
+          const int s = (int)((j % S2) * NMMA + (tl % NMMA));
+          mbar_wait(BAR(B_EMPTY + s), ((j / S2) & 1) ^ 1);
+          if (p.dbg && blockIdx.x == 0 && blockIdx.y == 0 && it < 64) p.dbg[it * 8 + 0] = clock64();
+          if (!(p.skip & 1)) {
+            mbar_arrive_expect_tx(BAR(B_FULL + s), p.stage_bytes);
+            tma_load_5d(smem_u32(sH + (size_t)s * p.stage_bytes), &in_map, BAR(B_FULL + s), 0,
+                        tx * TW - p.halo, ty * TH - p.halo, c * (p.KC >> 3), n);
+          } else {
+            mbar_arrive(BAR(B_FULL + s));
           }
+          if (p.dbg && blockIdx.x == 0 && blockIdx.y == 0 && it < 64) p.dbg[it * 8 + 1] = clock64();
         }
-        cp_async_arrive(bar_full + 8u * s);
-        if (p.dbg && blockIdx.x == 0 && blockIdx.y == 0 && ptid == 0 && it < 64) p.dbg[it * 8 + 1] = clock64();
       }
     }
   } else if (warp < NMMA) {
@@ -309,7 +296,6 @@ conv_tc5_kernel(const Tc5P p) {
         const int s = (int)((j % S2) * NMMA + (uint32_t)warp);
         mbar_wait(BAR(B_FULL + s), (j / S2) & 1);          // halo chunk landed
         if (p.dbg && blockIdx.x == 0 && blockIdx.y == 0 && lane == 0 && tl < 64) p.dbg[tl * 8 + 3] = clock64();
-        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // cp.async writes -> UMMA reads
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
         const uint32_t a_stage = (a0 + (uint32_t)s * p.stage_bytes) >> 4;
         const uint32_t w_chunk = (w0 >> 4) + (uint32_t)c * b_chunkstep;
@@ -336,26 +322,29 @@ conv_tc5_kernel(const Tc5P p) {
       if (p.dbg && blockIdx.x == 0 && blockIdx.y == 0 && lane == 0 && tl < 64) p.dbg[tl * 8 + 4] = clock64();
     }
   } else {
-    // ===================== epilogue (warps 8 .. 15) =====================
-    // 8 warps: TMEM lane quarter q = warp & 3 (hardware rule), column half = (warp - 8) >> 2.
+    // ===================== epilogue (warps 3 .. 18) =====================
+    // Two groups of 8 warps that alternate tiles (like the MMA warps).  Inside a group: TMEM lane
+    // quarter q = warp & 3 (hardware rule) and a column half.
     // These warps are what bounds the kernel once loads and MMA issue are out of the way: every
     // warp runs a serial ~6.6 cycles/instruction stream per tile (profiles/r1_notes.md), so the
     // code below is written for instruction count: magic-number tile decomposition, 32-bit element
     // offsets, 16-column blocks, packed bf16x2 ReLU, first residual term prefetched before the wait.
-    const int e = warp - EPI_WARP0;
+    const int eidx = (warp - EPI_WARP0) >> 2;   // 0..3 for each lane quarter
+    const int egroup = eidx & 1;
     const int q = warp & 3;
     const int row = q * 32 + lane;              // MMA row = pixel inside the patch
     const int hy = row >> 3, wx = row & 7;
     const int ncol = p.NS >> 1;                 // columns handled by this warp
-    const int cbeg = (e >= 4) ? ncol : 0;
+    const int cbeg = (eidx >> 1) ? ncol : 0;
     const int gch0 = slice * p.NS + cbeg;       // first global output channel of this warp
     const int nres = (p.skip & 4) ? 0 : p.nres;
     const float* biasp = sBias + cbeg;
     bf16* const outp = p.out + p.out_co + gch0;
     const uint32_t tq = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)cbeg;
     const uint32_t bar_accf = opaque(BAR(B_ACCF)), bar_acce = opaque(BAR(B_ACCE));
-    uint32_t tl = 0;
-    for (uint32_t t = (uint32_t)first; t < (uint32_t)p.ntiles; t += (uint32_t)step, ++tl) {
+    for (uint32_t tl = (uint32_t)egroup; ; tl += NEPI) {
+      const uint32_t t = (uint32_t)first + tl * (uint32_t)step;
+      if (t >= (uint32_t)p.ntiles) break;
       const uint32_t b = tl % (uint32_t)p.NACC;
       const uint32_t n = fastdiv(t, p.magic_tpi);                  // t / tiles_per_img
       const uint32_t rem = t - n * p.tiles_per_img;
@@ -374,7 +363,7 @@ conv_tc5_kernel(const Tc5P p) {
         pre1 = __ldg(reinterpret_cast<const uint4*>(r0p) + 1);
       }
       mbar_wait(bar_accf + 8u * b, (tl / (uint32_t)p.NACC) & 1);
-      if (p.dbg && blockIdx.x == 0 && blockIdx.y == 0 && threadIdx.x == 32 * EPI_WARP0 && tl < 64) p.dbg[tl * 8 + 5] = clock64();
+      if (p.dbg && blockIdx.x == 0 && blockIdx.y == 0 && (threadIdx.x == 32 * (EPI_WARP0 + 1) || threadIdx.x == 32 * (EPI_WARP0 + 5)) && tl < 64) p.dbg[tl * 8 + 5] = clock64();
       asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
       const uint32_t taddr = tq + b * (uint32_t)p.NS;
       for (int c0 = 0; c0 < ncol; c0 += 16) {
@@ -386,7 +375,7 @@ conv_tc5_kernel(const Tc5P p) {
           asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
           __syncwarp();
           if (lane == 0) mbar_arrive(bar_acce + 8u * b);
-          if (p.dbg && blockIdx.x == 0 && blockIdx.y == 0 && threadIdx.x == 32 * EPI_WARP0 && tl < 64) p.dbg[tl * 8 + 6] = clock64();
+          if (p.dbg && blockIdx.x == 0 && blockIdx.y == 0 && (threadIdx.x == 32 * (EPI_WARP0 + 1) || threadIdx.x == 32 * (EPI_WARP0 + 5)) && tl < 64) p.dbg[tl * 8 + 6] = clock64();
         }
         if (!ok || gch0 + c0 >= p.Cout) continue;        // padded output channels are never stored
         float f[16];
@@ -432,7 +421,7 @@ conv_tc5_kernel(const Tc5P p) {
           op[1] = o1;
         }
       }
-      if (p.dbg && blockIdx.x == 0 && blockIdx.y == 0 && threadIdx.x == 32 * EPI_WARP0 && tl < 64) p.dbg[tl * 8 + 7] = clock64();
+      if (p.dbg && blockIdx.x == 0 && blockIdx.y == 0 && (threadIdx.x == 32 * (EPI_WARP0 + 1) || threadIdx.x == 32 * (EPI_WARP0 + 5)) && tl < 64) p.dbg[tl * 8 + 7] = clock64();
     }
   }
   // ---- teardown
@@ -441,6 +430,34 @@ conv_tc5_kernel(const Tc5P p) {
   if (warp == 0) {
     asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(p.tmem_cols) : "memory");
   }
+}
+
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*,
+                                  CUtensorMapInterleave, CUtensorMapSwizzle, CUtensorMapL2promotion,
+                                  CUtensorMapFloatOOBfill);
+
+int make_halo_map(const ConvP& p, int halo, int KC, CUtensorMap* m) {
+  static EncodeTiledFn enc = nullptr;
+  if (!enc) {
+    void* f = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &f, cudaEnableDefault, &q) == cudaSuccess &&
+        q == cudaDriverEntryPointSuccess)
+      enc = (EncodeTiledFn)f;
+  }
+  RSG_REQUIRE(enc, "cuTensorMapEncodeTiled is not available from this driver");
+  const cuuint64_t es = 2;
+  cuuint64_t dims[5] = {8, (cuuint64_t)p.Win, (cuuint64_t)p.Hin, (cuuint64_t)(p.Cin / 8), (cuuint64_t)p.N};
+  cuuint64_t strides[4] = {(cuuint64_t)p.in_cs * es, (cuuint64_t)p.Win * p.in_cs * es, 16,
+                           (cuuint64_t)p.Hin * p.Win * p.in_cs * es};
+  cuuint32_t box[5] = {8, (cuuint32_t)(TW + 2 * halo), (cuuint32_t)(TH + 2 * halo), (cuuint32_t)(KC / 8), 1};
+  cuuint32_t estr[5] = {1, 1, 1, 1, 1};
+  CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 5, (void*)(p.in + p.in_co), dims, strides, box, estr,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE,
+                   CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  RSG_REQUIRE(r == CUDA_SUCCESS, "cuTensorMapEncodeTiled failed with %d", (int)r);
+  return RSG_OK;
 }
 
 }  // namespace
@@ -550,7 +567,10 @@ int conv_tc5_launch(const ConvP& p, cudaStream_t s, int* handled) {
   if (gx > k.ntiles) gx = k.ntiles;
   if (gx < 1) gx = 1;
   dim3 grid((unsigned)gx, (unsigned)nslices);
-  conv_tc5_kernel<<<grid, threads, smem, s>>>(k);
+  CUtensorMap map;
+  memset(&map, 0, sizeof(map));
+  { int rc = make_halo_map(p, halo, KC, &map); if (rc) return rc; }
+  conv_tc5_kernel<<<grid, threads, smem, s>>>(map, k);
   RSG_LAUNCH_CHECK();
   if (k.dbg) {
     static int dumped = 0;
