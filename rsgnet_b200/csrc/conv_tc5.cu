@@ -34,9 +34,9 @@
 namespace {
 
 constexpr int TH = 16, TW = 8;                 // pixel patch = 128 MMA rows
-constexpr int NTHREADS = 608;                  // one fat persistent CTA per SM (19 warps)
-constexpr int NMMA = 2;                        // MMA-issuing warps (0, 1): alternate tiles
-constexpr int EPI_WARP0 = 3;                   // warp 2 = TMA producer; epilogue warps 3..18: two groups of 8
+constexpr int NTHREADS = 672;                  // one fat persistent CTA per SM (21 warps)
+constexpr int MAX_MMA_WARPS = 4;               // warps 0..3 may issue MMAs (p.NMMA of them do), round-robin over tiles
+constexpr int EPI_WARP0 = 5;                   // warp 4 = TMA producer; epilogue warps 5..20: two groups of 8
 constexpr int NEPI = 2;
 constexpr uint32_t SPIN_LIMIT = 1u << 21;      // bounded waits: a protocol bug traps, never hangs
 
@@ -154,6 +154,7 @@ struct Tc5P {
   int KC, nchunks;      // channels per halo stage, Cin / KC
   int S;                // halo ring depth
   int NACC;             // TMEM accumulator ring depth
+  int NMMA;             // MMA-issuing warps: 2 or 4
   int EW;               // epilogue warps: 4, or 8 (two column halves per TMEM lane quarter)
   int ntaps;
   int8_t dy[9], dx[9];
@@ -225,15 +226,16 @@ conv_tc5_kernel(const __grid_constant__ CUtensorMap in_map, const Tc5P p) {
 
   const long long first = blockIdx.x, step = gridDim.x;
 
-  if (warp >= NMMA && warp < EPI_WARP0) {
+  const int NMMA = p.NMMA;
+  if (warp == MAX_MMA_WARPS) {
     // ===================== halo producer (TMA) =====================
-    const int ptid = threadIdx.x - 32 * NMMA;
+    const int ptid = lane;
     // One elected thread issues one 5-D TMA box per stage: (8 ch, 10 px, 18 rows, KC/8 planes, 1 crop)
     // lands in shared memory as [KC/8][18][10][8ch]; out-of-bounds coordinates are zero-filled, which
     // is the convolution's zero padding.
     if (ptid == 0) {
       asm volatile("prefetch.tensormap [%0];" ::"l"(&in_map) : "memory");
-      const uint32_t S2 = (uint32_t)p.S / NMMA;          // each MMA warp owns its own ring of S/2 stages
+      const uint32_t S2 = (uint32_t)(p.S / NMMA);        // each MMA warp owns its own ring of S/NMMA stages
       uint32_t tl = 0, it = 0;
       for (int t = (int)first; t < (int)p.ntiles; t += (int)step, ++tl) {
         const int n = (int)fastdiv((uint32_t)t, p.magic_tpi);
@@ -255,7 +257,8 @@ conv_tc5_kernel(const __grid_constant__ CUtensorMap in_map, const Tc5P p) {
         }
       }
     }
-  } else if (warp < NMMA) {
+  } else if (warp < MAX_MMA_WARPS) {
+   if (warp < NMMA) {
     // ===================== weight bulk copy + MMA issuers =====================
     // Two issuing warps, alternating tiles: one warp sustains one UTCHMMA per ~86 cycles whatever N
     // is, two together reach the operand-fetch floor (40 / 48 / 64 cycles for N = 32 / 64 / 128;
@@ -290,15 +293,17 @@ conv_tc5_kernel(const __grid_constant__ CUtensorMap in_map, const Tc5P p) {
       // Each issuing warp consumes its OWN ring of S/2 stages (slots warp, warp+2, ...).  With one
       // shared ring a warp could wait for phase k+1 of a slot before phase k had completed, and an
       // mbarrier parity wait cannot tell "not yet" from "one phase ago".
-      const uint32_t S2 = (uint32_t)p.S / NMMA;
+      const uint32_t S2 = (uint32_t)(p.S / NMMA);
       uint32_t j = (tl / NMMA) * (uint32_t)p.nchunks;
       for (int c = 0; c < p.nchunks; ++c, ++j) {
         const int s = (int)((j % S2) * NMMA + (uint32_t)warp);
         mbar_wait(BAR(B_FULL + s), (j / S2) & 1);          // halo chunk landed
         if (p.dbg && blockIdx.x == 0 && blockIdx.y == 0 && lane == 0 && tl < 64) p.dbg[tl * 8 + 3] = clock64();
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-        const uint32_t a_stage = (a0 + (uint32_t)s * p.stage_bytes) >> 4;
-        const uint32_t w_chunk = (w0 >> 4) + (uint32_t)c * b_chunkstep;
+        // low descriptor words: (address >> 4) | LBO << 16; adding 16-byte offsets never carries out of
+        // the 14-bit address field (shared memory is < 256 KB)
+        const uint32_t a_stage = ((a0 + (uint32_t)s * p.stage_bytes) >> 4) | lo_lbo_a;
+        const uint32_t w_chunk = ((w0 >> 4) + (uint32_t)c * b_chunkstep) | lo_lbo_b;
         if (elect_one()) {
           uint32_t acc = c > 0;
           const int ntp = (p.skip & 2) ? 1 : p.ntaps;
@@ -306,8 +311,8 @@ conv_tc5_kernel(const __grid_constant__ CUtensorMap in_map, const Tc5P p) {
             uint32_t alo = a_stage + (uint32_t)p.tapoff[tp];
             uint32_t blo = w_chunk + (uint32_t)tp * b_tapstep;
             for (int kc = 0; kc < kc2n; ++kc) {
-              const uint64_t ad = ((uint64_t)hiA << 32) | (alo & 0x3FFFu) | lo_lbo_a;
-              const uint64_t bd = ((uint64_t)hiB << 32) | (blo & 0x3FFFu) | lo_lbo_b;
+              const uint64_t ad = ((uint64_t)hiA << 32) | alo;
+              const uint64_t bd = ((uint64_t)hiB << 32) | blo;
               umma_f16(d_tmem, ad, bd, idesc, acc);
               acc = 1;
               alo += a_kstep;
@@ -321,8 +326,9 @@ conv_tc5_kernel(const __grid_constant__ CUtensorMap in_map, const Tc5P p) {
       }
       if (p.dbg && blockIdx.x == 0 && blockIdx.y == 0 && lane == 0 && tl < 64) p.dbg[tl * 8 + 4] = clock64();
     }
+   }
   } else {
-    // ===================== epilogue (warps 3 .. 18) =====================
+    // ===================== epilogue (warps 5 .. 20) =====================
     // Two groups of 8 warps that alternate tiles (like the MMA warps).  Inside a group: TMEM lane
     // quarter q = warp & 3 (hardware rule) and a column half.
     // These warps are what bounds the kernel once loads and MMA issue are out of the way: every
@@ -544,7 +550,13 @@ int conv_tc5_launch(const ConvP& p, cudaStream_t s, int* handled) {
   const uint32_t col_budget = 512u;                       // one CTA per SM owns all of TMEM
   int nacc = (int)(col_budget / (uint32_t)NS);
   if (nacc > MAX_ACC) nacc = MAX_ACC;
-  nacc &= ~1;                                             // even: tiles alternate between the two MMA warps
+  // thin layers are bound by the per-warp MMA issue rate (~110 cycles per MMA): four issuing warps when
+  // the rings can be split four ways
+  int nmma = (S % 4 == 0 && S >= 8) ? 4 : 2;
+  { const char* e = getenv("RSG_TC5_NMMA"); if (e) nmma = atoi(e); }
+  if (nmma == 4 && (S % 4 != 0 || nacc < 4)) nmma = 2;
+  k.NMMA = nmma;
+  nacc = nacc / nmma * nmma;                              // tiles go round-robin over the MMA warps
   if (nacc < 2) nacc = 2;
   { const char* e = getenv("RSG_TC5_NACC"); if (e) nacc = atoi(e); }
   k.NACC = nacc;

@@ -8,7 +8,9 @@ namespace {
 // conv1: 3x3 s2 p1, 3 -> 64, fp32 NCHW in (optionally W-reversed), bf16 NHWC out, BN folded, ReLU.
 // pose_rsgnet.py:612-613, 922-924 (+ input.flip(3), function.py:401).  fp32 FMA on CUDA cores:
 // K = 27 is too thin for the tensor pipe and the op is bound by its 128 B/pixel output stream.
-// A warp covers 8 consecutive output pixels x 4 groups of 16 channels -> 1 KB contiguous stores.
+// A warp covers 32 consecutive output pixels of ONE group of 16 channels: the weight reads are pure
+// shared-memory broadcasts (with the channel group varying inside a warp every LDS.128 took four
+// wavefronts and the kernel ran at 8 TFLOP/s), and every thread stores one full 32-byte sector.
 // ---------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256)
 stem_kernel(const float* __restrict__ x, int H, int W, const float* __restrict__ w,
@@ -20,9 +22,10 @@ stem_kernel(const float* __restrict__ x, int H, int W, const float* __restrict__
   __syncthreads();
   const int Ho = H >> 1, Wo = W >> 1;
   const long long total = (long long)nb * Ho * Wo;
-  const long long pix = (long long)blockIdx.x * 64 + (threadIdx.x >> 2);
+  const int warp = threadIdx.x >> 5;
+  const long long pix = (long long)blockIdx.x * 64 + (warp >> 2) * 32 + (threadIdx.x & 31);
   if (pix >= total) return;
-  const int cg = threadIdx.x & 3;
+  const int cg = warp & 3;
   const int ox = (int)(pix % Wo);
   const long long r = pix / Wo;
   const int oy = (int)(r % Ho);
@@ -294,7 +297,70 @@ relation_scores_kernel(const bf16* __restrict__ x, int cs, int co, int S, int C,
     }
 }
 
+// ---------------------------------------------------------------------------------------------
+// 1x1 heat-map head: bf16 NHWC [M, Cin] -> fp32 NCHW [N, Cout, H, W] (+bias), Cout <= 32, Cin <= 64
+// (final_layer / multi_final_layer, pose_rsgnet.py:961, 1000).  HBM-bound: one thread per pixel, the
+// Cin channels in registers, weights broadcast from shared memory, plane-coalesced fp32 stores.
+// ---------------------------------------------------------------------------------------------
+template <int CIN>
+__global__ void __launch_bounds__(256)
+head1x1_kernel(const bf16* __restrict__ in, int in_cs, int in_co, const bf16* __restrict__ w, int w_ld,
+               const float* __restrict__ bias, int Cout, long long M, int HW, float* __restrict__ out, int relu) {
+  __shared__ float sw[32 * CIN];
+  __shared__ float sb[32];
+  for (int i = threadIdx.x; i < Cout * CIN; i += blockDim.x) sw[i] = __bfloat162float(w[(i / CIN) * w_ld + (i % CIN)]);
+  if (threadIdx.x < Cout) sb[threadIdx.x] = bias[threadIdx.x];
+  __syncthreads();
+  const long long m = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (m >= M) return;
+  float x[CIN];
+  const uint4* src = reinterpret_cast<const uint4*>(in + (size_t)m * in_cs + in_co);
+#pragma unroll
+  for (int j = 0; j < CIN / 8; ++j) {
+    const uint4 u = __ldg(src + j);
+    const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&u);
+#pragma unroll
+    for (int e = 0; e < 4; ++e) { x[j * 8 + 2 * e] = __bfloat162float(h[e].x); x[j * 8 + 2 * e + 1] = __bfloat162float(h[e].y); }
+  }
+  const long long n = m / HW;
+  float* op = out + (size_t)n * Cout * HW + (m - n * HW);
+  for (int k = 0; k < Cout; ++k) {
+    float a = sb[k];
+    const float4* wk = reinterpret_cast<const float4*>(sw + k * CIN);
+#pragma unroll
+    for (int j = 0; j < CIN / 4; ++j) {
+      const float4 ww = wk[j];
+      a = fmaf(x[4 * j], ww.x, a); a = fmaf(x[4 * j + 1], ww.y, a);
+      a = fmaf(x[4 * j + 2], ww.z, a); a = fmaf(x[4 * j + 3], ww.w, a);
+    }
+    if (relu) a = fmaxf(a, 0.f);
+    op[(size_t)k * HW] = a;
+  }
+}
+
 }  // namespace
+
+int head1x1_launch(const ConvP& p, cudaStream_t s, int* handled) {
+  *handled = 0;
+  if (!p.out_f32 || p.out || p.ntaps != 1 || p.dy[0] != 0 || p.dx[0] != 0 || p.stride != 1 || p.omul != 1 ||
+      p.nres != 0 || p.Cout > 32 || p.in_cs % 8 != 0 || p.in_co % 8 != 0)
+    return RSG_OK;
+  if (p.Cin != 16 && p.Cin != 32 && p.Cin != 48 && p.Cin != 64) return RSG_OK;
+  *handled = 1;
+  if (p.M == 0) return RSG_OK;
+  const int HW = p.Hout * p.Wout;
+  dim3 grid(ceil_div(p.M, 256));
+#define RSG_HEAD(C) head1x1_kernel<C><<<grid, 256, 0, s>>>(p.in, p.in_cs, p.in_co, p.w, p.CinPad, p.bias, p.Cout, p.M, HW, p.out_f32, p.relu)
+  switch (p.Cin) {
+    case 16: RSG_HEAD(16); break;
+    case 32: RSG_HEAD(32); break;
+    case 48: RSG_HEAD(48); break;
+    default: RSG_HEAD(64); break;
+  }
+#undef RSG_HEAD
+  RSG_LAUNCH_CHECK();
+  return RSG_OK;
+}
 
 int stem_launch(cudaStream_t s, const float* x, int H, int W, const float* w, const float* bias,
                 bf16* out, int f0, int nb, int n_crops) {

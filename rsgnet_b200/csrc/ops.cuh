@@ -2,6 +2,8 @@
 #pragma once
 #include "conv_params.cuh"
 
+// returns *handled = 1 when the fp32-NCHW 1x1 head kernel covers this conv
+int head1x1_launch(const ConvP& p, cudaStream_t s, int* handled);
 int stem_launch(cudaStream_t s, const float* x, int H, int W, const float* w, const float* bias,
                 bf16* out, int f0, int nb, int n_crops);
 int fuse_launch(cudaStream_t s, int nterms, const ResP* terms, bf16* out, int out_cs, int out_co,

@@ -141,6 +141,12 @@ int run_conv(const rsg_conv_desc& d, const RunCtx& c, int N, cudaStream_t s, int
   int rc = fill_conv(d, c, N, &p);
   if (rc) return rc;
   if (used_tc5) *used_tc5 = 0;
+  if (d.engine == 0) {
+    int handled = 0;
+    rc = head1x1_launch(p, s, &handled);
+    if (rc) return rc;
+    if (handled) return RSG_OK;
+  }
   if (d.engine != 1) {
     int handled = 0;
     rc = conv_tc5_launch(p, s, &handled);
