@@ -37,11 +37,28 @@ class CropPipeline:
         self.use_graph = use_graph
         nf = batch * (2 if self.flip else 1)
         dev = self.device
-        self.x = torch.empty((batch, 3, self.spec.image_h, self.spec.image_w), dtype=torch.float32, device=dev)
+        # two input slots: slot i+1 is filled from pinned host memory on a copy stream while slot i computes
+        self._slots = [dict(x=torch.empty((batch, 3, self.spec.image_h, self.spec.image_w), dtype=torch.float32, device=dev),
+                            center=torch.empty((batch, 2), dtype=torch.float32, device=dev),
+                            scale=torch.empty((batch, 2), dtype=torch.float32, device=dev),
+                            ready=torch.cuda.Event(), free=torch.cuda.Event()) for _ in range(2)]
+        self._cur = 0
+        self._copy_stream = torch.cuda.Stream(dev)
         self.heat = torch.empty((nf, K, self.spec.heat_h, self.spec.heat_w), dtype=torch.float32, device=dev)
-        self.center = torch.empty((batch, 2), dtype=torch.float32, device=dev)
-        self.scale = torch.empty((batch, 2), dtype=torch.float32, device=dev)
         self.n_fwd = nf
+
+    # the current input slot (what run_device consumes)
+    @property
+    def x(self):
+        return self._slots[self._cur]['x']
+
+    @property
+    def center(self):
+        return self._slots[self._cur]['center']
+
+    @property
+    def scale(self):
+        return self._slots[self._cur]['scale']
 
     def run_device(self):
         """Inputs already in self.x / self.center / self.scale.  Returns CUDA (preds, maxvals)."""
@@ -51,6 +68,43 @@ class CropPipeline:
         out = decode_device(hm, self.center, self.scale, post_process=self.post, hm_flipped=hf,
                             flip_perm=self.perm, shift=self.shift)
         return out['preds'], out['maxvals']
+
+    def run_overlapped(self, batches, out=None):
+        """Process a sequence of host batches (x, center, scale) -- pinned tensors for true overlap --
+        with the H2D copy of batch i+1 running on a copy stream under the compute of batch i.
+        Returns a list of (preds, maxvals) CUDA tensors, or fills `out` = list of (preds_host,
+        maxvals_host) pinned tensors with non-blocking D2H copies (synchronise before reading)."""
+        main = torch.cuda.current_stream(self.device)
+        results = []
+
+        def upload(i, slot):
+            sl = self._slots[slot]
+            xb, cb, sb = batches[i]
+            with torch.cuda.stream(self._copy_stream):
+                self._copy_stream.wait_event(sl['free'])          # previous consumer of this slot is done
+                sl['x'].copy_(xb, non_blocking=True)
+                sl['center'].copy_(cb, non_blocking=True)
+                sl['scale'].copy_(sb, non_blocking=True)
+                sl['ready'].record(self._copy_stream)
+
+        for sl in self._slots:
+            sl['free'].record(main)
+        if len(batches):
+            upload(0, self._cur)
+        for i in range(len(batches)):
+            slot = self._cur
+            if i + 1 < len(batches):
+                upload(i + 1, slot ^ 1)
+            main.wait_event(self._slots[slot]['ready'])
+            preds, maxvals = self.run_device()
+            self._slots[slot]['free'].record(main)
+            if out is not None:
+                out[i][0].copy_(preds, non_blocking=True)
+                out[i][1].copy_(maxvals, non_blocking=True)
+            else:
+                results.append((preds, maxvals))
+            self._cur = slot ^ 1
+        return results
 
     def launches_per_step(self):
         return self.engine.last_launches() + 1

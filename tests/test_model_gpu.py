@@ -146,3 +146,24 @@ def test_pipeline_matches_reference_loop_on_oracle_heatmaps():
     o_preds, o_mv = decode_oracle.get_final_preds(True, avg, c, s)
     assert np.array_equal(preds, o_preds) and np.array_equal(maxvals, o_mv)
     assert pipe.launches_per_step() > 100
+
+
+def test_overlapped_pipeline_equals_sequential():
+    """run_overlapped (double-buffered H2D under compute, CUDA-graph replay) == step-by-step calls."""
+    from rsgnet_b200 import synth
+    from rsgnet_b200.pipeline import CropPipeline
+    cfg, net, sd = build('tiny', 0)
+    B = 4
+    batches = []
+    for i in range(5):
+        c, s = synth.centers_scales(B, seed=20 + i)
+        batches.append((crops(cfg, B, 30 + i).pin_memory(), torch.from_numpy(c).pin_memory(), torch.from_numpy(s).pin_memory()))
+    seq = CropPipeline(net, cfg, B, use_graph=False)
+    ref = [seq(x, c, s) for x, c, s in batches]
+    pipe = CropPipeline(net, cfg, B, use_graph=True)
+    st = torch.cuda.Stream()
+    with torch.cuda.stream(st):
+        got = pipe.run_overlapped(batches)
+    st.synchronize()
+    for (p, m), (rp, rm) in zip(got, ref):
+        assert np.array_equal(p.cpu().numpy(), rp) and np.array_equal(m.cpu().numpy(), rm)
