@@ -122,7 +122,9 @@ typedef struct rsg_conv_desc {
   int32_t nres;
   rsg_res res[RSG_MAX_RES];
   int32_t relu;
-  int32_t engine;              /* 0 = auto, 1 = force mma.sync path, 2 = force tcgen05 path */
+  int32_t engine;              /* 0 = auto, 1 = force mma.sync path, 2 = force tcgen05 path,
+                                  3 = weight-streaming tcgen05 path (w_tc5 packed with the NS of
+                                  rsg_conv_ws_config) */
 } rsg_conv_desc;
 
 int rsg_plan_create(rsg_plan** out, int chunk);
@@ -163,7 +165,8 @@ int rsg_plan_run(rsg_plan*, void* stream, void* const* ext, int n_ext, int n_fwd
                  int with_aux, int use_graph);
 /* Measurement aid: run ONE chunk of `nb` forwards eagerly with a CUDA event pair around every op.
  * ms[i] = device time of op i, kind[i]: 0 stem, 1 conv (generic mma.sync kernel), 2 conv (tcgen05
- * kernel), 3 fuse, 4 maxpool, 5 attention, 6 relation_scores, 7 groupnorm, 8 bilinear;
+ * kernel), 3 fuse, 4 maxpool, 5 attention, 6 relation_scores, 7 groupnorm, 8 bilinear, 9 conv
+ * (weight-streaming tcgen05 kernel);
  * flops[i] = MAC*2 the op executes for nb forwards (0 for the element-wise ops).  Arrays must hold
  * rsg_plan_num_ops entries; ops skipped (aux) get ms = -1. */
 int rsg_plan_profile(rsg_plan*, void* stream, void* const* ext, int n_ext, int nb, int n_crops,
@@ -175,6 +178,12 @@ int rsg_plan_last_launches(const rsg_plan*);
  * halo stage (KC) and ring depth (S).  Returns 0 when the shape is not covered (the generic kernel
  * runs instead).  The host packer needs NS to lay w_tc5 out as [CoutPad/NS][ntaps][Cin/8][NS][8]. */
 int rsg_conv_tc5_config(int Cin, int CoutPad, int ntaps, int halo, int* NS, int* KC, int* S);
+
+/* Weight-streaming tcgen05 conv kernel (many channels, small maps: the stage-3/4 low-resolution
+ * branches): returns 1 and the output channels per CTA (NS) when it covers a stride-1 conv of this
+ * shape on H x W maps, else 0.  The host packs w_tc5 as [CoutPad/NS][ntaps][Cin/8][NS][8] and sets
+ * engine = 3. */
+int rsg_conv_ws_config(int Cin, int CoutPad, int ntaps, int H, int W, int* NS);
 
 /* Stand-alone conv launch (unit tests / micro-benchmarks): desc refs must be absolute. */
 int rsg_conv_run(void* stream, const rsg_conv_desc*, int N);

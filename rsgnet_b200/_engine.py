@@ -177,7 +177,21 @@ class PlanBuilder:
         Hout = (Hin - 1) // stride + 1 if out_hw is None else out_hw[0]
         Wout = (Win - 1) // stride + 1 if out_hw is None else out_hw[1]
         w_tc5 = None
-        if (stride == 1 and omul == 1 and out_f32 is None and cin % 16 == 0 and cout % 8 == 0
+        tc5_ok = (stride == 1 and omul == 1 and out_f32 is None and cin % 16 == 0 and cout % 8 == 0
+                  and all(abs(dy) <= 1 and abs(dx) <= 1 for dy, dx in taps) and len(taps) <= 9)
+        ns = C.c_int()
+        # GEMM-shaped layers (K = taps*Cin >= 1152, >= 128 output channels) on maps small enough for the
+        # flat formulation: weight-streaming kernel
+        want_ws = engine == 3 or (engine == 0 and len(taps) * cin >= 1152 and cout_pad >= 128)
+        if (tc5_ok and want_ws and dst is not None
+                and _lib.lib().rsg_conv_ws_config(cin, cout_pad, len(taps), Hin, Win, C.byref(ns))):
+            NS = ns.value
+            wt = wp[:, :, :cin].reshape(len(taps), cout_pad // NS, NS, cin // 8, 8)
+            w_tc5 = self.const(_bf16_bits(wt.transpose(1, 0, 3, 2, 4)))
+            engine = 3
+        elif engine == 3:
+            raise ValueError(f'{name}: shape not covered by the weight-streaming kernel')
+        elif (stride == 1 and omul == 1 and out_f32 is None and cin % 16 == 0 and cout % 8 == 0
                 and all(abs(dy) <= 1 and abs(dx) <= 1 for dy, dx in taps) and len(taps) <= 9):
             halo = int(any(dy != 0 or dx != 0 for dy, dx in taps))
             ns, kc, st = C.c_int(), C.c_int(), C.c_int()

@@ -31,3 +31,6 @@ struct ConvP {
 int conv_mma_launch(const ConvP& p, cudaStream_t s);
 // returns RSG_OK and sets *handled=1 when the tcgen05 kernel covers this shape
 int conv_tc5_launch(const ConvP& p, cudaStream_t s, int* handled);
+// weight-streaming tcgen05 kernel (conv_ws.cu): many-channel stride-1 convs on small maps; w_tc5 must be
+// packed with the NS of rsg_conv_ws_config
+int conv_ws_launch(const ConvP& p, cudaStream_t s, int* handled);

@@ -1,0 +1,390 @@
+// Weight-streaming tcgen05 convolution for the GEMM-shaped end of HRNet: stride-1 3x3 / 1x1 convs with
+// many channels on small maps (128->128 @16x12, 256->256 @8x6 for W32; 192/384 for W48), where the
+// folded weights (0.3 - 1.2 MB) cannot stay resident in shared memory and conv_tc5.cu's 16x8 pixel
+// patch wastes most MMA rows.
+//
+// "Flat" implicit GEMM.  nimg whole images are brought into shared memory by ONE 5-D TMA box per
+// K-chunk, starting at (x,y) = (-1,-1), so that every image arrives as (H+1) rows of P = W+1 pixels
+// whose first row and first column are the convolution's zero padding (TMA out-of-bounds fill):
+//     plane[k8][img][r = y+1][c = x+1][8 ch]      (one plane per 8 input channels)
+// Seen as a flat pixel array with pitch P, the input of tap (dy,dx) for output pixel o = img*pitch +
+// y*P + x is simply flat[o + (1+dy)*P + (1+dx)]: the zero column doubles as the right padding of the
+// previous row and the zero row as the bottom padding of the previous image.  The 128 rows of an MMA
+// are therefore 128 CONSECUTIVE flat pixels (K-major SWIZZLE_NONE: core matrix = 8 pixels x 16 B,
+// SBO = 128 B, LBO = one plane), each tap is a start-address offset, and images of any size pack into
+// M tiles without patch quantisation (8x6: 75 % useful rows instead of 37 %).  Rows that fall on the
+// padding positions compute junk and are not stored.
+//
+// A supertile = nimg images = T <= 4 M tiles, each with its own TMEM accumulator of NS columns
+// (T * NS <= 512).  The K loop runs over chunks of KC input channels; one stage of the ring holds the
+// activation planes of the chunk plus the weights of all taps for that chunk ([tap][KC/8][NS][8],
+// bulk copies), and all T tiles consume the stage, so the weight stream is amortised over 512 pixels.
+//
+// Warp roles (640 threads, one persistent CTA per SM): warps 0-1 issue MMAs (tiles t = warp mod 2, so
+// two instruction streams feed the tensor pipe, profiles/r1_notes.md §1), warp 2 = TMA producer, warp 3
+// owns the TMEM allocation, warps 4-19 = two epilogue groups of 8 warps (tile parity), each warp one
+// TMEM lane quarter and one half of the NS columns: +bias, +residual terms, ReLU, bf16 NHWC stores.
+//
+// Reference ops subsumed: Conv2d(3x3|1x1, s1, bias=False) + BatchNorm2d(eval) [+ residual] [+ ReLU] of
+// the stage-3/4 low-resolution branches (pose_rsgnet.py:25-54 BasicBlock inside HighResolutionModule
+// :108-272).
+#include "umma.cuh"
+
+namespace {
+using namespace umma;
+
+constexpr int WS_THREADS = 640;
+constexpr int WS_EPI_WARP0 = 4;
+constexpr int WS_MAX_S = 8;
+constexpr int WS_MAX_T = 4;
+constexpr int WS_SMEM_BUDGET = 225 * 1024;
+
+struct WsP {
+  const bf16* w;        // [slice][tap][Cin/8][NS][8]
+  const float* bias;
+  int Cin, NS, Cout;
+  int KC, nchunks, S, T, nimg;
+  int ntaps;
+  int tapoff[9];        // (1+dy)*P + (1+dx), pixels (= 16-byte units)
+  int H, W, P, pitch;   // P = W + 1, pitch = (H + 1) * P pixels per image
+  uint32_t magic_pitch, magic_P;
+  int N, nsuper;
+  bf16* out;
+  int out_cs, out_co;
+  int nres;
+  ResP res[4];
+  int relu;
+  uint32_t plane_bytes, a_bytes, b_off, b_tap_bytes, stage_bytes, tmem_cols;
+};
+
+__global__ void __launch_bounds__(WS_THREADS, 1)
+conv_ws_kernel(const __grid_constant__ CUtensorMap in_map, const WsP p) {
+  extern __shared__ __align__(128) unsigned char smem_raw[];
+  __shared__ __align__(8) uint64_t bars[2 * WS_MAX_S + 2 * WS_MAX_T];
+  __shared__ uint32_t tmem_base_slot;
+  __shared__ __align__(16) float sBias[256];
+  const uint32_t bar0 = smem_u32(&bars[0]);
+  auto BAR = [&](int i) { return bar0 + 8u * i; };
+  const int B_FULL = 0, B_EMPTY = p.S, B_ACCF = 2 * p.S, B_ACCE = 2 * p.S + p.T;
+  const uint32_t sbase = (smem_u32(smem_raw) + 127u) & ~127u;        // TMA destinations: 128-byte aligned
+  unsigned char* const sgen = smem_raw + (sbase - smem_u32(smem_raw));
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int slice = blockIdx.y;
+
+  if (threadIdx.x == 0) {
+    for (int i = 0; i < p.S; ++i) { mbar_init(BAR(B_FULL + i), 1); mbar_init(BAR(B_EMPTY + i), 2); }
+    for (int i = 0; i < p.T; ++i) { mbar_init(BAR(B_ACCF + i), 1); mbar_init(BAR(B_ACCE + i), 8); }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  for (int i = threadIdx.x; i < p.NS; i += blockDim.x) sBias[i] = p.bias[slice * p.NS + i];
+  // the gap between the activation planes and the weights of every stage is what the bottom-right
+  // taps of the last image read: keep it zero (TMA never writes there)
+  {
+    const uint32_t gap16 = (p.b_off - p.a_bytes) >> 4;
+    for (uint32_t i = threadIdx.x; i < gap16 * (uint32_t)p.S; i += blockDim.x) {
+      const uint32_t s = i / gap16, j = i - s * gap16;
+      *reinterpret_cast<uint4*>(sgen + (size_t)s * p.stage_bytes + p.a_bytes + 16u * j) = make_uint4(0, 0, 0, 0);
+    }
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+  }
+  if (warp == 3) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_base_slot)), "r"(p.tmem_cols) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+  const uint32_t tmem_base = tmem_base_slot;
+  const int first = blockIdx.x, step = gridDim.x;
+
+  if (warp == 2) {
+    // ===================== producer: one TMA box + ntaps bulk copies per stage =====================
+    if (lane == 0) {
+      asm volatile("prefetch.tensormap [%0];" ::"l"(&in_map) : "memory");
+      const unsigned char* wsl = reinterpret_cast<const unsigned char*>(p.w) +
+                                 (size_t)slice * p.ntaps * (size_t)(p.Cin >> 3) * p.NS * 16u;
+      const size_t w_tap_stride = (size_t)(p.Cin >> 3) * p.NS * 16u;
+      const uint32_t tx_bytes = p.a_bytes + (uint32_t)p.ntaps * p.b_tap_bytes;
+      uint32_t it = 0;
+      for (int u = first; u < p.nsuper; u += step) {
+        for (int c = 0; c < p.nchunks; ++c, ++it) {
+          const uint32_t s = it % (uint32_t)p.S;
+          mbar_wait(BAR(B_EMPTY + s), ((it / (uint32_t)p.S) & 1) ^ 1);
+          const uint32_t dst = sbase + s * p.stage_bytes;
+          mbar_arrive_expect_tx(BAR(B_FULL + s), tx_bytes);
+          tma_load_5d(dst, &in_map, BAR(B_FULL + s), 0, -1, -1, u * p.nimg, c * (p.KC >> 3));
+          const unsigned char* wc = wsl + (size_t)c * p.b_tap_bytes;
+          for (int tp = 0; tp < p.ntaps; ++tp)
+            bulk_load(dst + p.b_off + (uint32_t)tp * p.b_tap_bytes, wc + (size_t)tp * w_tap_stride, p.b_tap_bytes,
+                      BAR(B_FULL + s));
+        }
+      }
+    }
+  } else if (warp < 2) {
+    // ===================== MMA issuers =====================
+    // Warp-uniform control flow, tcgen05 instructions predicated on one elected lane (UTCHMMA takes its
+    // descriptors from uniform registers; see conv_tc5.cu).
+    const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(p.NS >> 3) << 17) | ((128u >> 4) << 24);
+    const uint32_t hiA = desc_hi(128u), hiB = desc_hi(128u);
+    const uint32_t lo_lbo_a = ((p.plane_bytes >> 4) & 0x3FFFu) << 16;
+    const uint32_t lo_lbo_b = (((uint32_t)p.NS * 16u >> 4) & 0x3FFFu) << 16;
+    const uint32_t a_kstep = (2u * p.plane_bytes) >> 4, b_kstep = (2u * (uint32_t)p.NS * 16u) >> 4;
+    const uint32_t b_tapstep = p.b_tap_bytes >> 4;
+    const int kc2n = p.KC >> 4;
+    uint32_t it = 0, st = 0;
+    for (int u = first; u < p.nsuper; u += step, ++st) {
+      for (int c = 0; c < p.nchunks; ++c, ++it) {
+        const uint32_t s = it % (uint32_t)p.S;
+        mbar_wait(BAR(B_FULL + s), (it / (uint32_t)p.S) & 1);
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        const uint32_t stage16 = (sbase + s * p.stage_bytes) >> 4;
+        const uint32_t b_stage = (stage16 + (p.b_off >> 4)) | lo_lbo_b;
+        if (elect_one()) {
+          for (int t = warp; t < p.T; t += 2) {
+            if (c == 0) {                                   // accumulator drained by the epilogue
+              mbar_wait(BAR(B_ACCE + t), (st & 1) ^ 1);
+              asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+            }
+            const uint32_t d_tmem = tmem_base + (uint32_t)(t * p.NS);
+            const uint32_t a_tile = (stage16 + 128u * (uint32_t)t) | lo_lbo_a;
+            uint32_t acc = c > 0;
+            for (int tp = 0; tp < p.ntaps; ++tp) {
+              uint32_t alo = a_tile + (uint32_t)p.tapoff[tp];
+              uint32_t blo = b_stage + (uint32_t)tp * b_tapstep;
+              for (int kc = 0; kc < kc2n; ++kc) {
+                umma_f16(d_tmem, ((uint64_t)hiA << 32) | alo, ((uint64_t)hiB << 32) | blo, idesc, acc);
+                acc = 1;
+                alo += a_kstep;
+                blo += b_kstep;
+              }
+            }
+            if (c == p.nchunks - 1) umma_commit(BAR(B_ACCF + t));     // accumulator of tile t complete
+          }
+          umma_commit(BAR(B_EMPTY + s));                    // stage free once this warp's MMAs retire
+        }
+        __syncwarp();
+      }
+    }
+  } else if (warp >= WS_EPI_WARP0) {
+    // ===================== epilogue (warps 4 .. 19) =====================
+    const int eidx = (warp - WS_EPI_WARP0) >> 2;    // 0..3
+    const int egroup = eidx & 1;
+    const int q = warp & 3;                         // TMEM lane quarter (hardware rule: warp % 4)
+    const int ncol = p.NS >> 1;
+    const int cbeg = (eidx >> 1) ? ncol : 0;
+    const int gch0 = slice * p.NS + cbeg;
+    const int nres = p.nres;
+    const float* biasp = sBias + cbeg;
+    bf16* const outp = p.out + p.out_co + gch0;
+    const uint32_t tq = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)cbeg;
+    const uint32_t bar_accf = opaque(BAR(B_ACCF)), bar_acce = opaque(BAR(B_ACCE));
+    uint32_t st = 0;
+    for (int u = first; u < p.nsuper; u += step, ++st) {
+      for (int t = egroup; t < p.T; t += 2) {
+        const uint32_t o = (uint32_t)t * 128u + (uint32_t)(q * 32 + lane);
+        const uint32_t i = fastdiv(o, p.magic_pitch);
+        const uint32_t r = o - i * (uint32_t)p.pitch;
+        const uint32_t y = fastdiv(r, p.magic_P);
+        const uint32_t x = r - y * (uint32_t)p.P;
+        const uint32_t n = (uint32_t)u * (uint32_t)p.nimg + i;
+        const bool ok = i < (uint32_t)p.nimg && n < (uint32_t)p.N && y < (uint32_t)p.H && x < (uint32_t)p.W;
+        const uint32_t ooff = ((n * (uint32_t)p.H + y) * (uint32_t)p.W + x) * (uint32_t)p.out_cs;
+        const bf16* r0p = nullptr;
+        uint4 pre0 = make_uint4(0, 0, 0, 0), pre1 = pre0;
+        if (nres > 0 && ok && gch0 < p.Cout) {
+          const ResP& rr = p.res[0];
+          r0p = rr.p + rr.co + gch0 +
+                (((rr.bs0 ? 0u : n) * (uint32_t)rr.H + (y >> rr.shift)) * (uint32_t)rr.W + (x >> rr.shift)) * (uint32_t)rr.cs;
+          pre0 = __ldg(reinterpret_cast<const uint4*>(r0p));
+          pre1 = __ldg(reinterpret_cast<const uint4*>(r0p) + 1);
+        }
+        mbar_wait(bar_accf + 8u * (uint32_t)t, st & 1);
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        const uint32_t taddr = tq + (uint32_t)(t * p.NS);
+        for (int c0 = 0; c0 < ncol; c0 += 16) {
+          uint32_t v[16];
+          tmem_ld16(taddr + c0, v);
+          asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+          if (c0 + 16 >= ncol) {
+            asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+            __syncwarp();
+            if (lane == 0) mbar_arrive(bar_acce + 8u * (uint32_t)t);
+          }
+          if (!ok || gch0 + c0 >= p.Cout) continue;
+          float f[16];
+          const float4* bp = reinterpret_cast<const float4*>(biasp + c0);
+#pragma unroll
+          for (int j4 = 0; j4 < 4; ++j4) {
+            const float4 bb = bp[j4];
+            f[j4 * 4 + 0] = __uint_as_float(v[j4 * 4 + 0]) + bb.x;
+            f[j4 * 4 + 1] = __uint_as_float(v[j4 * 4 + 1]) + bb.y;
+            f[j4 * 4 + 2] = __uint_as_float(v[j4 * 4 + 2]) + bb.z;
+            f[j4 * 4 + 3] = __uint_as_float(v[j4 * 4 + 3]) + bb.w;
+          }
+          if (nres > 0) {
+            if (c0 == 0) { add_res8(f, pre0); add_res8(f + 8, pre1); }
+            else {
+              add_res8(f, __ldg(reinterpret_cast<const uint4*>(r0p + c0)));
+              add_res8(f + 8, __ldg(reinterpret_cast<const uint4*>(r0p + c0) + 1));
+            }
+            for (int qi = 1; qi < nres; ++qi) {
+              const ResP& rr = p.res[qi];
+              const bf16* rp = rr.p + rr.co + gch0 + c0 +
+                  (((rr.bs0 ? 0u : n) * (uint32_t)rr.H + (y >> rr.shift)) * (uint32_t)rr.W + (x >> rr.shift)) * (uint32_t)rr.cs;
+              add_res8(f, __ldg(reinterpret_cast<const uint4*>(rp)));
+              add_res8(f + 8, __ldg(reinterpret_cast<const uint4*>(rp) + 1));
+            }
+          }
+          uint4 o0, o1;
+          __nv_bfloat162* h0 = reinterpret_cast<__nv_bfloat162*>(&o0);
+          __nv_bfloat162* h1 = reinterpret_cast<__nv_bfloat162*>(&o1);
+#pragma unroll
+          for (int k2 = 0; k2 < 4; ++k2) {
+            h0[k2] = __floats2bfloat162_rn(f[2 * k2], f[2 * k2 + 1]);
+            h1[k2] = __floats2bfloat162_rn(f[8 + 2 * k2], f[8 + 2 * k2 + 1]);
+          }
+          if (p.relu) {
+            const __nv_bfloat162 z = __floats2bfloat162_rn(0.f, 0.f);
+#pragma unroll
+            for (int k2 = 0; k2 < 4; ++k2) { h0[k2] = __hmax2(h0[k2], z); h1[k2] = __hmax2(h1[k2], z); }
+          }
+          uint4* op = reinterpret_cast<uint4*>(outp + ooff + c0);
+          op[0] = o0;
+          op[1] = o1;
+        }
+      }
+    }
+  }
+  // ---- teardown
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  if (warp == 3) {
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(p.tmem_cols) : "memory");
+  }
+}
+
+struct WsCfg {
+  int NS, KC, nimg, T, S;
+  uint32_t plane_bytes, a_bytes, b_off, b_tap_bytes, stage_bytes;
+};
+
+bool ws_config(int Cin, int CoutPad, int ntaps, int H, int W, WsCfg* c) {
+  if (Cin % 16 != 0 || ntaps < 1 || ntaps > 9 || H < 1 || W < 1) return false;
+  int NS = 0;
+  if (CoutPad % 128 == 0) NS = 128;
+  else if (CoutPad <= 256 && CoutPad % 16 == 0) NS = CoutPad;
+  if (NS < 64) return false;
+  int tmax = 512 / NS;
+  if (tmax > WS_MAX_T) tmax = WS_MAX_T;
+  const int P = W + 1, pitch = (H + 1) * P;
+  if (P + 1 > 64 || P > 256 || H + 1 > 256) return false;
+  int nimg = tmax * 128 / pitch;
+  if (nimg < 1) return false;
+  if (nimg > 64) nimg = 64;
+  c->NS = NS; c->KC = 16; c->nimg = nimg;
+  c->T = (nimg * pitch + 127) / 128;
+  c->plane_bytes = (uint32_t)nimg * pitch * 16u;
+  c->a_bytes = (uint32_t)(c->KC / 8) * c->plane_bytes;
+  c->b_off = (c->a_bytes + (uint32_t)(P + 1) * 16u + 127u) & ~127u;
+  c->b_tap_bytes = (uint32_t)(c->KC / 8) * NS * 16u;
+  c->stage_bytes = (c->b_off + (uint32_t)ntaps * c->b_tap_bytes + 127u) & ~127u;
+  // junk rows of the last tile read up to (T*128 - nimg*pitch + 2P + 2) pixels past the last plane:
+  // that must stay inside the stage (gap + weights)
+  if ((uint32_t)(c->T * 128 - nimg * pitch + 2 * P + 2) * 16u > c->stage_bytes - c->a_bytes) return false;
+  int S = (WS_SMEM_BUDGET - 128) / (int)c->stage_bytes;
+  if (S > WS_MAX_S) S = WS_MAX_S;
+  if (S < 2) return false;
+  c->S = S;
+  return true;
+}
+
+int make_flat_map(const ConvP& p, const WsCfg& c, CUtensorMap* m) {
+  EncodeTiledFn enc = tensor_map_encoder();
+  RSG_REQUIRE(enc, "cuTensorMapEncodeTiled is not available from this driver");
+  const cuuint64_t es = 2;
+  // NHWC activation viewed as (8 ch, W, H, N, C/8): the image index sits INSIDE the channel-plane index so
+  // that a box lands as [KC/8][nimg][H+1][W+1][8ch]
+  cuuint64_t dims[5] = {8, (cuuint64_t)p.Win, (cuuint64_t)p.Hin, (cuuint64_t)p.N, (cuuint64_t)(p.Cin / 8)};
+  cuuint64_t strides[4] = {(cuuint64_t)p.in_cs * es, (cuuint64_t)p.Win * p.in_cs * es,
+                           (cuuint64_t)p.Hin * p.Win * p.in_cs * es, 16};
+  cuuint32_t box[5] = {8, (cuuint32_t)(p.Win + 1), (cuuint32_t)(p.Hin + 1), (cuuint32_t)c.nimg, (cuuint32_t)(c.KC / 8)};
+  cuuint32_t estr[5] = {1, 1, 1, 1, 1};
+  CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 5, (void*)(p.in + p.in_co), dims, strides, box, estr,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE,
+                   CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  RSG_REQUIRE(r == CUDA_SUCCESS, "cuTensorMapEncodeTiled (flat map) failed with %d", (int)r);
+  return RSG_OK;
+}
+
+}  // namespace
+
+// Shape -> output channels per CTA: the host packer lays w_tc5 out as [CoutPad/NS][ntaps][Cin/8][NS][8].
+// Returns 0 when the weight-streaming kernel does not cover the shape.
+extern "C" int rsg_conv_ws_config(int Cin, int CoutPad, int ntaps, int H, int W, int* NS) {
+  WsCfg c;
+  if (!ws_config(Cin, CoutPad, ntaps, H, W, &c)) return 0;
+  if (NS) *NS = c.NS;
+  return 1;
+}
+
+int conv_ws_launch(const ConvP& p, cudaStream_t s, int* handled) {
+  *handled = 0;
+  static const bool disabled = getenv("RSG_DISABLE_WS") != nullptr;
+  if (disabled) return RSG_OK;
+  if (!p.w_tc5 || !p.out || p.out_f32) return RSG_OK;
+  if (p.stride != 1 || p.omul != 1 || p.ooy != 0 || p.oox != 0) return RSG_OK;
+  if (p.Hout != p.Hin || p.Wout != p.Win || p.oH != p.Hin || p.oW != p.Win) return RSG_OK;
+  if (p.Cout % 16 != 0 || p.in_cs % 8 != 0 || p.in_co % 8 != 0 || p.out_cs % 8 != 0 || p.out_co % 8 != 0) return RSG_OK;
+  for (int t = 0; t < p.ntaps && t < 16; ++t)
+    if (p.dy[t] < -1 || p.dy[t] > 1 || p.dx[t] < -1 || p.dx[t] > 1) return RSG_OK;
+  for (int q = 0; q < p.nres; ++q)
+    if (p.res[q].cs % 8 != 0 || p.res[q].co % 8 != 0) return RSG_OK;
+  WsCfg c;
+  if (!ws_config(p.Cin, p.CoutPad, p.ntaps, p.Hin, p.Win, &c)) return RSG_OK;
+  if (p.M == 0) { *handled = 1; return RSG_OK; }
+  if ((long long)p.N * (p.Hin + 1) * (p.Win + 1) >= (1ll << 31)) return RSG_OK;
+
+  WsP k;
+  memset(&k, 0, sizeof(k));
+  k.w = p.w_tc5; k.bias = p.bias; k.Cin = p.Cin; k.NS = c.NS; k.Cout = p.Cout;
+  k.KC = c.KC; k.nchunks = p.Cin / c.KC; k.S = c.S; k.T = c.T; k.nimg = c.nimg;
+  k.ntaps = p.ntaps;
+  k.H = p.Hin; k.W = p.Win; k.P = p.Win + 1; k.pitch = (p.Hin + 1) * k.P;
+  for (int t = 0; t < p.ntaps; ++t) k.tapoff[t] = (1 + p.dy[t]) * k.P + (1 + p.dx[t]);
+  // magic = ceil(2^32 / d): exact for n * d < 2^32 (n < 512 here)
+  k.magic_pitch = k.pitch > 1 ? (uint32_t)(((1ull << 32) + k.pitch - 1) / k.pitch) : 0u;
+  k.magic_P = k.P > 1 ? (uint32_t)(((1ull << 32) + k.P - 1) / k.P) : 0u;
+  k.N = p.N; k.nsuper = (p.N + c.nimg - 1) / c.nimg;
+  k.out = p.out; k.out_cs = p.out_cs; k.out_co = p.out_co;
+  k.nres = p.nres;
+  for (int q = 0; q < p.nres; ++q) k.res[q] = p.res[q];
+  k.relu = p.relu;
+  k.plane_bytes = c.plane_bytes; k.a_bytes = c.a_bytes; k.b_off = c.b_off; k.b_tap_bytes = c.b_tap_bytes;
+  k.stage_bytes = c.stage_bytes;
+  uint32_t cols = 32;
+  while (cols < (uint32_t)(c.T * c.NS)) cols <<= 1;
+  k.tmem_cols = cols;
+  const size_t smem = (size_t)c.S * c.stage_bytes + 128;
+  const int nslices = p.CoutPad / c.NS;
+
+  static bool attr_done = false;
+  if (!attr_done) {
+    RSG_CUDA(cudaFuncSetAttribute(conv_ws_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, WS_SMEM_BUDGET));
+    RSG_CUDA(cudaFuncSetAttribute(conv_ws_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
+    attr_done = true;
+  }
+  static const bool dbg = getenv("RSG_DEBUG") != nullptr;
+  if (dbg) fprintf(stderr, "[ws] Cin=%d Cout=%d taps=%d %dx%d NS=%d nimg=%d T=%d S=%d stage=%u smem=%zu nsuper=%d\n", p.Cin,
+                   p.CoutPad, p.ntaps, p.Hin, p.Win, c.NS, c.nimg, c.T, c.S, c.stage_bytes, smem, k.nsuper);
+  int gx = rsg_num_sms() / nslices;
+  if (gx > k.nsuper) gx = k.nsuper;
+  if (gx < 1) gx = 1;
+  dim3 grid((unsigned)gx, (unsigned)nslices);
+  CUtensorMap map;
+  memset(&map, 0, sizeof(map));
+  { int rc = make_flat_map(p, c, &map); if (rc) return rc; }
+  conv_ws_kernel<<<grid, WS_THREADS, smem, s>>>(map, k);
+  RSG_LAUNCH_CHECK();
+  *handled = 1;
+  return RSG_OK;
+}

@@ -147,6 +147,17 @@ int run_conv(const rsg_conv_desc& d, const RunCtx& c, int N, cudaStream_t s, int
     if (rc) return rc;
     if (handled) return RSG_OK;
   }
+  if (d.engine == 3) {
+    // w_tc5 holds the weight-streaming kernel's packing (NS from rsg_conv_ws_config)
+    int handled = 0;
+    rc = conv_ws_launch(p, s, &handled);
+    if (rc) return rc;
+    if (handled) {
+      if (used_tc5) *used_tc5 = 2;
+      return RSG_OK;
+    }
+    return conv_mma_launch(p, s);
+  }
   if (d.engine != 1) {
     int handled = 0;
     rc = conv_tc5_launch(p, s, &handled);
@@ -374,7 +385,7 @@ extern "C" int rsg_plan_profile(rsg_plan* p, void* stream, void* const* ext, int
     rc = run_op(op, c, nb, n_crops, s, &tc5);
     cudaEventRecord(ev[2 * i + 1], s);
     if (op.kind == OP_CONV) {
-      if (tc5) kind[i] = 2;
+      if (tc5) kind[i] = tc5 == 2 ? 9 : 2;
       flops[i] = 2.0 * op.conv.ntaps * op.conv.Cin * op.conv.Cout * (double)op.conv.Hout * op.conv.Wout * nb;
     } else if (op.kind == OP_ATTN) {
       flops[i] = 4.0 * (double)op.i[6] * op.i[6] * op.i[7] * nb;

@@ -82,6 +82,50 @@ def test_conv_vs_torch(cin, cout, k, stride, H, W, relu, use_res):
     _lib.lib().rsg_plan_destroy(h)
 
 
+WS_CASES = [
+    # Cin, Cout, k, H, W, N, nres   (engine=3: the weight-streaming tcgen05 kernel, conv_ws.cu)
+    (128, 128, 3, 16, 12, 5, 1),      # 2 images / supertile, ragged last supertile
+    (256, 256, 3, 8, 6, 5, 1),        # 8 images / supertile (3 of them out of bounds), 2 N-slices
+    (256, 256, 3, 8, 6, 21, 0),
+    (128, 256, 3, 8, 6, 16, 2),
+    (384, 384, 3, 12, 9, 7, 1),       # W48 branch 3
+    (128, 128, 3, 16, 12, 700, 1),    # 350 supertiles > 148 CTAs: several per CTA (barrier phases wrap)
+    (1152, 128, 1, 8, 6, 9, 0),       # 1x1 through the same path
+]
+
+
+@pytest.mark.parametrize('cin,cout,k,H,W,N,nres', WS_CASES)
+def test_conv_ws_vs_torch(cin, cout, k, H, W, N, nres):
+    g = torch.Generator().manual_seed(cin * 7 + cout + N)
+    x = torch.randn(N, cin, H, W, generator=g).bfloat16().float()
+    w = (torch.randn(cout, cin, k, k, generator=g) / (cin * k * k) ** 0.5).bfloat16().float()
+    b = torch.randn(cout, generator=g) * 0.1
+    rs = [torch.randn(N, cout, H, W, generator=g).bfloat16().float() for _ in range(nres)]
+    pb = PlanBuilder(N, reuse=False)
+    xin = pb.buf('x', H, W, cin + 8)
+    rbs = [pb.buf(f'r{i}', H, W, cout) for i in range(nres)]
+    ob = pb.buf('o', H, W, cout + 16)
+    pb.conv(View(xin, 8, cin), w.double().numpy(), b.double().numpy(), relu=True, dst=View(ob, 8, cout),
+            res=[(View(rb), 0) for rb in rbs], engine=3)
+    assert pb.ops[-1][1]['engine'] == 3
+    h = _run(pb, N)
+    pb.tensor_of(xin)[:N, ..., 8:] = x.permute(0, 2, 3, 1).cuda().bfloat16()
+    pb.tensor_of(xin)[:N, ..., :8] = 1e4        # a neighbouring channel slice must not leak in
+    for rb, r in zip(rbs, rs):
+        pb.tensor_of(rb)[:N] = r.permute(0, 2, 3, 1).cuda().bfloat16()
+    pb.tensor_of(ob).fill_(7.0)
+    _exec(h, N)
+    ref = F.conv2d(x.cuda(), w.cuda(), b.cuda(), 1, k // 2)
+    for r in rs:
+        ref = ref + r.cuda()
+    ref = F.relu(ref).cpu()
+    got = pb.tensor_of(ob)[:N, ..., 8:8 + cout].float().permute(0, 3, 1, 2).cpu()
+    err = (got - ref).abs().max().item()
+    assert err <= 2e-2 * max(ref.abs().max().item(), 1.0), err
+    assert torch.all(pb.tensor_of(ob)[:N, ..., :8] == 7.0) and torch.all(pb.tensor_of(ob)[:N, ..., 8 + cout:] == 7.0)
+    _lib.lib().rsg_plan_destroy(h)
+
+
 def test_conv_fp32_nchw_output_and_upsampled_residuals():
     N, cin, K, H, W = 3, 32, 17, 16, 12
     g = torch.Generator().manual_seed(1)
