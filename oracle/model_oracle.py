@@ -242,11 +242,12 @@ def rsgnet_forward(sd, cfg, x, stages=None, relation_target=None):
     if up_scale > 1:
         multi = F.interpolate(multi, scale_factor=2, mode="bilinear", align_corners=True)
         limbs = F.interpolate(limbs, scale_factor=2, mode="bilinear", align_corners=True)
+    limbs_logits = limbs
     limbs = torch.sigmoid(limbs)
     if relation_target is not None:
         rel_scores = ((relation_target - rel_scores) ** 2).mean(dim=(1, 2))
     if stages is not None:
-        stages.update(vis=vis, type=typ, final_vis=fv, relation=rel, kpt_feat=kf)
+        stages.update(vis=vis, type=typ, final_vis=fv, relation=rel, kpt_feat=kf, limbs_logits=limbs_logits)
     return multi, kpt, limbs, rel_scores
 
 

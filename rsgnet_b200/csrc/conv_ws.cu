@@ -20,9 +20,9 @@
 // activation planes of the chunk plus the weights of all taps for that chunk ([tap][KC/8][NS][8],
 // bulk copies), and all T tiles consume the stage, so the weight stream is amortised over 512 pixels.
 //
-// Warp roles (640 threads, one persistent CTA per SM): warps 0-1 issue MMAs (tiles t = warp mod 2, so
-// two instruction streams feed the tensor pipe, profiles/r1_notes.md §1), warp 2 = TMA producer, warp 3
-// owns the TMEM allocation, warps 4-19 = two epilogue groups of 8 warps (tile parity), each warp one
+// Warp roles (608 threads, one persistent CTA per SM): warps 0-1 issue MMAs (tiles t = warp mod 2, so
+// two instruction streams feed the tensor pipe, profiles/r1_notes.md §1), warp 2 = TMA producer and
+// owner of the TMEM allocation, warps 3-18 = two epilogue groups of 8 warps (tile parity), each warp one
 // TMEM lane quarter and one half of the NS columns: +bias, +residual terms, ReLU, bf16 NHWC stores.
 //
 // Reference ops subsumed: Conv2d(3x3|1x1, s1, bias=False) + BatchNorm2d(eval) [+ residual] [+ ReLU] of
@@ -33,8 +33,8 @@
 namespace {
 using namespace umma;
 
-constexpr int WS_THREADS = 640;
-constexpr int WS_EPI_WARP0 = 4;
+constexpr int WS_THREADS = 608;                // 19 warps: 104 registers per thread
+constexpr int WS_EPI_WARP0 = 3;
 constexpr int WS_MAX_S = 8;
 constexpr int WS_MAX_T = 4;
 constexpr int WS_SMEM_BUDGET = 225 * 1024;
@@ -55,7 +55,16 @@ struct WsP {
   ResP res[4];
   int relu;
   uint32_t plane_bytes, a_bytes, b_off, b_tap_bytes, stage_bytes, tmem_cols;
+  long long* dbg;       // debug timeline of CTA (0,0): globaltimer stamps [16] or nullptr
+  int skip;             // debug: bit0 no loads, bit1 one tap only, bit2 no residual loads / stores
 };
+
+__device__ __forceinline__ long long gtime() {
+  long long t;
+  asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
+  return t;
+}
+#define WS_STAMP(i) do { if (p.dbg && blockIdx.x == 0 && blockIdx.y == 0) p.dbg[i] = gtime(); } while (0)
 
 __global__ void __launch_bounds__(WS_THREADS, 1)
 conv_ws_kernel(const __grid_constant__ CUtensorMap in_map, const WsP p) {
@@ -72,6 +81,7 @@ conv_ws_kernel(const __grid_constant__ CUtensorMap in_map, const WsP p) {
   const int slice = blockIdx.y;
 
   if (threadIdx.x == 0) {
+    WS_STAMP(0);
     for (int i = 0; i < p.S; ++i) { mbar_init(BAR(B_FULL + i), 1); mbar_init(BAR(B_EMPTY + i), 2); }
     for (int i = 0; i < p.T; ++i) { mbar_init(BAR(B_ACCF + i), 1); mbar_init(BAR(B_ACCE + i), 8); }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -87,7 +97,7 @@ conv_ws_kernel(const __grid_constant__ CUtensorMap in_map, const WsP p) {
     }
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
   }
-  if (warp == 3) {
+  if (warp == 2) {
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_base_slot)), "r"(p.tmem_cols) : "memory");
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
   }
@@ -96,6 +106,7 @@ conv_ws_kernel(const __grid_constant__ CUtensorMap in_map, const WsP p) {
   asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
   const uint32_t tmem_base = tmem_base_slot;
   const int first = blockIdx.x, step = gridDim.x;
+  if (threadIdx.x == 0) WS_STAMP(1);
 
   if (warp == 2) {
     // ===================== producer: one TMA box + ntaps bulk copies per stage =====================
@@ -111,12 +122,15 @@ conv_ws_kernel(const __grid_constant__ CUtensorMap in_map, const WsP p) {
           const uint32_t s = it % (uint32_t)p.S;
           mbar_wait(BAR(B_EMPTY + s), ((it / (uint32_t)p.S) & 1) ^ 1);
           const uint32_t dst = sbase + s * p.stage_bytes;
+          if (p.skip & 1) { mbar_arrive(BAR(B_FULL + s)); continue; }
           mbar_arrive_expect_tx(BAR(B_FULL + s), tx_bytes);
           tma_load_5d(dst, &in_map, BAR(B_FULL + s), 0, -1, -1, u * p.nimg, c * (p.KC >> 3));
           const unsigned char* wc = wsl + (size_t)c * p.b_tap_bytes;
           for (int tp = 0; tp < p.ntaps; ++tp)
             bulk_load(dst + p.b_off + (uint32_t)tp * p.b_tap_bytes, wc + (size_t)tp * w_tap_stride, p.b_tap_bytes,
                       BAR(B_FULL + s));
+          if (it == 0) WS_STAMP(2);
+          WS_STAMP(3);
         }
       }
     }
@@ -136,6 +150,7 @@ conv_ws_kernel(const __grid_constant__ CUtensorMap in_map, const WsP p) {
       for (int c = 0; c < p.nchunks; ++c, ++it) {
         const uint32_t s = it % (uint32_t)p.S;
         mbar_wait(BAR(B_FULL + s), (it / (uint32_t)p.S) & 1);
+        if (warp == 0 && lane == 0) { if (it == 0) WS_STAMP(4); if (it == (uint32_t)p.nchunks) WS_STAMP(6); }
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
         const uint32_t stage16 = (sbase + s * p.stage_bytes) >> 4;
         const uint32_t b_stage = (stage16 + (p.b_off >> 4)) | lo_lbo_b;
@@ -148,7 +163,8 @@ conv_ws_kernel(const __grid_constant__ CUtensorMap in_map, const WsP p) {
             const uint32_t d_tmem = tmem_base + (uint32_t)(t * p.NS);
             const uint32_t a_tile = (stage16 + 128u * (uint32_t)t) | lo_lbo_a;
             uint32_t acc = c > 0;
-            for (int tp = 0; tp < p.ntaps; ++tp) {
+            const int ntp = (p.skip & 2) ? 1 : p.ntaps;
+            for (int tp = 0; tp < ntp; ++tp) {
               uint32_t alo = a_tile + (uint32_t)p.tapoff[tp];
               uint32_t blo = b_stage + (uint32_t)tp * b_tapstep;
               for (int kc = 0; kc < kc2n; ++kc) {
@@ -163,17 +179,18 @@ conv_ws_kernel(const __grid_constant__ CUtensorMap in_map, const WsP p) {
           umma_commit(BAR(B_EMPTY + s));                    // stage free once this warp's MMAs retire
         }
         __syncwarp();
+        if (warp == 0 && lane == 0) { if (it == (uint32_t)p.nchunks - 1) WS_STAMP(5); WS_STAMP(7); }
       }
     }
   } else if (warp >= WS_EPI_WARP0) {
-    // ===================== epilogue (warps 4 .. 19) =====================
+    // ===================== epilogue (warps 3 .. 18) =====================
     const int eidx = (warp - WS_EPI_WARP0) >> 2;    // 0..3
     const int egroup = eidx & 1;
     const int q = warp & 3;                         // TMEM lane quarter (hardware rule: warp % 4)
     const int ncol = p.NS >> 1;
     const int cbeg = (eidx >> 1) ? ncol : 0;
     const int gch0 = slice * p.NS + cbeg;
-    const int nres = p.nres;
+    const int nres = (p.skip & 4) ? 0 : p.nres;
     const float* biasp = sBias + cbeg;
     bf16* const outp = p.out + p.out_co + gch0;
     const uint32_t tq = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)cbeg;
@@ -190,18 +207,27 @@ conv_ws_kernel(const __grid_constant__ CUtensorMap in_map, const WsP p) {
         const bool ok = i < (uint32_t)p.nimg && n < (uint32_t)p.N && y < (uint32_t)p.H && x < (uint32_t)p.W;
         const uint32_t ooff = ((n * (uint32_t)p.H + y) * (uint32_t)p.W + x) * (uint32_t)p.out_cs;
         const bf16* r0p = nullptr;
-        uint4 pre0 = make_uint4(0, 0, 0, 0), pre1 = pre0;
+        // the whole residual row segment of this thread (first 64 columns) is fetched BEFORE waiting for the
+        // accumulator: the epilogue warps are idle during the K loop, so the L2 latency is free
+        uint4 pre[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) pre[j] = make_uint4(0, 0, 0, 0);
         if (nres > 0 && ok && gch0 < p.Cout) {
           const ResP& rr = p.res[0];
           r0p = rr.p + rr.co + gch0 +
                 (((rr.bs0 ? 0u : n) * (uint32_t)rr.H + (y >> rr.shift)) * (uint32_t)rr.W + (x >> rr.shift)) * (uint32_t)rr.cs;
-          pre0 = __ldg(reinterpret_cast<const uint4*>(r0p));
-          pre1 = __ldg(reinterpret_cast<const uint4*>(r0p) + 1);
+#pragma unroll
+          for (int j = 0; j < 8; ++j)
+            if (j * 8 < ncol) pre[j] = __ldg(reinterpret_cast<const uint4*>(r0p) + j);
         }
         mbar_wait(bar_accf + 8u * (uint32_t)t, st & 1);
+        if (warp == WS_EPI_WARP0 && lane == 0 && st == 0 && t == egroup) WS_STAMP(8);
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
         const uint32_t taddr = tq + (uint32_t)(t * p.NS);
-        for (int c0 = 0; c0 < ncol; c0 += 16) {
+#pragma unroll
+        for (int ci = 0; ci < 8; ++ci) {
+          const int c0 = ci * 16;
+          if (c0 >= ncol) break;
           uint32_t v[16];
           tmem_ld16(taddr + c0, v);
           asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
@@ -222,7 +248,7 @@ conv_ws_kernel(const __grid_constant__ CUtensorMap in_map, const WsP p) {
             f[j4 * 4 + 3] = __uint_as_float(v[j4 * 4 + 3]) + bb.w;
           }
           if (nres > 0) {
-            if (c0 == 0) { add_res8(f, pre0); add_res8(f + 8, pre1); }
+            if (c0 < 64) { add_res8(f, pre[(c0 >> 3) & 7]); add_res8(f + 8, pre[((c0 >> 3) + 1) & 7]); }
             else {
               add_res8(f, __ldg(reinterpret_cast<const uint4*>(r0p + c0)));
               add_res8(f + 8, __ldg(reinterpret_cast<const uint4*>(r0p + c0) + 1));
@@ -248,18 +274,39 @@ conv_ws_kernel(const __grid_constant__ CUtensorMap in_map, const WsP p) {
 #pragma unroll
             for (int k2 = 0; k2 < 4; ++k2) { h0[k2] = __hmax2(h0[k2], z); h1[k2] = __hmax2(h1[k2], z); }
           }
-          uint4* op = reinterpret_cast<uint4*>(outp + ooff + c0);
-          op[0] = o0;
-          op[1] = o1;
+          if (!(p.skip & 4)) {
+            uint4* op = reinterpret_cast<uint4*>(outp + ooff + c0);
+            op[0] = o0;
+            op[1] = o1;
+          }
         }
+        if (warp == WS_EPI_WARP0 && lane == 0) { if (st == 0 && t == egroup) WS_STAMP(9); WS_STAMP(10); }
       }
     }
   }
   // ---- teardown
   asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
   __syncthreads();
-  if (warp == 3) {
+  if (threadIdx.x == 0) WS_STAMP(11);
+  if (warp == 2) {
     asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(p.tmem_cols) : "memory");
+  }
+}
+
+long long* g_dbg_buf = nullptr;
+void ws_dump_timeline() {
+  long long h[64 * 16];
+  if (cudaDeviceSynchronize() != cudaSuccess) return;
+  if (cudaMemcpy(h, g_dbg_buf, sizeof(h), cudaMemcpyDeviceToHost) != cudaSuccess) return;
+  long long t0 = 0;
+  for (int i = 0; i < 64; ++i) if (h[i * 16] && (!t0 || h[i * 16] < t0)) t0 = h[i * 16];
+  fprintf(stderr, "[ws timeline of CTA(0,0), ns] start prologue_done first_issue last_issue | mma_first_full mma_unit0_last_issued "
+                  "mma_unit1_first_full mma_last_issued | epi_first_accf epi_first_tile_done epi_last_done | teardown\n");
+  for (int i = 0; i < 64; ++i) {
+    if (!h[i * 16]) continue;
+    fprintf(stderr, "%2d:", i);
+    for (int j = 0; j < 12; ++j) fprintf(stderr, " %7lld", h[i * 16 + j] ? h[i * 16 + j] - t0 : -1);
+    fprintf(stderr, "\n");
   }
 }
 
@@ -281,7 +328,9 @@ bool ws_config(int Cin, int CoutPad, int ntaps, int H, int W, WsCfg* c) {
   int nimg = tmax * 128 / pitch;
   if (nimg < 1) return false;
   if (nimg > 64) nimg = 64;
-  c->NS = NS; c->KC = 16; c->nimg = nimg;
+  c->NS = NS; c->nimg = nimg;
+  c->KC = 16;
+  { const char* e = getenv("RSG_WS_KC"); if (e && Cin % atoi(e) == 0) c->KC = atoi(e); }
   c->T = (nimg * pitch + 127) / 128;
   c->plane_bytes = (uint32_t)nimg * pitch * 16u;
   c->a_bytes = (uint32_t)(c->KC / 8) * c->plane_bytes;
@@ -359,6 +408,16 @@ int conv_ws_launch(const ConvP& p, cudaStream_t s, int* handled) {
   k.nres = p.nres;
   for (int q = 0; q < p.nres; ++q) k.res[q] = p.res[q];
   k.relu = p.relu;
+  { const char* e = getenv("RSG_WS_SKIP"); k.skip = e ? atoi(e) : 0; }
+  static int dbg_launch = 0;
+  if (getenv("RSG_WS_TIMELINE")) {
+    if (!g_dbg_buf) {
+      cudaMalloc(&g_dbg_buf, 64 * 16 * sizeof(long long));
+      cudaMemset(g_dbg_buf, 0, 64 * 16 * sizeof(long long));
+      atexit(ws_dump_timeline);
+    }
+    k.dbg = g_dbg_buf + (size_t)(dbg_launch++ % 64) * 16;
+  }
   k.plane_bytes = c.plane_bytes; k.a_bytes = c.a_bytes; k.b_off = c.b_off; k.b_tap_bytes = c.b_tap_bytes;
   k.stage_bytes = c.stage_bytes;
   uint32_t cols = 32;
