@@ -125,6 +125,10 @@ typedef struct rsg_conv_desc {
   int32_t engine;              /* 0 = auto, 1 = force mma.sync path, 2 = force tcgen05 path,
                                   3 = weight-streaming tcgen05 path (w_tc5 packed with the NS of
                                   rsg_conv_ws_config) */
+  int32_t pixel_shuffle_c;     /* > 0 (tcgen05 path only, omul = 2): the Cout = 4 * pixel_shuffle_c output
+                                  columns are 4 sub-pixel phases of pixel_shuffle_c channels: column c goes
+                                  to out pixel (2y + (c / psc) / 2, 2x + (c / psc) % 2), channel c % psc.
+                                  ConvTranspose2d(4, 2, 1) as ONE 3x3 conv (pose_rsgnet.py:733-744) */
 } rsg_conv_desc;
 
 int rsg_plan_create(rsg_plan** out, int chunk);
@@ -174,10 +178,11 @@ int rsg_plan_profile(rsg_plan*, void* stream, void* const* ext, int n_ext, int n
 /* Kernel launches issued by the last rsg_plan_run (graph nodes when replayed). */
 int rsg_plan_last_launches(const rsg_plan*);
 
-/* Tiling the tcgen05 conv kernel uses for a shape: output channels per CTA (NS), channels per TMA
+/* mode: 0 = 1x1 stride 1, 1 = taps inside the 3x3 neighbourhood, stride 1, 2 = the same at stride 2.
+ * Tiling the tcgen05 conv kernel uses for a shape: output channels per CTA (NS), channels per TMA
  * halo stage (KC) and ring depth (S).  Returns 0 when the shape is not covered (the generic kernel
  * runs instead).  The host packer needs NS to lay w_tc5 out as [CoutPad/NS][ntaps][Cin/8][NS][8]. */
-int rsg_conv_tc5_config(int Cin, int CoutPad, int ntaps, int halo, int* NS, int* KC, int* S);
+int rsg_conv_tc5_config(int Cin, int CoutPad, int ntaps, int mode, int* NS, int* KC, int* S);
 
 /* Weight-streaming tcgen05 conv kernel (many channels, small maps: the stage-3/4 low-resolution
  * branches): returns 1 and the output channels per CTA (NS) when it covers a stride-1 conv of this

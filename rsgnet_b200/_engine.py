@@ -153,7 +153,8 @@ class PlanBuilder:
         self.ops.append((kind, payload, self.aux))
 
     def conv(self, src, w_oihw, bias, stride=1, relu=False, dst=None, res=(), taps=None,
-             out_f32=None, omul=1, ooy=0, oox=0, out_hw=None, name='conv', cout=None, engine=0):
+             out_f32=None, omul=1, ooy=0, oox=0, out_hw=None, name='conv', cout=None, engine=0,
+             pixel_shuffle_c=0):
         """w_oihw: folded fp64 [Cout, Cin, kh, kw] (or [ntaps, Cout, Cin] with explicit taps)."""
         if taps is None:
             co_, ci_, kh, kw = w_oihw.shape
@@ -177,12 +178,13 @@ class PlanBuilder:
         Hout = (Hin - 1) // stride + 1 if out_hw is None else out_hw[0]
         Wout = (Win - 1) // stride + 1 if out_hw is None else out_hw[1]
         w_tc5 = None
-        tc5_ok = (stride == 1 and omul == 1 and out_f32 is None and cin % 16 == 0 and cout % 8 == 0
-                  and all(abs(dy) <= 1 and abs(dx) <= 1 for dy, dx in taps) and len(taps) <= 9)
+        tc5_ok = (stride in (1, 2) and (omul == 1 or not res) and out_f32 is None and cin % 16 == 0
+                  and cout % 8 == 0 and all(abs(dy) <= 1 and abs(dx) <= 1 for dy, dx in taps) and len(taps) <= 9)
         ns = C.c_int()
         # GEMM-shaped layers (K = taps*Cin >= 1152, >= 128 output channels) on maps small enough for the
         # flat formulation: weight-streaming kernel
-        want_ws = engine == 3 or (engine == 0 and len(taps) * cin >= 1152 and cout_pad >= 128)
+        want_ws = (stride == 1 and omul == 1 and
+                   (engine == 3 or (engine == 0 and len(taps) * cin >= 1152 and cout_pad >= 128)))
         if (tc5_ok and want_ws and dst is not None
                 and _lib.lib().rsg_conv_ws_config(cin, cout_pad, len(taps), Hin, Win, C.byref(ns))):
             NS = ns.value
@@ -191,11 +193,10 @@ class PlanBuilder:
             engine = 3
         elif engine == 3:
             raise ValueError(f'{name}: shape not covered by the weight-streaming kernel')
-        elif (stride == 1 and omul == 1 and out_f32 is None and cin % 16 == 0 and cout % 8 == 0
-                and all(abs(dy) <= 1 and abs(dx) <= 1 for dy, dx in taps) and len(taps) <= 9):
-            halo = int(any(dy != 0 or dx != 0 for dy, dx in taps))
+        elif tc5_ok:
+            mode = 2 if stride == 2 else int(any(dy != 0 or dx != 0 for dy, dx in taps))
             ns, kc, st = C.c_int(), C.c_int(), C.c_int()
-            if _lib.lib().rsg_conv_tc5_config(cin, cout_pad, len(taps), halo, C.byref(ns), C.byref(kc), C.byref(st)):
+            if _lib.lib().rsg_conv_tc5_config(cin, cout_pad, len(taps), mode, C.byref(ns), C.byref(kc), C.byref(st)):
                 # [slice][tap][Cin/8][NS][8]: the K-major core-matrix order the kernel bulk-copies
                 NS = ns.value
                 wt = wp[:, :, :cin].reshape(len(taps), cout_pad // NS, NS, cin // 8, 8)
@@ -203,7 +204,9 @@ class PlanBuilder:
         payload = dict(src=src, w=self.const(_bf16_bits(wp)), w_tc5=w_tc5, bias=self.const(bp), cin=cin,
                        cout=cout, cout_pad=cout_pad, taps=taps, stride=stride, Hout=Hout, Wout=Wout,
                        dst=dst, out_f32=out_f32, res=list(res), relu=relu, omul=omul, ooy=ooy,
-                       oox=oox, name=name, engine=engine)
+                       oox=oox, name=name, engine=engine, psc=pixel_shuffle_c)
+        if pixel_shuffle_c and w_tc5 is None:
+            raise ValueError(f'{name}: pixel-shuffle output needs the tcgen05 kernel')
         reads = [src.buf] + [r[0].buf for r in res]
         writes = [dst.buf if dst is not None else None,
                   out_f32 if isinstance(out_f32, Buf) else None]
@@ -302,6 +305,7 @@ def emit(builder, plan):
             for q, (view, shift) in enumerate(p['res']):
                 d.res[q] = _res(view, shift, cp)
             d.relu = int(p['relu'])
+            d.pixel_shuffle_c = int(p.get('psc', 0))
             _lib.check(L.rsg_plan_add_conv(plan, C.byref(d)))
         elif kind == 'stem':
             _lib.check(L.rsg_plan_add_stem(plan, _ref(p['x'], cp), p['H'], p['W'], _ref(p['w'], cp),
@@ -464,6 +468,26 @@ def _deconv4(pb, P, name, src, dst):
     s, b = P.sub(name).bn('1')
     if w.shape[2] != 4:
         raise ValueError('only FINAL_DECONV_KERNEL_SIZE=4 is supported')
+    cin, cout = w.shape[0], w.shape[1]
+    ns, kc, st = C.c_int(), C.c_int(), C.c_int()
+    if (cout % 16 == 0 and cin % 16 == 0 and dst.co == 0 and dst.C == cout and
+            _lib.lib().rsg_conv_tc5_config(cin, _round_up(4 * cout, 32), 9, 1, C.byref(ns), C.byref(kc), C.byref(st))):
+        # ONE 3x3 conv with 4*Cout output columns (phase-major; taps a phase does not use are zero) whose
+        # epilogue pixel-shuffles: the input is read once instead of four times
+        taps9 = [(dy, dx) for dy in (-1, 0, 1) for dx in (-1, 0, 1)]
+        wf = np.zeros((9, 4 * cout, cin))
+        for py in (0, 1):
+            ys = [(1, 0), (3, -1)] if py == 0 else [(0, 1), (2, 0)]
+            for px in (0, 1):
+                xs = [(1, 0), (3, -1)] if px == 0 else [(0, 1), (2, 0)]
+                ph = 2 * py + px
+                for ky, dy in ys:
+                    for kx, dx in xs:
+                        wf[taps9.index((dy, dx)), ph * cout:(ph + 1) * cout, :] = (w[:, :, ky, kx] * s[None, :]).T
+        pb.conv(src, wf, np.tile(b, 4), relu=True, dst=dst, taps=taps9, omul=2, out_hw=(src.H, src.W),
+                name=P.prefix + name + '.fused', pixel_shuffle_c=cout)
+        pb.flops_per_fwd -= 2 * (9 * 4 - 16) * cin * cout * src.H * src.W      # zero taps are not credited
+        return dst
     for py in (0, 1):
         ys = [(1, 0), (3, -1)] if py == 0 else [(0, 1), (2, 0)]
         for px in (0, 1):

@@ -32,7 +32,7 @@ class ConvDesc(C.Structure):
                 ('out', Ref), ('out_cs', C.c_int32), ('out_co', C.c_int32), ('oH', C.c_int32),
                 ('oW', C.c_int32), ('omul', C.c_int32), ('ooy', C.c_int32), ('oox', C.c_int32),
                 ('out_f32', Ref), ('nres', C.c_int32), ('res', Res * MAX_RES),
-                ('relu', C.c_int32), ('engine', C.c_int32)]
+                ('relu', C.c_int32), ('engine', C.c_int32), ('pixel_shuffle_c', C.c_int32)]
 
 
 def null_ref():

@@ -20,6 +20,7 @@ struct ConvP {
   int Hout, Wout;
   bf16* out;
   int out_cs, out_co, oH, oW, omul, ooy, oox;
+  int psC;              // > 0: pixel-shuffle output (tcgen05 kernel only): column c -> phase c / psC, channel c % psC
   float* out_f32;
   int nres;
   ResP res[4];

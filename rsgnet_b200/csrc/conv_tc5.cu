@@ -46,10 +46,17 @@ struct Tc5P {
   int NMMA;             // MMA-issuing warps: 2 or 4
   int EW;               // epilogue warps: 4, or 8 (two column halves per TMEM lane quarter)
   int ntaps;
-  int8_t dy[9], dx[9];
-  int tapoff[9];        // A start-address offset of each tap inside the halo patch, 16-byte units
-  int halo;             // 1 for 3x3, 0 for 1x1
-  int H, W;
+  // per-tap A descriptor pieces: low word = (start offset inside the stage | LBO << 16) in 16-byte units,
+  // high word = SBO | version, k16 step in 16-byte units.  Stride 1: every tap addresses the one halo
+  // patch; stride 2: the patch of its (row parity, column parity) phase.
+  uint32_t tap_lo[9], tap_hi[9], tap_kstep[9];
+  int halo;             // 1 for 3x3, 0 for 1x1 (stride 1)
+  int stride;           // 1, or 2: four phase patches per stage, loaded with TMA element strides of 2
+  uint32_t ph_off[4];   // stride 2: byte offset of each phase patch inside a stage
+  int H, W;             // iteration space (= output of the conv before the omul/oo mapping)
+  int oH, oW, omul, ooy, oox;   // out pixel = (y*omul+ooy, x*omul+oox) in an oH x oW map
+  int psC;              // > 0: pixel shuffle -- output column c belongs to phase c / psC (oy = 2y + (ph>>1),
+                        // ox = 2x + (ph&1)) and channel c % psC: ConvTranspose(4,2,1) as ONE 3x3 conv
   const bf16* in;       // NHWC, channel stride in_cs, first channel in_co
   int in_cs, in_co;
   int tiles_x, tiles_y; // per image
@@ -60,17 +67,19 @@ struct Tc5P {
   int nres;
   ResP res[4];
   int relu;
-  uint32_t w_bytes, stage_bytes, tmem_cols;
+  uint32_t w_bytes, stage_bytes, tx_bytes, tmem_cols;
   long long* dbg;       // debug timeline (CTA 0): [tile][8] clock64 stamps, or nullptr
   int skip;             // debug: bit0 no halo loads, bit1 no MMAs, bit2 no residual loads, bit3 no stores
 };
 
 constexpr int MAX_STAGES = 8;
 constexpr int MAX_ACC = 8;
-constexpr int MAX_CHUNKS = 8;
+constexpr int MAX_CHUNKS = 32;
+
+struct Tc5Maps { CUtensorMap m[4]; };
 
 __global__ void __launch_bounds__(NTHREADS, 1)
-conv_tc5_kernel(const __grid_constant__ CUtensorMap in_map, const Tc5P p) {
+conv_tc5_kernel(const __grid_constant__ Tc5Maps maps, const Tc5P p) {
   extern __shared__ __align__(128) unsigned char smem[];
   __shared__ __align__(8) uint64_t bars[1 + 2 * MAX_STAGES + 2 * MAX_ACC];
   __shared__ uint32_t tmem_base_slot;
@@ -83,8 +92,6 @@ conv_tc5_kernel(const __grid_constant__ CUtensorMap in_map, const Tc5P p) {
   unsigned char* sW = smem;
   unsigned char* sH = smem + p.w_bytes;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int HW_ = TW + 2 * p.halo, HH_ = TH + 2 * p.halo;     // halo patch extent
-  const uint32_t lbo_a = (uint32_t)HW_ * HH_ * 16u, sbo_a = (uint32_t)HW_ * 16u;
   const uint32_t lbo_b = (uint32_t)p.NS * 16u, sbo_b = 128u;
   const int slice = blockIdx.y;
 
@@ -114,7 +121,8 @@ conv_tc5_kernel(const __grid_constant__ CUtensorMap in_map, const Tc5P p) {
     // lands in shared memory as [KC/8][18][10][8ch]; out-of-bounds coordinates are zero-filled, which
     // is the convolution's zero padding.
     if (ptid == 0) {
-      asm volatile("prefetch.tensormap [%0];" ::"l"(&in_map) : "memory");
+      const int nph = p.stride == 2 ? 4 : 1;
+      for (int i = 0; i < nph; ++i) asm volatile("prefetch.tensormap [%0];" ::"l"(&maps.m[i]) : "memory");
       const uint32_t S2 = (uint32_t)(p.S / NMMA);        // each MMA warp owns its own ring of S/NMMA stages
       uint32_t tl = 0, it = 0;
       for (int t = (int)first; t < (int)p.ntiles; t += (int)step, ++tl) {
@@ -127,9 +135,18 @@ conv_tc5_kernel(const __grid_constant__ CUtensorMap in_map, const Tc5P p) {
           mbar_wait(BAR(B_EMPTY + s), ((j / S2) & 1) ^ 1);
           if (p.dbg && blockIdx.x == 0 && blockIdx.y == 0 && it < 64) p.dbg[it * 8 + 0] = clock64();
           if (!(p.skip & 1)) {
-            mbar_arrive_expect_tx(BAR(B_FULL + s), p.stage_bytes);
-            tma_load_5d(smem_u32(sH + (size_t)s * p.stage_bytes), &in_map, BAR(B_FULL + s), 0,
-                        tx * TW - p.halo, ty * TH - p.halo, c * (p.KC >> 3), n);
+            mbar_arrive_expect_tx(BAR(B_FULL + s), p.tx_bytes);
+            const uint32_t dst = smem_u32(sH + (size_t)s * p.stage_bytes);
+            if (p.stride == 1) {
+              tma_load_5d(dst, &maps.m[0], BAR(B_FULL + s), 0, tx * TW - p.halo, ty * TH - p.halo, c * (p.KC >> 3), n);
+            } else {
+              // phase (row parity, column parity): even rows/cols start at the tile origin, odd ones one
+              // element earlier (the -1 taps); the box walks the input with element strides of 2
+#pragma unroll
+              for (int ph = 0; ph < 4; ++ph)
+                tma_load_5d(dst + p.ph_off[ph], &maps.m[ph], BAR(B_FULL + s), 0, 2 * tx * TW - (ph & 1),
+                            2 * ty * TH - (ph >> 1), c * (p.KC >> 3), n);
+            }
           } else {
             mbar_arrive(BAR(B_FULL + s));
           }
@@ -159,12 +176,12 @@ conv_tc5_kernel(const __grid_constant__ CUtensorMap in_map, const Tc5P p) {
     const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(p.NS >> 3) << 17) | ((128u >> 4) << 24);
     mbar_wait(BAR(0), 0);
     const int kc2n = p.KC >> 4;
-    const uint32_t hiA = desc_hi(sbo_a), hiB = desc_hi(sbo_b);
+    const uint32_t hiB = desc_hi(sbo_b);
     const uint32_t a0 = smem_u32(sH), w0 = smem_u32(sW);
-    const uint32_t a_kstep = (2u * lbo_a) >> 4, b_kstep = (2u * lbo_b) >> 4;     // per k16 step, in 16-byte units
+    const uint32_t b_kstep = (2u * lbo_b) >> 4;     // per k16 step, in 16-byte units
     const uint32_t b_tapstep = ((uint32_t)(p.Cin >> 3) * lbo_b) >> 4;
     const uint32_t b_chunkstep = ((uint32_t)(p.KC >> 3) * lbo_b) >> 4;
-    const uint32_t lo_lbo_a = ((lbo_a >> 4) & 0x3FFFu) << 16, lo_lbo_b = ((lbo_b >> 4) & 0x3FFFu) << 16;
+    const uint32_t lo_lbo_b = ((lbo_b >> 4) & 0x3FFFu) << 16;
     for (uint32_t tl = (uint32_t)warp; (long long)first + (long long)tl * step < p.ntiles; tl += NMMA) {
       const int b = tl % p.NACC;
       mbar_wait(BAR(B_ACCE + b), ((tl / p.NACC) & 1) ^ 1);  // accumulator drained by the epilogue
@@ -182,14 +199,15 @@ conv_tc5_kernel(const __grid_constant__ CUtensorMap in_map, const Tc5P p) {
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
         // low descriptor words: (address >> 4) | LBO << 16; adding 16-byte offsets never carries out of
         // the 14-bit address field (shared memory is < 256 KB)
-        const uint32_t a_stage = ((a0 + (uint32_t)s * p.stage_bytes) >> 4) | lo_lbo_a;
+        const uint32_t a_stage = (a0 + (uint32_t)s * p.stage_bytes) >> 4;
         const uint32_t w_chunk = ((w0 >> 4) + (uint32_t)c * b_chunkstep) | lo_lbo_b;
         if (elect_one()) {
           uint32_t acc = c > 0;
           const int ntp = (p.skip & 2) ? 1 : p.ntaps;
           for (int tp = 0; tp < ntp; ++tp) {
-            uint32_t alo = a_stage + (uint32_t)p.tapoff[tp];
+            uint32_t alo = a_stage + p.tap_lo[tp];
             uint32_t blo = w_chunk + (uint32_t)tp * b_tapstep;
+            const uint32_t hiA = p.tap_hi[tp], a_kstep = p.tap_kstep[tp];
             for (int kc = 0; kc < kc2n; ++kc) {
               const uint64_t ad = ((uint64_t)hiA << 32) | alo;
               const uint64_t bd = ((uint64_t)hiB << 32) | blo;
@@ -225,7 +243,7 @@ conv_tc5_kernel(const __grid_constant__ CUtensorMap in_map, const Tc5P p) {
     const int gch0 = slice * p.NS + cbeg;       // first global output channel of this warp
     const int nres = (p.skip & 4) ? 0 : p.nres;
     const float* biasp = sBias + cbeg;
-    bf16* const outp = p.out + p.out_co + gch0;
+    bf16* const outp = p.out + p.out_co;
     const uint32_t tq = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)cbeg;
     const uint32_t bar_accf = opaque(BAR(B_ACCF)), bar_acce = opaque(BAR(B_ACCE));
     for (uint32_t tl = (uint32_t)egroup; ; tl += NEPI) {
@@ -238,7 +256,8 @@ conv_tc5_kernel(const __grid_constant__ CUtensorMap in_map, const Tc5P p) {
       const uint32_t tx = rem - ty * (uint32_t)p.tiles_x;
       const int y = (int)ty * TH + hy, x = (int)tx * TW + wx;
       const bool ok = y < p.H && x < p.W;
-      const uint32_t ooff = ((n * (uint32_t)p.H + (uint32_t)y) * (uint32_t)p.W + (uint32_t)x) * (uint32_t)p.out_cs;
+      const uint32_t ooff = ((n * (uint32_t)p.oH + (uint32_t)(y * p.omul + p.ooy)) * (uint32_t)p.oW +
+                             (uint32_t)(x * p.omul + p.oox)) * (uint32_t)p.out_cs;
       const bf16* r0p = nullptr;
       uint4 pre0, pre1;
       if (nres > 0 && ok && gch0 < p.Cout) {
@@ -302,7 +321,13 @@ conv_tc5_kernel(const __grid_constant__ CUtensorMap in_map, const Tc5P p) {
           for (int k2 = 0; k2 < 4; ++k2) { h0[k2] = __hmax2(h0[k2], z); h1[k2] = __hmax2(h1[k2], z); }
         }
         if (!(p.skip & 8)) {
-          uint4* op = reinterpret_cast<uint4*>(outp + ooff + c0);
+          const uint32_t gc = (uint32_t)(gch0 + c0);
+          uint32_t off = ooff + gc;
+          if (p.psC) {                                       // pixel shuffle: column block -> output phase
+            const uint32_t ph = gc / (uint32_t)p.psC;
+            off = ooff + ((ph >> 1) * (uint32_t)p.oW + (ph & 1)) * (uint32_t)p.out_cs + (gc - ph * (uint32_t)p.psC);
+          }
+          uint4* op = reinterpret_cast<uint4*>(outp + off);
           op[0] = o0;
           op[1] = o1;
         }
@@ -318,42 +343,62 @@ conv_tc5_kernel(const __grid_constant__ CUtensorMap in_map, const Tc5P p) {
   }
 }
 
-int make_halo_map(const ConvP& p, int halo, int KC, CUtensorMap* m) {
+// box = (8 ch, bw px, bh rows, KC/8 planes, 1 crop) over the NHWC activation viewed as (8, W, H, C/8, N),
+// walked with element stride `es` along W and H (es = 2: every other pixel -- one phase of a stride-2 conv)
+int make_patch_map(const ConvP& p, int bw, int bh, int KC, int es, CUtensorMap* m) {
   EncodeTiledFn enc = tensor_map_encoder();
   RSG_REQUIRE(enc, "cuTensorMapEncodeTiled is not available from this driver");
-  const cuuint64_t es = 2;
+  const cuuint64_t esz = 2;
   cuuint64_t dims[5] = {8, (cuuint64_t)p.Win, (cuuint64_t)p.Hin, (cuuint64_t)(p.Cin / 8), (cuuint64_t)p.N};
-  cuuint64_t strides[4] = {(cuuint64_t)p.in_cs * es, (cuuint64_t)p.Win * p.in_cs * es, 16,
-                           (cuuint64_t)p.Hin * p.Win * p.in_cs * es};
-  cuuint32_t box[5] = {8, (cuuint32_t)(TW + 2 * halo), (cuuint32_t)(TH + 2 * halo), (cuuint32_t)(KC / 8), 1};
-  cuuint32_t estr[5] = {1, 1, 1, 1, 1};
+  cuuint64_t strides[4] = {(cuuint64_t)p.in_cs * esz, (cuuint64_t)p.Win * p.in_cs * esz, 16,
+                           (cuuint64_t)p.Hin * p.Win * p.in_cs * esz};
+  // with an element stride the box extent counts SOURCE elements: bw loaded pixels span bw * es of them
+  cuuint32_t box[5] = {8, (cuuint32_t)(bw * es), (cuuint32_t)(bh * es), (cuuint32_t)(KC / 8), 1};
+  cuuint32_t estr[5] = {1, (cuuint32_t)es, (cuuint32_t)es, 1, 1};
   CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 5, (void*)(p.in + p.in_co), dims, strides, box, estr,
                    CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE,
                    CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-  RSG_REQUIRE(r == CUDA_SUCCESS, "cuTensorMapEncodeTiled failed with %d", (int)r);
+  RSG_REQUIRE(r == CUDA_SUCCESS, "cuTensorMapEncodeTiled failed with %d (box %d x %d, stride %d)", (int)r, bw, bh, es);
   return RSG_OK;
+}
+
+// stride-2 phase patches: phase = 2 * (odd rows) + (odd cols); odd phases carry one extra leading row / column
+// (the -1 taps)
+inline uint32_t desc_hi_host(uint32_t sbo_bytes) { return ((sbo_bytes >> 4) & 0x3FFFu) | (1u << 14); }
+inline int ph_rows(int ph) { return TH + (ph >> 1); }
+inline int ph_cols(int ph) { return TW + (ph & 1); }
+inline uint32_t ph_bytes(int ph, int KC) { return ((uint32_t)(KC / 8) * ph_rows(ph) * ph_cols(ph) * 16u + 127u) & ~127u; }
+
+inline int stage_bytes_of(int mode, int kc) {
+  if (mode == 2) return (int)(ph_bytes(0, kc) + ph_bytes(1, kc) + ph_bytes(2, kc) + ph_bytes(3, kc));
+  return (TH + 2 * mode) * (TW + 2 * mode) * kc * 2;
 }
 
 }  // namespace
 
 // Shape -> (NS, KC, S): shared with the host-side packer through rsg_conv_tc5_config().
-extern "C" int rsg_conv_tc5_config(int Cin, int CoutPad, int ntaps, int halo, int* NS, int* KC, int* S) {
-  if (Cin % 16 != 0 || CoutPad % 32 != 0 || ntaps < 1 || ntaps > 9) return 0;
-  int kc = 0;
-  for (int c = 64; c >= 16; c -= 16)
-    if (Cin % c == 0) { kc = c; break; }
-  if (!kc || Cin / kc > MAX_CHUNKS) return 0;
-  const int stage = (TH + 2 * halo) * (TW + 2 * halo) * kc * 2;
+// mode: 0 = 1x1 stride 1, 1 = taps in the 3x3 neighbourhood, stride 1 (halo patch), 2 = 3x3 neighbourhood,
+// stride 2 (four phase patches).
+extern "C" int rsg_conv_tc5_config(int Cin, int CoutPad, int ntaps, int mode, int* NS, int* KC, int* S) {
+  if (Cin % 16 != 0 || CoutPad % 32 != 0 || ntaps < 1 || ntaps > 9 || mode < 0 || mode > 2) return 0;
+  const int budget = 196 * 1024;
   const int cands[4] = {128, 96, 64, 32};
-  for (int i = 0; i < 4; ++i) {
-    const int ns = cands[i];
-    if (ns > CoutPad || CoutPad % ns != 0) continue;
-    const long long wb = (long long)ntaps * Cin * ns * 2;
-    if (wb + 2 * stage > 196 * 1024) continue;
-    int s = MAX_STAGES;                         // even: the two MMA warps own half of the ring each
-    while (s > 2 && wb + (long long)s * stage > 196 * 1024) s -= 2;
-    *NS = ns; *KC = kc; *S = s;
-    return 1;
+  // prefer the widest slice that still leaves >= 4 stages; among the K chunkings the largest with >= 4 stages
+  for (int min_s = 4; min_s >= 2; min_s -= 2) {
+    for (int i = 0; i < 4; ++i) {
+      const int ns = cands[i];
+      if (ns > CoutPad || CoutPad % ns != 0) continue;
+      const long long wb = (long long)ntaps * Cin * ns * 2;
+      for (int kc = 64; kc >= 16; kc -= 16) {
+        if (Cin % kc != 0 || Cin / kc > MAX_CHUNKS) continue;
+        const int stage = stage_bytes_of(mode, kc);
+        if (wb + (long long)min_s * stage > budget) continue;
+        int s = MAX_STAGES;                     // even: the MMA warps own equal parts of the ring
+        while (s > 2 && wb + (long long)s * stage > budget) s -= 2;
+        *NS = ns; *KC = kc; *S = s;
+        return 1;
+      }
+    }
   }
   return 0;
 }
@@ -363,18 +408,23 @@ int conv_tc5_launch(const ConvP& p, cudaStream_t s, int* handled) {
   static const bool disabled = getenv("RSG_DISABLE_TC5") != nullptr;   // A/B switch for debugging
   if (disabled) return RSG_OK;
   if (!p.w_tc5 || !p.out || p.out_f32) return RSG_OK;
-  if (p.stride != 1 || p.omul != 1 || p.ooy != 0 || p.oox != 0) return RSG_OK;
-  if (p.Hout != p.Hin || p.Wout != p.Win || p.oH != p.Hin || p.oW != p.Win) return RSG_OK;
+  if (p.stride != 1 && p.stride != 2) return RSG_OK;
+  if (p.stride == 2 && getenv("RSG_TC5_NO_S2")) return RSG_OK;
+  if (p.omul < 1 || p.oH < p.Hout * p.omul || p.oW < p.Wout * p.omul) return RSG_OK;
+  if (p.Hout != (p.Hin - 1) / p.stride + 1 || p.Wout != (p.Win - 1) / p.stride + 1) return RSG_OK;
+  if (p.omul != 1 && p.nres != 0) return RSG_OK;
+  if (p.psC && (p.psC % 16 != 0 || p.Cout != 4 * p.psC || p.omul != 2 || p.ooy != 0 || p.oox != 0)) return RSG_OK;
   if (p.Cout % 16 != 0 || p.in_cs % 8 != 0 || p.in_co % 8 != 0 || p.out_cs % 8 != 0 || p.out_co % 8 != 0) return RSG_OK;
   int halo = 0;
   for (int t = 0; t < p.ntaps && t < 16; ++t) {
     if (p.dy[t] < -1 || p.dy[t] > 1 || p.dx[t] < -1 || p.dx[t] > 1) return RSG_OK;
     if (p.dy[t] != 0 || p.dx[t] != 0) halo = 1;
   }
+  const int mode = p.stride == 2 ? 2 : halo;
   for (int q = 0; q < p.nres; ++q)
     if (p.res[q].cs % 8 != 0 || p.res[q].co % 8 != 0) return RSG_OK;
   int NS, KC, S;
-  if (!rsg_conv_tc5_config(p.Cin, p.CoutPad, p.ntaps, halo, &NS, &KC, &S)) return RSG_OK;
+  if (!rsg_conv_tc5_config(p.Cin, p.CoutPad, p.ntaps, mode, &NS, &KC, &S)) return RSG_OK;
   if (p.M == 0) { *handled = 1; return RSG_OK; }
 
   Tc5P k;
@@ -383,13 +433,39 @@ int conv_tc5_launch(const ConvP& p, cudaStream_t s, int* handled) {
   k.KC = KC; k.nchunks = p.Cin / KC; k.S = S;
   k.EW = 8;
   k.ntaps = p.ntaps;
-  for (int t = 0; t < p.ntaps; ++t) {
-    k.dy[t] = p.dy[t]; k.dx[t] = p.dx[t];
-    k.tapoff[t] = (halo + p.dy[t]) * (TW + 2 * halo) + (halo + p.dx[t]);
+  k.stride = p.stride;
+  if (p.stride == 1) {
+    const uint32_t hw = TW + 2 * halo, hh = TH + 2 * halo, lbo16 = hw * hh;       // 16-byte units
+    for (int t = 0; t < p.ntaps; ++t) {
+      k.tap_lo[t] = (uint32_t)((halo + p.dy[t]) * (int)hw + (halo + p.dx[t])) | (lbo16 << 16);
+      k.tap_hi[t] = desc_hi_host(hw * 16u);
+      k.tap_kstep[t] = 2u * lbo16;
+    }
+    k.stage_bytes = hw * hh * (uint32_t)KC * 2u;
+    k.tx_bytes = k.stage_bytes;
+  } else {
+    uint32_t off = 0;
+    k.tx_bytes = 0;
+    for (int ph = 0; ph < 4; ++ph) {
+      k.ph_off[ph] = off;
+      off += ph_bytes(ph, KC);
+      k.tx_bytes += (uint32_t)(KC / 8) * ph_rows(ph) * ph_cols(ph) * 16u;
+    }
+    k.stage_bytes = off;
+    for (int t = 0; t < p.ntaps; ++t) {
+      // input pixel (2y+dy, 2x+dx): even offsets live in the even phase at patch index y, -1 in the odd
+      // phase at patch index y (it starts one element earlier), +1 in the odd phase at index y+1
+      const int ph = (p.dy[t] != 0 ? 2 : 0) + (p.dx[t] != 0 ? 1 : 0);
+      const uint32_t cols = ph_cols(ph), lbo16 = (uint32_t)ph_rows(ph) * cols;
+      k.tap_lo[t] = ((k.ph_off[ph] >> 4) + (uint32_t)((p.dy[t] == 1) * (int)cols + (p.dx[t] == 1))) | (lbo16 << 16);
+      k.tap_hi[t] = desc_hi_host(cols * 16u);
+      k.tap_kstep[t] = 2u * lbo16;
+    }
   }
-  k.halo = halo; k.H = p.Hin; k.W = p.Win;
+  k.halo = halo; k.H = p.Hout; k.W = p.Wout;
+  k.oH = p.oH; k.oW = p.oW; k.omul = p.omul; k.ooy = p.ooy; k.oox = p.oox; k.psC = p.psC;
   k.in = p.in; k.in_cs = p.in_cs; k.in_co = p.in_co;
-  k.tiles_x = (p.Win + TW - 1) / TW; k.tiles_y = (p.Hin + TH - 1) / TH;
+  k.tiles_x = (p.Wout + TW - 1) / TW; k.tiles_y = (p.Hout + TH - 1) / TH;
   k.ntiles = (long long)k.tiles_x * k.tiles_y * p.N;
   if (k.ntiles >= (1ll << 31)) return RSG_OK;
   k.tiles_per_img = (uint32_t)(k.tiles_x * k.tiles_y);
@@ -398,7 +474,7 @@ int conv_tc5_launch(const ConvP& p, cudaStream_t s, int* handled) {
   k.magic_tpi = k.tiles_per_img > 1 ? (uint32_t)(((1ull << 32) + k.tiles_per_img - 1) / k.tiles_per_img) : 0u;
   k.magic_tx = k.tiles_x > 1 ? (uint32_t)(((1ull << 32) + k.tiles_x - 1) / k.tiles_x) : 0u;
   // maps much smaller than the 16x8 patch waste most MMA rows (8x6: 37%): generic kernel instead
-  if (!getenv("RSG_TC5_ANYSIZE") && (double)p.Hin * p.Win < 0.6 * 128.0 * k.tiles_x * k.tiles_y) return RSG_OK;
+  if (!p.psC && !getenv("RSG_TC5_ANYSIZE") && (double)p.Hout * p.Wout < 0.6 * 128.0 * k.tiles_x * k.tiles_y) return RSG_OK;
   k.out = p.out; k.out_cs = p.out_cs; k.out_co = p.out_co;
   k.nres = p.nres;
   for (int q = 0; q < p.nres; ++q) k.res[q] = p.res[q];
@@ -411,7 +487,6 @@ int conv_tc5_launch(const ConvP& p, cudaStream_t s, int* handled) {
     k.dbg = dbg_buf;
   }
   k.w_bytes = (uint32_t)p.ntaps * p.Cin * NS * 2;
-  k.stage_bytes = (uint32_t)(TH + 2 * halo) * (TW + 2 * halo) * KC * 2;
   const size_t smem = (size_t)k.w_bytes + (size_t)S * k.stage_bytes;
   // accumulator ring: MMA completion + barrier wake-up latency is ~1-2k cycles per tile hand-off, so
   // two accumulators leave the tensor pipe idle (profiles/r1_notes.md); use up to 8
@@ -447,10 +522,18 @@ int conv_tc5_launch(const ConvP& p, cudaStream_t s, int* handled) {
   if (gx > k.ntiles) gx = k.ntiles;
   if (gx < 1) gx = 1;
   dim3 grid((unsigned)gx, (unsigned)nslices);
-  CUtensorMap map;
-  memset(&map, 0, sizeof(map));
-  { int rc = make_halo_map(p, halo, KC, &map); if (rc) return rc; }
-  conv_tc5_kernel<<<grid, threads, smem, s>>>(map, k);
+  Tc5Maps maps;
+  memset(&maps, 0, sizeof(maps));
+  if (p.stride == 1) {
+    int rc = make_patch_map(p, TW + 2 * halo, TH + 2 * halo, KC, 1, &maps.m[0]);
+    if (rc) return rc;
+  } else {
+    for (int ph = 0; ph < 4; ++ph) {
+      int rc = make_patch_map(p, ph_cols(ph), ph_rows(ph), KC, 2, &maps.m[ph]);
+      if (rc) return rc;
+    }
+  }
+  conv_tc5_kernel<<<grid, threads, smem, s>>>(maps, k);
   RSG_LAUNCH_CHECK();
   if (k.dbg) {
     static int dumped = 0;

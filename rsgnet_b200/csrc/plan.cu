@@ -124,7 +124,7 @@ int fill_conv(const rsg_conv_desc& d, const RunCtx& c, int N, ConvP* p) {
   p->stride = d.stride; p->Hout = d.Hout; p->Wout = d.Wout;
   p->out = is_null(d.out) ? nullptr : (bf16*)resolve(d.out, c);
   p->out_cs = d.out_cs; p->out_co = d.out_co; p->oH = d.oH; p->oW = d.oW;
-  p->omul = d.omul; p->ooy = d.ooy; p->oox = d.oox;
+  p->omul = d.omul; p->ooy = d.ooy; p->oox = d.oox; p->psC = d.pixel_shuffle_c;
   p->out_f32 = is_null(d.out_f32) ? nullptr : (float*)resolve(d.out_f32, c);
   p->nres = d.nres;
   for (int q = 0; q < d.nres; ++q) p->res[q] = resolve_res(d.res[q], c);
@@ -168,6 +168,7 @@ int run_conv(const rsg_conv_desc& d, const RunCtx& c, int N, cudaStream_t s, int
     }
     RSG_REQUIRE(d.engine != 2, "conv: shape not supported by the tcgen05 kernel (engine=2 forced)");
   }
+  RSG_REQUIRE(p.psC == 0, "conv: pixel-shuffle output needs the tcgen05 kernel (shape not covered)");
   return conv_mma_launch(p, s);
 }
 
@@ -387,6 +388,7 @@ extern "C" int rsg_plan_profile(rsg_plan* p, void* stream, void* const* ext, int
     if (op.kind == OP_CONV) {
       if (tc5) kind[i] = tc5 == 2 ? 9 : 2;
       flops[i] = 2.0 * op.conv.ntaps * op.conv.Cin * op.conv.Cout * (double)op.conv.Hout * op.conv.Wout * nb;
+      if (op.conv.pixel_shuffle_c) flops[i] *= 16.0 / 36.0;      // the zero taps of the fused deconv are not credited
     } else if (op.kind == OP_ATTN) {
       flops[i] = 4.0 * (double)op.i[6] * op.i[6] * op.i[7] * nb;
     } else if (op.kind == OP_STEM) {

@@ -126,6 +126,80 @@ def test_conv_ws_vs_torch(cin, cout, k, H, W, N, nres):
     _lib.lib().rsg_plan_destroy(h)
 
 
+S2_CASES = [
+    # Cin, Cout, Hin, Win, N, nres, res_shift   (engine=2: stride-2 3x3 on the tcgen05 kernel, four TMA phase patches)
+    (64, 64, 32, 24, 3, 0, 0),
+    (32, 64, 32, 24, 5, 2, 1),        # fuse layer: + identity term + nearest-upsampled term
+    (256, 64, 16, 12, 4, 0, 0),       # transition: many input channels, sliced weights
+    (64, 128, 13, 11, 3, 1, 0),       # odd input size: Hout = 7, Wout = 6
+    (32, 32, 64, 48, 40, 0, 0),       # more tiles than SMs
+    (128, 256, 16, 12, 6, 3, 0),
+]
+
+
+@pytest.mark.parametrize('cin,cout,H,W,N,nres,shift', S2_CASES)
+def test_conv_stride2_tcgen05_vs_torch(cin, cout, H, W, N, nres, shift):
+    g = torch.Generator().manual_seed(cin + 3 * cout + H)
+    x = torch.randn(N, cin, H, W, generator=g).bfloat16().float()
+    w = (torch.randn(cout, cin, 3, 3, generator=g) / (cin * 9) ** 0.5).bfloat16().float()
+    b = torch.randn(cout, generator=g) * 0.1
+    Ho, Wo = (H - 1) // 2 + 1, (W - 1) // 2 + 1
+    pb = PlanBuilder(N, reuse=False)
+    xin = pb.buf('x', H, W, cin + 8)
+    res, rts = [], []
+    for i in range(nres):
+        sh = shift if i == nres - 1 else 0
+        rh, rw = (Ho >> sh, Wo >> sh) if sh else (Ho, Wo)
+        rb = pb.buf(f'r{i}', rh, rw, cout)
+        res.append((View(rb), sh))
+        rts.append((rb, torch.randn(N, cout, rh, rw, generator=g).bfloat16().float(), sh))
+    ob = pb.buf('o', Ho, Wo, cout + 8)
+    pb.conv(View(xin, 8, cin), w.double().numpy(), b.double().numpy(), stride=2, relu=True,
+            dst=View(ob, 0, cout), res=res, engine=2)
+    h = _run(pb, N)
+    pb.tensor_of(xin)[:N, ..., 8:] = x.permute(0, 2, 3, 1).cuda().bfloat16()
+    pb.tensor_of(xin)[:N, ..., :8] = 1e4
+    for rb, r, _ in rts:
+        pb.tensor_of(rb)[:N] = r.permute(0, 2, 3, 1).cuda().bfloat16()
+    pb.tensor_of(ob).fill_(7.0)
+    _exec(h, N)
+    ref = F.conv2d(x.cuda(), w.cuda(), b.cuda(), 2, 1)
+    for _, r, sh in rts:
+        r = r.cuda()
+        ref = ref + (F.interpolate(r, scale_factor=2 ** sh, mode='nearest') if sh else r)
+    ref = F.relu(ref).cpu()
+    got = pb.tensor_of(ob)[:N, ..., :cout].float().permute(0, 3, 1, 2).cpu()
+    err = (got - ref).abs().max().item()
+    assert err <= 2e-2 * max(ref.abs().max().item(), 1.0), err
+    assert torch.all(pb.tensor_of(ob)[:N, ..., cout:] == 7.0)
+    _lib.lib().rsg_plan_destroy(h)
+
+
+@pytest.mark.parametrize('C_,H,W,N', [(32, 16, 12, 3), (32, 64, 48, 5), (16, 8, 6, 4), (48, 12, 9, 2)])
+def test_deconv4_fused_pixel_shuffle_vs_torch(C_, H, W, N):
+    """ConvTranspose2d(4, 2, 1) + BN + ReLU (pose_rsgnet.py:733-744) as one 3x3 conv with a pixel-shuffle
+    epilogue, against F.conv_transpose2d."""
+    g = torch.Generator().manual_seed(C_ + H)
+    x = torch.randn(N, C_, H, W, generator=g).bfloat16().float()
+    wt = (torch.randn(C_, C_, 4, 4, generator=g) / (C_ * 4) ** 0.5).bfloat16().float()
+    sd = {'d.0.weight': wt, 'd.1.weight': torch.ones(C_), 'd.1.bias': torch.randn(C_, generator=g) * 0.1,
+          'd.1.running_mean': torch.zeros(C_), 'd.1.running_var': torch.ones(C_) - _engine.EPS}
+    pb = PlanBuilder(N, reuse=False)
+    xin = pb.buf('x', H, W, C_)
+    ob = pb.buf('o', 2 * H, 2 * W, C_)
+    _engine._deconv4(pb, _engine._Params(sd), 'd', View(xin), View(ob))
+    assert len(pb.ops) == 1 and pb.ops[0][1]['psc'] == C_     # the fused form was chosen
+    h = _run(pb, N)
+    pb.tensor_of(xin)[:N] = x.permute(0, 2, 3, 1).cuda().bfloat16()
+    pb.tensor_of(ob).fill_(7.0)
+    _exec(h, N)
+    ref = F.relu(F.conv_transpose2d(x, wt, None, 2, 1) + sd['d.1.bias'][None, :, None, None])
+    got = pb.tensor_of(ob)[:N].float().permute(0, 3, 1, 2).cpu()
+    err = (got - ref).abs().max().item()
+    assert err <= 2e-2 * max(ref.abs().max().item(), 1.0), err
+    _lib.lib().rsg_plan_destroy(h)
+
+
 def test_conv_fp32_nchw_output_and_upsampled_residuals():
     N, cin, K, H, W = 3, 32, 17, 16, 12
     g = torch.Generator().manual_seed(1)

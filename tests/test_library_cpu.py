@@ -58,7 +58,7 @@ def test_no_cpu_fallback():
     assert oks_nms([], 0.9) == []
 
 
-@pytest.mark.parametrize('key,n_conv', [('w32_crowdpose', 308), ('hrnet_w32_coco', 292)])
+@pytest.mark.parametrize('key,n_conv', [('w32_crowdpose', 305), ('hrnet_w32_coco', 292)])
 def test_plan_builder_graph(key, n_conv):
     cfg = presets.preset(key)
     mod = pose_rsgnet if cfg.MODEL.NAME == 'pose_rsgnet' else pose_hrnet
