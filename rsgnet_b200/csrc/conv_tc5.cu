@@ -67,6 +67,7 @@ struct Tc5P {
   int nres;
   ResP res[4];
   int relu;
+  int v32;              // bit0: output rows 32-byte aligned, bit1: residual term 0 too (LDG/STG.256)
   uint32_t w_bytes, stage_bytes, tx_bytes, tmem_cols;
   long long* dbg;       // debug timeline (CTA 0): [tile][8] clock64 stamps, or nullptr
   int skip;             // debug: bit0 no halo loads, bit1 no MMAs, bit2 no residual loads, bit3 no stores
@@ -259,19 +260,27 @@ conv_tc5_kernel(const __grid_constant__ Tc5Maps maps, const Tc5P p) {
       const uint32_t ooff = ((n * (uint32_t)p.oH + (uint32_t)(y * p.omul + p.ooy)) * (uint32_t)p.oW +
                              (uint32_t)(x * p.omul + p.oox)) * (uint32_t)p.out_cs;
       const bf16* r0p = nullptr;
-      uint4 pre0, pre1;
+      // the thread's whole residual row segment (<= 64 columns) is fetched before waiting for the
+      // accumulator, so its L2 / HBM latency overlaps the MMAs instead of every 16-column step
+      uint4 pre[8];
+#pragma unroll
+      for (int j = 0; j < 8; ++j) pre[j] = make_uint4(0, 0, 0, 0);
       if (nres > 0 && ok && gch0 < p.Cout) {
         const ResP& rr = p.res[0];
         r0p = rr.p + rr.co + gch0 +
               (((rr.bs0 ? 0u : n) * (uint32_t)rr.H + (uint32_t)(y >> rr.shift)) * (uint32_t)rr.W + (uint32_t)(x >> rr.shift)) * (uint32_t)rr.cs;
-        pre0 = __ldg(reinterpret_cast<const uint4*>(r0p));
-        pre1 = __ldg(reinterpret_cast<const uint4*>(r0p) + 1);
+#pragma unroll
+        for (int j = 0; j < 8; ++j)
+          if (j * 8 < ncol && !(j & 1)) ldg32(r0p + j * 8, (p.v32 & 2) != 0, pre[j], pre[j | 1]);
       }
       mbar_wait(bar_accf + 8u * b, (tl / (uint32_t)p.NACC) & 1);
       if (p.dbg && blockIdx.x == 0 && blockIdx.y == 0 && (threadIdx.x == 32 * (EPI_WARP0 + 1) || threadIdx.x == 32 * (EPI_WARP0 + 5)) && tl < 64) p.dbg[tl * 8 + 5] = clock64();
       asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
       const uint32_t taddr = tq + b * (uint32_t)p.NS;
-      for (int c0 = 0; c0 < ncol; c0 += 16) {
+#pragma unroll
+      for (int ci = 0; ci < 4; ++ci) {
+        const int c0 = ci * 16;
+        if (c0 >= ncol) break;
         uint32_t v[16];
         tmem_ld16(taddr + c0, v);
         asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
@@ -294,7 +303,7 @@ conv_tc5_kernel(const __grid_constant__ Tc5Maps maps, const Tc5P p) {
           f[j4 * 4 + 3] = __uint_as_float(v[j4 * 4 + 3]) + bb.w;
         }
         if (nres > 0) {
-          if (c0 == 0) { add_res8(f, pre0); add_res8(f + 8, pre1); }
+          if (c0 < 64) { add_res8(f, pre[(c0 >> 3) & 7]); add_res8(f + 8, pre[((c0 >> 3) + 1) & 7]); }
           else {
             add_res8(f, __ldg(reinterpret_cast<const uint4*>(r0p + c0)));
             add_res8(f + 8, __ldg(reinterpret_cast<const uint4*>(r0p + c0) + 1));
@@ -327,9 +336,7 @@ conv_tc5_kernel(const __grid_constant__ Tc5Maps maps, const Tc5P p) {
             const uint32_t ph = gc / (uint32_t)p.psC;
             off = ooff + ((ph >> 1) * (uint32_t)p.oW + (ph & 1)) * (uint32_t)p.out_cs + (gc - ph * (uint32_t)p.psC);
           }
-          uint4* op = reinterpret_cast<uint4*>(outp + off);
-          op[0] = o0;
-          op[1] = o1;
+          stg32(outp + off, (p.v32 & 1) != 0, o0, o1);
         }
       }
       if (p.dbg && blockIdx.x == 0 && blockIdx.y == 0 && (threadIdx.x == 32 * (EPI_WARP0 + 1) || threadIdx.x == 32 * (EPI_WARP0 + 5)) && tl < 64) p.dbg[tl * 8 + 7] = clock64();
@@ -425,6 +432,9 @@ int conv_tc5_launch(const ConvP& p, cudaStream_t s, int* handled) {
     if (p.res[q].cs % 8 != 0 || p.res[q].co % 8 != 0) return RSG_OK;
   int NS, KC, S;
   if (!rsg_conv_tc5_config(p.Cin, p.CoutPad, p.ntaps, mode, &NS, &KC, &S)) return RSG_OK;
+  // a stride-2 layer whose weights leave room for only two phase-patch stages (256->64: 147 KB per 32-channel
+  // slice) measured 2x slower than the generic kernel
+  if (p.stride == 2 && S < 4 && !getenv("RSG_TC5_ANYSIZE")) return RSG_OK;
   if (p.M == 0) { *handled = 1; return RSG_OK; }
 
   Tc5P k;
@@ -479,6 +489,12 @@ int conv_tc5_launch(const ConvP& p, cudaStream_t s, int* handled) {
   k.nres = p.nres;
   for (int q = 0; q < p.nres; ++q) k.res[q] = p.res[q];
   k.relu = p.relu;
+  {
+    auto al32 = [](const void* ptr, int cs, int co) { return ((uintptr_t)ptr % 32 == 0) && cs % 16 == 0 && co % 16 == 0; };
+    k.v32 = (al32(p.out, p.out_cs, p.out_co) && (!p.psC || p.psC % 16 == 0) ? 1 : 0) |
+            (p.nres > 0 && al32(p.res[0].p, p.res[0].cs, p.res[0].co) ? 2 : 0);
+    if (getenv("RSG_NO_V32")) k.v32 = 0;
+  }
   { const char* e = getenv("RSG_TC5_SKIP"); k.skip = e ? atoi(e) : 0; }
   static long long* dbg_buf = nullptr;
   if (getenv("RSG_TC5_TIMELINE")) {

@@ -54,6 +54,7 @@ struct WsP {
   int nres;
   ResP res[4];
   int relu;
+  int v32;              // bit0: output rows 32-byte aligned, bit1: residual term 0 too (LDG/STG.256)
   uint32_t plane_bytes, a_bytes, b_off, b_tap_bytes, stage_bytes, tmem_cols;
   long long* dbg;       // debug timeline of CTA (0,0): globaltimer stamps [16] or nullptr
   int skip;             // debug: bit0 no loads, bit1 one tap only, bit2 no residual loads / stores
@@ -218,7 +219,7 @@ conv_ws_kernel(const __grid_constant__ CUtensorMap in_map, const WsP p) {
                 (((rr.bs0 ? 0u : n) * (uint32_t)rr.H + (y >> rr.shift)) * (uint32_t)rr.W + (x >> rr.shift)) * (uint32_t)rr.cs;
 #pragma unroll
           for (int j = 0; j < 8; ++j)
-            if (j * 8 < ncol) pre[j] = __ldg(reinterpret_cast<const uint4*>(r0p) + j);
+            if (j * 8 < ncol && !(j & 1)) ldg32(r0p + j * 8, (p.v32 & 2) != 0, pre[j], pre[j | 1]);
         }
         mbar_wait(bar_accf + 8u * (uint32_t)t, st & 1);
         if (warp == WS_EPI_WARP0 && lane == 0 && st == 0 && t == egroup) WS_STAMP(8);
@@ -275,9 +276,7 @@ conv_ws_kernel(const __grid_constant__ CUtensorMap in_map, const WsP p) {
             for (int k2 = 0; k2 < 4; ++k2) { h0[k2] = __hmax2(h0[k2], z); h1[k2] = __hmax2(h1[k2], z); }
           }
           if (!(p.skip & 4)) {
-            uint4* op = reinterpret_cast<uint4*>(outp + ooff + c0);
-            op[0] = o0;
-            op[1] = o1;
+            stg32(outp + ooff + c0, (p.v32 & 1) != 0, o0, o1);
           }
         }
         if (warp == WS_EPI_WARP0 && lane == 0) { if (st == 0 && t == egroup) WS_STAMP(9); WS_STAMP(10); }
@@ -408,6 +407,11 @@ int conv_ws_launch(const ConvP& p, cudaStream_t s, int* handled) {
   k.nres = p.nres;
   for (int q = 0; q < p.nres; ++q) k.res[q] = p.res[q];
   k.relu = p.relu;
+  {
+    auto al32 = [](const void* ptr, int cs, int co) { return ((uintptr_t)ptr % 32 == 0) && cs % 16 == 0 && co % 16 == 0; };
+    k.v32 = (al32(p.out, p.out_cs, p.out_co) ? 1 : 0) | (p.nres > 0 && al32(p.res[0].p, p.res[0].cs, p.res[0].co) ? 2 : 0);
+    if (getenv("RSG_NO_V32")) k.v32 = 0;
+  }
   { const char* e = getenv("RSG_WS_SKIP"); k.skip = e ? atoi(e) : 0; }
   static int dbg_launch = 0;
   if (getenv("RSG_WS_TIMELINE")) {

@@ -126,6 +126,29 @@ __device__ __forceinline__ void add_res8(float* f, const uint4& u) {
   }
 }
 
+// 32-byte global accesses (sm_100 LDG/STG.256): one full sector per thread per instruction.  `v32` is a
+// warp-uniform "the address is 32-byte aligned" flag; otherwise two 16-byte accesses.
+__device__ __forceinline__ void ldg32(const bf16* p, bool v32, uint4& a, uint4& b) {
+  if (v32) {
+    asm volatile("ld.global.nc.v8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+                 : "=r"(a.x), "=r"(a.y), "=r"(a.z), "=r"(a.w), "=r"(b.x), "=r"(b.y), "=r"(b.z), "=r"(b.w)
+                 : "l"(p));
+  } else {
+    a = __ldg(reinterpret_cast<const uint4*>(p));
+    b = __ldg(reinterpret_cast<const uint4*>(p) + 1);
+  }
+}
+__device__ __forceinline__ void stg32(bf16* p, bool v32, const uint4& a, const uint4& b) {
+  if (v32) {
+    asm volatile("st.global.v8.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};"
+                 ::"l"(p), "r"(a.x), "r"(a.y), "r"(a.z), "r"(a.w), "r"(b.x), "r"(b.y), "r"(b.z), "r"(b.w)
+                 : "memory");
+  } else {
+    reinterpret_cast<uint4*>(p)[0] = a;
+    reinterpret_cast<uint4*>(p)[1] = b;
+  }
+}
+
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
                                   const cuuint64_t*, const cuuint32_t*, const cuuint32_t*,
                                   CUtensorMapInterleave, CUtensorMapSwizzle, CUtensorMapL2promotion,
