@@ -32,9 +32,9 @@ namespace {
 using namespace umma;
 
 constexpr int TH = 16, TW = 8;                 // pixel patch = 128 MMA rows
-constexpr int NTHREADS = 672;                  // one fat persistent CTA per SM (21 warps)
-constexpr int MAX_MMA_WARPS = 4;               // warps 0..3 may issue MMAs (p.NMMA of them do), round-robin over tiles
-constexpr int EPI_WARP0 = 5;                   // warp 4 = TMA producer; epilogue warps 5..20: two groups of 8
+constexpr int NTHREADS = 608;                  // one fat persistent CTA per SM (19 warps -> 96 registers/thread)
+constexpr int MAX_MMA_WARPS = 2;               // warps 0..1 issue MMAs, round-robin over tiles (unrolled issue: two saturate N=32)
+constexpr int EPI_WARP0 = 3;                   // warp 2 = TMA producer; epilogue warps 3..18: two groups of 8
 constexpr int NEPI = 2;
 struct Tc5P {
   const bf16* w;        // [nslices][ntaps][Cin/8][NS][8]
@@ -78,6 +78,23 @@ constexpr int MAX_ACC = 8;
 constexpr int MAX_CHUNKS = 32;
 
 struct Tc5Maps { CUtensorMap m[4]; };
+
+// 9 taps x K2 k16 steps issued back to back from per-tap offsets held in registers.  The issuing thread is
+// bound by the latency of its own instruction stream (tools/umma_rate.cu: 137 cycles per MMA for a plain
+// loop, 203 with a tap-table lookup), so the hot shapes run fully unrolled.
+template <int K2>
+__device__ __forceinline__ void issue9(uint32_t d_tmem, uint32_t a_stage, uint32_t w_chunk, const uint32_t (&alo9)[9],
+                                       const uint32_t (&blo9)[9], uint32_t hiA, uint32_t hiB, uint32_t a_kstep,
+                                       uint32_t b_kstep, uint32_t idesc, uint32_t acc) {
+#pragma unroll
+  for (int tp = 0; tp < 9; ++tp) {
+#pragma unroll
+    for (int kc = 0; kc < K2; ++kc) {
+      umma_f16(d_tmem, ((uint64_t)hiA << 32) | (a_stage + alo9[tp] + (uint32_t)kc * a_kstep),
+               ((uint64_t)hiB << 32) | (w_chunk + blo9[tp] + (uint32_t)kc * b_kstep), idesc, (tp | kc) ? 1u : acc);
+    }
+  }
+}
 
 __global__ void __launch_bounds__(NTHREADS, 1)
 conv_tc5_kernel(const __grid_constant__ Tc5Maps maps, const Tc5P p) {
@@ -124,16 +141,20 @@ conv_tc5_kernel(const __grid_constant__ Tc5Maps maps, const Tc5P p) {
     if (ptid == 0) {
       const int nph = p.stride == 2 ? 4 : 1;
       for (int i = 0; i < nph; ++i) asm volatile("prefetch.tensormap [%0];" ::"l"(&maps.m[i]) : "memory");
-      const uint32_t S2 = (uint32_t)(p.S / NMMA);        // each MMA warp owns its own ring of S/NMMA stages
-      uint32_t tl = 0, it = 0;
-      for (int t = (int)first; t < (int)p.ntiles; t += (int)step, ++tl) {
+      // each MMA warp owns its own ring of S/2 stages (slots w, w+2, ...); ring positions and phases are
+      // carried incrementally: an integer division costs this single thread ~100 cycles of pure latency
+      const uint32_t S2 = (uint32_t)p.S >> 1;
+      uint32_t js[2] = {0, 0}, ph[2] = {0, 0};
+      uint32_t it = 0;
+      uint32_t w = 0;
+      for (int t = (int)first; t < (int)p.ntiles; t += (int)step, w ^= 1u) {
         const int n = (int)fastdiv((uint32_t)t, p.magic_tpi);
-        const int rem = t - n * (p.tiles_x * p.tiles_y);
+        const int rem = t - n * (int)p.tiles_per_img;
         const int ty = (int)fastdiv((uint32_t)rem, p.magic_tx), tx = rem - ty * p.tiles_x;
-        uint32_t j = (tl / NMMA) * (uint32_t)p.nchunks;  // stage counter inside the owning warp's ring
-        for (int c = 0; c < p.nchunks; ++c, ++j, ++it) {
-          const int s = (int)((j % S2) * NMMA + (tl % NMMA));
-          mbar_wait(BAR(B_EMPTY + s), ((j / S2) & 1) ^ 1);
+        uint32_t j = w ? js[1] : js[0], phase = w ? ph[1] : ph[0];
+        for (int c = 0; c < p.nchunks; ++c, ++it) {
+          const int s = (int)(j * 2u + w);
+          mbar_wait(BAR(B_EMPTY + s), phase ^ 1u);
           if (p.dbg && blockIdx.x == 0 && blockIdx.y == 0 && it < 64) p.dbg[it * 8 + 0] = clock64();
           if (!(p.skip & 1)) {
             mbar_arrive_expect_tx(BAR(B_FULL + s), p.tx_bytes);
@@ -144,15 +165,17 @@ conv_tc5_kernel(const __grid_constant__ Tc5Maps maps, const Tc5P p) {
               // phase (row parity, column parity): even rows/cols start at the tile origin, odd ones one
               // element earlier (the -1 taps); the box walks the input with element strides of 2
 #pragma unroll
-              for (int ph = 0; ph < 4; ++ph)
-                tma_load_5d(dst + p.ph_off[ph], &maps.m[ph], BAR(B_FULL + s), 0, 2 * tx * TW - (ph & 1),
-                            2 * ty * TH - (ph >> 1), c * (p.KC >> 3), n);
+              for (int ph4 = 0; ph4 < 4; ++ph4)
+                tma_load_5d(dst + p.ph_off[ph4], &maps.m[ph4], BAR(B_FULL + s), 0, 2 * tx * TW - (ph4 & 1),
+                            2 * ty * TH - (ph4 >> 1), c * (p.KC >> 3), n);
             }
           } else {
             mbar_arrive(BAR(B_FULL + s));
           }
           if (p.dbg && blockIdx.x == 0 && blockIdx.y == 0 && it < 64) p.dbg[it * 8 + 1] = clock64();
+          if (++j == S2) { j = 0; phase ^= 1u; }
         }
+        if (w) { js[1] = j; ph[1] = phase; } else { js[0] = j; ph[0] = phase; }
       }
     }
   } else if (warp < MAX_MMA_WARPS) {
@@ -183,19 +206,31 @@ conv_tc5_kernel(const __grid_constant__ Tc5Maps maps, const Tc5P p) {
     const uint32_t b_tapstep = ((uint32_t)(p.Cin >> 3) * lbo_b) >> 4;
     const uint32_t b_chunkstep = ((uint32_t)(p.KC >> 3) * lbo_b) >> 4;
     const uint32_t lo_lbo_b = ((lbo_b >> 4) & 0x3FFFu) << 16;
-    for (uint32_t tl = (uint32_t)warp; (long long)first + (long long)tl * step < p.ntiles; tl += NMMA) {
-      const int b = tl % p.NACC;
-      mbar_wait(BAR(B_ACCE + b), ((tl / p.NACC) & 1) ^ 1);  // accumulator drained by the epilogue
-      const uint32_t d_tmem = tmem_base + (uint32_t)b * p.NS;
+    // fast path: 3x3 stride 1 (one halo patch: the descriptor high word and k step are the same for every tap)
+    const bool fast9 = p.ntaps == 9 && p.stride == 1 && !(p.skip & 2) && (kc2n == 1 || kc2n == 2 || kc2n == 4);
+    uint32_t alo9[9], blo9[9];
+#pragma unroll
+    for (int tp = 0; tp < 9; ++tp) {
+      alo9[tp] = p.tap_lo[tp < p.ntaps ? tp : 0];
+      blo9[tp] = (uint32_t)tp * b_tapstep;
+    }
+    const uint32_t hiA0 = p.tap_hi[0], a_kstep0 = p.tap_kstep[0];
+    // ring / accumulator positions and phases are carried incrementally (no divisions on this latency-bound
+    // instruction stream).  Each issuing warp consumes its OWN ring of S/2 stages (slots warp, warp+2, ...):
+    // with one shared ring a warp could wait for phase k+1 of a slot before phase k had completed, and an
+    // mbarrier parity wait cannot tell "not yet" from "one phase ago".
+    const uint32_t S2 = (uint32_t)p.S >> 1;
+    uint32_t js = 0, sph = 0;                       // position / phase in this warp's stage ring
+    uint32_t b = (uint32_t)warp, aph = 0;           // accumulator index (NACC is even) / phase
+    uint32_t tl = (uint32_t)warp;
+    for (uint32_t t = (uint32_t)first + (uint32_t)warp * (uint32_t)step; t < (uint32_t)p.ntiles;
+         t += 2u * (uint32_t)step, tl += 2u) {
+      mbar_wait(BAR(B_ACCE + b), aph ^ 1u);          // accumulator drained by the epilogue
+      const uint32_t d_tmem = tmem_base + b * (uint32_t)p.NS;
       if (p.dbg && blockIdx.x == 0 && blockIdx.y == 0 && lane == 0 && tl < 64) p.dbg[tl * 8 + 2] = clock64();
-      // Each issuing warp consumes its OWN ring of S/2 stages (slots warp, warp+2, ...).  With one
-      // shared ring a warp could wait for phase k+1 of a slot before phase k had completed, and an
-      // mbarrier parity wait cannot tell "not yet" from "one phase ago".
-      const uint32_t S2 = (uint32_t)(p.S / NMMA);
-      uint32_t j = (tl / NMMA) * (uint32_t)p.nchunks;
-      for (int c = 0; c < p.nchunks; ++c, ++j) {
-        const int s = (int)((j % S2) * NMMA + (uint32_t)warp);
-        mbar_wait(BAR(B_FULL + s), (j / S2) & 1);          // halo chunk landed
+      for (int c = 0; c < p.nchunks; ++c) {
+        const int s = (int)(js * 2u + (uint32_t)warp);
+        mbar_wait(BAR(B_FULL + s), sph);               // halo chunk landed
         if (p.dbg && blockIdx.x == 0 && blockIdx.y == 0 && lane == 0 && tl < 64) p.dbg[tl * 8 + 3] = clock64();
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
         // low descriptor words: (address >> 4) | LBO << 16; adding 16-byte offsets never carries out of
@@ -204,7 +239,12 @@ conv_tc5_kernel(const __grid_constant__ Tc5Maps maps, const Tc5P p) {
         const uint32_t w_chunk = ((w0 >> 4) + (uint32_t)c * b_chunkstep) | lo_lbo_b;
         if (elect_one()) {
           uint32_t acc = c > 0;
-          const int ntp = (p.skip & 2) ? 1 : p.ntaps;
+          const int ntp = fast9 ? 0 : ((p.skip & 2) ? 1 : p.ntaps);
+          if (fast9) {
+            if (kc2n == 1) issue9<1>(d_tmem, a_stage, w_chunk, alo9, blo9, hiA0, hiB, a_kstep0, b_kstep, idesc, acc);
+            else if (kc2n == 2) issue9<2>(d_tmem, a_stage, w_chunk, alo9, blo9, hiA0, hiB, a_kstep0, b_kstep, idesc, acc);
+            else issue9<4>(d_tmem, a_stage, w_chunk, alo9, blo9, hiA0, hiB, a_kstep0, b_kstep, idesc, acc);
+          }
           for (int tp = 0; tp < ntp; ++tp) {
             uint32_t alo = a_stage + p.tap_lo[tp];
             uint32_t blo = w_chunk + (uint32_t)tp * b_tapstep;
@@ -222,8 +262,11 @@ conv_tc5_kernel(const __grid_constant__ Tc5Maps maps, const Tc5P p) {
           if (c == p.nchunks - 1) umma_commit(BAR(B_ACCF + b));   // accumulator ready
         }
         __syncwarp();
+        if (++js == S2) { js = 0; sph ^= 1u; }
       }
       if (p.dbg && blockIdx.x == 0 && blockIdx.y == 0 && lane == 0 && tl < 64) p.dbg[tl * 8 + 4] = clock64();
+      b += 2u;
+      if (b >= (uint32_t)p.NACC) { b -= (uint32_t)p.NACC; aph ^= 1u; }
     }
    }
   } else {
@@ -247,10 +290,9 @@ conv_tc5_kernel(const __grid_constant__ Tc5Maps maps, const Tc5P p) {
     bf16* const outp = p.out + p.out_co;
     const uint32_t tq = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)cbeg;
     const uint32_t bar_accf = opaque(BAR(B_ACCF)), bar_acce = opaque(BAR(B_ACCE));
-    for (uint32_t tl = (uint32_t)egroup; ; tl += NEPI) {
-      const uint32_t t = (uint32_t)first + tl * (uint32_t)step;
-      if (t >= (uint32_t)p.ntiles) break;
-      const uint32_t b = tl % (uint32_t)p.NACC;
+    uint32_t b = (uint32_t)egroup, aph = 0, tl = (uint32_t)egroup;      // accumulator index / phase, carried incrementally
+    for (uint32_t t = (uint32_t)first + (uint32_t)egroup * (uint32_t)step; t < (uint32_t)p.ntiles;
+         t += (uint32_t)NEPI * (uint32_t)step, tl += NEPI) {
       const uint32_t n = fastdiv(t, p.magic_tpi);                  // t / tiles_per_img
       const uint32_t rem = t - n * p.tiles_per_img;
       const uint32_t ty = fastdiv(rem, p.magic_tx);                // rem / tiles_x
@@ -273,7 +315,7 @@ conv_tc5_kernel(const __grid_constant__ Tc5Maps maps, const Tc5P p) {
         for (int j = 0; j < 8; ++j)
           if (j * 8 < ncol && !(j & 1)) ldg32(r0p + j * 8, (p.v32 & 2) != 0, pre[j], pre[j | 1]);
       }
-      mbar_wait(bar_accf + 8u * b, (tl / (uint32_t)p.NACC) & 1);
+      mbar_wait(bar_accf + 8u * b, aph);
       if (p.dbg && blockIdx.x == 0 && blockIdx.y == 0 && (threadIdx.x == 32 * (EPI_WARP0 + 1) || threadIdx.x == 32 * (EPI_WARP0 + 5)) && tl < 64) p.dbg[tl * 8 + 5] = clock64();
       asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
       const uint32_t taddr = tq + b * (uint32_t)p.NS;
@@ -340,6 +382,8 @@ conv_tc5_kernel(const __grid_constant__ Tc5Maps maps, const Tc5P p) {
         }
       }
       if (p.dbg && blockIdx.x == 0 && blockIdx.y == 0 && (threadIdx.x == 32 * (EPI_WARP0 + 1) || threadIdx.x == 32 * (EPI_WARP0 + 5)) && tl < 64) p.dbg[tl * 8 + 7] = clock64();
+      b += (uint32_t)NEPI;
+      if (b >= (uint32_t)p.NACC) { b -= (uint32_t)p.NACC; aph ^= 1u; }
     }
   }
   // ---- teardown
@@ -511,9 +555,7 @@ int conv_tc5_launch(const ConvP& p, cudaStream_t s, int* handled) {
   if (nacc > MAX_ACC) nacc = MAX_ACC;
   // thin layers are bound by the per-warp MMA issue rate (~110 cycles per MMA): four issuing warps when
   // the rings can be split four ways
-  int nmma = (S % 4 == 0 && S >= 8) ? 4 : 2;
-  { const char* e = getenv("RSG_TC5_NMMA"); if (e) nmma = atoi(e); }
-  if (nmma == 4 && (S % 4 != 0 || nacc < 4)) nmma = 2;
+  const int nmma = MAX_MMA_WARPS;
   k.NMMA = nmma;
   nacc = nacc / nmma * nmma;                              // tiles go round-robin over the MMA warps
   if (nacc < 2) nacc = 2;

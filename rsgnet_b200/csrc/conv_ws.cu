@@ -117,11 +117,10 @@ conv_ws_kernel(const __grid_constant__ CUtensorMap in_map, const WsP p) {
                                  (size_t)slice * p.ntaps * (size_t)(p.Cin >> 3) * p.NS * 16u;
       const size_t w_tap_stride = (size_t)(p.Cin >> 3) * p.NS * 16u;
       const uint32_t tx_bytes = p.a_bytes + (uint32_t)p.ntaps * p.b_tap_bytes;
-      uint32_t it = 0;
+      uint32_t it = 0, s = 0, sph = 0;              // ring slot / phase, carried incrementally (no divisions)
       for (int u = first; u < p.nsuper; u += step) {
-        for (int c = 0; c < p.nchunks; ++c, ++it) {
-          const uint32_t s = it % (uint32_t)p.S;
-          mbar_wait(BAR(B_EMPTY + s), ((it / (uint32_t)p.S) & 1) ^ 1);
+        for (int c = 0; c < p.nchunks; ++c, ++it, s = (s + 1 == (uint32_t)p.S ? 0u : s + 1), sph ^= (s == 0)) {
+          mbar_wait(BAR(B_EMPTY + s), sph ^ 1u);
           const uint32_t dst = sbase + s * p.stage_bytes;
           if (p.skip & 1) { mbar_arrive(BAR(B_FULL + s)); continue; }
           mbar_arrive_expect_tx(BAR(B_FULL + s), tx_bytes);
@@ -146,11 +145,21 @@ conv_ws_kernel(const __grid_constant__ CUtensorMap in_map, const WsP p) {
     const uint32_t a_kstep = (2u * p.plane_bytes) >> 4, b_kstep = (2u * (uint32_t)p.NS * 16u) >> 4;
     const uint32_t b_tapstep = p.b_tap_bytes >> 4;
     const int kc2n = p.KC >> 4;
-    uint32_t it = 0, st = 0;
+    // The issuing thread is bound by the LATENCY of its own instruction stream (tools/umma_rate.cu: one
+    // thread sustains one MMA per 137 cycles with a 10-instruction loop body, 203 with a tap lookup), so
+    // the hot shape (9 taps, one k16 step per chunk) runs fully unrolled from per-tap offsets kept in
+    // registers: two adds + the descriptor moves per MMA.
+    const bool fast9 = p.ntaps == 9 && kc2n == 1 && !(p.skip & 2);
+    uint32_t aoff[9], boff[9];
+#pragma unroll
+    for (int tp = 0; tp < 9; ++tp) {
+      aoff[tp] = (uint32_t)p.tapoff[tp < p.ntaps ? tp : 0];
+      boff[tp] = (uint32_t)tp * b_tapstep;
+    }
+    uint32_t it = 0, st = 0, s = 0, sph = 0;
     for (int u = first; u < p.nsuper; u += step, ++st) {
-      for (int c = 0; c < p.nchunks; ++c, ++it) {
-        const uint32_t s = it % (uint32_t)p.S;
-        mbar_wait(BAR(B_FULL + s), (it / (uint32_t)p.S) & 1);
+      for (int c = 0; c < p.nchunks; ++c, ++it, s = (s + 1 == (uint32_t)p.S ? 0u : s + 1), sph ^= (s == 0)) {
+        mbar_wait(BAR(B_FULL + s), sph);
         if (warp == 0 && lane == 0) { if (it == 0) WS_STAMP(4); if (it == (uint32_t)p.nchunks) WS_STAMP(6); }
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
         const uint32_t stage16 = (sbase + s * p.stage_bytes) >> 4;
@@ -164,6 +173,15 @@ conv_ws_kernel(const __grid_constant__ CUtensorMap in_map, const WsP p) {
             const uint32_t d_tmem = tmem_base + (uint32_t)(t * p.NS);
             const uint32_t a_tile = (stage16 + 128u * (uint32_t)t) | lo_lbo_a;
             uint32_t acc = c > 0;
+            if (fast9) {
+#pragma unroll
+              for (int tp = 0; tp < 9; ++tp) {
+                umma_f16(d_tmem, ((uint64_t)hiA << 32) | (a_tile + aoff[tp]), ((uint64_t)hiB << 32) | (b_stage + boff[tp]),
+                         idesc, tp == 0 ? acc : 1u);
+              }
+              if (c == p.nchunks - 1) umma_commit(BAR(B_ACCF + t));
+              continue;
+            }
             const int ntp = (p.skip & 2) ? 1 : p.ntaps;
             for (int tp = 0; tp < ntp; ++tp) {
               uint32_t alo = a_tile + (uint32_t)p.tapoff[tp];

@@ -17,7 +17,7 @@ __device__ __forceinline__ uint64_t make_desc(uint32_t saddr, uint32_t lbo, uint
   return d;
 }
 
-__global__ void __launch_bounds__(128) rate_kernel(int N, int layout, int iters, int a_lbo, int a_sbo, long long* out, int nissue) {
+__global__ void __launch_bounds__(128) rate_kernel(int N, int layout, int iters, int a_lbo, int a_sbo, long long* out, int nissue, int tap_pitch) {
   extern __shared__ __align__(1024) unsigned char smem[];
   __shared__ __align__(8) uint64_t bar4[4];
   __shared__ uint32_t tmem_slot;
@@ -38,13 +38,15 @@ __global__ void __launch_bounds__(128) rate_kernel(int N, int layout, int iters,
   const uint32_t tmem = tmem_slot;
   if ((threadIdx.x & 31) == 0 && warp < nissue) {
     uint64_t& bar = bar4[warp];
-    const uint32_t tmem_w = tmem + warp * 128;
+    const uint32_t tmem_w = tmem + (N > 128 ? (warp & 1) * 256 : warp * 128);
     const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(N >> 3) << 17) | ((128u >> 4) << 24);
     const uint32_t a0 = smem_u32(smem), b0 = smem_u32(smem + 32768);
     long long t0 = clock64();
     for (int i = 0; i < iters; ++i) {
       // walk K inside the operand like a real mainloop would (4 k-steps of 32 B for swizzled rows)
-      const uint32_t ko = (layout == 0) ? 0u : (uint32_t)(i & 3) * 32u;
+      // tap_pitch > 0: the A start address walks the 9 taps of a 3x3 neighbourhood (16-byte pixel steps)
+      const int tp = i % 9;
+      const uint32_t ko = (layout == 0) ? (tap_pitch > 0 ? (uint32_t)((tp / 3) * tap_pitch + tp % 3) * 16u : 0u) : (uint32_t)(i & 3) * 32u;
       uint64_t ad = make_desc(a0 + ko, a_lbo, a_sbo, layout);
       uint64_t bd = make_desc(b0 + ko, layout == 0 ? N * 16 : 0, layout == 0 ? 128 : (layout == 2 ? 1024 : (layout == 4 ? 512 : 256)), layout);
       uint32_t acc = i > 0;
@@ -70,13 +72,15 @@ int main() {
   cudaMalloc(&d, 148 * sizeof(long long));
   cudaFuncSetAttribute(rate_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024);
   const int iters = 2000;
-  struct Cfg { int layout; int lbo, sbo; const char* name; } cfgs[] = {
-      {0, 2880, 160, "none  halo(LBO 2880,SBO 160)"}, {0, 2048, 128, "none  dense(LBO 2048,SBO 128)"},
-      {2, 0, 1024, "sw128 dense SBO 1024"}};
+  struct Cfg { int layout; int lbo, sbo; const char* name; int tap_pitch; } cfgs[] = {
+      {0, 2880, 160, "none  halo(LBO 2880,SBO 160)", 0}, {0, 2880, 160, "none  halo + 3x3 tap starts", 10},
+      {0, 2048, 128, "none  dense(LBO 2048,SBO 128)", 0}, {0, 8064, 128, "none  flat(LBO 8064) + tap starts", 7},
+      {0, 8192, 128, "none  flat(LBO 8192) + tap starts", 8},
+      {2, 0, 1024, "sw128 dense SBO 1024", 0}};
   for (auto& c : cfgs)
-    for (int N : {32, 64, 128}) {
+    for (int N : {32, 64, 128, 256}) {
       for (int nissue : {1, 2, 4}) { const int grid = 148;
-        rate_kernel<<<grid, 128, 64 * 1024>>>(N, c.layout, iters, c.lbo, c.sbo, d, nissue);
+        rate_kernel<<<grid, 128, 64 * 1024>>>(N, c.layout, iters, c.lbo, c.sbo, d, nissue, c.tap_pitch);
         cudaError_t e = cudaDeviceSynchronize();
         long long h[148];
         cudaMemcpy(h, d, grid * sizeof(long long), cudaMemcpyDeviceToHost);
