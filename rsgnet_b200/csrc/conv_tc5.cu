@@ -32,9 +32,9 @@ namespace {
 using namespace umma;
 
 constexpr int TH = 16, TW = 8;                 // pixel patch = 128 MMA rows
-constexpr int NTHREADS = 608;                  // one fat persistent CTA per SM (19 warps -> 96 registers/thread)
-constexpr int MAX_MMA_WARPS = 2;               // warps 0..1 issue MMAs, round-robin over tiles (unrolled issue: two saturate N=32)
-constexpr int EPI_WARP0 = 3;                   // warp 2 = TMA producer; epilogue warps 3..18: two groups of 8
+constexpr int NTHREADS = 640;                  // one fat persistent CTA per SM (20 warps = 5 per scheduler -> 96 registers/thread)
+constexpr int MAX_MMA_WARPS = 3;               // warps 0..2 may issue MMAs (p.NMMA = 2 or 3 of them do), round-robin over tiles
+constexpr int EPI_WARP0 = 4;                   // warp 3 = TMA producer; epilogue warps 4..19: two groups of 8
 constexpr int NEPI = 2;
 struct Tc5P {
   const bf16* w;        // [nslices][ntaps][Cin/8][NS][8]
@@ -43,7 +43,7 @@ struct Tc5P {
   int KC, nchunks;      // channels per halo stage, Cin / KC
   int S;                // halo ring depth
   int NACC;             // TMEM accumulator ring depth
-  int NMMA;             // MMA-issuing warps: 2 or 4
+  int NMMA;             // MMA-issuing warps: 2 or 3 (S is a multiple of it: every issuer owns S/NMMA ring slots)
   int EW;               // epilogue warps: 4, or 8 (two column halves per TMEM lane quarter)
   int ntaps;
   // per-tap A descriptor pieces: low word = (start offset inside the stage | LBO << 16) in 16-byte units,
@@ -143,17 +143,17 @@ conv_tc5_kernel(const __grid_constant__ Tc5Maps maps, const Tc5P p) {
       for (int i = 0; i < nph; ++i) asm volatile("prefetch.tensormap [%0];" ::"l"(&maps.m[i]) : "memory");
       // each MMA warp owns its own ring of S/2 stages (slots w, w+2, ...); ring positions and phases are
       // carried incrementally: an integer division costs this single thread ~100 cycles of pure latency
-      const uint32_t S2 = (uint32_t)p.S >> 1;
-      uint32_t js[2] = {0, 0}, ph[2] = {0, 0};
+      const uint32_t S2 = (uint32_t)p.S / (uint32_t)NMMA, nmma = (uint32_t)NMMA;
+      uint32_t js0 = 0, js1 = 0, js2 = 0, ph0 = 0, ph1 = 0, ph2 = 0;     // per-issuer ring position / phase
       uint32_t it = 0;
       uint32_t w = 0;
-      for (int t = (int)first; t < (int)p.ntiles; t += (int)step, w ^= 1u) {
+      for (int t = (int)first; t < (int)p.ntiles; t += (int)step, w = (w + 1 == nmma ? 0u : w + 1)) {
         const int n = (int)fastdiv((uint32_t)t, p.magic_tpi);
         const int rem = t - n * (int)p.tiles_per_img;
         const int ty = (int)fastdiv((uint32_t)rem, p.magic_tx), tx = rem - ty * p.tiles_x;
-        uint32_t j = w ? js[1] : js[0], phase = w ? ph[1] : ph[0];
+        uint32_t j = w == 0 ? js0 : (w == 1 ? js1 : js2), phase = w == 0 ? ph0 : (w == 1 ? ph1 : ph2);
         for (int c = 0; c < p.nchunks; ++c, ++it) {
-          const int s = (int)(j * 2u + w);
+          const int s = (int)(j * nmma + w);
           mbar_wait(BAR(B_EMPTY + s), phase ^ 1u);
           if (p.dbg && blockIdx.x == 0 && blockIdx.y == 0 && it < 64) p.dbg[it * 8 + 0] = clock64();
           if (!(p.skip & 1)) {
@@ -175,7 +175,7 @@ conv_tc5_kernel(const __grid_constant__ Tc5Maps maps, const Tc5P p) {
           if (p.dbg && blockIdx.x == 0 && blockIdx.y == 0 && it < 64) p.dbg[it * 8 + 1] = clock64();
           if (++j == S2) { j = 0; phase ^= 1u; }
         }
-        if (w) { js[1] = j; ph[1] = phase; } else { js[0] = j; ph[0] = phase; }
+        if (w == 0) { js0 = j; ph0 = phase; } else if (w == 1) { js1 = j; ph1 = phase; } else { js2 = j; ph2 = phase; }
       }
     }
   } else if (warp < MAX_MMA_WARPS) {
@@ -219,17 +219,17 @@ conv_tc5_kernel(const __grid_constant__ Tc5Maps maps, const Tc5P p) {
     // instruction stream).  Each issuing warp consumes its OWN ring of S/2 stages (slots warp, warp+2, ...):
     // with one shared ring a warp could wait for phase k+1 of a slot before phase k had completed, and an
     // mbarrier parity wait cannot tell "not yet" from "one phase ago".
-    const uint32_t S2 = (uint32_t)p.S >> 1;
+    const uint32_t S2 = (uint32_t)p.S / (uint32_t)NMMA, nmma = (uint32_t)NMMA;
     uint32_t js = 0, sph = 0;                       // position / phase in this warp's stage ring
-    uint32_t b = (uint32_t)warp, aph = 0;           // accumulator index (NACC is even) / phase
+    uint32_t b = (uint32_t)warp, aph = 0;           // accumulator index (NACC >= NMMA) / phase
     uint32_t tl = (uint32_t)warp;
     for (uint32_t t = (uint32_t)first + (uint32_t)warp * (uint32_t)step; t < (uint32_t)p.ntiles;
-         t += 2u * (uint32_t)step, tl += 2u) {
+         t += nmma * (uint32_t)step, tl += nmma) {
       mbar_wait(BAR(B_ACCE + b), aph ^ 1u);          // accumulator drained by the epilogue
       const uint32_t d_tmem = tmem_base + b * (uint32_t)p.NS;
       if (p.dbg && blockIdx.x == 0 && blockIdx.y == 0 && lane == 0 && tl < 64) p.dbg[tl * 8 + 2] = clock64();
       for (int c = 0; c < p.nchunks; ++c) {
-        const int s = (int)(js * 2u + (uint32_t)warp);
+        const int s = (int)(js * nmma + (uint32_t)warp);
         mbar_wait(BAR(B_FULL + s), sph);               // halo chunk landed
         if (p.dbg && blockIdx.x == 0 && blockIdx.y == 0 && lane == 0 && tl < 64) p.dbg[tl * 8 + 3] = clock64();
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
@@ -265,7 +265,7 @@ conv_tc5_kernel(const __grid_constant__ Tc5Maps maps, const Tc5P p) {
         if (++js == S2) { js = 0; sph ^= 1u; }
       }
       if (p.dbg && blockIdx.x == 0 && blockIdx.y == 0 && lane == 0 && tl < 64) p.dbg[tl * 8 + 4] = clock64();
-      b += 2u;
+      b += nmma;
       if (b >= (uint32_t)p.NACC) { b -= (uint32_t)p.NACC; aph ^= 1u; }
     }
    }
@@ -555,7 +555,13 @@ int conv_tc5_launch(const ConvP& p, cudaStream_t s, int* handled) {
   if (nacc > MAX_ACC) nacc = MAX_ACC;
   // thin layers are bound by the per-warp MMA issue rate (~110 cycles per MMA): four issuing warps when
   // the rings can be split four ways
-  const int nmma = MAX_MMA_WARPS;
+  // three issuers when the ring splits three ways (keeps the tensor pipe fed while the others sit in their
+  // per-tile barrier round trips), else two
+  int nmma = S >= 6 ? 3 : 2;
+  { const char* e = getenv("RSG_TC5_NMMA"); if (e && (atoi(e) == 2 || atoi(e) == 3)) nmma = atoi(e); }
+  if (S < nmma) nmma = 2;
+  S = S / nmma * nmma;
+  k.S = S;
   k.NMMA = nmma;
   nacc = nacc / nmma * nmma;                              // tiles go round-robin over the MMA warps
   if (nacc < 2) nacc = 2;

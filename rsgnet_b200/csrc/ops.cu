@@ -6,71 +6,151 @@ namespace {
 
 // ---------------------------------------------------------------------------------------------
 // conv1: 3x3 s2 p1, 3 -> 64, fp32 NCHW in (optionally W-reversed), bf16 NHWC out, BN folded, ReLU.
-// pose_rsgnet.py:612-613, 922-924 (+ input.flip(3), function.py:401).  fp32 FMA on CUDA cores:
-// K = 27 is too thin for the tensor pipe and the op is bound by its 128 B/pixel output stream.
-// A warp covers 32 consecutive output pixels of ONE group of 16 channels: the weight reads are pure
-// shared-memory broadcasts (with the channel group varying inside a warp every LDS.128 took four
-// wavefronts and the kernel ran at 8 TFLOP/s), and every thread stores one full 32-byte sector.
+// pose_rsgnet.py:612-613, 922-924 (+ input.flip(3), function.py:401).
+//
+// Warp-level tensor-core formulation (the fp32 FMA version ran at 16 TFLOP/s, 8x its HBM floor).  A CTA
+// stages the (2*8+1) x (2*32+2) fp32 input patch of an 8 x 32 output tile in shared memory with cp.async,
+// one tile ahead of the math (persistent CTAs, double buffer).  For kernel row ky the GEMM K index is
+// k = kx*4 + c (kx = 0..3, c = 0..3; the kx = 3 and c = 3 entries have zero weights), so one k16 step of
+// mma.sync.m16n8k16 is one kernel row and each A-fragment register is two LDS.32 + one bf16x2 convert:
+// K = 3 x 16, N = 64 = 8 n-tiles, M = 16 consecutive output pixels.  All weights live in registers as
+// B fragments (48 per thread).  Outputs go through a per-warp shared-memory transpose so that every
+// global store is a fully used 16-byte piece of a contiguous 512-byte run.
 // ---------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(256)
+constexpr int ST_TY = 8, ST_TX = 32;
+constexpr int ST_IR = 2 * ST_TY + 1, ST_IC = 2 * ST_TX + 2;
+constexpr int ST_OPITCH = 144;                    // bytes per staged output pixel (128 + pad: conflict-free)
+
+__device__ __forceinline__ uint32_t pack2(float a, float b) {
+  __nv_bfloat162 t;
+  t.x = __float2bfloat16_rn(a);
+  t.y = __float2bfloat16_rn(b);
+  return *reinterpret_cast<uint32_t*>(&t);
+}
+
+__global__ void __launch_bounds__(256, 2)
 stem_kernel(const float* __restrict__ x, int H, int W, const float* __restrict__ w,
-            const float* __restrict__ bias, bf16* __restrict__ out, int f0, int nb, int n_crops) {
-  __shared__ float sw[27 * 64];
-  __shared__ float sb[64];
-  for (int i = threadIdx.x; i < 27 * 64; i += blockDim.x) sw[i] = w[i];
-  if (threadIdx.x < 64) sb[threadIdx.x] = bias[threadIdx.x];
-  __syncthreads();
+            const float* __restrict__ bias, bf16* __restrict__ out, int f0, int nb, int n_crops,
+            int tiles_x, int tiles_y, int ntiles) {
+  // raw fp32 patches [buffer][c][row][col], filled by cp.async one tile ahead of the math
+  __shared__ __align__(16) float sIn[2][3 * ST_IR * ST_IC];
+  __shared__ __align__(16) unsigned char sOut[8][16 * ST_OPITCH];
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int g = lane >> 2, tq = lane & 3;
   const int Ho = H >> 1, Wo = W >> 1;
-  const long long total = (long long)nb * Ho * Wo;
-  const int warp = threadIdx.x >> 5;
-  const long long pix = (long long)blockIdx.x * 64 + (warp >> 2) * 32 + (threadIdx.x & 31);
-  if (pix >= total) return;
-  const int cg = warp & 3;
-  const int ox = (int)(pix % Wo);
-  const long long r = pix / Wo;
-  const int oy = (int)(r % Ho);
-  const int fl = (int)(r / Ho);
-  const int f = f0 + fl;
-  const int crop = f % n_crops;
-  const bool flip = f >= n_crops;
-  const float* xin = x + (size_t)crop * 3 * H * W;
-  float acc[16];
+
+  auto decode = [&](int tile, int& tx, int& ty, int& fl) {
+    tx = tile % tiles_x; tile /= tiles_x;
+    ty = tile % tiles_y;
+    fl = tile / tiles_y;
+  };
+  // out-of-image pixels are the zero padding (cp.async with src-size 0 zero-fills); the W flip of the
+  // second forward is applied here, so the math below never knows about it
+  auto stage = [&](int tile, int buf) {
+    int tx, ty, fl;
+    decode(tile, tx, ty, fl);
+    const int f = f0 + fl;
+    const bool flip = f >= n_crops;
+    const float* xin = x + (size_t)(f % n_crops) * 3 * H * W;
+    const int gy0 = 2 * ty * ST_TY - 1, gx0 = 2 * tx * ST_TX - 1;
+    const uint32_t sbase = (uint32_t)__cvta_generic_to_shared(&sIn[buf][0]);
+    for (int i = tid; i < 3 * ST_IR * ST_IC; i += 256) {
+      const int c = i / (ST_IR * ST_IC);
+      const int rem = i - c * (ST_IR * ST_IC);
+      const int r = rem / ST_IC, col = rem - r * ST_IC;
+      const int gy = gy0 + r, gx = gx0 + col;
+      const bool ok = gy >= 0 && gy < H && gx >= 0 && gx < W;
+      const float* src = ok ? xin + ((size_t)c * H + gy) * W + (flip ? W - 1 - gx : gx) : xin;
+      const int sz = ok ? 4 : 0;
+      asm volatile("cp.async.ca.shared.global [%0], [%1], 4, %2;\n" ::"r"(sbase + 4u * (uint32_t)i), "l"(src), "r"(sz));
+    }
+    asm volatile("cp.async.commit_group;\n" ::);
+  };
+
+  int tile = blockIdx.x;
+  if (tile < ntiles) stage(tile, 0);
+
+  // ---- weights -> B fragments: b[ky][j][h] = {W[ky][kx][c], W[ky][kx][c+1]} for n = 8j+g, kx = tq/2 + 2h, c = 2(tq%2)
+  uint32_t bfr[3][8][2];
+  const int c0 = 2 * (tq & 1);
 #pragma unroll
-  for (int j = 0; j < 16; ++j) acc[j] = sb[cg * 16 + j];
+  for (int ky = 0; ky < 3; ++ky)
 #pragma unroll
-  for (int ci = 0; ci < 3; ++ci) {
+    for (int h = 0; h < 2; ++h) {
+      const int kx = (tq >> 1) + 2 * h;
 #pragma unroll
-    for (int ky = 0; ky < 3; ++ky) {
-      const int iy = oy * 2 - 1 + ky;
-#pragma unroll
-      for (int kx = 0; kx < 3; ++kx) {
-        const int ix = ox * 2 - 1 + kx;
-        float v = 0.f;
-        if (iy >= 0 && iy < H && ix >= 0 && ix < W)
-          v = __ldg(xin + ((size_t)ci * H + iy) * W + (flip ? W - 1 - ix : ix));
-        const float4* wp = reinterpret_cast<const float4*>(sw + ((ci * 3 + ky) * 3 + kx) * 64 + cg * 16);
-#pragma unroll
-        for (int q = 0; q < 4; ++q) {
-          float4 ww = wp[q];
-          acc[q * 4 + 0] = fmaf(v, ww.x, acc[q * 4 + 0]);
-          acc[q * 4 + 1] = fmaf(v, ww.y, acc[q * 4 + 1]);
-          acc[q * 4 + 2] = fmaf(v, ww.z, acc[q * 4 + 2]);
-          acc[q * 4 + 3] = fmaf(v, ww.w, acc[q * 4 + 3]);
+      for (int j = 0; j < 8; ++j) {
+        const int n = 8 * j + g;
+        float w0 = 0.f, w1 = 0.f;
+        if (kx < 3) {
+          w0 = __ldg(w + ((c0 * 3 + ky) * 3 + kx) * 64 + n);
+          if (c0 + 1 < 3) w1 = __ldg(w + (((c0 + 1) * 3 + ky) * 3 + kx) * 64 + n);
         }
+        bfr[ky][j][h] = pack2(w0, w1);
       }
     }
-  }
-  uint32_t pk[8];
+  float bs[8][2];
 #pragma unroll
-  for (int j = 0; j < 8; ++j) {
-    __nv_bfloat162 t;
-    t.x = __float2bfloat16_rn(fmaxf(acc[2 * j], 0.f));
-    t.y = __float2bfloat16_rn(fmaxf(acc[2 * j + 1], 0.f));
-    pk[j] = *reinterpret_cast<uint32_t*>(&t);
+  for (int j = 0; j < 8; ++j) { bs[j][0] = __ldg(bias + 8 * j + 2 * tq); bs[j][1] = __ldg(bias + 8 * j + 2 * tq + 1); }
+
+  unsigned char* so = sOut[warp];
+  for (int it = 0; tile < ntiles; tile += gridDim.x, ++it) {
+    const int buf = it & 1;
+    if (tile + (int)gridDim.x < ntiles) {
+      stage(tile + gridDim.x, buf ^ 1);
+      asm volatile("cp.async.wait_group 1;\n" ::);
+    } else {
+      asm volatile("cp.async.wait_group 0;\n" ::);
+    }
+    __syncthreads();
+    int tx, ty, fl;
+    decode(tile, tx, ty, fl);
+    const int oy = ty * ST_TY + warp, x0 = tx * ST_TX;      // one output row per warp
+    const float* p0 = &sIn[buf][c0 * ST_IR * ST_IC];        // plane of channel c0 (0 or 2)
+#pragma unroll 1
+    for (int xh = 0; xh < 2; ++xh) {
+      float acc[8][4];
+#pragma unroll
+      for (int j = 0; j < 8; ++j) { acc[j][0] = bs[j][0]; acc[j][1] = bs[j][1]; acc[j][2] = bs[j][0]; acc[j][3] = bs[j][1]; }
+#pragma unroll
+      for (int ky = 0; ky < 3; ++ky) {
+        // (row 2*warp+ky, col 2*(16*xh+g) + tq/2): channels c0, c0+1 of that pixel (channel 3 is zero)
+        const float* q0 = p0 + (2 * warp + ky) * ST_IC + 2 * (16 * xh + g) + (tq >> 1);
+        const float* q1 = q0 + ST_IR * ST_IC;
+        const bool two = c0 == 0;
+        uint32_t a[4];
+        a[0] = pack2(q0[0], two ? q1[0] : 0.f);        // pixel g,    kx = tq/2
+        a[1] = pack2(q0[16], two ? q1[16] : 0.f);      // pixel g+8
+        a[2] = pack2(q0[2], two ? q1[2] : 0.f);        // pixel g,    kx = tq/2 + 2
+        a[3] = pack2(q0[18], two ? q1[18] : 0.f);      // pixel g+8
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          asm volatile(
+              "mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};\n"
+              : "+f"(acc[j][0]), "+f"(acc[j][1]), "+f"(acc[j][2]), "+f"(acc[j][3])
+              : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(bfr[ky][j][0]), "r"(bfr[ky][j][1]));
+        }
+      }
+      // ---- ReLU, bf16, transpose through shared memory: thread (g,tq) holds channels 8j+2tq(+1) of pixels g, g+8
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        *reinterpret_cast<uint32_t*>(so + g * ST_OPITCH + j * 16 + tq * 4) = pack2(fmaxf(acc[j][0], 0.f), fmaxf(acc[j][1], 0.f));
+        *reinterpret_cast<uint32_t*>(so + (g + 8) * ST_OPITCH + j * 16 + tq * 4) = pack2(fmaxf(acc[j][2], 0.f), fmaxf(acc[j][3], 0.f));
+      }
+      __syncwarp();
+      if (oy < Ho) {
+        bf16* orow = out + (((size_t)fl * Ho + oy) * Wo + x0 + 16 * xh) * 64;
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          const int chunk = i * 32 + lane, px = chunk >> 3, part = chunk & 7;
+          if (x0 + 16 * xh + px < Wo)
+            *reinterpret_cast<uint4*>(orow + px * 64 + part * 8) = *reinterpret_cast<const uint4*>(so + px * ST_OPITCH + part * 16);
+        }
+      }
+      __syncwarp();
+    }
+    __syncthreads();          // every warp is done with sIn[buf] before the next iteration's prefetch overwrites it
   }
-  uint4* op = reinterpret_cast<uint4*>(out + ((size_t)fl * Ho * Wo + (size_t)oy * Wo + ox) * 64 + cg * 16);
-  op[0] = make_uint4(pk[0], pk[1], pk[2], pk[3]);
-  op[1] = make_uint4(pk[4], pk[5], pk[6], pk[7]);
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -367,7 +447,12 @@ int stem_launch(cudaStream_t s, const float* x, int H, int W, const float* w, co
   RSG_REQUIRE(H % 2 == 0 && W % 2 == 0, "stem: H and W must be even");
   const long long total = (long long)nb * (H / 2) * (W / 2);
   if (total == 0) return RSG_OK;
-  stem_kernel<<<ceil_div(total, 64), 256, 0, s>>>(x, H, W, w, bias, out, f0, nb, n_crops);
+  const int tiles_x = ceil_div(W / 2, ST_TX), tiles_y = ceil_div(H / 2, ST_TY);
+  const long long nblk = (long long)tiles_x * tiles_y * nb;
+  RSG_REQUIRE(nblk < (1ll << 31), "stem: too many tiles");
+  int grid = 2 * rsg_num_sms();                        // persistent: two CTAs per SM walk the tiles
+  if (grid > nblk) grid = (int)nblk;
+  stem_kernel<<<grid, 256, 0, s>>>(x, H, W, w, bias, out, f0, nb, n_crops, tiles_x, tiles_y, (int)nblk);
   RSG_LAUNCH_CHECK();
   return RSG_OK;
 }
