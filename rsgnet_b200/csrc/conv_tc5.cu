@@ -73,7 +73,7 @@ struct Tc5P {
   int skip;             // debug: bit0 no halo loads, bit1 no MMAs, bit2 no residual loads, bit3 no stores
 };
 
-constexpr int MAX_STAGES = 8;
+constexpr int MAX_STAGES = 12;
 constexpr int MAX_ACC = 8;
 constexpr int MAX_CHUNKS = 32;
 
@@ -135,27 +135,28 @@ conv_tc5_kernel(const __grid_constant__ Tc5Maps maps, const Tc5P p) {
   if (warp == MAX_MMA_WARPS) {
     // ===================== halo producer (TMA) =====================
     const int ptid = lane;
-    // One elected thread issues one 5-D TMA box per stage: (8 ch, 10 px, 18 rows, KC/8 planes, 1 crop)
-    // lands in shared memory as [KC/8][18][10][8ch]; out-of-bounds coordinates are zero-filled, which
-    // is the convolution's zero padding.
-    if (ptid == 0) {
-      const int nph = p.stride == 2 ? 4 : 1;
-      for (int i = 0; i < nph; ++i) asm volatile("prefetch.tensormap [%0];" ::"l"(&maps.m[i]) : "memory");
-      // each MMA warp owns its own ring of S/2 stages (slots w, w+2, ...); ring positions and phases are
-      // carried incrementally: an integer division costs this single thread ~100 cycles of pure latency
-      const uint32_t S2 = (uint32_t)p.S / (uint32_t)NMMA, nmma = (uint32_t)NMMA;
-      uint32_t js0 = 0, js1 = 0, js2 = 0, ph0 = 0, ph1 = 0, ph2 = 0;     // per-issuer ring position / phase
-      uint32_t it = 0;
-      uint32_t w = 0;
-      for (int t = (int)first; t < (int)p.ntiles; t += (int)step, w = (w + 1 == nmma ? 0u : w + 1)) {
+    // Lane w < NMMA feeds the ring of MMA warp w (tiles w, w+NMMA, ...): one 5-D TMA box per stage,
+    // (8 ch, 10 px, 18 rows, KC/8 planes, 1 crop), lands in shared memory as [KC/8][18][10][8ch];
+    // out-of-bounds coordinates are zero-filled, which is the convolution's zero padding.  A single
+    // thread's serial instruction stream costs ~10 cycles per instruction here, so ONE producer thread
+    // bounded the kernel at ~720 cycles per tile (profiles/r1_notes.md); the lanes run the same code on
+    // different tiles in lockstep.
+    if (ptid < NMMA) {
+      if (ptid == 0) {
+        const int nph = p.stride == 2 ? 4 : 1;
+        for (int i = 0; i < nph; ++i) asm volatile("prefetch.tensormap [%0];" ::"l"(&maps.m[i]) : "memory");
+      }
+      const uint32_t S2 = (uint32_t)p.S / (uint32_t)NMMA, nmma = (uint32_t)NMMA, w = (uint32_t)ptid;
+      uint32_t j = 0, phase = 0;                      // ring position / phase, carried incrementally
+      uint32_t it = w;                                // debug index = CTA-local tile number (nchunks == 1)
+      for (int t = (int)first + (int)w * (int)step; t < (int)p.ntiles; t += (int)nmma * (int)step) {
         const int n = (int)fastdiv((uint32_t)t, p.magic_tpi);
         const int rem = t - n * (int)p.tiles_per_img;
         const int ty = (int)fastdiv((uint32_t)rem, p.magic_tx), tx = rem - ty * p.tiles_x;
-        uint32_t j = w == 0 ? js0 : (w == 1 ? js1 : js2), phase = w == 0 ? ph0 : (w == 1 ? ph1 : ph2);
-        for (int c = 0; c < p.nchunks; ++c, ++it) {
+        for (int c = 0; c < p.nchunks; ++c) {
           const int s = (int)(j * nmma + w);
           mbar_wait(BAR(B_EMPTY + s), phase ^ 1u);
-          if (p.dbg && blockIdx.x == 0 && blockIdx.y == 0 && it < 64) p.dbg[it * 8 + 0] = clock64();
+          if (p.dbg && blockIdx.x == 0 && blockIdx.y == 0 && it < 64 && c == 0) p.dbg[it * 8 + 0] = clock64();
           if (!(p.skip & 1)) {
             mbar_arrive_expect_tx(BAR(B_FULL + s), p.tx_bytes);
             const uint32_t dst = smem_u32(sH + (size_t)s * p.stage_bytes);
@@ -172,10 +173,10 @@ conv_tc5_kernel(const __grid_constant__ Tc5Maps maps, const Tc5P p) {
           } else {
             mbar_arrive(BAR(B_FULL + s));
           }
-          if (p.dbg && blockIdx.x == 0 && blockIdx.y == 0 && it < 64) p.dbg[it * 8 + 1] = clock64();
+          if (p.dbg && blockIdx.x == 0 && blockIdx.y == 0 && it < 64 && c == 0) p.dbg[it * 8 + 1] = clock64();
           if (++j == S2) { j = 0; phase ^= 1u; }
         }
-        if (w == 0) { js0 = j; ph0 = phase; } else if (w == 1) { js1 = j; ph1 = phase; } else { js2 = j; ph2 = phase; }
+        it += nmma;
       }
     }
   } else if (warp < MAX_MMA_WARPS) {
@@ -442,9 +443,11 @@ extern "C" int rsg_conv_tc5_config(int Cin, int CoutPad, int ntaps, int mode, in
       const long long wb = (long long)ntaps * Cin * ns * 2;
       for (int kc = 64; kc >= 16; kc -= 16) {
         if (Cin % kc != 0 || Cin / kc > MAX_CHUNKS) continue;
+        { const char* e = getenv("RSG_TC5_KC"); if (e && atoi(e) != kc && Cin % atoi(e) == 0) continue; }
         const int stage = stage_bytes_of(mode, kc);
         if (wb + (long long)min_s * stage > budget) continue;
         int s = MAX_STAGES;                     // even: the MMA warps own equal parts of the ring
+        { const char* e = getenv("RSG_TC5_S"); if (e && atoi(e) >= 2 && atoi(e) <= MAX_STAGES) s = atoi(e) & ~1; }
         while (s > 2 && wb + (long long)s * stage > budget) s -= 2;
         *NS = ns; *KC = kc; *S = s;
         return 1;

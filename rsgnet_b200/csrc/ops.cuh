@@ -19,3 +19,6 @@ int relation_scores_launch(cudaStream_t s, const bf16* x, int cs, int co, int N,
                            float* out);
 int attention_launch(cudaStream_t s, const bf16* x, int x_cs, int x_co, const bf16* g, int g_cs,
                      int g_co, bf16* y, int y_cs, int y_co, int N, int S, int C);
+// tcgen05 version of the TRP core (attention_tc5.cu); *handled = 0 when the shape is left to attention_launch
+int attention_tc5_launch(cudaStream_t s, const bf16* x, int x_cs, int x_co, const bf16* g, int g_cs, int g_co,
+                         bf16* y, int y_cs, int y_co, int N, int S, int C, int* handled);

@@ -189,10 +189,16 @@ int run_op(const Op& op, const RunCtx& c, int nb, int n_crops, cudaStream_t s, i
     case OP_MAXPOOL:
       return maxpool_launch(s, (const bf16*)resolve(op.r[0], c), op.i[0], op.i[1], nb, op.i[2],
                             op.i[3], op.i[4], (bf16*)resolve(op.r[1], c));
-    case OP_ATTN:
+    case OP_ATTN: {
+      int handled = 0;
+      int rc = attention_tc5_launch(s, (const bf16*)resolve(op.r[0], c), op.i[0], op.i[1],
+                                    (const bf16*)resolve(op.r[1], c), op.i[2], op.i[3],
+                                    (bf16*)resolve(op.r[2], c), op.i[4], op.i[5], nb, op.i[6], op.i[7], &handled);
+      if (rc || handled) return rc;
       return attention_launch(s, (const bf16*)resolve(op.r[0], c), op.i[0], op.i[1],
                               (const bf16*)resolve(op.r[1], c), op.i[2], op.i[3],
                               (bf16*)resolve(op.r[2], c), op.i[4], op.i[5], nb, op.i[6], op.i[7]);
+    }
     case OP_RELSCORES:
       return relation_scores_launch(s, (const bf16*)resolve(op.r[0], c), op.i[0], op.i[1], nb,
                                     op.i[2], op.i[3], (float*)resolve(op.r[1], c));

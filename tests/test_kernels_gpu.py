@@ -233,7 +233,8 @@ def test_conv_fp32_nchw_output_and_upsampled_residuals():
     _lib.lib().rsg_plan_destroy(h)
 
 
-@pytest.mark.parametrize('C_,S_hw', [(32, (16, 12)), (16, (12, 8)), (48, (9, 7)), (64, (8, 8))])
+@pytest.mark.parametrize('C_,S_hw', [(32, (16, 12)), (16, (12, 8)), (48, (9, 7)), (64, (8, 8)), (32, (64, 48)),
+                                     (48, (24, 18)), (64, (20, 13))])
 def test_trp_attention_vs_torch(C_, S_hw):
     N = 3
     H, W = S_hw

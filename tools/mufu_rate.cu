@@ -10,7 +10,9 @@ __global__ void k(unsigned* out, int iters) {
     for (int i = 0; i < 8; ++i) {
       if (MODE == 0) asm volatile("tanh.approx.f32 %0, %0;" : "+r"(a[i]));
       else if (MODE == 1) asm volatile("tanh.approx.bf16x2 %0, %0;" : "+r"(a[i]));
-      else asm volatile("ex2.approx.ftz.bf16x2 %0, %0;" : "+r"(a[i]));
+      else if (MODE == 2) asm volatile("ex2.approx.ftz.bf16x2 %0, %0;" : "+r"(a[i]));
+      else if (MODE == 3) asm volatile("cvt.rn.bf16x2.f32 %0, %0, %1;" : "+r"(a[i]) : "r"(a[(i + 1) & 7]));
+      else { asm volatile("tanh.approx.f32 %0, %0;" : "+r"(a[i])); asm volatile("cvt.rn.bf16x2.f32 %0, %0, %1;" : "+r"(a[(i + 3) & 7]) : "r"(a[(i + 5) & 7])); }
     }
   }
   unsigned s = 0;
@@ -21,17 +23,19 @@ int main() {
   unsigned* d; cudaMalloc(&d, 148 * 8 * 1024 * 4);
   cudaEvent_t e0, e1; cudaEventCreate(&e0); cudaEventCreate(&e1);
   const int iters = 20000;
-  for (int mode = 0; mode < 3; ++mode) {
+  for (int mode = 0; mode < 5; ++mode) {
     for (int rep = 0; rep < 2; ++rep) {
       cudaEventRecord(e0);
       if (mode == 0) k<0><<<148 * 2, 1024>>>(d, iters);
       else if (mode == 1) k<1><<<148 * 2, 1024>>>(d, iters);
-      else k<2><<<148 * 2, 1024>>>(d, iters);
+      else if (mode == 2) k<2><<<148 * 2, 1024>>>(d, iters);
+      else if (mode == 3) k<3><<<148 * 2, 1024>>>(d, iters);
+      else k<4><<<148 * 2, 1024>>>(d, iters);
       cudaEventRecord(e1); cudaEventSynchronize(e1);
       float ms; cudaEventElapsedTime(&ms, e0, e1);
       double instr = 148.0 * 2 * 1024 * 8.0 * iters;      // thread-level MUFU instructions
       if (rep) printf("mode %d (%s): %.3f ms, %.2f thread-instr/clk/SM at 1.965 GHz (x2 results for packed)\n", mode,
-                      mode == 0 ? "tanh.f32" : mode == 1 ? "tanh.bf16x2" : "ex2.bf16x2", ms, instr / 148 / (ms * 1e-3 * 1.965e9));
+                      mode == 0 ? "tanh.f32" : mode == 1 ? "tanh.bf16x2" : mode == 2 ? "ex2.bf16x2" : mode == 3 ? "cvt.rn.bf16x2.f32" : "tanh.f32 + cvt.bf16x2 (pairs counted once)", ms, instr / 148 / (ms * 1e-3 * 1.965e9));
     }
   }
   return 0;
