@@ -23,10 +23,10 @@
 namespace {
 using namespace umma;
 
-constexpr int AT_BQ = 128, AT_BK = 128;
-constexpr int AT_THREADS = 608;                 // 3 + 16 warps
+constexpr int AT_BQ = 128, AT_BK = 64;
+constexpr int AT_THREADS = 352;                 // 3 + 8 warps; two CTAs per SM cover each other's barrier round trips
 constexpr int AT_W0 = 3;                        // first sigmoid warp
-constexpr int AT_SW = 16;                       // sigmoid warps
+constexpr int AT_SW = 8;                        // sigmoid warps
 constexpr int AT_KV_STAGES = 3;
 
 struct AttP {
@@ -37,7 +37,8 @@ struct AttP {
   int skip;                           // debug: bit0 no K/G loads after the first ring fill, bit1 no MUFU, bit2 no MMA2
 };
 
-struct AttMaps { CUtensorMap x, g; };
+struct AttMaps { CUtensorMap q, x, g; };     // q: 128-row boxes of x; x, g: AT_BK-row boxes
+constexpr uint32_t AT_TMEM_COLS = 256;          // S buffers at columns 0 / AT_BK, O at 2 * AT_BK
 
 __device__ __forceinline__ void tma_load_4d(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1, int c2, int c3) {
   asm volatile(
@@ -55,7 +56,7 @@ __device__ __forceinline__ uint32_t pack_bf16x2(float a, float b) {
   return *reinterpret_cast<uint32_t*>(&t);
 }
 
-__global__ void __launch_bounds__(AT_THREADS, 1)
+__global__ void __launch_bounds__(AT_THREADS, 2)
 trp_attention_tc5_kernel(const __grid_constant__ AttMaps maps, const AttP p) {
   extern __shared__ __align__(128) unsigned char smem_raw[];
   // barriers: 0 Q | KV full x3 | KV empty x3 | S full x2 | S empty x2 | P full x2 | P empty x2 | O full
@@ -77,31 +78,32 @@ trp_attention_tc5_kernel(const __grid_constant__ AttMaps maps, const AttP p) {
     mbar_init(BAR(B_Q), 1);
     for (int i = 0; i < AT_KV_STAGES; ++i) { mbar_init(BAR(B_KVF + i), 1); mbar_init(BAR(B_KVE + i), 1); }
     for (int i = 0; i < 2; ++i) {
-      mbar_init(BAR(B_SF + i), 1); mbar_init(BAR(B_SE + i), AT_SW / 2);
-      mbar_init(BAR(B_PF + i), AT_SW / 2); mbar_init(BAR(B_PE + i), 1);
+      mbar_init(BAR(B_SF + i), 1); mbar_init(BAR(B_SE + i), AT_SW);
+      mbar_init(BAR(B_PF + i), AT_SW); mbar_init(BAR(B_PE + i), 1);
     }
     mbar_init(BAR(B_OF), 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == 1) {
-    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_base_slot)), "r"(512) : "memory");
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_base_slot)), "r"(AT_TMEM_COLS) : "memory");
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
   }
   asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
   __syncthreads();
   asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
   const uint32_t tmem_base = tmem_base_slot;
-  const uint32_t tmem_o = tmem_base + 256u;            // S buffers at columns 0 / 128, O at 256
+  const uint32_t tmem_o = tmem_base + 2u * AT_BK;      // S buffers at columns 0 / AT_BK, O behind them
   const int nblk = p.nblk;
   const int c8 = p.C >> 3;
 
   if (warp == 0) {
     // ===================== TMA producer =====================
     if (lane == 0) {
+      asm volatile("prefetch.tensormap [%0];" ::"l"(&maps.q) : "memory");
       asm volatile("prefetch.tensormap [%0];" ::"l"(&maps.x) : "memory");
       asm volatile("prefetch.tensormap [%0];" ::"l"(&maps.g) : "memory");
       mbar_arrive_expect_tx(BAR(B_Q), p.q_bytes);
-      tma_load_4d(sbase, &maps.x, BAR(B_Q), 0, q0, 0, n);
+      tma_load_4d(sbase, &maps.q, BAR(B_Q), 0, q0, 0, n);
       uint32_t s = 0, ph = 0;
       for (int j = 0; j < nblk; ++j) {
         mbar_wait(BAR(B_KVE + s), ph ^ 1u);
@@ -123,8 +125,9 @@ trp_attention_tc5_kernel(const __grid_constant__ AttMaps maps, const AttP p) {
     const uint32_t idesc1 = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(AT_BK >> 3) << 17) | ((128u >> 4) << 24);
     const uint32_t idesc2 = (1u << 4) | (1u << 7) | (1u << 10) | (1u << 16) | ((uint32_t)(p.C >> 3) << 17) | ((128u >> 4) << 24);
     const uint32_t hi_k = desc_hi(128u);                          // K-major operands: SBO = 128 B (8 rows x 16 B)
-    const uint32_t lo_plane = ((2048u >> 4) & 0x3FFFu) << 16;     // ... LBO = one plane of 128 rows = 2048 B
-    const uint32_t hi_g = desc_hi(2048u);                         // G (MN-major): SBO = one channel plane
+    const uint32_t lo_plane = ((2048u >> 4) & 0x3FFFu) << 16;     // Q, P: LBO = one plane of 128 rows = 2048 B
+    const uint32_t lo_kplane = (((uint32_t)AT_BK * 16u >> 4) & 0x3FFFu) << 16;   // K: plane of AT_BK keys
+    const uint32_t hi_g = desc_hi((uint32_t)AT_BK * 16u);         // G (MN-major): SBO = one channel plane of AT_BK keys
     const uint32_t lo_g = ((128u >> 4) & 0x3FFFu) << 16;          // ... LBO = 8 keys x 16 B
     const int ks1 = p.C >> 4;                                     // k16 steps of MMA1
     const uint32_t q16 = sbase >> 4;
@@ -143,8 +146,8 @@ trp_attention_tc5_kernel(const __grid_constant__ AttMaps maps, const AttP p) {
         const uint32_t k16a = kv16 + s * kvs16;
         if (elect_one()) {
           for (int k = 0; k < ks1; ++k)
-            umma_f16(tmem_base + b * 128u, ((uint64_t)hi_k << 32) | ((q16 + (uint32_t)k * 256u) | lo_plane),
-                     ((uint64_t)hi_k << 32) | ((k16a + (uint32_t)k * 256u) | lo_plane), idesc1, k > 0);
+            umma_f16(tmem_base + b * (uint32_t)AT_BK, ((uint64_t)hi_k << 32) | ((q16 + (uint32_t)k * 256u) | lo_plane),
+                     ((uint64_t)hi_k << 32) | ((k16a + (uint32_t)k * (2u * AT_BK)) | lo_kplane), idesc1, k > 0);
           umma_commit(BAR(B_SF + b));
         }
         __syncwarp();
@@ -181,62 +184,49 @@ trp_attention_tc5_kernel(const __grid_constant__ AttMaps maps, const AttP p) {
       }
     }
   } else {
-    // ===================== sigmoid warps (3 .. 18) =====================
-    // Two groups of 8 warps; group g owns S / P buffer g, i.e. the even or the odd key blocks, so the
-    // barrier round trips of one group (~1000 cycles of pure latency per block) overlap the other's MUFU work.
-    const int grp = (warp - AT_W0) >> 3;               // 0 / 1
+    // ===================== sigmoid warps (3 .. 10) =====================
+    const int grp = 0;
     const int q = warp & 3;                            // TMEM lane quarter
-    const int half = ((warp - AT_W0) >> 2) & 1;        // key columns [64 half, 64 half + 64)
+    const int half = (warp - AT_W0) >> 2;              // key columns [32 half, 32 half + 32)
     const int row = q * 32 + lane;                     // query row inside the block
     const uint32_t tq = tmem_base + ((uint32_t)(q * 32) << 16);
-    const uint32_t b = (uint32_t)grp;
-    unsigned char* const pb = sgen + p0 + b * P_BYTES + (size_t)row * 16;
-    uint32_t ph = 0;
-    for (int j = grp; j < nblk; j += 2, ph ^= 1u) {
+    for (int j = 0; j < nblk; ++j) {
+      const uint32_t b = (uint32_t)j & 1u, ph = ((uint32_t)j >> 1) & 1u;
       mbar_wait(BAR(B_SF + b), ph);
       asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
       uint32_t v[2][16];
-      tmem_ld16(tq + b * 128u + (uint32_t)(half * 64), v[0]);
-      tmem_ld16(tq + b * 128u + (uint32_t)(half * 64 + 16), v[1]);
+      tmem_ld16(tq + b * (uint32_t)AT_BK + (uint32_t)(half * 32), v[0]);
+      tmem_ld16(tq + b * (uint32_t)AT_BK + (uint32_t)(half * 32 + 16), v[1]);
       mbar_wait(BAR(B_PE + b), ph ^ 1u);               // MMA2 of block j-2 has consumed this P buffer
+      asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+      // this warp's reads of S are done: MMA1 of block j+2 may overwrite the buffer
+      asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+      __syncwarp();
+      if (lane == 0) mbar_arrive(BAR(B_SE + b));
+      unsigned char* const pb = sgen + p0 + b * P_BYTES + (size_t)row * 16;
 #pragma unroll
-      for (int pr = 0; pr < 2; ++pr) {
-        asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-        uint32_t w[2][16];
-#pragma unroll
-        for (int i = 0; i < 16; ++i) { w[0][i] = v[0][i]; w[1][i] = v[1][i]; }
-        if (pr == 0) {                                 // second pair of 16-column loads flies during the first pair's math
-          tmem_ld16(tq + b * 128u + (uint32_t)(half * 64 + 32), v[0]);
-          tmem_ld16(tq + b * 128u + (uint32_t)(half * 64 + 48), v[1]);
-        } else {                                       // this warp's reads of S are done: MMA1 of block j+2 may overwrite it
-          asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
-          __syncwarp();
-          if (lane == 0) mbar_arrive(BAR(B_SE + b));
+      for (int cc = 0; cc < 2; ++cc) {
+        const int c0 = half * 32 + cc * 16;
+        const uint32_t* vv = v[cc];
+        uint4 o0, o1;
+        if (p.skip & 2) {
+          o0.x = pack_bf16x2(__uint_as_float(vv[0]), __uint_as_float(vv[1])); o0.y = pack_bf16x2(__uint_as_float(vv[2]), __uint_as_float(vv[3]));
+          o0.z = pack_bf16x2(__uint_as_float(vv[4]), __uint_as_float(vv[5])); o0.w = pack_bf16x2(__uint_as_float(vv[6]), __uint_as_float(vv[7]));
+          o1.x = pack_bf16x2(__uint_as_float(vv[8]), __uint_as_float(vv[9])); o1.y = pack_bf16x2(__uint_as_float(vv[10]), __uint_as_float(vv[11]));
+          o1.z = pack_bf16x2(__uint_as_float(vv[12]), __uint_as_float(vv[13])); o1.w = pack_bf16x2(__uint_as_float(vv[14]), __uint_as_float(vv[15]));
+        } else {
+          o0.x = pack_bf16x2(sigmoid_mufu(__uint_as_float(vv[0])), sigmoid_mufu(__uint_as_float(vv[1])));
+          o0.y = pack_bf16x2(sigmoid_mufu(__uint_as_float(vv[2])), sigmoid_mufu(__uint_as_float(vv[3])));
+          o0.z = pack_bf16x2(sigmoid_mufu(__uint_as_float(vv[4])), sigmoid_mufu(__uint_as_float(vv[5])));
+          o0.w = pack_bf16x2(sigmoid_mufu(__uint_as_float(vv[6])), sigmoid_mufu(__uint_as_float(vv[7])));
+          o1.x = pack_bf16x2(sigmoid_mufu(__uint_as_float(vv[8])), sigmoid_mufu(__uint_as_float(vv[9])));
+          o1.y = pack_bf16x2(sigmoid_mufu(__uint_as_float(vv[10])), sigmoid_mufu(__uint_as_float(vv[11])));
+          o1.z = pack_bf16x2(sigmoid_mufu(__uint_as_float(vv[12])), sigmoid_mufu(__uint_as_float(vv[13])));
+          o1.w = pack_bf16x2(sigmoid_mufu(__uint_as_float(vv[14])), sigmoid_mufu(__uint_as_float(vv[15])));
         }
-#pragma unroll
-        for (int cc = 0; cc < 2; ++cc) {
-          const int c0 = half * 64 + pr * 32 + cc * 16;
-          const uint32_t* vv = w[cc];
-          uint4 o0, o1;
-          if (p.skip & 2) {
-            o0.x = pack_bf16x2(__uint_as_float(vv[0]), __uint_as_float(vv[1])); o0.y = pack_bf16x2(__uint_as_float(vv[2]), __uint_as_float(vv[3]));
-            o0.z = pack_bf16x2(__uint_as_float(vv[4]), __uint_as_float(vv[5])); o0.w = pack_bf16x2(__uint_as_float(vv[6]), __uint_as_float(vv[7]));
-            o1.x = pack_bf16x2(__uint_as_float(vv[8]), __uint_as_float(vv[9])); o1.y = pack_bf16x2(__uint_as_float(vv[10]), __uint_as_float(vv[11]));
-            o1.z = pack_bf16x2(__uint_as_float(vv[12]), __uint_as_float(vv[13])); o1.w = pack_bf16x2(__uint_as_float(vv[14]), __uint_as_float(vv[15]));
-          } else {
-            o0.x = pack_bf16x2(sigmoid_mufu(__uint_as_float(vv[0])), sigmoid_mufu(__uint_as_float(vv[1])));
-            o0.y = pack_bf16x2(sigmoid_mufu(__uint_as_float(vv[2])), sigmoid_mufu(__uint_as_float(vv[3])));
-            o0.z = pack_bf16x2(sigmoid_mufu(__uint_as_float(vv[4])), sigmoid_mufu(__uint_as_float(vv[5])));
-            o0.w = pack_bf16x2(sigmoid_mufu(__uint_as_float(vv[6])), sigmoid_mufu(__uint_as_float(vv[7])));
-            o1.x = pack_bf16x2(sigmoid_mufu(__uint_as_float(vv[8])), sigmoid_mufu(__uint_as_float(vv[9])));
-            o1.y = pack_bf16x2(sigmoid_mufu(__uint_as_float(vv[10])), sigmoid_mufu(__uint_as_float(vv[11])));
-            o1.z = pack_bf16x2(sigmoid_mufu(__uint_as_float(vv[12])), sigmoid_mufu(__uint_as_float(vv[13])));
-            o1.w = pack_bf16x2(sigmoid_mufu(__uint_as_float(vv[14])), sigmoid_mufu(__uint_as_float(vv[15])));
-          }
-          // plane (c0/8 + i) holds keys c0+8i .. +7 of all 128 rows: consecutive lanes -> consecutive 16 bytes
-          *reinterpret_cast<uint4*>(pb + (size_t)(c0 >> 3) * 2048) = o0;
-          *reinterpret_cast<uint4*>(pb + (size_t)((c0 >> 3) + 1) * 2048) = o1;
-        }
+        // plane (c0/8 + i) holds keys c0+8i .. +7 of all 128 rows: consecutive lanes -> consecutive 16 bytes
+        *reinterpret_cast<uint4*>(pb + (size_t)(c0 >> 3) * 2048) = o0;
+        *reinterpret_cast<uint4*>(pb + (size_t)((c0 >> 3) + 1) * 2048) = o1;
       }
       asm volatile("fence.proxy.async.shared::cta;" ::: "memory");      // generic-proxy writes -> visible to the MMA
       __syncwarp();
@@ -250,7 +240,7 @@ trp_attention_tc5_kernel(const __grid_constant__ AttMaps maps, const AttP p) {
       bf16* dst = p.y + ((size_t)n * p.S + grow) * p.y_cs + p.y_co;
       for (int c0 = 0; c0 < p.C; c0 += 16) {
         uint32_t v[16];
-        tmem_ld16(tq + 256u + (uint32_t)c0, v);
+        tmem_ld16(tq + 2u * AT_BK + (uint32_t)c0, v);
         asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
         if (grow < p.S) {
           uint4 o0, o1;
@@ -271,18 +261,18 @@ trp_attention_tc5_kernel(const __grid_constant__ AttMaps maps, const AttP p) {
   asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
   __syncthreads();
   if (warp == 1) {
-    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512) : "memory");
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(AT_TMEM_COLS) : "memory");
   }
   (void)c8;
 }
 
-// [N, S, C] bf16 view (channel stride cs, offset co) as (8 ch, S, C/8, N); box = (8, 128, C/8, 1)
-int make_att_map(const bf16* base, int cs, int co, int N, int S, int C, CUtensorMap* m) {
+// [N, S, C] bf16 view (channel stride cs, offset co) as (8 ch, S, C/8, N); box = (8, rows, C/8, 1)
+int make_att_map(const bf16* base, int cs, int co, int N, int S, int C, int rows, CUtensorMap* m) {
   EncodeTiledFn enc = tensor_map_encoder();
   RSG_REQUIRE(enc, "cuTensorMapEncodeTiled is not available from this driver");
   cuuint64_t dims[4] = {8, (cuuint64_t)S, (cuuint64_t)(C / 8), (cuuint64_t)N};
   cuuint64_t strides[3] = {(cuuint64_t)cs * 2, 16, (cuuint64_t)S * cs * 2};
-  cuuint32_t box[4] = {8, 128, (cuuint32_t)(C / 8), 1};
+  cuuint32_t box[4] = {8, (cuuint32_t)rows, (cuuint32_t)(C / 8), 1};
   cuuint32_t estr[4] = {1, 1, 1, 1};
   CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, (void*)(base + co), dims, strides, box, estr,
                    CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
@@ -312,8 +302,9 @@ int attention_tc5_launch(cudaStream_t s, const bf16* x, int x_cs, int x_co, cons
   { const char* e = getenv("RSG_ATT_SKIP"); p.skip = e ? atoi(e) : 0; }
   AttMaps maps;
   memset(&maps, 0, sizeof(maps));
-  { int rc = make_att_map(x, x_cs, x_co, N, S, C, &maps.x); if (rc) return rc; }
-  { int rc = make_att_map(g, g_cs, g_co, N, S, C, &maps.g); if (rc) return rc; }
+  { int rc = make_att_map(x, x_cs, x_co, N, S, C, AT_BQ, &maps.q); if (rc) return rc; }
+  { int rc = make_att_map(x, x_cs, x_co, N, S, C, AT_BK, &maps.x); if (rc) return rc; }
+  { int rc = make_att_map(g, g_cs, g_co, N, S, C, AT_BK, &maps.g); if (rc) return rc; }
   const size_t smem = 128 + p.q_bytes + AT_KV_STAGES * 2u * p.kv_tile_bytes + 2u * AT_BQ * AT_BK * 2u;
   static bool attr_done = false;
   if (!attr_done) {
