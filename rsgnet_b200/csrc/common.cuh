@@ -4,6 +4,7 @@
 #include <cuda_bf16.h>
 #include <stdint.h>
 #include <stdio.h>
+#include <stdlib.h>
 #include <string.h>
 
 typedef __nv_bfloat16 bf16;
@@ -35,3 +36,25 @@ int rsg_cuda_fail(cudaError_t e, const char* what, const char* file, int line);
 static inline int ceil_div(long long a, long long b) { return (int)((a + b - 1) / b); }
 
 int rsg_num_sms();
+
+// Programmatic dependent launch (PDL): the kernel may start while its stream predecessor is still draining;
+// it must execute pdl_wait() before its first access to memory the predecessor produces or still reads.
+// Hides the launch latency and the prologue (barrier init, TMEM allocation, weight loads) of the ~300 kernels
+// of a step.  RSG_NO_PDL=1 restores plain stream-ordered launches.
+#ifdef __CUDACC__
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+
+template <typename... KArgs, typename... Args>
+inline cudaError_t launch_pdl(void (*kern)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t s, Args... args) {
+  static const bool off = getenv("RSG_NO_PDL") != nullptr;
+  cudaLaunchConfig_t cfg;
+  memset(&cfg, 0, sizeof(cfg));
+  cfg.gridDim = grid; cfg.blockDim = block; cfg.dynamicSmemBytes = smem; cfg.stream = s;
+  cudaLaunchAttribute at[1];
+  at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  at[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = at; cfg.numAttrs = off ? 0 : 1;
+  return cudaLaunchKernelEx(&cfg, kern, args...);
+}
+#endif

@@ -128,6 +128,7 @@ conv_tc5_kernel(const __grid_constant__ Tc5Maps maps, const Tc5P p) {
   __syncthreads();
   asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
   const uint32_t tmem_base = tmem_base_slot;
+  if (threadIdx.x == 0) pdl_launch_dependents();       // the next kernel may begin its prologue as SMs free up
 
   const long long first = blockIdx.x, step = gridDim.x;
 
@@ -142,6 +143,7 @@ conv_tc5_kernel(const __grid_constant__ Tc5Maps maps, const Tc5P p) {
     // bounded the kernel at ~720 cycles per tile (profiles/r1_notes.md); the lanes run the same code on
     // different tiles in lockstep.
     if (ptid < NMMA) {
+      pdl_wait();                                      // activations of the previous kernel
       if (ptid == 0) {
         const int nph = p.stride == 2 ? 4 : 1;
         for (int i = 0; i < nph; ++i) asm volatile("prefetch.tensormap [%0];" ::"l"(&maps.m[i]) : "memory");
@@ -291,6 +293,7 @@ conv_tc5_kernel(const __grid_constant__ Tc5Maps maps, const Tc5P p) {
     bf16* const outp = p.out + p.out_co;
     const uint32_t tq = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)cbeg;
     const uint32_t bar_accf = opaque(BAR(B_ACCF)), bar_acce = opaque(BAR(B_ACCE));
+    pdl_wait();                                        // residual terms are read, outputs written: previous kernel done
     uint32_t b = (uint32_t)egroup, aph = 0, tl = (uint32_t)egroup;      // accumulator index / phase, carried incrementally
     for (uint32_t t = (uint32_t)first + (uint32_t)egroup * (uint32_t)step; t < (uint32_t)p.ntiles;
          t += (uint32_t)NEPI * (uint32_t)step, tl += NEPI) {
@@ -600,8 +603,7 @@ int conv_tc5_launch(const ConvP& p, cudaStream_t s, int* handled) {
       if (rc) return rc;
     }
   }
-  conv_tc5_kernel<<<grid, threads, smem, s>>>(maps, k);
-  RSG_LAUNCH_CHECK();
+  RSG_CUDA(launch_pdl(conv_tc5_kernel, grid, dim3(threads), smem, s, maps, k));
   if (k.dbg) {
     static int dumped = 0;
     if (dumped++ == 3) {

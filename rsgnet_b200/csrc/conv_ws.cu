@@ -108,10 +108,12 @@ conv_ws_kernel(const __grid_constant__ CUtensorMap in_map, const WsP p) {
   const uint32_t tmem_base = tmem_base_slot;
   const int first = blockIdx.x, step = gridDim.x;
   if (threadIdx.x == 0) WS_STAMP(1);
+  if (threadIdx.x == 0) pdl_launch_dependents();
 
   if (warp == 2) {
     // ===================== producer: one TMA box + ntaps bulk copies per stage =====================
     if (lane == 0) {
+      pdl_wait();                                      // activations of the previous kernel
       asm volatile("prefetch.tensormap [%0];" ::"l"(&in_map) : "memory");
       const unsigned char* wsl = reinterpret_cast<const unsigned char*>(p.w) +
                                  (size_t)slice * p.ntaps * (size_t)(p.Cin >> 3) * p.NS * 16u;
@@ -214,6 +216,7 @@ conv_ws_kernel(const __grid_constant__ CUtensorMap in_map, const WsP p) {
     bf16* const outp = p.out + p.out_co + gch0;
     const uint32_t tq = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)cbeg;
     const uint32_t bar_accf = opaque(BAR(B_ACCF)), bar_acce = opaque(BAR(B_ACCE));
+    pdl_wait();                                        // residual terms are read, outputs written: previous kernel done
     uint32_t st = 0;
     for (int u = first; u < p.nsuper; u += step, ++st) {
       for (int t = egroup; t < p.T; t += 2) {
@@ -464,8 +467,7 @@ int conv_ws_launch(const ConvP& p, cudaStream_t s, int* handled) {
   CUtensorMap map;
   memset(&map, 0, sizeof(map));
   { int rc = make_flat_map(p, c, &map); if (rc) return rc; }
-  conv_ws_kernel<<<grid, WS_THREADS, smem, s>>>(map, k);
-  RSG_LAUNCH_CHECK();
+  RSG_CUDA(launch_pdl(conv_ws_kernel, grid, dim3(WS_THREADS), smem, s, map, k));
   *handled = 1;
   return RSG_OK;
 }
