@@ -141,7 +141,7 @@ def run_reference(args):
 
 # dram__bytes_read.sum + dram__bytes_write.sum per launch of the dominant kernel, from the committed
 # `ncu --set full` capture of this same command (profiles/r1_conv_tc5_ncu_details.txt, 512 forwards)
-NCU_TRAFFIC = {('conv_tcgen05', 'conv 32->32 taps9 s1 64x48'): 100.73e6 + 52.91e6}
+NCU_TRAFFIC = {('conv_tcgen05', 'conv 32->32 taps9 s1 64x48 +res'): 201.44e6 + 72.35e6}
 
 FAMILY = {0: 'stem', 1: 'conv_mma', 2: 'conv_tcgen05', 3: 'fuse', 4: 'maxpool', 5: 'trp_attention',
           6: 'relation_scores', 7: 'groupnorm', 8: 'bilinear', 9: 'conv_ws_tcgen05'}
@@ -254,26 +254,41 @@ def main():
     with torch.cuda.stream(stream):
         eng.profile(pipe.x, pipe.heat, nb, B)                     # warm
         ms_op, kind, flops, names, shapes = eng.profile(pipe.x, pipe.heat, nb, B)
+    op_bytes = eng.last_profile_bytes
     fam, groups = {}, {}
-    for m, k, f, sh in zip(ms_op, kind, flops, shapes):
+    for m, k, f, sh, by in zip(ms_op, kind, flops, shapes, op_bytes):
         if m < 0:
             continue
-        d = fam.setdefault(FAMILY[int(k)], [0.0, 0.0, 0])
-        d[0] += float(m); d[1] += float(f); d[2] += 1
-        g = groups.setdefault((FAMILY[int(k)], sh), [0.0, 0.0, 0])
-        g[0] += float(m); g[1] += float(f); g[2] += 1
+        d = fam.setdefault(FAMILY[int(k)], [0.0, 0.0, 0, 0.0])
+        d[0] += float(m); d[1] += float(f); d[2] += 1; d[3] += float(by)
+        g = groups.setdefault((FAMILY[int(k)], sh), [0.0, 0.0, 0, 0.0])
+        g[0] += float(m); g[1] += float(f); g[2] += 1; g[3] += float(by)
     total_ms = sum(v[0] for v in fam.values())
-    # dominant kernel = the (kernel, shape) group with the largest share of the step
-    (dom_fam, dom_shape), (dom_ms, dom_fl, dom_n) = max(groups.items(), key=lambda kv: kv[1][0])
+    # dominant kernel = the (kernel, shape) group with the largest share of the step.  Its roofline is the one
+    # that binds: the larger of (algorithmic bytes / measured HBM peak) and (executed FLOPs / measured bf16 peak).
+    (dom_fam, dom_shape), (dom_ms, dom_fl, dom_n, dom_by) = max(groups.items(), key=lambda kv: kv[1][0])
     per_launch_ms = dom_ms / dom_n
-    achieved = dom_fl / dom_n / (per_launch_ms * 1e-3) / 1e12 if dom_ms > 0 else 0.0
-    traffic = NCU_TRAFFIC.get((dom_fam, dom_shape.replace(' +res', '')))
-    roofline = {'bound': 'tensor', 'kernel': f'{dom_fam}: {dom_shape} x {nb} forwards', 'achieved': achieved,
-                'peak': pk['tf_sus'], 'unit': 'TFLOP/s', 'frac': achieved / pk['tf_sus'], 'traffic': traffic,
-                'peak_source': pk['src'] + ' bf16_tflops_sustained',
-                'algorithmic_flops_per_launch': dom_fl / dom_n, 'us_per_launch': per_launch_ms * 1e3,
+    tf = dom_fl / dom_n / (per_launch_ms * 1e-3) / 1e12 if dom_ms > 0 else 0.0
+    gbs = dom_by / dom_n / (per_launch_ms * 1e-3) / 1e9 if dom_ms > 0 else 0.0
+    floor_tensor_us = dom_fl / dom_n / (pk['tf_sus'] * 1e12) * 1e6
+    floor_hbm_us = dom_by / dom_n / (pk['hbm'] * 1e9) * 1e6
+    traffic = NCU_TRAFFIC.get((dom_fam, dom_shape))
+    hbm_bound = floor_hbm_us >= floor_tensor_us
+    roofline = {'bound': 'hbm' if hbm_bound else 'tensor',
+                'kernel': f'{dom_fam}: {dom_shape} x {nb} forwards',
+                'achieved': gbs if hbm_bound else tf,
+                'peak': pk['hbm'] if hbm_bound else pk['tf_sus'],
+                'unit': 'GB/s' if hbm_bound else 'TFLOP/s',
+                'frac': (gbs / pk['hbm']) if hbm_bound else (tf / pk['tf_sus']),
+                'traffic': traffic,
+                'peak_source': pk['src'] + (' hbm_gbs' if hbm_bound else ' bf16_tflops_sustained'),
+                'algorithmic_bytes_per_launch': dom_by / dom_n, 'algorithmic_flops_per_launch': dom_fl / dom_n,
+                'floor_us': {'hbm': floor_hbm_us, 'tensor': floor_tensor_us},
+                'other_bound': {'tflops': tf, 'frac_of_bf16_peak': tf / pk['tf_sus'], 'gbs': gbs, 'frac_of_hbm_peak': gbs / pk['hbm']},
+                'us_per_launch': per_launch_ms * 1e3,
                 'launches_per_step': dom_n, 'share_of_step': dom_ms / total_ms if total_ms else None,
                 'families': {k: {'ms': round(v[0], 4), 'tflops': (v[1] / (v[0] * 1e-3) / 1e12 if v[0] > 0 else 0.0),
+                                 'gbs_algorithmic': (v[3] / (v[0] * 1e-3) / 1e9 if v[0] > 0 else 0.0),
                                  'launches': v[2], 'share': round(v[0] / total_ms, 4)} for k, v in fam.items()}}
     if args.dump_profile:
         with open(args.dump_profile, 'w') as f:

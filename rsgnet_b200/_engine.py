@@ -697,14 +697,33 @@ class Engine:
             _lib.check(L.rsg_plan_profile(self.plan, _lib.stream_ptr(self.device), ext, N_EXT, nb,
                                           n_crops, 0, ms.ctypes.data, kind.ctypes.data,
                                           flops.ctypes.data))
-        names, shapes = [], []
+        names, shapes, nbytes = [], [], []
         for k, p, _ in self.pb.ops:
             names.append(p.get('name', k) if isinstance(p, dict) else k)
             if k == 'conv':
                 shapes.append(f"conv {p['cin']}->{p['cout']} taps{len(p['taps'])} s{p['stride']} "
                               f"{p['Hout']}x{p['Wout']}{' +res' * len(p['res'])}")
+                # algorithmic bytes per forward: input read once, output written once, every residual term read
+                # once at its own resolution (weights are negligible and L2-resident)
+                src = p['src']
+                by = src.H * src.W * p['cin'] * 2
+                by += p['Hout'] * p['Wout'] * p['omul'] ** 2 * p['cout'] * (4 if p['out_f32'] is not None else 2) \
+                    // (4 if p.get('psc') else 1)
+                by += sum(v.H * v.W * p['cout'] * 2 for v, _ in p['res'])
             else:
                 shapes.append(k)
+                if k == 'stem':
+                    by = 3 * p['H'] * p['W'] * 4 + (p['H'] // 2) * (p['W'] // 2) * 64 * 2
+                elif k == 'fuse':
+                    by = sum(v.H * v.W * p['dst'].C * 2 for v, _ in p['terms']) + p['dst'].H * p['dst'].W * p['dst'].C * 2
+                elif k == 'attention':
+                    by = 3 * p['x'].H * p['x'].W * p['x'].C * 2
+                elif k == 'groupnorm':
+                    by = 2 * p['x'].H * p['x'].W * p['x'].C * 2
+                else:
+                    by = 0
+            nbytes.append(float(by) * nb)
+        self.last_profile_bytes = np.asarray(nbytes)
         return ms, kind, flops, names, shapes
 
     def last_launches(self):
