@@ -174,6 +174,8 @@ def main():
     dist = None
     if world > 1:
         import torch.distributed as dist
+        # stdout carries exactly one JSON line: keep NCCL's version banner (NCCL_DEBUG=VERSION/INFO) off it
+        os.environ['NCCL_DEBUG'] = 'WARN'
         dist.init_process_group('nccl', device_id=dev)
 
     def barrier():
