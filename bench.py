@@ -10,8 +10,10 @@ flip-average, argmax / quarter-offset decode, inverse affine -> 12 bytes per joi
   value : crops/s with the batch already resident in HBM (device-timed, CUDA events)
   e2e   : crops/s through the public API (rsgnet_b200.pipeline.CropPipeline.__call__) with pinned
           HOST buffers: H2D of the crops + D2H of preds/maxvals inside the timed region
-  roofline : the dominant kernel family of the step (by device time, from rsg_plan_profile's
-          per-op CUDA-event timings taken live in this process), against MEASURED_PEAKS.json
+  roofline : the dominant (kernel, shape) group of the step (by device time, from rsg_plan_profile's
+          per-op CUDA-event timings taken live in this process) against the bound that binds it --
+          algorithmic bytes vs measured HBM copy bandwidth, or executed FLOPs vs measured bf16 peak
+          (MEASURED_PEAKS.json); both floors are reported
   cpu_baseline : the CPU oracle (oracle/model_oracle.py + oracle/decode_oracle.py, a port of the
           reference's torch/NumPy path) on this box's host cores, bounded sample
 `--impl reference` times that CPU path as its own arm (the reference is Python importing from
