@@ -157,6 +157,13 @@ int rsg_plan_add_relation_scores(rsg_plan*, rsg_ref x, int x_cs, int x_co, int S
 int rsg_plan_add_groupnorm(rsg_plan*, rsg_ref in, int in_cs, int in_co, rsg_ref gamma,
                            rsg_ref beta, int groups, float eps, rsg_ref out, int out_cs,
                            int out_co, int S, int C);
+/* Fused BasicBlock (pose_rsgnet.py:25-54): out = relu(bn2(conv2(relu(bn1(conv1(x))))) + x), two 3x3 stride-1
+ * C -> C convs with BN folded into w1/b1, w2/b2 (bf16 [9][C/8][C][8] = the tcgen05 packing with NS = C, f32 [C]).
+ * The intermediate never leaves the SM.  rsg_basic_block_supported says whether the fused kernel covers (C, H, W);
+ * otherwise describe the block as two rsg_plan_add_conv ops. */
+int rsg_basic_block_supported(int C, int H, int W);
+int rsg_plan_add_basic_block(rsg_plan*, rsg_ref in, int in_cs, int in_co, int H, int W, int C, rsg_ref w1, rsg_ref b1,
+                             rsg_ref w2, rsg_ref b2, rsg_ref out, int out_cs, int out_co);
 /* bilinear x2, align_corners=True (+ optional sigmoid) on f32 NCHW (pose_rsgnet.py:1009-1013). */
 int rsg_plan_add_bilinear2x(rsg_plan*, rsg_ref in, rsg_ref out, int C, int H, int W, int sigmoid);
 /* Mark ops added after this call as "aux": skipped by rsg_plan_run unless with_aux != 0. */
@@ -170,7 +177,7 @@ int rsg_plan_run(rsg_plan*, void* stream, void* const* ext, int n_ext, int n_fwd
 /* Measurement aid: run ONE chunk of `nb` forwards eagerly with a CUDA event pair around every op.
  * ms[i] = device time of op i, kind[i]: 0 stem, 1 conv (generic mma.sync kernel), 2 conv (tcgen05
  * kernel), 3 fuse, 4 maxpool, 5 attention, 6 relation_scores, 7 groupnorm, 8 bilinear, 9 conv
- * (weight-streaming tcgen05 kernel);
+ * (weight-streaming tcgen05 kernel), 10 fused basic block;
  * flops[i] = MAC*2 the op executes for nb forwards (0 for the element-wise ops).  Arrays must hold
  * rsg_plan_num_ops entries; ops skipped (aux) get ms = -1. */
 int rsg_plan_profile(rsg_plan*, void* stream, void* const* ext, int n_ext, int nb, int n_crops,

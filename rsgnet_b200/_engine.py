@@ -334,6 +334,11 @@ def emit(builder, plan):
                                                 _ref(p['gamma'], cp), _ref(p['beta'], cp),
                                                 p['groups'], EPS, _ref(y, cp), y.buf.C, y.co,
                                                 x.H * x.W, x.C))
+        elif kind == 'bblock':
+            src, dst = p['src'], p['dst']
+            _lib.check(L.rsg_plan_add_basic_block(plan, _ref(src, cp), src.buf.C, src.co, src.H, src.W, p['C'],
+                                                  _ref(p['w1'], cp), _ref(p['b1'], cp), _ref(p['w2'], cp),
+                                                  _ref(p['b2'], cp), _ref(dst, cp), dst.buf.C, dst.co))
         elif kind == 'bilinear':
             _lib.check(L.rsg_plan_add_bilinear2x(plan, _ref(p['src'], cp), _ref(p['out'], cp),
                                                  p['C'], p['H'], p['W'], int(p['sigmoid'])))
@@ -376,6 +381,22 @@ def _bottleneck(pb, P, x):
 
 
 def _basic(pb, P, x):
+    w1, b1 = _fold(P['conv1.weight'], P.bn('bn1'))
+    w2, b2 = _fold(P['conv2.weight'], P.bn('bn2'))
+    Cb = w1.shape[0]
+    if (w1.shape == (Cb, Cb, 3, 3) and w2.shape == (Cb, Cb, 3, 3) and x.C == Cb
+            and _lib.lib().rsg_basic_block_supported(Cb, x.H, x.W)):
+        # one fused kernel: the intermediate stays in shared memory, x is read once (input patch = residual)
+        dst = View(pb.buf(P.prefix + 'block', x.H, x.W, Cb))
+
+        def pack(w):        # [9][1 slice][C/8][C][8]: the tcgen05 packing with NS = C
+            wt = w.transpose(2, 3, 0, 1).reshape(9, 1, Cb, Cb // 8, 8)
+            return pb.const(_bf16_bits(wt.transpose(1, 0, 3, 2, 4)))
+        pb.simple('bblock', dict(src=x, dst=dst, C=Cb, w1=pack(w1), b1=pb.const(b1.astype(np.float32)),
+                                 w2=pack(w2), b2=pb.const(b2.astype(np.float32)), name=P.prefix + 'block(fused)'),
+                  [x.buf], [dst.buf])
+        pb.flops_per_fwd += 2 * 2 * 9 * Cb * Cb * x.H * x.W
+        return dst
     y = _conv_bn(pb, P, 'conv1', 'bn1', x, relu=True)
     return _conv_bn(pb, P, 'conv2', 'bn2', y, relu=True, res=[(x, 0)])
 
@@ -716,6 +737,8 @@ class Engine:
                     by = 3 * p['H'] * p['W'] * 4 + (p['H'] // 2) * (p['W'] // 2) * 64 * 2
                 elif k == 'fuse':
                     by = sum(v.H * v.W * p['dst'].C * 2 for v, _ in p['terms']) + p['dst'].H * p['dst'].W * p['dst'].C * 2
+                elif k == 'bblock':
+                    by = 2 * p['src'].H * p['src'].W * p['C'] * 2
                 elif k == 'attention':
                     by = 3 * p['x'].H * p['x'].W * p['x'].C * 2
                 elif k == 'groupnorm':

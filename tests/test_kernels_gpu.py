@@ -200,6 +200,40 @@ def test_deconv4_fused_pixel_shuffle_vs_torch(C_, H, W, N):
     _lib.lib().rsg_plan_destroy(h)
 
 
+@pytest.mark.parametrize('C_,H,W,N', [(32, 16, 8, 2), (32, 64, 48, 7), (48, 24, 18, 3), (32, 21, 13, 3), (32, 32, 24, 200)])
+def test_fused_basic_block_vs_torch(C_, H, W, N):
+    """BasicBlock (pose_rsgnet.py:25-54) as one kernel: relu(bn2(conv2(relu(bn1(conv1(x))))) + x); the fused kernel
+    rounds the intermediate to bf16 exactly like the two-conv path does."""
+    g = torch.Generator().manual_seed(C_ * 3 + H + N)
+    x = torch.randn(N, C_, H, W, generator=g).bfloat16().float()
+    sd = {}
+    for i in (1, 2):
+        sd[f'conv{i}.weight'] = (torch.randn(C_, C_, 3, 3, generator=g) / (C_ * 9) ** 0.5)
+        sd[f'bn{i}.weight'] = torch.rand(C_, generator=g) + 0.5
+        sd[f'bn{i}.bias'] = torch.randn(C_, generator=g) * 0.1
+        sd[f'bn{i}.running_mean'] = torch.randn(C_, generator=g) * 0.1
+        sd[f'bn{i}.running_var'] = torch.rand(C_, generator=g) + 0.5
+    pb = PlanBuilder(N, reuse=False)
+    xin = pb.buf('x', H, W, C_)
+    out = _engine._basic(pb, _engine._Params(sd), View(xin))
+    assert [k for k, _, _ in pb.ops] == ['bblock']          # the fused form was chosen
+    h = _run(pb, N)
+    pb.tensor_of(xin)[:N] = x.permute(0, 2, 3, 1).cuda().bfloat16()
+    pb.tensor_of(out.buf).fill_(7.0)
+    _exec(h, N)
+
+    def bn(v, i):
+        return F.batch_norm(v, sd[f'bn{i}.running_mean'].cuda(), sd[f'bn{i}.running_var'].cuda(), sd[f'bn{i}.weight'].cuda(),
+                            sd[f'bn{i}.bias'].cuda(), False, 0.0, _engine.EPS)
+    xc = x.cuda()
+    y = F.relu(bn(F.conv2d(xc, sd['conv1.weight'].cuda(), None, 1, 1), 1))
+    ref = F.relu(bn(F.conv2d(y, sd['conv2.weight'].cuda(), None, 1, 1), 2) + xc).cpu()
+    got = pb.tensor_of(out.buf)[:N].float().permute(0, 3, 1, 2).cpu()
+    err = (got - ref).abs().max().item()
+    assert err <= 2e-2 * max(ref.abs().max().item(), 1.0), err
+    _lib.lib().rsg_plan_destroy(h)
+
+
 def test_conv_fp32_nchw_output_and_upsampled_residuals():
     N, cin, K, H, W = 3, 32, 17, 16, 12
     g = torch.Generator().manual_seed(1)

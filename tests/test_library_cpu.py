@@ -68,7 +68,8 @@ def test_plan_builder_graph(key, n_conv):
     kinds = {}
     for k, _, _ in pb.ops:
         kinds[k] = kinds.get(k, 0) + 1
-    assert kinds['stem'] == 1 and kinds['conv'] == n_conv and kinds['fuse'] == 8
+    # a fused BasicBlock op (C0 = 32 branch) stands for two convs
+    assert kinds['stem'] == 1 and kinds['conv'] + 2 * kinds.get('bblock', 0) == n_conv and kinds['fuse'] == 8
     if key == 'w32_crowdpose':
         assert kinds['attention'] == 1 and kinds['groupnorm'] == 1 and info['S'] == 3072
         # executed FLOPs: the reference graph (18.881 GFLOP/fwd) minus the folded type
