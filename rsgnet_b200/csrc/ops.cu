@@ -183,31 +183,38 @@ __device__ __forceinline__ uint4 pack8(const float* a) {
   return o;
 }
 
+// one block per output row (n, y): 32-bit index math only (the first version spent most of its time in five
+// 64-bit divisions per thread), 16 bytes per thread, consecutive threads = consecutive bytes of the row
 __global__ void __launch_bounds__(256) fuse_kernel(const FuseP p) {
   const int c8 = p.C >> 3;
-  const long long total = (long long)p.N * p.H * p.W * c8;
-  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= total) return;
-  const int c = (int)(i % c8) * 8;
-  long long r = i / c8;
-  const int x = (int)(r % p.W);
-  r /= p.W;
-  const int y = (int)(r % p.H);
-  const int n = (int)(r / p.H);
-  float a[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+  const int row = blockIdx.x;
+  const int n = row / p.H, y = row - n * p.H;
+  const int per_row = p.W * c8;
+  const bf16* base[4];
 #pragma unroll
   for (int t = 0; t < 4; ++t) {
     if (t < p.nterms) {
       const ResP& q = p.t[t];
-      const bf16* src = q.p + ((size_t)((size_t)(q.bs0 ? 0 : n) * q.H + (y >> q.shift)) * q.W + (x >> q.shift)) * q.cs + q.co + c;
-      add8(a, __ldg(reinterpret_cast<const uint4*>(src)));
+      base[t] = q.p + ((size_t)(q.bs0 ? 0 : n) * q.H + (y >> q.shift)) * q.W * q.cs + q.co;
     }
   }
-  if (p.relu) {
+  bf16* orow = p.out + ((size_t)n * p.H + y) * p.W * p.out_cs + p.out_co;
+  for (int e = threadIdx.x; e < per_row; e += blockDim.x) {
+    const int x = e / c8, c = (e - x * c8) * 8;
+    float a[8] = {0, 0, 0, 0, 0, 0, 0, 0};
 #pragma unroll
-    for (int j = 0; j < 8; ++j) a[j] = fmaxf(a[j], 0.f);
+    for (int t = 0; t < 4; ++t) {
+      if (t < p.nterms) {
+        const ResP& q = p.t[t];
+        add8(a, __ldg(reinterpret_cast<const uint4*>(base[t] + (x >> q.shift) * q.cs + c)));
+      }
+    }
+    if (p.relu) {
+#pragma unroll
+      for (int j = 0; j < 8; ++j) a[j] = fmaxf(a[j], 0.f);
+    }
+    *reinterpret_cast<uint4*>(orow + (size_t)x * p.out_cs + c) = pack8(a);
   }
-  *reinterpret_cast<uint4*>(p.out + ((size_t)((size_t)n * p.H + y) * p.W + x) * p.out_cs + p.out_co + c) = pack8(a);
 }
 
 // 2x2 max-pool, stride 2 (association.py:254, 286-287)
@@ -385,36 +392,47 @@ relation_scores_kernel(const bf16* __restrict__ x, int cs, int co, int S, int C,
 template <int CIN>
 __global__ void __launch_bounds__(256)
 head1x1_kernel(const bf16* __restrict__ in, int in_cs, int in_co, const bf16* __restrict__ w, int w_ld,
-               const float* __restrict__ bias, int Cout, long long M, int HW, float* __restrict__ out, int relu) {
+               const float* __restrict__ bias, int Cout, unsigned M, unsigned HW, float* __restrict__ out, int relu) {
   __shared__ float sw[32 * CIN];
   __shared__ float sb[32];
   for (int i = threadIdx.x; i < Cout * CIN; i += blockDim.x) sw[i] = __bfloat162float(w[(i / CIN) * w_ld + (i % CIN)]);
   if (threadIdx.x < Cout) sb[threadIdx.x] = bias[threadIdx.x];
   __syncthreads();
-  const long long m = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-  if (m >= M) return;
-  float x[CIN];
-  const uint4* src = reinterpret_cast<const uint4*>(in + (size_t)m * in_cs + in_co);
+  // two pixels per thread (256 apart, so both stay coalesced): every broadcast weight read feeds 8 FMAs
+  const unsigned m0 = blockIdx.x * 512u + threadIdx.x, m1 = m0 + 256u;
+  if (m0 >= M) return;
+  const bool two = m1 < M;
+  float x0[CIN], x1[CIN];
+  const uint4* s0 = reinterpret_cast<const uint4*>(in + (size_t)m0 * in_cs + in_co);
+  const uint4* s1 = reinterpret_cast<const uint4*>(in + (size_t)(two ? m1 : m0) * in_cs + in_co);
 #pragma unroll
   for (int j = 0; j < CIN / 8; ++j) {
-    const uint4 u = __ldg(src + j);
-    const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&u);
+    const uint4 u0 = __ldg(s0 + j), u1 = __ldg(s1 + j);
+    const __nv_bfloat162* h0 = reinterpret_cast<const __nv_bfloat162*>(&u0);
+    const __nv_bfloat162* h1 = reinterpret_cast<const __nv_bfloat162*>(&u1);
 #pragma unroll
-    for (int e = 0; e < 4; ++e) { x[j * 8 + 2 * e] = __bfloat162float(h[e].x); x[j * 8 + 2 * e + 1] = __bfloat162float(h[e].y); }
+    for (int e = 0; e < 4; ++e) {
+      x0[j * 8 + 2 * e] = __bfloat162float(h0[e].x); x0[j * 8 + 2 * e + 1] = __bfloat162float(h0[e].y);
+      x1[j * 8 + 2 * e] = __bfloat162float(h1[e].x); x1[j * 8 + 2 * e + 1] = __bfloat162float(h1[e].y);
+    }
   }
-  const long long n = m / HW;
-  float* op = out + (size_t)n * Cout * HW + (m - n * HW);
+  const unsigned n0 = m0 / HW, n1 = (two ? m1 : m0) / HW;
+  float* op0 = out + (size_t)n0 * Cout * HW + (m0 - n0 * HW);
+  float* op1 = out + (size_t)n1 * Cout * HW + ((two ? m1 : m0) - n1 * HW);
   for (int k = 0; k < Cout; ++k) {
-    float a = sb[k];
+    float a0 = sb[k], a1 = a0;
     const float4* wk = reinterpret_cast<const float4*>(sw + k * CIN);
 #pragma unroll
     for (int j = 0; j < CIN / 4; ++j) {
       const float4 ww = wk[j];
-      a = fmaf(x[4 * j], ww.x, a); a = fmaf(x[4 * j + 1], ww.y, a);
-      a = fmaf(x[4 * j + 2], ww.z, a); a = fmaf(x[4 * j + 3], ww.w, a);
+      a0 = fmaf(x0[4 * j], ww.x, a0); a0 = fmaf(x0[4 * j + 1], ww.y, a0);
+      a0 = fmaf(x0[4 * j + 2], ww.z, a0); a0 = fmaf(x0[4 * j + 3], ww.w, a0);
+      a1 = fmaf(x1[4 * j], ww.x, a1); a1 = fmaf(x1[4 * j + 1], ww.y, a1);
+      a1 = fmaf(x1[4 * j + 2], ww.z, a1); a1 = fmaf(x1[4 * j + 3], ww.w, a1);
     }
-    if (relu) a = fmaxf(a, 0.f);
-    op[(size_t)k * HW] = a;
+    if (relu) { a0 = fmaxf(a0, 0.f); a1 = fmaxf(a1, 0.f); }
+    op0[(size_t)k * HW] = a0;
+    if (two) op1[(size_t)k * HW] = a1;
   }
 }
 
@@ -423,14 +441,14 @@ head1x1_kernel(const bf16* __restrict__ in, int in_cs, int in_co, const bf16* __
 int head1x1_launch(const ConvP& p, cudaStream_t s, int* handled) {
   *handled = 0;
   if (!p.out_f32 || p.out || p.ntaps != 1 || p.dy[0] != 0 || p.dx[0] != 0 || p.stride != 1 || p.omul != 1 ||
-      p.nres != 0 || p.Cout > 32 || p.in_cs % 8 != 0 || p.in_co % 8 != 0)
+      p.nres != 0 || p.Cout > 32 || p.in_cs % 8 != 0 || p.in_co % 8 != 0 || p.M >= (1ll << 31))
     return RSG_OK;
   if (p.Cin != 16 && p.Cin != 32 && p.Cin != 48 && p.Cin != 64) return RSG_OK;
   *handled = 1;
   if (p.M == 0) return RSG_OK;
   const int HW = p.Hout * p.Wout;
-  dim3 grid(ceil_div(p.M, 256));
-#define RSG_HEAD(C) head1x1_kernel<C><<<grid, 256, 0, s>>>(p.in, p.in_cs, p.in_co, p.w, p.CinPad, p.bias, p.Cout, p.M, HW, p.out_f32, p.relu)
+  dim3 grid(ceil_div(p.M, 512));
+#define RSG_HEAD(C) head1x1_kernel<C><<<grid, 256, 0, s>>>(p.in, p.in_cs, p.in_co, p.w, p.CinPad, p.bias, p.Cout, (unsigned)p.M, (unsigned)HW, p.out_f32, p.relu)
   switch (p.Cin) {
     case 16: RSG_HEAD(16); break;
     case 32: RSG_HEAD(32); break;
@@ -464,9 +482,12 @@ int fuse_launch(cudaStream_t s, int nterms, const ResP* terms, bf16* out, int ou
   p.nterms = nterms;
   for (int i = 0; i < nterms; ++i) p.t[i] = terms[i];
   p.out = out; p.out_cs = out_cs; p.out_co = out_co; p.N = N; p.H = H; p.W = W; p.C = C; p.relu = relu;
-  const long long total = (long long)N * H * W * (C / 8);
-  if (total == 0) return RSG_OK;
-  fuse_kernel<<<ceil_div(total, 256), 256, 0, s>>>(p);
+  const long long rows = (long long)N * H;
+  if (rows == 0 || W == 0) return RSG_OK;
+  RSG_REQUIRE(rows < (1ll << 31), "fuse: too many rows");
+  const int per_row = W * (C / 8);
+  const int threads = per_row >= 256 ? 256 : (per_row + 31) / 32 * 32;
+  fuse_kernel<<<(unsigned)rows, threads, 0, s>>>(p);
   RSG_LAUNCH_CHECK();
   return RSG_OK;
 }
