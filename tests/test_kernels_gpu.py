@@ -200,7 +200,8 @@ def test_deconv4_fused_pixel_shuffle_vs_torch(C_, H, W, N):
     _lib.lib().rsg_plan_destroy(h)
 
 
-@pytest.mark.parametrize('C_,H,W,N', [(32, 16, 8, 2), (32, 64, 48, 7), (48, 24, 18, 3), (32, 21, 13, 3), (32, 32, 24, 200)])
+@pytest.mark.parametrize('C_,H,W,N', [(32, 16, 8, 2), (32, 64, 48, 7), (48, 24, 18, 3), (32, 21, 13, 3), (32, 32, 24, 200),
+                                      (32, 19, 20, 5), (32, 16, 16, 1), (32, 64, 48, 300)])
 def test_fused_basic_block_vs_torch(C_, H, W, N):
     """BasicBlock (pose_rsgnet.py:25-54) as one kernel: relu(bn2(conv2(relu(bn1(conv1(x))))) + x); the fused kernel
     rounds the intermediate to bf16 exactly like the two-conv path does."""
