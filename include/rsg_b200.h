@@ -164,6 +164,16 @@ int rsg_plan_add_groupnorm(rsg_plan*, rsg_ref in, int in_cs, int in_co, rsg_ref 
 int rsg_basic_block_supported(int C, int H, int W);
 int rsg_plan_add_basic_block(rsg_plan*, rsg_ref in, int in_cs, int in_co, int H, int W, int C, rsg_ref w1, rsg_ref b1,
                              rsg_ref w2, rsg_ref b2, rsg_ref out, int out_cs, int out_co);
+/* Fused Bottleneck (pose_rsgnet.py:57-95; layer1, :619): out = relu(bn3(conv3(relu(bn2(conv2(relu(bn1(conv1(x)))))))) + res)
+ * with conv1 = 1x1 Cin -> 64, conv2 = 3x3 64 -> 64, conv3 = 1x1 64 -> 256, BN folded (weights bf16 in the tcgen05 packing
+ * [tap][K/8][N][8] with N = the conv's own output channels, biases f32).  `res` is a bf16 NHWC tensor with 256 channels:
+ * x itself for an identity block, the output of the block's 1x1 downsample conv otherwise.  Both intermediates stay in
+ * shared memory.  rsg_bottleneck_supported says whether the fused kernel covers the shape; otherwise describe the block
+ * as three rsg_plan_add_conv ops. */
+int rsg_bottleneck_supported(int Cin, int planes, int Cout, int H, int W);
+int rsg_plan_add_bottleneck(rsg_plan*, rsg_ref in, int in_cs, int in_co, int H, int W, int Cin, rsg_ref w1, rsg_ref b1,
+                            rsg_ref w2, rsg_ref b2, rsg_ref w3, rsg_ref b3, rsg_ref res, int res_cs, int res_co,
+                            rsg_ref out, int out_cs, int out_co);
 /* bilinear x2, align_corners=True (+ optional sigmoid) on f32 NCHW (pose_rsgnet.py:1009-1013). */
 int rsg_plan_add_bilinear2x(rsg_plan*, rsg_ref in, rsg_ref out, int C, int H, int W, int sigmoid);
 /* Mark ops added after this call as "aux": skipped by rsg_plan_run unless with_aux != 0. */

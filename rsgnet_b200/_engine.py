@@ -339,6 +339,12 @@ def emit(builder, plan):
             _lib.check(L.rsg_plan_add_basic_block(plan, _ref(src, cp), src.buf.C, src.co, src.H, src.W, p['C'],
                                                   _ref(p['w1'], cp), _ref(p['b1'], cp), _ref(p['w2'], cp),
                                                   _ref(p['b2'], cp), _ref(dst, cp), dst.buf.C, dst.co))
+        elif kind == 'bneck':
+            src, dst, r = p['src'], p['dst'], p['res']
+            _lib.check(L.rsg_plan_add_bottleneck(plan, _ref(src, cp), src.buf.C, src.co, src.H, src.W, p['Cin'],
+                                                 _ref(p['w1'], cp), _ref(p['b1'], cp), _ref(p['w2'], cp),
+                                                 _ref(p['b2'], cp), _ref(p['w3'], cp), _ref(p['b3'], cp),
+                                                 _ref(r, cp), r.buf.C, r.co, _ref(dst, cp), dst.buf.C, dst.co))
         elif kind == 'bilinear':
             _lib.check(L.rsg_plan_add_bilinear2x(plan, _ref(p['src'], cp), _ref(p['out'], cp),
                                                  p['C'], p['H'], p['W'], int(p['sigmoid'])))
@@ -373,7 +379,40 @@ def _conv_bn(pb, P, conv, bn, src, stride=1, relu=False, res=(), dst=None):
     return pb.conv(src, w, b, stride=stride, relu=relu, dst=dst, res=res, name=P.prefix + conv)
 
 
+def _pack_tc5(w):
+    """[Cout, Cin, kh, kw] -> bf16 [taps][Cin/8][Cout][8]: the tcgen05 packing with one slice of NS = Cout."""
+    co, ci, kh, kw = w.shape
+    wt = w.transpose(2, 3, 0, 1).reshape(kh * kw, co, ci // 8, 8)
+    return _bf16_bits(np.ascontiguousarray(wt.transpose(0, 2, 1, 3)))
+
+
+def _quad_perm(n):
+    """Accumulator column -> output channel for epilogues that read TMEM as 16x256b blocks (conv_bneck.cu, epilogue 3):
+    inside each group of 64, column 8g + 2j + e holds channel 16j + 2g + e, so that lane quad member j owns 16
+    consecutive channels."""
+    c = np.arange(n)
+    g, j, e = (c % 64) // 8, (c % 8) // 2, c % 2
+    return (c // 64) * 64 + 16 * j + 2 * g + e
+
+
 def _bottleneck(pb, P, x):
+    w1, b1 = _fold(P['conv1.weight'], P.bn('bn1'))
+    w2, b2 = _fold(P['conv2.weight'], P.bn('bn2'))
+    w3, b3 = _fold(P['conv3.weight'], P.bn('bn3'))
+    planes, cout = w1.shape[0], w3.shape[0]
+    if (w1.shape == (planes, x.C, 1, 1) and w2.shape == (planes, planes, 3, 3) and w3.shape == (cout, planes, 1, 1)
+            and _lib.lib().rsg_bottleneck_supported(x.C, planes, cout, x.H, x.W)):
+        # one fused kernel: both 64-channel intermediates stay in shared memory; the residual is x itself or the
+        # output of the (separate) 1x1 downsample conv
+        r = _cbr(pb, P, x, 'downsample', relu=False) if P.has('downsample.0.weight') else x
+        dst = View(pb.buf(P.prefix + 'block', x.H, x.W, cout))
+        f32 = lambda b: pb.const(b.astype(np.float32))
+        pb.simple('bneck', dict(src=x, dst=dst, res=r, Cin=x.C, w1=pb.const(_pack_tc5(w1)), b1=f32(b1),
+                                w2=pb.const(_pack_tc5(w2)), b2=f32(b2), w3=pb.const(_pack_tc5(w3[_quad_perm(cout)])), b3=f32(b3),
+                                name=P.prefix + 'block(fused)'),
+                  [x.buf, r.buf], [dst.buf])
+        pb.flops_per_fwd += 2 * (x.C * planes + 9 * planes * planes + planes * cout) * x.H * x.W
+        return dst
     y = _conv_bn(pb, P, 'conv1', 'bn1', x, relu=True)
     y = _conv_bn(pb, P, 'conv2', 'bn2', y, relu=True)
     r = _cbr(pb, P, x, 'downsample', relu=False) if P.has('downsample.0.weight') else x
@@ -739,6 +778,8 @@ class Engine:
                     by = sum(v.H * v.W * p['dst'].C * 2 for v, _ in p['terms']) + p['dst'].H * p['dst'].W * p['dst'].C * 2
                 elif k == 'bblock':
                     by = 2 * p['src'].H * p['src'].W * p['C'] * 2
+                elif k == 'bneck':       # x read once, residual read once, output written once
+                    by = p['src'].H * p['src'].W * (p['Cin'] + 256 + 256) * 2
                 elif k == 'attention':
                     by = 3 * p['x'].H * p['x'].W * p['x'].C * 2
                 elif k == 'groupnorm':

@@ -80,6 +80,8 @@ _SIGS = {
     'rsg_basic_block_supported': (C.c_int, [C.c_int] * 3),
     'rsg_plan_add_basic_block': (C.c_int, [C.c_void_p, Ref, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, Ref, Ref, Ref, Ref,
                                            Ref, C.c_int, C.c_int]),
+    'rsg_bottleneck_supported': (C.c_int, [C.c_int] * 5),
+    'rsg_plan_add_bottleneck': (C.c_int, [C.c_void_p, Ref] + [C.c_int] * 5 + [Ref] * 7 + [C.c_int, C.c_int, Ref, C.c_int, C.c_int]),
     'rsg_plan_add_bilinear2x': (C.c_int, [C.c_void_p, Ref, Ref] + [C.c_int] * 4),
     'rsg_plan_begin_aux': (C.c_int, [C.c_void_p]),
     'rsg_plan_run': (C.c_int, [C.c_void_p, C.c_void_p, C.POINTER(C.c_void_p), C.c_int, C.c_int,

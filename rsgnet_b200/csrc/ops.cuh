@@ -26,3 +26,8 @@ int attention_tc5_launch(cudaStream_t s, const bf16* x, int x_cs, int x_co, cons
 int conv_bb_launch(cudaStream_t s, const bf16* in, int in_cs, int in_co, int N, int H, int W, int C, const bf16* w1,
                    const float* b1, const bf16* w2, const float* b2, bf16* out, int out_cs, int out_co);
 extern "C" int rsg_basic_block_supported(int C, int H, int W);
+// fused Bottleneck (conv_bneck.cu): out = relu(conv3(relu(conv2(relu(conv1(x))))) + res), 1x1 Cin->64, 3x3 64->64, 1x1 64->256
+int conv_bneck_launch(cudaStream_t s, const bf16* in, int in_cs, int in_co, int N, int H, int W, int Cin, const bf16* w1,
+                      const float* b1, const bf16* w2, const float* b2, const bf16* w3, const float* b3, const bf16* res,
+                      int res_cs, int res_co, bf16* out, int out_cs, int out_co);
+extern "C" int rsg_bottleneck_supported(int Cin, int planes, int Cout, int H, int W);

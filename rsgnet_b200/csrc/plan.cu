@@ -48,13 +48,13 @@ extern "C" int rsg_device_info(int* out4) {
 }
 
 // ------------------------------------------------------------------------------------------------
-enum OpKind { OP_STEM, OP_CONV, OP_FUSE, OP_MAXPOOL, OP_ATTN, OP_RELSCORES, OP_GROUPNORM, OP_BILINEAR, OP_BBLOCK };
+enum OpKind { OP_STEM, OP_CONV, OP_FUSE, OP_MAXPOOL, OP_ATTN, OP_RELSCORES, OP_GROUPNORM, OP_BILINEAR, OP_BBLOCK, OP_BNECK };
 
 struct Op {
   OpKind kind;
   int aux;
   // generic slots
-  rsg_ref r[6];
+  rsg_ref r[10];
   int i[16];
   float f[2];
   rsg_conv_desc conv;
@@ -212,6 +212,13 @@ int run_op(const Op& op, const RunCtx& c, int nb, int n_crops, cudaStream_t s, i
                             (const bf16*)resolve(op.r[1], c), (const float*)resolve(op.r[2], c),
                             (const bf16*)resolve(op.r[3], c), (const float*)resolve(op.r[4], c),
                             (bf16*)resolve(op.r[5], c), op.i[5], op.i[6]);
+    case OP_BNECK:
+      return conv_bneck_launch(s, (const bf16*)resolve(op.r[0], c), op.i[0], op.i[1], nb, op.i[2], op.i[3], op.i[4],
+                               (const bf16*)resolve(op.r[1], c), (const float*)resolve(op.r[2], c),
+                               (const bf16*)resolve(op.r[3], c), (const float*)resolve(op.r[4], c),
+                               (const bf16*)resolve(op.r[5], c), (const float*)resolve(op.r[6], c),
+                               (const bf16*)resolve(op.r[7], c), op.i[5], op.i[6],
+                               (bf16*)resolve(op.r[8], c), op.i[7], op.i[8]);
     case OP_BILINEAR:
       return bilinear2x_launch(s, (const float*)resolve(op.r[0], c), (float*)resolve(op.r[1], c),
                                nb * op.i[0], op.i[1], op.i[2], op.i[3]);
@@ -338,6 +345,17 @@ extern "C" int rsg_plan_add_basic_block(rsg_plan* p, rsg_ref in, int in_cs, int 
   op.i[0] = in_cs; op.i[1] = in_co; op.i[2] = H; op.i[3] = W; op.i[4] = C; op.i[5] = out_cs; op.i[6] = out_co;
   return RSG_OK;
 }
+extern "C" int rsg_plan_add_bottleneck(rsg_plan* p, rsg_ref in, int in_cs, int in_co, int H, int W, int Cin, rsg_ref w1,
+                                       rsg_ref b1, rsg_ref w2, rsg_ref b2, rsg_ref w3, rsg_ref b3, rsg_ref res, int res_cs,
+                                       int res_co, rsg_ref out, int out_cs, int out_co) {
+  RSG_REQUIRE(p, "null plan");
+  RSG_REQUIRE(rsg_bottleneck_supported(Cin, 64, 256, H, W), "bottleneck: Cin=%d on %dx%d is not covered by the fused kernel", Cin, H, W);
+  Op& op = new_op(p, OP_BNECK);
+  op.r[0] = in; op.r[1] = w1; op.r[2] = b1; op.r[3] = w2; op.r[4] = b2; op.r[5] = w3; op.r[6] = b3; op.r[7] = res; op.r[8] = out;
+  op.i[0] = in_cs; op.i[1] = in_co; op.i[2] = H; op.i[3] = W; op.i[4] = Cin; op.i[5] = res_cs; op.i[6] = res_co;
+  op.i[7] = out_cs; op.i[8] = out_co;
+  return RSG_OK;
+}
 extern "C" int rsg_plan_add_bilinear2x(rsg_plan* p, rsg_ref in, rsg_ref out, int C, int H, int W,
                                        int sigmoid) {
   RSG_REQUIRE(p, "null plan");
@@ -397,7 +415,7 @@ extern "C" int rsg_plan_profile(rsg_plan* p, void* stream, void* const* ext, int
   for (size_t i = 0; i < n && rc == RSG_OK; ++i) {
     const Op& op = p->ops[i];
     ms[i] = -1.f; flops[i] = 0.0;
-    static const int kmap[] = {0, 1, 3, 4, 5, 6, 7, 8, 10};
+    static const int kmap[] = {0, 1, 3, 4, 5, 6, 7, 8, 10, 11};
     kind[i] = kmap[op.kind];
     if (op.aux && !with_aux) continue;
     cudaEventCreate(&ev[2 * i]); cudaEventCreate(&ev[2 * i + 1]);
@@ -411,6 +429,8 @@ extern "C" int rsg_plan_profile(rsg_plan* p, void* stream, void* const* ext, int
       if (op.conv.pixel_shuffle_c) flops[i] *= 16.0 / 36.0;      // the zero taps of the fused deconv are not credited
     } else if (op.kind == OP_BBLOCK) {
       flops[i] = 2.0 * 2.0 * 9 * op.i[4] * op.i[4] * (double)op.i[2] * op.i[3] * nb;
+    } else if (op.kind == OP_BNECK) {
+      flops[i] = 2.0 * (64.0 * op.i[4] + 9.0 * 64 * 64 + 64.0 * 256) * (double)op.i[2] * op.i[3] * nb;
     } else if (op.kind == OP_ATTN) {
       flops[i] = 4.0 * (double)op.i[6] * op.i[6] * op.i[7] * nb;
     } else if (op.kind == OP_STEM) {

@@ -116,6 +116,21 @@ __device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t* v) {
       : "r"(taddr));
 }
 
+// 16 TMEM lanes x 64 columns: lane t of the warp receives, for rows t/4 (h = 0) and 8 + t/4 (h = 1) of the 16-lane block
+// at `taddr`, columns 8g + 2(t%4) + e as v[4g + 2h + e] (g = 0..7, e = 0,1)  (cute SM100_TMEM_LOAD_16dp256b8x).  Four
+// consecutive lanes hold one row: with the accumulator columns permuted at weight-pack time (column 8g + 2j + e =
+// channel 16j + 2g + e) a quad owns 64 consecutive channels of a pixel = one full 128-byte line per store instruction.
+__device__ __forceinline__ void tmem_ld_16x256b_x8(uint32_t taddr, uint32_t* v) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.16x256b.x8.b32 "
+      "{%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,"
+      "%16,%17,%18,%19,%20,%21,%22,%23,%24,%25,%26,%27,%28,%29,%30,%31}, [%32];"
+      : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]),
+        "=r"(v[8]), "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]),
+        "=r"(v[16]), "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]),
+        "=r"(v[24]), "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
+      : "r"(taddr));
+}
 
 __device__ __forceinline__ void add_res8(float* f, const uint4& u) {
   const __nv_bfloat162* h2 = reinterpret_cast<const __nv_bfloat162*>(&u);

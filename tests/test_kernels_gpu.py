@@ -235,6 +235,51 @@ def test_fused_basic_block_vs_torch(C_, H, W, N):
     _lib.lib().rsg_plan_destroy(h)
 
 
+@pytest.mark.parametrize('cin,H,W,N', [(256, 16, 8, 2), (64, 16, 8, 1), (256, 64, 48, 5), (64, 64, 48, 3), (256, 21, 13, 3),
+                                       (128, 19, 20, 2), (256, 32, 24, 150), (64, 64, 48, 40)])
+def test_fused_bottleneck_vs_torch(cin, H, W, N):
+    """Bottleneck (pose_rsgnet.py:57-95) as one kernel: relu(bn3(conv3(relu(bn2(conv2(relu(bn1(conv1(x)))))))) + r) with
+    r = x (Cin = 256) or bn(downsample(x)); both intermediates are rounded to bf16 exactly like the three-conv path."""
+    g = torch.Generator().manual_seed(cin + H * 7 + N)
+    x = torch.randn(N, cin, H, W, generator=g).bfloat16().float()
+    sd = {}
+    shapes = {'conv1': (64, cin, 1, 1), 'conv2': (64, 64, 3, 3), 'conv3': (256, 64, 1, 1)}
+    bns = {'conv1': 'bn1', 'conv2': 'bn2', 'conv3': 'bn3'}
+    if cin != 256:
+        shapes['downsample.0'] = (256, cin, 1, 1)
+        bns['downsample.0'] = 'downsample.1'
+    for name, shp in shapes.items():
+        sd[f'{name}.weight'] = torch.randn(*shp, generator=g) / (shp[1] * shp[2] * shp[3]) ** 0.5
+        bn = bns[name]
+        sd[f'{bn}.weight'] = torch.rand(shp[0], generator=g) + 0.5
+        sd[f'{bn}.bias'] = torch.randn(shp[0], generator=g) * 0.1
+        sd[f'{bn}.running_mean'] = torch.randn(shp[0], generator=g) * 0.1
+        sd[f'{bn}.running_var'] = torch.rand(shp[0], generator=g) + 0.5
+    pb = PlanBuilder(N, reuse=False)
+    xin = pb.buf('x', H, W, cin)
+    out = _engine._bottleneck(pb, _engine._Params(sd), View(xin))
+    assert [k for k, _, _ in pb.ops][-1] == 'bneck'            # the fused form was chosen
+    h = _run(pb, N)
+    pb.tensor_of(xin)[:N] = x.permute(0, 2, 3, 1).cuda().bfloat16()
+    pb.tensor_of(out.buf).fill_(7.0)
+    _exec(h, N)
+
+    def cbn(v, name, pad=0):
+        bn = bns[name]
+        return F.batch_norm(F.conv2d(v, sd[f'{name}.weight'].cuda(), None, 1, pad), sd[f'{bn}.running_mean'].cuda(),
+                            sd[f'{bn}.running_var'].cuda(), sd[f'{bn}.weight'].cuda(), sd[f'{bn}.bias'].cuda(), False, 0.0,
+                            _engine.EPS)
+    xc = x.cuda()
+    y = F.relu(cbn(xc, 'conv1'))
+    y = F.relu(cbn(y, 'conv2', 1))
+    r = xc if cin == 256 else cbn(xc, 'downsample.0')
+    ref = F.relu(cbn(y, 'conv3') + r).cpu()
+    got = pb.tensor_of(out.buf)[:N].float().permute(0, 3, 1, 2).cpu()
+    err = (got - ref).abs().max().item()
+    assert err <= 2e-2 * max(ref.abs().max().item(), 1.0), err
+    _lib.lib().rsg_plan_destroy(h)
+
+
 def test_conv_fp32_nchw_output_and_upsampled_residuals():
     N, cin, K, H, W = 3, 32, 17, 16, 12
     g = torch.Generator().manual_seed(1)

@@ -68,8 +68,10 @@ def test_plan_builder_graph(key, n_conv):
     kinds = {}
     for k, _, _ in pb.ops:
         kinds[k] = kinds.get(k, 0) + 1
-    # a fused BasicBlock op (C0 = 32 branch) stands for two convs
-    assert kinds['stem'] == 1 and kinds['conv'] + 2 * kinds.get('bblock', 0) == n_conv and kinds['fuse'] == 8
+    # a fused BasicBlock op (C0 = 32 branch) stands for two convs, a fused Bottleneck op (layer1) for three
+    assert kinds['stem'] == 1 and kinds['fuse'] == 8
+    assert kinds['conv'] + 2 * kinds.get('bblock', 0) + 3 * kinds.get('bneck', 0) == n_conv
+    assert kinds.get('bneck', 0) == 4
     if key == 'w32_crowdpose':
         assert kinds['attention'] == 1 and kinds['groupnorm'] == 1 and info['S'] == 3072
         # executed FLOPs: the reference graph (18.881 GFLOP/fwd) minus the folded type
