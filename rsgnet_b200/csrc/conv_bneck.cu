@@ -7,23 +7,28 @@
 // it is x itself) and writes the output once; both intermediates live in shared memory.
 //
 // A CTA owns 16 x 8 output pixels.  Everything is a flat pixel array of pitch 10 (the 18 x 10 halo patch, 180 pixels):
-//   input       K-chunks of 64 channels, ONE 5-D TMA box each: [8 planes][180 px][8 ch] (out-of-image = zero fill),
-//               S-deep ring
-//   conv1 (1x1) on ALL 180 patch pixels (conv2 needs the halo): 2 M tiles of 128 consecutive flat pixels (SBO = 128 B),
+//   input       K-chunks of 64 channels, ONE TMA box each, S-deep ring.  Default ("wide"): a 4-D box of 128-byte
+//               pixel rows, [180 px][64 ch] SWIZZLE_128B = the K-major swizzled UMMA layout (conv1 is a 1x1 conv: no
+//               tap shifts, so the swizzle atoms stay aligned); RSG_BNECK_PLANAR=1: the conv kernels' planar 5-D box
+//               [8 planes][180 px][8 ch] (16-byte TMA elements: 453 instead of 425 us).  Out-of-image = zero fill.
+//   conv1 (1x1) on ALL 180 patch pixels (conv2 needs the halo): 2 M tiles of 128 consecutive flat pixels,
 //               N = 64, K = Cin accumulated over the chunks                               -> TMEM acc1 [2][64 cols]
 //   epilogue 1  +bias1, ReLU, ZERO outside the image (conv2's padding) -> bf16 -> mid1 [8][180 px][8 ch]
 //   conv2 (3x3) 128 output pixels = 16 rows of 8 (SBO = one pitch), tap (dy,dx) = start offset (1+dy)*10 + (1+dx)
 //                                                                                           -> TMEM acc2 [64 cols]
 //   epilogue 2  +bias2, ReLU -> bf16 -> mid2 [8][128 px][8 ch]
 //   conv3 (1x1) N = 256, K = 64                                                            -> TMEM acc3 [256 cols]
-//   epilogue 3  +bias3 + residual (global, prefetched before the accumulator wait) -> ReLU -> bf16 NHWC stores
-// The residual is a plain NHWC tensor: x itself for the identity blocks, the output of the separate 1x1 downsample
-// conv for the first block of layer1 (Cin = 64).
+//   epilogue 3  +bias3 + residual (global, prefetched one iteration early) -> ReLU -> bf16 NHWC stores, one full
+//               128-byte line per lane quad (16x256b TMEM loads + channel-permuted W3)
+// The residual is a plain NHWC tensor: x itself for the identity blocks (ncu: an L2 hit, DRAM read 903 MB for the
+// 805 MB map), the output of the separate 1x1 downsample conv for the first block of layer1 (Cin = 64).
 //
 // Every buffer exists once (weights 136 KB + ring + mid1 + mid2 fill the 227 KB; TMEM 448 of 512 columns), and the
 // three stages of DIFFERENT tiles overlap: while tile i is in conv1, tile i-1 is in conv2 and tile i-2 in conv3 /
-// epilogue 3.  With Cin = 256 the kernel is bound by the TMA element rate of the planar layout (5760 16-byte
-// elements per tile), which coincides with the HBM floor of the block (1.6 GB per 512 forwards).
+// epilogue 3.  Measured (512 forwards, 64x48): 425 us per identity block against 811 us for the three convs; the
+// clock64 timeline (RSG_BNECK_TIMELINE=1) shows a ~9000-cycle tile period made of the TMA round trip of the two
+// stages (~4500) and the epilogue warps' global stores / residual loads (~3000) that sit between two conv1 hand-offs;
+// DRAM runs at 3.9 TB/s (47 %), the tensor pipe at 42 %.
 //
 // Warps (640 threads, one persistent CTA per SM): 0 = conv1 issuer (+ TMEM, weights), 1 = conv2 issuer, 2 = TMA
 // producer, 3 = conv3 issuer, 4..19 = epilogue warps (all three epilogues, software-pipelined by one / two tiles).
@@ -51,10 +56,14 @@ struct BnP {
   int ntiles;
   const bf16* res; int res_cs, res_co;
   bf16* out; int out_cs, out_co;
-  uint32_t w1_bytes;
+  uint32_t w1_bytes, stage_bytes;
+  int wide;                            // 1: input chunks as [184 px][64 ch] rows of 128 B (SWIZZLE_128B), 0: planar [8][180 px][8 ch]
   int v32;                             // bit0: output rows 32-byte aligned, bit1: residual rows too
-  int skip;                            // debug: bit0 no stores, bit1 no residual loads, bit2 conv2 one tap, bit4 no TMA
+  long long* dbg;                      // debug timeline (CTA 0): [tile][16] clock64 stamps, or nullptr
+  int skip;                            // debug: bit0 no stores, bit1 no residual loads, bit2 conv2 one tap, bit4 no TMA, bit5 L2 prefetch of the next tile
 };
+
+#define BN_STAMP(tile, slot) do { if (p.dbg && blockIdx.x == 0 && (tile) < 32u) p.dbg[(tile) * 16u + (slot)] = clock64(); } while (0)
 
 // bias + ReLU + bf16 pack of 8 accumulator values
 __device__ __forceinline__ uint4 bias_relu_pack8(const uint32_t* v, const float* b) {
@@ -80,12 +89,12 @@ conv_bneck_kernel(const __grid_constant__ CUtensorMap in_map, const BnP p) {
   auto BAR = [&](int i) { return bar0 + 8u * i; };
   const int B_FULL = 1, B_EMPTY = 1 + p.S, B_A1F = 1 + 2 * p.S, B_A1E = B_A1F + 1, B_M1F = B_A1F + 2, B_M1E = B_A1F + 3,
             B_A2F = B_A1F + 4, B_A2E = B_A1F + 5, B_M2F = B_A1F + 6, B_M2E = B_A1F + 7, B_A3F = B_A1F + 8, B_A3E = B_A1F + 9;
-  const uint32_t sbase = (smem_u32(smem_raw) + 127u) & ~127u;
+  const uint32_t sbase = (smem_u32(smem_raw) + 1023u) & ~1023u;      // SWIZZLE_128B stages: 1024-byte aligned
   unsigned char* const sgen = smem_raw + (sbase - smem_u32(smem_raw));
   // layout: W1 | W2 | W3 | ring | mid1 | mid2.  conv1's second M tile reads 76 pixels past the end of each plane (rows
   // that are never used); for the last plane of the last stage that lands in mid1, inside the allocation.
   const uint32_t off_w2 = p.w1_bytes, off_w3 = off_w2 + BN_W2, off_st = off_w3 + BN_W3,
-                 off_m1 = off_st + (uint32_t)p.S * BN_STAGE, off_m2 = off_m1 + BN_STAGE;
+                 off_m1 = off_st + (uint32_t)p.S * p.stage_bytes, off_m2 = off_m1 + BN_STAGE;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 
   if (threadIdx.x == 0) {
@@ -119,17 +128,34 @@ conv_bneck_kernel(const __grid_constant__ CUtensorMap in_map, const BnP p) {
       pdl_wait();
       asm volatile("prefetch.tensormap [%0];" ::"l"(&in_map) : "memory");
       uint32_t s = 0, ph = 0;
-      for (int t = first; t < p.ntiles; t += step) {
-        const int n = (int)fastdiv((uint32_t)t, p.magic_tpi);
+      // Only S = 2 chunk stages fit beside the weights.  Prefetching the next tile's boxes into L2
+      // (cp.async.bulk.prefetch.tensor) was measured: the TMA wait per tile drops from ~5000 to ~3500 cycles but the
+      // kernel does not get faster (438 vs 428 us) -- the epilogue warps' global stores are the longer chain
+      // (profiles/r1_notes.md §12); RSG_BNECK_PREFETCH=1 (skip bit 5) re-enables it for experiments.
+      auto coords = [&](int t, int& n, int& ty, int& tx) {
+        n = (int)fastdiv((uint32_t)t, p.magic_tpi);
         const int rem = t - n * (int)p.tiles_per_img;
-        const int ty = (int)fastdiv((uint32_t)rem, p.magic_tx), tx = rem - ty * p.tiles_x;
+        ty = (int)fastdiv((uint32_t)rem, p.magic_tx);
+        tx = rem - ty * p.tiles_x;
+      };
+      const bool pf = (p.skip & 32) && !(p.skip & 16);
+      for (int t = first; t < p.ntiles; t += step) {
+        int n, ty, tx, n2 = 0, ty2 = 0, tx2 = 0;
+        coords(t, n, ty, tx);
+        const bool pf2 = pf && t + step < p.ntiles;
+        if (pf2) coords(t + step, n2, ty2, tx2);
         for (int c = 0; c < p.nchunks; ++c) {
           mbar_wait(BAR(B_EMPTY + s), ph ^ 1u);
           if (p.skip & 16) {
             mbar_arrive(BAR(B_FULL + s));
           } else {
             mbar_arrive_expect_tx(BAR(B_FULL + s), BN_STAGE);
-            tma_load_5d(sbase + off_st + s * BN_STAGE, &in_map, BAR(B_FULL + s), 0, tx * 8 - 1, ty * 16 - 1, c * 8, n);
+            if (p.wide) tma_load_4d(sbase + off_st + s * p.stage_bytes, &in_map, BAR(B_FULL + s), c * 64, tx * 8 - 1, ty * 16 - 1, n);
+            else tma_load_5d(sbase + off_st + s * p.stage_bytes, &in_map, BAR(B_FULL + s), 0, tx * 8 - 1, ty * 16 - 1, c * 8, n);
+          }
+          if (pf2) {
+            if (p.wide) tma_prefetch_4d(&in_map, c * 64, tx2 * 8 - 1, ty2 * 16 - 1, n2);
+            else tma_prefetch_5d(&in_map, 0, tx2 * 8 - 1, ty2 * 16 - 1, c * 8, n2);
           }
           if (++s == (uint32_t)p.S) { s = 0; ph ^= 1u; }
         }
@@ -156,28 +182,35 @@ conv_bneck_kernel(const __grid_constant__ CUtensorMap in_map, const BnP p) {
     mbar_wait(BAR(0), 0);
     if (warp == 0) {
       // ---- conv1: 1x1, Cin -> 64, on the 180 patch pixels (2 M tiles)
-      const uint32_t hiA = desc_hi(128u), hiB = desc_hi(128u);
+      // A operand: planar = K-major SWIZZLE_NONE (8-pixel core matrices 128 B apart, planes LBO apart; M tile = +128 px,
+      // k16 = +2 planes); wide = K-major SWIZZLE_128B (pixel rows of 128 B; M tile = +128 rows, k16 = +32 B)
+      const uint32_t hiA = p.wide ? desc_hi_sw128(1024u) : desc_hi(128u), hiB = desc_hi(128u);
+      const uint32_t a_lbo = p.wide ? (1u << 16) : ((uint32_t)BN_PX << 16);
+      const uint32_t a_mt = p.wide ? 1024u : 128u, a_kk = p.wide ? 2u : 2u * BN_PX;          // 16-byte units
       const uint32_t w16 = (sbase >> 4) | (64u << 16);                     // LBO = 64 rows x 16 B
       uint32_t s = 0, ph = 0, i = 0;
       for (int t = first; t < p.ntiles; t += step, ++i) {
         mbar_wait(BAR(B_A1E), (i & 1u) ^ 1u);
+        if (lane == 0) BN_STAMP(i, 0);
         for (int c = 0; c < p.nchunks; ++c) {
           mbar_wait(BAR(B_FULL + s), ph);
+          if (lane == 0 && c == p.nchunks - 1) BN_STAMP(i, 1);
           asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-          const uint32_t a16 = ((sbase + off_st + s * BN_STAGE) >> 4) | ((uint32_t)BN_PX << 16);   // LBO = one plane
+          const uint32_t a16 = ((sbase + off_st + s * p.stage_bytes) >> 4) | a_lbo;
           const uint32_t b16 = w16 + (uint32_t)c * 512u;                   // 8 planes x 1024 B per chunk
           if (elect_one()) {
 #pragma unroll
             for (int mt = 0; mt < 2; ++mt) {
 #pragma unroll
               for (int kk = 0; kk < 4; ++kk)
-                umma_f16(tmem_base + (uint32_t)mt * 64u, ((uint64_t)hiA << 32) | (a16 + (uint32_t)mt * 128u + (uint32_t)kk * (2u * BN_PX)),
+                umma_f16(tmem_base + (uint32_t)mt * 64u, ((uint64_t)hiA << 32) | (a16 + (uint32_t)mt * a_mt + (uint32_t)kk * a_kk),
                          ((uint64_t)hiB << 32) | (b16 + (uint32_t)kk * 128u), idesc64, (c | kk) ? 1u : 0u);
             }
             umma_commit(BAR(B_EMPTY + s));
             if (c == p.nchunks - 1) umma_commit(BAR(B_A1F));
           }
           __syncwarp();
+          if (lane == 0 && c == p.nchunks - 1) BN_STAMP(i, 2);
           if (++s == (uint32_t)p.S) { s = 0; ph ^= 1u; }
         }
       }
@@ -194,6 +227,7 @@ conv_bneck_kernel(const __grid_constant__ CUtensorMap in_map, const BnP p) {
         mbar_wait(BAR(B_M1F), i & 1u);
         mbar_wait(BAR(B_A2E), (i & 1u) ^ 1u);
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        if (lane == 0) BN_STAMP(i, 5);
         if (elect_one()) {
           if (p.skip & 4) {
             umma_f16(tmem_base + TM_ACC2, ((uint64_t)hiA << 32) | (a16 + toff[4]), ((uint64_t)hiB << 32) | (w16 + 4u * 512u), idesc64, 0u);
@@ -210,6 +244,7 @@ conv_bneck_kernel(const __grid_constant__ CUtensorMap in_map, const BnP p) {
           umma_commit(BAR(B_A2F));
         }
         __syncwarp();
+        if (lane == 0) BN_STAMP(i, 6);
       }
     } else {
       // ---- conv3: 1x1, 64 -> 256, on mid2
@@ -221,6 +256,7 @@ conv_bneck_kernel(const __grid_constant__ CUtensorMap in_map, const BnP p) {
         mbar_wait(BAR(B_M2F), i & 1u);
         mbar_wait(BAR(B_A3E), (i & 1u) ^ 1u);
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        if (lane == 0) BN_STAMP(i, 9);
         if (elect_one()) {
 #pragma unroll
           for (int kk = 0; kk < 4; ++kk)
@@ -257,6 +293,7 @@ conv_bneck_kernel(const __grid_constant__ CUtensorMap in_map, const BnP p) {
       const bool inside = gy >= 0 && gy < p.H && gx >= 0 && gx < p.W;
       mbar_wait(BAR(B_A1F), i & 1u);
       asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+      if (threadIdx.x == 128) BN_STAMP(i, 3);
       uint32_t v[32];
       tmem_ld32(tq + (uint32_t)(mt * 64 + cb), v);
       asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
@@ -276,6 +313,7 @@ conv_bneck_kernel(const __grid_constant__ CUtensorMap in_map, const BnP p) {
       asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
       __syncwarp();
       if (lane == 0) mbar_arrive(BAR(B_M1F));
+      if (threadIdx.x == 128) BN_STAMP(i, 4);
     };
 
     // ---- epilogue 2: 16 columns of conv2's accumulator -> mid2
@@ -283,6 +321,7 @@ conv_bneck_kernel(const __grid_constant__ CUtensorMap in_map, const BnP p) {
       const int cb = w4 * 16;
       mbar_wait(BAR(B_A2F), j & 1u);
       asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+      if (threadIdx.x == 128) BN_STAMP(j, 7);
       uint32_t v[16];
       tmem_ld16(tq + TM_ACC2 + (uint32_t)cb, v);
       asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
@@ -296,6 +335,7 @@ conv_bneck_kernel(const __grid_constant__ CUtensorMap in_map, const BnP p) {
       asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
       __syncwarp();
       if (lane == 0) mbar_arrive(BAR(B_M2F));
+      if (threadIdx.x == 128) BN_STAMP(j, 8);
     };
 
     // ---- epilogue 3: 64 columns of conv3's accumulator + residual -> global.
@@ -325,6 +365,7 @@ conv_bneck_kernel(const __grid_constant__ CUtensorMap in_map, const BnP p) {
       const int y0 = ty * 16 + q * 4, x = tx * 8 + wx3;
       mbar_wait(BAR(B_A3F), j & 1u);
       asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+      if (threadIdx.x == 128) BN_STAMP(j, 10);
       bf16* const outp = p.out + p.out_co + cb3 + (((size_t)n * p.H + (size_t)y0) * p.W + (size_t)x) * (size_t)p.out_cs;
       const float4* bp = reinterpret_cast<const float4*>(sB3 + cb3);
 #pragma unroll
@@ -363,6 +404,7 @@ conv_bneck_kernel(const __grid_constant__ CUtensorMap in_map, const BnP p) {
             stg32(outp + (size_t)k * p.W * p.out_cs, (p.v32 & 1) != 0, o0, o1);
         }
       }
+      if (threadIdx.x == 128) BN_STAMP(j, 11);
     };
 
     // tile i is in epilogue 1 while tile i-1 is in epilogue 2 and tile i-2 in epilogue 3: conv2 / conv3 of those tiles
@@ -406,8 +448,12 @@ int conv_bneck_launch(cudaStream_t s, const bf16* in, int in_cs, int in_co, int 
   k.w1 = w1; k.w2 = w2; k.w3 = w3; k.b1 = b1; k.b2 = b2; k.b3 = b3;
   k.Cin = Cin; k.H = H; k.W = W; k.N = N; k.nchunks = Cin / 64;
   k.w1_bytes = (uint32_t)Cin * 64u * 2u;
-  const size_t fixed = 128 + (size_t)k.w1_bytes + BN_W2 + BN_W3 + BN_STAGE + BN_MID2;
-  int S = (int)((225 * 1024 - (long long)fixed) / (long long)BN_STAGE);
+  // wide rows (one 128-byte TMA row per pixel instead of eight 16-byte elements): the planar boxes of a DRAM-resident
+  // 256-channel map arrive at ~11 B/cycle/SM with the two stages that fit (timeline: 8500 cycles per tile waiting for TMA)
+  k.wide = getenv("RSG_BNECK_PLANAR") ? 0 : 1;
+  k.stage_bytes = k.wide ? 184u * 128u : BN_STAGE;
+  const size_t fixed = 1024 + (size_t)k.w1_bytes + BN_W2 + BN_W3 + BN_STAGE + BN_MID2;
+  int S = (int)((225 * 1024 - (long long)fixed) / (long long)k.stage_bytes);
   if (S > BN_MAX_S) S = BN_MAX_S;
   { const char* e = getenv("RSG_BNECK_S"); if (e && atoi(e) >= 1 && atoi(e) <= S) S = atoi(e); }
   RSG_REQUIRE(S >= 2, "bottleneck: shared memory budget");
@@ -424,12 +470,28 @@ int conv_bneck_launch(cudaStream_t s, const bf16* in, int in_cs, int in_co, int 
   k.v32 = ((out_cs % 16 == 0 && out_co % 16 == 0 && ((uintptr_t)out & 31) == 0) ? 1 : 0) |
           ((res_cs % 16 == 0 && res_co % 16 == 0 && ((uintptr_t)res & 31) == 0) ? 2 : 0);
   { const char* e = getenv("RSG_BNECK_SKIP"); k.skip = e ? atoi(e) : 0; }
-  const size_t smem = fixed + (size_t)S * BN_STAGE;
+  if (getenv("RSG_BNECK_PREFETCH")) k.skip |= 32;
+  static long long* dbg_buf = nullptr;
+  if (getenv("RSG_BNECK_TIMELINE")) {
+    if (!dbg_buf) cudaMalloc(&dbg_buf, 32 * 16 * sizeof(long long));
+    cudaMemsetAsync(dbg_buf, 0, 32 * 16 * sizeof(long long), s);
+    k.dbg = dbg_buf;
+  }
+  const size_t smem = fixed + (size_t)S * k.stage_bytes;
   EncodeTiledFn enc = tensor_map_encoder();
   RSG_REQUIRE(enc, "cuTensorMapEncodeTiled is not available from this driver");
   CUtensorMap map;
   memset(&map, 0, sizeof(map));
-  {
+  if (k.wide) {
+    cuuint64_t dims[4] = {(cuuint64_t)Cin, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)N};
+    cuuint64_t strides[3] = {(cuuint64_t)in_cs * 2, (cuuint64_t)W * in_cs * 2, (cuuint64_t)H * W * in_cs * 2};
+    cuuint32_t box[4] = {64, BN_PITCH, 18, 1};
+    cuuint32_t estr[4] = {1, 1, 1, 1};
+    CUresult r = enc(&map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, (void*)(in + in_co), dims, strides, box, estr,
+                     CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                     CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    RSG_REQUIRE(r == CUDA_SUCCESS, "cuTensorMapEncodeTiled (bottleneck, wide) failed with %d", (int)r);
+  } else {
     cuuint64_t dims[5] = {8, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)(Cin / 8), (cuuint64_t)N};
     cuuint64_t strides[4] = {(cuuint64_t)in_cs * 2, (cuuint64_t)W * in_cs * 2, 16, (cuuint64_t)H * W * in_cs * 2};
     cuuint32_t box[5] = {8, BN_PITCH, 18, 8, 1};
@@ -449,5 +511,21 @@ int conv_bneck_launch(cudaStream_t s, const bf16* in, int in_cs, int in_co, int 
   int gx = rsg_num_sms();
   if (gx > k.ntiles) gx = k.ntiles;
   RSG_CUDA(launch_pdl(conv_bneck_kernel, dim3((unsigned)gx), dim3(BN_THREADS), smem, s, map, k));
+  if (k.dbg) {
+    static int dumped = 0;
+    if (dumped++ == 3) {
+      long long h[32 * 16];
+      cudaStreamSynchronize(s);
+      cudaMemcpy(h, k.dbg, sizeof(h), cudaMemcpyDeviceToHost);
+      fprintf(stderr, "[bneck timeline, CTA 0, cycles since conv1 start of tile 4] tile: c1_start c1_lastfull c1_issued e1_accok e1_done | "
+                      "c2_start c2_issued e2_accok e2_done | c3_start e3_accok e3_done\n");
+      const long long t0 = h[4 * 16];
+      for (int i = 4; i < 16; ++i) {
+        fprintf(stderr, "%2d:", i);
+        for (int j = 0; j < 12; ++j) fprintf(stderr, " %7lld", h[i * 16 + j] ? h[i * 16 + j] - t0 : -1);
+        fprintf(stderr, "\n");
+      }
+    }
+  }
   return RSG_OK;
 }
