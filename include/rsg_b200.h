@@ -74,6 +74,22 @@ int rsg_oks_iou(void* stream, const float* g, const float* d, double a_g, const 
 int rsg_rescore(void* stream, const float* maxvals, const double* box_scores, int n, int K,
                 double in_vis_thre, double* scores);
 
+/* Person-crop affine warp + normalisation for a batch of crops (the loader's input path).
+ * Replaces, per crop, cv2.warpAffine(img, trans, (out_w, out_h), flags=cv2.INTER_LINEAR) as called by
+ * lib/dataset/CPJointsDataset.py:1281-1285 and lib/utils/transforms.py:121-129 (crop), and
+ * transforms.Compose([ToTensor(), Normalize(mean, std)]) of tools/cp_test.py:107-115.  Bit-exact with OpenCV's 8-bit
+ * fixed-point bilinear warp (BORDER_CONSTANT 0).  All pointers are DEVICE pointers.
+ *   src      [N] pointers to uint8 HWC images with 3 channels (several crops may share one image)
+ *   src_dims i32 [N][3]  rows, cols, row stride in bytes of each source image
+ *   mats     f64 [N][6]  the forward 2x3 matrix `trans` (get_affine_transform, lib/utils/transforms.py:65-97)
+ *   reverse_channels     1: output channel k = source channel 2-k (cv2.cvtColor BGR2RGB before the warp,
+ *                        CPJointsDataset.py:1231-1232)
+ *   out_u8   u8 [N][out_h][out_w][3] or NULL: the warped crop as cv2.warpAffine returns it
+ *   out_f32  f32 [N][3][out_h][out_w] or NULL: the normalised model input; lut f32 [3][256] = ((u/255 - mean[k])/std[k])
+ *            evaluated in fp32 by the host for every byte value (indexed by OUTPUT channel) */
+int rsg_warp_affine(void* stream, const uint8_t* const* src, const int32_t* src_dims, const double* mats, int N,
+                    int out_h, int out_w, int reverse_channels, uint8_t* out_u8, float* out_f32, const float* lut);
+
 /* ------------------------------------------------------------------------------------------
  * Model plan: a flat list of device ops (the folded / packed network) executed per chunk of crops.
  * Replaces the nn.Module forward of lib/models/pose_rsgnet.py:955-1021 and

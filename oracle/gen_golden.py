@@ -141,15 +141,45 @@ def nms_cases():
         print('wrote', fn, os.path.getsize(fn) // 1024, 'KiB')
 
 
+def warp_cases():
+    """Loader input path (CPJointsDataset.py:1281-1290, cp_test.py:107-115) executed by the reference's own
+    get_affine_transform / crop (-> cv2.getAffineTransform, cv2.warpAffine) and torchvision's ToTensor + Normalize."""
+    import cv2
+    import torchvision.transforms as T
+    f = ref_import.ref_functions()
+    imgs, centers, scales = synth.images(10, seed=7)
+    rots = [0, 0, 0, 0, 0, 0, 30.0, -47.5, 0, 80.0]                 # test-time crops use rot = 0; training rotates
+    sizes = [(48, 64)] * 6 + [(192, 256), (48, 64), (288, 384), (48, 64)]
+    rec = dict(seed=7, n=10, rots=np.asarray(rots, np.float64), sizes=np.asarray(sizes, np.int32),
+               cv2_version=np.bytes_(cv2.__version__))
+    tf = T.Compose([T.ToTensor(), T.Normalize(mean=[0.485, 0.456, 0.406], std=[0.229, 0.224, 0.225])])
+    for i, img in enumerate(imgs):
+        trans = f['get_affine_transform'](centers[i], scales[i], rots[i], sizes[i])
+        rec[f'trans{i}'] = np.asarray(trans, np.float64)
+        rec[f'trans_inv{i}'] = np.asarray(f['get_affine_transform'](centers[i], scales[i], rots[i], sizes[i], inv=1), np.float64)
+        out = f['crop'](img, centers[i], scales[i], sizes[i], rots[i])
+        rec[f'crop{i}'] = out
+        if i in (0, 6):
+            rgb = cv2.cvtColor(img, cv2.COLOR_BGR2RGB)
+            rec[f'input{i}'] = tf(f['crop'](rgb, centers[i], scales[i], sizes[i], rots[i])).numpy()
+    ramp = np.repeat(np.arange(256, dtype=np.uint8)[:, None, None], 3, axis=2)       # [256,1,3]
+    rec['lut'] = tf(ramp).numpy()[:, :, 0]                                           # [3,256]
+    fn = os.path.join(OUT, 'warp_cases.npz')
+    np.savez_compressed(fn, **rec)
+    print('wrote', fn, os.path.getsize(fn) // 1024, 'KiB')
+
+
 def main():
     assert ref_import.available(), 'needs /root/reference'
     os.makedirs(OUT, exist_ok=True)
     torch.set_num_threads(8)
-    which = sys.argv[1:] or ['decode', 'nms', 'model']
+    which = sys.argv[1:] or ['decode', 'nms', 'warp', 'model']
     if 'decode' in which:
         decode_cases()
     if 'nms' in which:
         nms_cases()
+    if 'warp' in which:
+        warp_cases()
     if 'model' in which:
         model_case('tiny', 2, 0, full=True)
         model_case('tiny_cp_sub', 2, 1, full=True)

@@ -65,6 +65,7 @@ _SIGS = {
     'rsg_oks_iou': (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_double, C.c_void_p, C.c_void_p,
                               C.c_int, C.c_int, C.c_void_p]),
     'rsg_rescore': (C.c_int, [C.c_void_p] * 3 + [C.c_int, C.c_int, C.c_double, C.c_void_p]),
+    'rsg_warp_affine': (C.c_int, [C.c_void_p] * 4 + [C.c_int] * 4 + [C.c_void_p] * 3),
     'rsg_plan_create': (C.c_int, [C.POINTER(C.c_void_p), C.c_int]),
     'rsg_plan_destroy': (None, [C.c_void_p]),
     'rsg_plan_num_ops': (C.c_int, [C.c_void_p]),

@@ -1,0 +1,112 @@
+// Person-crop affine warp + normalisation on the device: what the reference's data loader does per
+// crop on a CPU worker (lib/dataset/CPJointsDataset.py:1281-1290: cv2.warpAffine(img, trans, (W, H), INTER_LINEAR);
+// tools/cp_test.py:107-115: ToTensor + Normalize), for a whole batch of crops in one launch.
+//
+// Bit-exact with OpenCV's 8-bit INTER_LINEAR / BORDER_CONSTANT(0) warpAffine (restated in oracle/warp_oracle.py, which
+// is pinned to cv2 + the reference's crop()): the forward 2x3 matrix is inverted in fp64 with separate multiplies and
+// adds (explicit _rn intrinsics: no FMA contraction), source coordinates are 10-bit fixed point rounded half-to-even,
+// the 5-bit fractions select 15-bit bilinear weights ((0,0) -> (32767, 0, 0, 1), OpenCV's table quirk), taps outside
+// the source read 0 and dst = (sum + 16384) >> 15.  Integer / byte work, HBM-bound: per crop it reads the source
+// footprint once (L2 absorbs the 2x2 tap overlap) and writes C*H*W bytes (u8 HWC) and/or 4*C*H*W bytes (normalised
+// f32 NCHW, the model's input layout) through a 256-entry-per-channel table built by the host from the reference's
+// fp32 formula.
+//
+// Launch: one CTA per (64-pixel row segment x 4 rows, crop); the inverse matrix of the crop is computed once per CTA.
+#include "common.cuh"
+#include "../../include/rsg_b200.h"
+
+namespace {
+
+constexpr int WARP_BX = 64, WARP_BY = 4;
+
+struct WarpP {
+  const uint8_t* const* src;     // [N] device pointers, HWC uint8, 3 channels
+  const int32_t* dims;           // [N][3] rows, cols, row stride in bytes
+  const double* mats;            // [N][6] forward matrix (dst = M * src), as passed to cv2.warpAffine
+  int N, H, W;
+  uint8_t* out_u8;               // [N][H][W][3] or nullptr
+  float* out_f32;                // [N][3][H][W] or nullptr
+  const float* lut;              // [3][256], indexed by OUTPUT channel
+  int reverse;                   // 1: output channel k = source channel 2-k (BGR -> RGB)
+};
+
+__global__ void __launch_bounds__(WARP_BX * WARP_BY) warp_affine_kernel(const WarpP p) {
+  __shared__ double sM[6];
+  __shared__ float sLut[3 * 256];
+  const int n = blockIdx.z;
+  const int tid = threadIdx.y * WARP_BX + threadIdx.x;
+  if (tid == 0) {
+    const double* m = p.mats + (size_t)n * 6;
+    const double m0 = m[0], m1 = m[1], m2 = m[2], m3 = m[3], m4 = m[4], m5 = m[5];
+    double d = __dsub_rn(__dmul_rn(m0, m4), __dmul_rn(m1, m3));
+    d = d != 0.0 ? __ddiv_rn(1.0, d) : 0.0;
+    const double a11 = __dmul_rn(m4, d), a22 = __dmul_rn(m0, d);
+    const double i0 = a11, i1 = __dmul_rn(m1, -d), i3 = __dmul_rn(m3, -d), i4 = a22;
+    sM[0] = i0; sM[1] = i1; sM[3] = i3; sM[4] = i4;
+    sM[2] = __dsub_rn(__dmul_rn(-i0, m2), __dmul_rn(i1, m5));
+    sM[5] = __dsub_rn(__dmul_rn(-i3, m2), __dmul_rn(i4, m5));
+  }
+  if (p.out_f32)
+    for (int i = tid; i < 3 * 256; i += WARP_BX * WARP_BY) sLut[i] = p.lut[i];
+  __syncthreads();
+  const int x = blockIdx.x * WARP_BX + threadIdx.x, y = blockIdx.y * WARP_BY + threadIdx.y;
+  if (x >= p.W || y >= p.H) return;
+  const int rows = p.dims[n * 3 + 0], cols = p.dims[n * 3 + 1], pitch = p.dims[n * 3 + 2];
+  const uint8_t* __restrict__ src = p.src[n];
+  // WarpAffineInvoker: adelta[x] = round(M0*x*1024), X0 = round((M1*y + M2)*1024) + 16  (AB_BITS = 10, INTER_BITS = 5)
+  const int adelta = __double2int_rn(__dmul_rn(__dmul_rn(sM[0], (double)x), 1024.0));
+  const int bdelta = __double2int_rn(__dmul_rn(__dmul_rn(sM[3], (double)x), 1024.0));
+  const int X0 = __double2int_rn(__dmul_rn(__dadd_rn(__dmul_rn(sM[1], (double)y), sM[2]), 1024.0)) + 16;
+  const int Y0 = __double2int_rn(__dmul_rn(__dadd_rn(__dmul_rn(sM[4], (double)y), sM[5]), 1024.0)) + 16;
+  const int X = (X0 + adelta) >> 5, Y = (Y0 + bdelta) >> 5;
+  const int sx = max(-32768, min(32767, X >> 5)), sy = max(-32768, min(32767, Y >> 5));
+  const int fx = X & 31, fy = Y & 31;
+  int w00 = (32 - fy) * (32 - fx) * 32, w01 = (32 - fy) * fx * 32, w10 = fy * (32 - fx) * 32, w11 = fy * fx * 32;
+  if ((fx | fy) == 0) { w00 = 32767; w11 = 1; }
+  const bool x0ok = sx >= 0 && sx < cols, x1ok = sx + 1 >= 0 && sx + 1 < cols;
+  const bool y0ok = sy >= 0 && sy < rows, y1ok = sy + 1 >= 0 && sy + 1 < rows;
+  int v[3] = {0, 0, 0};
+  auto tap = [&](bool ok, int yy, int xx, int w) {
+    if (ok && w) {
+      const uint8_t* q = src + (size_t)yy * pitch + (size_t)xx * 3;
+      v[0] += w * (int)q[0]; v[1] += w * (int)q[1]; v[2] += w * (int)q[2];
+    }
+  };
+  tap(y0ok && x0ok, sy, sx, w00);
+  tap(y0ok && x1ok, sy, sx + 1, w01);
+  tap(y1ok && x0ok, sy + 1, sx, w10);
+  tap(y1ok && x1ok, sy + 1, sx + 1, w11);
+  uint8_t u[3];
+#pragma unroll
+  for (int c = 0; c < 3; ++c) u[c] = (uint8_t)min(255, (v[c] + (1 << 14)) >> 15);
+  if (p.reverse) { const uint8_t t = u[0]; u[0] = u[2]; u[2] = t; }
+  if (p.out_u8) {
+    uint8_t* o = p.out_u8 + (((size_t)n * p.H + y) * p.W + x) * 3;
+    o[0] = u[0]; o[1] = u[1]; o[2] = u[2];
+  }
+  if (p.out_f32) {
+    const size_t plane = (size_t)p.H * p.W;
+    float* o = p.out_f32 + (size_t)n * 3 * plane + (size_t)y * p.W + x;
+    o[0] = sLut[u[0]]; o[plane] = sLut[256 + u[1]]; o[2 * plane] = sLut[512 + u[2]];
+  }
+}
+
+}  // namespace
+
+extern "C" int rsg_warp_affine(void* stream, const uint8_t* const* src, const int32_t* src_dims, const double* mats, int N,
+                               int out_h, int out_w, int reverse_channels, uint8_t* out_u8, float* out_f32,
+                               const float* lut) {
+  RSG_REQUIRE(N >= 0 && out_h >= 1 && out_w >= 1, "rsg_warp_affine: bad sizes N=%d out=%dx%d", N, out_h, out_w);
+  RSG_REQUIRE(N <= 65535, "rsg_warp_affine: at most 65535 crops per call (got %d)", N);
+  if (N == 0) return RSG_OK;
+  RSG_REQUIRE(src && src_dims && mats, "rsg_warp_affine: null input");
+  RSG_REQUIRE(out_u8 || out_f32, "rsg_warp_affine: no output requested");
+  RSG_REQUIRE(!out_f32 || lut, "rsg_warp_affine: the f32 output needs the normalisation table");
+  WarpP p;
+  p.src = src; p.dims = src_dims; p.mats = mats; p.N = N; p.H = out_h; p.W = out_w;
+  p.out_u8 = out_u8; p.out_f32 = out_f32; p.lut = lut; p.reverse = reverse_channels ? 1 : 0;
+  dim3 grid((unsigned)ceil_div(out_w, WARP_BX), (unsigned)ceil_div(out_h, WARP_BY), (unsigned)N);
+  warp_affine_kernel<<<grid, dim3(WARP_BX, WARP_BY), 0, (cudaStream_t)stream>>>(p);
+  RSG_LAUNCH_CHECK();
+  return RSG_OK;
+}

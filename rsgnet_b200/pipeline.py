@@ -15,7 +15,7 @@ from . import _engine, _lib
 from .config import KIND_RSGNET, cfg_get
 from .core.inference import decode_device
 from .presets import flip_pairs_for
-from .utils.transforms import flip_perm
+from .utils.transforms import affine_matrices, flip_perm, warp_crops
 
 
 class CropPipeline:
@@ -105,6 +105,22 @@ class CropPipeline:
                 results.append((preds, maxvals))
             self._cur = slot ^ 1
         return results
+
+    def infer_images(self, images, centers, scales, image_index=None, color_rgb=True, rots=0):
+        """Photos + person boxes -> key points, everything after the image upload on the device (SURVEY.md §8f-3 +
+        §8f-1): the loader's crop affine + cv2.warpAffine + ToTensor/Normalize (CPJointsDataset.py:1281-1290,
+        cp_test.py:107-115) as one kernel writing straight into the model's input buffer, then the flip-test run
+        and the fused decode.  images: uint8 HWC BGR arrays or CUDA tensors; centers/scales f32 [B,2] as the
+        dataset's db records hold them.  Returns CUDA (preds, maxvals)."""
+        centers = np.asarray(centers, np.float32)
+        scales = np.asarray(scales, np.float32)
+        assert centers.shape == (self.batch, 2) and scales.shape == (self.batch, 2), 'one box per crop of the step'
+        mats = affine_matrices(centers, scales, rots, (self.spec.image_w, self.spec.image_h))
+        warp_crops(images, mats, (self.spec.image_w, self.spec.image_h), image_index=image_index, color_rgb=color_rgb,
+                   out=self.x)
+        self.center.copy_(torch.from_numpy(centers), non_blocking=True)
+        self.scale.copy_(torch.from_numpy(scales), non_blocking=True)
+        return self.run_device()
 
     def launches_per_step(self):
         return self.engine.last_launches() + 1

@@ -92,3 +92,24 @@ def detections(n_imgs, per_img, k, seed=3, ragged=False):
     scores = rs.permutation(n).astype(np.float64) / max(n, 1) + rs.uniform(0, 0.5 / max(n, 1), n)
     areas = rs.uniform(2e3, 4e4, n).astype(np.float32).astype(np.float64)
     return kpts, scores, areas, offsets
+
+
+def images(n, seed=7, hw_range=((120, 480), (160, 640))):
+    """n uint8 HWC "photos" of different sizes: smooth colour waves + blobs + noise (so that bilinear taps differ and
+    the fixtures compress), plus the person boxes (centre, scale) the loader would crop: some far inside, some
+    hanging over every border, tiny and huge scales."""
+    rs = np.random.RandomState(seed)
+    imgs, centers, scales = [], [], []
+    for _ in range(n):
+        h = int(rs.randint(*hw_range[0]))
+        w = int(rs.randint(*hw_range[1]))
+        yy, xx = np.mgrid[0:h, 0:w].astype(np.float32)
+        img = np.zeros((h, w, 3), np.float32)
+        for c in range(3):
+            fx, fy, ph = rs.uniform(0.01, 0.15), rs.uniform(0.01, 0.15), rs.uniform(0, 6.28)
+            img[:, :, c] = 127 + 90 * np.sin(fx * xx + fy * yy + ph) + rs.normal(0, 12, (h, w))
+        imgs.append(np.clip(np.rint(img), 0, 255).astype(np.uint8))
+        centers.append([rs.uniform(-0.1, 1.1) * w, rs.uniform(-0.1, 1.1) * h])
+        s = rs.uniform(0.15, 3.5)
+        scales.append([s, s * 1.25])
+    return imgs, np.asarray(centers, np.float32), np.asarray(scales, np.float32)

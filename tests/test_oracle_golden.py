@@ -108,3 +108,53 @@ def test_model_oracle_vs_reference(golden_dir, key):
         assert got.shape == ref.shape
         err = np.abs(got - ref).max()
         assert err <= 2e-5 * max(ref_absmax, 1e-3), (name, err, ref_absmax)
+
+
+# ---------------------------------------------------------------------------------------------
+# Input side: crop affine + cv2.warpAffine + ToTensor/Normalize
+# ---------------------------------------------------------------------------------------------
+def test_warp_oracle_vs_reference(golden_dir):
+    """oracle/warp_oracle.py against crops made by the reference's get_affine_transform / crop (cv2.getAffineTransform +
+    cv2.warpAffine) and torchvision's ToTensor + Normalize: matrices to 1e-9, every byte and every float bit-exact."""
+    from oracle import warp_oracle
+    from rsgnet_b200.utils import transforms
+    g = _load(golden_dir, 'warp_cases.npz')
+    imgs, c, s = synth.images(int(g['n']), seed=int(g['seed']))
+    assert np.array_equal(warp_oracle.normalize_lut(), g['lut'])
+    assert np.array_equal(transforms.normalize_lut(), g['lut'])
+    for i, img in enumerate(imgs):
+        rot, size = float(g['rots'][i]), g['sizes'][i]
+        for inv, key in ((0, f'trans{i}'), (1, f'trans_inv{i}')):
+            t = warp_oracle.get_affine_transform(c[i], s[i], rot, size, inv=inv)
+            assert np.abs(t - g[key]).max() <= 1e-9
+            # the product's host-side matrix (rsgnet_b200/utils/transforms.py) agrees with both
+            assert np.abs(transforms.get_affine_transform(c[i], s[i], rot, size, inv=inv) - g[key]).max() <= 1e-9
+        assert np.array_equal(warp_oracle.crop(img, c[i], s[i], size, rot), g[f'crop{i}'])
+        assert np.array_equal(warp_oracle.warp_affine_u8(img, g[f'trans{i}'], size), g[f'crop{i}'])
+        if f'input{i}' in g.files:
+            assert np.array_equal(warp_oracle.crop_input(img, c[i], s[i], size, rot, color_rgb=True), g[f'input{i}'])
+    m = transforms.affine_matrices(c, s, g['rots'], (48, 64))
+    for i in range(len(imgs)):
+        assert np.array_equal(m[i], transforms.get_affine_transform(c[i], s[i], float(g['rots'][i]), (48, 64)))
+    assert np.allclose(transforms.affine_transform([3.0, 4.0], m[0]), m[0] @ np.array([3.0, 4.0, 1.0]))
+
+
+def test_warp_oracle_vs_cv2_random():
+    """Where OpenCV is importable (the authoring container; any box with the image's cv2), the restatement is compared
+    with cv2.warpAffine itself on fresh random images and general affine matrices."""
+    cv2 = pytest.importorskip('cv2')
+    from oracle import warp_oracle
+    rs = np.random.RandomState(11)
+    for trial in range(12):
+        sh, sw = int(rs.randint(1, 200)), int(rs.randint(1, 300))
+        img = rs.randint(0, 256, (sh, sw, 3)).astype(np.uint8)
+        ang, sc = rs.uniform(0, 6.28), rs.uniform(0.2, 4.0)
+        m = np.array([[sc * np.cos(ang), -sc * np.sin(ang), rs.uniform(-40, 80)],
+                      [sc * np.sin(ang), sc * np.cos(ang), rs.uniform(-40, 80)]])
+        if trial == 0:
+            m = np.array([[1.0, 0.0, 0.0], [0.0, 1.0, 0.0]])          # integer-aligned: the (32767, 0, 0, 1) weights
+        if trial == 1:
+            m = np.array([[2.0, 0.0, 3.0], [0.0, 2.0, -5.0]])
+        w, h = int(rs.randint(1, 100)), int(rs.randint(1, 100))
+        ref = cv2.warpAffine(img, m, (w, h), flags=cv2.INTER_LINEAR)
+        assert np.array_equal(warp_oracle.warp_affine_u8(img, m, (w, h)), ref), trial
