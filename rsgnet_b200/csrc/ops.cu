@@ -183,37 +183,41 @@ __device__ __forceinline__ uint4 pack8(const float* a) {
   return o;
 }
 
-// one block per output row (n, y): 32-bit index math only (the first version spent most of its time in five
-// 64-bit divisions per thread), 16 bytes per thread, consecutive threads = consecutive bytes of the row
-__global__ void __launch_bounds__(256) fuse_kernel(const FuseP p) {
+// FUSE_ROWS output rows (n, y) per block: 32-bit index math only (the first version spent most of its time in five
+// 64-bit divisions per thread), 16 bytes per thread, consecutive threads = consecutive bytes of the row.  One row per
+// block (32768 blocks of 192 threads for a 64x48x32 map) was bound by the block launch rate, not by HBM.
+constexpr int FUSE_ROWS = 8;
+__global__ void __launch_bounds__(256) fuse_kernel(const FuseP p, int rows) {
   const int c8 = p.C >> 3;
-  const int row = blockIdx.x;
-  const int n = row / p.H, y = row - n * p.H;
   const int per_row = p.W * c8;
-  const bf16* base[4];
-#pragma unroll
-  for (int t = 0; t < 4; ++t) {
-    if (t < p.nterms) {
-      const ResP& q = p.t[t];
-      base[t] = q.p + ((size_t)(q.bs0 ? 0 : n) * q.H + (y >> q.shift)) * q.W * q.cs + q.co;
-    }
-  }
-  bf16* orow = p.out + ((size_t)n * p.H + y) * p.W * p.out_cs + p.out_co;
-  for (int e = threadIdx.x; e < per_row; e += blockDim.x) {
-    const int x = e / c8, c = (e - x * c8) * 8;
-    float a[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+  const int row_end = min(rows, ((int)blockIdx.x + 1) * FUSE_ROWS);
+  for (int row = blockIdx.x * FUSE_ROWS; row < row_end; ++row) {
+    const int n = row / p.H, y = row - n * p.H;
+    const bf16* base[4];
 #pragma unroll
     for (int t = 0; t < 4; ++t) {
       if (t < p.nterms) {
         const ResP& q = p.t[t];
-        add8(a, __ldg(reinterpret_cast<const uint4*>(base[t] + (x >> q.shift) * q.cs + c)));
+        base[t] = q.p + ((size_t)(q.bs0 ? 0 : n) * q.H + (y >> q.shift)) * q.W * q.cs + q.co;
       }
     }
-    if (p.relu) {
+    bf16* orow = p.out + ((size_t)n * p.H + y) * p.W * p.out_cs + p.out_co;
+    for (int e = threadIdx.x; e < per_row; e += blockDim.x) {
+      const int x = e / c8, c = (e - x * c8) * 8;
+      float a[8] = {0, 0, 0, 0, 0, 0, 0, 0};
 #pragma unroll
-      for (int j = 0; j < 8; ++j) a[j] = fmaxf(a[j], 0.f);
+      for (int t = 0; t < 4; ++t) {
+        if (t < p.nterms) {
+          const ResP& q = p.t[t];
+          add8(a, __ldg(reinterpret_cast<const uint4*>(base[t] + (x >> q.shift) * q.cs + c)));
+        }
+      }
+      if (p.relu) {
+#pragma unroll
+        for (int j = 0; j < 8; ++j) a[j] = fmaxf(a[j], 0.f);
+      }
+      *reinterpret_cast<uint4*>(orow + (size_t)x * p.out_cs + c) = pack8(a);
     }
-    *reinterpret_cast<uint4*>(orow + (size_t)x * p.out_cs + c) = pack8(a);
   }
 }
 
@@ -487,7 +491,7 @@ int fuse_launch(cudaStream_t s, int nterms, const ResP* terms, bf16* out, int ou
   RSG_REQUIRE(rows < (1ll << 31), "fuse: too many rows");
   const int per_row = W * (C / 8);
   const int threads = per_row >= 256 ? 256 : (per_row + 31) / 32 * 32;
-  fuse_kernel<<<(unsigned)rows, threads, 0, s>>>(p);
+  fuse_kernel<<<(unsigned)((rows + FUSE_ROWS - 1) / FUSE_ROWS), threads, 0, s>>>(p, (int)rows);
   RSG_LAUNCH_CHECK();
   return RSG_OK;
 }
