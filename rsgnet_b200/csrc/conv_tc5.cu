@@ -566,12 +566,19 @@ int conv_tc5_launch(const ConvP& p, cudaStream_t s, int* handled) {
   int nmma = S >= 6 ? 3 : 2;
   { const char* e = getenv("RSG_TC5_NMMA"); if (e && (atoi(e) == 2 || atoi(e) == 3)) nmma = atoi(e); }
   if (S < nmma) nmma = 2;
+  // Tile tl is filled by MMA warp tl % NMMA into accumulator tl % NACC and drained by epilogue group tl % NEPI.  NACC
+  // must be a multiple of BOTH, so that an accumulator always belongs to one issuer and one group, in order: with
+  // NACC = 3 and two groups (NS = 128: four accumulators fit, three issuers) group 1 could reach its parity-1 wait for
+  // tile 5 on accumulator 2 before tile 2 had even been committed -- an mbarrier parity wait cannot tell "not yet" from
+  // "one phase ago" -- read garbage, release the accumulator early and shift the phase accounting until the CTA hung
+  // (seen once in 20 steps under the overlapped H2D pipeline).  Three issuers therefore need six accumulators.
+  if (nmma == 3 && nacc < 6) nmma = 2;
   S = S / nmma * nmma;
   k.S = S;
   k.NMMA = nmma;
-  nacc = nacc / nmma * nmma;                              // tiles go round-robin over the MMA warps
-  if (nacc < 2) nacc = 2;
-  { const char* e = getenv("RSG_TC5_NACC"); if (e) nacc = atoi(e); }
+  nacc = nacc / (nmma * NEPI) * (nmma * NEPI);           // nmma = 2: multiples of 2 (NEPI = 2), nmma = 3: 6
+  if (nmma == 2) nacc = (int)(col_budget / (uint32_t)NS) >= 8 ? 8 : ((int)(col_budget / (uint32_t)NS) >= 4 ? 4 : 2);
+  { const char* e = getenv("RSG_TC5_NACC"); if (e && atoi(e) >= 2 && atoi(e) % (nmma == 3 ? 6 : 2) == 0 && atoi(e) * NS <= 512 && atoi(e) <= MAX_ACC) nacc = atoi(e); }
   k.NACC = nacc;
   uint32_t cols = 32;
   while (cols < (uint32_t)(nacc * NS)) cols <<= 1;
