@@ -142,9 +142,11 @@ def run_reference(args):
 
 
 # dram__bytes_read.sum + dram__bytes_write.sum per launch of the dominant kernel, from the committed
-# `ncu --set full` captures (profiles/r1_conv_bb_ncu_details.txt, r1_conv_tc5_ncu_details.txt; 512 forwards)
+# `ncu --set full` captures (profiles/r1_conv_bb_ncu_details.txt, r1_conv_tc5_ncu_details.txt,
+# r1_conv_bneck_ncu_details.txt; 512 forwards)
 NCU_TRAFFIC = {('conv_tcgen05', 'conv 32->32 taps9 s1 64x48 +res'): 201.44e6 + 72.35e6,
-               ('basic_block_tcgen05', 'bblock'): 100.78e6 + 57.81e6}
+               ('basic_block_tcgen05', 'bblock'): 100.78e6 + 54.63e6,
+               ('bottleneck_tcgen05', 'bneck'): 902.87e6 + 759.45e6}
 
 FAMILY = {0: 'stem', 1: 'conv_mma', 2: 'conv_tcgen05', 3: 'fuse', 4: 'maxpool', 5: 'trp_attention',
           6: 'relation_scores', 7: 'groupnorm', 8: 'bilinear', 9: 'conv_ws_tcgen05', 10: 'basic_block_tcgen05',
