@@ -180,9 +180,20 @@ def main():
     dist = None
     if world > 1:
         import torch.distributed as dist
-        # stdout carries exactly one JSON line: keep NCCL's version banner (NCCL_DEBUG=VERSION/INFO) off it
-        os.environ['NCCL_DEBUG'] = 'WARN'
-        dist.init_process_group('nccl', device_id=dev)
+        # stdout carries exactly one JSON line: NCCL writes its version banner (any NCCL_DEBUG level >= VERSION, which
+        # includes WARN) to fd 1 when the communicator is created, so fd 1 points at stderr until the first collective
+        # has run
+        sys.stdout.flush()
+        saved_fd = os.dup(1)
+        os.dup2(2, 1)
+        try:
+            dist.init_process_group('nccl', device_id=dev)
+            dist.barrier()
+            torch.cuda.synchronize()
+        finally:
+            sys.stdout.flush()
+            os.dup2(saved_fd, 1)
+            os.close(saved_fd)
 
     def barrier():
         if dist is not None:

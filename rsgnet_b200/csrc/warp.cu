@@ -11,13 +11,15 @@
 // f32 NCHW, the model's input layout) through a 256-entry-per-channel table built by the host from the reference's
 // fp32 formula.
 //
-// Launch: one CTA per (64-pixel row segment x 4 rows, crop); the inverse matrix of the crop is computed once per CTA.
+// Launch: one CTA of 64 x 4 threads per (64-pixel column strip x 32 rows, crop), walking its rows four at a time; the inverse
+// matrix of the crop and the table are set up once per CTA (with one CTA per 64 x 4 pixels the serial fp64 inversion +
+// barrier in front of 256 pixels of work was most of the kernel: 111 us per 256 crops).
 #include "common.cuh"
 #include "../../include/rsg_b200.h"
 
 namespace {
 
-constexpr int WARP_BX = 64, WARP_BY = 4;
+constexpr int WARP_BX = 64, WARP_BY = 4, WARP_ROWS = 32;      // rows per CTA (WARP_BY at a time)
 
 struct WarpP {
   const uint8_t* const* src;     // [N] device pointers, HWC uint8, 3 channels
@@ -49,45 +51,48 @@ __global__ void __launch_bounds__(WARP_BX * WARP_BY) warp_affine_kernel(const Wa
   if (p.out_f32)
     for (int i = tid; i < 3 * 256; i += WARP_BX * WARP_BY) sLut[i] = p.lut[i];
   __syncthreads();
-  const int x = blockIdx.x * WARP_BX + threadIdx.x, y = blockIdx.y * WARP_BY + threadIdx.y;
-  if (x >= p.W || y >= p.H) return;
+  const int x = blockIdx.x * WARP_BX + threadIdx.x;
+  if (x >= p.W) return;
   const int rows = p.dims[n * 3 + 0], cols = p.dims[n * 3 + 1], pitch = p.dims[n * 3 + 2];
   const uint8_t* __restrict__ src = p.src[n];
   // WarpAffineInvoker: adelta[x] = round(M0*x*1024), X0 = round((M1*y + M2)*1024) + 16  (AB_BITS = 10, INTER_BITS = 5)
   const int adelta = __double2int_rn(__dmul_rn(__dmul_rn(sM[0], (double)x), 1024.0));
   const int bdelta = __double2int_rn(__dmul_rn(__dmul_rn(sM[3], (double)x), 1024.0));
-  const int X0 = __double2int_rn(__dmul_rn(__dadd_rn(__dmul_rn(sM[1], (double)y), sM[2]), 1024.0)) + 16;
-  const int Y0 = __double2int_rn(__dmul_rn(__dadd_rn(__dmul_rn(sM[4], (double)y), sM[5]), 1024.0)) + 16;
-  const int X = (X0 + adelta) >> 5, Y = (Y0 + bdelta) >> 5;
-  const int sx = max(-32768, min(32767, X >> 5)), sy = max(-32768, min(32767, Y >> 5));
-  const int fx = X & 31, fy = Y & 31;
-  int w00 = (32 - fy) * (32 - fx) * 32, w01 = (32 - fy) * fx * 32, w10 = fy * (32 - fx) * 32, w11 = fy * fx * 32;
-  if ((fx | fy) == 0) { w00 = 32767; w11 = 1; }
-  const bool x0ok = sx >= 0 && sx < cols, x1ok = sx + 1 >= 0 && sx + 1 < cols;
-  const bool y0ok = sy >= 0 && sy < rows, y1ok = sy + 1 >= 0 && sy + 1 < rows;
-  int v[3] = {0, 0, 0};
-  auto tap = [&](bool ok, int yy, int xx, int w) {
-    if (ok && w) {
-      const uint8_t* q = src + (size_t)yy * pitch + (size_t)xx * 3;
-      v[0] += w * (int)q[0]; v[1] += w * (int)q[1]; v[2] += w * (int)q[2];
-    }
-  };
-  tap(y0ok && x0ok, sy, sx, w00);
-  tap(y0ok && x1ok, sy, sx + 1, w01);
-  tap(y1ok && x0ok, sy + 1, sx, w10);
-  tap(y1ok && x1ok, sy + 1, sx + 1, w11);
-  uint8_t u[3];
+  const size_t plane = (size_t)p.H * p.W;
+  const int y_end = min(p.H, ((int)blockIdx.y + 1) * WARP_ROWS);
+  for (int y = blockIdx.y * WARP_ROWS + threadIdx.y; y < y_end; y += WARP_BY) {
+    const int X0 = __double2int_rn(__dmul_rn(__dadd_rn(__dmul_rn(sM[1], (double)y), sM[2]), 1024.0)) + 16;
+    const int Y0 = __double2int_rn(__dmul_rn(__dadd_rn(__dmul_rn(sM[4], (double)y), sM[5]), 1024.0)) + 16;
+    const int X = (X0 + adelta) >> 5, Y = (Y0 + bdelta) >> 5;
+    const int sx = max(-32768, min(32767, X >> 5)), sy = max(-32768, min(32767, Y >> 5));
+    const int fx = X & 31, fy = Y & 31;
+    int w00 = (32 - fy) * (32 - fx) * 32, w01 = (32 - fy) * fx * 32, w10 = fy * (32 - fx) * 32, w11 = fy * fx * 32;
+    if ((fx | fy) == 0) { w00 = 32767; w11 = 1; }
+    const bool x0ok = sx >= 0 && sx < cols, x1ok = sx + 1 >= 0 && sx + 1 < cols;
+    const bool y0ok = sy >= 0 && sy < rows, y1ok = sy + 1 >= 0 && sy + 1 < rows;
+    int v[3] = {0, 0, 0};
+    auto tap = [&](bool ok, int yy, int xx, int w) {
+      if (ok && w) {
+        const uint8_t* q = src + (size_t)yy * pitch + (size_t)xx * 3;
+        v[0] += w * (int)q[0]; v[1] += w * (int)q[1]; v[2] += w * (int)q[2];
+      }
+    };
+    tap(y0ok && x0ok, sy, sx, w00);
+    tap(y0ok && x1ok, sy, sx + 1, w01);
+    tap(y1ok && x0ok, sy + 1, sx, w10);
+    tap(y1ok && x1ok, sy + 1, sx + 1, w11);
+    uint8_t u[3];
 #pragma unroll
-  for (int c = 0; c < 3; ++c) u[c] = (uint8_t)min(255, (v[c] + (1 << 14)) >> 15);
-  if (p.reverse) { const uint8_t t = u[0]; u[0] = u[2]; u[2] = t; }
-  if (p.out_u8) {
-    uint8_t* o = p.out_u8 + (((size_t)n * p.H + y) * p.W + x) * 3;
-    o[0] = u[0]; o[1] = u[1]; o[2] = u[2];
-  }
-  if (p.out_f32) {
-    const size_t plane = (size_t)p.H * p.W;
-    float* o = p.out_f32 + (size_t)n * 3 * plane + (size_t)y * p.W + x;
-    o[0] = sLut[u[0]]; o[plane] = sLut[256 + u[1]]; o[2 * plane] = sLut[512 + u[2]];
+    for (int c = 0; c < 3; ++c) u[c] = (uint8_t)min(255, (v[c] + (1 << 14)) >> 15);
+    if (p.reverse) { const uint8_t t = u[0]; u[0] = u[2]; u[2] = t; }
+    if (p.out_u8) {
+      uint8_t* o = p.out_u8 + (((size_t)n * p.H + y) * p.W + x) * 3;
+      o[0] = u[0]; o[1] = u[1]; o[2] = u[2];
+    }
+    if (p.out_f32) {
+      float* o = p.out_f32 + (size_t)n * 3 * plane + (size_t)y * p.W + x;
+      o[0] = sLut[u[0]]; o[plane] = sLut[256 + u[1]]; o[2 * plane] = sLut[512 + u[2]];
+    }
   }
 }
 
@@ -105,7 +110,7 @@ extern "C" int rsg_warp_affine(void* stream, const uint8_t* const* src, const in
   WarpP p;
   p.src = src; p.dims = src_dims; p.mats = mats; p.N = N; p.H = out_h; p.W = out_w;
   p.out_u8 = out_u8; p.out_f32 = out_f32; p.lut = lut; p.reverse = reverse_channels ? 1 : 0;
-  dim3 grid((unsigned)ceil_div(out_w, WARP_BX), (unsigned)ceil_div(out_h, WARP_BY), (unsigned)N);
+  dim3 grid((unsigned)ceil_div(out_w, WARP_BX), (unsigned)ceil_div(out_h, WARP_ROWS), (unsigned)N);
   warp_affine_kernel<<<grid, dim3(WARP_BX, WARP_BY), 0, (cudaStream_t)stream>>>(p);
   RSG_LAUNCH_CHECK();
   return RSG_OK;
