@@ -39,6 +39,12 @@ from rsgnet_b200.models import _params, pose_rsgnet  # noqa: E402
 PRESET = 'w32_crowdpose'
 WORKLOAD = 'RSGNet-W32 256x192 CrowdPose K=14 flip-test inference (BASELINE.json configs[1])'
 METRIC = 'crops/sec RSGNet-W32 256x192 flip-test inference'
+# --workload: preset -> (workload description, metric)
+WORKLOADS = {
+    'w32_crowdpose': (WORKLOAD, METRIC),
+    'w48_coco_384': ('RSGNet-W48 384x288 COCO K=17 flip-test inference (BASELINE.json configs[2])',
+                     'crops/sec RSGNet-W48 384x288 flip-test inference'),
+}
 REF_GFLOP_PER_CROP = 37.762          # reference op graph, 2 forwards
 
 
@@ -165,7 +171,13 @@ def main():
     ap.add_argument('--no-graph', action='store_true')
     ap.add_argument('--no-cpu-baseline', action='store_true')
     ap.add_argument('--dump-profile', default='')
+    ap.add_argument('--workload', default='w32_crowdpose', choices=sorted(WORKLOADS),
+                    help='default = the headline configuration (BASELINE.json configs[1]); w48_coco_384 = configs[2], '
+                         'a secondary measurement (use --batch 128)')
     args = ap.parse_args()
+    global PRESET, WORKLOAD, METRIC
+    PRESET = args.workload
+    WORKLOAD, METRIC = WORKLOADS[PRESET]
     if args.warmup < 3:
         args.warmup = 3
     if args.impl == 'reference':

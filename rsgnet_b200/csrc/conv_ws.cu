@@ -341,9 +341,17 @@ bool ws_config(int Cin, int CoutPad, int ntaps, int H, int W, WsCfg* c) {
   if (CoutPad % 128 == 0) NS = 128;
   else if (CoutPad <= 256 && CoutPad % 16 == 0) NS = CoutPad;
   if (NS < 64) return false;
+  const int P = W + 1, pitch = (H + 1) * P;
+  // one whole image must fit into the T <= 4 accumulators of a supertile (T * NS <= 512 TMEM columns): a narrower
+  // slice when it does not (W48's 192 -> 192 @24x18: pitch 475 needs T = 4, i.e. NS = 96 x 2 slices)
+  auto fits = [&](int ns) { int t = 512 / ns; if (t > WS_MAX_T) t = WS_MAX_T; return t * 128 >= pitch; };
+  if (!fits(NS)) {
+    const int cands[3] = {128, 96, 64};
+    for (int i = 0; i < 3; ++i)
+      if (cands[i] < NS && CoutPad % cands[i] == 0 && fits(cands[i])) { NS = cands[i]; break; }
+  }
   int tmax = 512 / NS;
   if (tmax > WS_MAX_T) tmax = WS_MAX_T;
-  const int P = W + 1, pitch = (H + 1) * P;
   if (P + 1 > 64 || P > 256 || H + 1 > 256) return false;
   int nimg = tmax * 128 / pitch;
   if (nimg < 1) return false;

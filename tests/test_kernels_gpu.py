@@ -46,6 +46,7 @@ CASES = [
     (16, 16, 3, 1, 24, 16, True, True),
     (256, 256, 3, 1, 8, 6, True, True),
     (144, 48, 3, 1, 10, 8, True, False),
+    (192, 192, 3, 1, 24, 18, True, True),      # W48 branch 2: weight-streaming kernel with 96-column slices
 ]
 
 
