@@ -51,6 +51,15 @@ __global__ void __launch_bounds__(WARP_BX * WARP_BY) warp_affine_kernel(const Wa
   if (p.out_f32)
     for (int i = tid; i < 3 * 256; i += WARP_BX * WARP_BY) sLut[i] = p.lut[i];
   __syncthreads();
+  // per-row terms of the CTA's 32 rows, once per row instead of once per pixel (fp64 multiplies + conversions are
+  // slow-pipe instructions): X0 = round((M1*y + M2)*1024) + 16, Y0 = round((M4*y + M5)*1024) + 16
+  __shared__ int sXY[WARP_ROWS][2];
+  if (tid < WARP_ROWS) {
+    const double y = (double)(blockIdx.y * WARP_ROWS + tid);
+    sXY[tid][0] = __double2int_rn(__dmul_rn(__dadd_rn(__dmul_rn(sM[1], y), sM[2]), 1024.0)) + 16;
+    sXY[tid][1] = __double2int_rn(__dmul_rn(__dadd_rn(__dmul_rn(sM[4], y), sM[5]), 1024.0)) + 16;
+  }
+  __syncthreads();
   const int x = blockIdx.x * WARP_BX + threadIdx.x;
   if (x >= p.W) return;
   const int rows = p.dims[n * 3 + 0], cols = p.dims[n * 3 + 1], pitch = p.dims[n * 3 + 2];
@@ -60,38 +69,53 @@ __global__ void __launch_bounds__(WARP_BX * WARP_BY) warp_affine_kernel(const Wa
   const int bdelta = __double2int_rn(__dmul_rn(__dmul_rn(sM[3], (double)x), 1024.0));
   const size_t plane = (size_t)p.H * p.W;
   const int y_end = min(p.H, ((int)blockIdx.y + 1) * WARP_ROWS);
-  for (int y = blockIdx.y * WARP_ROWS + threadIdx.y; y < y_end; y += WARP_BY) {
-    const int X0 = __double2int_rn(__dmul_rn(__dadd_rn(__dmul_rn(sM[1], (double)y), sM[2]), 1024.0)) + 16;
-    const int Y0 = __double2int_rn(__dmul_rn(__dadd_rn(__dmul_rn(sM[4], (double)y), sM[5]), 1024.0)) + 16;
-    const int X = (X0 + adelta) >> 5, Y = (Y0 + bdelta) >> 5;
-    const int sx = max(-32768, min(32767, X >> 5)), sy = max(-32768, min(32767, Y >> 5));
-    const int fx = X & 31, fy = Y & 31;
-    int w00 = (32 - fy) * (32 - fx) * 32, w01 = (32 - fy) * fx * 32, w10 = fy * (32 - fx) * 32, w11 = fy * fx * 32;
-    if ((fx | fy) == 0) { w00 = 32767; w11 = 1; }
-    const bool x0ok = sx >= 0 && sx < cols, x1ok = sx + 1 >= 0 && sx + 1 < cols;
-    const bool y0ok = sy >= 0 && sy < rows, y1ok = sy + 1 >= 0 && sy + 1 < rows;
-    int v[3] = {0, 0, 0};
-    auto tap = [&](bool ok, int yy, int xx, int w) {
-      if (ok && w) {
-        const uint8_t* q = src + (size_t)yy * pitch + (size_t)xx * 3;
-        v[0] += w * (int)q[0]; v[1] += w * (int)q[1]; v[2] += w * (int)q[2];
-      }
-    };
-    tap(y0ok && x0ok, sy, sx, w00);
-    tap(y0ok && x1ok, sy, sx + 1, w01);
-    tap(y1ok && x0ok, sy + 1, sx, w10);
-    tap(y1ok && x1ok, sy + 1, sx + 1, w11);
-    uint8_t u[3];
+  // Two pixels (rows y and y + WARP_BY) per thread and iteration, branch-free: the taps are read from clamped
+  // coordinates and an invalid tap gets weight 0, so the 24 byte loads of an iteration are independent and in flight
+  // together (one pixel per thread kept ~15 KB per SM in flight: latency-bound at 1.8 TB/s).
+  for (int yb = blockIdx.y * WARP_ROWS + threadIdx.y; yb < y_end; yb += 2 * WARP_BY) {
+    int v[2][3];
+    bool live[2];
 #pragma unroll
-    for (int c = 0; c < 3; ++c) u[c] = (uint8_t)min(255, (v[c] + (1 << 14)) >> 15);
-    if (p.reverse) { const uint8_t t = u[0]; u[0] = u[2]; u[2] = t; }
-    if (p.out_u8) {
-      uint8_t* o = p.out_u8 + (((size_t)n * p.H + y) * p.W + x) * 3;
-      o[0] = u[0]; o[1] = u[1]; o[2] = u[2];
+    for (int k = 0; k < 2; ++k) {
+      const int y = yb + k * WARP_BY;
+      live[k] = y < y_end;
+      const int yr = live[k] ? y - blockIdx.y * WARP_ROWS : 0;
+      const int X0 = sXY[yr][0], Y0 = sXY[yr][1];
+      const int X = (X0 + adelta) >> 5, Y = (Y0 + bdelta) >> 5;
+      const int sx = max(-32768, min(32767, X >> 5)), sy = max(-32768, min(32767, Y >> 5));
+      const int fx = X & 31, fy = Y & 31;
+      int w00 = (32 - fy) * (32 - fx) * 32, w01 = (32 - fy) * fx * 32, w10 = fy * (32 - fx) * 32, w11 = fy * fx * 32;
+      if ((fx | fy) == 0) { w00 = 32767; w11 = 1; }
+      const bool x0ok = sx >= 0 && sx < cols, x1ok = sx + 1 >= 0 && sx + 1 < cols;
+      const bool y0ok = sy >= 0 && sy < rows, y1ok = sy + 1 >= 0 && sy + 1 < rows;
+      w00 = (y0ok && x0ok) ? w00 : 0; w01 = (y0ok && x1ok) ? w01 : 0;
+      w10 = (y1ok && x0ok) ? w10 : 0; w11 = (y1ok && x1ok) ? w11 : 0;
+      const int cx0 = min(max(sx, 0), cols - 1), cx1 = min(max(sx + 1, 0), cols - 1);
+      const int cy0 = min(max(sy, 0), rows - 1), cy1 = min(max(sy + 1, 0), rows - 1);
+      const uint8_t* r0 = src + (size_t)cy0 * pitch;
+      const uint8_t* r1 = src + (size_t)cy1 * pitch;
+      const uint8_t* q00 = r0 + cx0 * 3; const uint8_t* q01 = r0 + cx1 * 3;
+      const uint8_t* q10 = r1 + cx0 * 3; const uint8_t* q11 = r1 + cx1 * 3;
+#pragma unroll
+      for (int c = 0; c < 3; ++c)
+        v[k][c] = w00 * (int)__ldg(q00 + c) + w01 * (int)__ldg(q01 + c) + w10 * (int)__ldg(q10 + c) + w11 * (int)__ldg(q11 + c);
     }
-    if (p.out_f32) {
-      float* o = p.out_f32 + (size_t)n * 3 * plane + (size_t)y * p.W + x;
-      o[0] = sLut[u[0]]; o[plane] = sLut[256 + u[1]]; o[2 * plane] = sLut[512 + u[2]];
+#pragma unroll
+    for (int k = 0; k < 2; ++k) {
+      if (!live[k]) continue;
+      const int y = yb + k * WARP_BY;
+      uint8_t u[3];
+#pragma unroll
+      for (int c = 0; c < 3; ++c) u[c] = (uint8_t)min(255, (v[k][c] + (1 << 14)) >> 15);
+      if (p.reverse) { const uint8_t t = u[0]; u[0] = u[2]; u[2] = t; }
+      if (p.out_u8) {
+        uint8_t* o = p.out_u8 + (((size_t)n * p.H + y) * p.W + x) * 3;
+        o[0] = u[0]; o[1] = u[1]; o[2] = u[2];
+      }
+      if (p.out_f32) {
+        float* o = p.out_f32 + (size_t)n * 3 * plane + (size_t)y * p.W + x;
+        o[0] = sLut[u[0]]; o[plane] = sLut[256 + u[1]]; o[2 * plane] = sLut[512 + u[2]];
+      }
     }
   }
 }
