@@ -100,3 +100,41 @@ def test_pipeline_from_photos_equals_pipeline_from_crops():
     x = np.stack([warp_oracle.crop_input(imgs[i], c[i], s[i], size) for i in range(4)])
     p2, m2 = pipe(x, c, s)
     assert np.array_equal(p1, p2) and np.array_equal(m1, m2)
+
+
+def test_warp_full_step_properties():
+    """BASELINE step size (256 crops of 256x192 from 64 photos): size-independent properties instead of the oracle on
+    everything -- an integer translation reproduces the source window byte for byte (OpenCV's (32767, 0, 0, 1) weight set
+    rounds back to the centre tap), windows hanging over the border are zero there, and the normalised output is the
+    table applied to those bytes; a sample of general crops is checked against the oracle."""
+    rs = np.random.RandomState(4)
+    imgs = [rs.randint(0, 256, (480, 640, 3)).astype(np.uint8) for _ in range(8)]
+    dev = [torch.from_numpy(imgs[i % 8]).cuda().clone() for i in range(64)]
+    n, size = 256, (192, 256)
+    idx = np.arange(n) % 64
+    tx = rs.randint(-100, 500, n)
+    ty = rs.randint(-100, 300, n)
+    mats = np.zeros((n, 2, 3))
+    mats[:, 0, 0] = mats[:, 1, 1] = 1.0
+    mats[:, 0, 2] = -tx                                     # dst(x, y) = src(x + tx, y + ty)
+    mats[:, 1, 2] = -ty
+    x, u8 = transforms.warp_crops(dev, mats, size, image_index=idx, normalize=True, return_u8=True)
+    u8 = u8.cpu().numpy()
+    lut = torch.from_numpy(warp_oracle.normalize_lut()).cuda()
+    for k in range(3):
+        assert torch.equal(x[:, k], lut[k][torch.from_numpy(u8[..., k]).cuda().long()])
+    for i in range(n):
+        src = imgs[idx[i] % 8]
+        ref = np.zeros((256, 192, 3), np.uint8)
+        y0, y1 = max(0, -ty[i]), min(256, 480 - ty[i])
+        x0, x1 = max(0, -tx[i]), min(192, 640 - tx[i])
+        if y1 > y0 and x1 > x0:
+            ref[y0:y1, x0:x1] = src[y0 + ty[i]:y1 + ty[i], x0 + tx[i]:x1 + tx[i]]
+        assert np.array_equal(u8[i], ref), i
+    # general crops at the same batch size: a sample against the oracle
+    centers = np.stack([rs.uniform(0, 640, n), rs.uniform(0, 480, n)], axis=1).astype(np.float32)
+    sc = rs.uniform(0.3, 3.0, n).astype(np.float32)
+    m2 = transforms.affine_matrices(centers, np.stack([sc, sc * 1.25], axis=1), 0, size)
+    u2 = transforms.warp_crops(dev, m2, size, image_index=idx, normalize=False, return_u8=True).cpu().numpy()
+    for i in range(0, n, 37):
+        assert np.array_equal(u2[i], warp_oracle.warp_affine_u8(imgs[idx[i] % 8], m2[i], size)), i
