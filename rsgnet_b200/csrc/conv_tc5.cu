@@ -69,6 +69,9 @@ struct Tc5P {
   int relu;
   int v32;              // bit0: output rows 32-byte aligned, bit1: residual term 0 too (LDG/STG.256)
   uint32_t w_bytes, stage_bytes, tx_bytes, tmem_cols;
+  int wstream;          // 1: the weights of a K chunk travel with its halo stage ([tap][KC/8][NS][8] at a_bytes) instead of
+                        // staying resident (layers whose slice does not fit beside >= 4 stages: 256->64 stride 2)
+  uint32_t a_bytes, wtap_bytes;   // wstream: offset of the weights inside a stage, bytes per tap (KC/8 * NS * 16)
   long long* dbg;       // debug timeline (CTA 0): [tile][8] clock64 stamps, or nullptr
   int skip;             // debug: bit0 no halo loads, bit1 no MMAs, bit2 no residual loads, bit3 no stores
 };
@@ -96,6 +99,9 @@ __device__ __forceinline__ void issue9(uint32_t d_tmem, uint32_t a_stage, uint32
   }
 }
 
+// WSTREAM is a template parameter so that the resident-weights kernel (every layer but the stride-2 transitions) is
+// compiled exactly as before
+template <bool WSTREAM>
 __global__ void __launch_bounds__(NTHREADS, 1)
 conv_tc5_kernel(const __grid_constant__ Tc5Maps maps, const Tc5P p) {
   extern __shared__ __align__(128) unsigned char smem[];
@@ -108,7 +114,7 @@ conv_tc5_kernel(const __grid_constant__ Tc5Maps maps, const Tc5P p) {
   const int B_FULL = 1, B_EMPTY = 1 + p.S, B_ACCF = 1 + 2 * p.S, B_ACCE = 1 + 2 * p.S + p.NACC;
 
   unsigned char* sW = smem;
-  unsigned char* sH = smem + p.w_bytes;
+  unsigned char* sH = smem + (WSTREAM ? 0u : p.w_bytes);
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const uint32_t lbo_b = (uint32_t)p.NS * 16u, sbo_b = 128u;
   const int slice = blockIdx.y;
@@ -160,8 +166,16 @@ conv_tc5_kernel(const __grid_constant__ Tc5Maps maps, const Tc5P p) {
           mbar_wait(BAR(B_EMPTY + s), phase ^ 1u);
           if (p.dbg && blockIdx.x == 0 && blockIdx.y == 0 && it < 64 && c == 0) p.dbg[it * 8 + 0] = clock64();
           if (!(p.skip & 1)) {
-            mbar_arrive_expect_tx(BAR(B_FULL + s), p.tx_bytes);
+            mbar_arrive_expect_tx(BAR(B_FULL + s), p.tx_bytes + (WSTREAM ? (uint32_t)p.ntaps * p.wtap_bytes : 0u));
             const uint32_t dst = smem_u32(sH + (size_t)s * p.stage_bytes);
+            if (WSTREAM) {
+              // this chunk's planes of every tap: [slice][tap][Cin/8][NS][8] -> [tap][KC/8][NS][8] inside the stage
+              const unsigned char* wsrc = reinterpret_cast<const unsigned char*>(p.w) +
+                                          ((size_t)blockIdx.y * p.ntaps * (p.Cin >> 3) + (size_t)c * (p.KC >> 3)) * p.NS * 16u;
+              for (int tp = 0; tp < p.ntaps; ++tp)
+                bulk_load(dst + p.a_bytes + (uint32_t)tp * p.wtap_bytes, wsrc + (size_t)tp * (p.Cin >> 3) * p.NS * 16u,
+                          p.wtap_bytes, BAR(B_FULL + s));
+            }
             if (p.stride == 1) {
               tma_load_5d(dst, &maps.m[0], BAR(B_FULL + s), 0, tx * TW - p.halo, ty * TH - p.halo, c * (p.KC >> 3), n);
             } else {
@@ -191,7 +205,7 @@ conv_tc5_kernel(const __grid_constant__ Tc5Maps maps, const Tc5P p) {
     // are predicated on one elected lane: UTCHMMA takes its descriptors from UNIFORM registers, and
     // issuing from inside `if (lane == 0)` made the compiler wrap every MMA in a ~20-instruction
     // R2UR "waterfall" loop (~150 cycles per MMA, profiles/r1_notes.md).
-    if (warp == 0 && elect_one()) {
+    if (warp == 0 && !WSTREAM && elect_one()) {
       mbar_arrive_expect_tx(BAR(0), p.w_bytes);
       const unsigned char* wsrc = reinterpret_cast<const unsigned char*>(p.w) + (size_t)slice * p.w_bytes;
       for (uint32_t off = 0; off < p.w_bytes; off += 32768u) {
@@ -201,13 +215,13 @@ conv_tc5_kernel(const __grid_constant__ Tc5Maps maps, const Tc5P p) {
     }
     __syncwarp();
     const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(p.NS >> 3) << 17) | ((128u >> 4) << 24);
-    mbar_wait(BAR(0), 0);
+    if (!WSTREAM) mbar_wait(BAR(0), 0);
     const int kc2n = p.KC >> 4;
     const uint32_t hiB = desc_hi(sbo_b);
     const uint32_t a0 = smem_u32(sH), w0 = smem_u32(sW);
     const uint32_t b_kstep = (2u * lbo_b) >> 4;     // per k16 step, in 16-byte units
-    const uint32_t b_tapstep = ((uint32_t)(p.Cin >> 3) * lbo_b) >> 4;
-    const uint32_t b_chunkstep = ((uint32_t)(p.KC >> 3) * lbo_b) >> 4;
+    const uint32_t b_tapstep = ((uint32_t)((WSTREAM ? p.KC : p.Cin) >> 3) * lbo_b) >> 4;
+    const uint32_t b_chunkstep = WSTREAM ? 0u : ((uint32_t)(p.KC >> 3) * lbo_b) >> 4;
     const uint32_t lo_lbo_b = ((lbo_b >> 4) & 0x3FFFu) << 16;
     // fast path: 3x3 stride 1 (one halo patch: the descriptor high word and k step are the same for every tap)
     const bool fast9 = p.ntaps == 9 && p.stride == 1 && !(p.skip & 2) && (kc2n == 1 || kc2n == 2 || kc2n == 4);
@@ -239,7 +253,8 @@ conv_tc5_kernel(const __grid_constant__ Tc5Maps maps, const Tc5P p) {
         // low descriptor words: (address >> 4) | LBO << 16; adding 16-byte offsets never carries out of
         // the 14-bit address field (shared memory is < 256 KB)
         const uint32_t a_stage = (a0 + (uint32_t)s * p.stage_bytes) >> 4;
-        const uint32_t w_chunk = ((w0 >> 4) + (uint32_t)c * b_chunkstep) | lo_lbo_b;
+        const uint32_t w_chunk = WSTREAM ? (((a0 + (uint32_t)s * p.stage_bytes + p.a_bytes) >> 4) | lo_lbo_b)
+                                           : (((w0 >> 4) + (uint32_t)c * b_chunkstep) | lo_lbo_b);
         if (elect_one()) {
           uint32_t acc = c > 0;
           const int ntp = fast9 ? 0 : ((p.skip & 2) ? 1 : p.ntaps);
@@ -434,12 +449,32 @@ inline int stage_bytes_of(int mode, int kc) {
 // Shape -> (NS, KC, S): shared with the host-side packer through rsg_conv_tc5_config().
 // mode: 0 = 1x1 stride 1, 1 = taps in the 3x3 neighbourhood, stride 1 (halo patch), 2 = 3x3 neighbourhood,
 // stride 2 (four phase patches).
-extern "C" int rsg_conv_tc5_config(int Cin, int CoutPad, int ntaps, int mode, int* NS, int* KC, int* S) {
+// *stream = 1: the slice's weights do not fit beside >= 4 stride-2 stages, so every stage carries the weights of its own
+// K chunk (same w_tc5 packing; the producer bulk-copies ntaps pieces per stage).
+static int tc5_pick(int Cin, int CoutPad, int ntaps, int mode, int* NS, int* KC, int* S, int* stream) {
+  *stream = 0;
   if (Cin % 16 != 0 || CoutPad % 32 != 0 || ntaps < 1 || ntaps > 9 || mode < 0 || mode > 2) return 0;
   const int budget = 196 * 1024;
   const int cands[4] = {128, 96, 64, 32};
   // prefer the widest slice that still leaves >= 4 stages; among the K chunkings the largest with >= 4 stages
   for (int min_s = 4; min_s >= 2; min_s -= 2) {
+    if (min_s < 4 && mode == 2 && !getenv("RSG_TC5_NO_WSTREAM")) {
+      // stride 2 with fewer than four resident-weight stages measured 2x slower than the generic kernel: stream the
+      // weights with the halo stages instead (widest slice, largest chunk with >= 4 stages)
+      for (int i = 0; i < 4; ++i) {
+        const int ns = cands[i];
+        if (ns > CoutPad || CoutPad % ns != 0) continue;
+        for (int kc = 32; kc >= 16; kc -= 16) {
+          if (Cin % kc != 0 || Cin / kc > MAX_CHUNKS) continue;
+          const long long stage = stage_bytes_of(mode, kc) + (long long)ntaps * (kc / 8) * ns * 16;
+          if (4 * stage > budget) continue;
+          int s = (int)(budget / stage) & ~1;
+          if (s > MAX_STAGES) s = MAX_STAGES;
+          *NS = ns; *KC = kc; *S = s; *stream = 1;
+          return 1;
+        }
+      }
+    }
     for (int i = 0; i < 4; ++i) {
       const int ns = cands[i];
       if (ns > CoutPad || CoutPad % ns != 0) continue;
@@ -458,6 +493,11 @@ extern "C" int rsg_conv_tc5_config(int Cin, int CoutPad, int ntaps, int mode, in
     }
   }
   return 0;
+}
+
+extern "C" int rsg_conv_tc5_config(int Cin, int CoutPad, int ntaps, int mode, int* NS, int* KC, int* S) {
+  int stream = 0;
+  return tc5_pick(Cin, CoutPad, ntaps, mode, NS, KC, S, &stream);
 }
 
 int conv_tc5_launch(const ConvP& p, cudaStream_t s, int* handled) {
@@ -480,10 +520,10 @@ int conv_tc5_launch(const ConvP& p, cudaStream_t s, int* handled) {
   const int mode = p.stride == 2 ? 2 : halo;
   for (int q = 0; q < p.nres; ++q)
     if (p.res[q].cs % 8 != 0 || p.res[q].co % 8 != 0) return RSG_OK;
-  int NS, KC, S;
-  if (!rsg_conv_tc5_config(p.Cin, p.CoutPad, p.ntaps, mode, &NS, &KC, &S)) return RSG_OK;
+  int NS, KC, S, wstream = 0;
+  if (!tc5_pick(p.Cin, p.CoutPad, p.ntaps, mode, &NS, &KC, &S, &wstream)) return RSG_OK;
   // a stride-2 layer whose weights leave room for only two phase-patch stages (256->64: 147 KB per 32-channel
-  // slice) measured 2x slower than the generic kernel
+  // slice) measured 2x slower than the generic kernel (tc5_pick streams the weights instead where it can)
   if (p.stride == 2 && S < 4 && !getenv("RSG_TC5_ANYSIZE")) return RSG_OK;
   if (p.M == 0) { *handled = 1; return RSG_OK; }
 
@@ -553,7 +593,13 @@ int conv_tc5_launch(const ConvP& p, cudaStream_t s, int* handled) {
     k.dbg = dbg_buf;
   }
   k.w_bytes = (uint32_t)p.ntaps * p.Cin * NS * 2;
-  const size_t smem = (size_t)k.w_bytes + (size_t)S * k.stage_bytes;
+  k.wstream = wstream;
+  if (wstream) {
+    k.a_bytes = k.stage_bytes;                             // multiple of 128 (phase patches are padded to 128)
+    k.wtap_bytes = (uint32_t)(KC / 8) * NS * 16u;
+    k.stage_bytes += (uint32_t)p.ntaps * k.wtap_bytes;
+  }
+  const size_t smem = (wstream ? 0 : (size_t)k.w_bytes) + (size_t)S * k.stage_bytes;
   // accumulator ring: MMA completion + barrier wake-up latency is ~1-2k cycles per tile hand-off, so
   // two accumulators leave the tensor pipe idle (profiles/r1_notes.md); use up to 8
   const uint32_t col_budget = 512u;                       // one CTA per SM owns all of TMEM
@@ -588,8 +634,10 @@ int conv_tc5_launch(const ConvP& p, cudaStream_t s, int* handled) {
 
   static bool attr_done = false;
   if (!attr_done) {
-    RSG_CUDA(cudaFuncSetAttribute(conv_tc5_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
-    RSG_CUDA(cudaFuncSetAttribute(conv_tc5_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
+    RSG_CUDA(cudaFuncSetAttribute(conv_tc5_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+    RSG_CUDA(cudaFuncSetAttribute(conv_tc5_kernel<false>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
+    RSG_CUDA(cudaFuncSetAttribute(conv_tc5_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+    RSG_CUDA(cudaFuncSetAttribute(conv_tc5_kernel<true>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
     attr_done = true;
   }
   const int occ = 1;
@@ -610,7 +658,8 @@ int conv_tc5_launch(const ConvP& p, cudaStream_t s, int* handled) {
       if (rc) return rc;
     }
   }
-  RSG_CUDA(launch_pdl(conv_tc5_kernel, grid, dim3(threads), smem, s, maps, k));
+  if (wstream) RSG_CUDA(launch_pdl(conv_tc5_kernel<true>, grid, dim3(threads), smem, s, maps, k));
+  else RSG_CUDA(launch_pdl(conv_tc5_kernel<false>, grid, dim3(threads), smem, s, maps, k));
   if (k.dbg) {
     static int dumped = 0;
     if (dumped++ == 3) {

@@ -47,6 +47,8 @@ CASES = [
     (256, 256, 3, 1, 8, 6, True, True),
     (144, 48, 3, 1, 10, 8, True, False),
     (192, 192, 3, 1, 24, 18, True, True),      # W48 branch 2: weight-streaming kernel with 96-column slices
+    (256, 64, 3, 2, 32, 24, True, False),      # transition1: stride 2, weights streamed with the halo stages
+    (256, 96, 3, 2, 26, 20, False, True),      # W48 transition1 (ragged map)
 ]
 
 
