@@ -69,6 +69,14 @@ int rsg_oks_nms(void* stream, const float* kpts, const double* scores, const dou
 int rsg_oks_iou(void* stream, const float* g, const float* d, double a_g, const double* a_d,
                 const double* sigmas, int K, int M, double* out);
 
+/* Segmented soft OKS-NMS, one image per CTA.  Replaces lib/nms/nms.py:127-180 (rescore 'gaussian' + soft_oks_nms;
+ * imported by lib/dataset/coco.py:24, used when TEST.SOFT_NMS is set): up to max_dets rounds (the reference hard-codes
+ * 20), each keeping the best remaining detection and multiplying the other scores by exp(-oks^2 / thresh).
+ *   keep i32 [n_imgs][max_dets]: kept indices RELATIVE to the image in selection order;  keep_counts i32 [n_imgs] */
+int rsg_soft_oks_nms(void* stream, const float* kpts, const double* scores, const double* areas,
+                     const int32_t* img_offsets, int n_imgs, int max_per_img, const double* sigmas, int K,
+                     double thresh, int max_dets, int32_t* keep, int32_t* keep_counts);
+
 /* evaluate()-side rescoring, lib/dataset/crowdpose.py:1294-1306 / coco.py:1249-1261:
  * score[i] = box_score[i] * mean(maxvals[i,k] for maxvals[i,k] > in_vis_thre). */
 int rsg_rescore(void* stream, const float* maxvals, const double* box_scores, int n, int K,

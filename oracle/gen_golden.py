@@ -134,6 +134,17 @@ def nms_cases():
         for th in (0.5, 0.9, 0.99):
             db = [dict(keypoints=kb[j], score=sb[j], area=ab[j]) for j in range(len(sb))]
             big[f'big_keep_{th}'] = np.asarray(f['oks_nms'](db, th, sig), np.int32)
+        # soft_oks_nms (nms.py:138-180) on the first 40 images and on the bigger one (more than 20 detections)
+        soft_keep, soft_counts = [], []
+        for i in range(40):
+            db = [dict(keypoints=kpts[j], score=scores[j], area=areas[j]) for j in range(off[i], off[i + 1])]
+            kp = f['soft_oks_nms'](db, 0.9, sig)
+            soft_keep.extend(int(v) for v in kp)
+            soft_counts.append(len(kp))
+        db = [dict(keypoints=kb[j], score=sb[j], area=ab[j]) for j in range(len(sb))]
+        big['soft_big_keep'] = np.asarray(f['soft_oks_nms'](db, 0.5, sig), np.int32)
+        big['soft_keep'] = np.asarray(soft_keep, np.int32)
+        big['soft_counts'] = np.asarray(soft_counts, np.int32)
         fn = os.path.join(OUT, f'nms_{tag}.npz')
         np.savez_compressed(fn, k=k, seed=3, n_imgs=300, per_img=20, thresh=0.9,
                             keep=np.asarray(keeps, np.int32), counts=np.asarray(counts, np.int32),

@@ -7,6 +7,7 @@ unmodified reference's ``oks_nms`` (``oracle/gen_golden.py``).
 Reference lines followed (paths under /root/reference):
   lib/nms/nms.py:75-94            oks_iou (dx,dy,squares in fp32; the rest fp64; np.sum order)
   lib/nms/nms.py:97-124           oks_nms greedy sweep (keep oks <= thresh)
+  lib/nms/nms.py:127-180          rescore ('gaussian') + soft_oks_nms (at most 20 detections)
   lib/dataset/crowdpose.py:1294-1306   rescoring: box_score * mean(maxval > in_vis_thre)
 """
 import numpy as np
@@ -89,3 +90,28 @@ def rescore(box_score, maxvals, in_vis_thre):
     if valid != 0:
         kpt_score = kpt_score / valid
     return kpt_score * box_score
+
+
+def soft_oks_nms(kpts_db, thresh, sigmas=None, in_vis_thre=None):
+    """nms.py:138-180 (with rescore(), nms.py:127-135, type 'gaussian')."""
+    if len(kpts_db) == 0:
+        return []
+    scores = np.array([k['score'] for k in kpts_db])
+    kpts = np.array([k['keypoints'].flatten() for k in kpts_db])
+    areas = np.array([k['area'] for k in kpts_db])
+    order = scores.argsort()[::-1]
+    scores = scores[order]
+    max_dets = 20
+    keep = np.zeros(max_dets, dtype=np.intp)
+    keep_cnt = 0
+    while order.size > 0 and keep_cnt < max_dets:
+        i = order[0]
+        ovr = oks_iou(kpts[i], kpts[order[1:]], areas[i], areas[order[1:]], sigmas, in_vis_thre)
+        order = order[1:]
+        scores = scores[1:] * np.exp(-ovr ** 2 / thresh)
+        tmp = scores.argsort()[::-1]
+        order = order[tmp]
+        scores = scores[tmp]
+        keep[keep_cnt] = i
+        keep_cnt += 1
+    return keep[:keep_cnt]

@@ -91,8 +91,8 @@ def ref_model(cfg, name):
 def ref_functions():
     _install_shims()
     from core.inference import get_final_preds, get_max_preds
-    from nms.nms import oks_iou, oks_nms
+    from nms.nms import oks_iou, oks_nms, soft_oks_nms
     from utils.transforms import crop, flip_back, get_affine_transform
     return dict(get_final_preds=get_final_preds, get_max_preds=get_max_preds,
-                oks_nms=oks_nms, oks_iou=oks_iou, flip_back=flip_back,
+                oks_nms=oks_nms, oks_iou=oks_iou, soft_oks_nms=soft_oks_nms, flip_back=flip_back,
                 get_affine_transform=get_affine_transform, crop=crop)

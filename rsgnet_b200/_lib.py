@@ -62,6 +62,8 @@ _SIGS = {
     'rsg_flip_back': (C.c_int, [C.c_void_p] * 4 + [C.c_int] * 4),
     'rsg_oks_nms': (C.c_int, [C.c_void_p] * 5 + [C.c_int, C.c_int, C.c_void_p, C.c_int,
                                                  C.c_double, C.c_void_p, C.c_void_p]),
+    'rsg_soft_oks_nms': (C.c_int, [C.c_void_p] * 5 + [C.c_int, C.c_int, C.c_void_p, C.c_int, C.c_double, C.c_int,
+                                      C.c_void_p, C.c_void_p]),
     'rsg_oks_iou': (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_double, C.c_void_p, C.c_void_p,
                               C.c_int, C.c_int, C.c_void_p]),
     'rsg_rescore': (C.c_int, [C.c_void_p] * 3 + [C.c_int, C.c_int, C.c_double, C.c_void_p]),

@@ -96,6 +96,68 @@ oks_nms_kernel(const float* __restrict__ kpts, const double* __restrict__ scores
   if (tid == 0) keep_counts[img] = nkeep;
 }
 
+// soft_oks_nms (lib/nms/nms.py:138-180): up to max_dets rounds per image; every round keeps the best remaining detection
+// and multiplies the scores of the others by exp(-oks^2 / thresh) (rescore(), nms.py:127-135, 'gaussian').  The
+// reference re-sorts after every round; taking the maximum of the remaining scores is the same selection (ties: the
+// later index first, like scores.argsort()[::-1] on distinct positions).  One CTA per image.
+__global__ void __launch_bounds__(128)
+soft_oks_nms_kernel(const float* __restrict__ kpts, const double* __restrict__ scores,
+                    const double* __restrict__ areas, const int32_t* __restrict__ offs,
+                    const double* __restrict__ sigmas, int K, double thresh, int max_dets,
+                    int32_t* __restrict__ keep, int32_t* __restrict__ keep_counts) {
+  extern __shared__ unsigned char smem_raw[];
+  __shared__ double vars[RSG_NMS_MAXK];
+  __shared__ double wbest[4];
+  __shared__ int widx[4];
+  __shared__ int best_i;
+  const int img = blockIdx.x;
+  const int beg = offs[img], n = offs[img + 1] - beg;
+  double* cur = reinterpret_cast<double*>(smem_raw);      // [n] current scores
+  int* alive = reinterpret_cast<int*>(cur + n);           // [n]
+  const int tid = threadIdx.x, nt = blockDim.x;
+  if (tid < K) {
+    double s2 = __dmul_rn(sigmas[tid], 2.0);
+    vars[tid] = __dmul_rn(s2, s2);
+  }
+  for (int i = tid; i < n; i += nt) { cur[i] = scores[beg + i]; alive[i] = 1; }
+  __syncthreads();
+  int cnt = 0;
+  const int rounds = n < max_dets ? n : max_dets;
+  for (; cnt < rounds; ++cnt) {
+    // argmax of the remaining scores (value, then the later index)
+    double bv = 0.0;
+    int bi = -1;
+    for (int i = tid; i < n; i += nt)
+      if (alive[i] && (bi < 0 || cur[i] > bv || (cur[i] == bv && i > bi))) { bv = cur[i]; bi = i; }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      const double ov = __shfl_xor_sync(0xffffffffu, bv, o);
+      const int oi = __shfl_xor_sync(0xffffffffu, bi, o);
+      if (oi >= 0 && (bi < 0 || ov > bv || (ov == bv && oi > bi))) { bv = ov; bi = oi; }
+    }
+    if ((tid & 31) == 0) { wbest[tid >> 5] = bv; widx[tid >> 5] = bi; }
+    __syncthreads();
+    if (tid == 0) {
+      for (int w = 1; w < (nt >> 5); ++w)
+        if (widx[w] >= 0 && (bi < 0 || wbest[w] > bv || (wbest[w] == bv && widx[w] > bi))) { bv = wbest[w]; bi = widx[w]; }
+      best_i = bi;
+      keep[(size_t)img * max_dets + cnt] = bi;
+      alive[bi] = 0;
+    }
+    __syncthreads();
+    const int i = best_i;
+    const float* g = kpts + (size_t)(beg + i) * K * 3;
+    const double a_g = areas[beg + i];
+    for (int j = tid; j < n; j += nt) {
+      if (!alive[j]) continue;
+      const double oks = oks_pair(g, kpts + (size_t)(beg + j) * K * 3, a_g, areas[beg + j], vars, K);
+      cur[j] = __dmul_rn(cur[j], exp(__ddiv_rn(-__dmul_rn(oks, oks), thresh)));
+    }
+    __syncthreads();
+  }
+  if (tid == 0) keep_counts[img] = cnt;
+}
+
 __global__ void oks_iou_kernel(const float* __restrict__ g, const float* __restrict__ d, double a_g,
                                const double* __restrict__ a_d, const double* __restrict__ sigmas, int K,
                                int M, double* __restrict__ out) {
@@ -145,6 +207,24 @@ extern "C" int rsg_oks_nms(void* stream, const float* kpts, const double* scores
     RSG_CUDA(cudaFuncSetAttribute(oks_nms_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   oks_nms_kernel<<<n_imgs, 128, smem, (cudaStream_t)stream>>>(kpts, scores, areas, img_offsets,
                                                              sigmas, K, thresh, keep, keep_counts);
+  RSG_LAUNCH_CHECK();
+  return RSG_OK;
+}
+
+extern "C" int rsg_soft_oks_nms(void* stream, const float* kpts, const double* scores, const double* areas,
+                                const int32_t* img_offsets, int n_imgs, int max_per_img, const double* sigmas, int K,
+                                double thresh, int max_dets, int32_t* keep, int32_t* keep_counts) {
+  RSG_REQUIRE(n_imgs >= 0 && K > 0 && K <= RSG_NMS_MAXK, "rsg_soft_oks_nms: bad n_imgs=%d or K=%d", n_imgs, K);
+  RSG_REQUIRE(max_dets >= 1, "rsg_soft_oks_nms: max_dets=%d", max_dets);
+  if (n_imgs == 0) return RSG_OK;
+  RSG_REQUIRE(kpts && scores && areas && img_offsets && sigmas && keep && keep_counts, "rsg_soft_oks_nms: null pointer");
+  RSG_REQUIRE(max_per_img >= 0, "rsg_soft_oks_nms: max_per_img < 0");
+  size_t smem = (size_t)max_per_img * (sizeof(double) + sizeof(int));
+  RSG_REQUIRE(smem <= 200 * 1024, "rsg_soft_oks_nms: more than %d detections in one image", 17000);
+  if (smem > 48 * 1024)
+    RSG_CUDA(cudaFuncSetAttribute(soft_oks_nms_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  soft_oks_nms_kernel<<<n_imgs, 128, smem, (cudaStream_t)stream>>>(kpts, scores, areas, img_offsets, sigmas, K, thresh,
+                                                                  max_dets, keep, keep_counts);
   RSG_LAUNCH_CHECK();
   return RSG_OK;
 }

@@ -105,7 +105,43 @@ def rescore(maxvals, box_scores, in_vis_thre, device=None):
     return out.cpu().numpy()
 
 
+def soft_oks_nms_batched(kpts, scores, areas, img_offsets, thresh, sigmas=None, max_dets=20, device=None):
+    """Segmented soft OKS-NMS (nms.py:138-180 for all images of an evaluate() call): returns (keep i32 [n_imgs, max_dets]
+    -- indices relative to the image, in selection order --, counts i32 [n_imgs]) as NumPy arrays."""
+    _lib.require_cuda()
+    device = torch.device(device or 'cuda')
+    off_np = np.ascontiguousarray(img_offsets, dtype=np.int32)
+    n_imgs = len(off_np) - 1
+    if n_imgs <= 0:
+        return np.zeros((0, max_dets), np.int32), np.zeros(0, np.int32)
+    max_per = int(np.max(np.diff(off_np)))
+    k = torch.from_numpy(np.ascontiguousarray(kpts, np.float32)).to(device)
+    K = int(k.shape[1]) if k.dim() == 3 else int(k.shape[-1]) // 3
+    s = torch.from_numpy(np.ascontiguousarray(scores, np.float64)).to(device)
+    a = torch.from_numpy(np.ascontiguousarray(areas, np.float64)).to(device)
+    off = torch.from_numpy(off_np).to(device)
+    if sigmas is None or not isinstance(sigmas, np.ndarray):
+        sigmas = COCO_SIGMAS
+    assert len(sigmas) == K, f'{len(sigmas)} sigmas for K={K} key points'
+    sg = torch.from_numpy(np.ascontiguousarray(sigmas, np.float64)).to(device)
+    keep = torch.full((n_imgs, max_dets), -1, dtype=torch.int32, device=device)
+    counts = torch.zeros(n_imgs, dtype=torch.int32, device=device)
+    with torch.cuda.device(device):
+        _lib.check(_lib.lib().rsg_soft_oks_nms(_lib.stream_ptr(device), _p(k), _p(s), _p(a), _p(off), n_imgs, max_per,
+                                               _p(sg), K, float(thresh), int(max_dets), _p(keep), _p(counts)))
+    return keep.cpu().numpy(), counts.cpu().numpy()
+
+
 def soft_oks_nms(kpts_db, thresh, sigmas=None, in_vis_thre=None):
-    """Present only because lib/dataset/coco.py:24 imports the name; TEST.SOFT_NMS is False in
-    every config (lib/config/default.py:134) and the path is outside the hot path."""
-    raise NotImplementedError('soft_oks_nms is outside the RSGNet inference hot path (SOFT_NMS=False)')
+    """nms.py:138-180: at most 20 detections, chosen by repeatedly taking the best score and decaying the others by
+    exp(-oks^2 / thresh).  Returns an integer array of indices like the reference (``keep[:keep_cnt]``)."""
+    if len(kpts_db) == 0:
+        return []
+    if in_vis_thre is not None:
+        raise NotImplementedError('soft_oks_nms(in_vis_thre=...) is not supported (no reference caller uses it)')
+    scores = np.array([kpts_db[i]['score'] for i in range(len(kpts_db))], np.float64)
+    kpts = np.array([np.asarray(kpts_db[i]['keypoints'], np.float32).reshape(-1, 3)
+                     for i in range(len(kpts_db))], np.float32)
+    areas = np.array([kpts_db[i]['area'] for i in range(len(kpts_db))], np.float64)
+    keep, counts = soft_oks_nms_batched(kpts, scores, areas, np.array([0, len(kpts_db)], np.int32), thresh, sigmas)
+    return keep[0, :int(counts[0])].astype(np.intp)

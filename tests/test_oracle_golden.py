@@ -76,6 +76,15 @@ def test_nms_oracle_vs_reference(golden_dir, tag):
     db = [dict(keypoints=kb[j], score=sb[j], area=ab[j]) for j in range(len(sb))]
     assert [int(v) for v in nms_oracle.oks_nms(db, 0.9, sig)] == list(g['big_keep_0.9'])
     assert nms_oracle.oks_nms([], 0.9) == []
+    # soft_oks_nms (nms.py:138-180): first 40 images + the 150-detection image (more than max_dets = 20 candidates)
+    pos = 0
+    for i in range(40):
+        db = [dict(keypoints=kpts[j], score=scores[j], area=areas[j]) for j in range(off[i], off[i + 1])]
+        c = int(g['soft_counts'][i])
+        assert list(nms_oracle.soft_oks_nms(db, 0.9, sig)) == list(g['soft_keep'][pos:pos + c])
+        pos += c
+    db = [dict(keypoints=kb[j], score=sb[j], area=ab[j]) for j in range(len(sb))]
+    assert list(nms_oracle.soft_oks_nms(db, 0.5, sig)) == list(g['soft_big_keep'])
 
 
 @pytest.mark.parametrize('key', MODEL_CASES)

@@ -10,7 +10,7 @@ import torch
 from oracle import decode_oracle, nms_oracle
 from rsgnet_b200 import presets, synth
 from rsgnet_b200.core.inference import decode_device, get_final_preds, get_max_preds
-from rsgnet_b200.nms.nms import oks_iou, oks_nms, oks_nms_batched, rescore
+from rsgnet_b200.nms.nms import oks_iou, oks_nms, oks_nms_batched, rescore, soft_oks_nms, soft_oks_nms_batched
 from rsgnet_b200.utils.transforms import flip_back, flip_perm
 
 pytestmark = pytest.mark.gpu
@@ -158,3 +158,26 @@ def test_oks_iou_vs_oracle():
     got = oks_iou(flat[0], flat[1:], areas[0], areas[1:])
     ref = nms_oracle.oks_iou(flat[0], flat[1:], areas[0], areas[1:])
     assert np.abs(got - ref).max() <= 4e-16          # fp64 exp may differ from NumPy's by an ulp
+
+
+@pytest.mark.parametrize('tag', ['coco', 'crowdpose'])
+def test_soft_oks_nms_vs_reference(golden_dir, tag):
+    """soft_oks_nms (nms.py:138-180) on the device: the kept indices, in selection order, equal the reference's on the
+    fixtures (per image through the reference's dict interface, and all images in one segmented launch)."""
+    g = _load(golden_dir, f'nms_{tag}.npz')
+    k = int(g['k'])
+    sig = None if tag == 'coco' else nms_oracle.CROWDPOSE_SIGMAS
+    kpts, scores, areas, off = synth.detections(int(g['n_imgs']), int(g['per_img']), k, seed=int(g['seed']), ragged=True)
+    keep, counts = soft_oks_nms_batched(kpts[:off[40]], scores[:off[40]], areas[:off[40]], off[:41], 0.9, sig)
+    assert list(counts) == list(g['soft_counts'])
+    pos = 0
+    for i in range(40):
+        c = int(counts[i])
+        assert list(keep[i, :c]) == list(g['soft_keep'][pos:pos + c]), i
+        pos += c
+    kb, sb, ab, _ = synth.detections(1, int(g['big_n']), k, seed=int(g['big_seed']))
+    db = [dict(keypoints=kb[j], score=sb[j], area=ab[j]) for j in range(len(sb))]
+    got = soft_oks_nms(db, 0.5, sig)
+    assert got.dtype == np.intp and list(got) == list(g['soft_big_keep']) and len(got) == 20
+    assert list(got) == list(nms_oracle.soft_oks_nms(db, 0.5, sig))
+    assert soft_oks_nms([], 0.9) == []
