@@ -62,12 +62,15 @@ int rsg_flip_back(void* stream, const float* in, float* out, const int32_t* flip
  *                     greedy selection order;  keep_counts i32 [n_imgs] */
 int rsg_oks_nms(void* stream, const float* kpts, const double* scores, const double* areas,
                 const int32_t* img_offsets, int n_imgs, int max_per_img, const double* sigmas,
-                int K, double thresh, int32_t* keep, int32_t* keep_counts);
+                int K, double thresh, int32_t* keep, int32_t* keep_counts, int use_in_vis_thre, double in_vis_thre);
+/* use_in_vis_thre != 0 (the reference's in_vis_thre is not None, nms.py:85-90; all three OKS entry points): only key
+ * points of the compared detection d with score > in_vis_thre enter the mean (the reference's `list(a) and list(b)` is the
+ * second list), compared in fp32; a detection without visible key points has OKS 0. */
 
 /* lib/nms/nms.py:75-94 oks_iou: OKS of one detection g (f32 [K,3]) against M detections d (f32 [M,K,3]);
  * a_g, a_d f64 areas; out f64 [M]. */
 int rsg_oks_iou(void* stream, const float* g, const float* d, double a_g, const double* a_d,
-                const double* sigmas, int K, int M, double* out);
+                const double* sigmas, int K, int M, double* out, int use_in_vis_thre, double in_vis_thre);
 
 /* Segmented soft OKS-NMS, one image per CTA.  Replaces lib/nms/nms.py:127-180 (rescore 'gaussian' + soft_oks_nms;
  * imported by lib/dataset/coco.py:24, used when TEST.SOFT_NMS is set): up to max_dets rounds (the reference hard-codes
@@ -75,7 +78,8 @@ int rsg_oks_iou(void* stream, const float* g, const float* d, double a_g, const 
  *   keep i32 [n_imgs][max_dets]: kept indices RELATIVE to the image in selection order;  keep_counts i32 [n_imgs] */
 int rsg_soft_oks_nms(void* stream, const float* kpts, const double* scores, const double* areas,
                      const int32_t* img_offsets, int n_imgs, int max_per_img, const double* sigmas, int K,
-                     double thresh, int max_dets, int32_t* keep, int32_t* keep_counts);
+                     double thresh, int max_dets, int32_t* keep, int32_t* keep_counts, int use_in_vis_thre,
+                     double in_vis_thre);
 
 /* evaluate()-side rescoring, lib/dataset/crowdpose.py:1294-1306 / coco.py:1249-1261:
  * score[i] = box_score[i] * mean(maxvals[i,k] for maxvals[i,k] > in_vis_thre). */

@@ -145,6 +145,19 @@ def nms_cases():
         big['soft_big_keep'] = np.asarray(f['soft_oks_nms'](db, 0.5, sig), np.int32)
         big['soft_keep'] = np.asarray(soft_keep, np.int32)
         big['soft_counts'] = np.asarray(soft_counts, np.int32)
+        # in_vis_thre = 0.4 (nms.py:85-90; no caller of the reference passes it): oks_iou values, oks_nms and soft_oks_nms
+        flat = kb.reshape(len(sb), -1)
+        big['vis_oks'] = np.asarray(f['oks_iou'](flat[0], flat[1:], ab[0], ab[1:], sig, 0.4), np.float64)
+        vis_keep, vis_counts = [], []
+        for i in range(40):
+            db = [dict(keypoints=kpts[j], score=scores[j], area=areas[j]) for j in range(off[i], off[i + 1])]
+            kp = f['oks_nms'](db, 0.9, sig, 0.4)
+            vis_keep.extend(int(v) for v in kp)
+            vis_counts.append(len(kp))
+        big['vis_keep'] = np.asarray(vis_keep, np.int32)
+        big['vis_counts'] = np.asarray(vis_counts, np.int32)
+        db = [dict(keypoints=kb[j], score=sb[j], area=ab[j]) for j in range(len(sb))]
+        big['vis_soft_big_keep'] = np.asarray(f['soft_oks_nms'](db, 0.5, sig, 0.4), np.int32)
         fn = os.path.join(OUT, f'nms_{tag}.npz')
         np.savez_compressed(fn, k=k, seed=3, n_imgs=300, per_img=20, thresh=0.9,
                             keep=np.asarray(keeps, np.int32), counts=np.asarray(counts, np.int32),

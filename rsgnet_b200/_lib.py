@@ -61,11 +61,11 @@ _SIGS = {
                             [C.c_int] * 2 + [C.c_void_p] * 4),
     'rsg_flip_back': (C.c_int, [C.c_void_p] * 4 + [C.c_int] * 4),
     'rsg_oks_nms': (C.c_int, [C.c_void_p] * 5 + [C.c_int, C.c_int, C.c_void_p, C.c_int,
-                                                 C.c_double, C.c_void_p, C.c_void_p]),
+                                                 C.c_double, C.c_void_p, C.c_void_p, C.c_int, C.c_double]),
     'rsg_soft_oks_nms': (C.c_int, [C.c_void_p] * 5 + [C.c_int, C.c_int, C.c_void_p, C.c_int, C.c_double, C.c_int,
-                                      C.c_void_p, C.c_void_p]),
+                                      C.c_void_p, C.c_void_p, C.c_int, C.c_double]),
     'rsg_oks_iou': (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_double, C.c_void_p, C.c_void_p,
-                              C.c_int, C.c_int, C.c_void_p]),
+                              C.c_int, C.c_int, C.c_void_p, C.c_int, C.c_double]),
     'rsg_rescore': (C.c_int, [C.c_void_p] * 3 + [C.c_int, C.c_int, C.c_double, C.c_void_p]),
     'rsg_warp_affine': (C.c_int, [C.c_void_p] * 4 + [C.c_int] * 4 + [C.c_void_p] * 3),
     'rsg_plan_create': (C.c_int, [C.POINTER(C.c_void_p), C.c_int]),

@@ -35,24 +35,28 @@ __device__ double numpy_sum(const double* a, int n) {
 
 #define RSG_NMS_MAXK 64
 
+// in_vis_thre (nms.py:85-90): the reference evaluates `list(vg > t) and list(vd > t)`, which is the SECOND list (a
+// non-empty list is truthy): only key points of d with score > t count, compared in fp32 like NumPy does for a
+// float32 array against a Python float; no visible key point -> 0.
 __device__ double oks_pair(const float* __restrict__ g, const float* __restrict__ d, double a_g,
-                           double a_d, const double* __restrict__ vars, int K) {
+                           double a_d, const double* __restrict__ vars, int K, int use_vis, float vis) {
   double ex[RSG_NMS_MAXK];
   const double denom = __dadd_rn(__ddiv_rn(__dadd_rn(a_g, a_d), 2.0), 2.220446049250313e-16);
+  int m = 0;
   for (int k = 0; k < K; ++k) {
     float dx = __fsub_rn(d[3 * k], g[3 * k]);
     float dy = __fsub_rn(d[3 * k + 1], g[3 * k + 1]);
     float s = __fadd_rn(__fmul_rn(dx, dx), __fmul_rn(dy, dy));
     double e = __ddiv_rn(__ddiv_rn(__ddiv_rn((double)s, vars[k]), denom), 2.0);
-    ex[k] = exp(-e);
+    if (!use_vis || d[3 * k + 2] > vis) ex[m++] = exp(-e);
   }
-  return __ddiv_rn(numpy_sum(ex, K), (double)K);
+  return m ? __ddiv_rn(numpy_sum(ex, m), (double)m) : 0.0;
 }
 
 __global__ void __launch_bounds__(128)
 oks_nms_kernel(const float* __restrict__ kpts, const double* __restrict__ scores,
                const double* __restrict__ areas, const int32_t* __restrict__ offs,
-               const double* __restrict__ sigmas, int K, double thresh,
+               const double* __restrict__ sigmas, int K, double thresh, int use_vis, float vis,
                int32_t* __restrict__ keep, int32_t* __restrict__ keep_counts) {
   extern __shared__ unsigned char smem_raw[];
   __shared__ double vars[RSG_NMS_MAXK];
@@ -88,7 +92,7 @@ oks_nms_kernel(const float* __restrict__ kpts, const double* __restrict__ scores
     for (int q = p + 1 + tid; q < n; q += nt) {
       if (dead[q]) continue;
       const int j = order[q];
-      double oks = oks_pair(g, kpts + (size_t)(beg + j) * K * 3, a_g, areas[beg + j], vars, K);
+      double oks = oks_pair(g, kpts + (size_t)(beg + j) * K * 3, a_g, areas[beg + j], vars, K, use_vis, vis);
       if (oks > thresh) dead[q] = 1;
     }
     __syncthreads();
@@ -103,7 +107,7 @@ oks_nms_kernel(const float* __restrict__ kpts, const double* __restrict__ scores
 __global__ void __launch_bounds__(128)
 soft_oks_nms_kernel(const float* __restrict__ kpts, const double* __restrict__ scores,
                     const double* __restrict__ areas, const int32_t* __restrict__ offs,
-                    const double* __restrict__ sigmas, int K, double thresh, int max_dets,
+                    const double* __restrict__ sigmas, int K, double thresh, int max_dets, int use_vis, float vis,
                     int32_t* __restrict__ keep, int32_t* __restrict__ keep_counts) {
   extern __shared__ unsigned char smem_raw[];
   __shared__ double vars[RSG_NMS_MAXK];
@@ -150,7 +154,7 @@ soft_oks_nms_kernel(const float* __restrict__ kpts, const double* __restrict__ s
     const double a_g = areas[beg + i];
     for (int j = tid; j < n; j += nt) {
       if (!alive[j]) continue;
-      const double oks = oks_pair(g, kpts + (size_t)(beg + j) * K * 3, a_g, areas[beg + j], vars, K);
+      const double oks = oks_pair(g, kpts + (size_t)(beg + j) * K * 3, a_g, areas[beg + j], vars, K, use_vis, vis);
       cur[j] = __dmul_rn(cur[j], exp(__ddiv_rn(-__dmul_rn(oks, oks), thresh)));
     }
     __syncthreads();
@@ -160,7 +164,7 @@ soft_oks_nms_kernel(const float* __restrict__ kpts, const double* __restrict__ s
 
 __global__ void oks_iou_kernel(const float* __restrict__ g, const float* __restrict__ d, double a_g,
                                const double* __restrict__ a_d, const double* __restrict__ sigmas, int K,
-                               int M, double* __restrict__ out) {
+                               int M, int use_vis, float vis, double* __restrict__ out) {
   __shared__ double vars[RSG_NMS_MAXK];
   if (threadIdx.x < K) {
     double s2 = __dmul_rn(sigmas[threadIdx.x], 2.0);
@@ -168,7 +172,7 @@ __global__ void oks_iou_kernel(const float* __restrict__ g, const float* __restr
   }
   __syncthreads();
   int i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i < M) out[i] = oks_pair(g, d + (size_t)i * K * 3, a_g, a_d[i], vars, K);
+  if (i < M) out[i] = oks_pair(g, d + (size_t)i * K * 3, a_g, a_d[i], vars, K, use_vis, vis);
 }
 
 __global__ void rescore_kernel(const float* __restrict__ maxvals,
@@ -195,7 +199,7 @@ __global__ void rescore_kernel(const float* __restrict__ maxvals,
 extern "C" int rsg_oks_nms(void* stream, const float* kpts, const double* scores,
                            const double* areas, const int32_t* img_offsets, int n_imgs,
                            int max_per_img, const double* sigmas, int K, double thresh,
-                           int32_t* keep, int32_t* keep_counts) {
+                           int32_t* keep, int32_t* keep_counts, int use_in_vis_thre, double in_vis_thre) {
   RSG_REQUIRE(n_imgs >= 0 && K > 0 && K <= RSG_NMS_MAXK, "rsg_oks_nms: bad n_imgs=%d or K=%d", n_imgs, K);
   if (n_imgs == 0) return RSG_OK;
   RSG_REQUIRE(kpts && scores && areas && img_offsets && sigmas && keep && keep_counts,
@@ -205,15 +209,16 @@ extern "C" int rsg_oks_nms(void* stream, const float* kpts, const double* scores
   RSG_REQUIRE(smem <= 200 * 1024, "rsg_oks_nms: more than %d detections in one image", 25600);
   if (smem > 48 * 1024)
     RSG_CUDA(cudaFuncSetAttribute(oks_nms_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  oks_nms_kernel<<<n_imgs, 128, smem, (cudaStream_t)stream>>>(kpts, scores, areas, img_offsets,
-                                                             sigmas, K, thresh, keep, keep_counts);
+  oks_nms_kernel<<<n_imgs, 128, smem, (cudaStream_t)stream>>>(kpts, scores, areas, img_offsets, sigmas, K, thresh,
+                                                             use_in_vis_thre ? 1 : 0, (float)in_vis_thre, keep, keep_counts);
   RSG_LAUNCH_CHECK();
   return RSG_OK;
 }
 
 extern "C" int rsg_soft_oks_nms(void* stream, const float* kpts, const double* scores, const double* areas,
                                 const int32_t* img_offsets, int n_imgs, int max_per_img, const double* sigmas, int K,
-                                double thresh, int max_dets, int32_t* keep, int32_t* keep_counts) {
+                                double thresh, int max_dets, int32_t* keep, int32_t* keep_counts, int use_in_vis_thre,
+                                double in_vis_thre) {
   RSG_REQUIRE(n_imgs >= 0 && K > 0 && K <= RSG_NMS_MAXK, "rsg_soft_oks_nms: bad n_imgs=%d or K=%d", n_imgs, K);
   RSG_REQUIRE(max_dets >= 1, "rsg_soft_oks_nms: max_dets=%d", max_dets);
   if (n_imgs == 0) return RSG_OK;
@@ -224,17 +229,19 @@ extern "C" int rsg_soft_oks_nms(void* stream, const float* kpts, const double* s
   if (smem > 48 * 1024)
     RSG_CUDA(cudaFuncSetAttribute(soft_oks_nms_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   soft_oks_nms_kernel<<<n_imgs, 128, smem, (cudaStream_t)stream>>>(kpts, scores, areas, img_offsets, sigmas, K, thresh,
-                                                                  max_dets, keep, keep_counts);
+                                                                  max_dets, use_in_vis_thre ? 1 : 0, (float)in_vis_thre,
+                                                                  keep, keep_counts);
   RSG_LAUNCH_CHECK();
   return RSG_OK;
 }
 
 extern "C" int rsg_oks_iou(void* stream, const float* g, const float* d, double a_g, const double* a_d,
-                           const double* sigmas, int K, int M, double* out) {
+                           const double* sigmas, int K, int M, double* out, int use_in_vis_thre, double in_vis_thre) {
   RSG_REQUIRE(K > 0 && K <= RSG_NMS_MAXK && M >= 0, "rsg_oks_iou: bad K=%d or M=%d", K, M);
   if (M == 0) return RSG_OK;
   RSG_REQUIRE(g && d && a_d && sigmas && out, "rsg_oks_iou: null pointer");
-  oks_iou_kernel<<<ceil_div(M, 128), 128, 0, (cudaStream_t)stream>>>(g, d, a_g, a_d, sigmas, K, M, out);
+  oks_iou_kernel<<<ceil_div(M, 128), 128, 0, (cudaStream_t)stream>>>(g, d, a_g, a_d, sigmas, K, M, use_in_vis_thre ? 1 : 0,
+                                                                     (float)in_vis_thre, out);
   RSG_LAUNCH_CHECK();
   return RSG_OK;
 }

@@ -20,7 +20,12 @@ def _p(t):
     return C.c_void_p(t.data_ptr())
 
 
-def oks_nms_batched(kpts, scores, areas, img_offsets, thresh, sigmas=None, device=None):
+def _vis(in_vis_thre):
+    """(use_in_vis_thre, in_vis_thre) of the C ABI for the reference's `in_vis_thre=None | float`."""
+    return (0, 0.0) if in_vis_thre is None else (1, float(in_vis_thre))
+
+
+def oks_nms_batched(kpts, scores, areas, img_offsets, thresh, sigmas=None, device=None, in_vis_thre=None):
     """kpts f32 [n,K,3]; scores, areas f64 [n]; img_offsets i32 [n_imgs+1] (NumPy or CUDA tensors).
     Returns (keep i32 [n] -- per image, at keep[off[i]:off[i]+count[i]], indices relative to the
     image in selection order --, counts i32 [n_imgs]) as NumPy arrays."""
@@ -50,14 +55,12 @@ def oks_nms_batched(kpts, scores, areas, img_offsets, thresh, sigmas=None, devic
     with torch.cuda.device(device):
         _lib.check(_lib.lib().rsg_oks_nms(_lib.stream_ptr(device), _p(k), _p(s), _p(a), _p(off),
                                           n_imgs, max_per, _p(sg), K, float(thresh), _p(keep),
-                                          _p(counts)))
+                                          _p(counts), *_vis(in_vis_thre)))
     return keep[:n].cpu().numpy(), counts.cpu().numpy()
 
 
 def oks_iou(g, d, a_g, a_d, sigmas=None, in_vis_thre=None):
     """nms.py:75-94: OKS of detection g (f32 [3K]) with each row of d (f32 [M,3K]); returns f64 [M]."""
-    if in_vis_thre is not None:
-        raise NotImplementedError('oks_iou(in_vis_thre=...) is not supported (no reference caller uses it)')
     _lib.require_cuda()
     if not isinstance(sigmas, np.ndarray):
         sigmas = COCO_SIGMAS
@@ -69,23 +72,22 @@ def oks_iou(g, d, a_g, a_d, sigmas=None, in_vis_thre=None):
     K, M = gt.numel() // 3, dt.shape[0]
     assert len(sigmas) == K
     out = torch.zeros(M, dtype=torch.float64, device=dev)
-    _lib.check(_lib.lib().rsg_oks_iou(_lib.stream_ptr(dev), _p(gt), _p(dt), float(a_g), _p(at), _p(sg), K, M, _p(out)))
+    _lib.check(_lib.lib().rsg_oks_iou(_lib.stream_ptr(dev), _p(gt), _p(dt), float(a_g), _p(at), _p(sg), K, M, _p(out),
+                                      *_vis(in_vis_thre)))
     return out.cpu().numpy()
 
 
 def oks_nms(kpts_db, thresh, sigmas=None, in_vis_thre=None):
-    """nms.py:97-124.  `in_vis_thre` is never passed by any caller of the reference
-    (crowdpose.py:1315, coco.py:1269); a non-None value is rejected rather than guessed at."""
+    """nms.py:97-124.  `in_vis_thre` (never passed by the reference's own callers, crowdpose.py:1315, coco.py:1269)
+    follows the reference's oks_iou: only the compared detection's key points with score > in_vis_thre count."""
     if len(kpts_db) == 0:
         return []
-    if in_vis_thre is not None:
-        raise NotImplementedError('oks_nms(in_vis_thre=...) is not supported (no reference caller uses it)')
     scores = np.array([kpts_db[i]['score'] for i in range(len(kpts_db))], np.float64)
     kpts = np.array([np.asarray(kpts_db[i]['keypoints'], np.float32).reshape(-1, 3)
                      for i in range(len(kpts_db))], np.float32)
     areas = np.array([kpts_db[i]['area'] for i in range(len(kpts_db))], np.float64)
     keep, counts = oks_nms_batched(kpts, scores, areas, np.array([0, len(kpts_db)], np.int32),
-                                   thresh, sigmas)
+                                   thresh, sigmas, in_vis_thre=in_vis_thre)
     return [int(v) for v in keep[:int(counts[0])]]
 
 
@@ -105,7 +107,7 @@ def rescore(maxvals, box_scores, in_vis_thre, device=None):
     return out.cpu().numpy()
 
 
-def soft_oks_nms_batched(kpts, scores, areas, img_offsets, thresh, sigmas=None, max_dets=20, device=None):
+def soft_oks_nms_batched(kpts, scores, areas, img_offsets, thresh, sigmas=None, max_dets=20, device=None, in_vis_thre=None):
     """Segmented soft OKS-NMS (nms.py:138-180 for all images of an evaluate() call): returns (keep i32 [n_imgs, max_dets]
     -- indices relative to the image, in selection order --, counts i32 [n_imgs]) as NumPy arrays."""
     _lib.require_cuda()
@@ -128,7 +130,8 @@ def soft_oks_nms_batched(kpts, scores, areas, img_offsets, thresh, sigmas=None, 
     counts = torch.zeros(n_imgs, dtype=torch.int32, device=device)
     with torch.cuda.device(device):
         _lib.check(_lib.lib().rsg_soft_oks_nms(_lib.stream_ptr(device), _p(k), _p(s), _p(a), _p(off), n_imgs, max_per,
-                                               _p(sg), K, float(thresh), int(max_dets), _p(keep), _p(counts)))
+                                               _p(sg), K, float(thresh), int(max_dets), _p(keep), _p(counts),
+                                               *_vis(in_vis_thre)))
     return keep.cpu().numpy(), counts.cpu().numpy()
 
 
@@ -137,11 +140,10 @@ def soft_oks_nms(kpts_db, thresh, sigmas=None, in_vis_thre=None):
     exp(-oks^2 / thresh).  Returns an integer array of indices like the reference (``keep[:keep_cnt]``)."""
     if len(kpts_db) == 0:
         return []
-    if in_vis_thre is not None:
-        raise NotImplementedError('soft_oks_nms(in_vis_thre=...) is not supported (no reference caller uses it)')
     scores = np.array([kpts_db[i]['score'] for i in range(len(kpts_db))], np.float64)
     kpts = np.array([np.asarray(kpts_db[i]['keypoints'], np.float32).reshape(-1, 3)
                      for i in range(len(kpts_db))], np.float32)
     areas = np.array([kpts_db[i]['area'] for i in range(len(kpts_db))], np.float64)
-    keep, counts = soft_oks_nms_batched(kpts, scores, areas, np.array([0, len(kpts_db)], np.int32), thresh, sigmas)
+    keep, counts = soft_oks_nms_batched(kpts, scores, areas, np.array([0, len(kpts_db)], np.int32), thresh, sigmas,
+                                        in_vis_thre=in_vis_thre)
     return keep[0, :int(counts[0])].astype(np.intp)

@@ -36,10 +36,10 @@ def test_argument_errors_are_reported_without_a_device():
     L = _lib.lib()
     rc = L.rsg_flip_avg_decode(None, None, None, None, 4, 17, 0, 48, None, None, 1, 1, None, None, None, None)
     assert rc != 0 and b'bad shape' in L.rsg_last_error()
-    rc = L.rsg_oks_nms(None, None, None, None, None, 3, 5, None, 99, 0.9, None, None)
+    rc = L.rsg_oks_nms(None, None, None, None, None, 3, 5, None, 99, 0.9, None, None, 0, 0.0)
     assert rc != 0 and b'K=99' in L.rsg_last_error()
     # empty inputs are a no-op, like the reference's `if len(kpts_db) == 0: return []`
-    assert L.rsg_oks_nms(None, None, None, None, None, 0, 0, None, 17, 0.9, None, None) == 0
+    assert L.rsg_oks_nms(None, None, None, None, None, 0, 0, None, 17, 0.9, None, None, 0, 0.0) == 0
     assert L.rsg_flip_avg_decode(None, None, None, None, 0, 17, 64, 48, None, None, 1, 1, None, None, None, None) == 0
 
 

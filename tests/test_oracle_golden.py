@@ -85,6 +85,17 @@ def test_nms_oracle_vs_reference(golden_dir, tag):
         pos += c
     db = [dict(keypoints=kb[j], score=sb[j], area=ab[j]) for j in range(len(sb))]
     assert list(nms_oracle.soft_oks_nms(db, 0.5, sig)) == list(g['soft_big_keep'])
+    # in_vis_thre = 0.4 (nms.py:85-90)
+    flat = kb.reshape(len(sb), -1)
+    assert np.array_equal(nms_oracle.oks_iou(flat[0], flat[1:], ab[0], ab[1:], sig, 0.4), g['vis_oks'])
+    pos = 0
+    for i in range(40):
+        db = [dict(keypoints=kpts[j], score=scores[j], area=areas[j]) for j in range(off[i], off[i + 1])]
+        c = int(g['vis_counts'][i])
+        assert [int(v) for v in nms_oracle.oks_nms(db, 0.9, sig, 0.4)] == list(g['vis_keep'][pos:pos + c])
+        pos += c
+    db = [dict(keypoints=kb[j], score=sb[j], area=ab[j]) for j in range(len(sb))]
+    assert list(nms_oracle.soft_oks_nms(db, 0.5, sig, 0.4)) == list(g['vis_soft_big_keep'])
 
 
 @pytest.mark.parametrize('key', MODEL_CASES)

@@ -181,3 +181,28 @@ def test_soft_oks_nms_vs_reference(golden_dir, tag):
     assert got.dtype == np.intp and list(got) == list(g['soft_big_keep']) and len(got) == 20
     assert list(got) == list(nms_oracle.soft_oks_nms(db, 0.5, sig))
     assert soft_oks_nms([], 0.9) == []
+
+
+@pytest.mark.parametrize('tag', ['coco', 'crowdpose'])
+def test_in_vis_thre_vs_reference(golden_dir, tag):
+    """in_vis_thre (nms.py:85-90, the reference's `list(a) and list(b)` = the compared detection's visible key points):
+    oks_iou within 1 ulp of the reference (device exp), keep lists of oks_nms / soft_oks_nms identical."""
+    g = _load(golden_dir, f'nms_{tag}.npz')
+    k = int(g['k'])
+    sig = None if tag == 'coco' else nms_oracle.CROWDPOSE_SIGMAS
+    kb, sb, ab, _ = synth.detections(1, int(g['big_n']), k, seed=int(g['big_seed']))
+    flat = kb.reshape(len(sb), -1)
+    got = oks_iou(flat[0], flat[1:], ab[0], ab[1:], sig, 0.4)
+    assert np.allclose(got, g['vis_oks'], rtol=4e-16, atol=1e-300)
+    assert not np.array_equal(g['vis_oks'], nms_oracle.oks_iou(flat[0], flat[1:], ab[0], ab[1:], sig))   # the mask matters
+    kpts, scores, areas, off = synth.detections(int(g['n_imgs']), int(g['per_img']), k, seed=int(g['seed']), ragged=True)
+    keep, counts = oks_nms_batched(kpts[:off[40]], scores[:off[40]], areas[:off[40]], off[:41], 0.9, sig, in_vis_thre=0.4)
+    assert list(counts) == list(g['vis_counts'])
+    pos = 0
+    for i in range(40):
+        c = int(counts[i])
+        assert list(keep[off[i]:off[i] + c]) == list(g['vis_keep'][pos:pos + c]), i
+        pos += c
+    db = [dict(keypoints=kb[j], score=sb[j], area=ab[j]) for j in range(len(sb))]
+    assert list(soft_oks_nms(db, 0.5, sig, 0.4)) == list(g['vis_soft_big_keep'])
+    assert oks_nms(db, 0.9, sig, in_vis_thre=0.4) == [int(v) for v in nms_oracle.oks_nms(db, 0.9, sig, 0.4)]
