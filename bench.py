@@ -41,6 +41,8 @@ WORKLOAD = 'RSGNet-W32 256x192 CrowdPose K=14 flip-test inference (BASELINE.json
 METRIC = 'crops/sec RSGNet-W32 256x192 flip-test inference'
 # --workload: preset -> (workload description, metric)
 WORKLOADS = {
+    'postproc': ('post-processing only: get_final_preds decode + evaluate (rescoring, grouping, oks_nms) on 100k synthetic '
+                 'detections x 17 heat-maps at 64x48 (BASELINE.json configs[3])', 'crops/sec get_final_preds decode 17x64x48'),
     'w32_crowdpose': (WORKLOAD, METRIC),
     'w48_coco_384': ('RSGNet-W48 384x288 COCO K=17 flip-test inference (BASELINE.json configs[2])',
                      'crops/sec RSGNet-W48 384x288 flip-test inference'),
@@ -115,12 +117,43 @@ def cpu_reference_step(sd, cfg, x, c, s):
     return decode_oracle.get_final_preds(True, avg, c, s)
 
 
+def gpu_eager_baseline(sd, cfg, x_host, dev, n=64):
+    """The reference graph (oracle/model_oracle.py, plain torch ops) on the GPU: what `tools/cp_test.py` would run on
+    this box with stock PyTorch.  Bench leg only."""
+    from oracle import model_oracle
+    sd_dev = {k: v.to(dev) for k, v in sd.items()}
+    x = x_host[:n].to(dev)
+    res = {}
+    for tag, ctx in (('fp32', torch.autocast('cuda', enabled=False)), ('bf16_autocast', torch.autocast('cuda', dtype=torch.bfloat16))):
+        try:
+            with torch.no_grad(), ctx:
+                for _ in range(2):
+                    model_oracle.forward(sd_dev, cfg, x)
+                    model_oracle.forward(sd_dev, cfg, x.flip(3))
+                torch.cuda.synchronize()
+                e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                e0.record()
+                reps = 3
+                for _ in range(reps):
+                    model_oracle.forward(sd_dev, cfg, x)
+                    model_oracle.forward(sd_dev, cfg, x.flip(3))
+                e1.record()
+                torch.cuda.synchronize()
+            res[tag] = {'crops_per_s': n * reps / (e0.elapsed_time(e1) * 1e-3), 'batch': n}
+        except Exception as e:            # informational leg: never fails the bench
+            res[tag] = {'error': str(e)[:200]}
+    res['what'] = 'reference op graph, eager PyTorch (cuDNN/cuBLAS) on this GPU, 2 forwards per crop, no decode'
+    return res
+
+
 def run_reference(args):
     """--impl reference: the reference's own CPU implementation of the path (oracle port), all host
-    threads, bounded sample per step."""
+    threads, on our arm's workload, a bounded sample (--cpu-sample crops) per step."""
     rank = int(os.environ.get('RANK', '0'))
     if rank != 0:
         return
+    if PRESET == 'postproc':
+        return run_postproc_reference(args)
     cores = len(os.sched_getaffinity(0))
     torch.set_num_threads(cores)
     cfg = presets.preset(PRESET)
@@ -141,7 +174,8 @@ def run_reference(args):
         'impl': 'reference', 'metric': METRIC, 'value': val, 'unit': 'crops/s', 'n_gpus': args.gpus,
         'steps': args.steps, 'warmup': args.warmup, 'ms_per_step': dt / args.steps * 1e3,
         'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f32',
-        'data': 'synthetic', 'config': {'workload': WORKLOAD, 'crops_per_step': n},
+        'data': 'synthetic', 'config': {'workload': WORKLOAD, 'crops_per_step': n, 'forwards_per_crop': 2,
+                                        'sample': 'bounded: %d of the 256 crops per GPU per step of the workload' % n},
         'cpu_baseline': {'value': val, 'unit': 'crops/s', 'cores': cores, 'kind': 'port', 'sample': sample},
         'e2e': {'value': val, 'unit': 'crops/s', 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0},
         'gpu_launches': 0}))
@@ -159,6 +193,209 @@ FAMILY = {0: 'stem', 1: 'conv_mma', 2: 'conv_tcgen05', 3: 'fuse', 4: 'maxpool', 
           11: 'bottleneck_tcgen05'}
 
 
+# ---------------------------------------------------------------------------------------------
+# BASELINE.json configs[3]: post-processing only
+# ---------------------------------------------------------------------------------------------
+POST_K, POST_H, POST_W = 17, 64, 48
+
+
+def _post_heatmaps(n, device):
+    """SURVEY.md §8d config 4 on the device (20.9 GB for n = 100 k): Gaussian bump (sigma 2, centre anywhere incl. the
+    borders, amplitude U(0.1, 1)) + N(0, 0.01) noise, 15 % of the maps shifted by -2 so that their max <= 0."""
+    g = torch.Generator(device=device).manual_seed(2)
+    hm = torch.empty((n, POST_K, POST_H, POST_W), device=device)
+    ys = torch.arange(POST_H, device=device).view(1, 1, POST_H, 1).float()
+    xs = torch.arange(POST_W, device=device).view(1, 1, 1, POST_W).float()
+    for lo in range(0, n, 4000):
+        m = min(4000, n - lo)
+        r = lambda: torch.rand((m, POST_K, 1, 1), device=device, generator=g)
+        cx, cy, amp = r() * (POST_W + 1) - 1, r() * (POST_H + 1) - 1, r() * 0.9 + 0.1
+        t = amp * torch.exp(-((xs - cx) ** 2 + (ys - cy) ** 2) / 8.0)
+        t += 0.01 * torch.randn((m, POST_K, POST_H, POST_W), device=device, generator=g)
+        hm[lo:lo + m] = torch.where(r() < 0.15, t - 2.0, t)
+    return hm
+
+
+def _post_cpu(n_crops, n_imgs, hm_np, c_np, s_np, ev):
+    """The reference's CPU post-processing (oracle port) on a bounded slice: get_final_preds on n_crops maps and
+    evaluate() (rescoring + grouping + oks_nms) on n_imgs images.  Returns (crops/s, dets/s, results)."""
+    from oracle import decode_oracle, nms_oracle
+    t0 = time.perf_counter()
+    preds, mv = decode_oracle.get_final_preds(True, hm_np[:n_crops], c_np[:n_crops], s_np[:n_crops])
+    t_dec = time.perf_counter() - t0
+    p, b, ids = ev
+    sel = ids < (100000 + 7 * n_imgs)
+    t0 = time.perf_counter()
+    res = nms_oracle.evaluate(p[sel], b[sel], ids[sel], None, 0.2, 0.9)
+    t_nms = time.perf_counter() - t0
+    return n_crops / t_dec, int(sel.sum()) / t_nms, (preds, mv, res, np.nonzero(sel)[0])
+
+
+def run_postproc_reference(args):
+    cores = len(os.sched_getaffinity(0))
+    n_crops, n_imgs = 2048, 500
+    hm = _post_heatmaps_host(n_crops)
+    c, sc = synth.centers_scales(n_crops, seed=5)
+    ev = synth.evaluate_inputs(5000, 20, POST_K, seed=31, ragged=False)
+    vals = []
+    for i in range(args.warmup + args.steps):
+        t0 = time.perf_counter()
+        cps, dps, _ = _post_cpu(n_crops, n_imgs, hm, c, sc, ev)
+        if i >= args.warmup:
+            vals.append((cps, dps, time.perf_counter() - t0))
+    val = float(np.mean([v[0] for v in vals]))
+    sample = f'{n_crops} of 100000 crops decoded + {n_imgs} of 5000 images through evaluate() per step, NumPy (single thread)'
+    print(json.dumps({
+        'impl': 'reference', 'metric': METRIC, 'value': val, 'unit': 'crops/s', 'n_gpus': args.gpus, 'steps': args.steps,
+        'warmup': args.warmup, 'ms_per_step': float(np.mean([v[2] for v in vals])) * 1e3, 'higher_is_better': True,
+        'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f32', 'data': 'synthetic', 'config': {'workload': WORKLOAD, 'sample': sample},
+        'nms_dets_per_s': float(np.mean([v[1] for v in vals])),
+        'cpu_baseline': {'value': val, 'unit': 'crops/s', 'cores': 1, 'kind': 'port', 'sample': sample, 'host_cores': cores},
+        'e2e': {'value': val, 'unit': 'crops/s', 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0}, 'gpu_launches': 0}))
+
+
+def _post_heatmaps_host(n):
+    return synth.heatmaps(n, POST_K, POST_H, POST_W, seed=2)
+
+
+def run_postproc(args):
+    """`--workload postproc`: decode of N x 17 x 64x48 heat-maps against the HBM roof + evaluate_device dets/s."""
+    from rsgnet_b200.core.inference import decode_device, get_final_preds
+    from rsgnet_b200.nms.nms import evaluate_device
+    world = int(os.environ.get('WORLD_SIZE', '1'))
+    rank = int(os.environ.get('RANK', '0'))
+    local = int(os.environ.get('LOCAL_RANK', '0'))
+    torch.cuda.set_device(local)
+    dev = torch.device('cuda', local)
+    dist = None
+    if world > 1:
+        import torch.distributed as dist
+        sys.stdout.flush()
+        saved_fd = os.dup(1)
+        os.dup2(2, 1)
+        try:
+            dist.init_process_group('nccl', device_id=dev)
+            dist.barrier()
+            torch.cuda.synchronize()
+        finally:
+            sys.stdout.flush()
+            os.dup2(saved_fd, 1)
+            os.close(saved_fd)
+    N = args.batch if args.batch != 256 else 100000          # detections per GPU per step
+    pk = peaks()
+    hm = _post_heatmaps(N, dev)
+    c_np, s_np = synth.centers_scales(N, seed=5 + rank)
+    c, sc = torch.from_numpy(c_np).to(dev), torch.from_numpy(s_np).to(dev)
+    n_imgs = N // 20
+    ev_np = synth.evaluate_inputs(n_imgs, 20, POST_K, seed=31 + rank, ragged=False)
+    ev = (torch.from_numpy(ev_np[0]).to(dev), torch.from_numpy(ev_np[1]).to(dev), torch.from_numpy(ev_np[2]).to(dev))
+    stream = torch.cuda.Stream(dev)
+
+    def barrier():
+        if dist is not None:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def timed(fn, steps, sample=False):
+        barrier()
+        sampler = ClockSampler(local).start() if sample else None
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        with torch.cuda.stream(stream):
+            e0.record(stream)
+            for _ in range(steps):
+                fn()
+            e1.record(stream)
+        barrier()
+        ms = e0.elapsed_time(e1)
+        clocks = sampler.stop() if sampler else None
+        if dist is not None:
+            t = torch.tensor([ms], device=dev)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            ms = float(t.item())
+        return ms, clocks
+
+    out = {}
+
+    def step():                      # the hot path of configs[3]: decode + evaluate, device-resident
+        out['d'] = decode_device(hm, c, sc, post_process=True)
+        out['e'] = evaluate_device(ev[0], ev[1], ev[2], 0.9, 0.2)
+
+    def step_decode():
+        out['d'] = decode_device(hm, c, sc, post_process=True)
+
+    def step_eval():
+        out['e'] = evaluate_device(ev[0], ev[1], ev[2], 0.9, 0.2)
+
+    with torch.cuda.stream(stream):
+        for _ in range(args.warmup):
+            step()
+    ms_all, clocks = timed(step, args.steps, sample=(rank == 0))
+    ms_dec, _ = timed(step_decode, args.steps)
+    ms_ev, _ = timed(step_eval, args.steps)
+    # e2e: the reference-facing call with HOST buffers (get_final_preds(config, ndarray, center, scale)) on a slice
+    n_e2e = min(N, 8192)
+    cfg = presets.make_cfg(post_process=True)
+    hm_host = hm[:n_e2e].cpu().numpy()
+    get_final_preds(cfg, hm_host, c_np[:n_e2e], s_np[:n_e2e])
+    barrier()
+    t0 = time.perf_counter()
+    reps = 3
+    for _ in range(reps):
+        p_host, mv_host = get_final_preds(cfg, hm_host, c_np[:n_e2e], s_np[:n_e2e])
+    torch.cuda.synchronize()
+    t_e2e = (time.perf_counter() - t0) / reps
+    if dist is not None:
+        t = torch.tensor([t_e2e], device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        t_e2e = float(t.item())
+    if rank != 0:
+        if dist is not None:
+            dist.destroy_process_group()
+        return
+    byt = N * POST_K * POST_H * POST_W * 4 + N * POST_K * 12
+    per_ms = ms_dec / args.steps
+    gbs = byt / per_ms / 1e6
+    # parity of what was timed + CPU leg (bounded slice)
+    cpu = None
+    parity = None
+    if not args.no_cpu_baseline:
+        n_c, n_i = 2048, 500
+        cps, dps, (o_preds, o_mv, o_ev, sel) = _post_cpu(n_c, n_i, hm[:n_c].cpu().numpy(), c_np, s_np, ev_np)
+        d = out['d']
+        dec_ok = bool(np.array_equal(d['preds'][:n_c].cpu().numpy(), o_preds) and np.array_equal(d['maxvals'][:n_c].cpu().numpy(), o_mv))
+        sub = evaluate_device(ev_np[0][sel], ev_np[1][sel], ev_np[2][sel], 0.9, 0.2).host()
+        ev_ok = bool(np.array_equal(sub['images'], o_ev[0]) and np.array_equal(sub['counts'], o_ev[1]) and
+                     np.array_equal(sub['keep'], o_ev[2]) and np.array_equal(sub['scores'][sub['keep']], o_ev[3]))
+        parity = {'decode_bit_exact_vs_oracle': dec_ok, 'evaluate_keep_lists_equal_oracle': ev_ok,
+                  'sample': f'{n_c} crops, {n_i} images'}
+        if not (dec_ok and ev_ok):
+            raise SystemExit(f'bench: post-processing parity check failed: {parity}')
+        cpu = {'value': cps, 'unit': 'crops/s', 'cores': 1, 'kind': 'port', 'nms_dets_per_s': dps,
+               'sample': f'get_final_preds on {n_c} of {N} crops, evaluate() on {n_i} of {n_imgs} images (oracle port, NumPy)'}
+    line = {
+        'metric': METRIC, 'value': N * world * args.steps / (ms_dec * 1e-3), 'unit': 'crops/s', 'n_gpus': world,
+        'steps': args.steps, 'warmup': args.warmup, 'ms_per_step': per_ms, 'higher_is_better': True, 'scaling': 'weak',
+        'vs_baseline': None, 'dtype': 'f32', 'data': 'synthetic',
+        'config': {'workload': WORKLOAD, 'detections_per_gpu_per_step': N, 'K': POST_K, 'heatmap': [POST_H, POST_W],
+                   'images': n_imgs, 'l2': 'input (20.9 GB at 100k) exceeds the 126 MB L2; no explicit flush'},
+        'clocks': clocks, 'gpu_launches': 6 * args.steps,
+        'decode_plus_evaluate': {'ms_per_step': ms_all / args.steps, 'detections_per_s': N * world * args.steps / (ms_all * 1e-3)},
+        'evaluate_device': {'ms_per_step': ms_ev / args.steps, 'dets_per_s': N * world * args.steps / (ms_ev * 1e-3),
+                            'bound': 'latency (22 MB per 100 k detections): no roofline claimed'},
+        'e2e': {'value': n_e2e * world / t_e2e, 'unit': 'crops/s', 'h2d_bytes_per_step': int(hm_host.nbytes + 16 * n_e2e),
+                'd2h_bytes_per_step': int(p_host.nbytes + mv_host.nbytes), 'sample': f'{n_e2e} crops per call through '
+                'core.inference.get_final_preds(config, ndarray, center, scale) with pageable NumPy buffers, as the reference loop calls it'},
+        'roofline': {'bound': 'hbm', 'kernel': f'decode_kernel: {N} x {POST_K} maps of {POST_H}x{POST_W} f32', 'achieved': gbs,
+                     'peak': pk['hbm'], 'unit': 'GB/s', 'frac': gbs / pk['hbm'], 'traffic': None,
+                     'peak_source': pk['src'] + ' hbm_gbs', 'algorithmic_bytes_per_launch': byt, 'us_per_launch': per_ms * 1e3},
+        'parity_checked': bool(parity), 'parity': parity, 'cpu_baseline': cpu,
+    }
+    print(json.dumps(line))
+    if dist is not None:
+        dist.destroy_process_group()
+
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument('--gpus', type=int, default=1)
@@ -167,10 +404,13 @@ def main():
     ap.add_argument('--impl', default='ours')
     ap.add_argument('--batch', type=int, default=256, help='crops per GPU per step')
     ap.add_argument('--chunk', type=int, default=0, help='forwards per plan pass (0 = model default)')
-    ap.add_argument('--cpu-sample', type=int, default=4, help='crops per CPU-baseline step')
+    ap.add_argument('--cpu-sample', type=int, default=32, help='crops per step of the CPU arms (bounded sample of the workload)')
     ap.add_argument('--no-graph', action='store_true')
     ap.add_argument('--no-cpu-baseline', action='store_true')
     ap.add_argument('--dump-profile', default='')
+    ap.add_argument('--sustained-steps', type=int, default=150, help='extra timed run of this many steps (0 = skip)')
+    ap.add_argument('--gpu-eager-baseline', action='store_true',
+                    help='also time the reference op graph eagerly on the GPU through PyTorch (informational)')
     ap.add_argument('--workload', default='w32_crowdpose', choices=sorted(WORKLOADS),
                     help='default = the headline configuration (BASELINE.json configs[1]); w48_coco_384 = configs[2], '
                          'a secondary measurement (use --batch 128)')
@@ -182,6 +422,8 @@ def main():
         args.warmup = 3
     if args.impl == 'reference':
         return run_reference(args)
+    if PRESET == 'postproc':
+        return run_postproc(args)
 
     from rsgnet_b200.pipeline import CropPipeline
     world = int(os.environ.get('WORLD_SIZE', '1'))
@@ -321,6 +563,18 @@ def main():
                 'families': {k: {'ms': round(v[0], 4), 'tflops': (v[1] / (v[0] * 1e-3) / 1e12 if v[0] > 0 else 0.0),
                                  'gbs_algorithmic': (v[3] / (v[0] * 1e-3) / 1e9 if v[0] > 0 else 0.0),
                                  'launches': v[2], 'share': round(v[0] / total_ms, 4)} for k, v in fam.items()}}
+    # operand-fetch ceiling of the tensor pipe for this kernel's MMA shape (measured, tools/umma_rate.cu, profiles/r1_notes.md §1):
+    # an M=128, K=16 MMA with N output columns needs N/2 cycles of math but (4096 + 32 N) / 128 cycles of shared-memory
+    # operand fetch, so thin layers cannot exceed (N/2) / (32 + N/4) of the dense peak whatever the kernel does
+    import re
+    mm = re.search(r'->(\d+)', dom_shape)
+    n_cols = int(mm.group(1)) if mm else int(pipe.spec.head_channels)
+    n_cols = min(n_cols, 256)
+    cap = min(1.0, (n_cols / 2.0) / (32.0 + n_cols / 4.0))
+    roofline['ceiling'] = {'frac': cap, 'mma_n': n_cols, 'frac_of_ceiling': (tf / pk['tf_sus']) / cap if cap else None,
+                           'why': 'shared-memory operand fetch of an M=128 K=16 MMA: (4096 + 32 N) / 128 cycles vs N / 2 cycles of math'}
+    roofline['traffic_source'] = ('constant from the committed ncu --set full capture under profiles/ (not measured in this run)'
+                                  if traffic else None)
     if args.dump_profile:
         with open(args.dump_profile, 'w') as f:
             for m, k, fl, nm, sh in zip(ms_op, kind, flops, names, shapes):
@@ -333,21 +587,57 @@ def main():
     d2h = preds_host.numel() * 4 + mv_host.numel() * 4
     exec_tflops = value * 2 * eng.flops_per_fwd / 1e12 / world
 
-    cpu = None
+    # ---- parity of what was just timed: the first crops of the last step against the CPU oracle (fp32 reference port)
+    parity = None
     if not args.no_cpu_baseline:
         cores = len(os.sched_getaffinity(0))
         torch.set_num_threads(cores)
-        n = args.cpu_sample
-        xs = x_host[:n].clone()
-        cpu_reference_step(sd, cfg, xs, c_np[:n], s_np[:n])        # warm
-        t0 = time.perf_counter()
-        reps = 2
-        for _ in range(reps):
-            cpu_reference_step(sd, cfg, xs, c_np[:n], s_np[:n])
-        dt = (time.perf_counter() - t0) / reps
-        cpu = {'value': n / dt, 'unit': 'crops/s', 'cores': cores, 'kind': 'port',
-               'sample': f'{n} crops x {reps} reps (flip-test: 2 fp32 forwards/crop + flip-average + decode), '
-                         'oracle port of the reference torch/NumPy path'}
+        n = 4
+        o_preds, o_mv = cpu_reference_step(sd, cfg, x_host[:n].clone(), c_np[:n], s_np[:n])
+        g_preds, g_mv = preds_host[:n].numpy(), mv_host[:n].numpy()
+        # image px -> heat-map px: transform_preds scales by scale[0] * 200 / heat_w on both axes (transforms.py:57-103)
+        px = (s_np[:n, 0] * 200.0 / float(pipe.spec.heat_w))[:, None]
+        disp = np.hypot(g_preds[..., 0] - o_preds[..., 0], g_preds[..., 1] - o_preds[..., 1]) / px
+        mv_err = float(np.abs(g_mv - o_mv).max() / max(float(np.abs(o_mv).max()), 1e-12))
+        parity = {'crops': n, 'maxvals_rel_err': mv_err, 'kpt_disp_le_1px': float((disp <= 1.0).mean()),
+                  'kpt_disp_le_2px': float((disp <= 2.0).mean()), 'kpt_disp_max_px': float(disp.max()),
+                  'bar': 'bf16 pipeline vs fp32 oracle: maxvals within 0.05 * max, >= 90 % of the key points within 2 heat-map px '
+                         '(decode itself is bit-exact given identical heat-maps: tests/test_postproc_gpu.py)'}
+        if not (mv_err <= 0.05 and parity['kpt_disp_le_2px'] >= 0.9):
+            raise SystemExit(f'bench: parity check of the timed outputs failed: {parity}')
+
+    # ---- CPU baseline: BASELINE.json configs[0] (RSGNet-W32 256x192 COCO K=17, batch 32, the reference's CPU path)
+    cpu = None
+    if not args.no_cpu_baseline:
+        cfg0 = presets.preset('w32_coco')
+        net0 = pose_rsgnet.get_pose_net(cfg0, False)
+        sd0 = _params.synth_state_dict(net0, seed=3)
+        n0 = args.cpu_sample
+        x0 = torch.from_numpy(synth.crops(n0, cfg0.MODEL.IMAGE_SIZE, seed=0))
+        c0, s0 = synth.centers_scales(n0, seed=0)
+        cpu_reference_step(sd0, cfg0, x0[:2], c0[:2], s0[:2])        # warm (thread pool, oneDNN primitives)
+        ts = []
+        for _ in range(3):
+            t0 = time.perf_counter()
+            cpu_reference_step(sd0, cfg0, x0, c0, s0)
+            ts.append(time.perf_counter() - t0)
+        dt = float(np.median(ts))
+        cpu = {'value': n0 / dt, 'unit': 'crops/s', 'cores': cores, 'kind': 'port',
+               'sample': f'BASELINE.json configs[0]: RSGNet-W32 256x192 COCO K=17, batch {n0}, flip test (2 fp32 forwards/crop + '
+                         f'flip-average + get_final_preds), median of 3 reps, oracle port of the reference torch/NumPy path'}
+
+    # ---- sustained figure: the same step for >= 2.5 s (the power cap settles after ~1 s)
+    sustained = None
+    if args.sustained_steps > 0 and world == 1:
+        ms_sus, clocks_sus = timed(step_device, args.sustained_steps, sample_clocks=True)
+        sustained = {'steps': args.sustained_steps, 'ms_per_step': ms_sus / args.sustained_steps,
+                     'value': crops_per_step * args.sustained_steps / (ms_sus * 1e-3), 'clocks': clocks_sus}
+
+    # ---- informational: the reference's op graph run EAGERLY on this GPU by PyTorch (cuDNN / cuBLAS), fp32 and bf16
+    # autocast -- SURVEY.md §2.2 names it as the real bar; not our path, never part of `value`
+    eager = None
+    if args.gpu_eager_baseline:
+        eager = gpu_eager_baseline(sd, cfg, x_host, dev)
 
     line = {
         'metric': METRIC, 'value': value, 'unit': 'crops/s', 'n_gpus': world, 'steps': args.steps,
@@ -360,8 +650,9 @@ def main():
         'clocks': clocks, 'gpu_launches': launches,
         'e2e': {'value': e2e_val, 'unit': 'crops/s', 'h2d_bytes_per_step': h2d, 'd2h_bytes_per_step': d2h,
                 'ms_per_step': ms_e2e / args.steps},
-        'roofline': roofline, 'cpu_baseline': cpu,
-        'executed_tflops_per_gpu': exec_tflops,
+        'roofline': roofline, 'cpu_baseline': cpu, 'parity_checked': parity is not None, 'parity': parity,
+        'sustained': sustained, 'gpu_eager_baseline': eager,
+        'executed_tflops_per_gpu': exec_tflops, 'executed_frac_of_bf16_peak': exec_tflops / pk['tf_sus'],
         'reference_graph_tflops_per_gpu': value / world * REF_GFLOP_PER_CROP / 1e3,
     }
     print(json.dumps(line))

@@ -85,6 +85,35 @@ int rsg_soft_oks_nms(void* stream, const float* kpts, const double* scores, cons
  * score[i] = box_score[i] * mean(maxvals[i,k] for maxvals[i,k] > in_vis_thre). */
 int rsg_rescore(void* stream, const float* maxvals, const double* box_scores, int n, int K,
                 double in_vis_thre, double* scores);
+/* NumPy >= 2 (NEP 50) arithmetic is what is reproduced: the np.float32 maxvals are compared with the Python-float
+ * threshold and accumulated in fp32; the mean is multiplied with the fp64 box score in fp64.  (Under NumPy 1.x the
+ * same reference lines promote to fp64; that variant differs at ~1e-8 and is not reproduced.)
+ * Order of EXACTLY equal scores in the NMS entry points: the later index first (= reversing a stable ascending sort,
+ * what NumPy's argsort does for n <= 16); NumPy's order of exact ties is unspecified for longer lists.  NaN scores sort
+ * first, as NumPy's argsort()[::-1] places them.  An image with more than max_per_img detections is refused: its keep_counts entry is set to -1. */
+
+/* Device-resident evaluate(): group the detections by image, rescore, (soft-)OKS-NMS per image, compacted keep lists --
+ * lib/dataset/crowdpose.py:1272-1324 and lib/dataset/coco.py:1227-1277 in one call with no host round trip (n_imgs
+ * included: it stays on the device).  Inputs are what lib/core/function.py:376-380,452-458 accumulates:
+ *   preds     f32 [n,K,3]  image-space x, y and the maxval of every joint (all_preds)
+ *   boxes     f64 [n,6]    centre, scale, area (index 4), box score (index 5) (all_boxes)
+ *   image_ids i64 [n]      the image of every detection, in ANY order (the reference parses it from the file name);
+ *                          0x8080808080808080 is reserved (n_imgs = -1 is reported if it occurs)
+ *   sigmas    f64 [K];  in_vis_thre = TEST.IN_VIS_THRE (rescoring only, like the reference), oks_thre = TEST.OKS_THRE,
+ *   soft_nms = TEST.SOFT_NMS (max_dets rounds; the reference hard-codes 20)
+ * Outputs (device):
+ *   n_imgs      i32 [1]
+ *   images      i64 [n]    the distinct image ids in first-appearance order (entries [0, n_imgs))
+ *   img_offsets i32 [n+1]  kept detections of image r are keep[img_offsets[r] ... + keep_counts[r])
+ *   scores      f64 [n]    rescored score of EVERY detection, indexed like the inputs
+ *   keep        i32 [n]    GLOBAL detection indices, per image in selection order
+ *   keep_counts i32 [n]
+ * workspace: rsg_evaluate_workspace_bytes(n) bytes of device memory (no alignment requirement beyond 256). */
+int rsg_evaluate_workspace_bytes(int n, size_t* bytes);
+int rsg_evaluate(void* stream, const float* preds, const double* boxes, const int64_t* image_ids, int n, int K,
+                 const double* sigmas, double in_vis_thre, double oks_thre, int soft_nms, int max_dets, void* workspace,
+                 size_t workspace_bytes, int32_t* n_imgs, int64_t* images, int32_t* img_offsets, double* scores,
+                 int32_t* keep, int32_t* keep_counts);
 
 /* Person-crop affine warp + normalisation for a batch of crops (the loader's input path).
  * Replaces, per crop, cv2.warpAffine(img, trans, (out_w, out_h), flags=cv2.INTER_LINEAR) as called by

@@ -165,6 +165,31 @@ def nms_cases():
         print('wrote', fn, os.path.getsize(fn) // 1024, 'KiB')
 
 
+def evaluate_cases():
+    """dataset.evaluate() of the UNMODIFIED reference (crowdpose.py:1255-1324 with K=14 and its own sigmas;
+    coco.py:1210-1277 with K=17 and the default sigmas): per-image grouping in first-appearance order, rescoring,
+    OKS-NMS.  Pins rsgnet_b200.nms.evaluate_device and oracle/nms_oracle.{rescore,evaluate}."""
+    from oracle.nms_oracle import CROWDPOSE_SIGMAS
+    for tag, (k, sig) in dict(crowdpose=(14, CROWDPOSE_SIGMAS), coco=(17, None)).items():
+        rec = dict(k=k, n_imgs=400, per_img=12, seed=13, in_vis_thre=0.2, oks_thre=0.9)
+        preds, boxes, ids = synth.evaluate_inputs(400, 12, k, seed=13)
+        if tag == 'crowdpose':
+            paths = [f'data/crowdpose/images/{int(i)}.jpg' for i in ids]
+        else:
+            paths = [f'data/coco/images/val2017/{int(i):012d}.jpg' for i in ids]
+        run = ref_import.ref_dataset_evaluate(tag)
+        for soft in (False, True):
+            out = run(preds.copy(), boxes.copy(), paths, k, sig, 0.2, 0.9, soft_nms=soft)
+            sfx = '_soft' if soft else ''
+            rec['images' + sfx] = np.asarray([img[0]['image'] for img in out], np.int64)
+            rec['counts' + sfx] = np.asarray([len(img) for img in out], np.int32)
+            rec['keep' + sfx] = np.asarray([int(d['center'][0]) for img in out for d in img], np.int32)
+            rec['scores' + sfx] = np.asarray([d['score'] for img in out for d in img], np.float64)
+        fn = os.path.join(OUT, f'evaluate_{tag}.npz')
+        np.savez_compressed(fn, **rec)
+        print('wrote', fn, os.path.getsize(fn) // 1024, 'KiB', 'kept', int(rec['counts'].sum()), 'of', len(ids))
+
+
 def warp_cases():
     """Loader input path (CPJointsDataset.py:1281-1290, cp_test.py:107-115) executed by the reference's own
     get_affine_transform / crop (-> cv2.getAffineTransform, cv2.warpAffine) and torchvision's ToTensor + Normalize."""
@@ -197,13 +222,15 @@ def main():
     assert ref_import.available(), 'needs /root/reference'
     os.makedirs(OUT, exist_ok=True)
     torch.set_num_threads(8)
-    which = sys.argv[1:] or ['decode', 'nms', 'warp', 'model']
+    which = sys.argv[1:] or ['decode', 'nms', 'warp', 'evaluate', 'model']
     if 'decode' in which:
         decode_cases()
     if 'nms' in which:
         nms_cases()
     if 'warp' in which:
         warp_cases()
+    if 'evaluate' in which:
+        evaluate_cases()
     if 'model' in which:
         model_case('tiny', 2, 0, full=True)
         model_case('tiny_cp_sub', 2, 1, full=True)

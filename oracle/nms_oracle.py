@@ -115,3 +115,30 @@ def soft_oks_nms(kpts_db, thresh, sigmas=None, in_vis_thre=None):
         keep[keep_cnt] = i
         keep_cnt += 1
     return keep[:keep_cnt]
+
+
+def evaluate(all_preds, all_boxes, image_ids, sigmas, in_vis_thre, oks_thre, soft_nms=False):
+    """dataset.evaluate() up to the kept lists (crowdpose.py:1272-1324 / coco.py:1227-1277): group the detections by
+    image in first-appearance order, rescore each one (box score * mean of the maxvals above in_vis_thre), run
+    (soft-)OKS-NMS per image WITHOUT in_vis_thre (no caller passes it), keep everything if NMS keeps nothing.
+    all_preds f32 [N,K,3]; all_boxes f64 [N,6] (.., area at 4, box score at 5); image_ids int [N].
+    Returns (images i64 [n_imgs], counts i32 [n_imgs], keep i32 [sum counts] GLOBAL detection indices in the
+    per-image selection order, scores f64 [sum counts] rescored)."""
+    groups = {}
+    for idx, img in enumerate(image_ids):
+        groups.setdefault(int(img), []).append(idx)
+    images, counts, keep_all, scores_all = [], [], [], []
+    for img, members in groups.items():
+        db = []
+        for idx in members:
+            db.append(dict(keypoints=all_preds[idx], area=all_boxes[idx][4],
+                           score=rescore(all_boxes[idx][5], all_preds[idx][:, 2], in_vis_thre)))
+        keep = (soft_oks_nms if soft_nms else oks_nms)(db, oks_thre, sigmas)
+        if len(keep) == 0:
+            keep = list(range(len(db)))
+        images.append(img)
+        counts.append(len(keep))
+        keep_all.extend(members[int(j)] for j in keep)
+        scores_all.extend(db[int(j)]['score'] for j in keep)
+    return (np.asarray(images, np.int64), np.asarray(counts, np.int32), np.asarray(keep_all, np.int32),
+            np.asarray(scores_all, np.float64))

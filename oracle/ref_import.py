@@ -96,3 +96,47 @@ def ref_functions():
     return dict(get_final_preds=get_final_preds, get_max_preds=get_max_preds,
                 oks_nms=oks_nms, oks_iou=oks_iou, soft_oks_nms=soft_oks_nms, flip_back=flip_back,
                 get_affine_transform=get_affine_transform, crop=crop)
+
+
+def ref_dataset_evaluate(kind):
+    """The reference's own ``evaluate()`` (rescoring + per-image grouping + OKS-NMS), callable without the dataset
+    files: ``kind`` = 'crowdpose' -> CrowdPoseSkeletonDataset.evaluate (lib/dataset/crowdpose.py:1255-1324, what
+    cp_test.py / rsgnet_validate drive), 'coco' -> COCOCPDataset.evaluate (lib/dataset/coco.py:1210-1277).
+    The third-party evaluation packages the module imports at the top (json_tricks, crowdposetools, pycocotools; absent
+    here, never reached by this path) are stubbed in sys.modules, ``dataset`` is pre-registered as an empty package (its
+    __init__ imports every dataset), and the method is called UNBOUND on a stand-in ``self`` whose
+    ``_write_coco_keypoint_results`` captures the per-image kept lists.  Returns f(preds, all_boxes, img_path, k, sigmas,
+    in_vis_thre, oks_thre, soft_nms) -> list (per image, first-appearance order) of lists of kept detection dicts."""
+    _install_shims()
+    for n in ('json_tricks', 'crowdposetools', 'crowdposetools.coco', 'crowdposetools.cocoeval', 'pycocotools',
+              'pycocotools.coco', 'pycocotools.cocoeval', 'pycocotools._mask', 'pycocotools.mask'):
+        if n not in sys.modules:
+            m = types.ModuleType(n)
+            m.COCO = m.COCOeval = None
+            m.__path__ = []
+            sys.modules[n] = m
+    if 'dataset' not in sys.modules:
+        pkg = types.ModuleType('dataset')
+        pkg.__path__ = [os.path.join(REF, 'lib', 'dataset')]
+        sys.modules['dataset'] = pkg
+    if kind == 'crowdpose':
+        cls = importlib.import_module('dataset.crowdpose').CrowdPoseSkeletonDataset
+    else:
+        cls = importlib.import_module('dataset.coco').COCOCPDataset
+
+    def run(preds, all_boxes, img_path, k, sigmas, in_vis_thre, oks_thre, soft_nms=False):
+        captured = {}
+
+        def write(kpts, res_file):
+            captured['kpts'] = kpts
+        fake = types.SimpleNamespace(num_joints=k, in_vis_thre=in_vis_thre, oks_thre=oks_thre, soft_nms=soft_nms,
+                                     nms_sigmas=sigmas, image_set='val', _write_coco_keypoint_results=write,
+                                     _do_python_keypoint_eval=lambda *a: [('AP', 0.0)])
+        cfg = AttrDict(RANK=0)
+        out_dir = tempfile.mkdtemp()
+        try:
+            cls.evaluate(fake, cfg, preds, out_dir, all_boxes, img_path)
+        finally:
+            shutil.rmtree(out_dir, ignore_errors=True)
+        return captured['kpts']
+    return run

@@ -646,6 +646,7 @@ def build_network(pb, sd, spec):
 
     # ---- keypoint head (pose_rsgnet.py:991-1000)
     kf = _cbr(pb, P, View(cat2), 'kpt_net')
+    taps['kpt_net'] = kf
     if up > 1:
         kd = View(pb.buf('kpt_up', h * 2, w * 2, C0))
         kf = _deconv4(pb, P, 'predict_convtranspose', kf, kd)

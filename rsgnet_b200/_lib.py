@@ -67,6 +67,9 @@ _SIGS = {
     'rsg_oks_iou': (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_double, C.c_void_p, C.c_void_p,
                               C.c_int, C.c_int, C.c_void_p, C.c_int, C.c_double]),
     'rsg_rescore': (C.c_int, [C.c_void_p] * 3 + [C.c_int, C.c_int, C.c_double, C.c_void_p]),
+    'rsg_evaluate_workspace_bytes': (C.c_int, [C.c_int, C.POINTER(C.c_size_t)]),
+    'rsg_evaluate': (C.c_int, [C.c_void_p] * 4 + [C.c_int, C.c_int, C.c_void_p, C.c_double, C.c_double, C.c_int, C.c_int,
+                               C.c_void_p, C.c_size_t] + [C.c_void_p] * 6),
     'rsg_warp_affine': (C.c_int, [C.c_void_p] * 4 + [C.c_int] * 4 + [C.c_void_p] * 3),
     'rsg_plan_create': (C.c_int, [C.POINTER(C.c_void_p), C.c_int]),
     'rsg_plan_destroy': (None, [C.c_void_p]),

@@ -286,7 +286,7 @@ int make_att_map(const bf16* base, int cs, int co, int N, int S, int C, int rows
 int attention_tc5_launch(cudaStream_t s, const bf16* x, int x_cs, int x_co, const bf16* g, int g_cs, int g_co,
                          bf16* y, int y_cs, int y_co, int N, int S, int C, int* handled) {
   *handled = 0;
-  static const bool legacy = getenv("RSG_ATT_LEGACY") != nullptr;      // A/B switch: the mma.sync kernel
+  static const bool legacy = rsg_dbg_env("RSG_ATT_LEGACY") != nullptr;      // A/B switch: the mma.sync kernel
   if (legacy) return RSG_OK;
   if (C % 16 != 0 || C < 16 || C > 64 || N > 65535) return RSG_OK;
   if (x_cs % 8 != 0 || x_co % 8 != 0 || g_cs % 8 != 0 || g_co % 8 != 0 || y_cs % 8 != 0 || y_co % 8 != 0) return RSG_OK;
@@ -299,17 +299,17 @@ int attention_tc5_launch(cudaStream_t s, const bf16* x, int x_cs, int x_co, cons
   p.nblk = (S + AT_BK - 1) / AT_BK;
   p.q_bytes = (uint32_t)AT_BQ * C * 2;
   p.kv_tile_bytes = (uint32_t)AT_BK * C * 2;
-  { const char* e = getenv("RSG_ATT_SKIP"); p.skip = e ? atoi(e) : 0; }
+  { const char* e = rsg_dbg_env("RSG_ATT_SKIP"); p.skip = e ? atoi(e) : 0; }
   AttMaps maps;
   memset(&maps, 0, sizeof(maps));
   { int rc = make_att_map(x, x_cs, x_co, N, S, C, AT_BQ, &maps.q); if (rc) return rc; }
   { int rc = make_att_map(x, x_cs, x_co, N, S, C, AT_BK, &maps.x); if (rc) return rc; }
   { int rc = make_att_map(g, g_cs, g_co, N, S, C, AT_BK, &maps.g); if (rc) return rc; }
   const size_t smem = 128 + p.q_bytes + AT_KV_STAGES * 2u * p.kv_tile_bytes + 2u * AT_BQ * AT_BK * 2u;
-  static bool attr_done = false;
-  if (!attr_done) {
+  static DeviceOnce attr_once;
+  if (attr_once.first()) {
     RSG_CUDA(cudaFuncSetAttribute(trp_attention_tc5_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
-    attr_done = true;
+    attr_once.done();
   }
   dim3 grid((S + AT_BQ - 1) / AT_BQ, N);
   trp_attention_tc5_kernel<<<grid, AT_THREADS, smem, s>>>(maps, p);

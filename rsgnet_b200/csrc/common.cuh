@@ -35,7 +35,45 @@ int rsg_cuda_fail(cudaError_t e, const char* what, const char* file, int line);
 
 static inline int ceil_div(long long a, long long b) { return (int)((a + b - 1) / b); }
 
-int rsg_num_sms();
+int rsg_num_sms();          // SM count of the CURRENT device (cached per device)
+
+// Per-device one-time initialisation (cudaFuncSetAttribute is per device, and DataParallel-style callers drive
+// several devices from several threads of one process): `static DeviceOnce once; if (once.first()) {...}`.
+// first() returns true exactly until done() has been called for the current device.
+#include <mutex>
+struct DeviceOnce {
+  static constexpr int MAX_DEV = 64;
+  std::mutex mu;
+  bool flag[MAX_DEV] = {};
+  bool first(int* dev_out = nullptr) {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    if (dev_out) *dev_out = dev;
+    if (dev < 0 || dev >= MAX_DEV) return true;
+    std::lock_guard<std::mutex> g(mu);
+    return !flag[dev];
+  }
+  void done() {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    if (dev < 0 || dev >= MAX_DEV) return;
+    std::lock_guard<std::mutex> g(mu);
+    flag[dev] = true;
+  }
+};
+
+// Debug / tuning switches (RSG_*_SKIP, RSG_TC5_KC, ...) exist only in builds made with -DRSG_DEBUG_SWITCHES
+// (`make DEBUG_SWITCHES=1`, what the tools/ micro-benchmarks use): the product library never reads the environment
+// on a launch path, so no variable can silently change its results.
+#ifdef RSG_DEBUG_SWITCHES
+static inline const char* rsg_dbg_env(const char* name) { return getenv(name); }
+#else
+static inline const char* rsg_dbg_env(const char*) { return nullptr; }
+#endif
+static inline int rsg_dbg_int(const char* name, int dflt) {
+  const char* e = rsg_dbg_env(name);
+  return e ? atoi(e) : dflt;
+}
 
 // Programmatic dependent launch (PDL): the kernel may start while its stream predecessor is still draining;
 // it must execute pdl_wait() before its first access to memory the predecessor produces or still reads.
@@ -47,7 +85,7 @@ __device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepc
 
 template <typename... KArgs, typename... Args>
 inline cudaError_t launch_pdl(void (*kern)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t s, Args... args) {
-  static const bool off = getenv("RSG_NO_PDL") != nullptr;
+  static const bool off = rsg_dbg_env("RSG_NO_PDL") != nullptr;
   cudaLaunchConfig_t cfg;
   memset(&cfg, 0, sizeof(cfg));
   cfg.gridDim = grid; cfg.blockDim = block; cfg.dynamicSmemBytes = smem; cfg.stream = s;

@@ -375,13 +375,13 @@ conv_bb_kernel(const __grid_constant__ CUtensorMap in_map, const BbP p) {
 
 // 1 when the fused kernel covers a C -> C BasicBlock on H x W maps.
 extern "C" int rsg_basic_block_supported(int C, int H, int W) {
-  if (getenv("RSG_DISABLE_BB")) return 0;
+  if (rsg_dbg_env("RSG_DISABLE_BB")) return 0;
   return (C == 32 || C == 48) && H >= 16 && W >= 8 ? 1 : 0;
 }
 
 int conv_bb_launch(cudaStream_t s, const bf16* in, int in_cs, int in_co, int N, int H, int W, int C, const bf16* w1,
                    const float* b1, const bf16* w2, const float* b2, bf16* out, int out_cs, int out_co) {
-  RSG_REQUIRE(rsg_basic_block_supported(C, H, W) || getenv("RSG_DISABLE_BB"), "basic block: C=%d on %dx%d is not covered", C, H, W);
+  RSG_REQUIRE(rsg_basic_block_supported(C, H, W) || rsg_dbg_env("RSG_DISABLE_BB"), "basic block: C=%d on %dx%d is not covered", C, H, W);
   RSG_REQUIRE(in_cs % 8 == 0 && in_co % 8 == 0 && out_cs % 8 == 0 && out_co % 8 == 0, "basic block: channel strides/offsets must be multiples of 8");
   if (N == 0) return RSG_OK;
   BbP k;
@@ -390,14 +390,14 @@ int conv_bb_launch(cudaStream_t s, const bf16* in, int in_cs, int in_co, int N, 
   k.w_bytes = 9u * C * C * 2u;
   // 16-wide tiles (conv1 on 324 useful rows of 384 instead of 180 of 256) where the map and shared memory allow
   int twt = 16;
-  { const char* e = getenv("RSG_BB_TW"); if (e && (atoi(e) == 8 || atoi(e) == 16)) twt = atoi(e); }
+  { const char* e = rsg_dbg_env("RSG_BB_TW"); if (e && (atoi(e) == 8 || atoi(e) == 16)) twt = atoi(e); }
   int NB = 2, S = 0;
   for (;; twt = 8) {
     const int pitch = twt + 4, in_px = BB_IN_ROWS * pitch, mt1 = (18 * pitch + 127) / 128, mt2 = twt / 8;
     k.stage_bytes = (uint32_t)(C / 8) * in_px * 16u;
     k.mid_bytes = (uint32_t)(C / 8) * mt1 * 128u * 16u;
     NB = (2 * (mt1 + mt2) * 2 * C <= 512 && twt == 8) ? 4 : 2;            // TMEM: NB * (MT1 + MT2) * C columns
-    { const char* e = getenv("RSG_BB_NB"); if (e && (atoi(e) == 2 || atoi(e) == 4) && atoi(e) * (mt1 + mt2) * C <= 512) NB = atoi(e); }
+    { const char* e = rsg_dbg_env("RSG_BB_NB"); if (e && (atoi(e) == 2 || atoi(e) == 4) && atoi(e) * (mt1 + mt2) * C <= 512) NB = atoi(e); }
     S = (int)((220 * 1024 - 2 * (int)k.w_bytes - NB * (int)k.mid_bytes) / (int)k.stage_bytes);
     if (S > BB_MAX_S) S = BB_MAX_S;
     const bool fits = S >= 3 && NB * (mt1 + mt2) * C <= 512 && (twt == 8 || W >= 16);
@@ -418,7 +418,7 @@ int conv_bb_launch(cudaStream_t s, const bf16* in, int in_cs, int in_co, int N, 
   k.magic_tpi = k.tiles_per_img > 1 ? (uint32_t)(((1ull << 32) + k.tiles_per_img - 1) / k.tiles_per_img) : 0u;
   k.magic_tx = k.tiles_x > 1 ? (uint32_t)(((1ull << 32) + k.tiles_x - 1) / k.tiles_x) : 0u;
   k.out = out; k.out_cs = out_cs; k.out_co = out_co;
-  { const char* e = getenv("RSG_BB_SKIP"); k.skip = e ? atoi(e) : 0; }
+  { const char* e = rsg_dbg_env("RSG_BB_SKIP"); k.skip = e ? atoi(e) : 0; }
   const size_t smem = 128 + 2 * (size_t)k.w_bytes + (size_t)S * k.stage_bytes + NB * (size_t)k.mid_bytes + 1024;
   EncodeTiledFn enc = tensor_map_encoder();
   RSG_REQUIRE(enc, "cuTensorMapEncodeTiled is not available from this driver");
@@ -434,13 +434,13 @@ int conv_bb_launch(cudaStream_t s, const bf16* in, int in_cs, int in_co, int N, 
                      CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     RSG_REQUIRE(r == CUDA_SUCCESS, "cuTensorMapEncodeTiled (basic block) failed with %d", (int)r);
   }
-  static bool attr_done = false;
-  if (!attr_done) {
+  static DeviceOnce attr_once;
+  if (attr_once.first()) {
     RSG_CUDA(cudaFuncSetAttribute(conv_bb_kernel<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, 225 * 1024));
     RSG_CUDA(cudaFuncSetAttribute(conv_bb_kernel<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, 225 * 1024));
-    attr_done = true;
+    attr_once.done();
   }
-  static const bool dbg = getenv("RSG_DEBUG") != nullptr;
+  static const bool dbg = rsg_dbg_env("RSG_DEBUG") != nullptr;
   if (dbg) fprintf(stderr, "[bb] C=%d %dx%d tile 16x%d NB=%d S=%d smem=%zu tiles=%d tmem=%u\n", C, H, W, twt, NB, S, smem, k.ntiles, k.tmem_cols);
   int gx = rsg_num_sms();
   if (gx > k.ntiles) gx = k.ntiles;

@@ -431,7 +431,7 @@ conv_bneck_kernel(const __grid_constant__ CUtensorMap in_map, const BnP p) {
 
 // 1 when the fused kernel covers a Bottleneck (Cin -> planes -> planes -> Cout) on H x W maps.
 extern "C" int rsg_bottleneck_supported(int Cin, int planes, int Cout, int H, int W) {
-  if (getenv("RSG_DISABLE_BNECK")) return 0;
+  if (rsg_dbg_env("RSG_DISABLE_BNECK")) return 0;
   return planes == 64 && Cout == 256 && Cin >= 64 && Cin <= 256 && Cin % 64 == 0 && H >= 16 && W >= 8 ? 1 : 0;
 }
 
@@ -450,12 +450,12 @@ int conv_bneck_launch(cudaStream_t s, const bf16* in, int in_cs, int in_co, int 
   k.w1_bytes = (uint32_t)Cin * 64u * 2u;
   // wide rows (one 128-byte TMA row per pixel instead of eight 16-byte elements): the planar boxes of a DRAM-resident
   // 256-channel map arrive at ~11 B/cycle/SM with the two stages that fit (timeline: 8500 cycles per tile waiting for TMA)
-  k.wide = getenv("RSG_BNECK_PLANAR") ? 0 : 1;
+  k.wide = rsg_dbg_env("RSG_BNECK_PLANAR") ? 0 : 1;
   k.stage_bytes = k.wide ? 184u * 128u : BN_STAGE;
   const size_t fixed = 1024 + (size_t)k.w1_bytes + BN_W2 + BN_W3 + BN_STAGE + BN_MID2;
   int S = (int)((225 * 1024 - (long long)fixed) / (long long)k.stage_bytes);
   if (S > BN_MAX_S) S = BN_MAX_S;
-  { const char* e = getenv("RSG_BNECK_S"); if (e && atoi(e) >= 1 && atoi(e) <= S) S = atoi(e); }
+  { const char* e = rsg_dbg_env("RSG_BNECK_S"); if (e && atoi(e) >= 1 && atoi(e) <= S) S = atoi(e); }
   RSG_REQUIRE(S >= 2, "bottleneck: shared memory budget");
   k.S = S;
   k.tiles_x = (W + 7) / 8; k.tiles_y = (H + 15) / 16;
@@ -469,10 +469,10 @@ int conv_bneck_launch(cudaStream_t s, const bf16* in, int in_cs, int in_co, int 
   k.out = out; k.out_cs = out_cs; k.out_co = out_co;
   k.v32 = ((out_cs % 16 == 0 && out_co % 16 == 0 && ((uintptr_t)out & 31) == 0) ? 1 : 0) |
           ((res_cs % 16 == 0 && res_co % 16 == 0 && ((uintptr_t)res & 31) == 0) ? 2 : 0);
-  { const char* e = getenv("RSG_BNECK_SKIP"); k.skip = e ? atoi(e) : 0; }
-  if (getenv("RSG_BNECK_PREFETCH")) k.skip |= 32;
+  { const char* e = rsg_dbg_env("RSG_BNECK_SKIP"); k.skip = e ? atoi(e) : 0; }
+  if (rsg_dbg_env("RSG_BNECK_PREFETCH")) k.skip |= 32;
   static long long* dbg_buf = nullptr;
-  if (getenv("RSG_BNECK_TIMELINE")) {
+  if (rsg_dbg_env("RSG_BNECK_TIMELINE")) {
     if (!dbg_buf) cudaMalloc(&dbg_buf, 32 * 16 * sizeof(long long));
     cudaMemsetAsync(dbg_buf, 0, 32 * 16 * sizeof(long long), s);
     k.dbg = dbg_buf;
@@ -501,12 +501,12 @@ int conv_bneck_launch(cudaStream_t s, const bf16* in, int in_cs, int in_co, int 
                      CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     RSG_REQUIRE(r == CUDA_SUCCESS, "cuTensorMapEncodeTiled (bottleneck) failed with %d", (int)r);
   }
-  static bool attr_done = false;
-  if (!attr_done) {
+  static DeviceOnce attr_once;
+  if (attr_once.first()) {
     RSG_CUDA(cudaFuncSetAttribute(conv_bneck_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 225 * 1024));
-    attr_done = true;
+    attr_once.done();
   }
-  static const bool dbg = getenv("RSG_DEBUG") != nullptr;
+  static const bool dbg = rsg_dbg_env("RSG_DEBUG") != nullptr;
   if (dbg) fprintf(stderr, "[bneck] Cin=%d %dx%d S=%d smem=%zu tiles=%d\n", Cin, H, W, S, smem, k.ntiles);
   int gx = rsg_num_sms();
   if (gx > k.ntiles) gx = k.ntiles;

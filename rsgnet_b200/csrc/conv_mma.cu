@@ -209,11 +209,11 @@ conv_mma_kernel(const ConvP p) {
 template <int BN>
 int launch(const ConvP& p, cudaStream_t s) {
   const size_t smem = (size_t)STAGES * (BM + BN) * 64;
-  static bool attr_done = false;
-  if (!attr_done) {
+  static DeviceOnce attr_once;
+  if (attr_once.first()) {
     RSG_CUDA(cudaFuncSetAttribute(conv_mma_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                   (int)smem));
-    attr_done = true;
+    attr_once.done();
   }
   dim3 grid(ceil_div(p.M, BM), p.CoutPad / BN);
   conv_mma_kernel<BN><<<grid, THREADS, smem, s>>>(p);

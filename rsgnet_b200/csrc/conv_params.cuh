@@ -25,6 +25,7 @@ struct ConvP {
   int nres;
   ResP res[4];
   int relu;
+  int force;            // engine == 2: the caller insists on the tcgen05 kernel (unit tests): no size-based routing to the generic kernel
   int N;
   long long M;          // N * Hout * Wout
 };

@@ -458,7 +458,7 @@ static int tc5_pick(int Cin, int CoutPad, int ntaps, int mode, int* NS, int* KC,
   const int cands[4] = {128, 96, 64, 32};
   // prefer the widest slice that still leaves >= 4 stages; among the K chunkings the largest with >= 4 stages
   for (int min_s = 4; min_s >= 2; min_s -= 2) {
-    if (min_s < 4 && mode == 2 && !getenv("RSG_TC5_NO_WSTREAM")) {
+    if (min_s < 4 && mode == 2 && !rsg_dbg_env("RSG_TC5_NO_WSTREAM")) {
       // stride 2 with fewer than four resident-weight stages measured 2x slower than the generic kernel: stream the
       // weights with the halo stages instead (widest slice, largest chunk with >= 4 stages)
       for (int i = 0; i < 4; ++i) {
@@ -481,11 +481,11 @@ static int tc5_pick(int Cin, int CoutPad, int ntaps, int mode, int* NS, int* KC,
       const long long wb = (long long)ntaps * Cin * ns * 2;
       for (int kc = 64; kc >= 16; kc -= 16) {
         if (Cin % kc != 0 || Cin / kc > MAX_CHUNKS) continue;
-        { const char* e = getenv("RSG_TC5_KC"); if (e && atoi(e) != kc && Cin % atoi(e) == 0) continue; }
+        { const char* e = rsg_dbg_env("RSG_TC5_KC"); if (e && atoi(e) != kc && Cin % atoi(e) == 0) continue; }
         const int stage = stage_bytes_of(mode, kc);
         if (wb + (long long)min_s * stage > budget) continue;
         int s = MAX_STAGES;                     // even: the MMA warps own equal parts of the ring
-        { const char* e = getenv("RSG_TC5_S"); if (e && atoi(e) >= 2 && atoi(e) <= MAX_STAGES) s = atoi(e) & ~1; }
+        { const char* e = rsg_dbg_env("RSG_TC5_S"); if (e && atoi(e) >= 2 && atoi(e) <= MAX_STAGES) s = atoi(e) & ~1; }
         while (s > 2 && wb + (long long)s * stage > budget) s -= 2;
         *NS = ns; *KC = kc; *S = s;
         return 1;
@@ -502,11 +502,11 @@ extern "C" int rsg_conv_tc5_config(int Cin, int CoutPad, int ntaps, int mode, in
 
 int conv_tc5_launch(const ConvP& p, cudaStream_t s, int* handled) {
   *handled = 0;
-  static const bool disabled = getenv("RSG_DISABLE_TC5") != nullptr;   // A/B switch for debugging
+  static const bool disabled = rsg_dbg_env("RSG_DISABLE_TC5") != nullptr;   // A/B switch for debugging
   if (disabled) return RSG_OK;
   if (!p.w_tc5 || !p.out || p.out_f32) return RSG_OK;
   if (p.stride != 1 && p.stride != 2) return RSG_OK;
-  if (p.stride == 2 && getenv("RSG_TC5_NO_S2")) return RSG_OK;
+  if (p.stride == 2 && rsg_dbg_env("RSG_TC5_NO_S2")) return RSG_OK;
   if (p.omul < 1 || p.oH < p.Hout * p.omul || p.oW < p.Wout * p.omul) return RSG_OK;
   if (p.Hout != (p.Hin - 1) / p.stride + 1 || p.Wout != (p.Win - 1) / p.stride + 1) return RSG_OK;
   if (p.omul != 1 && p.nres != 0) return RSG_OK;
@@ -524,7 +524,7 @@ int conv_tc5_launch(const ConvP& p, cudaStream_t s, int* handled) {
   if (!tc5_pick(p.Cin, p.CoutPad, p.ntaps, mode, &NS, &KC, &S, &wstream)) return RSG_OK;
   // a stride-2 layer whose weights leave room for only two phase-patch stages (256->64: 147 KB per 32-channel
   // slice) measured 2x slower than the generic kernel (tc5_pick streams the weights instead where it can)
-  if (p.stride == 2 && S < 4 && !getenv("RSG_TC5_ANYSIZE")) return RSG_OK;
+  if (p.stride == 2 && S < 4 && !p.force) return RSG_OK;
   if (p.M == 0) { *handled = 1; return RSG_OK; }
 
   Tc5P k;
@@ -574,7 +574,7 @@ int conv_tc5_launch(const ConvP& p, cudaStream_t s, int* handled) {
   k.magic_tpi = k.tiles_per_img > 1 ? (uint32_t)(((1ull << 32) + k.tiles_per_img - 1) / k.tiles_per_img) : 0u;
   k.magic_tx = k.tiles_x > 1 ? (uint32_t)(((1ull << 32) + k.tiles_x - 1) / k.tiles_x) : 0u;
   // maps much smaller than the 16x8 patch waste most MMA rows (8x6: 37%): generic kernel instead
-  if (!p.psC && !getenv("RSG_TC5_ANYSIZE") && (double)p.Hout * p.Wout < 0.6 * 128.0 * k.tiles_x * k.tiles_y) return RSG_OK;
+  if (!p.psC && !p.force && (double)p.Hout * p.Wout < 0.6 * 128.0 * k.tiles_x * k.tiles_y) return RSG_OK;
   k.out = p.out; k.out_cs = p.out_cs; k.out_co = p.out_co;
   k.nres = p.nres;
   for (int q = 0; q < p.nres; ++q) k.res[q] = p.res[q];
@@ -583,11 +583,11 @@ int conv_tc5_launch(const ConvP& p, cudaStream_t s, int* handled) {
     auto al32 = [](const void* ptr, int cs, int co) { return ((uintptr_t)ptr % 32 == 0) && cs % 16 == 0 && co % 16 == 0; };
     k.v32 = (al32(p.out, p.out_cs, p.out_co) && (!p.psC || p.psC % 16 == 0) ? 1 : 0) |
             (p.nres > 0 && al32(p.res[0].p, p.res[0].cs, p.res[0].co) ? 2 : 0);
-    if (getenv("RSG_NO_V32")) k.v32 = 0;
+    if (rsg_dbg_env("RSG_NO_V32")) k.v32 = 0;
   }
-  { const char* e = getenv("RSG_TC5_SKIP"); k.skip = e ? atoi(e) : 0; }
+  { const char* e = rsg_dbg_env("RSG_TC5_SKIP"); k.skip = e ? atoi(e) : 0; }
   static long long* dbg_buf = nullptr;
-  if (getenv("RSG_TC5_TIMELINE")) {
+  if (rsg_dbg_env("RSG_TC5_TIMELINE")) {
     if (!dbg_buf) { cudaMalloc(&dbg_buf, 64 * 8 * sizeof(long long)); }
     cudaMemsetAsync(dbg_buf, 0, 64 * 8 * sizeof(long long), s);
     k.dbg = dbg_buf;
@@ -610,7 +610,7 @@ int conv_tc5_launch(const ConvP& p, cudaStream_t s, int* handled) {
   // three issuers when the ring splits three ways (keeps the tensor pipe fed while the others sit in their
   // per-tile barrier round trips), else two
   int nmma = S >= 6 ? 3 : 2;
-  { const char* e = getenv("RSG_TC5_NMMA"); if (e && (atoi(e) == 2 || atoi(e) == 3)) nmma = atoi(e); }
+  { const char* e = rsg_dbg_env("RSG_TC5_NMMA"); if (e && (atoi(e) == 2 || atoi(e) == 3)) nmma = atoi(e); }
   if (S < nmma) nmma = 2;
   // Tile tl is filled by MMA warp tl % NMMA into accumulator tl % NACC and drained by epilogue group tl % NEPI.  NACC
   // must be a multiple of BOTH, so that an accumulator always belongs to one issuer and one group, in order: with
@@ -624,7 +624,7 @@ int conv_tc5_launch(const ConvP& p, cudaStream_t s, int* handled) {
   k.NMMA = nmma;
   nacc = nacc / (nmma * NEPI) * (nmma * NEPI);           // nmma = 2: multiples of 2 (NEPI = 2), nmma = 3: 6
   if (nmma == 2) nacc = (int)(col_budget / (uint32_t)NS) >= 8 ? 8 : ((int)(col_budget / (uint32_t)NS) >= 4 ? 4 : 2);
-  { const char* e = getenv("RSG_TC5_NACC"); if (e && atoi(e) >= 2 && atoi(e) % (nmma == 3 ? 6 : 2) == 0 && atoi(e) * NS <= 512 && atoi(e) <= MAX_ACC) nacc = atoi(e); }
+  { const char* e = rsg_dbg_env("RSG_TC5_NACC"); if (e && atoi(e) >= 2 && atoi(e) % (nmma == 3 ? 6 : 2) == 0 && atoi(e) * NS <= 512 && atoi(e) <= MAX_ACC) nacc = atoi(e); }
   k.NACC = nacc;
   uint32_t cols = 32;
   while (cols < (uint32_t)(nacc * NS)) cols <<= 1;
@@ -632,16 +632,16 @@ int conv_tc5_launch(const ConvP& p, cudaStream_t s, int* handled) {
   const int nslices = p.CoutPad / NS;
   const int threads = NTHREADS;
 
-  static bool attr_done = false;
-  if (!attr_done) {
+  static DeviceOnce attr_once;
+  if (attr_once.first()) {
     RSG_CUDA(cudaFuncSetAttribute(conv_tc5_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
     RSG_CUDA(cudaFuncSetAttribute(conv_tc5_kernel<false>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
     RSG_CUDA(cudaFuncSetAttribute(conv_tc5_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
     RSG_CUDA(cudaFuncSetAttribute(conv_tc5_kernel<true>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
-    attr_done = true;
+    attr_once.done();
   }
   const int occ = 1;
-  static const bool dbg = getenv("RSG_DEBUG") != nullptr;
+  static const bool dbg = rsg_dbg_env("RSG_DEBUG") != nullptr;
   if (dbg) fprintf(stderr, "[tc5] Cin=%d Cout=%d taps=%d NS=%d KC=%d S=%d NACC=%d smem=%zu tiles=%lld\n", p.Cin, p.CoutPad, p.ntaps, NS, KC, S, k.NACC, smem, k.ntiles);
   long long gx = ((long long)rsg_num_sms() * occ + nslices - 1) / nslices;
   if (gx > k.ntiles) gx = k.ntiles;

@@ -358,7 +358,7 @@ bool ws_config(int Cin, int CoutPad, int ntaps, int H, int W, WsCfg* c) {
   if (nimg > 64) nimg = 64;
   c->NS = NS; c->nimg = nimg;
   c->KC = 16;
-  { const char* e = getenv("RSG_WS_KC"); if (e && Cin % atoi(e) == 0) c->KC = atoi(e); }
+  { const char* e = rsg_dbg_env("RSG_WS_KC"); if (e && Cin % atoi(e) == 0) c->KC = atoi(e); }
   c->T = (nimg * pitch + 127) / 128;
   c->plane_bytes = (uint32_t)nimg * pitch * 16u;
   c->a_bytes = (uint32_t)(c->KC / 8) * c->plane_bytes;
@@ -406,7 +406,7 @@ extern "C" int rsg_conv_ws_config(int Cin, int CoutPad, int ntaps, int H, int W,
 
 int conv_ws_launch(const ConvP& p, cudaStream_t s, int* handled) {
   *handled = 0;
-  static const bool disabled = getenv("RSG_DISABLE_WS") != nullptr;
+  static const bool disabled = rsg_dbg_env("RSG_DISABLE_WS") != nullptr;
   if (disabled) return RSG_OK;
   if (!p.w_tc5 || !p.out || p.out_f32) return RSG_OK;
   if (p.stride != 1 || p.omul != 1 || p.ooy != 0 || p.oox != 0) return RSG_OK;
@@ -439,11 +439,11 @@ int conv_ws_launch(const ConvP& p, cudaStream_t s, int* handled) {
   {
     auto al32 = [](const void* ptr, int cs, int co) { return ((uintptr_t)ptr % 32 == 0) && cs % 16 == 0 && co % 16 == 0; };
     k.v32 = (al32(p.out, p.out_cs, p.out_co) ? 1 : 0) | (p.nres > 0 && al32(p.res[0].p, p.res[0].cs, p.res[0].co) ? 2 : 0);
-    if (getenv("RSG_NO_V32")) k.v32 = 0;
+    if (rsg_dbg_env("RSG_NO_V32")) k.v32 = 0;
   }
-  { const char* e = getenv("RSG_WS_SKIP"); k.skip = e ? atoi(e) : 0; }
+  { const char* e = rsg_dbg_env("RSG_WS_SKIP"); k.skip = e ? atoi(e) : 0; }
   static int dbg_launch = 0;
-  if (getenv("RSG_WS_TIMELINE")) {
+  if (rsg_dbg_env("RSG_WS_TIMELINE")) {
     if (!g_dbg_buf) {
       cudaMalloc(&g_dbg_buf, 64 * 16 * sizeof(long long));
       cudaMemset(g_dbg_buf, 0, 64 * 16 * sizeof(long long));
@@ -459,13 +459,13 @@ int conv_ws_launch(const ConvP& p, cudaStream_t s, int* handled) {
   const size_t smem = (size_t)c.S * c.stage_bytes + 128;
   const int nslices = p.CoutPad / c.NS;
 
-  static bool attr_done = false;
-  if (!attr_done) {
+  static DeviceOnce attr_once;
+  if (attr_once.first()) {
     RSG_CUDA(cudaFuncSetAttribute(conv_ws_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, WS_SMEM_BUDGET));
     RSG_CUDA(cudaFuncSetAttribute(conv_ws_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
-    attr_done = true;
+    attr_once.done();
   }
-  static const bool dbg = getenv("RSG_DEBUG") != nullptr;
+  static const bool dbg = rsg_dbg_env("RSG_DEBUG") != nullptr;
   if (dbg) fprintf(stderr, "[ws] Cin=%d Cout=%d taps=%d %dx%d NS=%d nimg=%d T=%d S=%d stage=%u smem=%zu nsuper=%d\n", p.Cin,
                    p.CoutPad, p.ntaps, p.Hin, p.Win, c.NS, c.nimg, c.T, c.S, c.stage_bytes, smem, k.nsuper);
   int gx = rsg_num_sms() / nslices;

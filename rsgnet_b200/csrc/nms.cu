@@ -7,64 +7,28 @@
 //   lib/dataset/crowdpose.py:1294-1306, lib/dataset/coco.py:1249-1261   rescoring
 // Like the reference, OKS is evaluated lazily: only between a kept detection and the detections
 // still alive behind it in the score order.
-#include "common.cuh"
+#include "nms_common.cuh"
 #include "../../include/rsg_b200.h"
 
 namespace {
-
-// np.add.reduce over a contiguous fp64 vector of length n <= 128 (numpy's pairwise_sum).
-__device__ double numpy_sum(const double* a, int n) {
-  if (n < 8) {
-    double r = 0.0;
-    for (int i = 0; i < n; ++i) r = __dadd_rn(r, a[i]);
-    return r;
-  }
-  double r[8];
-#pragma unroll
-  for (int j = 0; j < 8; ++j) r[j] = a[j];
-  int i = 8;
-  for (; i < n - (n % 8); i += 8) {
-#pragma unroll
-    for (int j = 0; j < 8; ++j) r[j] = __dadd_rn(r[j], a[i + j]);
-  }
-  double res = __dadd_rn(__dadd_rn(__dadd_rn(r[0], r[1]), __dadd_rn(r[2], r[3])),
-                         __dadd_rn(__dadd_rn(r[4], r[5]), __dadd_rn(r[6], r[7])));
-  for (; i < n; ++i) res = __dadd_rn(res, a[i]);
-  return res;
-}
-
-#define RSG_NMS_MAXK 64
-
-// in_vis_thre (nms.py:85-90): the reference evaluates `list(vg > t) and list(vd > t)`, which is the SECOND list (a
-// non-empty list is truthy): only key points of d with score > t count, compared in fp32 like NumPy does for a
-// float32 array against a Python float; no visible key point -> 0.
-__device__ double oks_pair(const float* __restrict__ g, const float* __restrict__ d, double a_g,
-                           double a_d, const double* __restrict__ vars, int K, int use_vis, float vis) {
-  double ex[RSG_NMS_MAXK];
-  const double denom = __dadd_rn(__ddiv_rn(__dadd_rn(a_g, a_d), 2.0), 2.220446049250313e-16);
-  int m = 0;
-  for (int k = 0; k < K; ++k) {
-    float dx = __fsub_rn(d[3 * k], g[3 * k]);
-    float dy = __fsub_rn(d[3 * k + 1], g[3 * k + 1]);
-    float s = __fadd_rn(__fmul_rn(dx, dx), __fmul_rn(dy, dy));
-    double e = __ddiv_rn(__ddiv_rn(__ddiv_rn((double)s, vars[k]), denom), 2.0);
-    if (!use_vis || d[3 * k + 2] > vis) ex[m++] = exp(-e);
-  }
-  return m ? __ddiv_rn(numpy_sum(ex, m), (double)m) : 0.0;
-}
+using namespace rsgnms;
 
 __global__ void __launch_bounds__(128)
 oks_nms_kernel(const float* __restrict__ kpts, const double* __restrict__ scores,
                const double* __restrict__ areas, const int32_t* __restrict__ offs,
-               const double* __restrict__ sigmas, int K, double thresh, int use_vis, float vis,
+               const double* __restrict__ sigmas, int K, double thresh, int use_vis, float vis, int max_per_img,
                int32_t* __restrict__ keep, int32_t* __restrict__ keep_counts) {
-  extern __shared__ unsigned char smem_raw[];
+  extern __shared__ __align__(16) unsigned char smem_raw[];
   __shared__ double vars[RSG_NMS_MAXK];
   const int img = blockIdx.x;
   const int beg = offs[img], n = offs[img + 1] - beg;
   int* order = reinterpret_cast<int*>(smem_raw);          // [n] local indices, best first
   int* dead = order + n;                                  // [n] by position in `order`
   const int tid = threadIdx.x, nt = blockDim.x;
+  if (n < 0 || n > max_per_img) {                         // shared memory was sized for max_per_img: refuse, loudly
+    if (tid == 0) keep_counts[img] = -1;
+    return;
+  }
   if (tid < K) {
     double s2 = __dmul_rn(sigmas[tid], 2.0);
     vars[tid] = __dmul_rn(s2, s2);
@@ -73,10 +37,7 @@ oks_nms_kernel(const float* __restrict__ kpts, const double* __restrict__ scores
   for (int i = tid; i < n; i += nt) {
     const double si = scores[beg + i];
     int r = 0;
-    for (int j = 0; j < n; ++j) {
-      const double sj = scores[beg + j];
-      r += (sj > si) || (sj == si && j > i);
-    }
+    for (int j = 0; j < n; ++j) r += (j != i) && score_before(scores[beg + j], j, si, i);
     order[r] = i;
     dead[i] = 0;
   }
@@ -108,8 +69,8 @@ __global__ void __launch_bounds__(128)
 soft_oks_nms_kernel(const float* __restrict__ kpts, const double* __restrict__ scores,
                     const double* __restrict__ areas, const int32_t* __restrict__ offs,
                     const double* __restrict__ sigmas, int K, double thresh, int max_dets, int use_vis, float vis,
-                    int32_t* __restrict__ keep, int32_t* __restrict__ keep_counts) {
-  extern __shared__ unsigned char smem_raw[];
+                    int max_per_img, int32_t* __restrict__ keep, int32_t* __restrict__ keep_counts) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
   __shared__ double vars[RSG_NMS_MAXK];
   __shared__ double wbest[4];
   __shared__ int widx[4];
@@ -119,6 +80,10 @@ soft_oks_nms_kernel(const float* __restrict__ kpts, const double* __restrict__ s
   double* cur = reinterpret_cast<double*>(smem_raw);      // [n] current scores
   int* alive = reinterpret_cast<int*>(cur + n);           // [n]
   const int tid = threadIdx.x, nt = blockDim.x;
+  if (n < 0 || n > max_per_img) {
+    if (tid == 0) keep_counts[img] = -1;
+    return;
+  }
   if (tid < K) {
     double s2 = __dmul_rn(sigmas[tid], 2.0);
     vars[tid] = __dmul_rn(s2, s2);
@@ -132,18 +97,18 @@ soft_oks_nms_kernel(const float* __restrict__ kpts, const double* __restrict__ s
     double bv = 0.0;
     int bi = -1;
     for (int i = tid; i < n; i += nt)
-      if (alive[i] && (bi < 0 || cur[i] > bv || (cur[i] == bv && i > bi))) { bv = cur[i]; bi = i; }
+      if (alive[i] && (bi < 0 || score_before(cur[i], i, bv, bi))) { bv = cur[i]; bi = i; }
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) {
       const double ov = __shfl_xor_sync(0xffffffffu, bv, o);
       const int oi = __shfl_xor_sync(0xffffffffu, bi, o);
-      if (oi >= 0 && (bi < 0 || ov > bv || (ov == bv && oi > bi))) { bv = ov; bi = oi; }
+      if (oi >= 0 && (bi < 0 || score_before(ov, oi, bv, bi))) { bv = ov; bi = oi; }
     }
     if ((tid & 31) == 0) { wbest[tid >> 5] = bv; widx[tid >> 5] = bi; }
     __syncthreads();
     if (tid == 0) {
       for (int w = 1; w < (nt >> 5); ++w)
-        if (widx[w] >= 0 && (bi < 0 || wbest[w] > bv || (wbest[w] == bv && widx[w] > bi))) { bv = wbest[w]; bi = widx[w]; }
+        if (widx[w] >= 0 && (bi < 0 || score_before(wbest[w], widx[w], bv, bi))) { bv = wbest[w]; bi = widx[w]; }
       best_i = bi;
       keep[(size_t)img * max_dets + cnt] = bi;
       alive[bi] = 0;
@@ -180,18 +145,7 @@ __global__ void rescore_kernel(const float* __restrict__ maxvals,
                                double* __restrict__ out) {
   int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
-  // np.float32 accumulation; under NumPy 2 (NEP 50) float32 > python-float compares in fp32
-  float acc = 0.f;
-  const float thre32 = (float)thre;
-  int valid = 0;
-  for (int k = 0; k < K; ++k) {
-    float t = maxvals[(size_t)i * K + k];
-    if (t > thre32) { acc = __fadd_rn(acc, t); ++valid; }
-  }
-  double s;
-  if (valid != 0) s = (double)__fdiv_rn(acc, (float)valid);
-  else s = 0.0;
-  out[i] = __dmul_rn(s, box[i]);
+  out[i] = rescore_one(maxvals + (size_t)i * K, 1, K, (float)thre, box[i]);
 }
 
 }  // namespace
@@ -210,7 +164,7 @@ extern "C" int rsg_oks_nms(void* stream, const float* kpts, const double* scores
   if (smem > 48 * 1024)
     RSG_CUDA(cudaFuncSetAttribute(oks_nms_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   oks_nms_kernel<<<n_imgs, 128, smem, (cudaStream_t)stream>>>(kpts, scores, areas, img_offsets, sigmas, K, thresh,
-                                                             use_in_vis_thre ? 1 : 0, (float)in_vis_thre, keep, keep_counts);
+                                                             use_in_vis_thre ? 1 : 0, (float)in_vis_thre, max_per_img, keep, keep_counts);
   RSG_LAUNCH_CHECK();
   return RSG_OK;
 }
@@ -230,7 +184,7 @@ extern "C" int rsg_soft_oks_nms(void* stream, const float* kpts, const double* s
     RSG_CUDA(cudaFuncSetAttribute(soft_oks_nms_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   soft_oks_nms_kernel<<<n_imgs, 128, smem, (cudaStream_t)stream>>>(kpts, scores, areas, img_offsets, sigmas, K, thresh,
                                                                   max_dets, use_in_vis_thre ? 1 : 0, (float)in_vis_thre,
-                                                                  keep, keep_counts);
+                                                                  max_per_img, keep, keep_counts);
   RSG_LAUNCH_CHECK();
   return RSG_OK;
 }

@@ -24,12 +24,15 @@ int rsg_cuda_fail(cudaError_t e, const char* what, const char* file, int line) {
   return RSG_ERR_CUDA;
 }
 int rsg_num_sms() {
-  static int n = 0;
+  static int cache[DeviceOnce::MAX_DEV] = {};      // per device; a racing first call writes the same value twice
+  int dev = 0;
+  cudaGetDevice(&dev);
+  if (dev < 0 || dev >= DeviceOnce::MAX_DEV) return 148;
+  int n = cache[dev];
   if (n == 0) {
-    int dev = 0;
-    cudaGetDevice(&dev);
     cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev);
     if (n <= 0) n = 148;
+    cache[dev] = n;
   }
   return n;
 }
@@ -129,6 +132,7 @@ int fill_conv(const rsg_conv_desc& d, const RunCtx& c, int N, ConvP* p) {
   p->nres = d.nres;
   for (int q = 0; q < d.nres; ++q) p->res[q] = resolve_res(d.res[q], c);
   p->relu = d.relu;
+  p->force = d.engine == 2;
   p->N = N;
   p->M = (long long)N * d.Hout * d.Wout;
   RSG_REQUIRE(p->in && p->w && p->bias, "conv: unresolved in/w/bias pointer");

@@ -202,6 +202,25 @@ def add_rsgnet_heads(net, spec, c0):
     net.limbs_net = conv_bn(hc, hc, 3, relu=True)
 
 
+_HEAD_GAIN = {'predict_contact_net.1.weight': 0.03, 'type_conv.1.weight': 0.3, 'limbs_net.1.weight': 0.2,
+              'predict_net.1.weight': 0.3}
+
+
+def _norm_gain(name):
+    """Scale of a synthetic BN weight.  Eval-mode BN with synthetic running statistics does not normalise, so a
+    He-initialised residual network doubles its variance at every block and quadruples it at every fuse sum: after
+    8 HighResolutionModules the activations were O(1e5) and every sigmoid downstream (TRP affinity, limbs) saturated
+    to a 0/1 mask -- a vacuous parity check.  Like a trained network (zero-init-residual-style small last gammas),
+    the last BN of a residual branch and the BNs of the fuse paths get small weights, which keeps every stage O(1)."""
+    if '.branches.' in name and name.endswith('.bn2.weight'):
+        return 0.15
+    if name.startswith('layer1.') and name.endswith('.bn3.weight'):
+        return 0.2
+    if '.fuse_layers.' in name:
+        return 0.12
+    return _HEAD_GAIN.get(name, 1.0)
+
+
 def synth_state_dict(module, seed=0):
     """Deterministic, platform-independent, 'trained-like' weights for tests and the bench:
     He-scaled conv/linear weights, BN statistics and affine terms spread over realistic ranges so
@@ -233,7 +252,7 @@ def synth_state_dict(module, seed=0):
             is_norm = (owner + '.running_mean') in sd or owner.endswith('relation_head.W.1') \
                 or owner.endswith('relation_head.W.1.1')
             if is_norm and leaf == 'weight':
-                v = rs.uniform(0.5, 1.5, shape)
+                v = rs.uniform(0.5, 1.5, shape) * _norm_gain(name)
             else:
                 v = rs.normal(0, 0.1, shape)
         else:

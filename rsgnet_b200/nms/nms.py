@@ -56,7 +56,10 @@ def oks_nms_batched(kpts, scores, areas, img_offsets, thresh, sigmas=None, devic
         _lib.check(_lib.lib().rsg_oks_nms(_lib.stream_ptr(device), _p(k), _p(s), _p(a), _p(off),
                                           n_imgs, max_per, _p(sg), K, float(thresh), _p(keep),
                                           _p(counts), *_vis(in_vis_thre)))
-    return keep[:n].cpu().numpy(), counts.cpu().numpy()
+    counts_np = counts.cpu().numpy()
+    if (counts_np < 0).any():
+        raise _lib.RsgError('oks_nms: an image holds more detections than max_per_img')
+    return keep[:n].cpu().numpy(), counts_np
 
 
 def oks_iou(g, d, a_g, a_d, sigmas=None, in_vis_thre=None):
@@ -132,7 +135,10 @@ def soft_oks_nms_batched(kpts, scores, areas, img_offsets, thresh, sigmas=None, 
         _lib.check(_lib.lib().rsg_soft_oks_nms(_lib.stream_ptr(device), _p(k), _p(s), _p(a), _p(off), n_imgs, max_per,
                                                _p(sg), K, float(thresh), int(max_dets), _p(keep), _p(counts),
                                                *_vis(in_vis_thre)))
-    return keep.cpu().numpy(), counts.cpu().numpy()
+    counts_np = counts.cpu().numpy()
+    if (counts_np < 0).any():
+        raise _lib.RsgError('soft_oks_nms: an image holds more detections than max_per_img')
+    return keep.cpu().numpy(), counts_np
 
 
 def soft_oks_nms(kpts_db, thresh, sigmas=None, in_vis_thre=None):
@@ -147,3 +153,79 @@ def soft_oks_nms(kpts_db, thresh, sigmas=None, in_vis_thre=None):
     keep, counts = soft_oks_nms_batched(kpts, scores, areas, np.array([0, len(kpts_db)], np.int32), thresh, sigmas,
                                         in_vis_thre=in_vis_thre)
     return keep[0, :int(counts[0])].astype(np.intp)
+
+
+class EvalResult:
+    """Result of evaluate_device: everything lives in ONE device buffer; `.host()` is the single D2H copy."""
+
+    def __init__(self, buf, n, layout):
+        self.buf, self.n, self._layout = buf, n, layout
+
+    def _view(self, host, name):
+        off, count, dt = self._layout[name]
+        return host[off:off + count * np.dtype(dt).itemsize].view(dt)
+
+    def device(self, name):
+        """CUDA tensor view of one output ('n_imgs', 'images', 'img_offsets', 'scores', 'keep', 'keep_counts')."""
+        off, count, dt = self._layout[name]
+        tdt = {np.int32: torch.int32, np.int64: torch.int64, np.float64: torch.float64}[dt]
+        return self.buf[off:off + count * np.dtype(dt).itemsize].view(tdt)
+
+    def host(self):
+        """One D2H copy -> dict(images i64 [n_imgs], counts i32 [n_imgs], keep i32 [sum counts] (global detection indices,
+        per image in selection order, images in first-appearance order), keep_offsets i32 [n_imgs+1] into `keep`,
+        scores f64 [n] (rescored, every detection))."""
+        h = self.buf.cpu().numpy()
+        n_imgs = int(self._view(h, 'n_imgs')[0])
+        if n_imgs < 0:
+            raise _lib.RsgError('evaluate_device: an image id equals the reserved value 0x8080808080808080')
+        off = self._view(h, 'img_offsets')[:n_imgs + 1]
+        counts = self._view(h, 'keep_counts')[:n_imgs].copy()
+        keep_all = self._view(h, 'keep')
+        keep = np.concatenate([keep_all[off[r]:off[r] + counts[r]] for r in range(n_imgs)]) if n_imgs else np.zeros(0, np.int32)
+        ko = np.zeros(n_imgs + 1, np.int32)
+        ko[1:] = np.cumsum(counts)
+        return dict(images=self._view(h, 'images')[:n_imgs].copy(), counts=counts, keep=keep.astype(np.int32), keep_offsets=ko,
+                    scores=self._view(h, 'scores')[:self.n].copy())
+
+
+def evaluate_device(all_preds, all_boxes, image_ids, oks_thre, in_vis_thre, sigmas=None, soft_nms=False, max_dets=20,
+                    device=None):
+    """dataset.evaluate() up to the kept lists, on the device in one call (crowdpose.py:1272-1324, coco.py:1227-1277):
+    group by image (first-appearance order) -> rescore -> (soft-)OKS-NMS per image -> compacted keep lists.
+    all_preds f32 [N,K,3] (x, y, maxval -- what function.py:452-453 accumulates; a CUDA tensor stays on the device),
+    all_boxes f64 [N,6] (area at 4, box score at 5), image_ids int64 [N] in any order.  Returns an EvalResult."""
+    _lib.require_cuda()
+    device = torch.device(device or (all_preds.device if isinstance(all_preds, torch.Tensor) and all_preds.is_cuda else 'cuda'))
+
+    def to(a, tdt, ndt):
+        t = a if isinstance(a, torch.Tensor) else torch.from_numpy(np.ascontiguousarray(a, dtype=ndt))
+        return t.to(device, tdt).contiguous()
+    p = to(all_preds, torch.float32, np.float32)
+    b = to(all_boxes, torch.float64, np.float64)
+    ids = to(image_ids, torch.int64, np.int64)
+    n, K = int(p.shape[0]), int(p.shape[1])
+    assert p.dim() == 3 and p.shape[2] == 3 and tuple(b.shape) == (n, 6) and tuple(ids.shape) == (n,)
+    if sigmas is None or not isinstance(sigmas, np.ndarray):
+        sigmas = COCO_SIGMAS
+    assert len(sigmas) == K, f'{len(sigmas)} sigmas for K={K} key points'
+    sg = torch.from_numpy(np.ascontiguousarray(sigmas, np.float64)).to(device)
+    N = max(n, 1)
+    layout, off = {}, 0
+    for name, count, dt in (('n_imgs', 2, np.int32), ('images', N, np.int64), ('scores', N, np.float64),
+                            ('img_offsets', N + 1, np.int32), ('keep', N, np.int32), ('keep_counts', N, np.int32)):
+        layout[name] = (off, count, dt)
+        off += (count * np.dtype(dt).itemsize + 7) // 8 * 8
+    buf = torch.zeros(off, dtype=torch.uint8, device=device)
+    ws_bytes = C.c_size_t()
+    _lib.check(_lib.lib().rsg_evaluate_workspace_bytes(n, C.byref(ws_bytes)))
+    ws = torch.empty(ws_bytes.value, dtype=torch.uint8, device=device)
+    ptr = lambda name: C.c_void_p(buf.data_ptr() + layout[name][0])
+    with torch.cuda.device(device):
+        _lib.check(_lib.lib().rsg_evaluate(_lib.stream_ptr(device), _p(p), _p(b), _p(ids), n, K, _p(sg), float(in_vis_thre),
+                                           float(oks_thre), int(bool(soft_nms)), int(max_dets), _p(ws), ws_bytes.value,
+                                           ptr('n_imgs'), ptr('images'), ptr('img_offsets'), ptr('scores'), ptr('keep'),
+                                           ptr('keep_counts')))
+    res = EvalResult(buf, n, layout)
+    res._keepalive = (p, b, ids, sg, ws)
+    return res

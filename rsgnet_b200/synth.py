@@ -94,6 +94,37 @@ def detections(n_imgs, per_img, k, seed=3, ragged=False):
     return kpts, scores, areas, offsets
 
 
+def evaluate_inputs(n_imgs, per_img, k, seed=13, ragged=True, zero_frac=0.03):
+    """What rsgnet_validate hands to dataset.evaluate() (function.py:376-380, 452-458, 479): all_preds f32 [N,k,3]
+    (image-space x, y, maxval), all_boxes f64 [N,6] (centre, scale, area = prod(scale*200) computed in fp32, box score)
+    and one image id per detection -- with the detections of an image NOT contiguous (the loader order is arbitrary), a
+    few detections whose maxvals all sit below IN_VIS_THRE (rescored to exactly 0: score ties, only in images with at most
+    16 detections where NumPy's argsort is a stable insertion sort) and maxvals straddling the threshold.
+    all_boxes[:, 0] carries the detection's own index (the centre is unused by rescoring and NMS), so that the
+    reference's output dicts can be mapped back."""
+    kpts, _, _, off = detections(n_imgs, per_img, k, seed=seed, ragged=ragged)
+    rs = np.random.RandomState(seed + 500)
+    n = kpts.shape[0]
+    img_of = np.repeat(np.arange(n_imgs), np.diff(off))
+    counts = np.diff(off)
+    mv = rs.uniform(0.0, 1.0, (n, k)).astype(np.float32)
+    mv[rs.uniform(size=(n, k)) < 0.1] = np.float32(0.2)               # exactly at the threshold: not visible (strict >)
+    zero = (rs.uniform(size=n) < zero_frac) & (counts[img_of] <= 16)
+    mv[zero] = rs.uniform(0.0, 0.19, (int(zero.sum()), k)).astype(np.float32)
+    kpts[:, :, 2] = mv
+    perm = rs.permutation(n)                                          # interleave the images
+    kpts, img_of = kpts[perm], img_of[perm]
+    sc = rs.uniform(0.3, 4.0, (n, 2)).astype(np.float32)
+    boxes = np.zeros((n, 6))
+    boxes[:, 0] = np.arange(n)
+    boxes[:, 1] = rs.uniform(20, 600, n).astype(np.float32)
+    boxes[:, 2:4] = sc
+    boxes[:, 4] = np.prod(sc * 200, 1)
+    boxes[:, 5] = rs.uniform(0.05, 1.0, n)
+    image_ids = (100000 + 7 * img_of).astype(np.int64)
+    return np.ascontiguousarray(kpts), boxes, image_ids
+
+
 def images(n, seed=7, hw_range=((120, 480), (160, 640))):
     """n uint8 HWC "photos" of different sizes: smooth colour waves + blobs + noise (so that bilinear taps differ and
     the fixtures compress), plus the person boxes (centre, scale) the loader would crop: some far inside, some

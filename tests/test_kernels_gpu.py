@@ -11,9 +11,8 @@ from rsgnet_b200 import _engine, _lib
 from rsgnet_b200._engine import PlanBuilder, View
 
 pytestmark = pytest.mark.gpu
-# unit tests force the tcgen05 kernel (engine=2) also on maps smaller than its 16x8 patch
-import os
-os.environ['RSG_TC5_ANYSIZE'] = '1'
+# No environment switches: engine=0 cases follow the PRODUCTION routing (small maps -> conv_mma / conv_ws), engine=2
+# forces the tcgen05 kernel on any map size, engine=1 forces the mma.sync kernel, engine=3 the weight-streaming one.
 
 
 def _run(pb, n):
@@ -121,6 +120,59 @@ def test_conv_ws_vs_torch(cin, cout, k, H, W, N, nres):
     ref = F.conv2d(x.cuda(), w.cuda(), b.cuda(), 1, k // 2)
     for r in rs:
         ref = ref + r.cuda()
+    ref = F.relu(ref).cpu()
+    got = pb.tensor_of(ob)[:N, ..., 8:8 + cout].float().permute(0, 3, 1, 2).cpu()
+    err = (got - ref).abs().max().item()
+    assert err <= 2e-2 * max(ref.abs().max().item(), 1.0), err
+    assert torch.all(pb.tensor_of(ob)[:N, ..., :8] == 7.0) and torch.all(pb.tensor_of(ob)[:N, ..., 8 + cout:] == 7.0)
+    _lib.lib().rsg_plan_destroy(h)
+
+
+MMA_CASES = [
+    # Cin, Cout, k, stride, Hin, Win, nres, shifts  (engine=1: every shape the production plan of RSGNet-W32 sends to
+    # the mma.sync kernel -- the 8x6-output layers of stage 3/4 and transition3)
+    (128, 256, 3, 2, 16, 12, 3, (0, 0, 0)),     # stage4 fuse_layers.3.2 + three residual terms
+    (128, 256, 3, 2, 16, 12, 0, ()),            # transition3
+    (64, 256, 3, 2, 16, 12, 0, ()),             # stage4 fuse_layers.3.1.1
+    (32, 256, 3, 2, 16, 12, 0, ()),             # stage4 fuse_layers.3.0.2
+    (256, 32, 1, 1, 8, 6, 0, ()),               # stage4 fuse_layers.0.3
+    (256, 64, 1, 1, 8, 6, 0, ()),               # stage4 fuse_layers.1.3
+    (256, 128, 1, 1, 8, 6, 0, ()),              # stage4 fuse_layers.2.3
+    (192, 384, 3, 2, 24, 18, 3, (0, 0, 0)),     # W48 stage4 fuse_layers.3.2
+    (384, 48, 1, 1, 12, 9, 0, ()),              # W48 stage4 fuse_layers.0.3
+    (24, 32, 3, 1, 16, 12, 0, ()),              # odd channel count (Cin % 16 != 0)
+]
+
+
+@pytest.mark.parametrize('cin,cout,k,stride,H,W,nres,shifts', MMA_CASES)
+def test_conv_mma_production_shapes_vs_torch(cin, cout, k, stride, H, W, nres, shifts):
+    N = 7
+    g = torch.Generator().manual_seed(cin * 5 + cout + k + nres)
+    x = torch.randn(N, cin, H, W, generator=g).bfloat16().float()
+    w = (torch.randn(cout, cin, k, k, generator=g) / (cin * k * k) ** 0.5).bfloat16().float()
+    b = torch.randn(cout, generator=g) * 0.1
+    Ho, Wo = (H - 1) // stride + 1, (W - 1) // stride + 1
+    pb = PlanBuilder(N, reuse=False)
+    xin = pb.buf('x', H, W, cin + 8)
+    res, rts = [], []
+    for i in range(nres):
+        rb = pb.buf(f'r{i}', Ho >> shifts[i], Wo >> shifts[i], cout)
+        res.append((View(rb), shifts[i]))
+        rts.append((rb, torch.randn(N, cout, Ho >> shifts[i], Wo >> shifts[i], generator=g).bfloat16().float(), shifts[i]))
+    ob = pb.buf('o', Ho, Wo, cout + 16)
+    pb.conv(View(xin, 8, cin), w.double().numpy(), b.double().numpy(), stride=stride, relu=True,
+            dst=View(ob, 8, cout), res=res, engine=1)
+    h = _run(pb, N)
+    pb.tensor_of(xin)[:N, ..., 8:] = x.permute(0, 2, 3, 1).cuda().bfloat16()
+    pb.tensor_of(xin)[:N, ..., :8] = 1e4
+    for rb, r, _ in rts:
+        pb.tensor_of(rb)[:N] = r.permute(0, 2, 3, 1).cuda().bfloat16()
+    pb.tensor_of(ob).fill_(7.0)
+    _exec(h, N)
+    ref = F.conv2d(x.cuda(), w.cuda(), b.cuda(), stride, k // 2)
+    for _, r, sh in rts:
+        r = r.cuda()
+        ref = ref + (F.interpolate(r, scale_factor=2 ** sh, mode='nearest') if sh else r)
     ref = F.relu(ref).cpu()
     got = pb.tensor_of(ob)[:N, ..., 8:8 + cout].float().permute(0, 3, 1, 2).cpu()
     err = (got - ref).abs().max().item()

@@ -20,24 +20,38 @@ TOL = 0.03
 
 
 def _limbs_ok(got, ref, logits=None, tol=0.05):
-    """limbs_scores = sigmoid(logits); with the synthetic weights the logits are O(1e5), so the map is a
-    0/1 mask and a bf16-level relative error flips the pixels (sometimes a whole map) whose logit is ~0.
-    The bar is therefore stated where every other output's bar is stated -- on the pre-sigmoid values:
-    with the fp32 oracle logits l, sigmoid is monotone, so |l_got - l| <= tol * max|l| is equivalent to
-    sigmoid(l - tol*max|l|) <= got <= sigmoid(l + tol*max|l|), checked element-wise.  Against the
-    reference fixture (outputs only) the maps are additionally compared as masks (>= 95 % within 0.02)."""
+    """limbs_scores = sigmoid(up2(logits)) (pose_rsgnet.py:1005-1013).  The synthetic weights keep the logits O(1)
+    (rsgnet_b200/models/_params.py:_norm_gain), so the map is NOT a saturated 0/1 mask and is compared like every other
+    output: max|got - ref| <= tol * max|ref| -- and, stricter, on the PRE-sigmoid values against the fp32 oracle
+    logits l:  max|logit(got) - l| <= tol * max|l|."""
     got, ref = np.asarray(got, np.float64), np.asarray(ref, np.float64)
-    frac = float((np.abs(got - ref) <= 0.02).mean())
-    print(f'limbs mask agreement {frac:.5f}')
-    ok = frac >= 0.95
+    e = float(np.abs(got - ref).max() / np.abs(ref).max())
+    sat = float(((ref < 1e-3) | (ref > 1 - 1e-3)).mean())
+    print(f'limbs_scores rel err {e:.5f}, saturated fraction {sat:.4f}')
+    ok = e <= tol and sat < 0.2
     if logits is not None:
         l = np.asarray(logits, np.float64)
-        band = tol * np.abs(l).max()
-        sig = lambda v: 0.5 * (1.0 + np.tanh(0.5 * v))
-        inside = (got >= sig(l - band) - 1e-3) & (got <= sig(l + band) + 1e-3)
-        print(f'limbs inside the logit band: {inside.mean():.6f}')
-        ok = ok and bool(inside.all())
+        g = np.clip(got, 1e-7, 1 - 1e-7)
+        el = float(np.abs(np.log(g / (1 - g)) - l).max() / np.abs(l).max())
+        print(f'limbs logits rel err {el:.5f} (max|l| = {np.abs(l).max():.3f})')
+        ok = ok and el <= tol and np.abs(l).max() < 12.0
     return ok
+
+
+def _heatmap_report(got, ref, tag):
+    """What a heat-map error means for the decode: error normalised by each map's own dynamic range, arg-max agreement
+    and key-point displacement (in heat-map pixels) of the bf16 pipeline against the fp32 reference maps."""
+    n, k, h, w = ref.shape
+    g, r = got.reshape(n * k, -1).astype(np.float64), ref.reshape(n * k, -1).astype(np.float64)
+    rng = r.max(1) - r.min(1)
+    per_map = np.abs(g - r).max(1) / np.maximum(rng, 1e-12)
+    ig, ir = g.argmax(1), r.argmax(1)
+    disp = np.hypot(ig % w - ir % w, ig // w - ir // w)
+    rep = dict(per_map_norm_err_max=float(per_map.max()), per_map_norm_err_mean=float(per_map.mean()),
+               argmax_agree=float((ig == ir).mean()), disp_le1=float((disp <= 1.0).mean()),
+               disp_le2=float((disp <= 2.0).mean()), disp_max=float(disp.max()))
+    print(tag, 'heat-map decode report', {a: round(b, 4) for a, b in rep.items()})
+    return rep
 
 
 def _nchw(t):
@@ -101,21 +115,51 @@ def test_tiny_models_per_stage(golden_dir, key, seed):
     assert torch.equal(h2, heat)
 
 
+TAP_OF = {'layer1': 'layer1', 'stage2.0': 'stage2.0', 'stage2.1': 'stage2.1', 'stage3.0': 'stage3.0', 'stage3.1': 'stage3.1',
+          'stage3.2': 'stage3.2', 'stage4.0': 'stage4.0', 'vis_conv': 'vis', 'type_conv': 'type',
+          'predict_contact_net': 'final_vis', 'kpt_net': 'kpt_net', 'predict_net': 'kpt_feat'}
+FULL_TOL = 0.05
+
+
 @pytest.mark.parametrize('key,seed', [('w32_coco', 3), ('w32_crowdpose', 4), ('hrnet_w32_coco', 5),
                                       ('w48_coco_384', 6)])
 def test_full_models_vs_reference_golden(golden_dir, key, seed):
+    """Full-depth networks under the PRODUCTION kernel routing (no environment switches anywhere in the test suite)
+    against the outputs AND the per-stage taps of the unmodified reference (oracle/gen_golden.py: forward hooks on the
+    reference's top-level modules): max-abs error per stage relative to that stage's max|ref|."""
     g = np.load(os.path.join(golden_dir, f'model_{key}.npz'))
     cfg, net, sd = build(key, seed)
-    x = crops(cfg, int(g['batch']), seed + 11).cuda()
+    B = int(g['batch'])
+    x = crops(cfg, B, seed + 11).cuda()
     sub = int(g['sub'])
     out = net(x)
     if cfg.MODEL.NAME == 'pose_hrnet':
         outs = {'heatmaps': out}
     else:
         outs = dict(zip(('multi_kpt_scores', 'kpt_scores', 'limbs_scores', 'relation_scores'), out))
+    # the same plan with every buffer kept alive (reuse=False changes memory placement only, not the routing)
+    eng = _engine.Engine(net, 'cuda', chunk=B, reuse=False)
+    heat = torch.empty(eng.out_shapes(B)[_engine.EXT_HEAT], device='cuda')
+    eng.run(x, heat, B, B)
+    torch.cuda.synchronize()
+    main = out if cfg.MODEL.NAME == 'pose_hrnet' else out[1]
+    assert torch.equal(heat, main)
+    stage_rep = {}
+    for ref_name, tap in TAP_OF.items():
+        if 'tap.' + ref_name not in g.files or tap not in eng.info['taps']:
+            continue
+        got = _nchw(eng.pb.tensor_of(eng.info['taps'][tap])[:B]).reshape(-1)
+        ref = g['tap.' + ref_name]
+        got = got[::sub] if got.size > 65536 else got
+        assert got.shape == ref.shape, (ref_name, got.shape, ref.shape)
+        stage_rep[ref_name] = float(np.abs(got - ref).max() / float(g['tapabsmax.' + ref_name]))
+    print(key, 'per-stage max-abs error / max|ref|:', {k: f'{v:.4f}' for k, v in stage_rep.items()})
+    assert len(stage_rep) >= (7 if cfg.MODEL.NAME == 'pose_hrnet' else 11)
+    for nm, e in stage_rep.items():
+        assert e <= FULL_TOL, (nm, e)
     rep = {}
     logits = None
-    if 'limbs_scores' in outs:      # fp32 oracle logits for the rigorous limbs bar (see _limbs_ok)
+    if 'limbs_scores' in outs:      # fp32 oracle logits for the pre-sigmoid limbs bar (see _limbs_ok)
         st = {}
         model_oracle.forward(sd, cfg, x.cpu(), stages=st)
         logits = st['limbs_logits'].reshape(-1).numpy()
@@ -129,10 +173,15 @@ def test_full_models_vs_reference_golden(golden_dir, key, seed):
         rep[nm] = float(np.abs(got - ref).max() / float(g['absmax.' + nm]))
         if nm == 'limbs_scores':
             lg = logits.reshape(got.shape) if got.size == logits.size else logits[::sub]
-            rep[nm] = 0.0 if _limbs_ok(got, ref, lg, 0.05) else 1.0
+            assert _limbs_ok(got, ref, lg, FULL_TOL)
+        if nm == 'relation_scores':           # not a saturated mask: the TRP affinity is genuinely exercised
+            assert float(((ref > 1e-3) & (ref < 1 - 1e-3)).mean()) > 0.5
     print(key, {k: f'{v:.4f}' for k, v in rep.items()})
     for nm, e in rep.items():
-        assert e <= 0.05, (nm, e)
+        assert e <= FULL_TOL, (nm, e)
+    hm_name = 'heatmaps' if cfg.MODEL.NAME == 'pose_hrnet' else 'kpt_scores'
+    dec = _heatmap_report(outs[hm_name].cpu().numpy(), g['out.' + hm_name], key)
+    assert dec['per_map_norm_err_max'] <= 0.25 and dec['disp_le2'] >= 0.9, dec
 
 
 def test_flip_batch_equals_two_forwards():

@@ -206,3 +206,73 @@ def test_in_vis_thre_vs_reference(golden_dir, tag):
     db = [dict(keypoints=kb[j], score=sb[j], area=ab[j]) for j in range(len(sb))]
     assert list(soft_oks_nms(db, 0.5, sig, 0.4)) == list(g['vis_soft_big_keep'])
     assert oks_nms(db, 0.9, sig, in_vis_thre=0.4) == [int(v) for v in nms_oracle.oks_nms(db, 0.9, sig, 0.4)]
+
+
+@pytest.mark.parametrize('tag', ['crowdpose', 'coco'])
+def test_evaluate_device_vs_reference(golden_dir, tag):
+    """evaluate_device (grouping + rescoring + (soft-)OKS-NMS in one device call) against the UNMODIFIED reference's
+    dataset.evaluate() (crowdpose.py:1255-1324 / coco.py:1210-1277) on interleaved detections: image order, kept
+    detections in selection order and the rescored values, all bit-exact."""
+    from rsgnet_b200.nms.nms import evaluate_device
+    g = _load(golden_dir, f'evaluate_{tag}.npz')
+    k = int(g['k'])
+    sig = nms_oracle.CROWDPOSE_SIGMAS if tag == 'crowdpose' else None
+    preds, boxes, ids = synth.evaluate_inputs(int(g['n_imgs']), int(g['per_img']), k, seed=int(g['seed']))
+    for soft, sfx in ((False, ''), (True, '_soft')):
+        out = evaluate_device(preds, boxes, ids, float(g['oks_thre']), float(g['in_vis_thre']), sig, soft_nms=soft).host()
+        assert np.array_equal(out['images'], g['images' + sfx])
+        assert np.array_equal(out['counts'], g['counts' + sfx])
+        assert np.array_equal(out['keep'], g['keep' + sfx])
+        assert np.array_equal(out['scores'][out['keep']], g['scores' + sfx])
+    # every detection's rescored value equals the stand-alone rescoring entry point and the oracle
+    every = rescore(preds[:, :, 2], boxes[:, 5], float(g['in_vis_thre']))
+    assert np.array_equal(out['scores'], every)
+    assert np.array_equal(every[:64], np.array([nms_oracle.rescore(boxes[i, 5], preds[i, :, 2], float(g['in_vis_thre']))
+                                                for i in range(64)]))
+
+
+def test_evaluate_device_large_and_edge_cases():
+    """100 k detections / 5000 images (BASELINE.json config 4), shuffled: equals the oracle's evaluate() on the same
+    inputs; plus an empty call, a single detection, one image holding everything and NaN scores."""
+    from rsgnet_b200.nms.nms import evaluate_device
+    preds, boxes, ids = synth.evaluate_inputs(5000, 20, 17, seed=31, ragged=False)
+    out = evaluate_device(preds, boxes, ids, 0.9, 0.2).host()
+    images, counts, keep, scores = nms_oracle.evaluate(preds, boxes, ids, None, 0.2, 0.9)
+    assert np.array_equal(out['images'], images) and np.array_equal(out['counts'], counts)
+    assert np.array_equal(out['keep'], keep) and np.array_equal(out['scores'][keep], scores)
+    # device-resident inputs, one big image (600 detections: far more than any shared-memory table would hold)
+    p1, b1, _ = synth.evaluate_inputs(1, 600, 14, seed=5, ragged=False)
+    one = evaluate_device(torch.from_numpy(p1).cuda(), torch.from_numpy(b1).cuda(), torch.zeros(600, dtype=torch.int64).cuda(),
+                          0.9, 0.2, nms_oracle.CROWDPOSE_SIGMAS).host()
+    im, ct, kp, sc = nms_oracle.evaluate(p1, b1, np.zeros(600, np.int64), nms_oracle.CROWDPOSE_SIGMAS, 0.2, 0.9)
+    assert np.array_equal(one['keep'], kp) and np.array_equal(one['counts'], ct)
+    empty = evaluate_device(np.zeros((0, 17, 3), np.float32), np.zeros((0, 6)), np.zeros(0, np.int64), 0.9, 0.2).host()
+    assert len(empty['images']) == 0 and len(empty['keep']) == 0
+    single = evaluate_device(preds[:1], boxes[:1], ids[:1], 0.9, 0.2).host()
+    assert list(single['keep']) == [0] and list(single['counts']) == [1]
+    # NaN box scores: ranked like NumPy's argsort()[::-1] ranks them (first), every detection gets exactly one rank
+    bn = boxes[:40].copy()
+    bn[[3, 17], 5] = np.nan
+    nan = evaluate_device(preds[:40], bn, np.zeros(40, np.int64), 2.0, 0.2).host()       # thresh 2: nothing is suppressed
+    assert sorted(nan['keep']) == list(range(40)) and list(nan['keep'][:2]) == [17, 3]
+
+
+def test_oks_nms_refuses_oversized_image_and_orders_nan_like_numpy():
+    import ctypes as C
+    from rsgnet_b200 import _lib
+    kpts, scores, areas, off = synth.detections(1, 30, 17, seed=2)
+    scores = scores.copy()
+    scores[5] = np.nan
+    keep, counts = oks_nms_batched(kpts, scores, areas, off, 2.0)
+    assert sorted(keep[:30]) == list(range(30)) and keep[0] == 5
+    assert list(keep[:30]) == [int(v) for v in scores.argsort()[::-1]]
+    # the device-side guard: max_per_img smaller than the image -> keep_counts = -1, nothing written out of bounds
+    dev = torch.device('cuda')
+    t = lambda a, dt: torch.from_numpy(np.ascontiguousarray(a, dt)).to(dev)
+    k_, s_, a_, o_ = t(kpts, np.float32), t(np.nan_to_num(scores), np.float64), t(areas, np.float64), t(off, np.int32)
+    sg = t(nms_oracle.COCO_SIGMAS, np.float64)
+    kp = torch.full((30,), -7, dtype=torch.int32, device=dev)
+    ct = torch.zeros(1, dtype=torch.int32, device=dev)
+    p = lambda x: C.c_void_p(x.data_ptr())
+    _lib.check(_lib.lib().rsg_oks_nms(_lib.stream_ptr(dev), p(k_), p(s_), p(a_), p(o_), 1, 8, p(sg), 17, 0.9, p(kp), p(ct), 0, 0.0))
+    assert int(ct.item()) == -1 and bool((kp == -7).all())
