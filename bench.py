@@ -106,7 +106,7 @@ def build_model(device):
     return cfg, net.to(device).eval(), sd
 
 
-def cpu_reference_step(sd, cfg, x, c, s):
+def cpu_reference_step(sd, cfg, x, c, s, want_maps=False):
     """One bounded sample of the reference's CPU path (oracle port): 2 forwards, flip-average,
     get_final_preds."""
     from oracle import decode_oracle, model_oracle
@@ -114,6 +114,8 @@ def cpu_reference_step(sd, cfg, x, c, s):
     a = model_oracle.forward(sd, cfg, x)[1].numpy()
     b = model_oracle.forward(sd, cfg, x.flip(3))[1].numpy()
     avg = decode_oracle.flip_average(a, b, presets.flip_pairs_for(k), shift=True)
+    if want_maps:
+        return decode_oracle.get_final_preds(True, avg, c, s) + (avg,)
     return decode_oracle.get_final_preds(True, avg, c, s)
 
 
@@ -593,17 +595,33 @@ def main():
         cores = len(os.sched_getaffinity(0))
         torch.set_num_threads(cores)
         n = 4
-        o_preds, o_mv = cpu_reference_step(sd, cfg, x_host[:n].clone(), c_np[:n], s_np[:n])
+        from oracle import decode_oracle
+        o_preds, o_mv, o_avg = cpu_reference_step(sd, cfg, x_host[:n].clone(), c_np[:n], s_np[:n], want_maps=True)
         g_preds, g_mv = preds_host[:n].numpy(), mv_host[:n].numpy()
-        # image px -> heat-map px: transform_preds scales by scale[0] * 200 / heat_w on both axes (transforms.py:57-103)
+        # (1) heat-maps of the timed step (bf16 pipeline) against the fp32 oracle maps, flip-averaged the reference's way
+        hm, hf = pipe.heat[:n].cpu().numpy(), pipe.heat[B:B + n].cpu().numpy()
+        g_avg = decode_oracle.flip_average(hm, hf, presets.flip_pairs_for(K), shift=True)
+        hm_err = float(np.abs(g_avg - o_avg).max() / np.abs(o_avg).max())
+        # (2) the decode of the timed step is bit-exact given its own heat-maps
+        d_preds, d_mv = decode_oracle.get_final_preds(True, g_avg, c_np[:n], s_np[:n])
+        decode_exact = bool(np.array_equal(d_preds, g_preds) and np.array_equal(d_mv, g_mv))
+        # (3) arg-max agreement with the fp32 maps; a differing arg-max must be a near-tie of the REFERENCE map (its two
+        # candidates closer than twice the map's own error), i.e. explained by the stated heat-map tolerance
+        ga, oa = g_avg.reshape(n * K, -1), o_avg.reshape(n * K, -1)
+        ig, io = ga.argmax(1), oa.argmax(1)
+        rows = np.arange(n * K)
+        err_map = np.abs(ga - oa).max(1)
+        unexplained = int(((ig != io) & (oa[rows, io] - oa[rows, ig] > 2.0 * err_map)).sum())
         px = (s_np[:n, 0] * 200.0 / float(pipe.spec.heat_w))[:, None]
         disp = np.hypot(g_preds[..., 0] - o_preds[..., 0], g_preds[..., 1] - o_preds[..., 1]) / px
-        mv_err = float(np.abs(g_mv - o_mv).max() / max(float(np.abs(o_mv).max()), 1e-12))
-        parity = {'crops': n, 'maxvals_rel_err': mv_err, 'kpt_disp_le_1px': float((disp <= 1.0).mean()),
-                  'kpt_disp_le_2px': float((disp <= 2.0).mean()), 'kpt_disp_max_px': float(disp.max()),
-                  'bar': 'bf16 pipeline vs fp32 oracle: maxvals within 0.05 * max, >= 90 % of the key points within 2 heat-map px '
-                         '(decode itself is bit-exact given identical heat-maps: tests/test_postproc_gpu.py)'}
-        if not (mv_err <= 0.05 and parity['kpt_disp_le_2px'] >= 0.9):
+        rng = oa.max(1) - oa.min(1)
+        parity = {'crops': n, 'heatmap_rel_err': hm_err, 'per_map_norm_err_max': float((err_map / np.maximum(rng, 1e-12)).max()),
+                  'decode_bit_exact_given_own_heatmaps': decode_exact, 'argmax_agree': float((ig == io).mean()),
+                  'unexplained_argmax_flips': unexplained, 'kpt_disp_le_1px': float((disp <= 1.0).mean()),
+                  'maxvals_rel_err': float(np.abs(g_mv - o_mv).max() / max(float(np.abs(o_mv).max()), 1e-12)),
+                  'bar': 'bf16 pipeline vs fp32 oracle: averaged heat-maps within 0.05 * max|ref|; decode bit-exact given the '
+                         'same heat-maps; every differing arg-max is a near-tie of the fp32 map (gap <= 2 x that map\'s error)'}
+        if not (hm_err <= 0.05 and decode_exact and unexplained == 0):
             raise SystemExit(f'bench: parity check of the timed outputs failed: {parity}')
 
     # ---- CPU baseline: BASELINE.json configs[0] (RSGNet-W32 256x192 COCO K=17, batch 32, the reference's CPU path)

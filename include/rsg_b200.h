@@ -207,6 +207,15 @@ int rsg_plan_add_maxpool(rsg_plan*, rsg_ref in, int cs, int co, int H, int W, in
  * x, g, y are bf16 [N,S,C] views with channel strides/offsets. */
 int rsg_plan_add_attention(rsg_plan*, rsg_ref x, int x_cs, int x_co, rsg_ref g, int g_cs,
                            int g_co, rsg_ref y, int y_cs, int y_co, int S, int C);
+/* The same with y ALSO / INSTEAD as dense fp32 [N,S,C] (y_f32 non-null: the tcgen05 kernel writes fp32 only; y_bf16 is
+ * then just the scratch of the mma.sync fallback and may be null when the views are 16-byte aligned), and the fp32 tail
+ * of the TRP (association.py:236-245, 300): out = GroupNorm(8, C)(W y + b) with W f32 [C][C], b / gamma / beta f32 [C].
+ * y is a sum of S sigmoid-weighted terms whose mean dwarfs its spread over the positions and GroupNorm removes the
+ * mean, so this stretch is kept in fp32 end to end (bf16 storage of y or z costs ~10 % of the normalised signal). */
+int rsg_plan_add_attention_f32(rsg_plan*, rsg_ref x, int x_cs, int x_co, rsg_ref g, int g_cs, int g_co, rsg_ref y_bf16,
+                               int y_cs, int y_co, rsg_ref y_f32, int S, int C);
+int rsg_plan_add_trp_tail(rsg_plan*, rsg_ref y_f32, rsg_ref w, rsg_ref bias, rsg_ref gamma, rsg_ref beta, int groups,
+                          float eps, rsg_ref out, int out_cs, int out_co, int S, int C);
 /* relation_scores f32 [N,S,S] = sigmoid(x x^T) (4th output of RSGNet.forward). */
 int rsg_plan_add_relation_scores(rsg_plan*, rsg_ref x, int x_cs, int x_co, int S, int C,
                                  rsg_ref out);

@@ -321,9 +321,18 @@ def emit(builder, plan):
                                               src.C, _ref(p['dst'], cp)))
         elif kind == 'attention':
             x, g, y = p['x'], p['g'], p['y']
-            _lib.check(L.rsg_plan_add_attention(plan, _ref(x, cp), x.buf.C, x.co, _ref(g, cp),
-                                                g.buf.C, g.co, _ref(y, cp), y.buf.C, y.co,
-                                                x.H * x.W, x.C))
+            if p.get('y32') is not None:
+                _lib.check(L.rsg_plan_add_attention_f32(plan, _ref(x, cp), x.buf.C, x.co, _ref(g, cp), g.buf.C, g.co,
+                                                        _ref(y, cp), y.buf.C, y.co, _ref(p['y32'], cp), x.H * x.W, x.C))
+            else:
+                _lib.check(L.rsg_plan_add_attention(plan, _ref(x, cp), x.buf.C, x.co, _ref(g, cp),
+                                                    g.buf.C, g.co, _ref(y, cp), y.buf.C, y.co,
+                                                    x.H * x.W, x.C))
+        elif kind == 'trptail':
+            y32, o = p['y32'], p['out']
+            _lib.check(L.rsg_plan_add_trp_tail(plan, _ref(y32, cp), _ref(p['w'], cp), _ref(p['bias'], cp),
+                                               _ref(p['gamma'], cp), _ref(p['beta'], cp), p['groups'], EPS,
+                                               _ref(o, cp), o.buf.C, o.co, p['S'], p['C']))
         elif kind == 'relscores':
             x = p['x']
             _lib.check(L.rsg_plan_add_relation_scores(plan, _ref(x, cp), x.buf.C, x.co, x.H * x.W,
@@ -626,23 +635,29 @@ def build_network(pb, sd, spec):
     g = View(pb.buf('trp_g', xs.H, xs.W, C0))
     pb.conv(xs, R['g.weight'], R['g.bias'], dst=g, name='relation_head.g')
     yv = View(pb.buf('trp_y', xs.H, xs.W, C0))
-    pb.simple('attention', dict(x=xs, g=g, y=yv), [xs.buf, g.buf], [yv.buf])
     S = xs.H * xs.W
     pb.flops_per_fwd += 2 * 2 * S * S * C0
     info['S'] = S
     info['trp_x'] = xs
+    f32 = lambda a: pb.const(np.ascontiguousarray(a, np.float32))
     if spec.relation_sub_sample:
+        pb.simple('attention', dict(x=xs, g=g, y=yv), [xs.buf, g.buf], [yv.buf])
         yu = View(pb.buf('trp_up', h, w, C0))
-        _deconv4(pb, R, 'W.0', yv, yu)
-        yv, Wt = yu, R.sub('W.1')
+        _deconv4(pb, R, 'W.0', yv, yu)                  # ConvT + BN + ReLU in between: the bf16 conv path
+        Wt = R.sub('W.1')
+        z = View(pb.buf('trp_z', h, w, C0))
+        pb.conv(yu, Wt['0.weight'], Wt['0.bias'], dst=z, name='relation_head.W')
+        pb.simple('groupnorm', dict(x=z, y=View(cat2, 0, C0), groups=8, gamma=f32(Wt['1.weight']), beta=f32(Wt['1.bias'])),
+                  [z.buf], [cat2])
     else:
+        # y -> 1x1 W -> GroupNorm stays in fp32: y's mean over the positions dwarfs its spread and GroupNorm removes it
         Wt = R.sub('W')
-    z = View(pb.buf('trp_z', h, w, C0))
-    pb.conv(yv, Wt['0.weight'], Wt['0.bias'], dst=z, name='relation_head.W')
-    pb.simple('groupnorm', dict(x=z, y=View(cat2, 0, C0), groups=8,
-                                gamma=pb.const(Wt['1.weight'].astype(np.float32)),
-                                beta=pb.const(Wt['1.bias'].astype(np.float32))),
-              [z.buf], [cat2])
+        y32 = pb.buf('trp_y32', xs.H, xs.W, C0, itemsize=4)
+        pb.simple('attention', dict(x=xs, g=g, y=yv, y32=y32), [xs.buf, g.buf], [yv.buf, y32])
+        pb.simple('trptail', dict(y32=y32, out=View(cat2, 0, C0), w=f32(Wt['0.weight'][:, :, 0, 0]), bias=f32(Wt['0.bias']),
+                                  gamma=f32(Wt['1.weight']), beta=f32(Wt['1.bias']), groups=8, S=S, C=C0,
+                                  name='relation_head.W + GroupNorm (fp32)'), [y32], [cat2])
+        pb.flops_per_fwd += 2 * 2 * C0 * C0 * S          # z is computed twice (statistics pass + output pass), on CUDA cores
 
     # ---- keypoint head (pose_rsgnet.py:991-1000)
     kf = _cbr(pb, P, View(cat2), 'kpt_net')
@@ -711,6 +726,12 @@ class Engine:
             emit(pb, self.plan)
         self.flops_per_fwd = pb.flops_per_fwd
         self.lock = threading.Lock()
+        # the activation arena, the concat buffers and the graph cache belong to this engine: runs issued from different
+        # CUDA streams are ordered against each other with an event (see run)
+        self._last_stream = None
+        self._events = [torch.cuda.Event(), torch.cuda.Event()]
+        self._ev_i = 0
+        self._static = {}        # module_forward's static input / output buffers, keyed by with_aux
 
     def __del__(self):
         try:
@@ -740,8 +761,32 @@ class Engine:
             for slot, t in aux.items():
                 ext[slot] = t.data_ptr()
         with self.lock, torch.cuda.device(self.device):
+            st = torch.cuda.current_stream(self.device)
+            if self._last_stream is not None and self._last_stream != st:
+                # another stream ran this engine last: its work must finish before the arena is overwritten
+                st.wait_event(self._events[self._ev_i])
             _lib.check(_lib.lib().rsg_plan_run(self.plan, _lib.stream_ptr(self.device), ext, N_EXT,
                                                n_fwd, n_crops, with_aux, int(use_graph)))
+            self._ev_i ^= 1
+            self._events[self._ev_i].record(st)
+            self._last_stream = st
+
+    def static_buffers(self, with_aux):
+        """Persistent input / output tensors of module_forward (pointer-stable, so the whole forward replays as one
+        CUDA graph): x [chunk,3,H,W], heat, and with_aux the three auxiliary outputs."""
+        key = bool(with_aux)
+        if key not in self._static:
+            sp, dev = self.spec, self.device
+            shapes = self.out_shapes(self.chunk)
+            base = self._static.get(False)
+            bufs = dict(base) if (key and base) else dict(
+                x=torch.empty((self.chunk, 3, sp.image_h, sp.image_w), dtype=torch.float32, device=dev),
+                heat=torch.empty(shapes[EXT_HEAT], dtype=torch.float32, device=dev))
+            if key:
+                for slot in (EXT_MULTI, EXT_LIMBS, EXT_REL):
+                    bufs[slot] = torch.empty(shapes[slot], dtype=torch.float32, device=dev)
+            self._static[key] = bufs
+        return self._static[key]
 
     def profile(self, x, heat, nb, n_crops):
         """Per-op device times of one chunk (eager, event pair around every op).
@@ -797,52 +842,164 @@ class Engine:
 
 # ---------------------------------------------------------------------------------------------
 _engines_lock = threading.Lock()
+_CHUNKS = (32, 64, 128, 256, 512)
+
+
+def _source(module):
+    """The module that owns the real parameters: a DataParallel replica (torch.nn.parallel.replicate gives it an EMPTY
+    _parameters dict and per-forward broadcast copies) points back at the module it was replicated from."""
+    return module.__dict__.get('_rsg_source') or module
 
 
 def _param_version(module):
-    return tuple((id(t), t._version) for t in list(module.parameters()) + list(module.buffers()))
+    ts = module.__dict__.get('_rsg_tensors')
+    if ts is None:
+        ts = module.__dict__['_rsg_tensors'] = list(module.parameters()) + list(module.buffers())
+    return sum(t._version for t in ts), len(ts)
 
 
 def engine_for(module, device, chunk=None):
-    """Engine cache on the module, keyed by device; invalidated when any parameter/buffer changes
-    (load_state_dict, .to(), in-place edits)."""
-    key = str(torch.device(device))
+    """Engine cache on the parameter-owning module, keyed by (device, chunk); invalidated when any parameter / buffer
+    changes (load_state_dict, .to(), train() drop the cache through EngineOwner; in-place edits bump the tensors'
+    version counters).  Safe to call from DataParallel's per-device threads."""
+    module = _source(module)
+    chunk = int(chunk or getattr(module, 'chunk', 32))
+    key = (str(torch.device(device)), chunk)
     with _engines_lock:
         cache = module.__dict__.setdefault('_rsg_engines', {})
         ver = _param_version(module)
-        chunk = chunk or getattr(module, 'chunk', 32)
         ent = cache.get(key)
-        if ent is None or ent[0] != ver or ent[1].chunk != chunk:
+        if ent is None or ent[0] != ver:
+            for k in [k for k, e in cache.items() if e[0] != ver]:
+                del cache[k]
             cache[key] = ent = (ver, Engine(module, device, chunk))
         return ent[1]
 
 
+class LazyOutput:
+    """An output of RSGNet.forward that the eval loop never reads (function.py:389 uses outputs[1] only), computed by
+    a second run of the plan WITH the auxiliary ops when it is first touched (``model.lazy_aux = True``).  Behaves like
+    the tensor it stands for: attribute access, indexing and torch.* functions materialise it."""
+
+    def __init__(self, group, slot, shape, device):
+        self._group, self._slot, self._shape, self._device = group, slot, tuple(shape), device
+
+    def materialize(self):
+        return self._group.get(self._slot)
+
+    @property
+    def shape(self):
+        return torch.Size(self._shape)
+
+    @property
+    def device(self):
+        return self._device
+
+    @property
+    def dtype(self):
+        return torch.float32
+
+    def size(self, *a):
+        return torch.Size(self._shape) if not a else self._shape[a[0]]
+
+    def dim(self):
+        return len(self._shape)
+
+    def __len__(self):
+        return self._shape[0]
+
+    def __getitem__(self, idx):
+        return self.materialize()[idx]
+
+    def __getattr__(self, name):
+        if name.startswith('__'):
+            raise AttributeError(name)
+        return getattr(self.materialize(), name)
+
+    @classmethod
+    def __torch_function__(cls, func, types, args=(), kwargs=None):
+        un = lambda a: a.materialize() if isinstance(a, LazyOutput) else a
+        args = tuple([un(v) for v in a] if isinstance(a, (list, tuple)) else un(a) for a in args)
+        return func(*args, **{k: un(v) for k, v in (kwargs or {}).items()})
+
+
+class _LazyAuxGroup:
+    """Shared state of the three lazy outputs of one forward: the (cloned) input and, once touched, the tensors."""
+
+    def __init__(self, module, x, relation_target):
+        self.module, self.x, self.target, self.out = module, x, relation_target, None
+
+    def get(self, slot):
+        if self.out is None:
+            full = _forward_impl(self.module, self.x, self.target, with_aux=True)
+            self.out = {EXT_MULTI: full[0], EXT_LIMBS: full[2], EXT_REL: full[3]}
+            self.x = None
+        return self.out[slot]
+
+
+def _forward_impl(module, x, relation_target, with_aux):
+    src = _source(module)
+    spec = src.spec
+    if x.is_cuda:
+        dev = x.device
+    else:
+        dev = module.__dict__.get('_rsg_device') or next(src.parameters()).device
+    if dev.type != 'cuda':
+        raise _lib.RsgError('move the model to a CUDA device first (model.cuda()); no CPU path')
+    B = int(x.shape[0])
+    chunk = next((c for c in _CHUNKS if c >= B), _CHUNKS[-1])
+    eng = engine_for(src, dev, chunk)
+    rsg = spec.kind == KIND_RSGNET
+    outs = []
+    with torch.cuda.device(dev):
+        st = torch.cuda.current_stream(dev)
+        graph_ok = st.cuda_stream != 0            # capture needs a non-default stream; else the same plan runs eagerly
+        for lo in range(0, B, chunk):
+            nb = min(chunk, B - lo)
+            bufs = eng.static_buffers(with_aux)
+            bufs['x'][:nb].copy_(x[lo:lo + nb], non_blocking=True)       # H2D for DataParallel's CPU scatter, else D2D
+            aux = {s: bufs[s] for s in (EXT_MULTI, EXT_LIMBS, EXT_REL)} if (rsg and with_aux) else None
+            eng.run(bufs['x'], bufs['heat'], nb, nb, aux=aux, use_graph=graph_ok)
+            # results leave the static buffers as fresh tensors (the caller keeps `output` across the flipped forward)
+            got = {EXT_HEAT: bufs['heat'][:nb].clone()}
+            if aux:
+                for s, t in aux.items():
+                    got[s] = t[:nb].clone()
+            outs.append(got)
+    cat = lambda s: outs[0][s] if len(outs) == 1 else torch.cat([o[s] for o in outs])
+    heat = cat(EXT_HEAT)
+    if not rsg:
+        return heat
+    if not with_aux:
+        return None, heat, None, None
+    rel = cat(EXT_REL)
+    if relation_target is not None:
+        rel = ((relation_target.to(dev) - rel) ** 2).mean(dim=(1, 2))
+    return cat(EXT_MULTI), heat, cat(EXT_LIMBS), rel
+
+
 def module_forward(module, x, relation_target=None):
-    """nn.Module.forward of the drop-in models: the reference's return convention."""
-    if module.training:
+    """nn.Module.forward of the drop-in models: the reference's return convention (pose_rsgnet.py:955-1021,
+    pose_hrnet.py:428-463).  The input is copied into a pointer-stable buffer and the whole forward replays as one CUDA
+    graph per (batch size, device); DataParallel replicas build their engines from the source module's parameters."""
+    src = _source(module)
+    if module.training or src.training:
         raise _lib.RsgError('rsgnet_b200 implements the inference path only: call model.eval() '
                             '(training mode needs batch-statistics BatchNorm; SURVEY.md §8f-4)')
     _lib.require_cuda()
-    dev = next(module.parameters()).device
-    if dev.type != 'cuda':
-        raise _lib.RsgError('move the model to a CUDA device first (model.cuda()); no CPU path')
-    if x.dim() != 4 or x.shape[1] != 3 or x.shape[2] != module.spec.image_h or x.shape[3] != module.spec.image_w:
-        raise ValueError(f'expected input [B,3,{module.spec.image_h},{module.spec.image_w}], got {tuple(x.shape)}')
-    x = x.to(dev, torch.float32, non_blocking=True).contiguous()
-    eng = engine_for(module, dev)
-    B = x.shape[0]
-    shapes = eng.out_shapes(B)
-    heat = torch.empty(shapes[EXT_HEAT], dtype=torch.float32, device=dev)
-    if module.spec.kind != KIND_RSGNET:
-        eng.run(x, heat, B, B)
-        return heat
-    if getattr(module, 'lazy_aux', False):
-        eng.run(x, heat, B, B)
-        return None, heat, None, None
-    aux = {s: torch.empty(shapes[s], dtype=torch.float32, device=dev)
-           for s in (EXT_MULTI, EXT_LIMBS, EXT_REL)}
-    eng.run(x, heat, B, B, aux=aux)
-    rel = aux[EXT_REL]
-    if relation_target is not None:
-        rel = ((relation_target.to(dev) - rel) ** 2).mean(dim=(1, 2))
-    return aux[EXT_MULTI], heat, aux[EXT_LIMBS], rel
+    spec = src.spec
+    if x.dim() != 4 or x.shape[1] != 3 or x.shape[2] != spec.image_h or x.shape[3] != spec.image_w:
+        raise ValueError(f'expected input [B,3,{spec.image_h},{spec.image_w}], got {tuple(x.shape)}')
+    if x.dtype != torch.float32:
+        x = x.float()
+    if spec.kind != KIND_RSGNET:
+        return _forward_impl(module, x, None, False)
+    if getattr(src, 'lazy_aux', False) and relation_target is None:
+        _, heat, _, _ = _forward_impl(module, x, None, False)
+        B, i = int(x.shape[0]), engine_for(src, heat.device, next((c for c in _CHUNKS if c >= x.shape[0]), _CHUNKS[-1])).info
+        group = _LazyAuxGroup(module, x.detach().clone(), None)
+        shp = {EXT_MULTI: (B, i['K'], spec.heat_h, spec.heat_w), EXT_LIMBS: (B, i['L'], spec.heat_h, spec.heat_w),
+               EXT_REL: (B, i['S'], i['S'])}
+        lazy = {s: LazyOutput(group, s, shp[s], heat.device) for s in shp}
+        return lazy[EXT_MULTI], heat, lazy[EXT_LIMBS], lazy[EXT_REL]
+    return _forward_impl(module, x, relation_target, True)

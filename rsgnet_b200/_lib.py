@@ -80,6 +80,10 @@ _SIGS = {
     'rsg_plan_add_maxpool': (C.c_int, [C.c_void_p, Ref] + [C.c_int] * 5 + [Ref]),
     'rsg_plan_add_attention': (C.c_int, [C.c_void_p, Ref, C.c_int, C.c_int, Ref, C.c_int, C.c_int,
                                          Ref, C.c_int, C.c_int, C.c_int, C.c_int]),
+    'rsg_plan_add_attention_f32': (C.c_int, [C.c_void_p, Ref, C.c_int, C.c_int, Ref, C.c_int, C.c_int,
+                                             Ref, C.c_int, C.c_int, Ref, C.c_int, C.c_int]),
+    'rsg_plan_add_trp_tail': (C.c_int, [C.c_void_p, Ref, Ref, Ref, Ref, Ref, C.c_int, C.c_float, Ref, C.c_int, C.c_int,
+                                        C.c_int, C.c_int]),
     'rsg_plan_add_relation_scores': (C.c_int, [C.c_void_p, Ref] + [C.c_int] * 4 + [Ref]),
     'rsg_plan_add_groupnorm': (C.c_int, [C.c_void_p, Ref, C.c_int, C.c_int, Ref, Ref, C.c_int,
                                          C.c_float, Ref, C.c_int, C.c_int, C.c_int, C.c_int]),

@@ -31,6 +31,7 @@ constexpr int AT_KV_STAGES = 3;
 
 struct AttP {
   bf16* y;
+  float* y32;                         // non-null: y as dense fp32 [N,S,C] instead (feeds the fp32 W + GroupNorm tail)
   int y_cs, y_co;
   int S, C, nblk;
   uint32_t q_bytes, kv_tile_bytes;    // one [C/8][128][8] tile
@@ -238,11 +239,20 @@ trp_attention_tc5_kernel(const __grid_constant__ AttMaps maps, const AttP p) {
       asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
       const int grow = q0 + row;
       bf16* dst = p.y + ((size_t)n * p.S + grow) * p.y_cs + p.y_co;
+      float* dst32 = p.y32 ? p.y32 + ((size_t)n * p.S + grow) * p.C : nullptr;
       for (int c0 = 0; c0 < p.C; c0 += 16) {
         uint32_t v[16];
         tmem_ld16(tq + 2u * AT_BK + (uint32_t)c0, v);
         asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-        if (grow < p.S) {
+        if (dst32) {
+          // y is a sum of S sigmoid-weighted terms: |mean| >> spread over the positions, and GroupNorm removes the mean
+          // right after the 1x1 W conv -- a bf16 y would leave 2^-9 |mean| of rounding noise on a signal of that spread
+          if (grow < p.S) {
+#pragma unroll
+            for (int k = 0; k < 4; ++k)
+              reinterpret_cast<uint4*>(dst32 + c0)[k] = make_uint4(v[4 * k], v[4 * k + 1], v[4 * k + 2], v[4 * k + 3]);
+          }
+        } else if (grow < p.S) {
           uint4 o0, o1;
           o0.x = pack_bf16x2(__uint_as_float(v[0]), __uint_as_float(v[1]));
           o0.y = pack_bf16x2(__uint_as_float(v[2]), __uint_as_float(v[3]));
@@ -284,18 +294,19 @@ int make_att_map(const bf16* base, int cs, int co, int N, int S, int C, int rows
 }  // namespace
 
 int attention_tc5_launch(cudaStream_t s, const bf16* x, int x_cs, int x_co, const bf16* g, int g_cs, int g_co,
-                         bf16* y, int y_cs, int y_co, int N, int S, int C, int* handled) {
+                         bf16* y, int y_cs, int y_co, float* y32, int N, int S, int C, int* handled) {
   *handled = 0;
   static const bool legacy = rsg_dbg_env("RSG_ATT_LEGACY") != nullptr;      // A/B switch: the mma.sync kernel
   if (legacy) return RSG_OK;
   if (C % 16 != 0 || C < 16 || C > 64 || N > 65535) return RSG_OK;
   if (x_cs % 8 != 0 || x_co % 8 != 0 || g_cs % 8 != 0 || g_co % 8 != 0 || y_cs % 8 != 0 || y_co % 8 != 0) return RSG_OK;
-  if (((uintptr_t)x | (uintptr_t)g | (uintptr_t)y) % 16 != 0) return RSG_OK;
+  if (((uintptr_t)x | (uintptr_t)g | (uintptr_t)y | (uintptr_t)y32) % 16 != 0) return RSG_OK;
+  if (!y && !y32) return RSG_OK;
   *handled = 1;
   if (N == 0 || S == 0) return RSG_OK;
   AttP p;
   memset(&p, 0, sizeof(p));
-  p.y = y; p.y_cs = y_cs; p.y_co = y_co; p.S = S; p.C = C;
+  p.y = y; p.y32 = y32; p.y_cs = y_cs; p.y_co = y_co; p.S = S; p.C = C;
   p.nblk = (S + AT_BK - 1) / AT_BK;
   p.q_bytes = (uint32_t)AT_BQ * C * 2;
   p.kv_tile_bytes = (uint32_t)AT_BK * C * 2;

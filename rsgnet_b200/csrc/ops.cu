@@ -440,6 +440,110 @@ head1x1_kernel(const bf16* __restrict__ in, int in_cs, int in_co, const bf16* __
   }
 }
 
+
+// ------------------------------------------------------------------------------------------------
+// TRP tail (association.py:236-245, 300): z = W y + b (1x1 conv C -> C), out = GroupNorm(groups, C)(z), all in fp32.
+// y = sum_j sigmoid(x_i . x_j) g_j has |mean| >> spread over the positions of a crop and GroupNorm subtracts the mean,
+// so neither y, W nor z may be rounded to bf16 on the way (2^-9 |mean| of noise on a signal of size `spread`).
+// One CTA per crop, one thread per position: pass 1 accumulates the per-group sum / sum of squares of z (fp32 per
+// thread over a few dozen values, fp64 across threads), pass 2 recomputes z (y is L2-hot; cheaper than a round trip of
+// z through HBM) and writes the normalised bf16 output.  W is read as 16-byte broadcast loads from shared memory.
+template <int C, int G>
+__global__ void __launch_bounds__(256)
+trp_tail_kernel(const float* __restrict__ y32, const float* __restrict__ w, const float* __restrict__ bias,
+                const float* __restrict__ gamma, const float* __restrict__ beta, float eps,
+                bf16* __restrict__ out, int out_cs, int out_co, int S) {
+  constexpr int groups = G, cpg = C / G;
+  __shared__ __align__(16) float sW[C * C];
+  __shared__ float sB[C], sG[C], sBe[C];
+  __shared__ double red[8][2 * G];                  // [warp][sum g, sumsq g]
+  __shared__ float gmean[G], grstd[G];
+  const int n = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  for (int i = tid; i < C * C; i += 256) sW[i] = w[i];
+  for (int i = tid; i < C; i += 256) { sB[i] = bias[i]; sG[i] = gamma[i]; sBe[i] = beta[i]; }
+  __syncthreads();
+  const float* src = y32 + (size_t)n * S * C;
+  float gs[G], gq[G];
+#pragma unroll
+  for (int g = 0; g < G; ++g) { gs[g] = 0.f; gq[g] = 0.f; }
+
+  auto compute_z = [&](int p, float* z) {
+    float yv[C];
+    const float4* yp = reinterpret_cast<const float4*>(src + (size_t)p * C);
+#pragma unroll
+    for (int k = 0; k < C / 4; ++k) {
+      const float4 v = __ldg(yp + k);
+      yv[4 * k] = v.x; yv[4 * k + 1] = v.y; yv[4 * k + 2] = v.z; yv[4 * k + 3] = v.w;
+    }
+#pragma unroll
+    for (int c = 0; c < C; ++c) {
+      float a = sB[c];
+      const float4* wr = reinterpret_cast<const float4*>(sW + c * C);
+#pragma unroll
+      for (int k = 0; k < C / 4; ++k) {
+        const float4 ww = wr[k];
+        a = fmaf(ww.x, yv[4 * k], a); a = fmaf(ww.y, yv[4 * k + 1], a);
+        a = fmaf(ww.z, yv[4 * k + 2], a); a = fmaf(ww.w, yv[4 * k + 3], a);
+      }
+      z[c] = a;
+    }
+  };
+
+  for (int p = tid; p < S; p += 256) {
+    float z[C];
+    compute_z(p, z);
+#pragma unroll
+    for (int c = 0; c < C; ++c) {
+      gs[c / cpg] += z[c];              // compile-time group index: gs / gq stay in registers
+      gq[c / cpg] = fmaf(z[c], z[c], gq[c / cpg]);
+    }
+  }
+#pragma unroll
+  for (int g = 0; g < G; ++g) {
+    double a = (double)gs[g], b = (double)gq[g];
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) { a += __shfl_xor_sync(0xffffffffu, a, o); b += __shfl_xor_sync(0xffffffffu, b, o); }
+    if (lane == 0) { red[warp][g] = a; red[warp][G + g] = b; }
+  }
+  __syncthreads();
+  if (tid < groups) {
+    double a = 0.0, b = 0.0;
+    for (int wv = 0; wv < 8; ++wv) { a += red[wv][tid]; b += red[wv][G + tid]; }
+    const double cnt = (double)S * cpg, mean = a / cnt;
+    double var = b / cnt - mean * mean;
+    if (var < 0.0) var = 0.0;
+    gmean[tid] = (float)mean;
+    grstd[tid] = (float)(1.0 / sqrt(var + (double)eps));
+  }
+  __syncthreads();
+  bf16* dst = out + (size_t)n * S * out_cs + out_co;
+  for (int p = tid; p < S; p += 256) {
+    float z[C];
+    compute_z(p, z);
+#pragma unroll
+    for (int c8 = 0; c8 < C / 8; ++c8) {
+      uint4 o;
+      __nv_bfloat162* h = reinterpret_cast<__nv_bfloat162*>(&o);
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const int c = c8 * 8 + 2 * j, g0 = c / cpg, g1 = (c + 1) / cpg;
+        const float a = (z[c] - gmean[g0]) * grstd[g0] * sG[c] + sBe[c];
+        const float b = (z[c + 1] - gmean[g1]) * grstd[g1] * sG[c + 1] + sBe[c + 1];
+        h[j] = __floats2bfloat162_rn(a, b);
+      }
+      *reinterpret_cast<uint4*>(dst + (size_t)p * out_cs + c8 * 8) = o;
+    }
+  }
+}
+
+__global__ void cvt_f32_kernel(const bf16* __restrict__ in, int cs, int co, float* __restrict__ out, long long rows, int C) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= rows * C) return;
+  const long long r = i / C;
+  const int c = (int)(i - r * C);
+  out[i] = __bfloat162float(in[r * cs + co + c]);
+}
+
 }  // namespace
 
 int head1x1_launch(const ConvP& p, cudaStream_t s, int* handled) {
@@ -515,6 +619,30 @@ int groupnorm_launch(cudaStream_t s, const bf16* in, int in_cs, int in_co, const
   size_t smem = ((size_t)nthr * 16 + 2 * C + 2 * groups) * sizeof(float);
   groupnorm_kernel<<<N, 256, smem, s>>>(in, in_cs, in_co, gamma, beta, groups, eps, out, out_cs,
                                         out_co, S, C);
+  RSG_LAUNCH_CHECK();
+  return RSG_OK;
+}
+
+
+int trp_tail_launch(cudaStream_t s, const float* y32, const float* w, const float* bias, const float* gamma, const float* beta,
+                    int groups, float eps, bf16* out, int out_cs, int out_co, int N, int S, int C) {
+  RSG_REQUIRE(groups == 8 && C % 8 == 0, "trp_tail: GroupNorm(8, C) only (C=%d groups=%d)", C, groups);
+  RSG_REQUIRE(out_cs % 8 == 0 && out_co % 8 == 0, "trp_tail: output channel stride/offset must be multiples of 8");
+  if (N == 0) return RSG_OK;
+  switch (C) {
+    case 16: trp_tail_kernel<16, 8><<<N, 256, 0, s>>>(y32, w, bias, gamma, beta, eps, out, out_cs, out_co, S); break;
+    case 32: trp_tail_kernel<32, 8><<<N, 256, 0, s>>>(y32, w, bias, gamma, beta, eps, out, out_cs, out_co, S); break;
+    case 48: trp_tail_kernel<48, 8><<<N, 256, 0, s>>>(y32, w, bias, gamma, beta, eps, out, out_cs, out_co, S); break;
+    case 64: trp_tail_kernel<64, 8><<<N, 256, 0, s>>>(y32, w, bias, gamma, beta, eps, out, out_cs, out_co, S); break;
+    default: rsg_set_error("trp_tail: unsupported channel count %d (16/32/48/64)", C); return RSG_ERR_ARG;
+  }
+  RSG_LAUNCH_CHECK();
+  return RSG_OK;
+}
+
+int cvt_f32_launch(cudaStream_t s, const bf16* in, int cs, int co, float* out, long long rows, int C) {
+  if (rows == 0) return RSG_OK;
+  cvt_f32_kernel<<<ceil_div(rows * C, 256), 256, 0, s>>>(in, cs, co, out, rows, C);
   RSG_LAUNCH_CHECK();
   return RSG_OK;
 }

@@ -21,7 +21,12 @@ int attention_launch(cudaStream_t s, const bf16* x, int x_cs, int x_co, const bf
                      int g_co, bf16* y, int y_cs, int y_co, int N, int S, int C);
 // tcgen05 version of the TRP core (attention_tc5.cu); *handled = 0 when the shape is left to attention_launch
 int attention_tc5_launch(cudaStream_t s, const bf16* x, int x_cs, int x_co, const bf16* g, int g_cs, int g_co,
-                         bf16* y, int y_cs, int y_co, int N, int S, int C, int* handled);
+                         bf16* y, int y_cs, int y_co, float* y32, int N, int S, int C, int* handled);
+// TRP tail in fp32 (association.py:236-245, 300): out = GroupNorm(groups, C)(W y + b), y fp32 [N,S,C] dense, W fp32 [C][C]
+int trp_tail_launch(cudaStream_t s, const float* y32, const float* w, const float* bias, const float* gamma, const float* beta,
+                    int groups, float eps, bf16* out, int out_cs, int out_co, int N, int S, int C);
+// bf16 [N,S,C] view -> dense fp32 [N,S,C]
+int cvt_f32_launch(cudaStream_t s, const bf16* in, int cs, int co, float* out, long long rows, int C);
 // fused BasicBlock (conv_bb.cu): out = relu(conv2(relu(conv1(x))) + x), both 3x3 s1, BN folded, C = 32 / 48
 int conv_bb_launch(cudaStream_t s, const bf16* in, int in_cs, int in_co, int N, int H, int W, int C, const bf16* w1,
                    const float* b1, const bf16* w2, const float* b2, bf16* out, int out_cs, int out_co);

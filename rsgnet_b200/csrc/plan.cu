@@ -51,7 +51,7 @@ extern "C" int rsg_device_info(int* out4) {
 }
 
 // ------------------------------------------------------------------------------------------------
-enum OpKind { OP_STEM, OP_CONV, OP_FUSE, OP_MAXPOOL, OP_ATTN, OP_RELSCORES, OP_GROUPNORM, OP_BILINEAR, OP_BBLOCK, OP_BNECK };
+enum OpKind { OP_STEM, OP_CONV, OP_FUSE, OP_MAXPOOL, OP_ATTN, OP_RELSCORES, OP_GROUPNORM, OP_BILINEAR, OP_BBLOCK, OP_BNECK, OP_TRPTAIL };
 
 struct Op {
   OpKind kind;
@@ -195,14 +195,24 @@ int run_op(const Op& op, const RunCtx& c, int nb, int n_crops, cudaStream_t s, i
                             op.i[3], op.i[4], (bf16*)resolve(op.r[1], c));
     case OP_ATTN: {
       int handled = 0;
+      float* y32 = is_null(op.r[3]) ? nullptr : (float*)resolve(op.r[3], c);
+      bf16* y16 = is_null(op.r[2]) ? nullptr : (bf16*)resolve(op.r[2], c);
       int rc = attention_tc5_launch(s, (const bf16*)resolve(op.r[0], c), op.i[0], op.i[1],
                                     (const bf16*)resolve(op.r[1], c), op.i[2], op.i[3],
-                                    (bf16*)resolve(op.r[2], c), op.i[4], op.i[5], nb, op.i[6], op.i[7], &handled);
+                                    y32 ? nullptr : y16, op.i[4], op.i[5], y32, nb, op.i[6], op.i[7], &handled);
       if (rc || handled) return rc;
-      return attention_launch(s, (const bf16*)resolve(op.r[0], c), op.i[0], op.i[1],
-                              (const bf16*)resolve(op.r[1], c), op.i[2], op.i[3],
-                              (bf16*)resolve(op.r[2], c), op.i[4], op.i[5], nb, op.i[6], op.i[7]);
+      // shapes the tcgen05 kernel leaves out (unaligned views): the mma.sync kernel writes bf16, converted if fp32 is wanted
+      RSG_REQUIRE(y16, "attention: this shape needs the bf16 output buffer (mma.sync fallback)");
+      rc = attention_launch(s, (const bf16*)resolve(op.r[0], c), op.i[0], op.i[1],
+                            (const bf16*)resolve(op.r[1], c), op.i[2], op.i[3], y16, op.i[4], op.i[5], nb, op.i[6], op.i[7]);
+      if (rc || !y32) return rc;
+      return cvt_f32_launch(s, y16, op.i[4], op.i[5], y32, (long long)nb * op.i[6], op.i[7]);
     }
+    case OP_TRPTAIL:
+      return trp_tail_launch(s, (const float*)resolve(op.r[0], c), (const float*)resolve(op.r[1], c),
+                             (const float*)resolve(op.r[2], c), (const float*)resolve(op.r[3], c),
+                             (const float*)resolve(op.r[4], c), op.i[0], op.f[0], (bf16*)resolve(op.r[5], c), op.i[1], op.i[2],
+                             nb, op.i[3], op.i[4]);
     case OP_RELSCORES:
       return relation_scores_launch(s, (const bf16*)resolve(op.r[0], c), op.i[0], op.i[1], nb,
                                     op.i[2], op.i[3], (float*)resolve(op.r[1], c));
@@ -274,6 +284,7 @@ static Op& new_op(rsg_plan* p, OpKind k) {
   p->ops.emplace_back();
   Op& op = p->ops.back();
   memset(&op, 0, sizeof(Op));
+  for (rsg_ref& r : op.r) r.ext_slot = -1;          // unset refs are null, not "external slot 0"
   op.kind = k;
   op.aux = p->aux_mode;
   return op;
@@ -319,6 +330,23 @@ extern "C" int rsg_plan_add_attention(rsg_plan* p, rsg_ref x, int x_cs, int x_co
   op.r[0] = x; op.r[1] = g; op.r[2] = y;
   op.i[0] = x_cs; op.i[1] = x_co; op.i[2] = g_cs; op.i[3] = g_co; op.i[4] = y_cs; op.i[5] = y_co;
   op.i[6] = S; op.i[7] = C;
+  return RSG_OK;
+}
+extern "C" int rsg_plan_add_attention_f32(rsg_plan* p, rsg_ref x, int x_cs, int x_co, rsg_ref g, int g_cs, int g_co,
+                                          rsg_ref y_bf16, int y_cs, int y_co, rsg_ref y_f32, int S, int C) {
+  int rc = rsg_plan_add_attention(p, x, x_cs, x_co, g, g_cs, g_co, y_bf16, y_cs, y_co, S, C);
+  if (rc) return rc;
+  p->ops.back().r[3] = y_f32;
+  return RSG_OK;
+}
+extern "C" int rsg_plan_add_trp_tail(rsg_plan* p, rsg_ref y_f32, rsg_ref w, rsg_ref bias, rsg_ref gamma, rsg_ref beta, int groups,
+                                     float eps, rsg_ref out, int out_cs, int out_co, int S, int C) {
+  RSG_REQUIRE(p, "null plan");
+  RSG_REQUIRE(groups == 8 && (C == 16 || C == 32 || C == 48 || C == 64), "trp_tail: GroupNorm(8, C) with C in 16/32/48/64 (C=%d groups=%d)", C, groups);
+  Op& op = new_op(p, OP_TRPTAIL);
+  op.r[0] = y_f32; op.r[1] = w; op.r[2] = bias; op.r[3] = gamma; op.r[4] = beta; op.r[5] = out;
+  op.i[0] = groups; op.i[1] = out_cs; op.i[2] = out_co; op.i[3] = S; op.i[4] = C;
+  op.f[0] = eps;
   return RSG_OK;
 }
 extern "C" int rsg_plan_add_relation_scores(rsg_plan* p, rsg_ref x, int x_cs, int x_co, int S,
@@ -419,7 +447,7 @@ extern "C" int rsg_plan_profile(rsg_plan* p, void* stream, void* const* ext, int
   for (size_t i = 0; i < n && rc == RSG_OK; ++i) {
     const Op& op = p->ops[i];
     ms[i] = -1.f; flops[i] = 0.0;
-    static const int kmap[] = {0, 1, 3, 4, 5, 6, 7, 8, 10, 11};
+    static const int kmap[] = {0, 1, 3, 4, 5, 6, 7, 8, 10, 11, 7};
     kind[i] = kmap[op.kind];
     if (op.aux && !with_aux) continue;
     cudaEventCreate(&ev[2 * i]); cudaEventCreate(&ev[2 * i + 1]);

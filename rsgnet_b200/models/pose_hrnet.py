@@ -19,8 +19,12 @@ logger = logging.getLogger(__name__)
 class EngineOwner(nn.Module):
     """nn.Module whose packed-weight engines (rsgnet_b200._engine) are dropped whenever the
     parameters can have changed: load_state_dict, .to()/.cuda()/.half() (``_apply``), train().
-    The cache dict is shared with DataParallel replicas (``replicate`` shallow-copies __dict__), so
-    it is cleared in place."""
+
+    ``torch.nn.DataParallel`` (tools/cp_test.py:99, tools/test.py:97) replicates the module on every forward:
+    a replica has an EMPTY ``_parameters`` dict and per-forward broadcast copies of the weights, so it cannot own
+    packed weights.  A replica therefore only remembers the module it came from (``_rsg_source``) and the device of
+    its parameter copies; its forward takes the per-device engine from the SOURCE module's cache (built once per
+    device from the source parameters, never from the broadcast copies)."""
 
     chunk = 512       # forwards per pass of the plan (one pass per 256-crop flip-test step)
 
@@ -28,6 +32,12 @@ class EngineOwner(nn.Module):
         cache = self.__dict__.get('_rsg_engines')
         if cache:
             cache.clear()
+        self.__dict__.pop('_rsg_tensors', None)
+
+    def _replicate_for_data_parallel(self):
+        replica = super()._replicate_for_data_parallel()
+        replica.__dict__['_rsg_source'] = self.__dict__.get('_rsg_source') or self
+        return replica
 
     def _apply(self, fn, *a, **kw):
         self._drop_engines()

@@ -178,3 +178,40 @@ def crop(img, center, scale, output_size, rot=0):
     trans = get_affine_transform(center, scale, rot, output_size)
     out = warp_crops([img], trans[None], output_size, normalize=False, return_u8=True)
     return out[0].cpu().numpy()
+
+
+# ---------------------------------------------------------------------------------------------
+# Host-side helpers the reference's callers import from utils.transforms next to the hot-path functions
+# (lib/core/inference.py:16, lib/core/function.py:18, lib/dataset/*JointsDataset.py:20-22).  Plain NumPy; nothing on the
+# inference hot path calls them (decode does the inverse affine on the device, csrc/decode.cu).
+# ---------------------------------------------------------------------------------------------
+def transform_preds(coords, center, scale, output_size):
+    """transforms.py:57-62: heat-map coordinates [K,>=2] -> image coordinates through the inverse crop affine
+    (rot = 0).  Returns a float64 array shaped like `coords` (extra columns zero), as the reference does."""
+    coords = np.asarray(coords)
+    t = get_affine_transform(center, scale, 0, output_size, inv=1)
+    out = np.zeros(coords.shape)
+    out[:, 0:2] = coords[:, 0:2] @ t[:, :2].T + t[:, 2]
+    return out
+
+
+def fliplr_joints(joints, joints_vis, width, matched_parts):
+    """transforms.py:40-54 (training-time augmentation): mirror the x coordinates and swap the left/right joints, in
+    place like the reference; returns (joints * joints_vis, joints_vis)."""
+    joints[:, 0] = width - joints[:, 0] - 1
+    for a, b in matched_parts:
+        joints[[a, b]] = joints[[b, a]]
+        joints_vis[[a, b]] = joints_vis[[b, a]]
+    return joints * joints_vis, joints_vis
+
+
+# DensePose part-index symmetry (transforms.py:14-21): background 0 and the torso parts 1, 2 map to themselves, the
+# remaining 22 parts swap in left/right pairs (3<->4, 5<->6, ..., 23<->24)
+_DP_SYMMETRY = np.array([0, 1, 2] + [v for a in range(3, 25, 2) for v in (a + 1, a)])
+
+
+def flip_dp_back(I_heatmaps):
+    """transforms.py:14-21 (imported by lib/core/function.py:18; used by no RSGNet config): undo the horizontal flip of
+    a 25-channel DensePose part-index map: permute the channels by the left/right symmetry and reverse W."""
+    I_heatmaps = np.asarray(I_heatmaps)
+    return I_heatmaps[:, _DP_SYMMETRY][:, :, :, ::-1]

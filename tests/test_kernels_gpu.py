@@ -482,3 +482,46 @@ def test_conv_tcgen05_vs_torch(cin, cout, k, H, W, relu, nres):
     assert err <= 2e-2 * max(ref.abs().max().item(), 1.0), err
     assert torch.all(pb.tensor_of(ob)[:N, ..., :8] == 7.0) and torch.all(pb.tensor_of(ob)[:N, ..., 8 + cout:] == 7.0)
     _lib.lib().rsg_plan_destroy(h)
+
+
+@pytest.mark.parametrize('C_,S_hw', [(32, (64, 48)), (16, (24, 16)), (48, (24, 18)), (64, (9, 7))])
+def test_trp_fp32_tail_vs_torch(C_, S_hw):
+    """attention with fp32 output + the fp32 tail  GroupNorm(8, C)(W y + b)  (association.py:236-245, 288-300) on an
+    adversarial input: nearly uniform attention weights, so y's mean over the positions is ~50x its spread -- the
+    regime in which a bf16 y / z loses the normalised signal (measured 0.10 relative error on the tiny model)."""
+    N = 3
+    H, W = S_hw
+    S = H * W
+    g = torch.Generator().manual_seed(C_ + S)
+    x = (torch.randn(N, S, C_, generator=g) * 0.08).abs().bfloat16().float()          # post-ReLU features, small logits
+    gv = (torch.randn(N, S, C_, generator=g) + 0.7).bfloat16().float()
+    wt = torch.randn(C_, C_, generator=g) / C_ ** 0.5
+    bias, gamma, beta = torch.randn(C_, generator=g) * 0.1, torch.rand(C_, generator=g) + 0.5, torch.randn(C_, generator=g) * 0.1
+    pb = PlanBuilder(4, reuse=False)
+    xb = pb.buf('x', H, W, C_)
+    gb = pb.buf('g', H, W, C_)
+    yb = pb.buf('y', H, W, C_)
+    y32 = pb.buf('y32', H, W, C_, itemsize=4)
+    ob = pb.buf('o', H, W, 2 * C_)
+    f32 = lambda a: pb.const(a.numpy().astype(np.float32))
+    pb.simple('attention', dict(x=View(xb), g=View(gb), y=View(yb), y32=y32), [xb, gb], [yb, y32])
+    pb.simple('trptail', dict(y32=y32, out=View(ob, C_, C_), w=f32(wt), bias=f32(bias), gamma=f32(gamma), beta=f32(beta),
+                              groups=8, S=S, C=C_), [y32], [ob])
+    h = _run(pb, N)
+    pb.tensor_of(xb)[:N] = x.view(N, H, W, C_).cuda().bfloat16()
+    pb.tensor_of(gb)[:N] = gv.view(N, H, W, C_).cuda().bfloat16()
+    pb.tensor_of(ob).fill_(7.0)
+    _exec(h, N)
+    A = torch.sigmoid(x.double() @ x.double().transpose(1, 2))
+    y = A @ gv.double()                                                               # [N,S,C]
+    got_y = pb.tensor_of(y32)[:N].reshape(N, S, C_).cpu().double()
+    assert (got_y - y).abs().max().item() <= 6e-3 * y.abs().max().item()             # P is rounded to bf16 before P.G
+    z = got_y @ wt.double().t() + bias.double()
+    ref = F.group_norm(z.transpose(1, 2).reshape(N, C_, H, W), 8, gamma.double(), beta.double(), 1e-5)
+    got = pb.tensor_of(ob)[:N, ..., C_:].float().permute(0, 3, 1, 2).cpu().double()
+    # the tail itself, given the kernel's own fp32 y: fp32 arithmetic + one bf16 output rounding
+    assert (got - ref).abs().max().item() <= 6e-3 * ref.abs().max().item()
+    assert torch.all(pb.tensor_of(ob)[:N, ..., :C_] == 7.0)
+    spread = (y - y.mean(1, keepdim=True)).abs().max().item() / y.abs().max().item()
+    print(f'C={C_} S={S}: spread/|mean| of y = {spread:.4f}')
+    _lib.lib().rsg_plan_destroy(h)

@@ -47,9 +47,13 @@ def _heatmap_report(got, ref, tag):
     per_map = np.abs(g - r).max(1) / np.maximum(rng, 1e-12)
     ig, ir = g.argmax(1), r.argmax(1)
     disp = np.hypot(ig % w - ir % w, ig // w - ir // w)
+    # a differing arg-max must be a near-tie of the REFERENCE map: its two candidates closer than twice the map's error
+    rows = np.arange(n * k)
+    err_map = np.abs(g - r).max(1)
+    unexplained = int(((ig != ir) & (r[rows, ir] - r[rows, ig] > 2.0 * err_map)).sum())
     rep = dict(per_map_norm_err_max=float(per_map.max()), per_map_norm_err_mean=float(per_map.mean()),
                argmax_agree=float((ig == ir).mean()), disp_le1=float((disp <= 1.0).mean()),
-               disp_le2=float((disp <= 2.0).mean()), disp_max=float(disp.max()))
+               disp_le2=float((disp <= 2.0).mean()), disp_max=float(disp.max()), unexplained_argmax_flips=unexplained)
     print(tag, 'heat-map decode report', {a: round(b, 4) for a, b in rep.items()})
     return rep
 
@@ -181,7 +185,7 @@ def test_full_models_vs_reference_golden(golden_dir, key, seed):
         assert e <= FULL_TOL, (nm, e)
     hm_name = 'heatmaps' if cfg.MODEL.NAME == 'pose_hrnet' else 'kpt_scores'
     dec = _heatmap_report(outs[hm_name].cpu().numpy(), g['out.' + hm_name], key)
-    assert dec['per_map_norm_err_max'] <= 0.25 and dec['disp_le2'] >= 0.9, dec
+    assert dec['per_map_norm_err_max'] <= 0.06 and dec['unexplained_argmax_flips'] == 0, dec
 
 
 def test_flip_batch_equals_two_forwards():
@@ -236,3 +240,86 @@ def test_overlapped_pipeline_equals_sequential():
     st.synchronize()
     for (p, m), (rp, rm) in zip(got, ref):
         assert np.array_equal(p.cpu().numpy(), rp) and np.array_equal(m.cpu().numpy(), rm)
+
+
+def test_module_forward_graph_replay_batch_sizes_and_lazy_aux():
+    """nn.Module.forward as the reference's loop calls it (function.py:389-402): fresh output tensors per call (the
+    loop holds `output` across the flipped forward), CUDA-graph replay from the third call on, CPU inputs (what
+    DataParallel's caller passes), batch sizes on both sides of a chunk boundary, and the lazily materialised outputs."""
+    cfg, net, sd = build('tiny', 0)
+    x1, x2 = crops(cfg, 3, 5).cuda(), crops(cfg, 3, 6).cuda()
+    st = torch.cuda.Stream()
+    with torch.cuda.stream(st):
+        outs = [net(x1), net(x2), net(x1), net(x2), net(x1)]          # eager, capture, replay, replay, replay
+    st.synchronize()
+    for k in range(4):
+        assert torch.equal(outs[0][k], outs[2][k]) and torch.equal(outs[0][k], outs[4][k]) and torch.equal(outs[1][k], outs[3][k])
+        assert outs[0][k].data_ptr() != outs[2][k].data_ptr()
+    assert not torch.equal(outs[0][1], outs[1][1])
+    eng = _engine.engine_for(net, 'cuda', 32)
+    ref = torch.empty(eng.out_shapes(3)[_engine.EXT_HEAT], device='cuda')
+    eng.run(x1, ref, 3, 3)
+    assert torch.equal(ref, outs[0][1])
+    assert torch.equal(net(x1.cpu())[1], ref)                        # host input: copied into the static buffer
+    big = torch.cat([x1, crops(cfg, 34, 7).cuda()])                  # 37 crops: the 64-forward engine
+    assert torch.equal(net(big)[1][:3], ref)
+    net.lazy_aux = True
+    try:
+        lz = net(x1)
+        assert isinstance(lz[0], _engine.LazyOutput) and tuple(lz[0].shape) == tuple(outs[0][0].shape)
+        assert tuple(lz[3].shape) == tuple(outs[0][3].shape) and lz[2].device == ref.device
+        assert torch.equal(lz[1], ref)
+        assert torch.equal(lz[2].materialize(), outs[0][2])          # second run with the auxiliary ops, same numbers
+        assert torch.equal(torch.sigmoid(lz[0]), torch.sigmoid(outs[0][0]))      # torch functions accept it
+        assert torch.equal(lz[3][1], outs[0][3][1]) and torch.equal(lz[0].cpu(), outs[0][0].cpu())
+    finally:
+        net.lazy_aux = False
+
+
+def test_two_streams_share_an_engine_safely():
+    """Two pipelines on two CUDA streams share the cached engine (arena, concat buffers): runs are ordered by an event,
+    so interleaving them cannot corrupt either result."""
+    from rsgnet_b200 import synth
+    from rsgnet_b200.pipeline import CropPipeline
+    cfg, net, sd = build('tiny', 0)
+    B = 4
+    xa, xb = crops(cfg, B, 41), crops(cfg, B, 42)
+    ca, sa = synth.centers_scales(B, seed=3)
+    seq = CropPipeline(net, cfg, B, use_graph=False)
+    ra, rb = seq(xa, ca, sa), seq(xb, ca, sa)
+    pa, pb_ = CropPipeline(net, cfg, B, use_graph=False), CropPipeline(net, cfg, B, use_graph=False)
+    assert pa.engine is pb_.engine
+    s1, s2 = torch.cuda.Stream(), torch.cuda.Stream()
+    for p, x in ((pa, xa), (pb_, xb)):
+        p.x.copy_(x.cuda()); p.center.copy_(torch.from_numpy(ca).cuda()); p.scale.copy_(torch.from_numpy(sa).cuda())
+    torch.cuda.synchronize()
+    got = []
+    for _ in range(6):
+        with torch.cuda.stream(s1):
+            o1 = pa.run_device()
+        with torch.cuda.stream(s2):
+            o2 = pb_.run_device()
+        got.append((o1, o2))
+    torch.cuda.synchronize()
+    for o1, o2 in got[-2:]:
+        assert np.array_equal(o1[0].cpu().numpy(), ra[0]) and np.array_equal(o2[0].cpu().numpy(), rb[0])
+
+
+@pytest.mark.skipif(torch.cuda.device_count() < 2, reason='needs two CUDA devices')
+def test_dataparallel_two_devices():
+    """tools/cp_test.py:99 wraps the model in torch.nn.DataParallel unconditionally: replicas (empty _parameters,
+    per-forward broadcast copies) take their engine from the source module's per-device cache."""
+    cfg, net, sd = build('tiny', 0)
+    x = crops(cfg, 6, 5)
+    ref = [t.cpu() for t in net(x.cuda())]
+    dp = torch.nn.DataParallel(net, device_ids=[0, 1]).cuda()
+    dp.eval()
+    for _ in range(3):
+        out = dp(x)                                              # CPU input, as function.py:389 passes it
+        for a, b in zip(out, ref):
+            assert a.device.index == 0 and torch.equal(a.cpu(), b)
+    assert sorted(k[0] for k in net.__dict__['_rsg_engines']) == ['cuda:0', 'cuda:1']
+    hr = __import__('tests.gpu_util', fromlist=['build']).build('tiny_hrnet', 2)[1]
+    dph = torch.nn.DataParallel(hr, device_ids=[0, 1]).cuda().eval()
+    xh = crops(cfg, 5, 9)
+    assert torch.equal(dph(xh).cpu(), hr(xh.cuda()).cpu())
