@@ -111,9 +111,6 @@ eval_nms_kernel(const float* __restrict__ preds /*[n,K,3]*/, const double* __res
                 float vis_thre32, double oks_thre, int soft, int max_dets, double* __restrict__ scores /*[n] by detection*/,
                 int32_t* __restrict__ keep /*[n]*/, int32_t* __restrict__ keep_counts) {
   __shared__ double vars[RSG_NMS_MAXK];
-  __shared__ double wbest[4];
-  __shared__ int widx[4];
-  __shared__ int best_p;
   const int tid = threadIdx.x, nt = blockDim.x;
   if (tid < K) {
     const double s2 = __dmul_rn(sigmas[tid], 2.0);
@@ -166,38 +163,39 @@ eval_nms_kernel(const float* __restrict__ preds /*[n,K,3]*/, const double* __res
         __syncthreads();
       }
     } else {
-      // soft_oks_nms (nms.py:138-180): `dead` doubles as "already taken"
-      const int rounds = m < max_dets ? m : max_dets;
-      for (; nkeep < rounds; ++nkeep) {
-        double bv = 0.0;
-        int bi = -1;
-        for (int a = tid; a < m; a += nt)
-          if (!dead[beg + a] && (bi < 0 || score_before(cur[beg + a], a, bv, bi))) { bv = cur[beg + a]; bi = a; }
-#pragma unroll
-        for (int o = 16; o > 0; o >>= 1) {
-          const double ov = __shfl_xor_sync(0xffffffffu, bv, o);
-          const int oi = __shfl_xor_sync(0xffffffffu, bi, o);
-          if (oi >= 0 && (bi < 0 || score_before(ov, oi, bv, bi))) { bv = ov; bi = oi; }
-        }
-        if ((tid & 31) == 0) { wbest[tid >> 5] = bv; widx[tid >> 5] = bi; }
-        __syncthreads();
-        if (tid == 0) {
-          for (int w = 1; w < (nt >> 5); ++w)
-            if (widx[w] >= 0 && (bi < 0 || score_before(wbest[w], widx[w], bv, bi))) { bv = wbest[w]; bi = widx[w]; }
-          best_p = bi;
-          keep[beg + nkeep] = seg[beg + bi];
-          dead[beg + bi] = 1;
-        }
-        __syncthreads();
-        const int a = best_p, det = seg[beg + a];
+      // soft_oks_nms (nms.py:138-180) with the reference's own bookkeeping: an explicit `order` list that loses its
+      // head every round and is re-sorted by the decayed scores with scores.argsort()[::-1] -- so EQUAL scores (several
+      // detections rescored to exactly 0) come out in the reverse of their CURRENT relative order, round after round.
+      int L = m;
+      for (int a = tid; a < m; a += nt) {
+        const double sa = cur[beg + a];
+        int r = 0;
+        for (int b = 0; b < m; ++b) r += (b != a) && score_before(cur[beg + b], b, sa, a);
+        ord[beg + r] = a;
+      }
+      __syncthreads();
+      while (L > 0 && nkeep < max_dets) {
+        const int a = ord[beg], det = seg[beg + a];
+        if (tid == 0) keep[beg + nkeep] = det;
+        ++nkeep;
         const float* g = preds + (size_t)det * K * 3;
         const double a_g = boxes[(size_t)det * 6 + 4];
-        for (int b = tid; b < m; b += nt) {
-          if (dead[beg + b]) continue;
-          const int dj = seg[beg + b];
+        for (int u = 1 + tid; u < L; u += nt) {
+          const int e = ord[beg + u], dj = seg[beg + e];
           const double oks = oks_pair(g, preds + (size_t)dj * K * 3, a_g, boxes[(size_t)dj * 6 + 4], vars, K, 0, 0.f);
-          cur[beg + b] = __dmul_rn(cur[beg + b], exp(__ddiv_rn(-__dmul_rn(oks, oks), oks_thre)));
+          cur[beg + e] = __dmul_rn(cur[beg + e], exp(__ddiv_rn(-__dmul_rn(oks, oks), oks_thre)));
         }
+        __syncthreads();
+        --L;                                               // positions u' = 0 .. L-1 of the remaining list = ord[u' + 1]
+        for (int u = tid; u < L; u += nt) {
+          const int e = ord[beg + u + 1];
+          const double se = cur[beg + e];
+          int r = 0;
+          for (int v = 0; v < L; ++v) r += (v != u) && score_before(cur[beg + ord[beg + v + 1]], v, se, u);
+          tmp[beg + r] = e;
+        }
+        __syncthreads();
+        for (int u = tid; u < L; u += nt) ord[beg + u] = tmp[beg + u];
         __syncthreads();
       }
     }

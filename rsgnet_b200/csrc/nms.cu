@@ -61,10 +61,10 @@ oks_nms_kernel(const float* __restrict__ kpts, const double* __restrict__ scores
   if (tid == 0) keep_counts[img] = nkeep;
 }
 
-// soft_oks_nms (lib/nms/nms.py:138-180): up to max_dets rounds per image; every round keeps the best remaining detection
-// and multiplies the scores of the others by exp(-oks^2 / thresh) (rescore(), nms.py:127-135, 'gaussian').  The
-// reference re-sorts after every round; taking the maximum of the remaining scores is the same selection (ties: the
-// later index first, like scores.argsort()[::-1] on distinct positions).  One CTA per image.
+// soft_oks_nms (lib/nms/nms.py:138-180): up to max_dets rounds per image; every round keeps the head of the score-ordered
+// list and multiplies the scores of the others by exp(-oks^2 / thresh) (rescore(), nms.py:127-135, 'gaussian'), then
+// re-sorts what is left with scores.argsort()[::-1] -- reproduced with an explicit order list, so that EQUAL scores come
+// out in the reverse of their current relative order, exactly like the reference's re-sort does.  One CTA per image.
 __global__ void __launch_bounds__(128)
 soft_oks_nms_kernel(const float* __restrict__ kpts, const double* __restrict__ scores,
                     const double* __restrict__ areas, const int32_t* __restrict__ offs,
@@ -72,56 +72,52 @@ soft_oks_nms_kernel(const float* __restrict__ kpts, const double* __restrict__ s
                     int max_per_img, int32_t* __restrict__ keep, int32_t* __restrict__ keep_counts) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   __shared__ double vars[RSG_NMS_MAXK];
-  __shared__ double wbest[4];
-  __shared__ int widx[4];
-  __shared__ int best_i;
   const int img = blockIdx.x;
   const int beg = offs[img], n = offs[img + 1] - beg;
-  double* cur = reinterpret_cast<double*>(smem_raw);      // [n] current scores
-  int* alive = reinterpret_cast<int*>(cur + n);           // [n]
   const int tid = threadIdx.x, nt = blockDim.x;
   if (n < 0 || n > max_per_img) {
     if (tid == 0) keep_counts[img] = -1;
     return;
   }
+  double* cur = reinterpret_cast<double*>(smem_raw);      // [n] current scores, by detection
+  int* ord = reinterpret_cast<int*>(cur + max_per_img);   // [n] the remaining detections, best first
+  int* tmp = ord + max_per_img;                           // [n]
   if (tid < K) {
     double s2 = __dmul_rn(sigmas[tid], 2.0);
     vars[tid] = __dmul_rn(s2, s2);
   }
-  for (int i = tid; i < n; i += nt) { cur[i] = scores[beg + i]; alive[i] = 1; }
+  for (int i = tid; i < n; i += nt) cur[i] = scores[beg + i];
   __syncthreads();
-  int cnt = 0;
-  const int rounds = n < max_dets ? n : max_dets;
-  for (; cnt < rounds; ++cnt) {
-    // argmax of the remaining scores (value, then the later index)
-    double bv = 0.0;
-    int bi = -1;
-    for (int i = tid; i < n; i += nt)
-      if (alive[i] && (bi < 0 || score_before(cur[i], i, bv, bi))) { bv = cur[i]; bi = i; }
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) {
-      const double ov = __shfl_xor_sync(0xffffffffu, bv, o);
-      const int oi = __shfl_xor_sync(0xffffffffu, bi, o);
-      if (oi >= 0 && (bi < 0 || score_before(ov, oi, bv, bi))) { bv = ov; bi = oi; }
-    }
-    if ((tid & 31) == 0) { wbest[tid >> 5] = bv; widx[tid >> 5] = bi; }
-    __syncthreads();
-    if (tid == 0) {
-      for (int w = 1; w < (nt >> 5); ++w)
-        if (widx[w] >= 0 && (bi < 0 || score_before(wbest[w], widx[w], bv, bi))) { bv = wbest[w]; bi = widx[w]; }
-      best_i = bi;
-      keep[(size_t)img * max_dets + cnt] = bi;
-      alive[bi] = 0;
-    }
-    __syncthreads();
-    const int i = best_i;
+  for (int i = tid; i < n; i += nt) {
+    const double si = cur[i];
+    int r = 0;
+    for (int j = 0; j < n; ++j) r += (j != i) && score_before(cur[j], j, si, i);
+    ord[r] = i;
+  }
+  __syncthreads();
+  int cnt = 0, L = n;
+  while (L > 0 && cnt < max_dets) {
+    const int i = ord[0];
+    if (tid == 0) keep[(size_t)img * max_dets + cnt] = i;
+    ++cnt;
     const float* g = kpts + (size_t)(beg + i) * K * 3;
     const double a_g = areas[beg + i];
-    for (int j = tid; j < n; j += nt) {
-      if (!alive[j]) continue;
+    for (int u = 1 + tid; u < L; u += nt) {
+      const int j = ord[u];
       const double oks = oks_pair(g, kpts + (size_t)(beg + j) * K * 3, a_g, areas[beg + j], vars, K, use_vis, vis);
       cur[j] = __dmul_rn(cur[j], exp(__ddiv_rn(-__dmul_rn(oks, oks), thresh)));
     }
+    __syncthreads();
+    --L;
+    for (int u = tid; u < L; u += nt) {
+      const int e = ord[u + 1];
+      const double se = cur[e];
+      int r = 0;
+      for (int v = 0; v < L; ++v) r += (v != u) && score_before(cur[ord[v + 1]], v, se, u);
+      tmp[r] = e;
+    }
+    __syncthreads();
+    for (int u = tid; u < L; u += nt) ord[u] = tmp[u];
     __syncthreads();
   }
   if (tid == 0) keep_counts[img] = cnt;
@@ -178,8 +174,8 @@ extern "C" int rsg_soft_oks_nms(void* stream, const float* kpts, const double* s
   if (n_imgs == 0) return RSG_OK;
   RSG_REQUIRE(kpts && scores && areas && img_offsets && sigmas && keep && keep_counts, "rsg_soft_oks_nms: null pointer");
   RSG_REQUIRE(max_per_img >= 0, "rsg_soft_oks_nms: max_per_img < 0");
-  size_t smem = (size_t)max_per_img * (sizeof(double) + sizeof(int));
-  RSG_REQUIRE(smem <= 200 * 1024, "rsg_soft_oks_nms: more than %d detections in one image", 17000);
+  size_t smem = (size_t)max_per_img * (sizeof(double) + 2 * sizeof(int));
+  RSG_REQUIRE(smem <= 200 * 1024, "rsg_soft_oks_nms: more than %d detections in one image", 12800);
   if (smem > 48 * 1024)
     RSG_CUDA(cudaFuncSetAttribute(soft_oks_nms_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   soft_oks_nms_kernel<<<n_imgs, 128, smem, (cudaStream_t)stream>>>(kpts, scores, areas, img_offsets, sigmas, K, thresh,

@@ -448,8 +448,8 @@ head1x1_kernel(const bf16* __restrict__ in, int in_cs, int in_co, const bf16* __
 // One CTA per crop, one thread per position: pass 1 accumulates the per-group sum / sum of squares of z (fp32 per
 // thread over a few dozen values, fp64 across threads), pass 2 recomputes z (y is L2-hot; cheaper than a round trip of
 // z through HBM) and writes the normalised bf16 output.  W is read as 16-byte broadcast loads from shared memory.
-template <int C, int G>
-__global__ void __launch_bounds__(256)
+template <int C, int G, int PPT>
+__global__ void __launch_bounds__(256, 2)
 trp_tail_kernel(const float* __restrict__ y32, const float* __restrict__ w, const float* __restrict__ bias,
                 const float* __restrict__ gamma, const float* __restrict__ beta, float eps,
                 bf16* __restrict__ out, int out_cs, int out_co, int S) {
@@ -467,35 +467,58 @@ trp_tail_kernel(const float* __restrict__ y32, const float* __restrict__ w, cons
 #pragma unroll
   for (int g = 0; g < G; ++g) { gs[g] = 0.f; gq[g] = 0.f; }
 
-  auto compute_z = [&](int p, float* z) {
-    float yv[C];
-    const float4* yp = reinterpret_cast<const float4*>(src + (size_t)p * C);
+  // PPT positions at once (p, p + 256, ...): every 16-byte broadcast load of W feeds 4 * PPT FMAs; z is produced eight
+  // channels at a time and consumed at once, so only y stays in registers.  Positions past the end of the crop are
+  // clamped (computed, never used).
+  auto load_y = [&](int p, float (&yv)[PPT][C]) {
 #pragma unroll
-    for (int k = 0; k < C / 4; ++k) {
-      const float4 v = __ldg(yp + k);
-      yv[4 * k] = v.x; yv[4 * k + 1] = v.y; yv[4 * k + 2] = v.z; yv[4 * k + 3] = v.w;
+    for (int q = 0; q < PPT; ++q) {
+      const int pp = min(p + 256 * q, S - 1);
+      const float4* yp = reinterpret_cast<const float4*>(src + (size_t)pp * C);
+#pragma unroll
+      for (int k = 0; k < C / 4; ++k) {
+        const float4 v = __ldg(yp + k);
+        yv[q][4 * k] = v.x; yv[q][4 * k + 1] = v.y; yv[q][4 * k + 2] = v.z; yv[q][4 * k + 3] = v.w;
+      }
     }
+  };
+  auto z_chunk = [&](const float (&yv)[PPT][C], int c8, float (&z)[PPT][8]) {
 #pragma unroll
-    for (int c = 0; c < C; ++c) {
-      float a = sB[c];
+    for (int j = 0; j < 8; ++j) {
+      const int c = c8 * 8 + j;
+#pragma unroll
+      for (int q = 0; q < PPT; ++q) z[q][j] = sB[c];
       const float4* wr = reinterpret_cast<const float4*>(sW + c * C);
 #pragma unroll
       for (int k = 0; k < C / 4; ++k) {
         const float4 ww = wr[k];
-        a = fmaf(ww.x, yv[4 * k], a); a = fmaf(ww.y, yv[4 * k + 1], a);
-        a = fmaf(ww.z, yv[4 * k + 2], a); a = fmaf(ww.w, yv[4 * k + 3], a);
+#pragma unroll
+        for (int q = 0; q < PPT; ++q) {
+          z[q][j] = fmaf(ww.x, yv[q][4 * k], z[q][j]); z[q][j] = fmaf(ww.y, yv[q][4 * k + 1], z[q][j]);
+          z[q][j] = fmaf(ww.z, yv[q][4 * k + 2], z[q][j]); z[q][j] = fmaf(ww.w, yv[q][4 * k + 3], z[q][j]);
+        }
       }
-      z[c] = a;
     }
   };
 
-  for (int p = tid; p < S; p += 256) {
-    float z[C];
-    compute_z(p, z);
+  for (int p = tid; p < S; p += 256 * PPT) {
+    float yv[PPT][C];
+    load_y(p, yv);
 #pragma unroll
-    for (int c = 0; c < C; ++c) {
-      gs[c / cpg] += z[c];              // compile-time group index: gs / gq stay in registers
-      gq[c / cpg] = fmaf(z[c], z[c], gq[c / cpg]);
+    for (int c8 = 0; c8 < C / 8; ++c8) {
+      float z[PPT][8];
+      z_chunk(yv, c8, z);
+#pragma unroll
+      for (int q = 0; q < PPT; ++q) {
+        if (p + 256 * q < S) {
+#pragma unroll
+          for (int j = 0; j < 8; ++j) {
+            const int g = (c8 * 8 + j) / cpg;            // compile-time after unrolling: gs / gq stay in registers
+            gs[g] += z[q][j];
+            gq[g] = fmaf(z[q][j], z[q][j], gq[g]);
+          }
+        }
+      }
     }
   }
 #pragma unroll
@@ -517,21 +540,29 @@ trp_tail_kernel(const float* __restrict__ y32, const float* __restrict__ w, cons
   }
   __syncthreads();
   bf16* dst = out + (size_t)n * S * out_cs + out_co;
-  for (int p = tid; p < S; p += 256) {
-    float z[C];
-    compute_z(p, z);
+  for (int p = tid; p < S; p += 256 * PPT) {
+    float yv[PPT][C];
+    load_y(p, yv);
 #pragma unroll
     for (int c8 = 0; c8 < C / 8; ++c8) {
-      uint4 o;
-      __nv_bfloat162* h = reinterpret_cast<__nv_bfloat162*>(&o);
+      float z[PPT][8];
+      z_chunk(yv, c8, z);
 #pragma unroll
-      for (int j = 0; j < 4; ++j) {
-        const int c = c8 * 8 + 2 * j, g0 = c / cpg, g1 = (c + 1) / cpg;
-        const float a = (z[c] - gmean[g0]) * grstd[g0] * sG[c] + sBe[c];
-        const float b = (z[c + 1] - gmean[g1]) * grstd[g1] * sG[c + 1] + sBe[c + 1];
-        h[j] = __floats2bfloat162_rn(a, b);
+      for (int q = 0; q < PPT; ++q) {
+        const int pp = p + 256 * q;
+        if (pp < S) {
+          uint4 o;
+          __nv_bfloat162* h = reinterpret_cast<__nv_bfloat162*>(&o);
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            const int c = c8 * 8 + 2 * j, g0 = c / cpg, g1 = (c + 1) / cpg;
+            const float a = (z[q][2 * j] - gmean[g0]) * grstd[g0] * sG[c] + sBe[c];
+            const float b = (z[q][2 * j + 1] - gmean[g1]) * grstd[g1] * sG[c + 1] + sBe[c + 1];
+            h[j] = __floats2bfloat162_rn(a, b);
+          }
+          *reinterpret_cast<uint4*>(dst + (size_t)pp * out_cs + c8 * 8) = o;
+        }
       }
-      *reinterpret_cast<uint4*>(dst + (size_t)p * out_cs + c8 * 8) = o;
     }
   }
 }
@@ -630,10 +661,10 @@ int trp_tail_launch(cudaStream_t s, const float* y32, const float* w, const floa
   RSG_REQUIRE(out_cs % 8 == 0 && out_co % 8 == 0, "trp_tail: output channel stride/offset must be multiples of 8");
   if (N == 0) return RSG_OK;
   switch (C) {
-    case 16: trp_tail_kernel<16, 8><<<N, 256, 0, s>>>(y32, w, bias, gamma, beta, eps, out, out_cs, out_co, S); break;
-    case 32: trp_tail_kernel<32, 8><<<N, 256, 0, s>>>(y32, w, bias, gamma, beta, eps, out, out_cs, out_co, S); break;
-    case 48: trp_tail_kernel<48, 8><<<N, 256, 0, s>>>(y32, w, bias, gamma, beta, eps, out, out_cs, out_co, S); break;
-    case 64: trp_tail_kernel<64, 8><<<N, 256, 0, s>>>(y32, w, bias, gamma, beta, eps, out, out_cs, out_co, S); break;
+    case 16: trp_tail_kernel<16, 8, 2><<<N, 256, 0, s>>>(y32, w, bias, gamma, beta, eps, out, out_cs, out_co, S); break;
+    case 32: trp_tail_kernel<32, 8, 2><<<N, 256, 0, s>>>(y32, w, bias, gamma, beta, eps, out, out_cs, out_co, S); break;
+    case 48: trp_tail_kernel<48, 8, 1><<<N, 256, 0, s>>>(y32, w, bias, gamma, beta, eps, out, out_cs, out_co, S); break;
+    case 64: trp_tail_kernel<64, 8, 1><<<N, 256, 0, s>>>(y32, w, bias, gamma, beta, eps, out, out_cs, out_co, S); break;
     default: rsg_set_error("trp_tail: unsupported channel count %d (16/32/48/64)", C); return RSG_ERR_ARG;
   }
   RSG_LAUNCH_CHECK();

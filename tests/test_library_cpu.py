@@ -70,10 +70,11 @@ def test_plan_builder_graph(key, n_conv):
         kinds[k] = kinds.get(k, 0) + 1
     # a fused BasicBlock op (C0 = 32 branch) stands for two convs, a fused Bottleneck op (layer1) for three
     assert kinds['stem'] == 1 and kinds['fuse'] == 8
-    assert kinds['conv'] + 2 * kinds.get('bblock', 0) + 3 * kinds.get('bneck', 0) == n_conv
+    # ... and the fp32 TRP tail (1x1 W conv + GroupNorm) for one conv
+    assert kinds['conv'] + 2 * kinds.get('bblock', 0) + 3 * kinds.get('bneck', 0) + kinds.get('trptail', 0) == n_conv
     assert kinds.get('bneck', 0) == 4
     if key == 'w32_crowdpose':
-        assert kinds['attention'] == 1 and kinds['groupnorm'] == 1 and info['S'] == 3072
+        assert kinds['attention'] == 1 and kinds['trptail'] == 1 and info['S'] == 3072
         # executed FLOPs: the reference graph (18.881 GFLOP/fwd) minus the folded type
         # branch (~1.1 GFLOP), plus nothing else
         assert 17.0e9 < pb.flops_per_fwd < 18.9e9
