@@ -53,6 +53,15 @@ class RsgError(RuntimeError):
 
 _lib = None
 
+
+def use_library(path):
+    """Bind another build of the library (tools/ experiments use librsg_b200_dbg.so = `make DEBUG_SWITCHES=1`, which keeps
+    the RSG_* environment switches of the kernels).  Must be called before the first lib() call."""
+    global LIB_PATH
+    if _lib is not None:
+        raise RsgError('use_library: the library is already loaded')
+    LIB_PATH = os.path.abspath(path)
+
 _SIGS = {
     'rsg_abi_version': (C.c_int, []),
     'rsg_last_error': (C.c_char_p, []),

@@ -164,8 +164,9 @@ eval_nms_kernel(const float* __restrict__ preds /*[n,K,3]*/, const double* __res
       }
     } else {
       // soft_oks_nms (nms.py:138-180) with the reference's own bookkeeping: an explicit `order` list that loses its
-      // head every round and is re-sorted by the decayed scores with scores.argsort()[::-1] -- so EQUAL scores (several
-      // detections rescored to exactly 0) come out in the reverse of their CURRENT relative order, round after round.
+      // head every round and is re-sorted by the decayed scores with scores.argsort()[::-1].  The re-sort is modelled
+      // as a STABLE sort (equal scores come out in the reverse of their current relative order); what NumPy does with
+      // exactly equal scores is implementation-defined, so ties are unspecified against the reference.
       int L = m;
       for (int a = tid; a < m; a += nt) {
         const double sa = cur[beg + a];

@@ -63,8 +63,9 @@ oks_nms_kernel(const float* __restrict__ kpts, const double* __restrict__ scores
 
 // soft_oks_nms (lib/nms/nms.py:138-180): up to max_dets rounds per image; every round keeps the head of the score-ordered
 // list and multiplies the scores of the others by exp(-oks^2 / thresh) (rescore(), nms.py:127-135, 'gaussian'), then
-// re-sorts what is left with scores.argsort()[::-1] -- reproduced with an explicit order list, so that EQUAL scores come
-// out in the reverse of their current relative order, exactly like the reference's re-sort does.  One CTA per image.
+// re-sorts what is left with scores.argsort()[::-1] -- reproduced with an explicit order list and a STABLE sort (equal
+// scores come out in the reverse of their current relative order; NumPy's own order of exactly equal scores is
+// implementation-defined, so ties are unspecified against the reference).  One CTA per image.
 __global__ void __launch_bounds__(128)
 soft_oks_nms_kernel(const float* __restrict__ kpts, const double* __restrict__ scores,
                     const double* __restrict__ areas, const int32_t* __restrict__ offs,

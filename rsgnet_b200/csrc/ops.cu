@@ -183,41 +183,46 @@ __device__ __forceinline__ uint4 pack8(const float* a) {
   return o;
 }
 
-// FUSE_ROWS output rows (n, y) per block: 32-bit index math only (the first version spent most of its time in five
-// 64-bit divisions per thread), 16 bytes per thread, consecutive threads = consecutive bytes of the row.  One row per
-// block (32768 blocks of 192 threads for a 64x48x32 map) was bound by the block launch rate, not by HBM.
-constexpr int FUSE_ROWS = 8;
-__global__ void __launch_bounds__(256) fuse_kernel(const FuseP p, int rows) {
-  const int c8 = p.C >> 3;
-  const int per_row = p.W * c8;
-  const int row_end = min(rows, ((int)blockIdx.x + 1) * FUSE_ROWS);
-  for (int row = blockIdx.x * FUSE_ROWS; row < row_end; ++row) {
-    const int n = row / p.H, y = row - n * p.H;
-    const bf16* base[4];
+// Flat element space (pixel, 8-channel group) with FUSE_E independent elements per thread: all loads of all terms are
+// issued before the first add, so ~16 16-byte loads are in flight per thread (the row-per-block version kept one per
+// term in flight and ran at 2.9 TB/s); divisions by runtime constants are multiplications by precomputed magics.
+constexpr int FUSE_E = 4;
+struct FuseIdx { uint32_t c8, W, H, magic_c8, magic_W, magic_H; };
+__global__ void __launch_bounds__(256) fuse_kernel(const FuseP p, const FuseIdx ix, uint32_t total) {
+  const uint32_t e0 = blockIdx.x * (256u * FUSE_E) + threadIdx.x;
+  uint4 v[FUSE_E][4];
+  uint32_t ooff[FUSE_E];
+  bool ok[FUSE_E];
+#pragma unroll
+  for (int k = 0; k < FUSE_E; ++k) {
+    const uint32_t e = e0 + 256u * k;
+    ok[k] = e < total;
+    const uint32_t ee = ok[k] ? e : 0u;
+    const uint32_t pix = ix.magic_c8 ? __umulhi(ee, ix.magic_c8) : ee, c = (ee - pix * ix.c8) * 8u;
+    const uint32_t row = ix.magic_W ? __umulhi(pix, ix.magic_W) : pix, x = pix - row * ix.W;
+    const uint32_t n = ix.magic_H ? __umulhi(row, ix.magic_H) : row, y = row - n * ix.H;
+    ooff[k] = pix * (uint32_t)p.out_cs + c;
 #pragma unroll
     for (int t = 0; t < 4; ++t) {
       if (t < p.nterms) {
         const ResP& q = p.t[t];
-        base[t] = q.p + ((size_t)(q.bs0 ? 0 : n) * q.H + (y >> q.shift)) * q.W * q.cs + q.co;
+        const bf16* src = q.p + ((size_t)((q.bs0 ? 0u : n) * (uint32_t)q.H + (y >> q.shift)) * (uint32_t)q.W + (x >> q.shift)) * q.cs + q.co + c;
+        v[k][t] = __ldg(reinterpret_cast<const uint4*>(src));
       }
     }
-    bf16* orow = p.out + ((size_t)n * p.H + y) * p.W * p.out_cs + p.out_co;
-    for (int e = threadIdx.x; e < per_row; e += blockDim.x) {
-      const int x = e / c8, c = (e - x * c8) * 8;
-      float a[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+  }
 #pragma unroll
-      for (int t = 0; t < 4; ++t) {
-        if (t < p.nterms) {
-          const ResP& q = p.t[t];
-          add8(a, __ldg(reinterpret_cast<const uint4*>(base[t] + (x >> q.shift) * q.cs + c)));
-        }
-      }
-      if (p.relu) {
+  for (int k = 0; k < FUSE_E; ++k) {
+    if (!ok[k]) continue;
+    float a[8] = {0, 0, 0, 0, 0, 0, 0, 0};
 #pragma unroll
-        for (int j = 0; j < 8; ++j) a[j] = fmaxf(a[j], 0.f);
-      }
-      *reinterpret_cast<uint4*>(orow + (size_t)x * p.out_cs + c) = pack8(a);
+    for (int t = 0; t < 4; ++t)
+      if (t < p.nterms) add8(a, v[k][t]);
+    if (p.relu) {
+#pragma unroll
+      for (int j = 0; j < 8; ++j) a[j] = fmaxf(a[j], 0.f);
     }
+    *reinterpret_cast<uint4*>(p.out + p.out_co + ooff[k]) = pack8(a);
   }
 }
 
@@ -393,50 +398,74 @@ relation_scores_kernel(const bf16* __restrict__ x, int cs, int co, int S, int C,
 // (final_layer / multi_final_layer, pose_rsgnet.py:961, 1000).  HBM-bound: one thread per pixel, the
 // Cin channels in registers, weights broadcast from shared memory, plane-coalesced fp32 stores.
 // ---------------------------------------------------------------------------------------------
-template <int CIN>
+// Tensor-core version (mma.sync m16n8k16; the fp32-FMA version needed Cout * CIN FMAs per pixel and ran at 2.5 TB/s):
+// a warp owns 16 consecutive pixels per step, A fragments come straight from global memory (lane (g, tq) reads the two
+// bf16 pairs of pixel rows g and g+8 it needs: four lanes cover one 16-byte run), the weights live in registers as B
+// fragments, and every accumulator register is one 32-byte run of a channel plane (8 consecutive pixels).
+template <int CIN, int NT>
 __global__ void __launch_bounds__(256)
 head1x1_kernel(const bf16* __restrict__ in, int in_cs, int in_co, const bf16* __restrict__ w, int w_ld,
                const float* __restrict__ bias, int Cout, unsigned M, unsigned HW, float* __restrict__ out, int relu) {
-  __shared__ float sw[32 * CIN];
-  __shared__ float sb[32];
-  for (int i = threadIdx.x; i < Cout * CIN; i += blockDim.x) sw[i] = __bfloat162float(w[(i / CIN) * w_ld + (i % CIN)]);
-  if (threadIdx.x < Cout) sb[threadIdx.x] = bias[threadIdx.x];
-  __syncthreads();
-  // two pixels per thread (256 apart, so both stay coalesced): every broadcast weight read feeds 8 FMAs
-  const unsigned m0 = blockIdx.x * 512u + threadIdx.x, m1 = m0 + 256u;
-  if (m0 >= M) return;
-  const bool two = m1 < M;
-  float x0[CIN], x1[CIN];
-  const uint4* s0 = reinterpret_cast<const uint4*>(in + (size_t)m0 * in_cs + in_co);
-  const uint4* s1 = reinterpret_cast<const uint4*>(in + (size_t)(two ? m1 : m0) * in_cs + in_co);
+  constexpr int KS = CIN / 16;
+  const int lane = threadIdx.x & 31, g = lane >> 2, tq = lane & 3;
+  const unsigned warp_global = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, nwarps = (gridDim.x * blockDim.x) >> 5;
+  // B fragments: b0 = W[n = 8j+g][k = 16ks + 2tq, +1], b1 = the same at k + 8
+  uint32_t bfr[NT][KS][2];
+  float bs[NT][2];
 #pragma unroll
-  for (int j = 0; j < CIN / 8; ++j) {
-    const uint4 u0 = __ldg(s0 + j), u1 = __ldg(s1 + j);
-    const __nv_bfloat162* h0 = reinterpret_cast<const __nv_bfloat162*>(&u0);
-    const __nv_bfloat162* h1 = reinterpret_cast<const __nv_bfloat162*>(&u1);
+  for (int j = 0; j < NT; ++j) {
+    const int n = 8 * j + g;
 #pragma unroll
-    for (int e = 0; e < 4; ++e) {
-      x0[j * 8 + 2 * e] = __bfloat162float(h0[e].x); x0[j * 8 + 2 * e + 1] = __bfloat162float(h0[e].y);
-      x1[j * 8 + 2 * e] = __bfloat162float(h1[e].x); x1[j * 8 + 2 * e + 1] = __bfloat162float(h1[e].y);
+    for (int ks = 0; ks < KS; ++ks) {
+      uint32_t b0 = 0, b1 = 0;
+      if (n < Cout) {
+        b0 = *reinterpret_cast<const uint32_t*>(w + (size_t)n * w_ld + 16 * ks + 2 * tq);
+        b1 = *reinterpret_cast<const uint32_t*>(w + (size_t)n * w_ld + 16 * ks + 2 * tq + 8);
+      }
+      bfr[j][ks][0] = b0; bfr[j][ks][1] = b1;
     }
+    bs[j][0] = (8 * j + 2 * tq < Cout) ? __ldg(bias + 8 * j + 2 * tq) : 0.f;
+    bs[j][1] = (8 * j + 2 * tq + 1 < Cout) ? __ldg(bias + 8 * j + 2 * tq + 1) : 0.f;
   }
-  const unsigned n0 = m0 / HW, n1 = (two ? m1 : m0) / HW;
-  float* op0 = out + (size_t)n0 * Cout * HW + (m0 - n0 * HW);
-  float* op1 = out + (size_t)n1 * Cout * HW + ((two ? m1 : m0) - n1 * HW);
-  for (int k = 0; k < Cout; ++k) {
-    float a0 = sb[k], a1 = a0;
-    const float4* wk = reinterpret_cast<const float4*>(sw + k * CIN);
+  const unsigned ntiles = (M + 15u) >> 4;
+  for (unsigned tile = warp_global; tile < ntiles; tile += nwarps) {
+    const unsigned m0 = tile * 16u + g, m1 = m0 + 8u;
+    const bool ok0 = m0 < M, ok1 = m1 < M;
+    const uint32_t* r0 = reinterpret_cast<const uint32_t*>(in + (size_t)(ok0 ? m0 : 0u) * in_cs + in_co) + tq;
+    const uint32_t* r1 = reinterpret_cast<const uint32_t*>(in + (size_t)(ok1 ? m1 : 0u) * in_cs + in_co) + tq;
+    uint32_t a[KS][4];
 #pragma unroll
-    for (int j = 0; j < CIN / 4; ++j) {
-      const float4 ww = wk[j];
-      a0 = fmaf(x0[4 * j], ww.x, a0); a0 = fmaf(x0[4 * j + 1], ww.y, a0);
-      a0 = fmaf(x0[4 * j + 2], ww.z, a0); a0 = fmaf(x0[4 * j + 3], ww.w, a0);
-      a1 = fmaf(x1[4 * j], ww.x, a1); a1 = fmaf(x1[4 * j + 1], ww.y, a1);
-      a1 = fmaf(x1[4 * j + 2], ww.z, a1); a1 = fmaf(x1[4 * j + 3], ww.w, a1);
+    for (int ks = 0; ks < KS; ++ks) {
+      a[ks][0] = __ldg(r0 + 8 * ks); a[ks][1] = __ldg(r1 + 8 * ks);
+      a[ks][2] = __ldg(r0 + 8 * ks + 4); a[ks][3] = __ldg(r1 + 8 * ks + 4);
     }
-    if (relu) { a0 = fmaxf(a0, 0.f); a1 = fmaxf(a1, 0.f); }
-    op0[(size_t)k * HW] = a0;
-    if (two) op1[(size_t)k * HW] = a1;
+    float acc[NT][4];
+#pragma unroll
+    for (int j = 0; j < NT; ++j) { acc[j][0] = bs[j][0]; acc[j][1] = bs[j][1]; acc[j][2] = bs[j][0]; acc[j][3] = bs[j][1]; }
+#pragma unroll
+    for (int ks = 0; ks < KS; ++ks)
+#pragma unroll
+      for (int j = 0; j < NT; ++j)
+        asm volatile(
+            "mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};\n"
+            : "+f"(acc[j][0]), "+f"(acc[j][1]), "+f"(acc[j][2]), "+f"(acc[j][3])
+            : "r"(a[ks][0]), "r"(a[ks][1]), "r"(a[ks][2]), "r"(a[ks][3]), "r"(bfr[j][ks][0]), "r"(bfr[j][ks][1]));
+    const unsigned n0 = m0 / HW, n1 = m1 / HW;
+    float* o0 = out + (size_t)n0 * Cout * HW + (m0 - n0 * HW);
+    float* o1 = out + (size_t)n1 * Cout * HW + (m1 - n1 * HW);
+#pragma unroll
+    for (int j = 0; j < NT; ++j) {
+#pragma unroll
+      for (int e = 0; e < 2; ++e) {
+        const int c = 8 * j + 2 * tq + e;
+        if (c < Cout) {
+          float v0 = acc[j][e], v1 = acc[j][2 + e];
+          if (relu) { v0 = fmaxf(v0, 0.f); v1 = fmaxf(v1, 0.f); }
+          if (ok0) o0[(size_t)c * HW] = v0;
+          if (ok1) o1[(size_t)c * HW] = v1;
+        }
+      }
+    }
   }
 }
 
@@ -586,14 +615,21 @@ int head1x1_launch(const ConvP& p, cudaStream_t s, int* handled) {
   *handled = 1;
   if (p.M == 0) return RSG_OK;
   const int HW = p.Hout * p.Wout;
-  dim3 grid(ceil_div(p.M, 512));
-#define RSG_HEAD(C) head1x1_kernel<C><<<grid, 256, 0, s>>>(p.in, p.in_cs, p.in_co, p.w, p.CinPad, p.bias, p.Cout, (unsigned)p.M, (unsigned)HW, p.out_f32, p.relu)
+  // persistent-ish: 8 CTAs of 8 warps per SM walk the 16-pixel tiles
+  long long nblk = ceil_div(ceil_div(p.M, 16), 8);
+  if (nblk > 8ll * rsg_num_sms()) nblk = 8ll * rsg_num_sms();
+  dim3 grid((unsigned)nblk);
+  RSG_REQUIRE(p.CinPad % 2 == 0 && ((uintptr_t)p.w % 4) == 0 && ((uintptr_t)p.in % 4) == 0, "head1x1: unaligned operand");
+  const int nt = (p.Cout + 7) / 8;
+#define RSG_HEAD2(C, T) head1x1_kernel<C, T><<<grid, 256, 0, s>>>(p.in, p.in_cs, p.in_co, p.w, p.CinPad, p.bias, p.Cout, (unsigned)p.M, (unsigned)HW, p.out_f32, p.relu)
+#define RSG_HEAD(C) do { if (nt <= 2) RSG_HEAD2(C, 2); else if (nt == 3) RSG_HEAD2(C, 3); else RSG_HEAD2(C, 4); } while (0)
   switch (p.Cin) {
     case 16: RSG_HEAD(16); break;
     case 32: RSG_HEAD(32); break;
     case 48: RSG_HEAD(48); break;
     default: RSG_HEAD(64); break;
   }
+#undef RSG_HEAD2
 #undef RSG_HEAD
   RSG_LAUNCH_CHECK();
   return RSG_OK;
@@ -621,12 +657,14 @@ int fuse_launch(cudaStream_t s, int nterms, const ResP* terms, bf16* out, int ou
   p.nterms = nterms;
   for (int i = 0; i < nterms; ++i) p.t[i] = terms[i];
   p.out = out; p.out_cs = out_cs; p.out_co = out_co; p.N = N; p.H = H; p.W = W; p.C = C; p.relu = relu;
-  const long long rows = (long long)N * H;
-  if (rows == 0 || W == 0) return RSG_OK;
-  RSG_REQUIRE(rows < (1ll << 31), "fuse: too many rows");
-  const int per_row = W * (C / 8);
-  const int threads = per_row >= 256 ? 256 : (per_row + 31) / 32 * 32;
-  fuse_kernel<<<(unsigned)((rows + FUSE_ROWS - 1) / FUSE_ROWS), threads, 0, s>>>(p, (int)rows);
+  const long long total = (long long)N * H * W * (C / 8);
+  if (total == 0) return RSG_OK;
+  RSG_REQUIRE(total < (1ll << 31) && (long long)N * H * W * out_cs < (1ll << 32), "fuse: tensor too large for 32-bit indexing");
+  auto magic = [](uint32_t d) { return d > 1 ? (uint32_t)(((1ull << 32) + d - 1) / d) : 0u; };   // exact while n * d < 2^32
+  FuseIdx ix{(uint32_t)(C / 8), (uint32_t)W, (uint32_t)H, magic((uint32_t)(C / 8)), magic((uint32_t)W), magic((uint32_t)H)};
+  RSG_REQUIRE((unsigned long long)total * (unsigned long long)(C / 8 > W ? (C / 8 > H ? C / 8 : H) : (W > H ? W : H)) < (1ull << 32),
+              "fuse: tensor too large for the division magics");
+  fuse_kernel<<<(unsigned)((total + 256 * FUSE_E - 1) / (256 * FUSE_E)), 256, 0, s>>>(p, ix, (uint32_t)total);
   RSG_LAUNCH_CHECK();
   return RSG_OK;
 }

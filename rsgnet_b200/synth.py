@@ -98,8 +98,9 @@ def evaluate_inputs(n_imgs, per_img, k, seed=13, ragged=True, zero_frac=0.03):
     """What rsgnet_validate hands to dataset.evaluate() (function.py:376-380, 452-458, 479): all_preds f32 [N,k,3]
     (image-space x, y, maxval), all_boxes f64 [N,6] (centre, scale, area = prod(scale*200) computed in fp32, box score)
     and one image id per detection -- with the detections of an image NOT contiguous (the loader order is arbitrary), a
-    few detections whose maxvals all sit below IN_VIS_THRE (rescored to exactly 0: score ties, only in images with at most
-    16 detections where NumPy's argsort is a stable insertion sort) and maxvals straddling the threshold.
+    few detections whose maxvals all sit below IN_VIS_THRE (rescored to exactly 0 -- at most ONE per image: the order
+    NumPy's argsort gives to exactly equal scores is implementation-defined (introsort / SIMD sorting networks), so
+    a fixture with score ties would pin an artefact of one NumPy build) and maxvals sitting exactly on the threshold.
     all_boxes[:, 0] carries the detection's own index (the centre is unused by rescoring and NMS), so that the
     reference's output dicts can be mapped back."""
     kpts, _, _, off = detections(n_imgs, per_img, k, seed=seed, ragged=ragged)
@@ -109,7 +110,8 @@ def evaluate_inputs(n_imgs, per_img, k, seed=13, ragged=True, zero_frac=0.03):
     counts = np.diff(off)
     mv = rs.uniform(0.0, 1.0, (n, k)).astype(np.float32)
     mv[rs.uniform(size=(n, k)) < 0.1] = np.float32(0.2)               # exactly at the threshold: not visible (strict >)
-    zero = (rs.uniform(size=n) < zero_frac) & (counts[img_of] <= 16)
+    zero = rs.uniform(size=n) < zero_frac
+    zero &= np.concatenate([[True], img_of[1:] != img_of[:-1]])        # only an image's first detection: no score ties
     mv[zero] = rs.uniform(0.0, 0.19, (int(zero.sum()), k)).astype(np.float32)
     kpts[:, :, 2] = mv
     perm = rs.permutation(n)                                          # interleave the images

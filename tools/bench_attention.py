@@ -7,6 +7,8 @@ import torch
 
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 from rsgnet_b200 import _engine, _lib  # noqa: E402
+if os.environ.get('RSG_DBG'):      # the build with the kernels' RSG_* switches: make -C rsgnet_b200/csrc DEBUG_SWITCHES=1
+    _lib.use_library(os.path.join(os.path.dirname(_lib.LIB_PATH), 'librsg_b200_dbg.so'))
 from rsgnet_b200._engine import PlanBuilder, View  # noqa: E402
 
 Cc = int(sys.argv[1]) if len(sys.argv) > 1 else 32
