@@ -192,7 +192,7 @@ NCU_TRAFFIC = {('conv_tcgen05', 'conv 32->32 taps9 s1 64x48 +res'): 201.44e6 + 7
 
 FAMILY = {0: 'stem', 1: 'conv_mma', 2: 'conv_tcgen05', 3: 'fuse', 4: 'maxpool', 5: 'trp_attention',
           6: 'relation_scores', 7: 'groupnorm', 8: 'bilinear', 9: 'conv_ws_tcgen05', 10: 'basic_block_tcgen05',
-          11: 'bottleneck_tcgen05'}
+          11: 'bottleneck_tcgen05', 12: 'conv_ws2_tcgen05'}
 
 
 # ---------------------------------------------------------------------------------------------

@@ -181,7 +181,8 @@ typedef struct rsg_conv_desc {
   int32_t relu;
   int32_t engine;              /* 0 = auto, 1 = force mma.sync path, 2 = force tcgen05 path,
                                   3 = weight-streaming tcgen05 path (w_tc5 packed with the NS of
-                                  rsg_conv_ws_config) */
+                                  rsg_conv_ws_config), 4 = the same on CTA pairs (w_tc5 packed as
+                                  rsg_conv_ws2_config describes) */
   int32_t pixel_shuffle_c;     /* > 0 (tcgen05 path only, omul = 2): the Cout = 4 * pixel_shuffle_c output
                                   columns are 4 sub-pixel phases of pixel_shuffle_c channels: column c goes
                                   to out pixel (2y + (c / psc) / 2, 2x + (c / psc) % 2), channel c % psc.
@@ -252,8 +253,8 @@ int rsg_plan_run(rsg_plan*, void* stream, void* const* ext, int n_ext, int n_fwd
                  int with_aux, int use_graph);
 /* Measurement aid: run ONE chunk of `nb` forwards eagerly with a CUDA event pair around every op.
  * ms[i] = device time of op i, kind[i]: 0 stem, 1 conv (generic mma.sync kernel), 2 conv (tcgen05
- * kernel), 3 fuse, 4 maxpool, 5 attention, 6 relation_scores, 7 groupnorm, 8 bilinear, 9 conv
- * (weight-streaming tcgen05 kernel), 10 fused basic block;
+ * kernel), 3 fuse, 4 maxpool, 5 attention, 6 relation_scores, 7 groupnorm / fp32 TRP tail, 8 bilinear, 9 conv
+ * (weight-streaming tcgen05 kernel), 10 fused basic block, 11 fused bottleneck, 12 conv (weight-streaming CTA-pair kernel);
  * flops[i] = MAC*2 the op executes for nb forwards (0 for the element-wise ops).  Arrays must hold
  * rsg_plan_num_ops entries; ops skipped (aux) get ms = -1. */
 int rsg_plan_profile(rsg_plan*, void* stream, void* const* ext, int n_ext, int nb, int n_crops,
@@ -269,9 +270,16 @@ int rsg_conv_tc5_config(int Cin, int CoutPad, int ntaps, int mode, int* NS, int*
 
 /* Weight-streaming tcgen05 conv kernel (many channels, small maps: the stage-3/4 low-resolution
  * branches): returns 1 and the output channels per CTA (NS) when it covers a stride-1 conv of this
- * shape on H x W maps, else 0.  The host packs w_tc5 as [CoutPad/NS][ntaps][Cin/8][NS][8] and sets
- * engine = 3. */
+ * shape on H x W maps, else 0.  The host packs w_tc5 as [CoutPad/NS][Cin/16][ntaps][2][NS][8] (the weights of a
+ * 16-channel chunk are ONE contiguous block: one bulk copy per pipeline stage) and sets engine = 3. */
 int rsg_conv_ws_config(int Cin, int CoutPad, int ntaps, int H, int W, int* NS);
+
+/* The same layers on CTA pairs (tcgen05.mma.cta_group::2, conv_ws2.cu): returns 1 when the pair kernel covers a stride-1
+ * conv of this shape (Cout a multiple of 128, a 256-pixel supertile at least 70 % full).  The host then packs w_tc5 as
+ * [CoutPad/128][2 halves][Cin/16][ntaps][2][64][8] (each CTA of a pair streams the 64 output channels of its half,
+ * one contiguous block per 16-channel chunk; inside every group of 64 output channels accumulator column 8g + 2j + e
+ * holds channel 16j + 2g + e, so that a lane quad of the epilogue owns one 128-byte line) and sets engine = 4. */
+int rsg_conv_ws2_config(int Cin, int CoutPad, int ntaps, int H, int W);
 
 /* Stand-alone conv launch (unit tests / micro-benchmarks): desc refs must be absolute. */
 int rsg_conv_run(void* stream, const rsg_conv_desc*, int N);

@@ -184,12 +184,25 @@ class PlanBuilder:
         # GEMM-shaped layers (K = taps*Cin >= 1152, >= 128 output channels) on maps small enough for the
         # flat formulation: weight-streaming kernel
         want_ws = (stride == 1 and omul == 1 and
-                   (engine == 3 or (engine == 0 and len(taps) * cin >= 1152 and cout_pad >= 128)))
-        if (tc5_ok and want_ws and dst is not None
+                   (engine in (3, 4) or (engine == 0 and len(taps) * cin >= 1152 and cout_pad >= 128)))
+        # the CTA-pair kernel is opt-in (engine=4): measured equal to the 1-CTA kernel in isolation and ~7 % slower inside
+        # the step (profiles/r2_notes.md), so the automatic routing keeps conv_ws
+        if (tc5_ok and want_ws and dst is not None and engine == 4
+                and _lib.lib().rsg_conv_ws2_config(cin, cout_pad, len(taps), Hin, Win)):
+            # CTA-pair kernel (tcgen05.mma.cta_group::2): each CTA streams the 64 output channels of its half
+            # [slice][half][16-channel chunk][tap][2 planes][64][8]: one contiguous block (one bulk copy) per chunk; the
+            # output channels of every group of 64 in accumulator-column order (the epilogue reads 16x256b TMEM blocks)
+            wt = wp[:, _quad_perm(cout_pad), :cin].reshape(len(taps), cout_pad // 128, 2, 64, cin // 16, 2, 8)
+            w_tc5 = self.const(_bf16_bits(wt.transpose(1, 2, 4, 0, 5, 3, 6)))
+            engine = 4
+        elif engine == 4:
+            raise ValueError(f'{name}: shape not covered by the CTA-pair weight-streaming kernel')
+        elif (tc5_ok and want_ws and dst is not None
                 and _lib.lib().rsg_conv_ws_config(cin, cout_pad, len(taps), Hin, Win, C.byref(ns))):
             NS = ns.value
-            wt = wp[:, :, :cin].reshape(len(taps), cout_pad // NS, NS, cin // 8, 8)
-            w_tc5 = self.const(_bf16_bits(wt.transpose(1, 0, 3, 2, 4)))
+            # [slice][16-channel chunk][tap][2 planes][NS][8]: one contiguous block per chunk
+            wt = wp[:, :, :cin].reshape(len(taps), cout_pad // NS, NS, cin // 16, 2, 8)
+            w_tc5 = self.const(_bf16_bits(wt.transpose(1, 3, 0, 4, 2, 5)))
             engine = 3
         elif engine == 3:
             raise ValueError(f'{name}: shape not covered by the weight-streaming kernel')

@@ -36,3 +36,5 @@ int conv_tc5_launch(const ConvP& p, cudaStream_t s, int* handled);
 // weight-streaming tcgen05 kernel (conv_ws.cu): many-channel stride-1 convs on small maps; w_tc5 must be
 // packed with the NS of rsg_conv_ws_config
 int conv_ws_launch(const ConvP& p, cudaStream_t s, int* handled);
+// the same on CTA pairs (conv_ws2.cu, tcgen05.mma.cta_group::2): w_tc5 packed as [CoutPad/128][2][ntaps][Cin/8][64][8]
+int conv_ws2_launch(const ConvP& p, cudaStream_t s, int* handled);

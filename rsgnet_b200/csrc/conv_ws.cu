@@ -40,7 +40,7 @@ constexpr int WS_MAX_T = 4;
 constexpr int WS_SMEM_BUDGET = 225 * 1024;
 
 struct WsP {
-  const bf16* w;        // [slice][tap][Cin/8][NS][8]
+  const bf16* w;        // [slice][chunk][tap][KC/8][NS][8]: the weights of a 16-channel chunk are one contiguous block
   const float* bias;
   int Cin, NS, Cout;
   int KC, nchunks, S, T, nimg;
@@ -112,27 +112,31 @@ conv_ws_kernel(const __grid_constant__ CUtensorMap in_map, const WsP p) {
 
   if (warp == 2) {
     // ===================== producer: one TMA box + ntaps bulk copies per stage =====================
-    if (lane == 0) {
-      pdl_wait();                                      // activations of the previous kernel
-      asm volatile("prefetch.tensormap [%0];" ::"l"(&in_map) : "memory");
-      const unsigned char* wsl = reinterpret_cast<const unsigned char*>(p.w) +
-                                 (size_t)slice * p.ntaps * (size_t)(p.Cin >> 3) * p.NS * 16u;
-      const size_t w_tap_stride = (size_t)(p.Cin >> 3) * p.NS * 16u;
-      const uint32_t tx_bytes = p.a_bytes + (uint32_t)p.ntaps * p.b_tap_bytes;
-      uint32_t it = 0, s = 0, sph = 0;              // ring slot / phase, carried incrementally (no divisions)
-      for (int u = first; u < p.nsuper; u += step) {
-        for (int c = 0; c < p.nchunks; ++c, ++it, s = (s + 1 == (uint32_t)p.S ? 0u : s + 1), sph ^= (s == 0)) {
-          mbar_wait(BAR(B_EMPTY + s), sph ^ 1u);
-          const uint32_t dst = sbase + s * p.stage_bytes;
-          if (p.skip & 1) { mbar_arrive(BAR(B_FULL + s)); continue; }
+    // The activation box (tensor TMA, lane 0) and the weights of ALL taps of the chunk as one contiguous block (bulk
+    // copies of at most 32 KB, lanes 1..): the weights are packed chunk-major for this.  A TMA operation costs ~100
+    // cycles of engine time whatever its size and ~130 cycles of a single thread's time to issue
+    // (tools/bulk_rate.cu); ten copies per chunk ran the kernel at the producer's rate.  A copy completing before the
+    // barrier is armed only drives the transaction count negative for a moment.
+    pdl_wait();                                      // activations of the previous kernel
+    if (lane == 0) asm volatile("prefetch.tensormap [%0];" ::"l"(&in_map) : "memory");
+    const uint32_t w_chunk_bytes = (uint32_t)p.ntaps * p.b_tap_bytes;
+    const unsigned char* wsl = reinterpret_cast<const unsigned char*>(p.w) + (size_t)slice * p.nchunks * (size_t)w_chunk_bytes;
+    const uint32_t tx_bytes = p.a_bytes + w_chunk_bytes;
+    const uint32_t piece = 32768u, my_off = (uint32_t)(lane - 1) * piece;
+    const uint32_t my_bytes = (lane >= 1 && my_off < w_chunk_bytes) ? (w_chunk_bytes - my_off < piece ? w_chunk_bytes - my_off : piece) : 0u;
+    uint32_t it = 0, s = 0, sph = 0;              // ring slot / phase, carried incrementally (no divisions)
+    for (int u = first; u < p.nsuper; u += step) {
+      for (int c = 0; c < p.nchunks; ++c, ++it, s = (s + 1 == (uint32_t)p.S ? 0u : s + 1), sph ^= (s == 0)) {
+        mbar_wait(BAR(B_EMPTY + s), sph ^ 1u);
+        const uint32_t dst = sbase + s * p.stage_bytes;
+        if (p.skip & 1) { if (lane == 0) mbar_arrive(BAR(B_FULL + s)); continue; }
+        if (lane == 0) {
           mbar_arrive_expect_tx(BAR(B_FULL + s), tx_bytes);
           tma_load_5d(dst, &in_map, BAR(B_FULL + s), 0, -1, -1, u * p.nimg, c * (p.KC >> 3));
-          const unsigned char* wc = wsl + (size_t)c * p.b_tap_bytes;
-          for (int tp = 0; tp < p.ntaps; ++tp)
-            bulk_load(dst + p.b_off + (uint32_t)tp * p.b_tap_bytes, wc + (size_t)tp * w_tap_stride, p.b_tap_bytes,
-                      BAR(B_FULL + s));
           if (it == 0) WS_STAMP(2);
           WS_STAMP(3);
+        } else if (my_bytes) {
+          bulk_load(dst + p.b_off + my_off, wsl + (size_t)c * w_chunk_bytes + my_off, my_bytes, BAR(B_FULL + s));
         }
       }
     }
@@ -357,8 +361,7 @@ bool ws_config(int Cin, int CoutPad, int ntaps, int H, int W, WsCfg* c) {
   if (nimg < 1) return false;
   if (nimg > 64) nimg = 64;
   c->NS = NS; c->nimg = nimg;
-  c->KC = 16;
-  { const char* e = rsg_dbg_env("RSG_WS_KC"); if (e && Cin % atoi(e) == 0) c->KC = atoi(e); }
+  c->KC = 16;                                    // fixed: the host packs the weights in 16-channel chunks
   c->T = (nimg * pitch + 127) / 128;
   c->plane_bytes = (uint32_t)nimg * pitch * 16u;
   c->a_bytes = (uint32_t)(c->KC / 8) * c->plane_bytes;
@@ -395,7 +398,7 @@ int make_flat_map(const ConvP& p, const WsCfg& c, CUtensorMap* m) {
 
 }  // namespace
 
-// Shape -> output channels per CTA: the host packer lays w_tc5 out as [CoutPad/NS][ntaps][Cin/8][NS][8].
+// Shape -> output channels per CTA: the host packer lays w_tc5 out as [CoutPad/NS][Cin/16 chunks][ntaps][2][NS][8].
 // Returns 0 when the weight-streaming kernel does not cover the shape.
 extern "C" int rsg_conv_ws_config(int Cin, int CoutPad, int ntaps, int H, int W, int* NS) {
   WsCfg c;

@@ -186,8 +186,8 @@ __device__ __forceinline__ uint4 pack8(const float* a) {
 // Flat element space (pixel, 8-channel group) with FUSE_E independent elements per thread: all loads of all terms are
 // issued before the first add, so ~16 16-byte loads are in flight per thread (the row-per-block version kept one per
 // term in flight and ran at 2.9 TB/s); divisions by runtime constants are multiplications by precomputed magics.
-constexpr int FUSE_E = 4;
 struct FuseIdx { uint32_t c8, W, H, magic_c8, magic_W, magic_H; };
+template <int FUSE_E>
 __global__ void __launch_bounds__(256) fuse_kernel(const FuseP p, const FuseIdx ix, uint32_t total) {
   const uint32_t e0 = blockIdx.x * (256u * FUSE_E) + threadIdx.x;
   uint4 v[FUSE_E][4];
@@ -223,6 +223,40 @@ __global__ void __launch_bounds__(256) fuse_kernel(const FuseP p, const FuseIdx 
       for (int j = 0; j < 8; ++j) a[j] = fmaxf(a[j], 0.f);
     }
     *reinterpret_cast<uint4*>(p.out + p.out_co + ooff[k]) = pack8(a);
+  }
+}
+
+__global__ void __launch_bounds__(256) fuse_rows_kernel(const FuseP p, int rows) {
+  const int c8 = p.C >> 3;
+  const int per_row = p.W * c8;
+  const int row_end = min(rows, ((int)blockIdx.x + 1) * 8);
+  for (int row = blockIdx.x * 8; row < row_end; ++row) {
+    const int n = row / p.H, y = row - n * p.H;
+    const bf16* base[4];
+#pragma unroll
+    for (int t = 0; t < 4; ++t) {
+      if (t < p.nterms) {
+        const ResP& q = p.t[t];
+        base[t] = q.p + ((size_t)(q.bs0 ? 0 : n) * q.H + (y >> q.shift)) * q.W * q.cs + q.co;
+      }
+    }
+    bf16* orow = p.out + ((size_t)n * p.H + y) * p.W * p.out_cs + p.out_co;
+    for (int e = threadIdx.x; e < per_row; e += blockDim.x) {
+      const int x = e / c8, c = (e - x * c8) * 8;
+      float a[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+#pragma unroll
+      for (int t = 0; t < 4; ++t) {
+        if (t < p.nterms) {
+          const ResP& q = p.t[t];
+          add8(a, __ldg(reinterpret_cast<const uint4*>(base[t] + (x >> q.shift) * q.cs + c)));
+        }
+      }
+      if (p.relu) {
+#pragma unroll
+        for (int j = 0; j < 8; ++j) a[j] = fmaxf(a[j], 0.f);
+      }
+      *reinterpret_cast<uint4*>(orow + (size_t)x * p.out_cs + c) = pack8(a);
+    }
   }
 }
 
@@ -664,7 +698,15 @@ int fuse_launch(cudaStream_t s, int nterms, const ResP* terms, bf16* out, int ou
   FuseIdx ix{(uint32_t)(C / 8), (uint32_t)W, (uint32_t)H, magic((uint32_t)(C / 8)), magic((uint32_t)W), magic((uint32_t)H)};
   RSG_REQUIRE((unsigned long long)total * (unsigned long long)(C / 8 > W ? (C / 8 > H ? C / 8 : H) : (W > H ? W : H)) < (1ull << 32),
               "fuse: tensor too large for the division magics");
-  fuse_kernel<<<(unsigned)((total + 256 * FUSE_E - 1) / (256 * FUSE_E)), 256, 0, s>>>(p, ix, (uint32_t)total);
+  const int fe = rsg_dbg_int("RSG_FUSE_E", 1);      // measured (tools/bench_ops.py fuse): 1 element per thread 51 us, 2: 59, 4: 95, row kernel: 72
+  if (fe == 0) {
+    const long long rows = (long long)N * H;
+    const int per_row = W * (C / 8);
+    const int threads = per_row >= 256 ? 256 : (per_row + 31) / 32 * 32;
+    fuse_rows_kernel<<<(unsigned)((rows + 8 - 1) / 8), threads, 0, s>>>(p, (int)rows);
+  } else if (fe == 1) fuse_kernel<1><<<(unsigned)((total + 256 - 1) / 256), 256, 0, s>>>(p, ix, (uint32_t)total);
+  else if (fe == 2) fuse_kernel<2><<<(unsigned)((total + 512 - 1) / 512), 256, 0, s>>>(p, ix, (uint32_t)total);
+  else fuse_kernel<4><<<(unsigned)((total + 1024 - 1) / 1024), 256, 0, s>>>(p, ix, (uint32_t)total);
   RSG_LAUNCH_CHECK();
   return RSG_OK;
 }

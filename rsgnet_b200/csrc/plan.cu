@@ -151,6 +151,15 @@ int run_conv(const rsg_conv_desc& d, const RunCtx& c, int N, cudaStream_t s, int
     if (rc) return rc;
     if (handled) return RSG_OK;
   }
+  if (d.engine == 4) {
+    // w_tc5 holds the CTA-pair kernel's packing (rsg_conv_ws2_config): no other kernel can read it
+    int handled = 0;
+    rc = conv_ws2_launch(p, s, &handled);
+    if (rc) return rc;
+    RSG_REQUIRE(handled, "conv: shape not covered by the CTA-pair weight-streaming kernel (engine=4)");
+    if (used_tc5) *used_tc5 = 3;
+    return RSG_OK;
+  }
   if (d.engine == 3) {
     // w_tc5 holds the weight-streaming kernel's packing (NS from rsg_conv_ws_config)
     int handled = 0;
@@ -456,7 +465,7 @@ extern "C" int rsg_plan_profile(rsg_plan* p, void* stream, void* const* ext, int
     rc = run_op(op, c, nb, n_crops, s, &tc5);
     cudaEventRecord(ev[2 * i + 1], s);
     if (op.kind == OP_CONV) {
-      if (tc5) kind[i] = tc5 == 2 ? 9 : 2;
+      if (tc5) kind[i] = tc5 == 3 ? 12 : (tc5 == 2 ? 9 : 2);
       flops[i] = 2.0 * op.conv.ntaps * op.conv.Cin * op.conv.Cout * (double)op.conv.Hout * op.conv.Wout * nb;
       if (op.conv.pixel_shuffle_c) flops[i] *= 16.0 / 36.0;      // the zero taps of the fused deconv are not credited
     } else if (op.kind == OP_BBLOCK) {

@@ -181,6 +181,51 @@ def test_conv_mma_production_shapes_vs_torch(cin, cout, k, stride, H, W, nres, s
     _lib.lib().rsg_plan_destroy(h)
 
 
+WS2_CASES = [
+    # Cin, Cout, k, H, W, N, nres   (engine=4: the CTA-pair weight-streaming kernel, conv_ws2.cu, tcgen05.mma.cta_group::2)
+    (128, 128, 3, 16, 12, 5, 1),      # one image per CTA; the last pair-unit has an out-of-bounds image
+    (128, 128, 3, 16, 12, 1, 0),      # a single image: the peer CTA computes nothing but must keep the protocol
+    (256, 256, 3, 8, 6, 21, 1),       # four images per CTA, two N slices
+    (128, 256, 3, 8, 6, 16, 2),
+    (128, 128, 3, 16, 12, 700, 1),    # 350 pair-units > 74 pairs: several per pair, both accumulator buffers, phases wrap
+    (256, 256, 3, 8, 6, 1200, 0),
+    (1152, 128, 1, 8, 6, 9, 0),       # 1x1 through the same path (72 K chunks)
+]
+
+
+@pytest.mark.parametrize('cin,cout,k,H,W,N,nres', WS2_CASES)
+def test_conv_ws2_cta_pair_vs_torch(cin, cout, k, H, W, N, nres):
+    g = torch.Generator().manual_seed(cin * 11 + cout + N)
+    x = torch.randn(N, cin, H, W, generator=g).bfloat16().float()
+    w = (torch.randn(cout, cin, k, k, generator=g) / (cin * k * k) ** 0.5).bfloat16().float()
+    b = torch.randn(cout, generator=g) * 0.1
+    rs = [torch.randn(N, cout, H, W, generator=g).bfloat16().float() for _ in range(nres)]
+    pb = PlanBuilder(N, reuse=False)
+    xin = pb.buf('x', H, W, cin + 8)
+    rbs = [pb.buf(f'r{i}', H, W, cout) for i in range(nres)]
+    ob = pb.buf('o', H, W, cout + 16)
+    pb.conv(View(xin, 8, cin), w.double().numpy(), b.double().numpy(), relu=True, dst=View(ob, 8, cout),
+            res=[(View(rb), 0) for rb in rbs], engine=4)
+    assert pb.ops[-1][1]['engine'] == 4
+    h = _run(pb, N)
+    pb.tensor_of(xin)[:N, ..., 8:] = x.permute(0, 2, 3, 1).cuda().bfloat16()
+    pb.tensor_of(xin)[:N, ..., :8] = 1e4
+    for rb, r in zip(rbs, rs):
+        pb.tensor_of(rb)[:N] = r.permute(0, 2, 3, 1).cuda().bfloat16()
+    pb.tensor_of(ob).fill_(7.0)
+    for _ in range(2):                       # twice: barrier state / TMEM are per launch
+        _exec(h, N)
+    ref = F.conv2d(x.cuda(), w.cuda(), b.cuda(), 1, k // 2)
+    for r in rs:
+        ref = ref + r.cuda()
+    ref = F.relu(ref).cpu()
+    got = pb.tensor_of(ob)[:N, ..., 8:8 + cout].float().permute(0, 3, 1, 2).cpu()
+    err = (got - ref).abs().max().item()
+    assert err <= 2e-2 * max(ref.abs().max().item(), 1.0), err
+    assert torch.all(pb.tensor_of(ob)[:N, ..., :8] == 7.0) and torch.all(pb.tensor_of(ob)[:N, ..., 8 + cout:] == 7.0)
+    _lib.lib().rsg_plan_destroy(h)
+
+
 S2_CASES = [
     # Cin, Cout, Hin, Win, N, nres, res_shift   (engine=2: stride-2 3x3 on the tcgen05 kernel, four TMA phase patches)
     (64, 64, 32, 24, 3, 0, 0),
