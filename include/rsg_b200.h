@@ -273,6 +273,10 @@ int rsg_conv_tc5_config(int Cin, int CoutPad, int ntaps, int mode, int* NS, int*
  * shape on H x W maps, else 0.  The host packs w_tc5 as [CoutPad/NS][Cin/16][ntaps][2][NS][8] (the weights of a
  * 16-channel chunk are ONE contiguous block: one bulk copy per pipeline stage) and sets engine = 3. */
 int rsg_conv_ws_config(int Cin, int CoutPad, int ntaps, int H, int W, int* NS);
+/* The same for stride 1 or 2 (Hin x Win = the INPUT map).  Stride 2 (the fuse-layer / transition down-paths onto the
+ * 16x12 and 8x6 maps, pose_rsgnet.py:219-246, 841-853) keeps the four pixel-parity phases of the input as separate
+ * plane sets per stage (TMA boxes with an element stride of 2), so no MMA row or tap is wasted. */
+int rsg_conv_ws_config2(int Cin, int CoutPad, int ntaps, int Hin, int Win, int stride, int* NS);
 
 /* The same layers on CTA pairs (tcgen05.mma.cta_group::2, conv_ws2.cu): returns 1 when the pair kernel covers a stride-1
  * conv of this shape (Cout a multiple of 128, a 256-pixel supertile at least 70 % full).  The host then packs w_tc5 as

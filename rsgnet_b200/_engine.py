@@ -183,8 +183,11 @@ class PlanBuilder:
         ns = C.c_int()
         # GEMM-shaped layers (K = taps*Cin >= 1152, >= 128 output channels) on maps small enough for the
         # flat formulation: weight-streaming kernel
-        want_ws = (stride == 1 and omul == 1 and
-                   (engine in (3, 4) or (engine == 0 and len(taps) * cin >= 1152 and cout_pad >= 128)))
+        # ... and the stride-2 down-paths whose OUTPUT map is small (<= 16x12: the 3x3 s2 convs of the fuse layers and
+        # transitions onto branches 2 and 3), in the flat stride-2 formulation of the same kernel
+        want_ws = (omul == 1 and
+                   (engine in (3, 4) or (engine == 0 and stride == 1 and len(taps) * cin >= 1152 and cout_pad >= 128)
+                    or (engine == 0 and stride == 2 and len(taps) == 9 and cout_pad >= 64 and Hout * Wout <= 192)))
         # the CTA-pair kernel is opt-in (engine=4): measured equal to the 1-CTA kernel in isolation and ~7 % slower inside
         # the step (profiles/r2_notes.md), so the automatic routing keeps conv_ws
         if (tc5_ok and want_ws and dst is not None and engine == 4
@@ -197,8 +200,8 @@ class PlanBuilder:
             engine = 4
         elif engine == 4:
             raise ValueError(f'{name}: shape not covered by the CTA-pair weight-streaming kernel')
-        elif (tc5_ok and want_ws and dst is not None
-                and _lib.lib().rsg_conv_ws_config(cin, cout_pad, len(taps), Hin, Win, C.byref(ns))):
+        elif (tc5_ok and want_ws and dst is not None and engine != 4
+                and _lib.lib().rsg_conv_ws_config2(cin, cout_pad, len(taps), Hin, Win, stride, C.byref(ns))):
             NS = ns.value
             # [slice][16-channel chunk][tap][2 planes][NS][8]: one contiguous block per chunk
             wt = wp[:, :, :cin].reshape(len(taps), cout_pad // NS, NS, cin // 16, 2, 8)

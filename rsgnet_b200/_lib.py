@@ -110,6 +110,7 @@ _SIGS = {
                                    C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p]),
     'rsg_conv_tc5_config': (C.c_int, [C.c_int] * 4 + [C.POINTER(C.c_int)] * 3),
     'rsg_conv_ws_config': (C.c_int, [C.c_int] * 5 + [C.POINTER(C.c_int)]),
+    'rsg_conv_ws_config2': (C.c_int, [C.c_int] * 6 + [C.POINTER(C.c_int)]),
     'rsg_conv_ws2_config': (C.c_int, [C.c_int] * 5),
     'rsg_conv_run': (C.c_int, [C.c_void_p, C.POINTER(ConvDesc), C.c_int]),
 }

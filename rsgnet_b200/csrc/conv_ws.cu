@@ -44,9 +44,10 @@ struct WsP {
   const float* bias;
   int Cin, NS, Cout;
   int KC, nchunks, S, T, nimg;
+  int nph;              // 1 (stride 1) or 4 phase-plane sets (stride 2): one TMA box each
   int ntaps;
-  int tapoff[9];        // (1+dy)*P + (1+dx), pixels (= 16-byte units)
-  int H, W, P, pitch;   // P = W + 1, pitch = (H + 1) * P pixels per image
+  int tapoff[9];        // [phase block +] (1+dy)*P + (1+dx), pixels (= 16-byte units)
+  int H, W, P, pitch;   // OUTPUT map size; P = W + 1, pitch = (H + 1) * P pixels per image
   uint32_t magic_pitch, magic_P;
   int N, nsuper;
   bf16* out;
@@ -55,7 +56,7 @@ struct WsP {
   ResP res[4];
   int relu;
   int v32;              // bit0: output rows 32-byte aligned, bit1: residual term 0 too (LDG/STG.256)
-  uint32_t plane_bytes, a_bytes, b_off, b_tap_bytes, stage_bytes, tmem_cols;
+  uint32_t plane_bytes, phase_bytes, a_bytes, b_off, b_tap_bytes, stage_bytes, tmem_cols;   // phase_bytes: one phase's planes, padded to 128 B
   long long* dbg;       // debug timeline of CTA (0,0): globaltimer stamps [16] or nullptr
   int skip;             // debug: bit0 no loads, bit1 one tap only, bit2 no residual loads / stores
 };
@@ -121,7 +122,7 @@ conv_ws_kernel(const __grid_constant__ CUtensorMap in_map, const WsP p) {
     if (lane == 0) asm volatile("prefetch.tensormap [%0];" ::"l"(&in_map) : "memory");
     const uint32_t w_chunk_bytes = (uint32_t)p.ntaps * p.b_tap_bytes;
     const unsigned char* wsl = reinterpret_cast<const unsigned char*>(p.w) + (size_t)slice * p.nchunks * (size_t)w_chunk_bytes;
-    const uint32_t tx_bytes = p.a_bytes + w_chunk_bytes;
+    const uint32_t tx_bytes = (uint32_t)p.nph * (uint32_t)(p.KC >> 3) * p.plane_bytes + w_chunk_bytes;   // bytes the copies deliver (phase blocks are padded)
     const uint32_t piece = 32768u, my_off = (uint32_t)(lane - 1) * piece;
     const uint32_t my_bytes = (lane >= 1 && my_off < w_chunk_bytes) ? (w_chunk_bytes - my_off < piece ? w_chunk_bytes - my_off : piece) : 0u;
     uint32_t it = 0, s = 0, sph = 0;              // ring slot / phase, carried incrementally (no divisions)
@@ -132,9 +133,16 @@ conv_ws_kernel(const __grid_constant__ CUtensorMap in_map, const WsP p) {
         if (p.skip & 1) { if (lane == 0) mbar_arrive(BAR(B_FULL + s)); continue; }
         if (lane == 0) {
           mbar_arrive_expect_tx(BAR(B_FULL + s), tx_bytes);
-          tma_load_5d(dst, &in_map, BAR(B_FULL + s), 0, -1, -1, u * p.nimg, c * (p.KC >> 3));
+          if (p.nph == 1) tma_load_5d(dst, &in_map, BAR(B_FULL + s), 0, -1, -1, u * p.nimg, c * (p.KC >> 3));
           if (it == 0) WS_STAMP(2);
           WS_STAMP(3);
+        }
+        if (p.nph == 4 && lane >= 28) {
+          // stride 2: phase (py, px) = the input pixels (2y' + py, 2x' + px), loaded with an element stride of 2 from
+          // (px - 2, py - 2) so that plane row / column 0 is y' / x' = -1 (out of bounds: the zero padding)
+          const int ph = lane - 28;
+          tma_load_5d(dst + (uint32_t)ph * p.phase_bytes, &in_map, BAR(B_FULL + s), 0, (ph & 1) - 2,
+                      (ph >> 1) - 2, u * p.nimg, c * (p.KC >> 3));
         } else if (my_bytes) {
           bulk_load(dst + p.b_off + my_off, wsl + (size_t)c * w_chunk_bytes + my_off, my_bytes, BAR(B_FULL + s));
         }
@@ -335,12 +343,15 @@ void ws_dump_timeline() {
 }
 
 struct WsCfg {
-  int NS, KC, nimg, T, S;
+  int NS, KC, nimg, T, S, nph;
+  uint32_t phase_bytes;
   uint32_t plane_bytes, a_bytes, b_off, b_tap_bytes, stage_bytes;
 };
 
-bool ws_config(int Cin, int CoutPad, int ntaps, int H, int W, WsCfg* c) {
-  if (Cin % 16 != 0 || ntaps < 1 || ntaps > 9 || H < 1 || W < 1) return false;
+// H, W: the OUTPUT map ((Hin - 1) / stride + 1 ...); stride 2 keeps four phase-plane sets of the input per stage
+bool ws_config(int Cin, int CoutPad, int ntaps, int H, int W, int stride, WsCfg* c) {
+  if (Cin % 16 != 0 || ntaps < 1 || ntaps > 9 || H < 1 || W < 1 || (stride != 1 && stride != 2)) return false;
+  c->nph = stride == 2 ? 4 : 1;
   int NS = 0;
   if (CoutPad % 128 == 0) NS = 128;
   else if (CoutPad <= 256 && CoutPad % 16 == 0) NS = CoutPad;
@@ -356,7 +367,7 @@ bool ws_config(int Cin, int CoutPad, int ntaps, int H, int W, WsCfg* c) {
   }
   int tmax = 512 / NS;
   if (tmax > WS_MAX_T) tmax = WS_MAX_T;
-  if (P + 1 > 64 || P > 256 || H + 1 > 256) return false;
+  if (P + 1 > 64 || P * stride > 256 || (H + 1) * stride > 256) return false;
   int nimg = tmax * 128 / pitch;
   if (nimg < 1) return false;
   if (nimg > 64) nimg = 64;
@@ -364,7 +375,8 @@ bool ws_config(int Cin, int CoutPad, int ntaps, int H, int W, WsCfg* c) {
   c->KC = 16;                                    // fixed: the host packs the weights in 16-channel chunks
   c->T = (nimg * pitch + 127) / 128;
   c->plane_bytes = (uint32_t)nimg * pitch * 16u;
-  c->a_bytes = (uint32_t)(c->KC / 8) * c->plane_bytes;
+  c->phase_bytes = ((uint32_t)(c->KC / 8) * c->plane_bytes + 127u) & ~127u;       // TMA destinations are 128-byte aligned
+  c->a_bytes = c->nph == 1 ? (uint32_t)(c->KC / 8) * c->plane_bytes : 4u * c->phase_bytes;
   c->b_off = (c->a_bytes + (uint32_t)(P + 1) * 16u + 127u) & ~127u;
   c->b_tap_bytes = (uint32_t)(c->KC / 8) * NS * 16u;
   c->stage_bytes = (c->b_off + (uint32_t)ntaps * c->b_tap_bytes + 127u) & ~127u;
@@ -378,7 +390,7 @@ bool ws_config(int Cin, int CoutPad, int ntaps, int H, int W, WsCfg* c) {
   return true;
 }
 
-int make_flat_map(const ConvP& p, const WsCfg& c, CUtensorMap* m) {
+int make_flat_map(const ConvP& p, const WsCfg& c, int stride, CUtensorMap* m) {
   EncodeTiledFn enc = tensor_map_encoder();
   RSG_REQUIRE(enc, "cuTensorMapEncodeTiled is not available from this driver");
   const cuuint64_t es = 2;
@@ -387,12 +399,14 @@ int make_flat_map(const ConvP& p, const WsCfg& c, CUtensorMap* m) {
   cuuint64_t dims[5] = {8, (cuuint64_t)p.Win, (cuuint64_t)p.Hin, (cuuint64_t)p.N, (cuuint64_t)(p.Cin / 8)};
   cuuint64_t strides[4] = {(cuuint64_t)p.in_cs * es, (cuuint64_t)p.Win * p.in_cs * es,
                            (cuuint64_t)p.Hin * p.Win * p.in_cs * es, 16};
-  cuuint32_t box[5] = {8, (cuuint32_t)(p.Win + 1), (cuuint32_t)(p.Hin + 1), (cuuint32_t)c.nimg, (cuuint32_t)(c.KC / 8)};
-  cuuint32_t estr[5] = {1, 1, 1, 1, 1};
+  // with an element stride the box extent counts SOURCE elements: Wout + 1 loaded pixels span (Wout + 1) * stride of them
+  cuuint32_t box[5] = {8, (cuuint32_t)((p.Wout + 1) * stride), (cuuint32_t)((p.Hout + 1) * stride), (cuuint32_t)c.nimg,
+                       (cuuint32_t)(c.KC / 8)};
+  cuuint32_t estr[5] = {1, (cuuint32_t)stride, (cuuint32_t)stride, 1, 1};
   CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 5, (void*)(p.in + p.in_co), dims, strides, box, estr,
                    CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE,
                    CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-  RSG_REQUIRE(r == CUDA_SUCCESS, "cuTensorMapEncodeTiled (flat map) failed with %d", (int)r);
+  RSG_REQUIRE(r == CUDA_SUCCESS, "cuTensorMapEncodeTiled (flat map, stride %d) failed with %d", stride, (int)r);
   return RSG_OK;
 }
 
@@ -400,11 +414,15 @@ int make_flat_map(const ConvP& p, const WsCfg& c, CUtensorMap* m) {
 
 // Shape -> output channels per CTA: the host packer lays w_tc5 out as [CoutPad/NS][Cin/16 chunks][ntaps][2][NS][8].
 // Returns 0 when the weight-streaming kernel does not cover the shape.
-extern "C" int rsg_conv_ws_config(int Cin, int CoutPad, int ntaps, int H, int W, int* NS) {
+extern "C" int rsg_conv_ws_config2(int Cin, int CoutPad, int ntaps, int Hin, int Win, int stride, int* NS) {
+  if (stride != 1 && stride != 2) return 0;
   WsCfg c;
-  if (!ws_config(Cin, CoutPad, ntaps, H, W, &c)) return 0;
+  if (!ws_config(Cin, CoutPad, ntaps, (Hin - 1) / stride + 1, (Win - 1) / stride + 1, stride, &c)) return 0;
   if (NS) *NS = c.NS;
   return 1;
+}
+extern "C" int rsg_conv_ws_config(int Cin, int CoutPad, int ntaps, int H, int W, int* NS) {
+  return rsg_conv_ws_config2(Cin, CoutPad, ntaps, H, W, 1, NS);
 }
 
 int conv_ws_launch(const ConvP& p, cudaStream_t s, int* handled) {
@@ -412,25 +430,34 @@ int conv_ws_launch(const ConvP& p, cudaStream_t s, int* handled) {
   static const bool disabled = rsg_dbg_env("RSG_DISABLE_WS") != nullptr;
   if (disabled) return RSG_OK;
   if (!p.w_tc5 || !p.out || p.out_f32) return RSG_OK;
-  if (p.stride != 1 || p.omul != 1 || p.ooy != 0 || p.oox != 0) return RSG_OK;
-  if (p.Hout != p.Hin || p.Wout != p.Win || p.oH != p.Hin || p.oW != p.Win) return RSG_OK;
+  if ((p.stride != 1 && p.stride != 2) || p.omul != 1 || p.ooy != 0 || p.oox != 0) return RSG_OK;
+  if (p.Hout != (p.Hin - 1) / p.stride + 1 || p.Wout != (p.Win - 1) / p.stride + 1 || p.oH != p.Hout || p.oW != p.Wout) return RSG_OK;
   if (p.Cout % 16 != 0 || p.in_cs % 8 != 0 || p.in_co % 8 != 0 || p.out_cs % 8 != 0 || p.out_co % 8 != 0) return RSG_OK;
   for (int t = 0; t < p.ntaps && t < 16; ++t)
     if (p.dy[t] < -1 || p.dy[t] > 1 || p.dx[t] < -1 || p.dx[t] > 1) return RSG_OK;
   for (int q = 0; q < p.nres; ++q)
     if (p.res[q].cs % 8 != 0 || p.res[q].co % 8 != 0) return RSG_OK;
   WsCfg c;
-  if (!ws_config(p.Cin, p.CoutPad, p.ntaps, p.Hin, p.Win, &c)) return RSG_OK;
+  if (!ws_config(p.Cin, p.CoutPad, p.ntaps, p.Hout, p.Wout, p.stride, &c)) return RSG_OK;
   if (p.M == 0) { *handled = 1; return RSG_OK; }
   if ((long long)p.N * (p.Hin + 1) * (p.Win + 1) >= (1ll << 31)) return RSG_OK;
 
   WsP k;
   memset(&k, 0, sizeof(k));
   k.w = p.w_tc5; k.bias = p.bias; k.Cin = p.Cin; k.NS = c.NS; k.Cout = p.Cout;
-  k.KC = c.KC; k.nchunks = p.Cin / c.KC; k.S = c.S; k.T = c.T; k.nimg = c.nimg;
+  k.KC = c.KC; k.nchunks = p.Cin / c.KC; k.S = c.S; k.T = c.T; k.nimg = c.nimg; k.nph = c.nph;
   k.ntaps = p.ntaps;
-  k.H = p.Hin; k.W = p.Win; k.P = p.Win + 1; k.pitch = (p.Hin + 1) * k.P;
-  for (int t = 0; t < p.ntaps; ++t) k.tapoff[t] = (1 + p.dy[t]) * k.P + (1 + p.dx[t]);
+  k.H = p.Hout; k.W = p.Wout; k.P = p.Wout + 1; k.pitch = (p.Hout + 1) * k.P;
+  for (int t = 0; t < p.ntaps; ++t) {
+    if (p.stride == 1) k.tapoff[t] = (1 + p.dy[t]) * k.P + (1 + p.dx[t]);
+    else {
+      // input pixel (2y + dy, 2x + dx): dy = 0 -> even-row phase at y' = y; dy = -1 -> odd-row phase at y' = y - 1; dy = +1 -> odd-row
+      // phase at y' = y (the same for x); plane row / column 0 is y' / x' = -1
+      const int ph = (p.dy[t] != 0 ? 2 : 0) + (p.dx[t] != 0 ? 1 : 0);
+      const int phase_px = ph * (int)(c.phase_bytes / 16u);
+      k.tapoff[t] = phase_px + (1 + (p.dy[t] == -1 ? -1 : 0)) * k.P + (1 + (p.dx[t] == -1 ? -1 : 0));
+    }
+  }
   // magic = ceil(2^32 / d): exact for n * d < 2^32 (n < 512 here)
   k.magic_pitch = k.pitch > 1 ? (uint32_t)(((1ull << 32) + k.pitch - 1) / k.pitch) : 0u;
   k.magic_P = k.P > 1 ? (uint32_t)(((1ull << 32) + k.P - 1) / k.P) : 0u;
@@ -454,7 +481,7 @@ int conv_ws_launch(const ConvP& p, cudaStream_t s, int* handled) {
     }
     k.dbg = g_dbg_buf + (size_t)(dbg_launch++ % 64) * 16;
   }
-  k.plane_bytes = c.plane_bytes; k.a_bytes = c.a_bytes; k.b_off = c.b_off; k.b_tap_bytes = c.b_tap_bytes;
+  k.plane_bytes = c.plane_bytes; k.phase_bytes = c.phase_bytes; k.a_bytes = c.a_bytes; k.b_off = c.b_off; k.b_tap_bytes = c.b_tap_bytes;
   k.stage_bytes = c.stage_bytes;
   uint32_t cols = 32;
   while (cols < (uint32_t)(c.T * c.NS)) cols <<= 1;
@@ -477,7 +504,7 @@ int conv_ws_launch(const ConvP& p, cudaStream_t s, int* handled) {
   dim3 grid((unsigned)gx, (unsigned)nslices);
   CUtensorMap map;
   memset(&map, 0, sizeof(map));
-  { int rc = make_flat_map(p, c, &map); if (rc) return rc; }
+  { int rc = make_flat_map(p, c, p.stride, &map); if (rc) return rc; }
   RSG_CUDA(launch_pdl(conv_ws_kernel, grid, dim3(WS_THREADS), smem, s, map, k));
   *handled = 1;
   return RSG_OK;

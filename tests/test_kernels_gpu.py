@@ -226,6 +226,59 @@ def test_conv_ws2_cta_pair_vs_torch(cin, cout, k, H, W, N, nres):
     _lib.lib().rsg_plan_destroy(h)
 
 
+WS_S2_CASES = [
+    # Cin, Cout, Hin, Win, N, nres, res_shift   (engine=3, stride 2: the flat stride-2 formulation of conv_ws.cu, four phase-plane sets)
+    (128, 256, 16, 12, 7, 3, 0),      # stage4 fuse_layers.3.2 + three residual terms -> 8x6
+    (128, 256, 16, 12, 9, 0, 0),      # transition3
+    (64, 256, 16, 12, 5, 0, 0),
+    (32, 256, 16, 12, 5, 0, 0),
+    (64, 128, 32, 24, 5, 2, 1),       # stage3/4 fuse_layers.2.1 + identity + up-sampled term -> 16x12
+    (32, 128, 32, 24, 300, 0, 0),     # more supertiles than CTAs
+    (64, 64, 32, 24, 3, 0, 0),        # NS = 64
+    (64, 128, 13, 11, 3, 1, 0),       # odd input size: Hout = 7, Wout = 6
+    (192, 384, 24, 18, 4, 3, 0),      # W48 stage4 fuse_layers.3.2
+]
+
+
+@pytest.mark.parametrize('cin,cout,H,W,N,nres,shift', WS_S2_CASES)
+def test_conv_ws_stride2_vs_torch(cin, cout, H, W, N, nres, shift):
+    g = torch.Generator().manual_seed(cin + 5 * cout + H + N)
+    x = torch.randn(N, cin, H, W, generator=g).bfloat16().float()
+    w = (torch.randn(cout, cin, 3, 3, generator=g) / (cin * 9) ** 0.5).bfloat16().float()
+    b = torch.randn(cout, generator=g) * 0.1
+    Ho, Wo = (H - 1) // 2 + 1, (W - 1) // 2 + 1
+    pb = PlanBuilder(N, reuse=False)
+    xin = pb.buf('x', H, W, cin + 8)
+    res, rts = [], []
+    for i in range(nres):
+        sh = shift if i == nres - 1 else 0
+        rh, rw = (Ho >> sh, Wo >> sh) if sh else (Ho, Wo)
+        rb = pb.buf(f'r{i}', rh, rw, cout)
+        res.append((View(rb), sh))
+        rts.append((rb, torch.randn(N, cout, rh, rw, generator=g).bfloat16().float(), sh))
+    ob = pb.buf('o', Ho, Wo, cout + 8)
+    pb.conv(View(xin, 8, cin), w.double().numpy(), b.double().numpy(), stride=2, relu=True,
+            dst=View(ob, 0, cout), res=res, engine=3)
+    assert pb.ops[-1][1]['engine'] == 3
+    h = _run(pb, N)
+    pb.tensor_of(xin)[:N, ..., 8:] = x.permute(0, 2, 3, 1).cuda().bfloat16()
+    pb.tensor_of(xin)[:N, ..., :8] = 1e4
+    for rb, r, _ in rts:
+        pb.tensor_of(rb)[:N] = r.permute(0, 2, 3, 1).cuda().bfloat16()
+    pb.tensor_of(ob).fill_(7.0)
+    _exec(h, N)
+    ref = F.conv2d(x.cuda(), w.cuda(), b.cuda(), 2, 1)
+    for _, r, sh in rts:
+        r = r.cuda()
+        ref = ref + (F.interpolate(r, scale_factor=2 ** sh, mode='nearest') if sh else r)
+    ref = F.relu(ref).cpu()
+    got = pb.tensor_of(ob)[:N, ..., :cout].float().permute(0, 3, 1, 2).cpu()
+    err = (got - ref).abs().max().item()
+    assert err <= 2e-2 * max(ref.abs().max().item(), 1.0), err
+    assert torch.all(pb.tensor_of(ob)[:N, ..., cout:] == 7.0)
+    _lib.lib().rsg_plan_destroy(h)
+
+
 S2_CASES = [
     # Cin, Cout, Hin, Win, N, nres, res_shift   (engine=2: stride-2 3x3 on the tcgen05 kernel, four TMA phase patches)
     (64, 64, 32, 24, 3, 0, 0),

@@ -17,15 +17,17 @@ cin, cout, k, H, W, N = [int(v) for v in sys.argv[1:7]]
 nres = int(sys.argv[7]) if len(sys.argv) > 7 else 0
 engine = int(sys.argv[8]) if len(sys.argv) > 8 else 0
 iters = int(sys.argv[9]) if len(sys.argv) > 9 else 20
+stride = int(sys.argv[10]) if len(sys.argv) > 10 else 1
+Ho, Wo = (H - 1) // stride + 1, (W - 1) // stride + 1
 rs = np.random.RandomState(0)
 w = rs.standard_normal((cout, cin, k, k)) / np.sqrt(cin * k * k)
 pb = PlanBuilder(N, reuse=False)
 xin = pb.buf('x', H, W, cin)
-rb = pb.buf('r', H, W, cout)
-ob = pb.buf('o', H, W, cout)
+rb = pb.buf('r', Ho, Wo, cout)
+ob = pb.buf('o', Ho, Wo, cout)
 REPS = 10    # identical launches per graph replay: the host launch path must not bound the measurement
 for _ in range(REPS):
-    pb.conv(View(xin), w, np.zeros(cout), relu=True, dst=View(ob), res=[(View(rb), 0)] * nres, engine=engine)
+    pb.conv(View(xin), w, np.zeros(cout), stride=stride, relu=True, dst=View(ob), res=[(View(rb), 0)] * nres, engine=engine)
 pb.allocate('cuda')
 h = C.c_void_p()
 _lib.check(_lib.lib().rsg_plan_create(C.byref(h), N))
@@ -45,6 +47,6 @@ with torch.cuda.stream(s):
     e1.record(s)
 s.synchronize()
 ms = e0.elapsed_time(e1) / iters / REPS
-fl = 2.0 * k * k * cin * cout * H * W * N
-by = (cin + cout * (1 + nres)) * H * W * N * 2.0
-print(f'conv {cin}->{cout} k{k} {H}x{W} N={N} nres={nres}: {ms * 1e3:.1f} us  {fl / ms / 1e9:.1f} TFLOP/s  {by / ms / 1e6:.1f} GB/s (algorithmic)')
+fl = 2.0 * k * k * cin * cout * Ho * Wo * N
+by = (cin * H * W + cout * (1 + nres) * Ho * Wo) * N * 2.0
+print(f'conv {cin}->{cout} k{k} s{stride} {H}x{W} N={N} nres={nres} engine={engine}: {ms * 1e3:.1f} us  {fl / ms / 1e9:.1f} TFLOP/s  {by / ms / 1e6:.1f} GB/s (algorithmic)')
