@@ -148,6 +148,47 @@ def gpu_eager_baseline(sd, cfg, x_host, dev, n=64):
     return res
 
 
+def dropin_loop_throughput(net, cfg, x_host, c_np, s_np, dev, batch=32, iters=6):
+    """The reference loop's own call sequence (lib/core/function.py:389-450) at its TEST.BATCH_SIZE_PER_GPU = 32, with the
+    drop-in modules standing where the shim puts them: model(input) -> model(input.flip(3)) -> flip_back(.cpu().numpy()) ->
+    back to the device -> 1-px shift -> average -> get_final_preds(config, output.clone().cpu().numpy(), c, s).
+    Three D2H copies of full heat-maps per batch, exactly as the unchanged caller does them."""
+    from rsgnet_b200.core.inference import get_final_preds
+    from rsgnet_b200.utils.transforms import flip_back
+    pairs = presets.flip_pairs_for(int(cfg.MODEL.NUM_JOINTS))
+    x = x_host[:batch].clone()
+    c, s = c_np[:batch], s_np[:batch]
+    was_lazy = getattr(net, 'lazy_aux', False)
+    net.lazy_aux = True                                 # INTEGRATION.md §1: the loop reads outputs[1] only
+    st = torch.cuda.Stream(dev)
+
+    def one_batch():
+        outputs = net(x)                                # CPU tensor in, as DataParallel's caller passes it
+        output = outputs[1]
+        input_flipped = x.flip(3)
+        output_flipped = net(input_flipped)[1]
+        output_flipped = flip_back(output_flipped.cpu().numpy(), pairs)
+        output_flipped = torch.from_numpy(output_flipped.copy()).to(dev)
+        output_flipped[:, :, :, 1:] = output_flipped.clone()[:, :, :, 0:-1]
+        output = (output + output_flipped) * 0.5
+        return get_final_preds(cfg, output.clone().cpu().numpy(), c, s)
+    try:
+        with torch.cuda.stream(st):
+            for _ in range(3):
+                one_batch()
+            torch.cuda.synchronize()
+            t0 = time.perf_counter()
+            for _ in range(iters):
+                one_batch()
+            torch.cuda.synchronize()
+            dt = (time.perf_counter() - t0) / iters
+    finally:
+        net.lazy_aux = was_lazy
+    return {'crops_per_s': batch / dt, 'batch': batch, 'ms_per_batch': dt * 1e3,
+            'what': 'lib/core/function.py:389-450 call sequence through the drop-in modules (2 module forwards with graph replay, '
+                    'host flip_back, 3 D2H copies of full heat-maps, get_final_preds on NumPy), wall clock'}
+
+
 def run_reference(args):
     """--impl reference: the reference's own CPU implementation of the path (oracle port), all host
     threads, on our arm's workload, a bounded sample (--cpu-sample crops) per step."""
@@ -656,6 +697,12 @@ def main():
     eager = None
     if args.gpu_eager_baseline:
         eager = gpu_eager_baseline(sd, cfg, x_host, dev)
+    dropin = None
+    if not args.no_cpu_baseline:
+        try:
+            dropin = dropin_loop_throughput(net, cfg, x_host, c_np, s_np, dev)
+        except Exception as e:                       # informational leg
+            dropin = {'error': str(e)[:300]}
 
     line = {
         'metric': METRIC, 'value': value, 'unit': 'crops/s', 'n_gpus': world, 'steps': args.steps,
@@ -669,7 +716,7 @@ def main():
         'e2e': {'value': e2e_val, 'unit': 'crops/s', 'h2d_bytes_per_step': h2d, 'd2h_bytes_per_step': d2h,
                 'ms_per_step': ms_e2e / args.steps},
         'roofline': roofline, 'cpu_baseline': cpu, 'parity_checked': parity is not None, 'parity': parity,
-        'sustained': sustained, 'gpu_eager_baseline': eager,
+        'sustained': sustained, 'gpu_eager_baseline': eager, 'dropin_loop': dropin,
         'executed_tflops_per_gpu': exec_tflops, 'executed_frac_of_bf16_peak': exec_tflops / pk['tf_sus'],
         'reference_graph_tflops_per_gpu': value / world * REF_GFLOP_PER_CROP / 1e3,
     }

@@ -276,6 +276,218 @@ trp_attention_tc5_kernel(const __grid_constant__ AttMaps maps, const AttP p) {
   (void)c8;
 }
 
+// ------------------------------------------------------------------------------------------------------------------
+// Two query tiles per CTA (256 query positions, one CTA per SM, 16 sigmoid warps).  The 128-query kernel above is bound
+// by the TMA element rate, not by the MUFU: every 64-key block costs one K and one G tile of 16-byte elements (512
+// elements = 512 cycles of the SM's TMA engine, tools/tma_rate.cu) for 8192 sigmoids (512 MUFU cycles), and with two
+// CTAs per SM the blocks took 820 cycles each (skip modes: 1.40 ms with the MUFU work removed, 1.85 ms with it).  Here a
+// K / G tile serves two query tiles: 512 TMA cycles per 16384 sigmoids (1024 MUFU cycles).
+// TMEM (512 columns): S[t][b] at (2t + b) * 64, O[t] at 256 + 64t (C columns each).
+// ------------------------------------------------------------------------------------------------------------------
+constexpr int AT2_THREADS = 608;                // 3 + 16 warps
+constexpr int AT2_KV_STAGES = 4;
+
+__global__ void __launch_bounds__(AT2_THREADS, 1)
+trp_attention_tc5x2_kernel(const __grid_constant__ AttMaps maps, const AttP p) {
+  extern __shared__ __align__(128) unsigned char smem_raw[];
+  // barriers: Q | KVF[4] | KVE[4] | SF[t][b] (4) | SE (4) | PF (4) | PE (4) | OF
+  __shared__ __align__(8) uint64_t bars[1 + 2 * AT2_KV_STAGES + 17];
+  __shared__ uint32_t tmem_base_slot;
+  const uint32_t bar0 = smem_u32(&bars[0]);
+  auto BAR = [&](int i) { return bar0 + 8u * i; };
+  constexpr int B_Q = 0, B_KVF = 1, B_KVE = 1 + AT2_KV_STAGES, B_SF = 1 + 2 * AT2_KV_STAGES, B_SE = B_SF + 4,
+                B_PF = B_SE + 4, B_PE = B_PF + 4, B_OF = B_PE + 4;
+  const uint32_t sbase = (smem_u32(smem_raw) + 127u) & ~127u;
+  unsigned char* const sgen = smem_raw + (sbase - smem_u32(smem_raw));
+  // layout: Q (two 128-row tiles) | KV stage s: K tile, G tile | P buffers [t][b] (4 x 128 x 64 bf16)
+  const uint32_t kv0 = 2u * p.q_bytes, p0 = kv0 + AT2_KV_STAGES * 2u * p.kv_tile_bytes;
+  constexpr uint32_t P_BYTES = AT_BQ * AT_BK * 2;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int n = blockIdx.y, q0 = blockIdx.x * 2 * AT_BQ;
+
+  if (threadIdx.x == 0) {
+    mbar_init(BAR(B_Q), 1);
+    for (int i = 0; i < AT2_KV_STAGES; ++i) { mbar_init(BAR(B_KVF + i), 1); mbar_init(BAR(B_KVE + i), 1); }
+    for (int i = 0; i < 4; ++i) {
+      mbar_init(BAR(B_SF + i), 1); mbar_init(BAR(B_SE + i), AT_SW);
+      mbar_init(BAR(B_PF + i), AT_SW); mbar_init(BAR(B_PE + i), 1);
+    }
+    mbar_init(BAR(B_OF), 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 1) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_base_slot)), "r"(512u) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+  const uint32_t tmem_base = tmem_base_slot;
+  const uint32_t tmem_o = tmem_base + 4u * AT_BK;        // O[t] at tmem_o + 64 t
+  const int nblk = p.nblk;
+
+  if (warp == 0) {
+    // ===================== TMA producer =====================
+    if (lane == 0) {
+      asm volatile("prefetch.tensormap [%0];" ::"l"(&maps.q) : "memory");
+      asm volatile("prefetch.tensormap [%0];" ::"l"(&maps.x) : "memory");
+      asm volatile("prefetch.tensormap [%0];" ::"l"(&maps.g) : "memory");
+      mbar_arrive_expect_tx(BAR(B_Q), 2u * p.q_bytes);
+      tma_load_4d(sbase, &maps.q, BAR(B_Q), 0, q0, 0, n);
+      tma_load_4d(sbase + p.q_bytes, &maps.q, BAR(B_Q), 0, q0 + AT_BQ, 0, n);
+      uint32_t s = 0, ph = 0;
+      for (int j = 0; j < nblk; ++j) {
+        mbar_wait(BAR(B_KVE + s), ph ^ 1u);
+        const uint32_t dst = sbase + kv0 + s * 2u * p.kv_tile_bytes;
+        mbar_arrive_expect_tx(BAR(B_KVF + s), 2u * p.kv_tile_bytes);
+        tma_load_4d(dst, &maps.x, BAR(B_KVF + s), 0, j * AT_BK, 0, n);
+        tma_load_4d(dst + p.kv_tile_bytes, &maps.g, BAR(B_KVF + s), 0, j * AT_BK, 0, n);
+        if (++s == AT2_KV_STAGES) { s = 0; ph ^= 1u; }
+      }
+    }
+  } else if (warp < AT_W0) {
+    const uint32_t idesc1 = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(AT_BK >> 3) << 17) | ((128u >> 4) << 24);
+    const uint32_t idesc2 = (1u << 4) | (1u << 7) | (1u << 10) | (1u << 16) | ((uint32_t)(p.C >> 3) << 17) | ((128u >> 4) << 24);
+    const uint32_t hi_k = desc_hi(128u);
+    const uint32_t lo_plane = ((2048u >> 4) & 0x3FFFu) << 16;
+    const uint32_t lo_kplane = (((uint32_t)AT_BK * 16u >> 4) & 0x3FFFu) << 16;
+    const uint32_t hi_g = desc_hi((uint32_t)AT_BK * 16u);
+    const uint32_t lo_g = ((128u >> 4) & 0x3FFFu) << 16;
+    const int ks1 = p.C >> 4;
+    const uint32_t q16 = sbase >> 4, qt16 = p.q_bytes >> 4;
+    const uint32_t kv16 = (sbase + kv0) >> 4, kvs16 = (2u * p.kv_tile_bytes) >> 4;
+    if (warp == 1) {
+      // ---- MMA1: S[t][j&1] = Q_t . K_j^T for both query tiles
+      mbar_wait(BAR(B_Q), 0);
+      uint32_t s = 0, phs = 0;
+      for (int j = 0; j < nblk; ++j) {
+        const uint32_t b = (uint32_t)j & 1u, pj = (((uint32_t)j >> 1) & 1u);
+        mbar_wait(BAR(B_KVF + s), phs);
+        const uint32_t k16a = kv16 + s * kvs16;
+#pragma unroll
+        for (uint32_t t = 0; t < 2; ++t) {
+          mbar_wait(BAR(B_SE + 2 * t + b), pj ^ 1u);
+          asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+          if (elect_one()) {
+            for (int k = 0; k < ks1; ++k)
+              umma_f16(tmem_base + (2u * t + b) * (uint32_t)AT_BK, ((uint64_t)hi_k << 32) | ((q16 + t * qt16 + (uint32_t)k * 256u) | lo_plane),
+                       ((uint64_t)hi_k << 32) | ((k16a + (uint32_t)k * (2u * AT_BK)) | lo_kplane), idesc1, k > 0);
+            umma_commit(BAR(B_SF + 2 * t + b));
+          }
+          __syncwarp();
+        }
+        if (++s == AT2_KV_STAGES) { s = 0; phs ^= 1u; }
+      }
+    } else {
+      // ---- MMA2: O[t] += P[t][b] . G_j; releases the P buffers and, after both tiles, the K/G stage
+      const uint32_t g16_0 = kv16 + (p.kv_tile_bytes >> 4);
+      const uint32_t p16_0 = (sbase + p0) >> 4;
+      uint32_t s = 0;
+      for (int j = 0; j < nblk; ++j) {
+        const uint32_t b = (uint32_t)j & 1u, pj = (((uint32_t)j >> 1) & 1u);
+        const uint32_t g16 = (g16_0 + s * kvs16) | lo_g;
+#pragma unroll
+        for (uint32_t t = 0; t < 2; ++t) {
+          mbar_wait(BAR(B_PF + 2 * t + b), pj);
+          asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+          const uint32_t p16 = (p16_0 + (2u * t + b) * (P_BYTES >> 4)) | lo_plane;
+          if (elect_one()) {
+#pragma unroll
+            for (int k = 0; k < AT_BK / 16; ++k)
+              umma_f16(tmem_o + 64u * t, ((uint64_t)hi_k << 32) | (p16 + (uint32_t)k * 256u), ((uint64_t)hi_g << 32) | (g16 + (uint32_t)k * 16u),
+                       idesc2, (j | k) != 0);
+            umma_commit(BAR(B_PE + 2 * t + b));
+            if (t == 1) {
+              umma_commit(BAR(B_KVE + s));
+              if (j == nblk - 1) umma_commit(BAR(B_OF));
+            }
+          }
+          __syncwarp();
+        }
+        if (++s == AT2_KV_STAGES) s = 0;
+      }
+    }
+  } else {
+    // ===================== sigmoid warps (3 .. 18): tile t = (warp - 3) / 8 =====================
+    const int t = (warp - AT_W0) >> 3;
+    const int q = warp & 3;                            // TMEM lane quarter
+    const int half = ((warp - AT_W0) >> 2) & 1;        // key columns [32 half, 32 half + 32)
+    const int row = q * 32 + lane;                     // query row inside the tile
+    const uint32_t tq = tmem_base + ((uint32_t)(q * 32) << 16);
+    // (software-pipelining the TMEM load of block j+1 under the sigmoids of block j was measured slower: 1662 vs 1594 us)
+    for (int j = 0; j < nblk; ++j) {
+      const uint32_t b = (uint32_t)j & 1u, ph = ((uint32_t)j >> 1) & 1u;
+      const uint32_t sb = 2u * (uint32_t)t + b;
+      mbar_wait(BAR(B_SF + sb), ph);
+      asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+      uint32_t v[2][16];
+      tmem_ld16(tq + sb * (uint32_t)AT_BK + (uint32_t)(half * 32), v[0]);
+      tmem_ld16(tq + sb * (uint32_t)AT_BK + (uint32_t)(half * 32 + 16), v[1]);
+      mbar_wait(BAR(B_PE + sb), ph ^ 1u);              // MMA2 of block j-2 has consumed this P buffer
+      asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+      asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+      __syncwarp();
+      if (lane == 0) mbar_arrive(BAR(B_SE + sb));
+      unsigned char* const pb = sgen + p0 + sb * P_BYTES + (size_t)row * 16;
+#pragma unroll
+      for (int cc = 0; cc < 2; ++cc) {
+        const int c0 = half * 32 + cc * 16;
+        const uint32_t* vv = v[cc];
+        uint4 o0, o1;
+        o0.x = pack_bf16x2(sigmoid_mufu(__uint_as_float(vv[0])), sigmoid_mufu(__uint_as_float(vv[1])));
+        o0.y = pack_bf16x2(sigmoid_mufu(__uint_as_float(vv[2])), sigmoid_mufu(__uint_as_float(vv[3])));
+        o0.z = pack_bf16x2(sigmoid_mufu(__uint_as_float(vv[4])), sigmoid_mufu(__uint_as_float(vv[5])));
+        o0.w = pack_bf16x2(sigmoid_mufu(__uint_as_float(vv[6])), sigmoid_mufu(__uint_as_float(vv[7])));
+        o1.x = pack_bf16x2(sigmoid_mufu(__uint_as_float(vv[8])), sigmoid_mufu(__uint_as_float(vv[9])));
+        o1.y = pack_bf16x2(sigmoid_mufu(__uint_as_float(vv[10])), sigmoid_mufu(__uint_as_float(vv[11])));
+        o1.z = pack_bf16x2(sigmoid_mufu(__uint_as_float(vv[12])), sigmoid_mufu(__uint_as_float(vv[13])));
+        o1.w = pack_bf16x2(sigmoid_mufu(__uint_as_float(vv[14])), sigmoid_mufu(__uint_as_float(vv[15])));
+        *reinterpret_cast<uint4*>(pb + (size_t)(c0 >> 3) * 2048) = o0;
+        *reinterpret_cast<uint4*>(pb + (size_t)((c0 >> 3) + 1) * 2048) = o1;
+      }
+      asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+      __syncwarp();
+      if (lane == 0) mbar_arrive(BAR(B_PF + sb));
+    }
+    // ---- output: O[t] (128 x C fp32 in TMEM) -> y rows; the four warps of half 0 of each tile
+    if (half == 0) {
+      mbar_wait(BAR(B_OF), 0);
+      asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+      const int grow = q0 + t * AT_BQ + row;
+      bf16* dst = p.y + ((size_t)n * p.S + grow) * p.y_cs + p.y_co;
+      float* dst32 = p.y32 ? p.y32 + ((size_t)n * p.S + grow) * p.C : nullptr;
+      for (int c0 = 0; c0 < p.C; c0 += 16) {
+        uint32_t v[16];
+        tmem_ld16(tq + 4u * AT_BK + 64u * (uint32_t)t + (uint32_t)c0, v);
+        asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+        if (grow >= p.S) continue;
+        if (dst32) {
+#pragma unroll
+          for (int k = 0; k < 4; ++k)
+            reinterpret_cast<uint4*>(dst32 + c0)[k] = make_uint4(v[4 * k], v[4 * k + 1], v[4 * k + 2], v[4 * k + 3]);
+        } else {
+          uint4 o0, o1;
+          o0.x = pack_bf16x2(__uint_as_float(v[0]), __uint_as_float(v[1]));
+          o0.y = pack_bf16x2(__uint_as_float(v[2]), __uint_as_float(v[3]));
+          o0.z = pack_bf16x2(__uint_as_float(v[4]), __uint_as_float(v[5]));
+          o0.w = pack_bf16x2(__uint_as_float(v[6]), __uint_as_float(v[7]));
+          o1.x = pack_bf16x2(__uint_as_float(v[8]), __uint_as_float(v[9]));
+          o1.y = pack_bf16x2(__uint_as_float(v[10]), __uint_as_float(v[11]));
+          o1.z = pack_bf16x2(__uint_as_float(v[12]), __uint_as_float(v[13]));
+          o1.w = pack_bf16x2(__uint_as_float(v[14]), __uint_as_float(v[15]));
+          reinterpret_cast<uint4*>(dst + c0)[0] = o0;
+          reinterpret_cast<uint4*>(dst + c0)[1] = o1;
+        }
+      }
+    }
+  }
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  if (warp == 1) {
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512u) : "memory");
+  }
+}
+
 // [N, S, C] bf16 view (channel stride cs, offset co) as (8 ch, S, C/8, N); box = (8, rows, C/8, 1)
 int make_att_map(const bf16* base, int cs, int co, int N, int S, int C, int rows, CUtensorMap* m) {
   EncodeTiledFn enc = tensor_map_encoder();
@@ -321,6 +533,20 @@ int attention_tc5_launch(cudaStream_t s, const bf16* x, int x_cs, int x_co, cons
   if (attr_once.first()) {
     RSG_CUDA(cudaFuncSetAttribute(trp_attention_tc5_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
     attr_once.done();
+  }
+  static const bool one_tile = rsg_dbg_env("RSG_ATT_1TILE") != nullptr;
+  if (S > AT_BQ && !one_tile) {
+    // two query tiles per CTA: a K / G tile is loaded once per 256 query positions
+    const size_t smem2 = 128 + 2u * p.q_bytes + AT2_KV_STAGES * 2u * p.kv_tile_bytes + 4u * AT_BQ * AT_BK * 2u;
+    static DeviceOnce attr2_once;
+    if (attr2_once.first()) {
+      RSG_CUDA(cudaFuncSetAttribute(trp_attention_tc5x2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+      attr2_once.done();
+    }
+    dim3 grid2((S + 2 * AT_BQ - 1) / (2 * AT_BQ), N);
+    trp_attention_tc5x2_kernel<<<grid2, AT2_THREADS, smem2, s>>>(maps, p);
+    RSG_LAUNCH_CHECK();
+    return RSG_OK;
   }
   dim3 grid((S + AT_BQ - 1) / AT_BQ, N);
   trp_attention_tc5_kernel<<<grid, AT_THREADS, smem, s>>>(maps, p);
