@@ -286,20 +286,21 @@ trp_attention_tc5_kernel(const __grid_constant__ AttMaps maps, const AttP p) {
 // ------------------------------------------------------------------------------------------------------------------
 constexpr int AT2_THREADS = 608;                // 3 + 16 warps
 constexpr int AT2_KV_STAGES = 4;
+constexpr int AT2_NB = 3;                       // S / P buffers per query tile: MMA1 runs up to two key blocks ahead of the sigmoids
 
 __global__ void __launch_bounds__(AT2_THREADS, 1)
 trp_attention_tc5x2_kernel(const __grid_constant__ AttMaps maps, const AttP p) {
   extern __shared__ __align__(128) unsigned char smem_raw[];
-  // barriers: Q | KVF[4] | KVE[4] | SF[t][b] (4) | SE (4) | PF (4) | PE (4) | OF
-  __shared__ __align__(8) uint64_t bars[1 + 2 * AT2_KV_STAGES + 17];
+  // barriers: Q | KVF[4] | KVE[4] | SF[t][b] (2 NB) | SE | PF | PE | OF
+  __shared__ __align__(8) uint64_t bars[1 + 2 * AT2_KV_STAGES + 8 * AT2_NB + 1];
   __shared__ uint32_t tmem_base_slot;
   const uint32_t bar0 = smem_u32(&bars[0]);
   auto BAR = [&](int i) { return bar0 + 8u * i; };
-  constexpr int B_Q = 0, B_KVF = 1, B_KVE = 1 + AT2_KV_STAGES, B_SF = 1 + 2 * AT2_KV_STAGES, B_SE = B_SF + 4,
-                B_PF = B_SE + 4, B_PE = B_PF + 4, B_OF = B_PE + 4;
+  constexpr int B_Q = 0, B_KVF = 1, B_KVE = 1 + AT2_KV_STAGES, B_SF = 1 + 2 * AT2_KV_STAGES, B_SE = B_SF + 2 * AT2_NB,
+                B_PF = B_SE + 2 * AT2_NB, B_PE = B_PF + 2 * AT2_NB, B_OF = B_PE + 2 * AT2_NB;
   const uint32_t sbase = (smem_u32(smem_raw) + 127u) & ~127u;
   unsigned char* const sgen = smem_raw + (sbase - smem_u32(smem_raw));
-  // layout: Q (two 128-row tiles) | KV stage s: K tile, G tile | P buffers [t][b] (4 x 128 x 64 bf16)
+  // layout: Q (two 128-row tiles) | KV stage s: K tile, G tile | P buffers [t][b] (2 NB x 128 x 64 bf16)
   const uint32_t kv0 = 2u * p.q_bytes, p0 = kv0 + AT2_KV_STAGES * 2u * p.kv_tile_bytes;
   constexpr uint32_t P_BYTES = AT_BQ * AT_BK * 2;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -308,7 +309,7 @@ trp_attention_tc5x2_kernel(const __grid_constant__ AttMaps maps, const AttP p) {
   if (threadIdx.x == 0) {
     mbar_init(BAR(B_Q), 1);
     for (int i = 0; i < AT2_KV_STAGES; ++i) { mbar_init(BAR(B_KVF + i), 1); mbar_init(BAR(B_KVE + i), 1); }
-    for (int i = 0; i < 4; ++i) {
+    for (int i = 0; i < 2 * AT2_NB; ++i) {
       mbar_init(BAR(B_SF + i), 1); mbar_init(BAR(B_SE + i), AT_SW);
       mbar_init(BAR(B_PF + i), AT_SW); mbar_init(BAR(B_PE + i), 1);
     }
@@ -323,7 +324,7 @@ trp_attention_tc5x2_kernel(const __grid_constant__ AttMaps maps, const AttP p) {
   __syncthreads();
   asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
   const uint32_t tmem_base = tmem_base_slot;
-  const uint32_t tmem_o = tmem_base + 4u * AT_BK;        // O[t] at tmem_o + 64 t
+  const uint32_t tmem_o = tmem_base + (uint32_t)(2 * AT2_NB) * AT_BK;        // O[t] at tmem_o + 64 t
   const int nblk = p.nblk;
 
   if (warp == 0) {
@@ -359,20 +360,19 @@ trp_attention_tc5x2_kernel(const __grid_constant__ AttMaps maps, const AttP p) {
     if (warp == 1) {
       // ---- MMA1: S[t][j&1] = Q_t . K_j^T for both query tiles
       mbar_wait(BAR(B_Q), 0);
-      uint32_t s = 0, phs = 0;
-      for (int j = 0; j < nblk; ++j) {
-        const uint32_t b = (uint32_t)j & 1u, pj = (((uint32_t)j >> 1) & 1u);
+      uint32_t s = 0, phs = 0, b = 0, pj = 0;        // b = j % NB, pj = (j / NB) & 1, carried incrementally
+      for (int j = 0; j < nblk; ++j, b = (b + 1 == AT2_NB ? 0u : b + 1), pj ^= (b == 0)) {
         mbar_wait(BAR(B_KVF + s), phs);
         const uint32_t k16a = kv16 + s * kvs16;
 #pragma unroll
         for (uint32_t t = 0; t < 2; ++t) {
-          mbar_wait(BAR(B_SE + 2 * t + b), pj ^ 1u);
+          mbar_wait(BAR(B_SE + AT2_NB * t + b), pj ^ 1u);
           asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
           if (elect_one()) {
             for (int k = 0; k < ks1; ++k)
-              umma_f16(tmem_base + (2u * t + b) * (uint32_t)AT_BK, ((uint64_t)hi_k << 32) | ((q16 + t * qt16 + (uint32_t)k * 256u) | lo_plane),
+              umma_f16(tmem_base + ((uint32_t)AT2_NB * t + b) * (uint32_t)AT_BK, ((uint64_t)hi_k << 32) | ((q16 + t * qt16 + (uint32_t)k * 256u) | lo_plane),
                        ((uint64_t)hi_k << 32) | ((k16a + (uint32_t)k * (2u * AT_BK)) | lo_kplane), idesc1, k > 0);
-            umma_commit(BAR(B_SF + 2 * t + b));
+            umma_commit(BAR(B_SF + AT2_NB * t + b));
           }
           __syncwarp();
         }
@@ -382,21 +382,20 @@ trp_attention_tc5x2_kernel(const __grid_constant__ AttMaps maps, const AttP p) {
       // ---- MMA2: O[t] += P[t][b] . G_j; releases the P buffers and, after both tiles, the K/G stage
       const uint32_t g16_0 = kv16 + (p.kv_tile_bytes >> 4);
       const uint32_t p16_0 = (sbase + p0) >> 4;
-      uint32_t s = 0;
-      for (int j = 0; j < nblk; ++j) {
-        const uint32_t b = (uint32_t)j & 1u, pj = (((uint32_t)j >> 1) & 1u);
+      uint32_t s = 0, b = 0, pj = 0;
+      for (int j = 0; j < nblk; ++j, b = (b + 1 == AT2_NB ? 0u : b + 1), pj ^= (b == 0)) {
         const uint32_t g16 = (g16_0 + s * kvs16) | lo_g;
 #pragma unroll
         for (uint32_t t = 0; t < 2; ++t) {
-          mbar_wait(BAR(B_PF + 2 * t + b), pj);
+          mbar_wait(BAR(B_PF + AT2_NB * t + b), pj);
           asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-          const uint32_t p16 = (p16_0 + (2u * t + b) * (P_BYTES >> 4)) | lo_plane;
+          const uint32_t p16 = (p16_0 + ((uint32_t)AT2_NB * t + b) * (P_BYTES >> 4)) | lo_plane;
           if (elect_one()) {
 #pragma unroll
             for (int k = 0; k < AT_BK / 16; ++k)
               umma_f16(tmem_o + 64u * t, ((uint64_t)hi_k << 32) | (p16 + (uint32_t)k * 256u), ((uint64_t)hi_g << 32) | (g16 + (uint32_t)k * 16u),
                        idesc2, (j | k) != 0);
-            umma_commit(BAR(B_PE + 2 * t + b));
+            umma_commit(BAR(B_PE + AT2_NB * t + b));
             if (t == 1) {
               umma_commit(BAR(B_KVE + s));
               if (j == nblk - 1) umma_commit(BAR(B_OF));
@@ -415,15 +414,15 @@ trp_attention_tc5x2_kernel(const __grid_constant__ AttMaps maps, const AttP p) {
     const int row = q * 32 + lane;                     // query row inside the tile
     const uint32_t tq = tmem_base + ((uint32_t)(q * 32) << 16);
     // (software-pipelining the TMEM load of block j+1 under the sigmoids of block j was measured slower: 1662 vs 1594 us)
-    for (int j = 0; j < nblk; ++j) {
-      const uint32_t b = (uint32_t)j & 1u, ph = ((uint32_t)j >> 1) & 1u;
-      const uint32_t sb = 2u * (uint32_t)t + b;
+    uint32_t b = 0, ph = 0;
+    for (int j = 0; j < nblk; ++j, b = (b + 1 == AT2_NB ? 0u : b + 1), ph ^= (b == 0)) {
+      const uint32_t sb = (uint32_t)AT2_NB * (uint32_t)t + b;
       mbar_wait(BAR(B_SF + sb), ph);
       asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
       uint32_t v[2][16];
       tmem_ld16(tq + sb * (uint32_t)AT_BK + (uint32_t)(half * 32), v[0]);
       tmem_ld16(tq + sb * (uint32_t)AT_BK + (uint32_t)(half * 32 + 16), v[1]);
-      mbar_wait(BAR(B_PE + sb), ph ^ 1u);              // MMA2 of block j-2 has consumed this P buffer
+      mbar_wait(BAR(B_PE + sb), ph ^ 1u);              // MMA2 of block j-NB has consumed this P buffer
       asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
       asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
       __syncwarp();
@@ -458,7 +457,7 @@ trp_attention_tc5x2_kernel(const __grid_constant__ AttMaps maps, const AttP p) {
       float* dst32 = p.y32 ? p.y32 + ((size_t)n * p.S + grow) * p.C : nullptr;
       for (int c0 = 0; c0 < p.C; c0 += 16) {
         uint32_t v[16];
-        tmem_ld16(tq + 4u * AT_BK + 64u * (uint32_t)t + (uint32_t)c0, v);
+        tmem_ld16(tq + (uint32_t)(2 * AT2_NB) * AT_BK + 64u * (uint32_t)t + (uint32_t)c0, v);
         asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
         if (grow >= p.S) continue;
         if (dst32) {
@@ -537,7 +536,7 @@ int attention_tc5_launch(cudaStream_t s, const bf16* x, int x_cs, int x_co, cons
   static const bool one_tile = rsg_dbg_env("RSG_ATT_1TILE") != nullptr;
   if (S > AT_BQ && !one_tile) {
     // two query tiles per CTA: a K / G tile is loaded once per 256 query positions
-    const size_t smem2 = 128 + 2u * p.q_bytes + AT2_KV_STAGES * 2u * p.kv_tile_bytes + 4u * AT_BQ * AT_BK * 2u;
+    const size_t smem2 = 128 + 2u * p.q_bytes + AT2_KV_STAGES * 2u * p.kv_tile_bytes + (size_t)(2 * AT2_NB) * AT_BQ * AT_BK * 2u;
     static DeviceOnce attr2_once;
     if (attr2_once.first()) {
       RSG_CUDA(cudaFuncSetAttribute(trp_attention_tc5x2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));

@@ -17,8 +17,15 @@ namespace {
 // B fragments (48 per thread).  Outputs go through a per-warp shared-memory transpose so that every
 // global store is a fully used 16-byte piece of a contiguous 512-byte run.
 // ---------------------------------------------------------------------------------------------
+//
+// Staging: the patch is an ALIGNED superset of the 66 needed columns ([64 tx - 4, 64 tx + 68): 18 sixteen-byte chunks per
+// row), so that every copy is a 16-byte cp.async (the first version copied 3366 single floats per tile and was bound by
+// the LSU, 2.4 TB/s).  The W flip of the second forward cannot be a reversed copy then; it is folded into the math
+// instead: conv(flip(x))[ox] = sum_kx w[kx] x[2 ox' + 2 - kx] with ox' = Wo-1-ox, i.e. the UNFLIPPED patch read with a
+// mirrored tap window and the output row written mirrored (FLIP instantiation) -- bit-identical to flipping the crop.
 constexpr int ST_TY = 8, ST_TX = 32;
-constexpr int ST_IR = 2 * ST_TY + 1, ST_IC = 2 * ST_TX + 2;
+constexpr int ST_IR = 2 * ST_TY + 1, ST_IC = 2 * ST_TX + 8;      // 72 columns: patch column c is image column 64 tx - 4 + c
+constexpr int ST_C4 = ST_IC / 4;
 constexpr int ST_OPITCH = 144;                    // bytes per staged output pixel (128 + pad: conflict-free)
 
 __device__ __forceinline__ uint32_t pack2(float a, float b) {
@@ -28,9 +35,10 @@ __device__ __forceinline__ uint32_t pack2(float a, float b) {
   return *reinterpret_cast<uint32_t*>(&t);
 }
 
+template <bool FLIP>
 __global__ void __launch_bounds__(256, 2)
 stem_kernel(const float* __restrict__ x, int H, int W, const float* __restrict__ w,
-            const float* __restrict__ bias, bf16* __restrict__ out, int f0, int nb, int n_crops,
+            const float* __restrict__ bias, bf16* __restrict__ out, int f0, int fl0, int n_crops,
             int tiles_x, int tiles_y, int ntiles) {
   // raw fp32 patches [buffer][c][row][col], filled by cp.async one tile ahead of the math
   __shared__ __align__(16) float sIn[2][3 * ST_IR * ST_IC];
@@ -44,25 +52,24 @@ stem_kernel(const float* __restrict__ x, int H, int W, const float* __restrict__
     ty = tile % tiles_y;
     fl = tile / tiles_y;
   };
-  // out-of-image pixels are the zero padding (cp.async with src-size 0 zero-fills); the W flip of the
-  // second forward is applied here, so the math below never knows about it
+  // out-of-image chunks are the zero padding (cp.async with src-size 0 zero-fills); W is a multiple of 4, so an aligned
+  // chunk is either inside the row or outside
   auto stage = [&](int tile, int buf) {
     int tx, ty, fl;
     decode(tile, tx, ty, fl);
-    const int f = f0 + fl;
-    const bool flip = f >= n_crops;
+    const int f = f0 + fl0 + fl;
     const float* xin = x + (size_t)(f % n_crops) * 3 * H * W;
-    const int gy0 = 2 * ty * ST_TY - 1, gx0 = 2 * tx * ST_TX - 1;
+    const int gy0 = 2 * ty * ST_TY - 1, gx0 = 2 * tx * ST_TX - 4;
     const uint32_t sbase = (uint32_t)__cvta_generic_to_shared(&sIn[buf][0]);
-    for (int i = tid; i < 3 * ST_IR * ST_IC; i += 256) {
-      const int c = i / (ST_IR * ST_IC);
-      const int rem = i - c * (ST_IR * ST_IC);
-      const int r = rem / ST_IC, col = rem - r * ST_IC;
-      const int gy = gy0 + r, gx = gx0 + col;
+    for (int i = tid; i < 3 * ST_IR * ST_C4; i += 256) {
+      const int c = i / (ST_IR * ST_C4);
+      const int rem = i - c * (ST_IR * ST_C4);
+      const int r = rem / ST_C4, c4 = rem - r * ST_C4;
+      const int gy = gy0 + r, gx = gx0 + 4 * c4;
       const bool ok = gy >= 0 && gy < H && gx >= 0 && gx < W;
-      const float* src = ok ? xin + ((size_t)c * H + gy) * W + (flip ? W - 1 - gx : gx) : xin;
-      const int sz = ok ? 4 : 0;
-      asm volatile("cp.async.ca.shared.global [%0], [%1], 4, %2;\n" ::"r"(sbase + 4u * (uint32_t)i), "l"(src), "r"(sz));
+      const float* src = ok ? xin + ((size_t)c * H + gy) * W + gx : xin;
+      const int sz = ok ? 16 : 0;
+      asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;\n" ::"r"(sbase + 16u * (uint32_t)i), "l"(src), "r"(sz));
     }
     asm volatile("cp.async.commit_group;\n" ::);
   };
@@ -115,14 +122,19 @@ stem_kernel(const float* __restrict__ x, int H, int W, const float* __restrict__
 #pragma unroll
       for (int ky = 0; ky < 3; ++ky) {
         // (row 2*warp+ky, col 2*(16*xh+g) + tq/2): channels c0, c0+1 of that pixel (channel 3 is zero)
-        const float* q0 = p0 + (2 * warp + ky) * ST_IC + 2 * (16 * xh + g) + (tq >> 1);
+        // K slot kx of the MMA holds w[kx] * x[image column 2 ox - 1 + kx] = patch column 2 ox + kx + 3.  FLIP: the same
+        // slot holds w[kx] * flip(x)[2 ox - 1 + kx] = w[kx] * x[2 ox' + 2 - kx] with ox' = Wo - 1 - ox the column this
+        // thread computes, i.e. patch column 2 ox' + 6 - kx: the slots (and with them the accumulation order) are those
+        // of the unfused "flip the crop, then convolve", so both give the same bits.
+        constexpr int KS = FLIP ? -1 : 1;
+        const float* q0 = p0 + (2 * warp + ky) * ST_IC + 2 * (16 * xh + g) + (FLIP ? 6 - (tq >> 1) : 3 + (tq >> 1));
         const float* q1 = q0 + ST_IR * ST_IC;
         const bool two = c0 == 0;
         uint32_t a[4];
-        a[0] = pack2(q0[0], two ? q1[0] : 0.f);        // pixel g,    kx = tq/2
-        a[1] = pack2(q0[16], two ? q1[16] : 0.f);      // pixel g+8
-        a[2] = pack2(q0[2], two ? q1[2] : 0.f);        // pixel g,    kx = tq/2 + 2
-        a[3] = pack2(q0[18], two ? q1[18] : 0.f);      // pixel g+8
+        a[0] = pack2(q0[0], two ? q1[0] : 0.f);                      // pixel g,    kx = tq/2
+        a[1] = pack2(q0[16], two ? q1[16] : 0.f);                    // pixel g+8
+        a[2] = pack2(q0[2 * KS], two ? q1[2 * KS] : 0.f);            // pixel g,    kx = tq/2 + 2
+        a[3] = pack2(q0[16 + 2 * KS], two ? q1[16 + 2 * KS] : 0.f);  // pixel g+8
 #pragma unroll
         for (int j = 0; j < 8; ++j) {
           asm volatile(
@@ -139,12 +151,14 @@ stem_kernel(const float* __restrict__ x, int H, int W, const float* __restrict__
       }
       __syncwarp();
       if (oy < Ho) {
-        bf16* orow = out + (((size_t)fl * Ho + oy) * Wo + x0 + 16 * xh) * 64;
+        bf16* orow = out + ((size_t)(fl0 + fl) * Ho + oy) * Wo * 64;
 #pragma unroll
         for (int i = 0; i < 4; ++i) {
           const int chunk = i * 32 + lane, px = chunk >> 3, part = chunk & 7;
-          if (x0 + 16 * xh + px < Wo)
-            *reinterpret_cast<uint4*>(orow + px * 64 + part * 8) = *reinterpret_cast<const uint4*>(so + px * ST_OPITCH + part * 16);
+          const int xo = x0 + 16 * xh + px;                  // computed column; the flipped forward stores it mirrored
+          if (xo < Wo)
+            *reinterpret_cast<uint4*>(orow + (size_t)(FLIP ? Wo - 1 - xo : xo) * 64 + part * 8) =
+                *reinterpret_cast<const uint4*>(so + px * ST_OPITCH + part * 16);
         }
       }
       __syncwarp();
@@ -672,16 +686,25 @@ int head1x1_launch(const ConvP& p, cudaStream_t s, int* handled) {
 
 int stem_launch(cudaStream_t s, const float* x, int H, int W, const float* w, const float* bias,
                 bf16* out, int f0, int nb, int n_crops) {
-  RSG_REQUIRE(H % 2 == 0 && W % 2 == 0, "stem: H and W must be even");
-  const long long total = (long long)nb * (H / 2) * (W / 2);
-  if (total == 0) return RSG_OK;
+  RSG_REQUIRE(H % 2 == 0 && W % 4 == 0, "stem: H must be even and W a multiple of 4");
+  RSG_REQUIRE(((uintptr_t)x % 16) == 0, "stem: the input must be 16-byte aligned");
+  if (nb == 0) return RSG_OK;
   const int tiles_x = ceil_div(W / 2, ST_TX), tiles_y = ceil_div(H / 2, ST_TY);
-  const long long nblk = (long long)tiles_x * tiles_y * nb;
-  RSG_REQUIRE(nblk < (1ll << 31), "stem: too many tiles");
-  int grid = 2 * rsg_num_sms();                        // persistent: two CTAs per SM walk the tiles
-  if (grid > nblk) grid = (int)nblk;
-  stem_kernel<<<grid, 256, 0, s>>>(x, H, W, w, bias, out, f0, nb, n_crops, tiles_x, tiles_y, (int)nblk);
-  RSG_LAUNCH_CHECK();
+  // forwards [f0, f0 + nb) of the run: the first n_unf read their crop as it is, the rest W-flipped (f >= n_crops)
+  int n_unf = n_crops - f0;
+  if (n_unf < 0) n_unf = 0;
+  if (n_unf > nb) n_unf = nb;
+  for (int part = 0; part < 2; ++part) {
+    const int cnt = part == 0 ? n_unf : nb - n_unf, fl0 = part == 0 ? 0 : n_unf;
+    if (cnt == 0) continue;
+    const long long nblk = (long long)tiles_x * tiles_y * cnt;
+    RSG_REQUIRE(nblk < (1ll << 31), "stem: too many tiles");
+    int grid = 2 * rsg_num_sms();                      // persistent: two CTAs per SM walk the tiles
+    if (grid > nblk) grid = (int)nblk;
+    if (part == 0) stem_kernel<false><<<grid, 256, 0, s>>>(x, H, W, w, bias, out, f0, fl0, n_crops, tiles_x, tiles_y, (int)nblk);
+    else stem_kernel<true><<<grid, 256, 0, s>>>(x, H, W, w, bias, out, f0, fl0, n_crops, tiles_x, tiles_y, (int)nblk);
+    RSG_LAUNCH_CHECK();
+  }
   return RSG_OK;
 }
 
