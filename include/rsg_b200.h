@@ -288,6 +288,108 @@ int rsg_conv_ws2_config(int Cin, int CoutPad, int ntaps, int H, int W);
 /* Stand-alone conv launch (unit tests / micro-benchmarks): desc refs must be absolute. */
 int rsg_conv_run(void* stream, const rsg_conv_desc*, int N);
 
+/* ------------------------------------------------------------------------------------------
+ * Training step (BASELINE.json configs[4]).  Replaces what torch autograd + cuDNN / cuBLAS + torch.optim
+ * execute for lib/core/function.py:240-363 (rsgnet_train): train-mode forward of lib/models/pose_rsgnet.py:955-1021 (batch-
+ * statistics BatchNorm), the losses (lib/core/loss.py:14-38 JointsMSELoss, BCELoss, the relation MSE), the backward pass
+ * and Adam (lib/utils/utils.py:70-74).  Every tensor is fp32; activations are NHWC, i.e. row-major [pixels, channels]
+ * matrices.  The host side (rsgnet_b200/train) sequences these calls with its own tape.
+ * ---------------------------------------------------------------------------------------- */
+
+/* C[b] (M x Nc, row pitch ldc) = (beta ? C[b] : 0) + gather(A[b]) . B[b] (+ bias[n]),  b < batch (strides sA/sB/sC elements).
+ *   mode 0  plain GEMM: A is M x Ca (row pitch lda), or Ca x M when transA
+ *   mode 1  convolution forward gather: C rows are the pixels (n, y, x) of the Hc x Wc grid, A rows the pixels of the
+ *           Ha x Wa grid; tap (dy, dx) reads A pixel (y*stride - pad + dy, x*stride - pad + dx), zero outside
+ *   mode 2  convolution input-gradient gather (= ConvTranspose forward): tap (dy, dx) reads A pixel
+ *           ((y + pad - dy) / stride, (x + pad - dx) / stride) when both divisions are exact and inside the grid
+ *   B       [taps][Ca][Nc] (row pitch ldb), or with transB [taps][Nc][Ca]: element (c, n) at B[tap*Nc*ldb + n*ldb + c]
+ *           (the input-gradient pass reads the forward weights [tap][Cin][Cout] transposed)
+ *   geom    {Ha, Wa, Hc, Wc, kh, kw, stride, pad} for modes 1 / 2 (taps = kh*kw), ignored for mode 0
+ *   precise 0: TF32 mma.sync with fp32 accumulation; 1: 3xTF32 (fp32-class products), for parity tests */
+int rsg_train_gemm(void* stream, const float* A, const float* B, float* C, const float* bias, int M, int Nc, int Ca,
+                   int lda, int ldb, int ldc, int batch, long long sA, long long sB, long long sC, int mode,
+                   int transA, int transB, int beta, const int* geom, int precise);
+
+/* Weight gradient: dW[tap][ci][co] += sum over the M pixels m of dY's grid of X[src(m, tap)][ci] * dY[m][co]  (fp32 atomics
+ * over pixel splits: dW must hold zeros or the gradient accumulated so far).  mode / geom as for rsg_train_gemm, the
+ * gather applies to X.  With mode 0 this is dW[ci][co] += X^T dY (Linear / 1x1 weight gradients, either orientation). */
+int rsg_train_wgrad(void* stream, const float* X, const float* dY, float* dW, int M, int Ca, int Nc, int ldx, int ldy,
+                    int mode, const int* geom, int precise);
+
+/* BatchNorm over the rows of x [M, C] with batch statistics (torch batch_norm, training=True): y = (x - mean) * invstd *
+ * gamma + beta (+ ReLU); running_mean / running_var (may be NULL) are updated with `momentum`, running_var with the
+ * unbiased variance.  save_mean / save_invstd [C] feed the backward pass; ws = 2*C doubles of scratch. */
+int rsg_train_bn_fwd(void* stream, const float* x, long long M, int C, const float* gamma, const float* beta, float eps,
+                     float momentum, float* running_mean, float* running_var, int relu, float* y, float* save_mean,
+                     float* save_invstd, double* ws);
+/* dx (may be NULL) = gamma * invstd * (dy' - mean(dy') - xhat * mean(dy' * xhat)), dgamma += sum dy' * xhat, dbeta += sum dy',
+ * with dy' = dy * [y > 0] when relu (y = the forward output). */
+int rsg_train_bn_bwd(void* stream, const float* x, const float* y, const float* dy, long long M, int C, const float* gamma,
+                     const float* save_mean, const float* save_invstd, int relu, float* dx, float* dgamma, float* dbeta,
+                     double* ws);
+/* out[c] (+)= sum over the M rows of x[m][c]  (bias gradients; backward of a batch broadcast).  ws = C doubles. */
+int rsg_train_colsum(void* stream, const float* x, long long M, int C, float* out, int accumulate, double* ws);
+
+/* GroupNorm(G, C) over x [B, S, C] (association.py:243-246); mean / rstd are [B*G]. */
+int rsg_train_gn_fwd(void* stream, const float* x, int B, int S, int C, int G, const float* gamma, const float* beta, float eps,
+                     float* y, float* mean, float* rstd);
+int rsg_train_gn_bwd(void* stream, const float* x, const float* dy, int B, int S, int C, int G, const float* gamma,
+                     const float* mean, const float* rstd, float* dx, float* dgamma, float* dbeta);
+
+/* out = in[0] + ... + in[nin-1] (+ ReLU); `in` is a HOST array of 1..4 device pointers. */
+int rsg_train_add(void* stream, int nin, const float* const* in, int relu, long long n, float* out);
+/* Element-wise: op 0 out = a * [b > 0] (ReLU backward, b = the ReLU output); 1 out = sigmoid(a); 2 out = a * b * (1 - b)
+ * (sigmoid backward, b = the sigmoid output); 3 out = leaky_relu(a, slope); 4 out = a * (b > 0 ? 1 : slope); 5 out = a * b;
+ * 6 out += a; 7 out = a * slope. */
+int rsg_train_ew(void* stream, int op, const float* a, const float* b, float slope, long long n, float* out);
+/* rows x cols copy between pitched matrices (pitches in elements; src_pitch 0 broadcasts one row; accumulate: dst += src):
+ * channel concatenation / slicing and the batch repeat of the location branch. */
+int rsg_train_copy2d(void* stream, const float* src, long long src_pitch, float* dst, long long dst_pitch, long long rows,
+                     int cols, int accumulate);
+/* dst[i0][i1][i2] (contiguous D0 x D1 x D2) (+)= src[i0*s0 + i1*s1 + i2*s2] for i1 < V1 and i2 < V2, else 0: NCHW <-> NHWC and
+ * the weight packing OIHW -> [tap][Cin][Cout] / gradient unpacking. */
+int rsg_train_permute3(void* stream, const float* src, float* dst, int D0, int D1, int D2, long long s0, long long s1,
+                       long long s2, int V1, int V2, int accumulate);
+typedef struct rsg_perm_entry {
+  const float* src; float* dst;
+  int32_t D0, D1, D2, V1, V2;
+  long long s0, s1, s2;
+  int32_t accumulate;
+} rsg_perm_entry;
+/* The same for a DEVICE table of `count` entries in one launch (all conv weights of a step). */
+int rsg_train_permute3_batch(void* stream, const void* table, int count, int blocks_per_entry);
+/* kind 0 nearest up-sampling x f ([N,h,w,C] -> [N,hf,wf,C]); 1 its backward (in = dy [N,hf,wf,C], out = dx); 2 bilinear x2
+ * with align_corners=True; 3 its backward (out is zeroed here).  pose_rsgnet.py:207-219, 1009-1012. */
+int rsg_train_resample(void* stream, int kind, const float* in, int N, int h, int w, int C, int f, float* out);
+/* 2x2 max pooling of [N,H,W,C] (association.py:221); idx [N,H/2,W/2,C] keeps the arg-max for backward (in = dy, out = dx). */
+int rsg_train_maxpool(void* stream, int backward, const float* in, unsigned char* idx, int N, int H, int W, int C, float* out);
+
+/* JointsMSELoss (lib/core/loss.py:14-38) on NCHW [B,K,HW] with target_weight tw [B,K] (NULL = 1): *loss_acc += 0.5/(K B HW) *
+ * sum (tw (pred - target))^2; grad (may be NULL) = up * d loss / d pred. */
+int rsg_train_mse_joints(void* stream, const float* pred, const float* target, const float* tw, int B, int K, int HW, float up,
+                         double* loss_acc, float* grad);
+/* weight * BCELoss(mean) (function.py:253, 307): logs clamped at -100 as torch does. */
+int rsg_train_bce(void* stream, const float* p, const float* t, long long n, double weight, float up, double* loss_acc,
+                  float* grad);
+/* pose_rsgnet.py:1014-1018: out_acc[b] += mean_ij (T[b,i,j] - P[b,i,j])^2; T [B,S,S] or NULL with T = v v^T, v [B,S]
+ * (function.py:261-269 builds exactly that outer product). */
+int rsg_train_relation_mse(void* stream, const float* P, const float* T, const float* v, int B, int S, double* out_acc);
+/* The rank-1 factor of the relation target (lib/core/function.py:261-269): v [B, (H/2)*(W/2)] = bilinear(align_corners=True,
+ * scale 1/2) of max_k target[b,k]; relation_target = v v^T is never materialised on this path. */
+int rsg_train_person_mask(void* stream, const float* target, int B, int K, int H, int W, float* v);
+/* dA = (dP + coef[b] * (P - T)) * P * (1 - P): backward of relation_score = sigmoid(A) with the relation-loss term folded
+ * in (dP NULL = 0; coef NULL = no loss term; coef[b] = 2 / S^2 * d loss / d out[b]). */
+int rsg_train_trp_dscore(void* stream, const float* P, const float* dP, const float* T, const float* v, const float* coef,
+                         int B, int S, float* dA);
+/* cudaMemsetAsync(p, 0, bytes) on `stream` (gradient buffers, loss accumulators). */
+int rsg_train_zero(void* stream, void* p, size_t bytes);
+/* out[i] (+)= (float)in[i] * scale  (loss accumulators are doubles). */
+int rsg_train_d2f(void* stream, const double* in, float scale, int n, int accumulate, float* out);
+/* torch.optim.Adam (no weight decay, no amsgrad) on flat buffers; step >= 1; the gradient is read as g * grad_scale
+ * (1 / world_size after a summing all-reduce). */
+int rsg_train_adam(void* stream, float* p, const float* g, float* m, float* v, long long n, float lr, float beta1, float beta2,
+                   float eps, int step, float grad_scale);
+
 #ifdef __cplusplus
 }
 #endif

@@ -218,6 +218,104 @@ def warp_cases():
     print('wrote', fn, os.path.getsize(fn) // 1024, 'KiB')
 
 
+TSUB = 997          # prime stride of the sub-sampled flat gradient / parameter vectors of the training fixtures
+
+
+def train_case(key, batch, seed):
+    """One iteration of the UNMODIFIED lib/core/function.py:rsgnet_train (or :train for the vanilla HRNet) on the CPU:
+    reference model in train mode, reference criterion, torch.optim.Adam(lr=1e-3) as lib/utils/utils.py:70-74 builds it.
+    Tensor.cuda() / Module.cuda() are identity here (no GPU in this container) -- the only patch, outside the reference.
+    The loop runs twice: in fp32 (what the reference does) and in fp64 (the same code on .double() weights and inputs).
+    The fp64 run is the yard-stick: the GroupNorm behind the TRP amplifies fp32 rounding (its input has a mean ~1000x its
+    spread with these weights), so two CORRECT fp32 implementations differ by ~1 % in the gradients upstream of it;
+    tests bound an implementation's distance to the fp64 run by a multiple of the reference's own fp32 distance."""
+    import contextlib
+    import io
+    import re
+    import tempfile
+    import types
+    f = ref_import.ref_train_functions()
+    cfg = presets.preset(key)
+    name = cfg.MODEL.NAME
+    ours = (pose_rsgnet if name == 'pose_rsgnet' else pose_hrnet).get_pose_net(cfg, False)
+    sd = _params.synth_state_dict(ours, seed=seed)
+    hw = cfg.MODEL.HEATMAP_SIZE
+    b = synth.train_batch(batch, cfg.MODEL.IMAGE_SIZE, hw, cfg.MODEL.NUM_JOINTS, max(int(cfg.MODEL.NUM_LIMBS), 1), seed=seed)
+    config = presets._wrap(dict(MODEL=dict(UDP_POSE_ON=False), LOSS=dict(USE_TARGET_WEIGHT=True), PRINT_FREQ=100,
+                                DEBUG=dict(DEBUG=False, SAVE_BATCH_IMAGES_GT=False, SAVE_BATCH_IMAGES_PRED=False,
+                                           SAVE_HEATMAPS_GT=False, SAVE_HEATMAPS_PRED=False)))
+
+    def run(dtype):
+        ref = ref_import.ref_model(cfg, name)
+        ref.load_state_dict(sd, strict=True)
+        ref = ref.to(dtype)
+        tb = {k: torch.from_numpy(v).to(dtype) for k, v in b.items()}
+        meta = {}
+        if name == 'pose_rsgnet':
+            loader = [(tb['input'], tb['target'], tb['target_weight'], tb['all_ins_target'], tb['all_ins_target_weight'],
+                       tb['target_limbs'], meta)]
+            loop = f['rsgnet_train']
+        else:
+            loader = [(tb['input'], tb['target'], tb['target_weight'], meta)]
+            loop = f['train']
+        criterion = f['JointsMSELoss'](use_target_weight=True)
+        optimizer = torch.optim.Adam(ref.parameters(), lr=1e-3)
+        writer = types.SimpleNamespace(add_scalar=lambda *a, **k: None)
+        writer_dict = dict(writer=writer, train_global_steps=0)
+        old_t, old_m = torch.Tensor.cuda, torch.nn.Module.cuda
+        torch.Tensor.cuda = lambda self, *a, **k: self
+        torch.nn.Module.cuda = lambda self, *a, **k: self
+        out = io.StringIO()
+        logging_disable = __import__('logging').disable
+        try:
+            logging_disable(50)
+            with contextlib.redirect_stdout(out), tempfile.TemporaryDirectory() as tmp:
+                loop(config, loader, ref, criterion, optimizer, 0, tmp, tmp, writer_dict)
+        finally:
+            logging_disable(0)
+            torch.Tensor.cuda, torch.nn.Module.cuda = old_t, old_m
+        losses = None
+        if name == 'pose_rsgnet':
+            m = re.search(r'multi_kpt_loss: (\S+) kpt_loss: (\S+)\s+limbs_loss: (\S+) relation loss: (\S+)', out.getvalue())
+            assert m, out.getvalue()
+            losses = np.array([float(v) for v in m.groups()], np.float64)     # multi, target, skeleton, relation
+        return ref, losses
+
+    ref, losses = run(torch.float32)
+    ref64, losses64 = run(torch.float64)
+    rec = dict(preset=key, batch=batch, seed=seed, sub=TSUB)
+    if losses is not None:
+        rec['losses'], rec['losses64'] = losses, losses64
+    new_sd, new_sd64 = ref.state_dict(), ref64.state_dict()
+    names = [k for k, p in ref.named_parameters() if p.requires_grad]
+    grads, grads64 = dict(ref.named_parameters()), dict(ref64.named_parameters())
+    rec['names'] = np.array(names)
+    rec['grad_norm'] = np.array([float(grads[k].grad.double().norm()) for k in names])
+    rec['grad_norm64'] = np.array([float(grads64[k].grad.norm()) for k in names])
+    rec['grad_err32'] = np.array([float((grads[k].grad.double() - grads64[k].grad).norm()) for k in names])
+    flat_g = torch.cat([grads[k].grad.reshape(-1) for k in names])
+    flat_g64 = torch.cat([grads64[k].grad.reshape(-1) for k in names])
+    flat_d = torch.cat([(new_sd[k] - sd[k]).reshape(-1) for k in names])
+    rec['grad_sub'] = flat_g[::TSUB].numpy().copy()
+    rec['grad_sub64'] = flat_g64[::TSUB].numpy().copy()
+    rec['delta_sub'] = flat_d[::TSUB].numpy().copy()
+    for k in ('final_layer.weight', 'kt_machine.matrix_limb', 'relation_head.g.weight', 'conv1.weight', 'type_features',
+              'stage2.0.fuse_layers.0.1.0.weight'):
+        if k in grads and grads[k].grad is not None:
+            rec['grad.' + k] = grads[k].grad.numpy().copy()
+            rec['grad64.' + k] = grads64[k].grad.numpy().copy()
+    bufs = [k for k in new_sd if k.endswith('running_mean') or k.endswith('running_var')]
+    rec['buf_names'] = np.array(bufs)
+    rec['buf_sub'] = torch.cat([new_sd[k].reshape(-1) for k in bufs])[::7].numpy().copy()
+    rec['buf_sub64'] = torch.cat([new_sd64[k].reshape(-1) for k in bufs])[::7].numpy().copy()
+    rec['num_batches_tracked'] = np.int64(new_sd['bn1.num_batches_tracked'])
+    fn = os.path.join(OUT, f'train_{key}.npz')
+    np.savez_compressed(fn, **rec)
+    rel = rec['grad_err32'] / np.maximum(rec['grad_norm64'], 1e-30)
+    print('wrote', fn, os.path.getsize(fn) // 1024, 'KiB', rec.get('losses'), 'fp32-vs-fp64 grad error per tensor: median %.2e max %.2e'
+          % (np.median(rel), rel.max()))
+
+
 def main():
     assert ref_import.available(), 'needs /root/reference'
     os.makedirs(OUT, exist_ok=True)
@@ -239,6 +337,10 @@ def main():
         model_case('w32_crowdpose', 1, 4, full=False)
         model_case('hrnet_w32_coco', 1, 5, full=False)
         model_case('w48_coco_384', 1, 6, full=False)
+    if 'train' in which:
+        train_case('tiny', 2, 0)
+        train_case('tiny_cp', 3, 1)
+        train_case('tiny_hrnet', 2, 2)
 
 
 if __name__ == '__main__':

@@ -48,10 +48,18 @@ class _W:
         return f"{self.prefix}{name}" in self.sd
 
     def __getitem__(self, name):
-        return self.sd[f"{self.prefix}{name}"].float()
+        return self.sd[f"{self.prefix}{name}"].to(DTYPE)
+
+
+DTYPE = torch.float32  # oracle/train_oracle.py runs the same graph in float64 as a yard-stick
+TRAIN = False        # oracle/train_oracle.py flips this: batch statistics + running-stat updates (momentum 0.1), as
+                     # nn.BatchNorm2d(momentum=BN_MOMENTUM) does in train mode (pose_rsgnet.py:16, 32-36)
 
 
 def _bn(w, x):
+    if TRAIN:
+        return F.batch_norm(x, w.sd[w.prefix + "running_mean"], w.sd[w.prefix + "running_var"], w["weight"], w["bias"],
+                            True, 0.1, EPS)
     return F.batch_norm(x, w["running_mean"], w["running_var"], w["weight"], w["bias"],
                         False, 0.0, EPS)
 
@@ -211,8 +219,7 @@ def rsgnet_forward(sd, cfg, x, stages=None, relation_target=None):
 
     # type branch: scores^T . relu(bn1d(type_features W^T)) spread over space, then 3x3 conv
     tf = F.linear(w["type_features"], w["type_fc.0.weight"])
-    tf = F.relu(F.batch_norm(tf, w["type_fc.1.running_mean"], w["type_fc.1.running_var"],
-                             w["type_fc.1.weight"], w["type_fc.1.bias"], False, 0.0, EPS))
+    tf = F.relu(_bn(w.sub("type_fc.1"), tf))
     Kj, H, Wd = multi.shape[1:]
     t = multi.reshape(B, Kj, H * Wd).permute(0, 2, 1) @ tf            # B,S,T
     t = t.permute(0, 2, 1).reshape(B, tf.shape[1], H, Wd)

@@ -140,3 +140,24 @@ def ref_dataset_evaluate(kind):
             shutil.rmtree(out_dir, ignore_errors=True)
         return captured['kpts']
     return run
+
+
+def ref_train_functions():
+    """The reference's own training loops and criterion, importable here: lib/core/function.py (rsgnet_train, train) and
+    lib/core/loss.py (JointsMSELoss), UNMODIFIED.  ``yacs`` (lib/config builds its defaults with CfgNode at import) and
+    ``tensorboardX`` are absent offline and never reached by one iteration of the loop: both are stubbed in sys.modules."""
+    _install_shims()
+    sys.modules.setdefault('tensorboardX', types.ModuleType('tensorboardX'))
+    if 'yacs' not in sys.modules:
+        class CN(dict):
+            def __init__(self, init_dict=None, new_allowed=False):
+                super().__init__(init_dict or {})
+            __getattr__ = dict.__getitem__
+            __setattr__ = dict.__setitem__
+        y, yc = types.ModuleType('yacs'), types.ModuleType('yacs.config')
+        yc.CfgNode = CN
+        y.config = yc
+        sys.modules['yacs'], sys.modules['yacs.config'] = y, yc
+    fn = importlib.import_module('core.function')
+    loss = importlib.import_module('core.loss')
+    return dict(rsgnet_train=fn.rsgnet_train, train=fn.train, JointsMSELoss=loss.JointsMSELoss)

@@ -1000,8 +1000,13 @@ def module_forward(module, x, relation_target=None):
     graph per (batch size, device); DataParallel replicas build their engines from the source module's parameters."""
     src = _source(module)
     if module.training or src.training:
-        raise _lib.RsgError('rsgnet_b200 implements the inference path only: call model.eval() '
-                            '(training mode needs batch-statistics BatchNorm; SURVEY.md §8f-4)')
+        # train mode: batch-statistics BatchNorm + a differentiable output (lib/core/function.py:271 calls
+        # model(input, relation_target) and then loss.backward()): rsgnet_b200/train, not the folded inference plan
+        if src is not module:
+            raise _lib.RsgError('training mode under nn.DataParallel replicas is not supported: run one process per GPU '
+                                '(rsgnet_b200.train.TrainStep all-reduces the gradients over NCCL)')
+        from .train.step import module_forward_train
+        return module_forward_train(module, x, relation_target)
     _lib.require_cuda()
     spec = src.spec
     if x.dim() != 4 or x.shape[1] != 3 or x.shape[2] != spec.image_h or x.shape[3] != spec.image_w:

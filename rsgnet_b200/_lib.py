@@ -47,6 +47,13 @@ def ext_ref(slot, offset=0, crop_stride=0):
     return Ref(None, int(slot), int(offset), int(crop_stride))
 
 
+class PermEntry(C.Structure):
+    """rsg_perm_entry (include/rsg_b200.h)."""
+    _fields_ = [('src', C.c_void_p), ('dst', C.c_void_p), ('D0', C.c_int32), ('D1', C.c_int32), ('D2', C.c_int32),
+                ('V1', C.c_int32), ('V2', C.c_int32), ('s0', C.c_longlong), ('s1', C.c_longlong), ('s2', C.c_longlong),
+                ('accumulate', C.c_int32)]
+
+
 class RsgError(RuntimeError):
     pass
 
@@ -113,6 +120,34 @@ _SIGS = {
     'rsg_conv_ws_config2': (C.c_int, [C.c_int] * 6 + [C.POINTER(C.c_int)]),
     'rsg_conv_ws2_config': (C.c_int, [C.c_int] * 5),
     'rsg_conv_run': (C.c_int, [C.c_void_p, C.POINTER(ConvDesc), C.c_int]),
+    # ---- training step (include/rsg_b200.h 'Training step') ----
+    'rsg_train_gemm': (C.c_int, [C.c_void_p] * 5 + [C.c_int] * 7 + [C.c_longlong] * 3 + [C.c_int] * 4 +
+                       [C.POINTER(C.c_int), C.c_int]),
+    'rsg_train_wgrad': (C.c_int, [C.c_void_p] * 4 + [C.c_int] * 6 + [C.POINTER(C.c_int), C.c_int]),
+    'rsg_train_bn_fwd': (C.c_int, [C.c_void_p, C.c_void_p, C.c_longlong, C.c_int, C.c_void_p, C.c_void_p, C.c_float,
+                                   C.c_float, C.c_void_p, C.c_void_p, C.c_int] + [C.c_void_p] * 4),
+    'rsg_train_bn_bwd': (C.c_int, [C.c_void_p] * 4 + [C.c_longlong, C.c_int] + [C.c_void_p] * 3 + [C.c_int] +
+                         [C.c_void_p] * 4),
+    'rsg_train_colsum': (C.c_int, [C.c_void_p, C.c_void_p, C.c_longlong, C.c_int, C.c_void_p, C.c_int, C.c_void_p]),
+    'rsg_train_gn_fwd': (C.c_int, [C.c_void_p, C.c_void_p] + [C.c_int] * 4 + [C.c_void_p] * 2 + [C.c_float] +
+                         [C.c_void_p] * 3),
+    'rsg_train_gn_bwd': (C.c_int, [C.c_void_p] * 3 + [C.c_int] * 4 + [C.c_void_p] * 6),
+    'rsg_train_add': (C.c_int, [C.c_void_p, C.c_int, C.POINTER(C.c_void_p), C.c_int, C.c_longlong, C.c_void_p]),
+    'rsg_train_ew': (C.c_int, [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_float, C.c_longlong, C.c_void_p]),
+    'rsg_train_copy2d': (C.c_int, [C.c_void_p, C.c_void_p, C.c_longlong, C.c_void_p, C.c_longlong, C.c_longlong,
+                                   C.c_int, C.c_int]),
+    'rsg_train_permute3': (C.c_int, [C.c_void_p] * 3 + [C.c_int] * 3 + [C.c_longlong] * 3 + [C.c_int] * 3),
+    'rsg_train_permute3_batch': (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int]),
+    'rsg_train_resample': (C.c_int, [C.c_void_p, C.c_int, C.c_void_p] + [C.c_int] * 5 + [C.c_void_p]),
+    'rsg_train_maxpool': (C.c_int, [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p] + [C.c_int] * 4 + [C.c_void_p]),
+    'rsg_train_mse_joints': (C.c_int, [C.c_void_p] * 4 + [C.c_int] * 3 + [C.c_float, C.c_void_p, C.c_void_p]),
+    'rsg_train_bce': (C.c_int, [C.c_void_p] * 3 + [C.c_longlong, C.c_double, C.c_float, C.c_void_p, C.c_void_p]),
+    'rsg_train_relation_mse': (C.c_int, [C.c_void_p] * 4 + [C.c_int, C.c_int, C.c_void_p]),
+    'rsg_train_trp_dscore': (C.c_int, [C.c_void_p] * 6 + [C.c_int, C.c_int, C.c_void_p]),
+    'rsg_train_person_mask': (C.c_int, [C.c_void_p, C.c_void_p] + [C.c_int] * 4 + [C.c_void_p]),
+    'rsg_train_zero': (C.c_int, [C.c_void_p, C.c_void_p, C.c_size_t]),
+    'rsg_train_d2f': (C.c_int, [C.c_void_p, C.c_void_p, C.c_float, C.c_int, C.c_int, C.c_void_p]),
+    'rsg_train_adam': (C.c_int, [C.c_void_p] * 5 + [C.c_longlong] + [C.c_float] * 4 + [C.c_int, C.c_float]),
 }
 
 EXPORTS = tuple(_SIGS)

@@ -1,0 +1,753 @@
+// Training-step element-wise, normalisation, re-sampling, loss and optimiser kernels.  All tensors are
+// fp32; activations are NHWC = row-major [M pixels, C channels].  Reference semantics (paths under the reference):
+//   BatchNorm2d / BatchNorm1d in train mode  torch batch_norm: biased variance for the output, unbiased for running_var,
+//                                            running = (1 - momentum) running + momentum batch   (pose_rsgnet.py BN_MOMENTUM 0.1)
+//   GroupNorm(8, C)                          association.py:243-246
+//   nearest / bilinear(align_corners=True)   pose_rsgnet.py:207-219 (fuse layers), :1009-1012 (x2 up-sampling of the scores)
+//   JointsMSELoss                            lib/core/loss.py:14-38
+//   BCELoss, relation MSE                    lib/core/function.py:253, 307-311; pose_rsgnet.py:1014-1018
+//   Adam                                     lib/utils/utils.py:70-74 (torch.optim.Adam defaults: betas .9/.999, eps 1e-8)
+// These are HBM-bound streaming kernels: coalesced along the channel dimension, reductions in fp32 per thread and fp64
+// across threads / blocks (atomicAdd on double), grids sized from the SM count.
+#include "common.cuh"
+#include "../../include/rsg_b200.h"
+
+namespace {
+
+constexpr int EW_THREADS = 256;
+
+inline int ew_grid(long long n, int per_thread = 1) {
+  long long b = (n + (long long)EW_THREADS * per_thread - 1) / ((long long)EW_THREADS * per_thread);
+  const long long cap = 32ll * rsg_num_sms();
+  if (b > cap) b = cap;
+  if (b < 1) b = 1;
+  return (int)b;
+}
+
+#define GRID_STRIDE(i, n) for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < (n); i += (long long)gridDim.x * blockDim.x)
+
+// ------------------------------------------------------------------------------------------------------------------
+// Per-channel reductions over the rows of [M, C]: out[0][c] += sum f0, out[1][c] += sum f1 (double).
+// Thread layout: CT = min(C, 256) channel lanes, G = 256 / CT row groups; channel tiles loop when C > 256.
+// KIND 0: f0 = x, f1 = x^2                       (batch statistics)
+// KIND 1: f0 = dy', f1 = dy' * (x - mean) * invstd  with dy' = dy (or dy * [y > 0] when relu)   (BN backward sums)
+// KIND 2: f0 = x only                              (column sum: bias gradients, repeat backward)
+template <int KIND>
+__global__ void __launch_bounds__(EW_THREADS) chan_reduce_kernel(const float* __restrict__ x, const float* __restrict__ dy,
+                                                                 const float* __restrict__ y, const float* __restrict__ mean,
+                                                                 const float* __restrict__ invstd, int relu, long long M, int C,
+                                                                 int rows_per_block, double* __restrict__ out) {
+  __shared__ float red0[EW_THREADS], red1[EW_THREADS];
+  const int CT = C < EW_THREADS ? C : EW_THREADS, G = EW_THREADS / CT;
+  const int tid = threadIdx.x, g = tid / CT, cl = tid - g * CT;
+  const bool active = g < G;
+  const long long r0 = (long long)blockIdx.x * rows_per_block;
+  long long r1 = r0 + rows_per_block;
+  if (r1 > M) r1 = M;
+  for (int cb = 0; cb < C; cb += CT) {
+    const int c = cb + cl;
+    float s0 = 0.f, s1 = 0.f;
+    if (active && c < C) {
+      float mu = 0.f, is = 0.f;
+      if (KIND == 1) { mu = mean[c]; is = invstd[c]; }
+      for (long long r = r0 + g; r < r1; r += G) {
+        const long long i = r * C + c;
+        if (KIND == 0) { const float v = x[i]; s0 += v; s1 += v * v; }
+        else if (KIND == 1) {
+          float d = dy[i];
+          if (relu && !(y[i] > 0.f)) d = 0.f;
+          s0 += d;
+          s1 += d * (x[i] - mu) * is;
+        } else s0 += x[i];
+      }
+    }
+    red0[tid] = s0; red1[tid] = s1;
+    __syncthreads();
+    if (g == 0 && c < C) {
+      double a0 = 0.0, a1 = 0.0;
+      for (int k = 0; k < G; ++k) { a0 += (double)red0[k * CT + cl]; a1 += (double)red1[k * CT + cl]; }
+      atomicAdd(out + c, a0);
+      if (KIND != 2) atomicAdd(out + C + c, a1);
+    }
+    __syncthreads();
+  }
+}
+
+inline void chan_reduce_cfg(long long M, int& rows_per_block, int& blocks) {
+  long long b = (M + 63) / 64;                       // at least 64 rows per block
+  const long long cap = 8ll * rsg_num_sms();
+  if (b > cap) b = cap;
+  if (b < 1) b = 1;
+  rows_per_block = (int)((M + b - 1) / b);
+  blocks = (int)((M + rows_per_block - 1) / rows_per_block);
+}
+
+__global__ void bn_finalize_kernel(const double* __restrict__ sums, long long M, int C, float eps, float momentum,
+                                   float* __restrict__ mean, float* __restrict__ invstd, float* __restrict__ running_mean,
+                                   float* __restrict__ running_var) {
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= C) return;
+  const double mu = sums[c] / (double)M;
+  double var = sums[C + c] / (double)M - mu * mu;
+  if (var < 0.0) var = 0.0;
+  mean[c] = (float)mu;
+  invstd[c] = (float)(1.0 / sqrt(var + (double)eps));
+  if (running_mean) running_mean[c] = (1.f - momentum) * running_mean[c] + momentum * (float)mu;
+  if (running_var) {
+    const double unb = M > 1 ? var * (double)M / (double)(M - 1) : var;
+    running_var[c] = (1.f - momentum) * running_var[c] + momentum * (float)unb;
+  }
+}
+
+__global__ void __launch_bounds__(EW_THREADS) bn_apply_kernel(const float* __restrict__ x, const float* __restrict__ mean,
+                                                              const float* __restrict__ invstd, const float* __restrict__ gamma,
+                                                              const float* __restrict__ beta, int relu, long long n, int C,
+                                                              float* __restrict__ y) {
+  GRID_STRIDE(i, n) {
+    const int c = (int)(i % C);
+    float v = (x[i] - mean[c]) * invstd[c] * gamma[c] + beta[c];
+    if (relu) v = fmaxf(v, 0.f);
+    y[i] = v;
+  }
+}
+
+// dx = gamma * invstd * (dy' - sum_dy / M - xhat * sum_dy_xhat / M); block 0 also accumulates dgamma / dbeta
+__global__ void __launch_bounds__(EW_THREADS) bn_bwd_apply_kernel(const float* __restrict__ x, const float* __restrict__ dy,
+                                                                  const float* __restrict__ y, const float* __restrict__ mean,
+                                                                  const float* __restrict__ invstd, const float* __restrict__ gamma,
+                                                                  const double* __restrict__ sums, int relu, long long n, int C,
+                                                                  long long M, float* __restrict__ dx, float* __restrict__ dgamma,
+                                                                  float* __restrict__ dbeta) {
+  if (blockIdx.x == 0) {
+    for (int c = threadIdx.x; c < C; c += blockDim.x) {
+      if (dbeta) dbeta[c] += (float)sums[c];
+      if (dgamma) dgamma[c] += (float)sums[C + c];
+    }
+  }
+  if (!dx) return;
+  const double invM = 1.0 / (double)M;
+  GRID_STRIDE(i, n) {
+    const int c = (int)(i % C);
+    float d = dy[i];
+    if (relu && !(y[i] > 0.f)) d = 0.f;
+    const float xh = (x[i] - mean[c]) * invstd[c];
+    const float m0 = (float)(sums[c] * invM), m1 = (float)(sums[C + c] * invM);
+    dx[i] = gamma[c] * invstd[c] * (d - m0 - xh * m1);
+  }
+}
+
+// ------------------------------------------------------------------------------------------------------------------
+// GroupNorm over [B, S, C] with G groups: one block per (b, group); two passes (mean, then centred variance).
+__device__ __forceinline__ double block_sum(double v, double* sh) {
+  const int tid = threadIdx.x;
+  sh[tid] = v;
+  __syncthreads();
+  for (int s = blockDim.x >> 1; s > 0; s >>= 1) {
+    if (tid < s) sh[tid] += sh[tid + s];
+    __syncthreads();
+  }
+  const double r = sh[0];
+  __syncthreads();
+  return r;
+}
+
+__global__ void __launch_bounds__(EW_THREADS) gn_fwd_kernel(const float* __restrict__ x, int S, int C, int G, const float* __restrict__ gamma,
+                                                            const float* __restrict__ beta, float eps, float* __restrict__ y,
+                                                            float* __restrict__ mean, float* __restrict__ rstd) {
+  __shared__ double sh[EW_THREADS];
+  const int b = blockIdx.x / G, grp = blockIdx.x % G, cg = C / G, n = S * cg;
+  const float* xb = x + (long long)b * S * C + grp * cg;
+  double s = 0.0;
+  for (int i = threadIdx.x; i < n; i += blockDim.x) s += (double)xb[(long long)(i / cg) * C + i % cg];
+  const double mu = block_sum(s, sh) / n;
+  double q = 0.0;
+  for (int i = threadIdx.x; i < n; i += blockDim.x) { const double d = (double)xb[(long long)(i / cg) * C + i % cg] - mu; q += d * d; }
+  const double var = block_sum(q, sh) / n;
+  const float rs = (float)(1.0 / sqrt(var + (double)eps)), muf = (float)mu;
+  if (threadIdx.x == 0) { mean[blockIdx.x] = muf; rstd[blockIdx.x] = rs; }
+  float* yb = y + (long long)b * S * C + grp * cg;
+  for (int i = threadIdx.x; i < n; i += blockDim.x) {
+    const int c = i % cg;
+    const long long o = (long long)(i / cg) * C + c;
+    yb[o] = (xb[o] - muf) * rs * gamma[grp * cg + c] + beta[grp * cg + c];
+  }
+}
+
+__global__ void __launch_bounds__(EW_THREADS) gn_bwd_kernel(const float* __restrict__ x, const float* __restrict__ dy, int S, int C, int G,
+                                                            const float* __restrict__ gamma, const float* __restrict__ mean,
+                                                            const float* __restrict__ rstd, float* __restrict__ dx,
+                                                            float* __restrict__ dgamma, float* __restrict__ dbeta) {
+  __shared__ double sh[EW_THREADS];
+  __shared__ float sdg[64], sdb[64];                 // per-channel partials of this (b, group); C / G <= 64
+  const int b = blockIdx.x / G, grp = blockIdx.x % G, cg = C / G, n = S * cg;
+  const float muf = mean[blockIdx.x], rs = rstd[blockIdx.x];
+  const float* xb = x + (long long)b * S * C + grp * cg;
+  const float* db = dy + (long long)b * S * C + grp * cg;
+  for (int c = threadIdx.x; c < cg; c += blockDim.x) { sdg[c] = 0.f; sdb[c] = 0.f; }
+  __syncthreads();
+  double s1 = 0.0, s2 = 0.0;
+  // thread-private per-channel sums are impractical for arbitrary cg: channel of element i is i % cg, and a thread's
+  // elements i = tid + k * 256 keep the same channel only when 256 % cg == 0 -- shared atomics cover the general case
+  for (int i = threadIdx.x; i < n; i += blockDim.x) {
+    const int c = i % cg;
+    const long long o = (long long)(i / cg) * C + c;
+    const float d = db[o], xh = (xb[o] - muf) * rs, dg = d * gamma[grp * cg + c];
+    s1 += (double)dg;
+    s2 += (double)(dg * xh);
+    atomicAdd(&sdg[c], d * xh);
+    atomicAdd(&sdb[c], d);
+  }
+  const double m1 = block_sum(s1, sh) / n, m2 = block_sum(s2, sh) / n;
+  for (int c = threadIdx.x; c < cg; c += blockDim.x) {
+    if (dgamma) atomicAdd(dgamma + grp * cg + c, sdg[c]);
+    if (dbeta) atomicAdd(dbeta + grp * cg + c, sdb[c]);
+  }
+  if (!dx) return;
+  float* dxb = dx + (long long)b * S * C + grp * cg;
+  for (int i = threadIdx.x; i < n; i += blockDim.x) {
+    const int c = i % cg;
+    const long long o = (long long)(i / cg) * C + c;
+    const float xh = (xb[o] - muf) * rs, dg = db[o] * gamma[grp * cg + c];
+    dxb[o] = rs * (dg - (float)m1 - xh * (float)m2);
+  }
+}
+
+// ------------------------------------------------------------------------------------------------------------------
+// element-wise
+struct Ptr4 { const float* p[4]; };
+
+__global__ void __launch_bounds__(EW_THREADS) add_kernel(Ptr4 in, int nin, int relu, long long n, float* __restrict__ out) {
+  GRID_STRIDE(i, n) {
+    float v = in.p[0][i];
+    for (int k = 1; k < nin; ++k) v += in.p[k][i];
+    if (relu) v = fmaxf(v, 0.f);
+    out[i] = v;
+  }
+}
+
+// OP 0: dx = dy * [y > 0]            (ReLU backward, y = the ReLU output)
+// OP 1: y = sigmoid(x)               (a = x)
+// OP 2: dx = dy * y * (1 - y)        (a = dy, b = y)
+// OP 3: y = leaky(x, slope)          (a = x)
+// OP 4: dx = dy * (x > 0 ? 1 : slope) (a = dy, b = x)
+// OP 5: out = a * b
+// OP 6: out += a
+// OP 7: out = a * slope              (scale)
+template <int OP>
+__global__ void __launch_bounds__(EW_THREADS) ew_kernel(const float* __restrict__ a, const float* __restrict__ b, float slope, long long n,
+                                                        float* __restrict__ out) {
+  GRID_STRIDE(i, n) {
+    float v;
+    if (OP == 0) v = b[i] > 0.f ? a[i] : 0.f;
+    else if (OP == 1) v = 1.f / (1.f + expf(-a[i]));
+    else if (OP == 2) { const float yy = b[i]; v = a[i] * yy * (1.f - yy); }
+    else if (OP == 3) { const float xx = a[i]; v = xx > 0.f ? xx : xx * slope; }
+    else if (OP == 4) v = b[i] > 0.f ? a[i] : a[i] * slope;
+    else if (OP == 5) v = a[i] * b[i];
+    else if (OP == 6) v = out[i] + a[i];
+    else v = a[i] * slope;
+    out[i] = v;
+  }
+}
+
+// rows x cols copy between pitched matrices (pitch in elements; src_pitch 0 broadcasts one row); accumulate: dst += src
+__global__ void __launch_bounds__(EW_THREADS) copy2d_kernel(const float* __restrict__ src, long long src_pitch, float* __restrict__ dst,
+                                                            long long dst_pitch, long long rows, int cols, int accumulate) {
+  const long long n = rows * cols;
+  GRID_STRIDE(i, n) {
+    const long long r = i / cols;
+    const int c = (int)(i - r * cols);
+    const float v = src[r * src_pitch + c];
+    float* d = dst + r * dst_pitch + c;
+    *d = accumulate ? *d + v : v;
+  }
+}
+
+// dst[i0][i1][i2] (contiguous, dims D0 x D1 x D2) = src[i0 s0 + i1 s1 + i2 s2] where i1 < V1 and i2 < V2, else 0
+struct Perm {
+  const float* src; float* dst;
+  int D0, D1, D2, V1, V2;
+  long long s0, s1, s2;
+  int accumulate;
+};
+
+__device__ __forceinline__ void perm_body(const Perm& q, long long lo, long long stride) {
+  const long long n = (long long)q.D0 * q.D1 * q.D2;
+  for (long long i = lo; i < n; i += stride) {
+    const int i2 = (int)(i % q.D2);
+    const long long r = i / q.D2;
+    const int i1 = (int)(r % q.D1);
+    const long long i0 = r / q.D1;
+    float v = 0.f;
+    if (i1 < q.V1 && i2 < q.V2) v = q.src[i0 * q.s0 + i1 * q.s1 + i2 * q.s2];
+    q.dst[i] = q.accumulate ? q.dst[i] + v : v;
+  }
+}
+
+__global__ void __launch_bounds__(EW_THREADS) permute3_kernel(const Perm q) {
+  perm_body(q, (long long)blockIdx.x * blockDim.x + threadIdx.x, (long long)gridDim.x * blockDim.x);
+}
+
+// one launch for a whole table of permutations (the per-step weight packing / gradient unpacking): blockIdx.y = entry
+__global__ void __launch_bounds__(EW_THREADS) permute3_batch_kernel(const Perm* __restrict__ table) {
+  const Perm q = table[blockIdx.y];
+  perm_body(q, (long long)blockIdx.x * blockDim.x + threadIdx.x, (long long)gridDim.x * blockDim.x);
+}
+
+// nearest-neighbour up-sampling by an integer factor f: [N, h, w, C] -> [N, h f, w f, C]; backward = f x f block sums
+__global__ void __launch_bounds__(EW_THREADS) nearest_fwd_kernel(const float* __restrict__ x, int h, int w, int C, int f, long long n,
+                                                                 float* __restrict__ y) {
+  const int W = w * f, H = h * f;
+  GRID_STRIDE(i, n) {
+    const int c = (int)(i % C);
+    long long r = i / C;
+    const int X = (int)(r % W); r /= W;
+    const int Y = (int)(r % H);
+    const long long nb = r / H;
+    y[i] = x[((nb * h + Y / f) * w + X / f) * C + c];
+  }
+}
+
+__global__ void __launch_bounds__(EW_THREADS) nearest_bwd_kernel(const float* __restrict__ dy, int h, int w, int C, int f, long long n,
+                                                                 float* __restrict__ dx) {
+  const int W = w * f, H = h * f;
+  GRID_STRIDE(i, n) {                    // n = elements of dx
+    const int c = (int)(i % C);
+    long long r = i / C;
+    const int xx = (int)(r % w); r /= w;
+    const int yy = (int)(r % h);
+    const long long nb = r / h;
+    float s = 0.f;
+    for (int a = 0; a < f; ++a)
+      for (int b2 = 0; b2 < f; ++b2) s += dy[((nb * H + yy * f + a) * W + xx * f + b2) * C + c];
+    dx[i] = s;
+  }
+}
+
+// bilinear x2, align_corners=True: src = dst * (in - 1) / (out - 1) (torch area_pixel_compute_source_index)
+__device__ __forceinline__ void bil_src(int o, int in, int out, int& i0, int& i1, float& l1) {
+  const float scale = out > 1 ? (float)(in - 1) / (float)(out - 1) : 0.f;
+  const float s = scale * (float)o;
+  i0 = (int)s;
+  if (i0 > in - 1) i0 = in - 1;
+  i1 = i0 + (i0 < in - 1 ? 1 : 0);
+  l1 = s - (float)i0;
+}
+
+__global__ void __launch_bounds__(EW_THREADS) bilinear_fwd_kernel(const float* __restrict__ x, int h, int w, int C, long long n,
+                                                                  float* __restrict__ y) {
+  const int H = 2 * h, W = 2 * w;
+  GRID_STRIDE(i, n) {
+    const int c = (int)(i % C);
+    long long r = i / C;
+    const int X = (int)(r % W); r /= W;
+    const int Y = (int)(r % H);
+    const long long nb = r / H;
+    int y0, y1, x0, x1;
+    float ly, lx;
+    bil_src(Y, h, H, y0, y1, ly);
+    bil_src(X, w, W, x0, x1, lx);
+    const float* xb = x + nb * h * w * C + c;
+    const float v00 = xb[((long long)y0 * w + x0) * C], v01 = xb[((long long)y0 * w + x1) * C];
+    const float v10 = xb[((long long)y1 * w + x0) * C], v11 = xb[((long long)y1 * w + x1) * C];
+    const float hy = 1.f - ly, hx = 1.f - lx;
+    y[i] = hy * (hx * v00 + lx * v01) + ly * (hx * v10 + lx * v11);
+  }
+}
+
+__global__ void __launch_bounds__(EW_THREADS) bilinear_bwd_kernel(const float* __restrict__ dy, int h, int w, int C, long long n,
+                                                                  float* __restrict__ dx) {   // dx zeroed by the caller
+  const int H = 2 * h, W = 2 * w;
+  GRID_STRIDE(i, n) {                    // n = elements of dy
+    const int c = (int)(i % C);
+    long long r = i / C;
+    const int X = (int)(r % W); r /= W;
+    const int Y = (int)(r % H);
+    const long long nb = r / H;
+    int y0, y1, x0, x1;
+    float ly, lx;
+    bil_src(Y, h, H, y0, y1, ly);
+    bil_src(X, w, W, x0, x1, lx);
+    float* xb = dx + nb * h * w * C + c;
+    const float d = dy[i], hy = 1.f - ly, hx = 1.f - lx;
+    atomicAdd(xb + ((long long)y0 * w + x0) * C, d * hy * hx);
+    atomicAdd(xb + ((long long)y0 * w + x1) * C, d * hy * lx);
+    atomicAdd(xb + ((long long)y1 * w + x0) * C, d * ly * hx);
+    atomicAdd(xb + ((long long)y1 * w + x1) * C, d * ly * lx);
+  }
+}
+
+// 2x2 max pooling (TRP sub_sample, association.py:221): idx = arg-max position 0..3 kept for the backward pass
+__global__ void __launch_bounds__(EW_THREADS) maxpool_fwd_kernel(const float* __restrict__ x, int H, int W, int C, long long n,
+                                                                 float* __restrict__ y, unsigned char* __restrict__ idx) {
+  const int h = H / 2, w = W / 2;
+  GRID_STRIDE(i, n) {
+    const int c = (int)(i % C);
+    long long r = i / C;
+    const int xx = (int)(r % w); r /= w;
+    const int yy = (int)(r % h);
+    const long long nb = r / h;
+    float best = 0.f;
+    int bi = 0;
+    for (int k = 0; k < 4; ++k) {
+      const float v = x[((nb * H + 2 * yy + (k >> 1)) * W + 2 * xx + (k & 1)) * C + c];
+      if (k == 0 || v > best) { best = v; bi = k; }
+    }
+    y[i] = best;
+    idx[i] = (unsigned char)bi;
+  }
+}
+
+__global__ void __launch_bounds__(EW_THREADS) maxpool_bwd_kernel(const float* __restrict__ dy, const unsigned char* __restrict__ idx, int H,
+                                                                 int W, int C, long long n, float* __restrict__ dx) {
+  const int h = H / 2, w = W / 2;
+  GRID_STRIDE(i, n) {                    // n = elements of dx; odd trailing rows / columns get zero
+    const int c = (int)(i % C);
+    long long r = i / C;
+    const int X = (int)(r % W); r /= W;
+    const int Y = (int)(r % H);
+    const long long nb = r / H;
+    float v = 0.f;
+    if ((Y >> 1) < h && (X >> 1) < w) {
+      const long long o = ((nb * h + (Y >> 1)) * w + (X >> 1)) * C + c;
+      if (idx[o] == (unsigned char)(((Y & 1) << 1) | (X & 1))) v = dy[o];
+    }
+    dx[i] = v;
+  }
+}
+
+// ------------------------------------------------------------------------------------------------------------------
+// losses: out[0] += coef * sum; grad written per element
+__device__ __forceinline__ void block_atomic_add(double v, double* out) {
+  __shared__ double sh[EW_THREADS];
+  const double s = block_sum(v, sh);
+  if (threadIdx.x == 0) atomicAdd(out, s);
+}
+
+// JointsMSELoss on NCHW [B, K, HW]: loss = 0.5 / (K B HW) sum (w (p - t))^2 ; dp = up / (K B HW) * w^2 (p - t)
+__global__ void __launch_bounds__(EW_THREADS) mse_joints_kernel(const float* __restrict__ p, const float* __restrict__ t,
+                                                                const float* __restrict__ tw, int HW, long long n, double coef, float up,
+                                                                double* __restrict__ loss, float* __restrict__ grad) {
+  double s = 0.0;
+  const float gcoef = (float)(2.0 * coef) * up;
+  GRID_STRIDE(i, n) {
+    const float w = tw ? tw[i / HW] : 1.f;
+    const float d = w * (p[i] - t[i]);
+    s += (double)d * (double)d;
+    if (grad) grad[i] = gcoef * w * d;
+  }
+  block_atomic_add(s * coef, loss);
+}
+
+// BCELoss(mean): loss = -coef sum (t log p + (1 - t) log(1 - p)), logs clamped at -100 (torch); dp = up * coef * (p - t) / max(p (1 - p), 1e-12)
+__global__ void __launch_bounds__(EW_THREADS) bce_kernel(const float* __restrict__ p, const float* __restrict__ t, long long n, double coef,
+                                                         float up, double* __restrict__ loss, float* __restrict__ grad) {
+  double s = 0.0;
+  GRID_STRIDE(i, n) {
+    const float pp = p[i], tt = t[i];
+    const float lp = fmaxf(logf(pp), -100.f), lq = fmaxf(logf(1.f - pp), -100.f);
+    s -= (double)(tt * lp + (1.f - tt) * lq);
+    if (grad) grad[i] = up * (float)coef * (pp - tt) / fmaxf(pp * (1.f - pp), 1e-12f);
+  }
+  block_atomic_add(s * coef, loss);
+}
+
+// relation MSE (pose_rsgnet.py:1014-1018): out[b] = mean_ij (T[b,i,j] - P[b,i,j])^2, T given in full or as the rank-1
+// factor v[b] (T = v v^T: lib/core/function.py:261-269 builds it from the person mask)
+__global__ void __launch_bounds__(EW_THREADS) relation_mse_kernel(const float* __restrict__ P, const float* __restrict__ T,
+                                                                  const float* __restrict__ v, int S, int blocks_per_b,
+                                                                  double* __restrict__ out) {
+  const int b = blockIdx.x / blocks_per_b, part = blockIdx.x % blocks_per_b;
+  const long long n = (long long)S * S;
+  const float* Pb = P + (long long)b * n;
+  double s = 0.0;
+  for (long long i = (long long)part * blockDim.x + threadIdx.x; i < n; i += (long long)blocks_per_b * blockDim.x) {
+    const float tt = T ? T[(long long)b * n + i] : v[(long long)b * S + i / S] * v[(long long)b * S + i % S];
+    const float d = tt - Pb[i];
+    s += (double)d * (double)d;
+  }
+  block_atomic_add(s / (double)n, out + b);
+}
+
+// dA = (dP + coef[b] (P - T)) * P (1 - P):  the sigmoid backward of the TRP affinity with the relation-loss gradient folded in
+// (dP may be NULL = zero, coef NULL = no relation term)
+__global__ void __launch_bounds__(EW_THREADS) trp_dscore_kernel(const float* __restrict__ P, const float* __restrict__ dP,
+                                                                const float* __restrict__ T, const float* __restrict__ v,
+                                                                const float* __restrict__ coef, int S, int blocks_per_b,
+                                                                float* __restrict__ dA) {
+  const int b = blockIdx.x / blocks_per_b, part = blockIdx.x % blocks_per_b;
+  const long long n = (long long)S * S, base = (long long)b * n;
+  const float cb = coef ? coef[b] : 0.f;
+  for (long long i = (long long)part * blockDim.x + threadIdx.x; i < n; i += (long long)blocks_per_b * blockDim.x) {
+    const float pp = P[base + i];
+    float d = dP ? dP[base + i] : 0.f;
+    if (coef) {
+      const float tt = T ? T[base + i] : v[(long long)b * S + i / S] * v[(long long)b * S + i % S];
+      d += cb * (pp - tt);
+    }
+    dA[base + i] = d * pp * (1.f - pp);
+  }
+}
+
+// lib/core/function.py:261-267: v[b, y, x] = bilinear(align_corners=True, size H/2 x W/2) of max_k target[b, k, :, :]
+__global__ void __launch_bounds__(EW_THREADS) person_mask_kernel(const float* __restrict__ t, int K, int H, int W, long long n,
+                                                                 float* __restrict__ v) {
+  const int h = H / 2, w = W / 2;
+  GRID_STRIDE(i, n) {
+    const int x = (int)(i % w);
+    long long r = i / w;
+    const int y = (int)(r % h);
+    const long long b = r / h;
+    int y0, y1, x0, x1;
+    float ly, lx;
+    bil_src(y, H, h, y0, y1, ly);
+    bil_src(x, W, w, x0, x1, lx);
+    const float* tb = t + b * K * H * W;
+    float m00 = -INFINITY, m01 = -INFINITY, m10 = -INFINITY, m11 = -INFINITY;
+    for (int k = 0; k < K; ++k) {
+      const float* tk = tb + (long long)k * H * W;
+      m00 = fmaxf(m00, tk[y0 * W + x0]); m01 = fmaxf(m01, tk[y0 * W + x1]);
+      m10 = fmaxf(m10, tk[y1 * W + x0]); m11 = fmaxf(m11, tk[y1 * W + x1]);
+    }
+    const float hy = 1.f - ly, hx = 1.f - lx;
+    v[i] = hy * (hx * m00 + lx * m01) + ly * (hx * m10 + lx * m11);
+  }
+}
+
+__global__ void d2f_kernel(const double* __restrict__ in, float scale, int n, int accumulate, float* __restrict__ out) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) out[i] = (accumulate ? out[i] : 0.f) + (float)in[i] * scale;
+}
+
+// Adam (torch.optim.Adam, no weight decay / amsgrad): one launch over the flat parameter buffer
+__global__ void __launch_bounds__(EW_THREADS) adam_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m,
+                                                          float* __restrict__ v, long long n, float lr, float b1, float b2, float eps,
+                                                          float bc1, float bc2_sqrt, float gscale) {
+  const float step = lr / bc1;
+  GRID_STRIDE(i, n) {
+    const float gg = g[i] * gscale;
+    const float mm = b1 * m[i] + (1.f - b1) * gg;
+    const float vv = b2 * v[i] + (1.f - b2) * gg * gg;
+    m[i] = mm; v[i] = vv;
+    p[i] -= step * mm / (sqrtf(vv) / bc2_sqrt + eps);
+  }
+}
+
+}  // namespace
+
+#define ST ((cudaStream_t)stream)
+
+// ------------------------------------------------------------------------------------------------------------------
+// C ABI
+extern "C" int rsg_train_bn_fwd(void* stream, const float* x, long long M, int C, const float* gamma, const float* beta, float eps,
+                                float momentum, float* running_mean, float* running_var, int relu, float* y, float* save_mean,
+                                float* save_invstd, double* ws) {
+  RSG_REQUIRE(x && y && gamma && beta && save_mean && save_invstd && ws && M > 0 && C > 0, "bn_fwd: bad arguments");
+  RSG_CUDA(cudaMemsetAsync(ws, 0, 2 * (size_t)C * sizeof(double), ST));
+  int rpb, blocks;
+  chan_reduce_cfg(M, rpb, blocks);
+  chan_reduce_kernel<0><<<blocks, EW_THREADS, 0, ST>>>(x, nullptr, nullptr, nullptr, nullptr, 0, M, C, rpb, ws);
+  bn_finalize_kernel<<<ceil_div(C, 128), 128, 0, ST>>>(ws, M, C, eps, momentum, save_mean, save_invstd, running_mean, running_var);
+  const long long n = M * C;
+  bn_apply_kernel<<<ew_grid(n, 4), EW_THREADS, 0, ST>>>(x, save_mean, save_invstd, gamma, beta, relu, n, C, y);
+  RSG_LAUNCH_CHECK();
+  return RSG_OK;
+}
+
+extern "C" int rsg_train_bn_bwd(void* stream, const float* x, const float* y, const float* dy, long long M, int C, const float* gamma,
+                                const float* save_mean, const float* save_invstd, int relu, float* dx, float* dgamma, float* dbeta,
+                                double* ws) {
+  RSG_REQUIRE(x && dy && gamma && save_mean && save_invstd && ws && M > 0 && C > 0 && (!relu || y), "bn_bwd: bad arguments");
+  RSG_CUDA(cudaMemsetAsync(ws, 0, 2 * (size_t)C * sizeof(double), ST));
+  int rpb, blocks;
+  chan_reduce_cfg(M, rpb, blocks);
+  chan_reduce_kernel<1><<<blocks, EW_THREADS, 0, ST>>>(x, dy, y, save_mean, save_invstd, relu, M, C, rpb, ws);
+  const long long n = M * C;
+  bn_bwd_apply_kernel<<<ew_grid(n, 4), EW_THREADS, 0, ST>>>(x, dy, y, save_mean, save_invstd, gamma, ws, relu, n, C, M, dx, dgamma, dbeta);
+  RSG_LAUNCH_CHECK();
+  return RSG_OK;
+}
+
+extern "C" int rsg_train_colsum(void* stream, const float* x, long long M, int C, float* out, int accumulate, double* ws) {
+  RSG_REQUIRE(x && out && ws && M > 0 && C > 0, "colsum: bad arguments");
+  RSG_CUDA(cudaMemsetAsync(ws, 0, (size_t)C * sizeof(double), ST));
+  int rpb, blocks;
+  chan_reduce_cfg(M, rpb, blocks);
+  chan_reduce_kernel<2><<<blocks, EW_THREADS, 0, ST>>>(x, nullptr, nullptr, nullptr, nullptr, 0, M, C, rpb, ws);
+  d2f_kernel<<<ceil_div(C, 128), 128, 0, ST>>>(ws, 1.f, C, accumulate, out);
+  RSG_LAUNCH_CHECK();
+  return RSG_OK;
+}
+
+extern "C" int rsg_train_gn_fwd(void* stream, const float* x, int B, int S, int C, int G, const float* gamma, const float* beta, float eps,
+                                float* y, float* mean, float* rstd) {
+  RSG_REQUIRE(x && y && gamma && beta && mean && rstd && B > 0 && S > 0 && G > 0 && C % G == 0, "gn_fwd: bad arguments");
+  gn_fwd_kernel<<<B * G, EW_THREADS, 0, ST>>>(x, S, C, G, gamma, beta, eps, y, mean, rstd);
+  RSG_LAUNCH_CHECK();
+  return RSG_OK;
+}
+
+extern "C" int rsg_train_gn_bwd(void* stream, const float* x, const float* dy, int B, int S, int C, int G, const float* gamma,
+                                const float* mean, const float* rstd, float* dx, float* dgamma, float* dbeta) {
+  RSG_REQUIRE(x && dy && gamma && mean && rstd && B > 0 && S > 0 && G > 0 && C % G == 0 && C / G <= 64, "gn_bwd: bad arguments");
+  gn_bwd_kernel<<<B * G, EW_THREADS, 0, ST>>>(x, dy, S, C, G, gamma, mean, rstd, dx, dgamma, dbeta);
+  RSG_LAUNCH_CHECK();
+  return RSG_OK;
+}
+
+extern "C" int rsg_train_add(void* stream, int nin, const float* const* in, int relu, long long n, float* out) {
+  RSG_REQUIRE(nin >= 1 && nin <= 4 && in && out, "add: 1..4 inputs");
+  if (n == 0) return RSG_OK;
+  Ptr4 q;
+  for (int k = 0; k < 4; ++k) q.p[k] = k < nin ? in[k] : nullptr;
+  add_kernel<<<ew_grid(n, 4), EW_THREADS, 0, ST>>>(q, nin, relu, n, out);
+  RSG_LAUNCH_CHECK();
+  return RSG_OK;
+}
+
+extern "C" int rsg_train_ew(void* stream, int op, const float* a, const float* b, float slope, long long n, float* out) {
+  RSG_REQUIRE(a && out && op >= 0 && op <= 7, "ew: bad arguments");
+  RSG_REQUIRE(b || !(op == 0 || op == 2 || op == 4 || op == 5), "ew: op %d needs a second operand", op);
+  if (n == 0) return RSG_OK;
+  const int g = ew_grid(n, 4);
+  switch (op) {
+    case 0: ew_kernel<0><<<g, EW_THREADS, 0, ST>>>(a, b, slope, n, out); break;
+    case 1: ew_kernel<1><<<g, EW_THREADS, 0, ST>>>(a, b, slope, n, out); break;
+    case 2: ew_kernel<2><<<g, EW_THREADS, 0, ST>>>(a, b, slope, n, out); break;
+    case 3: ew_kernel<3><<<g, EW_THREADS, 0, ST>>>(a, b, slope, n, out); break;
+    case 4: ew_kernel<4><<<g, EW_THREADS, 0, ST>>>(a, b, slope, n, out); break;
+    case 5: ew_kernel<5><<<g, EW_THREADS, 0, ST>>>(a, b, slope, n, out); break;
+    case 6: ew_kernel<6><<<g, EW_THREADS, 0, ST>>>(a, b, slope, n, out); break;
+    default: ew_kernel<7><<<g, EW_THREADS, 0, ST>>>(a, b, slope, n, out); break;
+  }
+  RSG_LAUNCH_CHECK();
+  return RSG_OK;
+}
+
+extern "C" int rsg_train_copy2d(void* stream, const float* src, long long src_pitch, float* dst, long long dst_pitch, long long rows,
+                                int cols, int accumulate) {
+  RSG_REQUIRE(src && dst && rows >= 0 && cols > 0, "copy2d: bad arguments");
+  if (rows == 0) return RSG_OK;
+  copy2d_kernel<<<ew_grid(rows * cols, 4), EW_THREADS, 0, ST>>>(src, src_pitch, dst, dst_pitch, rows, cols, accumulate);
+  RSG_LAUNCH_CHECK();
+  return RSG_OK;
+}
+
+extern "C" int rsg_train_permute3(void* stream, const float* src, float* dst, int D0, int D1, int D2, long long s0, long long s1,
+                                  long long s2, int V1, int V2, int accumulate) {
+  RSG_REQUIRE(src && dst && D0 > 0 && D1 > 0 && D2 > 0, "permute3: bad arguments");
+  Perm q;
+  q.src = src; q.dst = dst; q.D0 = D0; q.D1 = D1; q.D2 = D2; q.V1 = V1; q.V2 = V2; q.s0 = s0; q.s1 = s1; q.s2 = s2;
+  q.accumulate = accumulate;
+  permute3_kernel<<<ew_grid((long long)D0 * D1 * D2, 4), EW_THREADS, 0, ST>>>(q);
+  RSG_LAUNCH_CHECK();
+  return RSG_OK;
+}
+
+/* table: device array of `count` records laid out as struct Perm (see rsg_b200.h: rsg_perm_entry) */
+extern "C" int rsg_train_permute3_batch(void* stream, const void* table, int count, int blocks_per_entry) {
+  RSG_REQUIRE(table && count >= 0 && blocks_per_entry > 0, "permute3_batch: bad arguments");
+  static_assert(sizeof(Perm) == sizeof(rsg_perm_entry), "rsg_perm_entry layout");
+  if (count == 0) return RSG_OK;
+  RSG_REQUIRE(count <= 65535, "permute3_batch: too many entries");
+  permute3_batch_kernel<<<dim3((unsigned)blocks_per_entry, (unsigned)count), EW_THREADS, 0, ST>>>(reinterpret_cast<const Perm*>(table));
+  RSG_LAUNCH_CHECK();
+  return RSG_OK;
+}
+
+extern "C" int rsg_train_resample(void* stream, int kind, const float* in, int N, int h, int w, int C, int f, float* out) {
+  // kind 0 nearest fwd (in [N,h,w,C] -> out [N,hf,wf,C]); 1 nearest bwd (in = dy [N,hf,wf,C] -> out = dx [N,h,w,C]);
+  // 2 bilinear x2 fwd; 3 bilinear x2 bwd (out zeroed here)
+  RSG_REQUIRE(in && out && N > 0 && h > 0 && w > 0 && C > 0 && kind >= 0 && kind <= 3, "resample: bad arguments");
+  RSG_REQUIRE(kind >= 2 || f >= 1, "resample: factor");
+  const long long small = (long long)N * h * w * C;
+  if (kind == 0) { const long long n = small * f * f; nearest_fwd_kernel<<<ew_grid(n, 4), EW_THREADS, 0, ST>>>(in, h, w, C, f, n, out); }
+  else if (kind == 1) nearest_bwd_kernel<<<ew_grid(small, 2), EW_THREADS, 0, ST>>>(in, h, w, C, f, small, out);
+  else if (kind == 2) { const long long n = small * 4; bilinear_fwd_kernel<<<ew_grid(n, 4), EW_THREADS, 0, ST>>>(in, h, w, C, n, out); }
+  else {
+    RSG_CUDA(cudaMemsetAsync(out, 0, (size_t)small * sizeof(float), ST));
+    const long long n = small * 4;
+    bilinear_bwd_kernel<<<ew_grid(n, 4), EW_THREADS, 0, ST>>>(in, h, w, C, n, out);
+  }
+  RSG_LAUNCH_CHECK();
+  return RSG_OK;
+}
+
+extern "C" int rsg_train_maxpool(void* stream, int backward, const float* in, unsigned char* idx, int N, int H, int W, int C, float* out) {
+  RSG_REQUIRE(in && idx && out && N > 0 && H >= 2 && W >= 2 && C > 0, "maxpool: bad arguments");
+  if (!backward) { const long long n = (long long)N * (H / 2) * (W / 2) * C; maxpool_fwd_kernel<<<ew_grid(n, 2), EW_THREADS, 0, ST>>>(in, H, W, C, n, out, idx); }
+  else { const long long n = (long long)N * H * W * C; maxpool_bwd_kernel<<<ew_grid(n, 4), EW_THREADS, 0, ST>>>(in, idx, H, W, C, n, out); }
+  RSG_LAUNCH_CHECK();
+  return RSG_OK;
+}
+
+extern "C" int rsg_train_mse_joints(void* stream, const float* pred, const float* target, const float* tw, int B, int K, int HW, float up,
+                                    double* loss_acc, float* grad) {
+  RSG_REQUIRE(pred && target && loss_acc && B > 0 && K > 0 && HW > 0, "mse_joints: bad arguments");
+  const long long n = (long long)B * K * HW;
+  mse_joints_kernel<<<ew_grid(n, 8), EW_THREADS, 0, ST>>>(pred, target, tw, HW, n, 0.5 / (double)n, up, loss_acc, grad);
+  RSG_LAUNCH_CHECK();
+  return RSG_OK;
+}
+
+extern "C" int rsg_train_bce(void* stream, const float* p, const float* t, long long n, double weight, float up, double* loss_acc,
+                             float* grad) {
+  RSG_REQUIRE(p && t && loss_acc && n > 0, "bce: bad arguments");
+  bce_kernel<<<ew_grid(n, 8), EW_THREADS, 0, ST>>>(p, t, n, weight / (double)n, up, loss_acc, grad);
+  RSG_LAUNCH_CHECK();
+  return RSG_OK;
+}
+
+extern "C" int rsg_train_relation_mse(void* stream, const float* P, const float* T, const float* v, int B, int S, double* out_acc) {
+  RSG_REQUIRE(P && (T || v) && out_acc && B > 0 && S > 0, "relation_mse: bad arguments");
+  int bpb = ceil_div(8ll * rsg_num_sms(), B);
+  const long long per = ((long long)S * S + EW_THREADS - 1) / EW_THREADS;
+  if (bpb > per) bpb = (int)per;
+  if (bpb < 1) bpb = 1;
+  relation_mse_kernel<<<B * bpb, EW_THREADS, 0, ST>>>(P, T, v, S, bpb, out_acc);
+  RSG_LAUNCH_CHECK();
+  return RSG_OK;
+}
+
+extern "C" int rsg_train_trp_dscore(void* stream, const float* P, const float* dP, const float* T, const float* v, const float* coef,
+                                    int B, int S, float* dA) {
+  RSG_REQUIRE(P && dA && B > 0 && S > 0 && (!coef || T || v), "trp_dscore: bad arguments");
+  int bpb = ceil_div(16ll * rsg_num_sms(), B);
+  const long long per = ((long long)S * S + EW_THREADS - 1) / EW_THREADS;
+  if (bpb > per) bpb = (int)per;
+  if (bpb < 1) bpb = 1;
+  trp_dscore_kernel<<<B * bpb, EW_THREADS, 0, ST>>>(P, dP, T, v, coef, S, bpb, dA);
+  RSG_LAUNCH_CHECK();
+  return RSG_OK;
+}
+
+extern "C" int rsg_train_person_mask(void* stream, const float* target, int B, int K, int H, int W, float* v) {
+  RSG_REQUIRE(target && v && B > 0 && K > 0 && H >= 2 && W >= 2, "person_mask: bad arguments");
+  const long long n = (long long)B * (H / 2) * (W / 2);
+  person_mask_kernel<<<ew_grid(n), EW_THREADS, 0, ST>>>(target, K, H, W, n, v);
+  RSG_LAUNCH_CHECK();
+  return RSG_OK;
+}
+
+extern "C" int rsg_train_zero(void* stream, void* p, size_t bytes) {
+  RSG_REQUIRE(p || bytes == 0, "zero: null pointer");
+  if (bytes) RSG_CUDA(cudaMemsetAsync(p, 0, bytes, ST));
+  return RSG_OK;
+}
+
+extern "C" int rsg_train_d2f(void* stream, const double* in, float scale, int n, int accumulate, float* out) {
+  RSG_REQUIRE(in && out && n > 0, "d2f: bad arguments");
+  d2f_kernel<<<ceil_div(n, 128), 128, 0, ST>>>(in, scale, n, accumulate, out);
+  RSG_LAUNCH_CHECK();
+  return RSG_OK;
+}
+
+extern "C" int rsg_train_adam(void* stream, float* p, const float* g, float* m, float* v, long long n, float lr, float beta1, float beta2,
+                              float eps, int step, float grad_scale) {
+  RSG_REQUIRE(p && g && m && v && n >= 0 && step >= 1, "adam: bad arguments");
+  if (n == 0) return RSG_OK;
+  const double bc1 = 1.0 - pow((double)beta1, (double)step), bc2 = 1.0 - pow((double)beta2, (double)step);
+  adam_kernel<<<ew_grid(n, 4), EW_THREADS, 0, ST>>>(p, g, m, v, n, lr, beta1, beta2, eps, (float)bc1, (float)sqrt(bc2), grad_scale);
+  RSG_LAUNCH_CHECK();
+  return RSG_OK;
+}

@@ -41,6 +41,7 @@ class EngineOwner(nn.Module):
 
     def _apply(self, fn, *a, **kw):
         self._drop_engines()
+        self.__dict__.pop('_rsg_train_store', None)      # .cuda() / .to() re-allocate the parameters: the flat views are stale
         return super()._apply(fn, *a, **kw)
 
     def load_state_dict(self, *a, **kw):

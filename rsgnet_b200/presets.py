@@ -65,6 +65,10 @@ PRESETS = {
                  modules=(1, 2, 2), blocks=2),
     'tiny_cp_sub': dict(channels=[16, 32, 64, 128], image_wh=(64, 96), num_joints=14,
                         num_limbs=14, modules=(1, 1, 2), blocks=2, sub_sample=True),
+    # CrowdPose joints without TRP sub-sampling (the reference's training loop builds its relation target at the
+    # feature-map size, lib/core/function.py:256-269, so RELATION_SUB_SAMPLE configs cannot be trained by the reference)
+    'tiny_cp': dict(channels=[16, 32, 64, 128], image_wh=(64, 96), num_joints=14, num_limbs=14,
+                    modules=(1, 1, 2), blocks=2),
     'tiny_hrnet': dict(name='pose_hrnet', channels=[16, 32, 64, 128], image_wh=(64, 96),
                        num_joints=17, modules=(1, 2, 2), blocks=2),
 }

@@ -146,3 +146,30 @@ def images(n, seed=7, hw_range=((120, 480), (160, 640))):
         s = rs.uniform(0.15, 3.5)
         scales.append([s, s * 1.25])
     return imgs, np.asarray(centers, np.float32), np.asarray(scales, np.float32)
+
+
+def train_batch(n, image_wh, heat_wh, num_joints, num_limbs, seed=0):
+    """One synthetic training batch in the layout of the reference's loader (lib/core/function.py:258: input, target,
+    target_weight, all_ins_target, all_ins_target_weight, target_limbs): Gaussian joint maps (sigma 2) of a target person,
+    the same plus a second person for the 'all instances' maps, 0/1 joint weights, smooth limb maps in (0, 1)."""
+    rs = np.random.RandomState(seed + 77)
+    w, h = heat_wh
+    xs = np.arange(w, dtype=np.float32)[None, None, None, :]
+    ys = np.arange(h, dtype=np.float32)[None, None, :, None]
+
+    def bumps(k):
+        cx = rs.uniform(2, w - 2, (n, k, 1, 1)).astype(np.float32)
+        cy = rs.uniform(2, h - 2, (n, k, 1, 1)).astype(np.float32)
+        return np.exp(-((xs - cx) ** 2 + (ys - cy) ** 2) / np.float32(8.0)).astype(np.float32)
+
+    target = bumps(num_joints)
+    tw = (rs.uniform(size=(n, num_joints, 1)) > 0.2).astype(np.float32)
+    target = target * tw[..., None]
+    other = bumps(num_joints)
+    all_target = np.maximum(target, other).astype(np.float32)
+    all_tw = np.maximum(tw, (rs.uniform(size=(n, num_joints, 1)) > 0.3).astype(np.float32))
+    limbs = np.clip(0.5 * bumps(num_limbs) + 0.5 * bumps(num_limbs), 0.0, 1.0).astype(np.float32)
+    x = rs.standard_normal((n, 3, image_wh[1], image_wh[0])).astype(np.float32)
+    c = np.ascontiguousarray
+    return dict(input=c(x), target=c(target), target_weight=c(tw), all_ins_target=c(all_target),
+                all_ins_target_weight=c(all_tw), target_limbs=c(limbs))

@@ -1,0 +1,472 @@
+"""A minimal reverse-mode tape over the library's training kernels (include/rsg_b200.h, 'Training step').
+
+The reference gets its backward pass from torch autograd over cuDNN / cuBLAS (lib/core/function.py:240-363 calls
+``loss.backward()``).  Here every operation of the train-mode forward (lib/models/pose_rsgnet.py:955-1021) is one or a few
+calls into librsg_b200.so, and records a closure that issues the matching backward kernels.  torch supplies device memory
+(``torch.empty``) and the current stream only; no torch kernel computes anything on this path.
+
+Activations are fp32 NHWC tensors ``[N, H, W, C]`` (or plain matrices ``[M, C]``).
+"""
+import ctypes as C
+
+import torch
+
+from .. import _lib
+
+
+class T:
+    """A tape value: ``v`` the tensor, ``g`` its gradient (None until something flows back)."""
+    __slots__ = ('v', 'g', 'req', 'own')
+
+    def __init__(self, v, req=True, g=None):
+        self.v = v
+        self.g = g
+        self.req = req
+        self.own = g is not None      # whether g may be updated in place (False when the tensor is shared with another node)
+
+    @property
+    def shape(self):
+        return tuple(self.v.shape)
+
+
+def _p(t):
+    return C.c_void_p(t.data_ptr()) if t is not None else None
+
+
+class Tape:
+    def __init__(self, device, precise=False):
+        self.device = device
+        self.lib = _lib.lib()
+        self.ops = []
+        self.precise = 1 if precise else 0
+        self.launches = 0
+        self._ws = torch.empty(4096, dtype=torch.float64, device=device)      # reduction scratch (2 * C doubles)
+
+    # ------------------------------------------------------------------ plumbing
+    @property
+    def st(self):
+        return _lib.stream_ptr(self.device)
+
+    def new(self, *shape):
+        return torch.empty(shape, dtype=torch.float32, device=self.device)
+
+    def call(self, name, *args, n=1):
+        _lib.check(getattr(self.lib, name)(self.st, *args))
+        self.launches += n
+
+    def record(self, fn):
+        self.ops.append(fn)
+
+    def backward(self):
+        while self.ops:
+            self.ops.pop()()
+
+    def acc(self, t, g, shared=False):
+        """Add gradient tensor g into node t.  `shared`: g is also handed to another node (must not be modified)."""
+        if not t.req:
+            return
+        if t.g is None:
+            t.g = g
+            t.own = not shared
+        elif t.own:
+            self.call('rsg_train_ew', 6, _p(g), None, 0.0, g.numel(), _p(t.g))
+        else:
+            out = self.new(*t.g.shape)
+            ptrs = (C.c_void_p * 2)(t.g.data_ptr(), g.data_ptr())
+            self.call('rsg_train_add', 2, ptrs, 0, g.numel(), _p(out))
+            t.g = out
+            t.own = True
+
+    def grad_buf(self, t):
+        """The gradient buffer of node t for kernels that ACCUMULATE into it (wgrad atomics): parameters own a persistent
+        one; computed weights (the type vectors, the KTMachine's limb filters) get a zeroed buffer on first use."""
+        if t.g is None:
+            t.g = self.new(*t.v.shape)
+            self.call('rsg_train_zero', _p(t.g), C.c_size_t(4 * t.g.numel()))
+            t.own = True
+        elif not t.own:
+            g = self.new(*t.g.shape)
+            self.call('rsg_train_copy2d', _p(t.g), 0, _p(g), 0, 1, t.g.numel(), 0)
+            t.g, t.own = g, True
+        return t.g
+
+    def ws(self, n):
+        if self._ws.numel() < n:
+            self._ws = torch.empty(n, dtype=torch.float64, device=self.device)
+        return self._ws
+
+    # ------------------------------------------------------------------ matrix ops
+    def _gemm(self, A, B, Cm, bias, M, Nc, Ca, lda, ldb, ldc, mode=0, transA=0, transB=0, beta=0, geom=None, batch=1,
+              sA=0, sB=0, sC=0):
+        g = (C.c_int * 8)(*geom) if geom is not None else None
+        self.call('rsg_train_gemm', _p(A), _p(B), _p(Cm), _p(bias), M, Nc, Ca, lda, ldb, ldc, batch, sA, sB, sC, mode,
+                  transA, transB, beta, g, self.precise)
+
+    def _wgrad(self, X, dY, dW, M, Ca, Nc, mode=0, geom=None):
+        g = (C.c_int * 8)(*geom) if geom is not None else None
+        self.call('rsg_train_wgrad', _p(X), _p(dY), _p(dW), M, Ca, Nc, Ca, Nc, mode, g, self.precise)
+
+    def conv(self, x, wp, k, stride=1, pad=None, bias=None):
+        """x [N,H,W,Ci], wp packed [k*k, Ci, Co] -> [N,Ho,Wo,Co] (nn.Conv2d, pose_rsgnet.py:19-22 conv3x3 and friends)."""
+        if pad is None:
+            pad = k // 2
+        N, H, W, Ci = x.shape
+        taps, Cip, Co = wp.shape
+        assert taps == k * k and Cip == Ci, (wp.shape, x.shape, k)
+        Ho, Wo = (H + 2 * pad - k) // stride + 1, (W + 2 * pad - k) // stride + 1
+        y = self.new(N, Ho, Wo, Co)
+        M = N * Ho * Wo
+        fg = (H, W, Ho, Wo, k, k, stride, pad)
+        self._gemm(x.v, wp.v, y, bias.v if bias is not None else None, M, Co, Ci, Ci, Co, Co, mode=1, geom=fg)
+        out = T(y)
+
+        def bwd():
+            dy = out.g
+            if dy is None:
+                return
+            if wp.req:
+                self._wgrad(x.v, dy, self.grad_buf(wp), M, Ci, Co, mode=1, geom=fg)
+            if bias is not None and bias.req:
+                self.call('rsg_train_colsum', _p(dy), M, Co, _p(self.grad_buf(bias)), 1, _p(self.ws(Co)), n=2)
+            if x.req:
+                dx = self.new(N, H, W, Ci)
+                self._gemm(dy, wp.v, dx, None, N * H * W, Ci, Co, Co, Co, Ci, mode=2, transB=1,
+                           geom=(Ho, Wo, H, W, k, k, stride, pad))
+                self.acc(x, dx)
+        self.record(bwd)
+        return out
+
+    def conv_transpose(self, x, wp, k, stride, pad, opad=0):
+        """x [N,h,w,Ci], wp packed [k*k, Ci, Co] from the ConvTranspose2d weight [Ci,Co,k,k] -> [N,H,W,Co]."""
+        N, h, w, Ci = x.shape
+        taps, Cip, Co = wp.shape
+        assert taps == k * k and Cip == Ci
+        H, W = (h - 1) * stride - 2 * pad + k + opad, (w - 1) * stride - 2 * pad + k + opad
+        y = self.new(N, H, W, Co)
+        M = N * H * W
+        tg = (h, w, H, W, k, k, stride, pad)
+        self._gemm(x.v, wp.v, y, None, M, Co, Ci, Ci, Co, Co, mode=2, geom=tg)
+        out = T(y)
+
+        def bwd():
+            dy = out.g
+            if dy is None:
+                return
+            if wp.req:
+                self._wgrad(x.v, dy, self.grad_buf(wp), M, Ci, Co, mode=2, geom=tg)
+            if x.req:
+                dx = self.new(N, h, w, Ci)
+                self._gemm(dy, wp.v, dx, None, N * h * w, Ci, Co, Co, Co, Ci, mode=1, transB=1,
+                           geom=(H, W, h, w, k, k, stride, pad))
+                self.acc(x, dx)
+        self.record(bwd)
+        return out
+
+    def linear(self, x, w, bias=None):
+        """x [..., I], w raw [O, I] (nn.Linear weight or a 1x1 conv's OIHW weight) -> [..., O]."""
+        I = x.shape[-1]
+        O = w.v.shape[0]
+        assert w.v.numel() == O * I, (w.v.shape, x.shape)
+        M = x.v.numel() // I
+        y = self.new(*x.shape[:-1], O)
+        self._gemm(x.v, w.v, y, bias.v if bias is not None else None, M, O, I, I, I, O, transB=1)
+        out = T(y)
+
+        def bwd():
+            dy = out.g
+            if dy is None:
+                return
+            if w.req:
+                self._wgrad(dy, x.v, self.grad_buf(w), M, O, I)
+            if bias is not None and bias.req:
+                self.call('rsg_train_colsum', _p(dy), M, O, _p(self.grad_buf(bias)), 1, _p(self.ws(O)), n=2)
+            if x.req:
+                dx = self.new(*x.shape)
+                self._gemm(dy, w.v, dx, None, M, I, O, O, I, I)
+                self.acc(x, dx)
+        self.record(bwd)
+        return out
+
+    def matmul(self, a, b):
+        """a [M, K] @ b [K, N] with gradients to both (KTMachine: matrix_relation @ final_layer.weight)."""
+        M, K = a.shape
+        N = b.v.numel() // K
+        y = self.new(M, N)
+        self._gemm(a.v, b.v, y, None, M, N, K, K, N, N)
+        out = T(y)
+
+        def bwd():
+            dy = out.g
+            if dy is None:
+                return
+            if b.req:
+                self._wgrad(a.v, dy, self.grad_buf(b), M, K, N)
+            if a.req:
+                da = self.new(M, K)
+                self._gemm(dy, b.v, da, None, M, K, N, N, N, K, transB=1)
+                self.acc(a, da)
+        self.record(bwd)
+        return out
+
+    # ------------------------------------------------------------------ normalisation
+    def batchnorm(self, x, gamma, beta, running_mean, running_var, relu=False, eps=1e-5, momentum=0.1):
+        Cn = x.shape[-1]
+        M = x.v.numel() // Cn
+        y = self.new(*x.shape)
+        mean, invstd = self.new(Cn), self.new(Cn)
+        self.call('rsg_train_bn_fwd', _p(x.v), M, Cn, _p(gamma.v), _p(beta.v), eps, momentum, _p(running_mean),
+                  _p(running_var), 1 if relu else 0, _p(y), _p(mean), _p(invstd), _p(self.ws(2 * Cn)), n=4)
+        out = T(y)
+
+        def bwd():
+            dy = out.g
+            if dy is None:
+                return
+            dx = self.new(*x.shape) if x.req else None
+            self.call('rsg_train_bn_bwd', _p(x.v), _p(y), _p(dy), M, Cn, _p(gamma.v), _p(mean), _p(invstd),
+                      1 if relu else 0, _p(dx), _p(gamma.g) if gamma.req else None, _p(beta.g) if beta.req else None,
+                      _p(self.ws(2 * Cn)), n=3)
+            if dx is not None:
+                self.acc(x, dx)
+        self.record(bwd)
+        return out
+
+    def groupnorm(self, x, gamma, beta, groups=8, eps=1e-5):
+        B = x.shape[0]
+        Cn = x.shape[-1]
+        S = x.v.numel() // (B * Cn)
+        y = self.new(*x.shape)
+        mean, rstd = self.new(B * groups), self.new(B * groups)
+        self.call('rsg_train_gn_fwd', _p(x.v), B, S, Cn, groups, _p(gamma.v), _p(beta.v), eps, _p(y), _p(mean), _p(rstd))
+        out = T(y)
+
+        def bwd():
+            dy = out.g
+            if dy is None:
+                return
+            dx = self.new(*x.shape) if x.req else None
+            self.call('rsg_train_gn_bwd', _p(x.v), _p(dy), B, S, Cn, groups, _p(gamma.v), _p(mean), _p(rstd), _p(dx),
+                      _p(gamma.g) if gamma.req else None, _p(beta.g) if beta.req else None)
+            if dx is not None:
+                self.acc(x, dx)
+        self.record(bwd)
+        return out
+
+    # ------------------------------------------------------------------ element-wise
+    def add(self, xs, relu=False):
+        y = self.new(*xs[0].shape)
+        ptrs = (C.c_void_p * len(xs))(*[x.v.data_ptr() for x in xs])
+        self.call('rsg_train_add', len(xs), ptrs, 1 if relu else 0, y.numel(), _p(y))
+        out = T(y)
+
+        def bwd():
+            dy = out.g
+            if dy is None:
+                return
+            if relu:
+                g = self.new(*y.shape)
+                self.call('rsg_train_ew', 0, _p(dy), _p(y), 0.0, y.numel(), _p(g))
+            else:
+                g = dy
+            for x in xs:
+                self.acc(x, g, shared=True)
+        self.record(bwd)
+        return out
+
+    def _unary(self, x, fop, bop, slope=0.0, save_input=False):
+        y = self.new(*x.shape)
+        self.call('rsg_train_ew', fop, _p(x.v), None, slope, y.numel(), _p(y))
+        out = T(y)
+
+        def bwd():
+            dy = out.g
+            if dy is None or not x.req:
+                return
+            dx = self.new(*x.shape)
+            self.call('rsg_train_ew', bop, _p(dy), _p(x.v if save_input else y), slope, y.numel(), _p(dx))
+            self.acc(x, dx)
+        self.record(bwd)
+        return out
+
+    def sigmoid(self, x):
+        return self._unary(x, 1, 2)
+
+    def leaky_relu(self, x, slope):
+        return self._unary(x, 3, 4, slope, save_input=True)
+
+    def mul_const(self, x, c):
+        """x * c with c a constant tensor of the same shape (KTMachine's real_matrix_limb mask)."""
+        y = self.new(*x.shape)
+        self.call('rsg_train_ew', 5, _p(x.v), _p(c), 0.0, y.numel(), _p(y))
+        out = T(y)
+
+        def bwd():
+            if out.g is None or not x.req:
+                return
+            dx = self.new(*x.shape)
+            self.call('rsg_train_ew', 5, _p(out.g), _p(c), 0.0, y.numel(), _p(dx))
+            self.acc(x, dx)
+        self.record(bwd)
+        return out
+
+    def cat(self, xs):
+        """Concatenate along the channel (last) dimension."""
+        lead = xs[0].shape[:-1]
+        M = xs[0].v.numel() // xs[0].shape[-1]
+        Ct = sum(x.shape[-1] for x in xs)
+        y = self.new(*lead, Ct)
+        off = 0
+        offs = []
+        for x in xs:
+            c = x.shape[-1]
+            self.call('rsg_train_copy2d', _p(x.v), c, C.c_void_p(y.data_ptr() + 4 * off), Ct, M, c, 0)
+            offs.append(off)
+            off += c
+        out = T(y)
+
+        def bwd():
+            dy = out.g
+            if dy is None:
+                return
+            for x, o in zip(xs, offs):
+                if not x.req:
+                    continue
+                c = x.shape[-1]
+                dx = self.new(*x.shape)
+                self.call('rsg_train_copy2d', C.c_void_p(dy.data_ptr() + 4 * o), Ct, _p(dx), c, M, c, 0)
+                self.acc(x, dx)
+        self.record(bwd)
+        return out
+
+    def repeat_batch(self, x, n):
+        """x [1, ...] -> [n, ...] (pose_rsgnet.py:980 loc_features.repeat)."""
+        cols = x.v.numel()
+        y = self.new(n, *x.shape[1:])
+        self.call('rsg_train_copy2d', _p(x.v), 0, _p(y), cols, n, cols, 0)
+        out = T(y)
+
+        def bwd():
+            if out.g is None or not x.req:
+                return
+            dx = self.new(*x.shape)
+            self.call('rsg_train_colsum', _p(out.g), n, cols, _p(dx), 0, _p(self.ws(cols)), n=3)
+            self.acc(x, dx)
+        self.record(bwd)
+        return out
+
+    def _resample(self, x, kf, kb, f):
+        N, h, w, Cn = x.shape
+        y = self.new(N, h * f, w * f, Cn)
+        self.call('rsg_train_resample', kf, _p(x.v), N, h, w, Cn, f, _p(y))
+        out = T(y)
+
+        def bwd():
+            if out.g is None or not x.req:
+                return
+            dx = self.new(*x.shape)
+            self.call('rsg_train_resample', kb, _p(out.g), N, h, w, Cn, f, _p(dx), n=1 if kb == 1 else 2)
+            self.acc(x, dx)
+        self.record(bwd)
+        return out
+
+    def upsample_nearest(self, x, f):
+        return self._resample(x, 0, 1, f)
+
+    def bilinear2x(self, x):
+        return self._resample(x, 2, 3, 2)
+
+    def maxpool2(self, x):
+        N, H, W, Cn = x.shape
+        y = self.new(N, H // 2, W // 2, Cn)
+        idx = torch.empty(y.shape, dtype=torch.uint8, device=self.device)
+        self.call('rsg_train_maxpool', 0, _p(x.v), _p(idx), N, H, W, Cn, _p(y))
+        out = T(y)
+
+        def bwd():
+            if out.g is None or not x.req:
+                return
+            dx = self.new(*x.shape)
+            self.call('rsg_train_maxpool', 1, _p(out.g), _p(idx), N, H, W, Cn, _p(dx))
+            self.acc(x, dx)
+        self.record(bwd)
+        return out
+
+    # ------------------------------------------------------------------ layout
+    def view(self, x, *shape):
+        """Reshape without copying; the gradient of the view flows back to x as a view of the same storage."""
+        out = T(x.v.view(*shape), req=x.req)
+
+        def bwd():
+            if out.g is not None and x.req:
+                self.acc(x, out.g.view(*x.shape), shared=not out.own)
+        self.record(bwd)
+        return out
+
+    def from_nchw(self, x, cpad=None):
+        """torch NCHW tensor -> NHWC node (channels zero-padded to cpad); no gradient flows to the input."""
+        N, Cn, H, W = x.shape
+        cp = cpad or Cn
+        y = self.new(N, H, W, cp)
+        self.call('rsg_train_permute3', _p(x), _p(y), N, H * W, cp, Cn * H * W, 1, H * W, H * W, Cn, 0)
+        return T(y, req=False)
+
+    def to_nchw(self, x):
+        """NHWC node -> NCHW node (the tensors the reference's caller sees)."""
+        N, H, W, Cn = x.shape
+        y = self.new(N, Cn, H, W)
+        self.call('rsg_train_permute3', _p(x.v), _p(y), N, Cn, H * W, H * W * Cn, 1, Cn, Cn, H * W, 0)
+        out = T(y)
+
+        def bwd():
+            if out.g is None or not x.req:
+                return
+            dx = self.new(*x.shape)
+            self.call('rsg_train_permute3', _p(out.g), _p(dx), N, H * W, Cn, Cn * H * W, 1, H * W, H * W, Cn, 0)
+            self.acc(x, dx)
+        self.record(bwd)
+        return out
+
+    # ------------------------------------------------------------------ TRP (association.py:280-301)
+    def trp_attention(self, x, g):
+        """x [B,S,C] (theta = phi = x), g [B,S,Cg] -> (y [B,S,Cg] = sigmoid(x x^T) g, P [B,S,S] as a node).
+        The gradient of a loss on P (the relation MSE) is added by the caller through ``P.g`` or ``rel_hook``."""
+        B, S, Cx = x.shape
+        Cg = g.shape[-1]
+        P = self.new(B, S, S)
+        self._gemm(x.v, x.v, P, None, S, S, Cx, Cx, Cx, S, transB=1, batch=B, sA=S * Cx, sB=S * Cx, sC=S * S)
+        self.call('rsg_train_ew', 1, _p(P), None, 0.0, P.numel(), _p(P))
+        y = self.new(B, S, Cg)
+        self._gemm(P, g.v, y, None, S, Cg, S, S, Cg, Cg, batch=B, sA=S * S, sB=S * Cg, sC=S * Cg)
+        out, Pn = T(y), T(P)
+        Pn.g = None
+        hook = {}
+
+        def bwd():
+            dy = out.g
+            dP = None
+            if dy is not None:
+                if g.req:
+                    dg = self.new(B, S, Cg)          # P is symmetric: P^T dy = P dy
+                    self._gemm(P, dy, dg, None, S, Cg, S, S, Cg, Cg, batch=B, sA=S * S, sB=S * Cg, sC=S * Cg)
+                    self.acc(g, dg)
+                dP = self.new(B, S, S)
+                self._gemm(dy, g.v, dP, None, S, S, Cg, Cg, Cg, S, transB=1, batch=B, sA=S * Cg, sB=S * Cg, sC=S * S)
+            if Pn.g is not None:                      # a caller differentiated through the returned scores directly
+                if dP is None:
+                    dP = Pn.g
+                else:
+                    self.call('rsg_train_ew', 6, _p(Pn.g), None, 0.0, dP.numel(), _p(dP))
+            rel = hook.get('rel')                     # (T_full | None, v | None, coef [B])
+            if dP is None and rel is None:
+                return
+            if not x.req:
+                return
+            dA = dP if dP is not None else self.new(B, S, S)
+            self.call('rsg_train_trp_dscore', _p(P), _p(dP), _p(rel[0]) if rel else None, _p(rel[1]) if rel else None,
+                      _p(rel[2]) if rel else None, B, S, _p(dA))
+            dx = self.new(B, S, Cx)                   # A = x x^T: dx = dA x + dA^T x
+            self._gemm(dA, x.v, dx, None, S, Cx, S, S, Cx, Cx, batch=B, sA=S * S, sB=S * Cx, sC=S * Cx)
+            self._gemm(dA, x.v, dx, None, S, Cx, S, S, Cx, Cx, transA=1, beta=1, batch=B, sA=S * S, sB=S * Cx, sC=S * Cx)
+            self.acc(x, dx)
+        self.record(bwd)
+        return out, Pn, hook
