@@ -5,6 +5,8 @@ transitions :817-856, _forward_visual_encoder :921-953, RSGNet.forward :955-1021
 lib/models/association.py:280-301 (SpatialRelationHead.forward); vanilla HRNet: lib/models/pose_hrnet.py:428-463.
 The parameter containers are the ones of ``rsgnet_b200.models._params`` (reference names and shapes).
 """
+import torch.nn as nn
+
 from ..config import KIND_RSGNET
 
 
@@ -28,7 +30,7 @@ class Net:
     def cbr(self, x, seq, relu):
         """Sequential(conv, BN[, ReLU]) as built by _params.conv_bn."""
         conv = seq[0]
-        if hasattr(conv, 'output_padding'):
+        if isinstance(conv, nn.ConvTranspose2d):
             y = self.t.conv_transpose(x, self.s.packed(conv), conv.kernel_size[0], conv.stride[0], conv.padding[0],
                                       conv.output_padding[0])
         else:
@@ -148,20 +150,24 @@ class Net:
         return self.t.view(y, B, h, w, tf.shape[-1])
 
     def trp(self, x):
+        """association.py:280-301.  The relation features are the GroupNorm of W (P g): every row of P g is close to
+        (S/2) mean(g) -- a mean hundreds of times its spread -- so product rounding in P g, in the 1x1 W conv or in g
+        becomes O(1) noise behind the GroupNorm.  These few small products always use the 3xTF32 (fp32-class) mode."""
         t, rh = self.t, self.m.relation_head
         spec = self.m.spec
         if spec.relation_sub_sample:
             x = t.maxpool2(x)
         B, h, w, c = x.shape
-        g = self.conv(x, rh.g)
-        y, P, hook = t.trp_attention(t.view(x, B, h * w, c), t.view(g, B, h * w, c))
-        y = t.view(y, B, h, w, c)
-        if spec.relation_sub_sample:
-            y = self.cbr(y, rh.W[0], True)
-            tail = rh.W[1]
-        else:
-            tail = rh.W
-        z = self.conv(y, tail[0])
+        with t.precision(True):
+            g = self.conv(x, rh.g)
+            y, P, hook = t.trp_attention(t.view(x, B, h * w, c), t.view(g, B, h * w, c))
+            y = t.view(y, B, h, w, c)
+            if spec.relation_sub_sample:
+                y = self.cbr(y, rh.W[0], True)
+                tail = rh.W[1]
+            else:
+                tail = rh.W
+            z = self.conv(y, tail[0])
         gn = tail[1]
         z = t.groupnorm(z, self.s.raw(gn.weight), self.s.raw(gn.bias), gn.num_groups, gn.eps)
         return z, P, hook

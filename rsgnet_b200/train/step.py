@@ -189,25 +189,30 @@ class TrainStep:
             B = int(x.shape[0])
             losses = Losses(tape, B if mod.spec.kind == KIND_RSGNET else 0)
             cont = lambda t: t.to(dev, torch.float32).contiguous()
+            keep = []            # device copies of the targets must outlive the asynchronous launches that read them
             if mod.spec.kind != KIND_RSGNET:
                 out = net.hrnet(x)
                 K, HW = out.shape[1], out.shape[2] * out.shape[3]
                 out.g = tape.new(*out.shape)
-                tape.call('rsg_train_mse_joints', _p(out.v), _p(cont(target)), _p(cont(target_weight)), B, K, HW, 1.0,
+                target, target_weight = cont(target), cont(target_weight)
+                keep += [target, target_weight]
+                tape.call('rsg_train_mse_joints', _p(out.v), _p(target), _p(target_weight), B, K, HW, 1.0,
                           losses.slot(1), _p(out.g))
                 outputs = (out.v,)
             else:
                 multi, kpt, limbs, P, hook = net.rsgnet(x)
                 K, HW = kpt.shape[1], kpt.shape[2] * kpt.shape[3]
-                target = cont(target)
+                target, target_weight = cont(target), cont(target_weight)
+                all_target, all_target_weight, target_limbs = cont(all_target), cont(all_target_weight), cont(target_limbs)
+                keep += [target, target_weight, all_target, all_target_weight, target_limbs]
                 kpt.g = tape.new(*kpt.shape)
-                tape.call('rsg_train_mse_joints', _p(kpt.v), _p(target), _p(cont(target_weight)), B, K, HW, 1.0,
+                tape.call('rsg_train_mse_joints', _p(kpt.v), _p(target), _p(target_weight), B, K, HW, 1.0,
                           losses.slot(1), _p(kpt.g))
                 multi.g = tape.new(*multi.shape)
-                tape.call('rsg_train_mse_joints', _p(multi.v), _p(cont(all_target)), _p(cont(all_target_weight)), B, K, HW,
+                tape.call('rsg_train_mse_joints', _p(multi.v), _p(all_target), _p(all_target_weight), B, K, HW,
                           1.0, losses.slot(0), _p(multi.g))
                 limbs.g = tape.new(*limbs.shape)
-                tape.call('rsg_train_bce', _p(limbs.v), _p(cont(target_limbs)), limbs.v.numel(), 0.01, 1.0, losses.slot(2),
+                tape.call('rsg_train_bce', _p(limbs.v), _p(target_limbs), limbs.v.numel(), 0.01, 1.0, losses.slot(2),
                           _p(limbs.g))
                 S = P.shape[1]
                 full = vec = None
@@ -226,6 +231,7 @@ class TrainStep:
             tape.backward()
             st.unpack_grads(tape)
             self.last_launches = tape.launches
+            losses.keep = keep
             if st.bn_counters:
                 torch._foreach_add_(st.bn_counters, 1)
         return losses, outputs

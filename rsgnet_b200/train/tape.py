@@ -96,18 +96,33 @@ class Tape:
         return self._ws
 
     # ------------------------------------------------------------------ matrix ops
-    def _gemm(self, A, B, Cm, bias, M, Nc, Ca, lda, ldb, ldc, mode=0, transA=0, transB=0, beta=0, geom=None, batch=1,
+    def _gemm(self, pr, A, B, Cm, bias, M, Nc, Ca, lda, ldb, ldc, mode=0, transA=0, transB=0, beta=0, geom=None, batch=1,
               sA=0, sB=0, sC=0):
         g = (C.c_int * 8)(*geom) if geom is not None else None
         self.call('rsg_train_gemm', _p(A), _p(B), _p(Cm), _p(bias), M, Nc, Ca, lda, ldb, ldc, batch, sA, sB, sC, mode,
-                  transA, transB, beta, g, self.precise)
+                  transA, transB, beta, g, pr)
 
-    def _wgrad(self, X, dY, dW, M, Ca, Nc, mode=0, geom=None):
+    def _wgrad(self, pr, X, dY, dW, M, Ca, Nc, mode=0, geom=None):
         g = (C.c_int * 8)(*geom) if geom is not None else None
-        self.call('rsg_train_wgrad', _p(X), _p(dY), _p(dW), M, Ca, Nc, Ca, Nc, mode, g, self.precise)
+        self.call('rsg_train_wgrad', _p(X), _p(dY), _p(dW), M, Ca, Nc, Ca, Nc, mode, g, pr)
+
+    def precision(self, precise):
+        """Context manager: matrix ops RECORDED inside use 3xTF32 products (forward and backward), whatever the tape's
+        default -- the TRP needs it: the GroupNorm behind it amplifies product rounding ~1000x (profiles/r2_notes.md §7)."""
+        tape = self
+
+        class _Ctx:
+            def __enter__(self):
+                self.old = tape.precise
+                tape.precise = 1 if precise else 0
+
+            def __exit__(self, *a):
+                tape.precise = self.old
+        return _Ctx()
 
     def conv(self, x, wp, k, stride=1, pad=None, bias=None):
         """x [N,H,W,Ci], wp packed [k*k, Ci, Co] -> [N,Ho,Wo,Co] (nn.Conv2d, pose_rsgnet.py:19-22 conv3x3 and friends)."""
+        pr = self.precise
         if pad is None:
             pad = k // 2
         N, H, W, Ci = x.shape
@@ -117,7 +132,7 @@ class Tape:
         y = self.new(N, Ho, Wo, Co)
         M = N * Ho * Wo
         fg = (H, W, Ho, Wo, k, k, stride, pad)
-        self._gemm(x.v, wp.v, y, bias.v if bias is not None else None, M, Co, Ci, Ci, Co, Co, mode=1, geom=fg)
+        self._gemm(pr, x.v, wp.v, y, bias.v if bias is not None else None, M, Co, Ci, Ci, Co, Co, mode=1, geom=fg)
         out = T(y)
 
         def bwd():
@@ -125,12 +140,12 @@ class Tape:
             if dy is None:
                 return
             if wp.req:
-                self._wgrad(x.v, dy, self.grad_buf(wp), M, Ci, Co, mode=1, geom=fg)
+                self._wgrad(pr, x.v, dy, self.grad_buf(wp), M, Ci, Co, mode=1, geom=fg)
             if bias is not None and bias.req:
                 self.call('rsg_train_colsum', _p(dy), M, Co, _p(self.grad_buf(bias)), 1, _p(self.ws(Co)), n=2)
             if x.req:
                 dx = self.new(N, H, W, Ci)
-                self._gemm(dy, wp.v, dx, None, N * H * W, Ci, Co, Co, Co, Ci, mode=2, transB=1,
+                self._gemm(pr, dy, wp.v, dx, None, N * H * W, Ci, Co, Co, Co, Ci, mode=2, transB=1,
                            geom=(Ho, Wo, H, W, k, k, stride, pad))
                 self.acc(x, dx)
         self.record(bwd)
@@ -138,6 +153,7 @@ class Tape:
 
     def conv_transpose(self, x, wp, k, stride, pad, opad=0):
         """x [N,h,w,Ci], wp packed [k*k, Ci, Co] from the ConvTranspose2d weight [Ci,Co,k,k] -> [N,H,W,Co]."""
+        pr = self.precise
         N, h, w, Ci = x.shape
         taps, Cip, Co = wp.shape
         assert taps == k * k and Cip == Ci
@@ -145,7 +161,7 @@ class Tape:
         y = self.new(N, H, W, Co)
         M = N * H * W
         tg = (h, w, H, W, k, k, stride, pad)
-        self._gemm(x.v, wp.v, y, None, M, Co, Ci, Ci, Co, Co, mode=2, geom=tg)
+        self._gemm(pr, x.v, wp.v, y, None, M, Co, Ci, Ci, Co, Co, mode=2, geom=tg)
         out = T(y)
 
         def bwd():
@@ -153,10 +169,10 @@ class Tape:
             if dy is None:
                 return
             if wp.req:
-                self._wgrad(x.v, dy, self.grad_buf(wp), M, Ci, Co, mode=2, geom=tg)
+                self._wgrad(pr, x.v, dy, self.grad_buf(wp), M, Ci, Co, mode=2, geom=tg)
             if x.req:
                 dx = self.new(N, h, w, Ci)
-                self._gemm(dy, wp.v, dx, None, N * h * w, Ci, Co, Co, Co, Ci, mode=1, transB=1,
+                self._gemm(pr, dy, wp.v, dx, None, N * h * w, Ci, Co, Co, Co, Ci, mode=1, transB=1,
                            geom=(H, W, h, w, k, k, stride, pad))
                 self.acc(x, dx)
         self.record(bwd)
@@ -164,12 +180,13 @@ class Tape:
 
     def linear(self, x, w, bias=None):
         """x [..., I], w raw [O, I] (nn.Linear weight or a 1x1 conv's OIHW weight) -> [..., O]."""
+        pr = self.precise
         I = x.shape[-1]
         O = w.v.shape[0]
         assert w.v.numel() == O * I, (w.v.shape, x.shape)
         M = x.v.numel() // I
         y = self.new(*x.shape[:-1], O)
-        self._gemm(x.v, w.v, y, bias.v if bias is not None else None, M, O, I, I, I, O, transB=1)
+        self._gemm(pr, x.v, w.v, y, bias.v if bias is not None else None, M, O, I, I, I, O, transB=1)
         out = T(y)
 
         def bwd():
@@ -177,22 +194,23 @@ class Tape:
             if dy is None:
                 return
             if w.req:
-                self._wgrad(dy, x.v, self.grad_buf(w), M, O, I)
+                self._wgrad(pr, dy, x.v, self.grad_buf(w), M, O, I)
             if bias is not None and bias.req:
                 self.call('rsg_train_colsum', _p(dy), M, O, _p(self.grad_buf(bias)), 1, _p(self.ws(O)), n=2)
             if x.req:
                 dx = self.new(*x.shape)
-                self._gemm(dy, w.v, dx, None, M, I, O, O, I, I)
+                self._gemm(pr, dy, w.v, dx, None, M, I, O, O, I, I)
                 self.acc(x, dx)
         self.record(bwd)
         return out
 
     def matmul(self, a, b):
         """a [M, K] @ b [K, N] with gradients to both (KTMachine: matrix_relation @ final_layer.weight)."""
+        pr = self.precise
         M, K = a.shape
         N = b.v.numel() // K
         y = self.new(M, N)
-        self._gemm(a.v, b.v, y, None, M, N, K, K, N, N)
+        self._gemm(pr, a.v, b.v, y, None, M, N, K, K, N, N)
         out = T(y)
 
         def bwd():
@@ -200,10 +218,10 @@ class Tape:
             if dy is None:
                 return
             if b.req:
-                self._wgrad(a.v, dy, self.grad_buf(b), M, K, N)
+                self._wgrad(pr, a.v, dy, self.grad_buf(b), M, K, N)
             if a.req:
                 da = self.new(M, K)
-                self._gemm(dy, b.v, da, None, M, K, N, N, N, K, transB=1)
+                self._gemm(pr, dy, b.v, da, None, M, K, N, N, N, K, transB=1)
                 self.acc(a, da)
         self.record(bwd)
         return out
@@ -430,13 +448,14 @@ class Tape:
     def trp_attention(self, x, g):
         """x [B,S,C] (theta = phi = x), g [B,S,Cg] -> (y [B,S,Cg] = sigmoid(x x^T) g, P [B,S,S] as a node).
         The gradient of a loss on P (the relation MSE) is added by the caller through ``P.g`` or ``rel_hook``."""
+        pr = self.precise
         B, S, Cx = x.shape
         Cg = g.shape[-1]
         P = self.new(B, S, S)
-        self._gemm(x.v, x.v, P, None, S, S, Cx, Cx, Cx, S, transB=1, batch=B, sA=S * Cx, sB=S * Cx, sC=S * S)
+        self._gemm(pr, x.v, x.v, P, None, S, S, Cx, Cx, Cx, S, transB=1, batch=B, sA=S * Cx, sB=S * Cx, sC=S * S)
         self.call('rsg_train_ew', 1, _p(P), None, 0.0, P.numel(), _p(P))
         y = self.new(B, S, Cg)
-        self._gemm(P, g.v, y, None, S, Cg, S, S, Cg, Cg, batch=B, sA=S * S, sB=S * Cg, sC=S * Cg)
+        self._gemm(pr, P, g.v, y, None, S, Cg, S, S, Cg, Cg, batch=B, sA=S * S, sB=S * Cg, sC=S * Cg)
         out, Pn = T(y), T(P)
         Pn.g = None
         hook = {}
@@ -447,10 +466,10 @@ class Tape:
             if dy is not None:
                 if g.req:
                     dg = self.new(B, S, Cg)          # P is symmetric: P^T dy = P dy
-                    self._gemm(P, dy, dg, None, S, Cg, S, S, Cg, Cg, batch=B, sA=S * S, sB=S * Cg, sC=S * Cg)
+                    self._gemm(pr, P, dy, dg, None, S, Cg, S, S, Cg, Cg, batch=B, sA=S * S, sB=S * Cg, sC=S * Cg)
                     self.acc(g, dg)
                 dP = self.new(B, S, S)
-                self._gemm(dy, g.v, dP, None, S, S, Cg, Cg, Cg, S, transB=1, batch=B, sA=S * Cg, sB=S * Cg, sC=S * S)
+                self._gemm(pr, dy, g.v, dP, None, S, S, Cg, Cg, Cg, S, transB=1, batch=B, sA=S * Cg, sB=S * Cg, sC=S * S)
             if Pn.g is not None:                      # a caller differentiated through the returned scores directly
                 if dP is None:
                     dP = Pn.g
@@ -465,8 +484,8 @@ class Tape:
             self.call('rsg_train_trp_dscore', _p(P), _p(dP), _p(rel[0]) if rel else None, _p(rel[1]) if rel else None,
                       _p(rel[2]) if rel else None, B, S, _p(dA))
             dx = self.new(B, S, Cx)                   # A = x x^T: dx = dA x + dA^T x
-            self._gemm(dA, x.v, dx, None, S, Cx, S, S, Cx, Cx, batch=B, sA=S * S, sB=S * Cx, sC=S * Cx)
-            self._gemm(dA, x.v, dx, None, S, Cx, S, S, Cx, Cx, transA=1, beta=1, batch=B, sA=S * S, sB=S * Cx, sC=S * Cx)
+            self._gemm(pr, dA, x.v, dx, None, S, Cx, S, S, Cx, Cx, batch=B, sA=S * S, sB=S * Cx, sC=S * Cx)
+            self._gemm(pr, dA, x.v, dx, None, S, Cx, S, S, Cx, Cx, transA=1, beta=1, batch=B, sA=S * S, sB=S * Cx, sC=S * Cx)
             self.acc(x, dx)
         self.record(bwd)
         return out, Pn, hook
