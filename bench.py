@@ -43,6 +43,9 @@ METRIC = 'crops/sec RSGNet-W32 256x192 flip-test inference'
 WORKLOADS = {
     'postproc': ('post-processing only: get_final_preds decode + evaluate (rescoring, grouping, oks_nms) on 100k synthetic '
                  'detections x 17 heat-maps at 64x48 (BASELINE.json configs[3])', 'crops/sec get_final_preds decode 17x64x48'),
+    'train': ('RSGNet-W32 256x192 COCO K=17 training step (forward + losses + backward + Adam), batch 32/GPU, data-parallel '
+              'with one NCCL all-reduce of the flat gradient buffer (BASELINE.json configs[4])',
+              'samples/sec RSGNet-W32 256x192 training step'),
     'w32_crowdpose': (WORKLOAD, METRIC),
     'w48_coco_384': ('RSGNet-W48 384x288 COCO K=17 flip-test inference (BASELINE.json configs[2])',
                      'crops/sec RSGNet-W48 384x288 flip-test inference'),
@@ -197,6 +200,8 @@ def run_reference(args):
         return
     if PRESET == 'postproc':
         return run_postproc_reference(args)
+    if PRESET == 'train':
+        return run_train_reference(args)
     cores = len(os.sched_getaffinity(0))
     torch.set_num_threads(cores)
     cfg = presets.preset(PRESET)
@@ -439,6 +444,205 @@ def run_postproc(args):
 
 
 
+# ---------------------------------------------------------------------------------------------
+# BASELINE.json configs[4]: training step
+# ---------------------------------------------------------------------------------------------
+TRAIN_PRESET = 'w32_coco'
+
+
+def _train_batch(cfg, n, seed):
+    return synth.train_batch(n, cfg.MODEL.IMAGE_SIZE, cfg.MODEL.HEATMAP_SIZE, cfg.MODEL.NUM_JOINTS, cfg.MODEL.NUM_LIMBS, seed=seed)
+
+
+def _train_cpu(cfg, sd, n, reps):
+    """The reference's CPU training iteration (oracle/train_oracle.py: torch CPU ops + autograd + Adam) on n samples."""
+    from oracle import train_oracle
+    b = {k: torch.from_numpy(v) for k, v in _train_batch(cfg, n, 1).items()}
+    cur = {k: v.clone() for k, v in sd.items()}
+    state = None
+    times, losses = [], None
+    for i in range(reps + 1):
+        t0 = time.perf_counter()
+        losses, grads, bufs, _ = train_oracle.forward_backward(cur, cfg, b)
+        new, state = train_oracle.adam_step(cur, grads, state=state)
+        cur.update(new)
+        cur.update(bufs)
+        if i:
+            times.append(time.perf_counter() - t0)
+        if i == 0:
+            first = (losses, grads)
+    return n / float(np.median(times)), first
+
+
+def run_train_reference(args):
+    cores = len(os.sched_getaffinity(0))
+    torch.set_num_threads(cores)
+    cfg = presets.preset(TRAIN_PRESET)
+    net = pose_rsgnet.get_pose_net(cfg, True)
+    sd = _params.synth_state_dict(net, seed=4)
+    n = min(args.cpu_sample, 8)
+    val, _ = _train_cpu(cfg, sd, n, max(1, min(args.steps, 3)))
+    sample = f'{n} of the 32 samples per GPU per step: fp32 forward (batch-statistics BN) + losses + autograd backward + Adam, torch CPU ops'
+    print(json.dumps({
+        'impl': 'reference', 'metric': METRIC, 'value': val, 'unit': 'samples/s', 'n_gpus': args.gpus, 'steps': args.steps,
+        'warmup': args.warmup, 'ms_per_step': n / val * 1e3, 'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None,
+        'dtype': 'f32', 'data': 'synthetic', 'config': {'workload': WORKLOAD, 'samples_per_step': n, 'sample': sample},
+        'cpu_baseline': {'value': val, 'unit': 'samples/s', 'cores': cores, 'kind': 'port', 'sample': sample},
+        'e2e': {'value': val, 'unit': 'samples/s', 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0}, 'gpu_launches': 0}))
+
+
+def run_train(args):
+    """`--workload train`: one optimisation step per bench step on B samples per GPU (weak scaling), gradients averaged
+    with one NCCL all-reduce of the flat buffer.  `value`: batch resident in HBM, replayed as a CUDA graph; `e2e`: the
+    batch comes from pinned host memory every step and the losses are read back."""
+    import collections
+    from rsgnet_b200.train import TrainStep
+    world = int(os.environ.get('WORLD_SIZE', '1'))
+    rank = int(os.environ.get('RANK', '0'))
+    local = int(os.environ.get('LOCAL_RANK', '0'))
+    torch.cuda.set_device(local)
+    dev = torch.device('cuda', local)
+    dist = None
+    if world > 1:
+        import torch.distributed as dist
+        sys.stdout.flush()
+        saved_fd = os.dup(1)
+        os.dup2(2, 1)
+        try:
+            dist.init_process_group('nccl', device_id=dev)
+            dist.barrier()
+            torch.cuda.synchronize()
+        finally:
+            sys.stdout.flush()
+            os.dup2(saved_fd, 1)
+            os.close(saved_fd)
+    B = args.batch if args.batch != 256 else 32
+    pk = peaks()
+    cfg = presets.preset(TRAIN_PRESET)
+    net = pose_rsgnet.get_pose_net(cfg, True)
+    sd = _params.synth_state_dict(net, seed=4)
+    net.load_state_dict(sd)
+    net = net.to(dev).train()
+    keys = ('input', 'target', 'target_weight', 'all_ins_target', 'all_ins_target_weight', 'target_limbs')
+    host = {k: torch.from_numpy(v).pin_memory() for k, v in _train_batch(cfg, B, 100 + rank).items()}
+    batch = [host[k].to(dev) for k in keys]
+    ts = TrainStep(net, lr=1e-3)
+    stream = torch.cuda.Stream(dev)
+
+    def barrier():
+        if dist is not None:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    # parity of the path that is timed: the first samples through the GPU step and through the CPU oracle (same weights)
+    parity, cpu = None, None
+    if rank == 0 and not args.no_cpu_baseline:
+        n_c = 2
+        cps, (o_loss, o_grads) = _train_cpu(cfg, sd, n_c, 1)
+        small = {k: torch.from_numpy(v).to(dev) for k, v in _train_batch(cfg, n_c, 1).items()}
+        pnet = pose_rsgnet.get_pose_net(cfg, True)
+        pnet.load_state_dict(sd)
+        pnet = pnet.to(dev).train()
+        pts = TrainStep(pnet, lr=1e-3)
+        L, _ = pts.forward_backward(*[small[k] for k in keys])
+        L = L.read()
+        P = dict(pnet.named_parameters())
+        rel = []
+        for k, g in o_grads.items():
+            off, n = pts.store.offsets[id(P[k])]
+            ours = pts.store.flat_g[off:off + n].cpu().double()
+            ref = g.reshape(-1).double()
+            if float(ref.norm()) > 0:
+                rel.append(abs(float(ours.norm()) - float(ref.norm())) / float(ref.norm()))
+        lerr = max(abs(L[k] - o_loss[k]) / abs(o_loss[k]) for k in ('multi_loss', 'target_loss', 'skeleton_loss', 'relation_loss'))
+        parity = {'samples': n_c, 'loss_rel_err_max': lerr, 'grad_norm_rel_err_median': float(np.median(rel)),
+                  'bar': 'TF32 products vs the fp32 CPU oracle: every loss term within 5e-3, median per-tensor gradient norm within 3 %'}
+        if not (lerr < 5e-3 and np.median(rel) < 0.03):
+            raise SystemExit(f'bench: training parity check failed: {parity}')
+        cpu = {'value': cps, 'unit': 'samples/s', 'cores': torch.get_num_threads(), 'kind': 'port',
+               'sample': f'{n_c} of the {B} samples per step: forward + losses + backward + Adam, oracle port of the reference loop (torch CPU ops)'}
+        del pts, pnet, small
+        torch.cuda.empty_cache()
+
+    with torch.cuda.stream(stream):
+        ts.build_graph(*batch)
+        for _ in range(args.warmup):
+            ts.step_graph(*batch, sync=False)
+    barrier()
+
+    def timed(fn, steps, sample=False):
+        barrier()
+        sampler = ClockSampler(local).start() if sample else None
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        with torch.cuda.stream(stream):
+            e0.record(stream)
+            for _ in range(steps):
+                fn()
+            e1.record(stream)
+        barrier()
+        ms = e0.elapsed_time(e1)
+        clocks = sampler.stop() if sampler else None
+        if dist is not None:
+            t = torch.tensor([ms], device=dev)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            ms = float(t.item())
+        return ms, clocks
+
+    ms, clocks = timed(lambda: ts.step_graph(*batch, sync=False), args.steps, sample=(rank == 0))
+    last = {}
+
+    def e2e_step():
+        last['L'], _ = ts.step_graph(*[host[k] for k in keys], sync=True)     # H2D of the batch + D2H of the losses
+    ms_e2e, _ = timed(e2e_step, args.steps)
+    # eager step with CUDA events around every library call: per-kernel-family time and executed FLOPs
+    ts.profile = True
+    with torch.cuda.stream(stream):
+        ts(*batch, sync=False)
+    torch.cuda.synchronize()
+    ts.profile = False
+    agg = collections.defaultdict(lambda: [0.0, 0, 0.0])
+    for name, a, b_, fl in ts.tape.prof:
+        r = agg[name]
+        r[0] += a.elapsed_time(b_)
+        r[1] += 1
+        r[2] += fl
+    launches, gflop = ts.last_launches, ts.last_flops / 1e9
+    if rank != 0:
+        if dist is not None:
+            dist.destroy_process_group()
+        return
+    per_ms = ms / args.steps
+    tot = sum(r[0] for r in agg.values())
+    fam = {k: {'ms': round(r[0], 3), 'launches': r[1], 'tflops': (r[2] / r[0] / 1e9 if r[0] and r[2] else 0.0),
+               'share': round(r[0] / tot, 4)} for k, r in sorted(agg.items(), key=lambda kv: -kv[1][0])}
+    g = agg['rsg_train_gemm']
+    tf32_peak = pk['tf_sus'] / 2.0
+    h2d = int(sum(host[k].numel() * 4 for k in keys))
+    line = {
+        'metric': METRIC, 'value': B * world * args.steps / (ms * 1e-3), 'unit': 'samples/s', 'n_gpus': world, 'steps': args.steps,
+        'warmup': args.warmup, 'ms_per_step': per_ms, 'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None,
+        'dtype': 'tf32', 'data': 'synthetic',
+        'config': {'workload': WORKLOAD, 'samples_per_gpu_per_step': B, 'cuda_graph': True, 'optimizer': 'Adam lr 1e-3',
+                   'weights': 'random-init trained-like (synth_state_dict seed 4)',
+                   'l2': 'activations of a step (~12 GB) exceed the 126 MB L2; no explicit flush'},
+        'clocks': clocks, 'gpu_launches': launches * args.steps,
+        'e2e': {'value': B * world * args.steps / (ms_e2e * 1e-3), 'unit': 'samples/s', 'h2d_bytes_per_step': h2d,
+                'd2h_bytes_per_step': 8 * (3 + B), 'ms_per_step': ms_e2e / args.steps, 'last_loss': last['L']['loss']},
+        'roofline': {'bound': 'tensor', 'kernel': 'gather_gemm_kernel (TF32 mma.sync implicit GEMM: conv forward / input gradient, Linear, TRP products)',
+                     'achieved': g[2] / g[0] / 1e9, 'peak': tf32_peak, 'unit': 'TFLOP/s', 'frac': g[2] / g[0] / 1e9 / tf32_peak,
+                     'traffic': None, 'peak_source': pk['src'] + ' bf16_tflops_sustained / 2 (TF32 runs at half the bf16 rate)',
+                     'algorithmic_flops_per_launch': g[2] / max(g[1], 1), 'us_per_launch': g[0] / max(g[1], 1) * 1e3,
+                     'launches_per_step': g[1], 'share_of_step': g[0] / tot, 'families': fam,
+                     'note': 'first-correct kernels of the SURVEY 8f-4 row (mma.sync, register-staged tiles); per-family times from an '
+                             'eager step with CUDA events around every call'},
+        'executed_gflop_per_step_per_gpu': gflop, 'executed_tflops_per_gpu': gflop / per_ms,
+        'parity_checked': bool(parity), 'parity': parity, 'cpu_baseline': cpu,
+    }
+    print(json.dumps(line))
+    if dist is not None:
+        dist.destroy_process_group()
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument('--gpus', type=int, default=1)
@@ -467,6 +671,8 @@ def main():
         return run_reference(args)
     if PRESET == 'postproc':
         return run_postproc(args)
+    if PRESET == 'train':
+        return run_train(args)
 
     from rsgnet_b200.pipeline import CropPipeline
     world = int(os.environ.get('WORLD_SIZE', '1'))

@@ -389,6 +389,10 @@ int rsg_train_d2f(void* stream, const double* in, float scale, int n, int accumu
  * (1 / world_size after a summing all-reduce). */
 int rsg_train_adam(void* stream, float* p, const float* g, float* m, float* v, long long n, float lr, float beta1, float beta2,
                    float eps, int step, float grad_scale);
+/* The same with the step count in DEVICE memory: *step_dev is incremented, then used -- a captured CUDA graph of the whole
+ * training step replays with the right bias corrections. */
+int rsg_train_adam_graph(void* stream, float* p, const float* g, float* m, float* v, long long n, float lr, float beta1,
+                         float beta2, float eps, int* step_dev, float grad_scale);
 
 #ifdef __cplusplus
 }

@@ -148,6 +148,7 @@ _SIGS = {
     'rsg_train_zero': (C.c_int, [C.c_void_p, C.c_void_p, C.c_size_t]),
     'rsg_train_d2f': (C.c_int, [C.c_void_p, C.c_void_p, C.c_float, C.c_int, C.c_int, C.c_void_p]),
     'rsg_train_adam': (C.c_int, [C.c_void_p] * 5 + [C.c_longlong] + [C.c_float] * 4 + [C.c_int, C.c_float]),
+    'rsg_train_adam_graph': (C.c_int, [C.c_void_p] * 5 + [C.c_longlong] + [C.c_float] * 4 + [C.c_void_p, C.c_float]),
 }
 
 EXPORTS = tuple(_SIGS)

@@ -521,17 +521,28 @@ __global__ void d2f_kernel(const double* __restrict__ in, float scale, int n, in
   if (i < n) out[i] = (accumulate ? out[i] : 0.f) + (float)in[i] * scale;
 }
 
-// Adam (torch.optim.Adam, no weight decay / amsgrad): one launch over the flat parameter buffer
+// Adam (torch.optim.Adam, no weight decay / amsgrad): one launch over the flat parameter buffer.  The step count comes from
+// a kernel argument or, when `step_dev` is given, from device memory (incremented by step_inc_kernel), so that a captured
+// CUDA graph of the whole training step replays with the right bias corrections.
+__global__ void step_inc_kernel(int* step) { *step += 1; }
+
 __global__ void __launch_bounds__(EW_THREADS) adam_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m,
                                                           float* __restrict__ v, long long n, float lr, float b1, float b2, float eps,
-                                                          float bc1, float bc2_sqrt, float gscale) {
-  const float step = lr / bc1;
+                                                          int step, const int* __restrict__ step_dev, float gscale) {
+  __shared__ float sh[2];
+  if (threadIdx.x == 0) {
+    const int t = step_dev ? *step_dev : step;
+    sh[0] = (float)(1.0 - pow((double)b1, (double)t));
+    sh[1] = (float)sqrt(1.0 - pow((double)b2, (double)t));
+  }
+  __syncthreads();
+  const float stepsz = lr / sh[0], bc2_sqrt = sh[1];
   GRID_STRIDE(i, n) {
     const float gg = g[i] * gscale;
     const float mm = b1 * m[i] + (1.f - b1) * gg;
     const float vv = b2 * v[i] + (1.f - b2) * gg * gg;
     m[i] = mm; v[i] = vv;
-    p[i] -= step * mm / (sqrtf(vv) / bc2_sqrt + eps);
+    p[i] -= stepsz * mm / (sqrtf(vv) / bc2_sqrt + eps);
   }
 }
 
@@ -748,8 +759,16 @@ extern "C" int rsg_train_adam(void* stream, float* p, const float* g, float* m, 
                               float eps, int step, float grad_scale) {
   RSG_REQUIRE(p && g && m && v && n >= 0 && step >= 1, "adam: bad arguments");
   if (n == 0) return RSG_OK;
-  const double bc1 = 1.0 - pow((double)beta1, (double)step), bc2 = 1.0 - pow((double)beta2, (double)step);
-  adam_kernel<<<ew_grid(n, 4), EW_THREADS, 0, ST>>>(p, g, m, v, n, lr, beta1, beta2, eps, (float)bc1, (float)sqrt(bc2), grad_scale);
+  adam_kernel<<<ew_grid(n, 4), EW_THREADS, 0, ST>>>(p, g, m, v, n, lr, beta1, beta2, eps, step, nullptr, grad_scale);
+  RSG_LAUNCH_CHECK();
+  return RSG_OK;
+}
+
+extern "C" int rsg_train_adam_graph(void* stream, float* p, const float* g, float* m, float* v, long long n, float lr, float beta1,
+                                    float beta2, float eps, int* step_dev, float grad_scale) {
+  RSG_REQUIRE(p && g && m && v && n >= 0 && step_dev, "adam_graph: bad arguments");
+  step_inc_kernel<<<1, 1, 0, ST>>>(step_dev);
+  if (n) adam_kernel<<<ew_grid(n, 4), EW_THREADS, 0, ST>>>(p, g, m, v, n, lr, beta1, beta2, eps, 0, step_dev, grad_scale);
   RSG_LAUNCH_CHECK();
   return RSG_OK;
 }

@@ -169,6 +169,7 @@ class TrainStep:
         if process_group is not None or (torch.distributed.is_available() and torch.distributed.is_initialized()):
             self.world = torch.distributed.get_world_size(process_group)
         self.last_launches = 0
+        self.profile = False          # True: CUDA events around every library call of the next step (see tape.prof)
         # frozen parameters (loc_features, kt_machine.real_matrix_limb) keep a zero gradient and are skipped by masking lr:
         # Adam with g = 0, m = v = 0 leaves them unchanged (update = 0 / (0 + eps) = 0)
 
@@ -181,6 +182,9 @@ class TrainStep:
         mod, dev = self.module, self.device
         with torch.cuda.device(dev):
             tape = Tape(dev, self.precise)
+            if self.profile:
+                tape.prof = []
+            self.tape = tape
             st = self.store
             st.zero_grads(tape)
             st.pack_all(tape)
@@ -231,6 +235,7 @@ class TrainStep:
             tape.backward()
             st.unpack_grads(tape)
             self.last_launches = tape.launches
+            self.last_flops = tape.flops
             losses.keep = keep
             if st.bn_counters:
                 torch._foreach_add_(st.bn_counters, 1)
@@ -263,6 +268,44 @@ class TrainStep:
         losses, outputs = self.forward_backward(x, target, target_weight, all_target, all_target_weight, target_limbs,
                                                 relation_target)
         with torch.cuda.device(self.device):
+            self.all_reduce()
+            self.adam()
+        return (losses.read() if sync else losses), outputs
+
+    # ---- CUDA-graph replay -------------------------------------------------------------------------------------------------
+    # A step is ~4 000 small launches issued from Python: eagerly the host is the bottleneck.  The sequence is static for a
+    # fixed batch shape, so forward + losses + backward are captured ONCE into a CUDA graph over pointer-stable input
+    # buffers and replayed; the gradient all-reduce and the Adam launch follow the replay on the same stream.
+    def build_graph(self, x, target, target_weight, all_target=None, all_target_weight=None, target_limbs=None):
+        dev = self.device
+        args = (x, target, target_weight, all_target, all_target_weight, target_limbs)
+        with torch.cuda.device(dev):
+            self._static = [a.to(dev, torch.float32).contiguous().clone() if a is not None else None for a in args]
+            bufs = [b for b in self.module.buffers()]
+            saved = [b.detach().clone() for b in bufs]
+            side = torch.cuda.Stream(dev)
+            side.wait_stream(torch.cuda.current_stream(dev))
+            with torch.cuda.stream(side):                   # one eager pass: lazy initialisation, allocator warm-up
+                self.forward_backward(*self._static)
+            torch.cuda.current_stream(dev).wait_stream(side)
+            torch.cuda.synchronize(dev)
+            for b, sv in zip(bufs, saved):                  # the warm-up pass must not count as a training step
+                b.copy_(sv)
+            graph = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(graph):
+                losses, outputs = self.forward_backward(*self._static)
+            self.tape = None
+            self._graph = (graph, losses, outputs)
+        return self
+
+    def step_graph(self, x, target, target_weight, all_target=None, all_target_weight=None, target_limbs=None, sync=True):
+        """One optimisation step by graph replay (build_graph first; same batch shape every call)."""
+        graph, losses, outputs = self._graph
+        with torch.cuda.device(self.device):
+            for s, a in zip(self._static, (x, target, target_weight, all_target, all_target_weight, target_limbs)):
+                if s is not None:
+                    s.copy_(a, non_blocking=True)
+            graph.replay()
             self.all_reduce()
             self.adam()
         return (losses.read() if sync else losses), outputs

@@ -40,6 +40,8 @@ class Tape:
         self.ops = []
         self.precise = 1 if precise else 0
         self.launches = 0
+        self.flops = 0.0              # executed multiply-adds * 2 of the matrix kernels (3x in the 3xTF32 mode not counted)
+        self.prof = None              # list of (kernel, start event, end event, flops) when profiling
         self._ws = torch.empty(4096, dtype=torch.float64, device=device)      # reduction scratch (2 * C doubles)
 
     # ------------------------------------------------------------------ plumbing
@@ -50,9 +52,17 @@ class Tape:
     def new(self, *shape):
         return torch.empty(shape, dtype=torch.float32, device=self.device)
 
-    def call(self, name, *args, n=1):
-        _lib.check(getattr(self.lib, name)(self.st, *args))
+    def call(self, name, *args, n=1, flops=0.0):
+        if self.prof is not None:
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            _lib.check(getattr(self.lib, name)(self.st, *args))
+            e1.record()
+            self.prof.append((name, e0, e1, flops))
+        else:
+            _lib.check(getattr(self.lib, name)(self.st, *args))
         self.launches += n
+        self.flops += flops
 
     def record(self, fn):
         self.ops.append(fn)
@@ -99,12 +109,14 @@ class Tape:
     def _gemm(self, pr, A, B, Cm, bias, M, Nc, Ca, lda, ldb, ldc, mode=0, transA=0, transB=0, beta=0, geom=None, batch=1,
               sA=0, sB=0, sC=0):
         g = (C.c_int * 8)(*geom) if geom is not None else None
+        taps = geom[4] * geom[5] if geom is not None else 1
         self.call('rsg_train_gemm', _p(A), _p(B), _p(Cm), _p(bias), M, Nc, Ca, lda, ldb, ldc, batch, sA, sB, sC, mode,
-                  transA, transB, beta, g, pr)
+                  transA, transB, beta, g, pr, flops=2.0 * M * Nc * Ca * taps * batch)
 
     def _wgrad(self, pr, X, dY, dW, M, Ca, Nc, mode=0, geom=None):
         g = (C.c_int * 8)(*geom) if geom is not None else None
-        self.call('rsg_train_wgrad', _p(X), _p(dY), _p(dW), M, Ca, Nc, Ca, Nc, mode, g, pr)
+        taps = geom[4] * geom[5] if geom is not None else 1
+        self.call('rsg_train_wgrad', _p(X), _p(dY), _p(dW), M, Ca, Nc, Ca, Nc, mode, g, pr, flops=2.0 * M * Ca * Nc * taps)
 
     def precision(self, precise):
         """Context manager: matrix ops RECORDED inside use 3xTF32 products (forward and backward), whatever the tape's
