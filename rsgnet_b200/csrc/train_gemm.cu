@@ -396,6 +396,17 @@ __global__ void __launch_bounds__(GM_THREADS) wgrad_kernel(const WgradP p) {
       }
 }
 
+}  // namespace
+
+// train_tc5.cu: the tcgen05 kind::tf32 kernel (K-major B only)
+int train_tc5_supported(const float* A, const float* B, int Ca, int lda, int ldb, long long sA, long long sB, long long tapB,
+                        int transA, int transB, int precise);
+int train_tc5_launch(cudaStream_t s, const float* A, const float* B, float* C, const float* bias, int M, int Nc, int Ca, int lda,
+                     int ldb, int ldc, int batch, long long sA, long long sB, long long sC, long long tapB, int mode, int beta,
+                     const int* geom);
+
+namespace {
+
 inline bool al16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; }
 
 }  // namespace
@@ -421,6 +432,10 @@ extern "C" int rsg_train_gemm(void* stream, const float* A, const float* B, floa
     RSG_REQUIRE(p.taps >= 1 && p.stride >= 1 && p.Hc > 0 && p.Wc > 0 && M % (p.Hc * p.Wc) == 0, "train gemm: bad geometry");
   }
   p.tapB = transB ? (long long)Nc * ldb : (long long)Ca * ldb;
+  // precise: 0 = TF32 on the tcgen05 kernel where it applies (K-major B), 1 = 3xTF32 on mma.sync, 2 = TF32 on mma.sync
+  if (train_tc5_supported(A, B, Ca, lda, ldb, sA, sB, p.tapB, transA, transB, precise))
+    return train_tc5_launch((cudaStream_t)stream, A, B, C, bias, M, Nc, Ca, lda, ldb, ldc, batch, sA, sB, sC, p.tapB, mode, beta, geom);
+  p.precise = precise == 1;
   p.vecA = al16(A) && lda % 4 == 0 && sA % 4 == 0;
   p.vecB = al16(B) && ldb % 4 == 0 && sB % 4 == 0 && p.tapB % 4 == 0;
   cudaStream_t s = (cudaStream_t)stream;
@@ -444,7 +459,7 @@ extern "C" int rsg_train_wgrad(void* stream, const float* X, const float* dY, fl
   WgradP p;
   memset(&p, 0, sizeof(p));
   p.X = X; p.dY = dY; p.dW = dW; p.M = M; p.Ca = Ca; p.Nc = Nc; p.ldx = ldx; p.ldy = ldy; p.mode = mode;
-  p.taps = 1; p.kw = 1; p.Hc = 1; p.Wc = 1; p.precise = precise;
+  p.taps = 1; p.kw = 1; p.Hc = 1; p.Wc = 1; p.precise = precise == 1;
   if (mode != 0) {
     p.Ha = geom[0]; p.Wa = geom[1]; p.Hc = geom[2]; p.Wc = geom[3];
     p.taps = geom[4] * geom[5]; p.kw = geom[5]; p.stride = geom[6]; p.pad = geom[7];

@@ -16,12 +16,11 @@ class Net:
 
     # ---- building blocks -------------------------------------------------------------------------------------------
     def conv(self, x, conv, bias=True):
-        """nn.Conv2d with its own parameters (1x1 -> the raw OIHW weight, larger kernels -> the packed copy)."""
+        """nn.Conv2d with its own parameters (both packed forms of the weight come from the store)."""
         k = conv.kernel_size[0]
         b = self.s.raw(conv.bias) if (bias and conv.bias is not None) else None
-        if k == 1 and conv.stride[0] == 1:
-            return self.t.linear(x, self.s.raw(conv.weight), b)
-        return self.t.conv(x, self.s.packed(conv), k, conv.stride[0], conv.padding[0], b)
+        wp, wT = self.s.packed(conv)
+        return self.t.conv(x, wp, wT, k, conv.stride[0], conv.padding[0], b)
 
     def bn(self, x, bn, relu=False):
         return self.t.batchnorm(x, self.s.raw(bn.weight), self.s.raw(bn.bias), bn.running_mean, bn.running_var, relu,
@@ -31,7 +30,8 @@ class Net:
         """Sequential(conv, BN[, ReLU]) as built by _params.conv_bn."""
         conv = seq[0]
         if isinstance(conv, nn.ConvTranspose2d):
-            y = self.t.conv_transpose(x, self.s.packed(conv), conv.kernel_size[0], conv.stride[0], conv.padding[0],
+            wp, wT = self.s.packed(conv)
+            y = self.t.conv_transpose(x, wp, wT, conv.kernel_size[0], conv.stride[0], conv.padding[0],
                                       conv.output_padding[0])
         else:
             y = self.conv(x, conv)

@@ -54,9 +54,11 @@ class ParamStore:
             self.offsets[id(p)] = (off, n)
             off += _ceil4(n)
         self.total = total
-        # packed conv weights ([tap][CinPad][Cout]) and their gradients
-        convs = [m for m in module.modules()
-                 if isinstance(m, nn.ConvTranspose2d) or (isinstance(m, nn.Conv2d) and (m.kernel_size[0] > 1 or m.stride[0] > 1))]
+        # Packed conv weights and their gradients.  Every Conv2d / ConvTranspose2d weight is kept in the two K-major forms
+        # the implicit-GEMM kernels read: wT [tap][Cout][CinPad] (reduction over Cin contiguous: the forward pass) and
+        # w [tap][CinPad][Cout] (reduction over Cout contiguous: the input-gradient pass; also the layout the weight-gradient
+        # kernel writes).  For a 1x1 Conv2d, wT is the parameter itself.
+        convs = [m for m in module.modules() if isinstance(m, (nn.ConvTranspose2d, nn.Conv2d))]
         sizes = []
         for m in convs:
             w = m.weight
@@ -65,31 +67,42 @@ class ParamStore:
             sizes.append((m, tr, ci, _ceil4(ci), co, w.shape[2] * w.shape[3]))
         ptotal = sum(t * cip * co for (_, _, _, cip, co, t) in sizes)
         self.packed_w = torch.zeros(max(ptotal, 4), dtype=torch.float32, device=device)
+        self.packed_wT = torch.zeros(max(ptotal, 4), dtype=torch.float32, device=device)
         self.packed_g = torch.zeros(max(ptotal, 4), dtype=torch.float32, device=device)
         self.packed = {}
-        pack = (_lib.PermEntry * max(len(sizes), 1))()
-        unpack = (_lib.PermEntry * max(len(sizes), 1))()
+        pack, unpack = [], []
         off = 0
-        for i, (m, tr, ci, cip, co, t) in enumerate(sizes):
+        for (m, tr, ci, cip, co, t) in sizes:
             n = t * cip * co
             wv = self.packed_w[off:off + n].view(t, cip, co)
             gv = self.packed_g[off:off + n].view(t, cip, co)
-            self.packed[id(m)] = T(wv, req=m.weight.requires_grad, g=gv)
             src = m.weight.data.data_ptr()
             poff, _ = self.offsets[id(m.weight)]
             gdst = self.flat_g.data_ptr() + 4 * poff
-            if not tr:      # OIHW: packed[tap][ci][co] = w[co*Ci*T + ci*T + tap]
-                pack[i] = _lib.PermEntry(src, wv.data_ptr(), t, cip, co, ci, co, 1, t, ci * t, 0)
+            if not tr and t == 1 and cip == ci:
+                wT = m.weight.data.view(1, co, ci)              # [Cout][Cin] is already the forward operand
+            else:
+                wT = self.packed_wT[off:off + n].view(t, co, cip)
+            node = T(wv, req=m.weight.requires_grad, g=gv)
+            self.packed[id(m)] = (node, wT)
+            if not tr:      # OIHW: w[tap][ci][co] = W[co*Ci*T + ci*T + tap];  wT[tap][co][ci] likewise
+                pack.append(_lib.PermEntry(src, wv.data_ptr(), t, cip, co, ci, co, 1, t, ci * t, 0))
+                if wT.data_ptr() != src:
+                    pack.append(_lib.PermEntry(src, wT.data_ptr(), t, co, cip, co, ci, 1, ci * t, t, 0))
                 # grad OIHW [co][ci][tap] += packed_g[tap*CiP*Co + ci*Co + co]
-                unpack[i] = _lib.PermEntry(gv.data_ptr(), gdst, co, ci, t, ci, t, 1, co, cip * co, 1)
-            else:           # ConvTranspose2d [Ci][Co][kh][kw]: packed[tap][ci][co] = w[ci*Co*T + co*T + tap]
-                pack[i] = _lib.PermEntry(src, wv.data_ptr(), t, cip, co, ci, co, 1, co * t, t, 0)
-                unpack[i] = _lib.PermEntry(gv.data_ptr(), gdst, ci, co, t, co, t, co, 1, cip * co, 1)
+                unpack.append(_lib.PermEntry(gv.data_ptr(), gdst, co, ci, t, ci, t, 1, co, cip * co, 1))
+            else:           # ConvTranspose2d [Ci][Co][kh][kw]: w[tap][ci][co] = W[ci*Co*T + co*T + tap]
+                pack.append(_lib.PermEntry(src, wv.data_ptr(), t, cip, co, ci, co, 1, co * t, t, 0))
+                pack.append(_lib.PermEntry(src, wT.data_ptr(), t, co, cip, co, ci, 1, t, co * t, 0))
+                unpack.append(_lib.PermEntry(gv.data_ptr(), gdst, ci, co, t, co, t, co, 1, cip * co, 1))
             off += n
         self.n_packed = len(sizes)
-        nbytes = C.sizeof(_lib.PermEntry) * max(len(sizes), 1)
-        self.pack_table = torch.frombuffer(bytearray(bytes(pack)), dtype=torch.uint8).clone()[:nbytes].to(device)
-        self.unpack_table = torch.frombuffer(bytearray(bytes(unpack)), dtype=torch.uint8).clone()[:nbytes].to(device)
+
+        def table(entries):
+            arr = (_lib.PermEntry * max(len(entries), 1))(*entries)
+            return torch.frombuffer(bytearray(bytes(arr)), dtype=torch.uint8).clone().to(device), len(entries)
+        self.pack_table, self.n_pack = table(pack)
+        self.unpack_table, self.n_unpack = table(unpack)
         self.bn_counters = [m.num_batches_tracked for m in module.modules()
                             if isinstance(m, (nn.BatchNorm2d, nn.BatchNorm1d)) and m.num_batches_tracked is not None]
 
@@ -97,12 +110,12 @@ class ParamStore:
         return self.leaf[id(p)]
 
     def pack_all(self, tape):
-        if self.n_packed:
-            tape.call('rsg_train_permute3_batch', _p(self.pack_table), self.n_packed, 16)
+        if self.n_pack:
+            tape.call('rsg_train_permute3_batch', _p(self.pack_table), self.n_pack, 16)
 
     def unpack_grads(self, tape):
-        if self.n_packed:
-            tape.call('rsg_train_permute3_batch', _p(self.unpack_table), self.n_packed, 16)
+        if self.n_unpack:
+            tape.call('rsg_train_permute3_batch', _p(self.unpack_table), self.n_unpack, 16)
 
     def zero_grads(self, tape):
         tape.call('rsg_train_zero', _p(self.flat_g), C.c_size_t(4 * self.flat_g.numel()))

@@ -38,7 +38,7 @@ class Tape:
         self.device = device
         self.lib = _lib.lib()
         self.ops = []
-        self.precise = 1 if precise else 0
+        self.precise = int(precise)       # 0 TF32 (tcgen05 kernel where it applies), 1 3xTF32 (fp32-class), 2 TF32 on mma.sync
         self.launches = 0
         self.flops = 0.0              # executed multiply-adds * 2 of the matrix kernels (3x in the 3xTF32 mode not counted)
         self.prof = None              # list of (kernel, start event, end event, flops) when profiling
@@ -132,19 +132,22 @@ class Tape:
                 tape.precise = self.old
         return _Ctx()
 
-    def conv(self, x, wp, k, stride=1, pad=None, bias=None):
-        """x [N,H,W,Ci], wp packed [k*k, Ci, Co] -> [N,Ho,Wo,Co] (nn.Conv2d, pose_rsgnet.py:19-22 conv3x3 and friends)."""
+    def conv(self, x, wp, wT, k, stride=1, pad=None, bias=None):
+        """x [N,H,W,Ci] -> [N,Ho,Wo,Co] (nn.Conv2d).  wp: node of the packed weight [k*k, Ci, Co] (carries the gradient);
+        wT: the same weights as [k*k, Co, Ci] (plain tensor), the K-major operand of the forward pass."""
         pr = self.precise
         if pad is None:
             pad = k // 2
         N, H, W, Ci = x.shape
         taps, Cip, Co = wp.shape
-        assert taps == k * k and Cip == Ci, (wp.shape, x.shape, k)
+        assert taps == k * k and Cip == Ci and tuple(wT.shape) == (taps, Co, Ci), (wp.shape, wT.shape, x.shape, k)
         Ho, Wo = (H + 2 * pad - k) // stride + 1, (W + 2 * pad - k) // stride + 1
         y = self.new(N, Ho, Wo, Co)
         M = N * Ho * Wo
-        fg = (H, W, Ho, Wo, k, k, stride, pad)
-        self._gemm(pr, x.v, wp.v, y, bias.v if bias is not None else None, M, Co, Ci, Ci, Co, Co, mode=1, geom=fg)
+        plain = k == 1 and stride == 1 and pad == 0
+        fg = None if plain else (H, W, Ho, Wo, k, k, stride, pad)
+        self._gemm(pr, x.v, wT, y, bias.v if bias is not None else None, M, Co, Ci, Ci, Ci, Co, mode=0 if plain else 1,
+                   transB=1, geom=fg)
         out = T(y)
 
         def bwd():
@@ -152,28 +155,28 @@ class Tape:
             if dy is None:
                 return
             if wp.req:
-                self._wgrad(pr, x.v, dy, self.grad_buf(wp), M, Ci, Co, mode=1, geom=fg)
+                self._wgrad(pr, x.v, dy, self.grad_buf(wp), M, Ci, Co, mode=0 if plain else 1, geom=fg)
             if bias is not None and bias.req:
                 self.call('rsg_train_colsum', _p(dy), M, Co, _p(self.grad_buf(bias)), 1, _p(self.ws(Co)), n=2)
             if x.req:
                 dx = self.new(N, H, W, Ci)
-                self._gemm(pr, dy, wp.v, dx, None, N * H * W, Ci, Co, Co, Co, Ci, mode=2, transB=1,
-                           geom=(Ho, Wo, H, W, k, k, stride, pad))
+                self._gemm(pr, dy, wp.v, dx, None, N * H * W, Ci, Co, Co, Co, Ci, mode=0 if plain else 2, transB=1,
+                           geom=None if plain else (Ho, Wo, H, W, k, k, stride, pad))
                 self.acc(x, dx)
         self.record(bwd)
         return out
 
-    def conv_transpose(self, x, wp, k, stride, pad, opad=0):
-        """x [N,h,w,Ci], wp packed [k*k, Ci, Co] from the ConvTranspose2d weight [Ci,Co,k,k] -> [N,H,W,Co]."""
+    def conv_transpose(self, x, wp, wT, k, stride, pad, opad=0):
+        """x [N,h,w,Ci] -> [N,H,W,Co] (nn.ConvTranspose2d, weight [Ci,Co,k,k]); wp [k*k, Ci, Co] (node), wT [k*k, Co, Ci]."""
         pr = self.precise
         N, h, w, Ci = x.shape
         taps, Cip, Co = wp.shape
-        assert taps == k * k and Cip == Ci
+        assert taps == k * k and Cip == Ci and tuple(wT.shape) == (taps, Co, Ci)
         H, W = (h - 1) * stride - 2 * pad + k + opad, (w - 1) * stride - 2 * pad + k + opad
         y = self.new(N, H, W, Co)
         M = N * H * W
         tg = (h, w, H, W, k, k, stride, pad)
-        self._gemm(pr, x.v, wp.v, y, None, M, Co, Ci, Ci, Co, Co, mode=2, geom=tg)
+        self._gemm(pr, x.v, wT, y, None, M, Co, Ci, Ci, Ci, Co, mode=2, transB=1, geom=tg)
         out = T(y)
 
         def bwd():

@@ -72,10 +72,14 @@ CONV_CASES = [  # N, H, W, Ci, Co, k, stride, bias
     (2, 24, 16, 64, 64, 3, 1, False),
     (3, 24, 16, 256, 16, 3, 1, False),      # transition1: many input channels, few output channels, several pixel splits
     (3, 24, 16, 256, 32, 3, 2, False),
+    (2, 24, 16, 64, 256, 1, 1, False),      # layer1's 1x1 convs (plain GEMM form), N = 256
+    (2, 24, 16, 256, 64, 1, 1, True),
+    (1, 9, 5, 96, 288, 3, 1, False),        # more than 256 output channels: two column tiles
+    (5, 7, 3, 32, 32, 3, 1, False),         # 105 pixels: one partial row tile
 ]
 
 
-@pytest.mark.parametrize('precise,tol', [(True, 1e-4), (False, 4e-3)])
+@pytest.mark.parametrize('precise,tol', [(1, 1e-4), (0, 4e-3), (2, 4e-3)])      # 3xTF32 | TF32 tcgen05 | TF32 mma.sync
 @pytest.mark.parametrize('case', CONV_CASES)
 def test_conv_forward_dgrad_wgrad(case, precise, tol):
     N, H, W, Ci, Co, k, s, bias = case
@@ -89,7 +93,8 @@ def test_conv_forward_dgrad_wgrad(case, precise, tol):
     tape = _tape(precise)
     xn, wn = _node(xp), _param(pack_conv(w))
     bn = _param(b) if bias else None
-    out = tape.conv(xn, wn, k, s, k // 2, bn)
+    wT = wn.v.permute(0, 2, 1).contiguous()
+    out = tape.conv(xn, wn, wT, k, s, k // 2, bn)
     R = _run(tape, out, rs)
     xt = torch.from_numpy(x).double().requires_grad_(True)
     wt = torch.from_numpy(w).double().requires_grad_(True)
@@ -113,7 +118,7 @@ def test_conv_transpose_4_2_1(case, precise, tol):
     tape = _tape(precise)
     xn = _node(x.transpose(0, 2, 3, 1))
     wn = _param(w.transpose(2, 3, 0, 1).reshape(16, Ci, Co))
-    out = tape.conv_transpose(xn, wn, 4, 2, 1, 0)
+    out = tape.conv_transpose(xn, wn, wn.v.permute(0, 2, 1).contiguous(), 4, 2, 1, 0)
     R = _run(tape, out, rs)
     xt = torch.from_numpy(x).double().requires_grad_(True)
     wt = torch.from_numpy(w).double().requires_grad_(True)

@@ -42,29 +42,41 @@ def test_flat_layout_aliases_the_module_parameters():
     assert not net.loc_features.requires_grad and not st.leaf[id(net.loc_features)].req
 
 
-def test_pack_tables_cover_every_spatial_conv():
+def test_pack_tables_cover_every_conv():
+    """Every Conv2d / ConvTranspose2d weight is packed to [tap][Cin][Cout] (input-gradient operand, gradient layout) and to
+    [tap][Cout][Cin] (forward operand; a 1x1 Conv2d's parameter already is that).  The tables are emulated on the host."""
     net, st = _store()
-    convs = [m for m in net.modules() if isinstance(m, nn.ConvTranspose2d) or
-             (isinstance(m, nn.Conv2d) and m.kernel_size[0] > 1)]
-    assert st.n_packed == len(convs) and len(st.packed) == len(convs)
+    convs = [m for m in net.modules() if isinstance(m, (nn.ConvTranspose2d, nn.Conv2d))]
+    assert st.n_packed == len(convs) and len(st.packed) == len(convs) and st.n_unpack == len(convs)
+    by_src = {m.weight.data.data_ptr(): m for m in convs}
     raw = bytes(st.pack_table.numpy().tobytes())
-    ent = (_lib.PermEntry * st.n_packed).from_buffer_copy(raw)
-    size = 0
-    for e, m in zip(ent, convs):
+    ent = (_lib.PermEntry * st.n_pack).from_buffer_copy(raw)
+    seen = set()
+    for e in ent:
+        m = by_src[e.src]
+        node, wT = st.packed[id(m)]
         t = m.kernel_size[0] * m.kernel_size[1]
         tr = isinstance(m, nn.ConvTranspose2d)
-        ci, co = (m.weight.shape[0], m.weight.shape[1]) if tr else (m.weight.shape[1], m.weight.shape[0])
-        assert (e.D0, e.D2, e.V1, e.V2) == (t, co, ci, co) and e.D1 % 4 == 0 and e.D1 >= ci
-        assert e.src == m.weight.data.data_ptr() and e.accumulate == 0
-        # emulate the permutation on the host and compare with the reference layout [tap][ci][co]
         w = m.weight.detach()
-        want = (w.permute(2, 3, 0, 1) if tr else w.permute(2, 3, 1, 0)).reshape(t, ci, co)
+        ci, co = (w.shape[0], w.shape[1]) if tr else (w.shape[1], w.shape[0])
+        w_tcc = (w.permute(2, 3, 0, 1) if tr else w.permute(2, 3, 1, 0)).reshape(t, ci, co)       # [tap][ci][co]
         flat = w.reshape(-1)
-        i0, i1, i2 = torch.meshgrid(torch.arange(t), torch.arange(ci), torch.arange(co), indexing='ij')
-        got = flat[(i0 * e.s0 + i1 * e.s1 + i2 * e.s2).reshape(-1)].reshape(t, ci, co)
-        assert torch.equal(got, want)
-        size += e.D0 * e.D1 * e.D2
-    assert size <= st.packed_w.numel()
+        i0, i1, i2 = torch.meshgrid(torch.arange(e.D0), torch.arange(e.V1), torch.arange(e.V2), indexing='ij')
+        got = flat[(i0 * e.s0 + i1 * e.s1 + i2 * e.s2).reshape(-1)].reshape(e.D0, e.V1, e.V2)
+        assert e.accumulate == 0 and e.D0 == t
+        if e.dst == node.v.data_ptr():
+            assert (e.D1, e.D2, e.V1, e.V2) == (node.v.shape[1], co, ci, co) and e.D1 % 4 == 0 and torch.equal(got, w_tcc)
+            seen.add((id(m), 'w'))
+        else:
+            assert e.dst == wT.data_ptr() and (e.D1, e.D2, e.V1, e.V2) == (co, wT.shape[2], co, ci)
+            assert torch.equal(got, w_tcc.permute(0, 2, 1))
+            seen.add((id(m), 'wT'))
+    for m in convs:
+        node, wT = st.packed[id(m)]
+        assert (id(m), 'w') in seen
+        if (id(m), 'wT') not in seen:          # 1x1 Conv2d with Cin % 4 == 0: the parameter itself
+            assert wT.data_ptr() == m.weight.data.data_ptr() and m.kernel_size == (1, 1)
+            assert torch.equal(wT, m.weight.detach().view(1, m.weight.shape[0], m.weight.shape[1]))
     assert ctypes.sizeof(_lib.PermEntry) == 72
 
 
