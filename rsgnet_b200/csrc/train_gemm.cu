@@ -407,6 +407,136 @@ int train_tc5_launch(cudaStream_t s, const float* A, const float* B, float* C, c
 
 namespace {
 
+// wgrad for narrow layers (Ca <= 32 and Nc <= 32: the C0 = 32 branch at 64x48 and the heads at 128x96, 40 % of all weight-
+// gradient time with the 64 x 64 tile above, which is 75 % empty for them): the whole 32 x 32 tile belongs to every warp,
+// the 8 warps split the PIXELS of a 128-pixel chunk (16 each), and the 8 partial tiles are summed through shared memory
+// before one atomicAdd per element and CTA.
+constexpr int W32_PX = 128, W32_PITCH = 40;    // Xs[px][ci]: bank = (8 t + g) mod 32
+
+__global__ void __launch_bounds__(GM_THREADS, 2) wgrad32_kernel(const WgradP p) {
+  __shared__ __align__(16) float Xs[W32_PX * W32_PITCH];
+  __shared__ __align__(16) float Ys[W32_PX * W32_PITCH];
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, g = lane >> 2, t = lane & 3;
+  const int tap = blockIdx.y, dy = tap / p.kw, dx = tap % p.kw;
+  const int mb = blockIdx.z * p.rows_per_split;
+  const int me = min(p.M, mb + p.rows_per_split);
+  const int hw = p.Hc * p.Wc;
+  const int q4 = (tid & 7) * 4, pr0 = tid >> 3;       // staged: pixels pr0 + 32 j, channels q4 .. q4+3
+  float acc[2][4][4];
+#pragma unroll
+  for (int i = 0; i < 2; ++i)
+#pragma unroll
+    for (int j = 0; j < 4; ++j)
+#pragma unroll
+      for (int k = 0; k < 4; ++k) acc[i][j][k] = 0.f;
+  float4 rx[4], ry[4];
+  auto fetch = [&](int mc) {
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const int m = mc + pr0 + 32 * j;
+      rx[j] = make_float4(0.f, 0.f, 0.f, 0.f);
+      ry[j] = rx[j];
+      if (m < me) {
+        long long src = m;
+        if (p.mode != 0) {
+          const int n = m / hw, rem = m - n * hw, y = rem / p.Wc, x = rem - y * p.Wc;
+          src = gather_row(p.mode, n, y, x, dy, dx, p.Ha, p.Wa, p.stride, p.pad);
+        }
+        if (src >= 0) rx[j] = load4(p.X + src * p.ldx + q4, p.Ca - q4, p.vecX != 0);
+        ry[j] = load4(p.dY + (long long)m * p.ldy + q4, p.Nc - q4, p.vecY != 0);
+      }
+    }
+  };
+  if (mb < me) fetch(mb);
+  for (int mc = mb; mc < me; mc += W32_PX) {
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      *reinterpret_cast<float4*>(&Xs[(pr0 + 32 * j) * W32_PITCH + q4]) = rx[j];
+      *reinterpret_cast<float4*>(&Ys[(pr0 + 32 * j) * W32_PITCH + q4]) = ry[j];
+    }
+    __syncthreads();
+    if (mc + W32_PX < me) fetch(mc + W32_PX);
+#pragma unroll
+    for (int k8 = 0; k8 < 2; ++k8) {
+      const int kr = warp * 16 + k8 * 8;
+      float af[2][4], bfr[4][2];
+#pragma unroll
+      for (int mt = 0; mt < 2; ++mt) {
+        const float* a = &Xs[(kr + t) * W32_PITCH + mt * 16 + g];
+        af[mt][0] = a[0];
+        af[mt][1] = a[8];
+        af[mt][2] = a[4 * W32_PITCH];
+        af[mt][3] = a[4 * W32_PITCH + 8];
+      }
+#pragma unroll
+      for (int nt = 0; nt < 4; ++nt) {
+        const float* b = &Ys[(kr + t) * W32_PITCH + nt * 8 + g];
+        bfr[nt][0] = b[0];
+        bfr[nt][1] = b[4 * W32_PITCH];
+      }
+      uint32_t ah[2][4], bh[4][2];
+#pragma unroll
+      for (int mt = 0; mt < 2; ++mt)
+#pragma unroll
+        for (int i = 0; i < 4; ++i) ah[mt][i] = to_tf32(af[mt][i]);
+#pragma unroll
+      for (int nt = 0; nt < 4; ++nt) { bh[nt][0] = to_tf32(bfr[nt][0]); bh[nt][1] = to_tf32(bfr[nt][1]); }
+      if (p.precise) {
+        uint32_t al[2][4], bl[4][2];
+#pragma unroll
+        for (int mt = 0; mt < 2; ++mt)
+#pragma unroll
+          for (int i = 0; i < 4; ++i) al[mt][i] = to_tf32(af[mt][i] - __uint_as_float(ah[mt][i]));
+#pragma unroll
+        for (int nt = 0; nt < 4; ++nt)
+#pragma unroll
+          for (int i = 0; i < 2; ++i) bl[nt][i] = to_tf32(bfr[nt][i] - __uint_as_float(bh[nt][i]));
+#pragma unroll
+        for (int mt = 0; mt < 2; ++mt)
+#pragma unroll
+          for (int nt = 0; nt < 4; ++nt) {
+            float part[4] = {0.f, 0.f, 0.f, 0.f};
+            mma_tf32(part, al[mt], bh[nt]);
+            mma_tf32(part, ah[mt], bl[nt]);
+            mma_tf32(part, ah[mt], bh[nt]);
+#pragma unroll
+            for (int i = 0; i < 4; ++i) acc[mt][nt][i] += part[i];
+          }
+      } else {
+#pragma unroll
+        for (int mt = 0; mt < 2; ++mt)
+#pragma unroll
+          for (int nt = 0; nt < 4; ++nt) mma_tf32(acc[mt][nt], ah[mt], bh[nt]);
+      }
+    }
+    __syncthreads();
+  }
+  // cross-warp sum through the staging buffers: the 32 x 32 partial tiles of warps 0-4 in Xs, of warps 5-7 in Ys
+  static_assert(W32_PX * W32_PITCH >= 5 * 1024, "reduction buffer");
+#pragma unroll
+  for (int mt = 0; mt < 2; ++mt)
+#pragma unroll
+    for (int nt = 0; nt < 4; ++nt)
+#pragma unroll
+      for (int h = 0; h < 2; ++h)
+#pragma unroll
+        for (int e = 0; e < 2; ++e) {
+          const int ci = mt * 16 + g + 8 * h, co = nt * 8 + 2 * t + e;
+          float* dst = (warp < 5 ? Xs : Ys) + ((warp < 5 ? warp : warp - 5) * 1024 + ci * 32 + co);
+          *dst = acc[mt][nt][2 * h + e];
+        }
+  __syncthreads();
+  float* W = p.dW + (long long)tap * p.Ca * p.Nc;
+  for (int i = tid; i < 1024; i += GM_THREADS) {
+    const int ci = i >> 5, co = i & 31;
+    if (ci >= p.Ca || co >= p.Nc) continue;
+    float sum = 0.f;
+#pragma unroll
+    for (int w = 0; w < 8; ++w) sum += (w < 5 ? Xs : Ys)[(w < 5 ? w : w - 5) * 1024 + i];
+    atomicAdd(W + (long long)ci * p.Nc + co, sum);
+  }
+}
+
 inline bool al16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; }
 
 }  // namespace
@@ -467,6 +597,18 @@ extern "C" int rsg_train_wgrad(void* stream, const float* X, const float* dY, fl
   }
   p.vecX = al16(X) && ldx % 4 == 0;
   p.vecY = al16(dY) && ldy % 4 == 0;
+  if (Ca <= 32 && Nc <= 32) {                  // narrow layers: pixel-split warps on one 32 x 32 tile
+    long long want = (4ll * rsg_num_sms() + p.taps - 1) / p.taps, maxsplit = (M + 1023) / 1024;
+    if (want > maxsplit) want = maxsplit;
+    if (want < 1) want = 1;
+    if (want > 65535) want = 65535;
+    int rows = ceil_div(M, want);
+    rows = (rows + W32_PX - 1) / W32_PX * W32_PX;
+    p.rows_per_split = rows;
+    wgrad32_kernel<<<dim3(1, (unsigned)p.taps, (unsigned)ceil_div(M, rows)), GM_THREADS, 0, (cudaStream_t)stream>>>(p);
+    RSG_LAUNCH_CHECK();
+    return RSG_OK;
+  }
   const int tiles_m = ceil_div(Ca, WG_T);
   p.tiles_n = ceil_div(Nc, WG_T);
   const long long base = (long long)tiles_m * p.tiles_n * p.taps;

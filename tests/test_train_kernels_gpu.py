@@ -76,6 +76,9 @@ CONV_CASES = [  # N, H, W, Ci, Co, k, stride, bias
     (2, 24, 16, 256, 64, 1, 1, True),
     (1, 9, 5, 96, 288, 3, 1, False),        # more than 256 output channels: two column tiles
     (5, 7, 3, 32, 32, 3, 1, False),         # 105 pixels: one partial row tile
+    (4, 40, 30, 32, 32, 3, 1, False),       # narrow-layer weight-gradient kernel, several pixel splits
+    (3, 33, 21, 16, 24, 3, 2, True),
+    (2, 128, 96, 3, 32, 3, 2, False),
 ]
 
 
