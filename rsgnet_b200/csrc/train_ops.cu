@@ -44,7 +44,8 @@ __global__ void __launch_bounds__(EW_THREADS) chan_reduce_kernel(const float* __
   const long long r0 = (long long)blockIdx.x * rows_per_block;
   long long r1 = r0 + rows_per_block;
   if (r1 > M) r1 = M;
-  for (int cb = 0; cb < C; cb += CT) {
+  {
+    const int cb = blockIdx.y * CT;              // one channel tile per blockIdx.y (C > 256: the batch-repeat backward has C = h w C0)
     const int c = cb + cl;
     // double accumulators: var = E[x^2] - mean^2 cancels (mean^2 / var) digits, and fp32 partial sums left a 1e-4-class
     // error in invstd for channels whose mean is ~10x their spread (visible as 3e-4 in the gradients of a 50-layer net)
@@ -75,9 +76,12 @@ __global__ void __launch_bounds__(EW_THREADS) chan_reduce_kernel(const float* __
   }
 }
 
-inline void chan_reduce_cfg(long long M, int& rows_per_block, int& blocks) {
+// Row blocks of a channel reduction: every block ends in one fp64 atomicAdd per channel on the SAME 2 C addresses, so the
+// block count is kept near 2 per SM (1184 blocks cost ~10 us of same-address atomics on a 12 MB tensor, 296 cost 2 us).
+inline void chan_reduce_cfg(long long M, int& rows_per_block, int& blocks, int ytiles = 1) {
   long long b = (M + 63) / 64;                       // at least 64 rows per block
-  const long long cap = 8ll * rsg_num_sms();
+  long long cap = 2ll * rsg_num_sms() / ytiles;
+  if (cap < 1) cap = 1;
   if (b > cap) b = cap;
   if (b < 1) b = 1;
   rows_per_block = (int)((M + b - 1) / b);
@@ -136,6 +140,149 @@ __global__ void __launch_bounds__(EW_THREADS) bn_bwd_apply_kernel(const float* _
     const float m0 = (float)(sums[c] * invM), m1 = (float)(sums[C + c] * invM);
     dx[i] = gamma[c] * invstd[c] * (d - m0 - xh * m1);
   }
+}
+
+
+// ---- float4 forms (C % 4 == 0: every BatchNorm of the network).  Same thread layout as chan_reduce_kernel on channel
+// QUADS: a thread keeps its quad's statistics / affine terms in registers and streams rows, so the per-element work is one
+// 16-byte load per operand and no index division (the scalar kernels spend a 64-bit modulo per element).
+struct F4 { float v[4]; };
+__device__ __forceinline__ F4 ld4(const float* p) { const float4 t = *reinterpret_cast<const float4*>(p); return F4{{t.x, t.y, t.z, t.w}}; }
+__device__ __forceinline__ void st4(float* p, const F4& a) { *reinterpret_cast<float4*>(p) = make_float4(a.v[0], a.v[1], a.v[2], a.v[3]); }
+
+template <int KIND>      // 0: sum x, sum x^2;  1: sum dy', sum dy' xhat
+__global__ void __launch_bounds__(EW_THREADS) chan_reduce4_kernel(const float* __restrict__ x, const float* __restrict__ dy,
+                                                                  const float* __restrict__ y, const float* __restrict__ mean,
+                                                                  const float* __restrict__ invstd, int relu, long long M, int C,
+                                                                  int rows_per_block, double* __restrict__ out) {
+  __shared__ double red[2][4][EW_THREADS];
+  const int CQ = C >> 2, CT = CQ < EW_THREADS ? CQ : EW_THREADS, G = EW_THREADS / CT;
+  const int tid = threadIdx.x, g = tid / CT, cl = tid - g * CT;
+  const bool active = g < G;
+  const long long r0 = (long long)blockIdx.x * rows_per_block;
+  long long r1 = r0 + rows_per_block;
+  if (r1 > M) r1 = M;
+  {
+    const int cb = blockIdx.y * CT;
+    const int cq = cb + cl;
+    double s0[4] = {0, 0, 0, 0}, s1[4] = {0, 0, 0, 0};
+    if (active && cq < CQ) {
+      F4 mu = {{0, 0, 0, 0}}, is = mu;
+      if (KIND == 1) { mu = ld4(mean + 4 * cq); is = ld4(invstd + 4 * cq); }
+      for (long long r = r0 + g; r < r1; r += G) {
+        const long long i = r * C + 4 * cq;
+        const F4 xv = ld4(x + i);
+        if (KIND == 0) {
+#pragma unroll
+          for (int e = 0; e < 4; ++e) { const double v = (double)xv.v[e]; s0[e] += v; s1[e] += v * v; }
+        } else {
+          F4 d = ld4(dy + i);
+          if (relu) {
+            const F4 yv = ld4(y + i);
+#pragma unroll
+            for (int e = 0; e < 4; ++e) if (!(yv.v[e] > 0.f)) d.v[e] = 0.f;
+          }
+#pragma unroll
+          for (int e = 0; e < 4; ++e) { s0[e] += (double)d.v[e]; s1[e] += (double)d.v[e] * (double)((xv.v[e] - mu.v[e]) * is.v[e]); }
+        }
+      }
+    }
+#pragma unroll
+    for (int e = 0; e < 4; ++e) { red[0][e][tid] = s0[e]; red[1][e][tid] = s1[e]; }
+    __syncthreads();
+    if (g == 0 && cq < CQ) {
+#pragma unroll
+      for (int e = 0; e < 4; ++e) {
+        double a0 = 0.0, a1 = 0.0;
+        for (int k = 0; k < G; ++k) { a0 += red[0][e][k * CT + cl]; a1 += red[1][e][k * CT + cl]; }
+        atomicAdd(out + 4 * cq + e, a0);
+        atomicAdd(out + C + 4 * cq + e, a1);
+      }
+    }
+    __syncthreads();
+  }
+}
+
+__global__ void __launch_bounds__(EW_THREADS) bn_apply4_kernel(const float* __restrict__ x, const float* __restrict__ mean,
+                                                               const float* __restrict__ invstd, const float* __restrict__ gamma,
+                                                               const float* __restrict__ beta, int relu, long long M, int C,
+                                                               int rows_per_block, float* __restrict__ y) {
+  const int CQ = C >> 2, CT = CQ < EW_THREADS ? CQ : EW_THREADS, G = EW_THREADS / CT;
+  const int tid = threadIdx.x, g = tid / CT, cl = tid - g * CT;
+  if (g >= G) return;
+  const long long r0 = (long long)blockIdx.x * rows_per_block;
+  long long r1 = r0 + rows_per_block;
+  if (r1 > M) r1 = M;
+  for (int cq = cl; cq < CQ; cq += CT) {
+    const F4 mu = ld4(mean + 4 * cq), is = ld4(invstd + 4 * cq), ga = ld4(gamma + 4 * cq), be = ld4(beta + 4 * cq);
+    for (long long r = r0 + g; r < r1; r += G) {
+      const long long i = r * C + 4 * cq;
+      F4 v = ld4(x + i);
+#pragma unroll
+      for (int e = 0; e < 4; ++e) {
+        v.v[e] = (v.v[e] - mu.v[e]) * is.v[e] * ga.v[e] + be.v[e];
+        if (relu) v.v[e] = fmaxf(v.v[e], 0.f);
+      }
+      st4(y + i, v);
+    }
+  }
+}
+
+__global__ void __launch_bounds__(EW_THREADS) bn_bwd_apply4_kernel(const float* __restrict__ x, const float* __restrict__ dy,
+                                                                   const float* __restrict__ y, const float* __restrict__ mean,
+                                                                   const float* __restrict__ invstd, const float* __restrict__ gamma,
+                                                                   const double* __restrict__ sums, int relu, long long M, int C,
+                                                                   int rows_per_block, float* __restrict__ dx, float* __restrict__ dgamma,
+                                                                   float* __restrict__ dbeta) {
+  if (blockIdx.x == 0) {
+    for (int c = threadIdx.x; c < C; c += blockDim.x) {
+      if (dbeta) dbeta[c] += (float)sums[c];
+      if (dgamma) dgamma[c] += (float)sums[C + c];
+    }
+  }
+  if (!dx) return;
+  const int CQ = C >> 2, CT = CQ < EW_THREADS ? CQ : EW_THREADS, G = EW_THREADS / CT;
+  const int tid = threadIdx.x, g = tid / CT, cl = tid - g * CT;
+  if (g >= G) return;
+  const long long r0 = (long long)blockIdx.x * rows_per_block;
+  long long r1 = r0 + rows_per_block;
+  if (r1 > M) r1 = M;
+  const double invM = 1.0 / (double)M;
+  for (int cq = cl; cq < CQ; cq += CT) {
+    const F4 mu = ld4(mean + 4 * cq), is = ld4(invstd + 4 * cq), ga = ld4(gamma + 4 * cq);
+    float m0[4], m1[4], sc[4];
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+      m0[e] = (float)(sums[4 * cq + e] * invM);
+      m1[e] = (float)(sums[C + 4 * cq + e] * invM);
+      sc[e] = ga.v[e] * is.v[e];
+    }
+    for (long long r = r0 + g; r < r1; r += G) {
+      const long long i = r * C + 4 * cq;
+      const F4 xv = ld4(x + i);
+      F4 d = ld4(dy + i);
+      if (relu) {
+        const F4 yv = ld4(y + i);
+#pragma unroll
+        for (int e = 0; e < 4; ++e) if (!(yv.v[e] > 0.f)) d.v[e] = 0.f;
+      }
+      F4 o;
+#pragma unroll
+      for (int e = 0; e < 4; ++e) o.v[e] = sc[e] * (d.v[e] - m0[e] - (xv.v[e] - mu.v[e]) * is.v[e] * m1[e]);
+      st4(dx + i, o);
+    }
+  }
+}
+
+inline bool al16p(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; }
+
+inline void rows_cfg(long long M, int per_sm, int& rows_per_block, int& blocks) {
+  long long b = (M + 15) / 16;                       // at least 16 rows per block
+  const long long cap = (long long)per_sm * rsg_num_sms();
+  if (b > cap) b = cap;
+  if (b < 1) b = 1;
+  rows_per_block = (int)((M + b - 1) / b);
+  blocks = (int)((M + rows_per_block - 1) / rows_per_block);
 }
 
 // ------------------------------------------------------------------------------------------------------------------
@@ -227,6 +374,18 @@ __global__ void __launch_bounds__(EW_THREADS) add_kernel(Ptr4 in, int nin, int r
   }
 }
 
+__global__ void __launch_bounds__(EW_THREADS) add4_kernel(Ptr4 in, int nin, int relu, long long n4, float* __restrict__ out) {
+  GRID_STRIDE(i, n4) {
+    float4 v = reinterpret_cast<const float4*>(in.p[0])[i];
+    for (int k = 1; k < nin; ++k) {
+      const float4 w = reinterpret_cast<const float4*>(in.p[k])[i];
+      v.x += w.x; v.y += w.y; v.z += w.z; v.w += w.w;
+    }
+    if (relu) { v.x = fmaxf(v.x, 0.f); v.y = fmaxf(v.y, 0.f); v.z = fmaxf(v.z, 0.f); v.w = fmaxf(v.w, 0.f); }
+    reinterpret_cast<float4*>(out)[i] = v;
+  }
+}
+
 // OP 0: dx = dy * [y > 0]            (ReLU backward, y = the ReLU output)
 // OP 1: y = sigmoid(x)               (a = x)
 // OP 2: dx = dy * y * (1 - y)        (a = dy, b = y)
@@ -236,19 +395,37 @@ __global__ void __launch_bounds__(EW_THREADS) add_kernel(Ptr4 in, int nin, int r
 // OP 6: out += a
 // OP 7: out = a * slope              (scale)
 template <int OP>
+__device__ __forceinline__ float ew_op(float a, float b, float o, float slope) {
+  if (OP == 0) return b > 0.f ? a : 0.f;
+  if (OP == 1) return 1.f / (1.f + expf(-a));
+  if (OP == 2) return a * b * (1.f - b);
+  if (OP == 3) return a > 0.f ? a : a * slope;
+  if (OP == 4) return b > 0.f ? a : a * slope;
+  if (OP == 5) return a * b;
+  if (OP == 6) return o + a;
+  return a * slope;
+}
+
+template <int OP>
 __global__ void __launch_bounds__(EW_THREADS) ew_kernel(const float* __restrict__ a, const float* __restrict__ b, float slope, long long n,
                                                         float* __restrict__ out) {
-  GRID_STRIDE(i, n) {
-    float v;
-    if (OP == 0) v = b[i] > 0.f ? a[i] : 0.f;
-    else if (OP == 1) v = 1.f / (1.f + expf(-a[i]));
-    else if (OP == 2) { const float yy = b[i]; v = a[i] * yy * (1.f - yy); }
-    else if (OP == 3) { const float xx = a[i]; v = xx > 0.f ? xx : xx * slope; }
-    else if (OP == 4) v = b[i] > 0.f ? a[i] : a[i] * slope;
-    else if (OP == 5) v = a[i] * b[i];
-    else if (OP == 6) v = out[i] + a[i];
-    else v = a[i] * slope;
-    out[i] = v;
+  constexpr bool NB = OP == 0 || OP == 2 || OP == 4 || OP == 5;
+  GRID_STRIDE(i, n) out[i] = ew_op<OP>(a[i], NB ? b[i] : 0.f, OP == 6 ? out[i] : 0.f, slope);
+}
+
+template <int OP>
+__global__ void __launch_bounds__(EW_THREADS) ew4_kernel(const float* __restrict__ a, const float* __restrict__ b, float slope, long long n4,
+                                                         float* __restrict__ out) {
+  constexpr bool NB = OP == 0 || OP == 2 || OP == 4 || OP == 5;
+  GRID_STRIDE(i, n4) {
+    const float4 av = reinterpret_cast<const float4*>(a)[i];
+    float4 bv = make_float4(0.f, 0.f, 0.f, 0.f), ov = bv;
+    if (NB) bv = reinterpret_cast<const float4*>(b)[i];
+    if (OP == 6) ov = reinterpret_cast<const float4*>(out)[i];
+    float4 r;
+    r.x = ew_op<OP>(av.x, bv.x, ov.x, slope); r.y = ew_op<OP>(av.y, bv.y, ov.y, slope);
+    r.z = ew_op<OP>(av.z, bv.z, ov.z, slope); r.w = ew_op<OP>(av.w, bv.w, ov.w, slope);
+    reinterpret_cast<float4*>(out)[i] = r;
   }
 }
 
@@ -557,12 +734,20 @@ extern "C" int rsg_train_bn_fwd(void* stream, const float* x, long long M, int C
                                 float* save_invstd, double* ws) {
   RSG_REQUIRE(x && y && gamma && beta && save_mean && save_invstd && ws && M > 0 && C > 0, "bn_fwd: bad arguments");
   RSG_CUDA(cudaMemsetAsync(ws, 0, 2 * (size_t)C * sizeof(double), ST));
+  const bool v4 = (C & 3) == 0 && al16p(x) && al16p(y) && al16p(gamma) && al16p(beta) && al16p(save_mean) && al16p(save_invstd);
   int rpb, blocks;
-  chan_reduce_cfg(M, rpb, blocks);
-  chan_reduce_kernel<0><<<blocks, EW_THREADS, 0, ST>>>(x, nullptr, nullptr, nullptr, nullptr, 0, M, C, rpb, ws);
+  const int yt = v4 ? ceil_div(C / 4, EW_THREADS) : ceil_div(C, EW_THREADS);
+  chan_reduce_cfg(M, rpb, blocks, yt);
+  if (v4) chan_reduce4_kernel<0><<<dim3(blocks, yt), EW_THREADS, 0, ST>>>(x, nullptr, nullptr, nullptr, nullptr, 0, M, C, rpb, ws);
+  else chan_reduce_kernel<0><<<dim3(blocks, yt), EW_THREADS, 0, ST>>>(x, nullptr, nullptr, nullptr, nullptr, 0, M, C, rpb, ws);
   bn_finalize_kernel<<<ceil_div(C, 128), 128, 0, ST>>>(ws, M, C, eps, momentum, save_mean, save_invstd, running_mean, running_var);
   const long long n = M * C;
-  bn_apply_kernel<<<ew_grid(n, 4), EW_THREADS, 0, ST>>>(x, save_mean, save_invstd, gamma, beta, relu, n, C, y);
+  if (v4) {
+    rows_cfg(M, 16, rpb, blocks);
+    bn_apply4_kernel<<<blocks, EW_THREADS, 0, ST>>>(x, save_mean, save_invstd, gamma, beta, relu, M, C, rpb, y);
+  } else {
+    bn_apply_kernel<<<ew_grid(n, 4), EW_THREADS, 0, ST>>>(x, save_mean, save_invstd, gamma, beta, relu, n, C, y);
+  }
   RSG_LAUNCH_CHECK();
   return RSG_OK;
 }
@@ -572,11 +757,20 @@ extern "C" int rsg_train_bn_bwd(void* stream, const float* x, const float* y, co
                                 double* ws) {
   RSG_REQUIRE(x && dy && gamma && save_mean && save_invstd && ws && M > 0 && C > 0 && (!relu || y), "bn_bwd: bad arguments");
   RSG_CUDA(cudaMemsetAsync(ws, 0, 2 * (size_t)C * sizeof(double), ST));
+  const bool v4 = (C & 3) == 0 && al16p(x) && al16p(dy) && (!relu || al16p(y)) && (!dx || al16p(dx)) && al16p(gamma) &&
+                  al16p(save_mean) && al16p(save_invstd);
   int rpb, blocks;
-  chan_reduce_cfg(M, rpb, blocks);
-  chan_reduce_kernel<1><<<blocks, EW_THREADS, 0, ST>>>(x, dy, y, save_mean, save_invstd, relu, M, C, rpb, ws);
+  const int yt = v4 ? ceil_div(C / 4, EW_THREADS) : ceil_div(C, EW_THREADS);
+  chan_reduce_cfg(M, rpb, blocks, yt);
+  if (v4) chan_reduce4_kernel<1><<<dim3(blocks, yt), EW_THREADS, 0, ST>>>(x, dy, y, save_mean, save_invstd, relu, M, C, rpb, ws);
+  else chan_reduce_kernel<1><<<dim3(blocks, yt), EW_THREADS, 0, ST>>>(x, dy, y, save_mean, save_invstd, relu, M, C, rpb, ws);
   const long long n = M * C;
-  bn_bwd_apply_kernel<<<ew_grid(n, 4), EW_THREADS, 0, ST>>>(x, dy, y, save_mean, save_invstd, gamma, ws, relu, n, C, M, dx, dgamma, dbeta);
+  if (v4) {
+    rows_cfg(M, 16, rpb, blocks);
+    bn_bwd_apply4_kernel<<<blocks, EW_THREADS, 0, ST>>>(x, dy, y, save_mean, save_invstd, gamma, ws, relu, M, C, rpb, dx, dgamma, dbeta);
+  } else {
+    bn_bwd_apply_kernel<<<ew_grid(n, 4), EW_THREADS, 0, ST>>>(x, dy, y, save_mean, save_invstd, gamma, ws, relu, n, C, M, dx, dgamma, dbeta);
+  }
   RSG_LAUNCH_CHECK();
   return RSG_OK;
 }
@@ -585,8 +779,9 @@ extern "C" int rsg_train_colsum(void* stream, const float* x, long long M, int C
   RSG_REQUIRE(x && out && ws && M > 0 && C > 0, "colsum: bad arguments");
   RSG_CUDA(cudaMemsetAsync(ws, 0, (size_t)C * sizeof(double), ST));
   int rpb, blocks;
-  chan_reduce_cfg(M, rpb, blocks);
-  chan_reduce_kernel<2><<<blocks, EW_THREADS, 0, ST>>>(x, nullptr, nullptr, nullptr, nullptr, 0, M, C, rpb, ws);
+  const int yt = ceil_div(C, EW_THREADS);
+  chan_reduce_cfg(M, rpb, blocks, yt);
+  chan_reduce_kernel<2><<<dim3(blocks, yt), EW_THREADS, 0, ST>>>(x, nullptr, nullptr, nullptr, nullptr, 0, M, C, rpb, ws);
   d2f_kernel<<<ceil_div(C, 128), 128, 0, ST>>>(ws, 1.f, C, accumulate, out);
   RSG_LAUNCH_CHECK();
   return RSG_OK;
@@ -612,26 +807,33 @@ extern "C" int rsg_train_add(void* stream, int nin, const float* const* in, int 
   RSG_REQUIRE(nin >= 1 && nin <= 4 && in && out, "add: 1..4 inputs");
   if (n == 0) return RSG_OK;
   Ptr4 q;
-  for (int k = 0; k < 4; ++k) q.p[k] = k < nin ? in[k] : nullptr;
-  add_kernel<<<ew_grid(n, 4), EW_THREADS, 0, ST>>>(q, nin, relu, n, out);
+  bool v4 = (n & 3) == 0 && al16p(out);
+  for (int k = 0; k < 4; ++k) { q.p[k] = k < nin ? in[k] : nullptr; v4 = v4 && al16p(q.p[k]); }
+  if (v4) add4_kernel<<<ew_grid(n / 4, 2), EW_THREADS, 0, ST>>>(q, nin, relu, n / 4, out);
+  else add_kernel<<<ew_grid(n, 4), EW_THREADS, 0, ST>>>(q, nin, relu, n, out);
   RSG_LAUNCH_CHECK();
   return RSG_OK;
+}
+
+template <int OP>
+static void ew_launch(cudaStream_t s, const float* a, const float* b, float slope, long long n, float* out) {
+  if ((n & 3) == 0 && al16p(a) && al16p(b) && al16p(out)) ew4_kernel<OP><<<ew_grid(n / 4, 2), EW_THREADS, 0, s>>>(a, b, slope, n / 4, out);
+  else ew_kernel<OP><<<ew_grid(n, 4), EW_THREADS, 0, s>>>(a, b, slope, n, out);
 }
 
 extern "C" int rsg_train_ew(void* stream, int op, const float* a, const float* b, float slope, long long n, float* out) {
   RSG_REQUIRE(a && out && op >= 0 && op <= 7, "ew: bad arguments");
   RSG_REQUIRE(b || !(op == 0 || op == 2 || op == 4 || op == 5), "ew: op %d needs a second operand", op);
   if (n == 0) return RSG_OK;
-  const int g = ew_grid(n, 4);
   switch (op) {
-    case 0: ew_kernel<0><<<g, EW_THREADS, 0, ST>>>(a, b, slope, n, out); break;
-    case 1: ew_kernel<1><<<g, EW_THREADS, 0, ST>>>(a, b, slope, n, out); break;
-    case 2: ew_kernel<2><<<g, EW_THREADS, 0, ST>>>(a, b, slope, n, out); break;
-    case 3: ew_kernel<3><<<g, EW_THREADS, 0, ST>>>(a, b, slope, n, out); break;
-    case 4: ew_kernel<4><<<g, EW_THREADS, 0, ST>>>(a, b, slope, n, out); break;
-    case 5: ew_kernel<5><<<g, EW_THREADS, 0, ST>>>(a, b, slope, n, out); break;
-    case 6: ew_kernel<6><<<g, EW_THREADS, 0, ST>>>(a, b, slope, n, out); break;
-    default: ew_kernel<7><<<g, EW_THREADS, 0, ST>>>(a, b, slope, n, out); break;
+    case 0: ew_launch<0>(ST, a, b, slope, n, out); break;
+    case 1: ew_launch<1>(ST, a, b, slope, n, out); break;
+    case 2: ew_launch<2>(ST, a, b, slope, n, out); break;
+    case 3: ew_launch<3>(ST, a, b, slope, n, out); break;
+    case 4: ew_launch<4>(ST, a, b, slope, n, out); break;
+    case 5: ew_launch<5>(ST, a, b, slope, n, out); break;
+    case 6: ew_launch<6>(ST, a, b, slope, n, out); break;
+    default: ew_launch<7>(ST, a, b, slope, n, out); break;
   }
   RSG_LAUNCH_CHECK();
   return RSG_OK;

@@ -110,18 +110,26 @@ __global__ void __launch_bounds__(T5_THREADS) gemm_tf32_tc5_kernel(const T5P p) 
     }
     const int nb = p.n_mma >> 4;                                // B rows per thread: rr + 16 j, j < nb
     uint32_t s = 0, ph = 0;
+    const float* srcp[8];                                       // source row of this thread's 8 rows for the current tap
+    int tap = 0, ch = 0;
     for (int it = 0; it < niter; ++it) {
-      const int tap = it / kchunks, c0 = (it - tap * kchunks) * T5_BK, k = c0 + q * 4;
+      if (ch == 0) {                                            // a new tap: the gather is the same for all its channel chunks
+        const int dy = tap / p.kw, dx = tap - dy * p.kw;
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          long long src = -1;
+          if ((rok >> j) & 1u) src = p.mode == 0 ? (long long)rn[j] : t5_gather_row(p.mode, rn[j], ry[j], rx[j], dy, dx, p.Ha, p.Wa, p.stride, p.pad);
+          srcp[j] = src < 0 ? nullptr : Ap + src * p.lda + q * 4;
+        }
+      }
+      const int c0 = ch * T5_BK, k = c0 + q * 4;
       const bool kok = k < p.Ca;
       mbar_wait(BAR(T5_STAGES + s), ph ^ 1u);
       const uint32_t sa = sbase + s * p.stage_bytes + (uint32_t)q * p.a_plane + (uint32_t)rr * 16u;
-      const int dy = tap / p.kw, dx = tap - dy * p.kw;
 #pragma unroll
       for (int j = 0; j < 8; ++j) {
-        long long src = -1;
-        if ((rok >> j) & 1u) src = p.mode == 0 ? (long long)rn[j] : t5_gather_row(p.mode, rn[j], ry[j], rx[j], dy, dx, p.Ha, p.Wa, p.stride, p.pad);
-        const bool ok = kok && src >= 0;
-        cp_async16(sa + (uint32_t)j * 256u, ok ? (const void*)(Ap + src * p.lda + k) : (const void*)Ap, ok ? 16u : 0u);
+        const bool ok = kok && srcp[j] != nullptr;
+        cp_async16(sa + (uint32_t)j * 256u, ok ? (const void*)(srcp[j] + c0) : (const void*)Ap, ok ? 16u : 0u);
       }
       const uint32_t sb = sbase + s * p.stage_bytes + T5_KG * p.a_plane + (uint32_t)q * p.b_plane + (uint32_t)rr * 16u;
       const float* Bt = Bp + (long long)tap * p.tapB + k;
@@ -137,6 +145,7 @@ __global__ void __launch_bounds__(T5_THREADS) gemm_tf32_tc5_kernel(const T5P p) 
         mbar_arrive(BAR((it - T5_LAG) % T5_STAGES));
       }
       if (++s == T5_STAGES) { s = 0; ph ^= 1u; }
+      if (++ch == kchunks) { ch = 0; ++tap; }
     }
     asm volatile("cp.async.wait_group 0;" ::: "memory");
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
