@@ -284,11 +284,11 @@ struct WgradP {
   int vecX, vecY, precise;
 };
 
-constexpr int WG_T = 64, WG_PITCH = WG_T + 8;
+constexpr int WG_T = 64, WG_PITCH = WG_T + 8, WG_PX = 64;      // 64 x 64 output tile, 64-pixel reduction chunks
 
-__global__ void __launch_bounds__(GM_THREADS) wgrad_kernel(const WgradP p) {
-  __shared__ __align__(16) float Xs[GM_BK * WG_PITCH];
-  __shared__ __align__(16) float Ys[GM_BK * WG_PITCH];
+__global__ void __launch_bounds__(GM_THREADS, 2) wgrad_kernel(const WgradP p) {
+  __shared__ __align__(16) float Xs[WG_PX * WG_PITCH];
+  __shared__ __align__(16) float Ys[WG_PX * WG_PITCH];
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, g = lane >> 2, t = lane & 3;
   const int wm = warp >> 2, wn = warp & 3;            // 2 (ci) x 4 (co) warps: 32 x 16 each
   const int ci0 = (blockIdx.x / p.tiles_n) * WG_T, co0 = (blockIdx.x % p.tiles_n) * WG_T;
@@ -296,7 +296,7 @@ __global__ void __launch_bounds__(GM_THREADS) wgrad_kernel(const WgradP p) {
   const int mb = blockIdx.z * p.rows_per_split;
   const int me = min(p.M, mb + p.rows_per_split);
   const int hw = p.Hc * p.Wc;
-  const int kr = tid >> 4, q4 = (tid & 15) * 4;       // staged element: pixel kr of the chunk, channels q4 .. q4+3
+  const int kr = tid >> 4, q4 = (tid & 15) * 4;       // staged elements: pixels kr + 16 j of the chunk, channels q4 .. q4+3
   float acc[2][2][4];
 #pragma unroll
   for (int i = 0; i < 2; ++i)
@@ -304,29 +304,35 @@ __global__ void __launch_bounds__(GM_THREADS) wgrad_kernel(const WgradP p) {
     for (int j = 0; j < 2; ++j)
 #pragma unroll
       for (int k = 0; k < 4; ++k) acc[i][j][k] = 0.f;
-  float4 rx, ry;
+  float4 rx[4], ry[4];
   auto fetch = [&](int mc) {
-    const int m = mc + kr;
-    rx = make_float4(0.f, 0.f, 0.f, 0.f);
-    ry = rx;
-    if (m < me) {
-      long long src = m;
-      if (p.mode != 0) {
-        const int n = m / hw, rem = m - n * hw, y = rem / p.Wc, x = rem - y * p.Wc;
-        src = gather_row(p.mode, n, y, x, dy, dx, p.Ha, p.Wa, p.stride, p.pad);
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const int m = mc + kr + 16 * j;
+      rx[j] = make_float4(0.f, 0.f, 0.f, 0.f);
+      ry[j] = rx[j];
+      if (m < me) {
+        long long src = m;
+        if (p.mode != 0) {
+          const int n = m / hw, rem = m - n * hw, y = rem / p.Wc, x = rem - y * p.Wc;
+          src = gather_row(p.mode, n, y, x, dy, dx, p.Ha, p.Wa, p.stride, p.pad);
+        }
+        if (src >= 0) rx[j] = load4(p.X + src * p.ldx + ci0 + q4, p.Ca - (ci0 + q4), p.vecX != 0);
+        ry[j] = load4(p.dY + (long long)m * p.ldy + co0 + q4, p.Nc - (co0 + q4), p.vecY != 0);
       }
-      if (src >= 0) rx = load4(p.X + src * p.ldx + ci0 + q4, p.Ca - (ci0 + q4), p.vecX != 0);
-      ry = load4(p.dY + (long long)m * p.ldy + co0 + q4, p.Nc - (co0 + q4), p.vecY != 0);
     }
   };
   if (mb < me) fetch(mb);
-  for (int mc = mb; mc < me; mc += GM_BK) {
-    *reinterpret_cast<float4*>(&Xs[kr * WG_PITCH + q4]) = rx;
-    *reinterpret_cast<float4*>(&Ys[kr * WG_PITCH + q4]) = ry;
-    __syncthreads();
-    if (mc + GM_BK < me) fetch(mc + GM_BK);
+  for (int mc = mb; mc < me; mc += WG_PX) {
 #pragma unroll
-    for (int k8 = 0; k8 < GM_BK / 8; ++k8) {
+    for (int j = 0; j < 4; ++j) {
+      *reinterpret_cast<float4*>(&Xs[(kr + 16 * j) * WG_PITCH + q4]) = rx[j];
+      *reinterpret_cast<float4*>(&Ys[(kr + 16 * j) * WG_PITCH + q4]) = ry[j];
+    }
+    __syncthreads();
+    if (mc + WG_PX < me) fetch(mc + WG_PX);
+#pragma unroll
+    for (int k8 = 0; k8 < WG_PX / 8; ++k8) {
       float af[2][4], bfr[2][2];
 #pragma unroll
       for (int mt = 0; mt < 2; ++mt) {                // A(row = ci, col = pixel) = Xs[pixel][ci]
@@ -398,7 +404,7 @@ __global__ void __launch_bounds__(GM_THREADS) wgrad_kernel(const WgradP p) {
 
 }  // namespace
 
-// train_tc5.cu: the tcgen05 kind::tf32 kernel (K-major B only)
+// train_tc5.cu: the tcgen05 kind::tf32 kernels (K-major B only)
 int train_tc5_supported(const float* A, const float* B, int Ca, int lda, int ldb, long long sA, long long sB, long long tapB,
                         int transA, int transB, int precise);
 int train_tc5_launch(cudaStream_t s, const float* A, const float* B, float* C, const float* bias, int M, int Nc, int Ca, int lda,
@@ -618,7 +624,7 @@ extern "C" int rsg_train_wgrad(void* stream, const float* X, const float* dY, fl
   if (want < 1) want = 1;
   if (want > 65535) want = 65535;
   int rows = ceil_div(M, want);
-  rows = (rows + GM_BK - 1) / GM_BK * GM_BK;
+  rows = (rows + WG_PX - 1) / WG_PX * WG_PX;
   p.rows_per_split = rows;
   const int ksplit = ceil_div(M, rows);
   wgrad_kernel<<<dim3((unsigned)(tiles_m * p.tiles_n), (unsigned)p.taps, (unsigned)ksplit), GM_THREADS, 0, (cudaStream_t)stream>>>(p);
