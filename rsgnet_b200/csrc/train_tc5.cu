@@ -393,6 +393,7 @@ __global__ void __launch_bounds__(T5_THREADS) conv3x3_tf32_tc5_kernel(const T5F 
   }
 }
 
+
 }  // namespace
 
 // 1 when the tcgen05 kernel covers this call of rsg_train_gemm (else the mma.sync kernel runs)
@@ -473,3 +474,4 @@ int train_tc5_launch(cudaStream_t s, const float* A, const float* B, float* C, c
   RSG_LAUNCH_CHECK();
   return RSG_OK;
 }
+
