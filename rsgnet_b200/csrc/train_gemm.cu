@@ -405,6 +405,107 @@ __global__ void __launch_bounds__(GM_THREADS, 2) wgrad_kernel(const WgradP p) {
       }
 }
 
+
+// The same tile with a 3-stage cp.async ring (aligned operands, Ca % 4 == Nc % 4 == 0): the register-staged version above keeps
+// ONE chunk of global loads in flight per thread and is bound by that latency, not by barriers or issue slots.
+constexpr int WGA_STAGES = 3;
+
+__device__ __forceinline__ void wg_cp16(float* dst, const float* src, bool ok) {
+  const uint32_t d = (uint32_t)__cvta_generic_to_shared(dst);
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 16, %2;" ::"r"(d), "l"(src), "r"(ok ? 16u : 0u) : "memory");
+}
+
+__global__ void __launch_bounds__(GM_THREADS, 2) wgrad_async_kernel(const WgradP p) {
+  extern __shared__ __align__(16) float wg_smem[];                // [stage][X | Y][WG_PX][WG_PITCH]
+  constexpr int TILE = WG_PX * WG_PITCH;
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, g = lane >> 2, t = lane & 3;
+  const int wm = warp >> 2, wn = warp & 3;
+  const int ci0 = (blockIdx.x / p.tiles_n) * WG_T, co0 = (blockIdx.x % p.tiles_n) * WG_T;
+  const int tap = blockIdx.y, dy = tap / p.kw, dx = tap % p.kw;
+  const int mb = blockIdx.z * p.rows_per_split;
+  const int me = min(p.M, mb + p.rows_per_split);
+  const int hw = p.Hc * p.Wc;
+  const int kr = tid >> 4, q4 = (tid & 15) * 4;
+  const bool xok = ci0 + q4 < p.Ca, yok = co0 + q4 < p.Nc;
+  const int nchunk = me > mb ? (me - mb + WG_PX - 1) / WG_PX : 0;
+  float acc[2][2][4];
+#pragma unroll
+  for (int i = 0; i < 2; ++i)
+#pragma unroll
+    for (int j = 0; j < 2; ++j)
+#pragma unroll
+      for (int k = 0; k < 4; ++k) acc[i][j][k] = 0.f;
+  auto issue = [&](int c) {
+    if (c < nchunk) {
+      float* Xs = wg_smem + (c % WGA_STAGES) * 2 * TILE;
+      float* Ys = Xs + TILE;
+      const int mc = mb + c * WG_PX;
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const int m = mc + kr + 16 * j;
+        long long src = -1;
+        if (m < me) {
+          src = m;
+          if (p.mode != 0) {
+            const int n = m / hw, rem = m - n * hw, y = rem / p.Wc, x = rem - y * p.Wc;
+            src = gather_row(p.mode, n, y, x, dy, dx, p.Ha, p.Wa, p.stride, p.pad);
+          }
+        }
+        wg_cp16(&Xs[(kr + 16 * j) * WG_PITCH + q4], src >= 0 && xok ? p.X + src * p.ldx + ci0 + q4 : p.X, src >= 0 && xok);
+        wg_cp16(&Ys[(kr + 16 * j) * WG_PITCH + q4], m < me && yok ? p.dY + (long long)m * p.ldy + co0 + q4 : p.dY, m < me && yok);
+      }
+    }
+    asm volatile("cp.async.commit_group;" ::: "memory");
+  };
+  issue(0);
+  issue(1);
+  for (int c = 0; c < nchunk; ++c) {
+    asm volatile("cp.async.wait_group 1;" ::: "memory");
+    __syncthreads();                                             // chunk c has landed for everyone; chunk c - 1 is consumed
+    issue(c + 2);
+    const float* Xs = wg_smem + (c % WGA_STAGES) * 2 * TILE;
+    const float* Ys = Xs + TILE;
+#pragma unroll
+    for (int k8 = 0; k8 < WG_PX / 8; ++k8) {
+      uint32_t ah[2][4], bh[2][2];
+#pragma unroll
+      for (int mt = 0; mt < 2; ++mt) {
+        const float* a = &Xs[(k8 * 8 + t) * WG_PITCH + wm * 32 + mt * 16 + g];
+        ah[mt][0] = to_tf32(a[0]);
+        ah[mt][1] = to_tf32(a[8]);
+        ah[mt][2] = to_tf32(a[4 * WG_PITCH]);
+        ah[mt][3] = to_tf32(a[4 * WG_PITCH + 8]);
+      }
+#pragma unroll
+      for (int nt = 0; nt < 2; ++nt) {
+        const float* b = &Ys[(k8 * 8 + t) * WG_PITCH + wn * 16 + nt * 8 + g];
+        bh[nt][0] = to_tf32(b[0]);
+        bh[nt][1] = to_tf32(b[4 * WG_PITCH]);
+      }
+#pragma unroll
+      for (int mt = 0; mt < 2; ++mt)
+#pragma unroll
+        for (int nt = 0; nt < 2; ++nt) mma_tf32(acc[mt][nt], ah[mt], bh[nt]);
+    }
+  }
+  asm volatile("cp.async.wait_group 0;" ::: "memory");
+  float* W = p.dW + (long long)tap * p.Ca * p.Nc;
+#pragma unroll
+  for (int mt = 0; mt < 2; ++mt)
+#pragma unroll
+    for (int nt = 0; nt < 2; ++nt)
+#pragma unroll
+      for (int h = 0; h < 2; ++h) {
+        const int ci = ci0 + wm * 32 + mt * 16 + g + 8 * h;
+        if (ci >= p.Ca) continue;
+#pragma unroll
+        for (int e = 0; e < 2; ++e) {
+          const int co = co0 + wn * 16 + nt * 8 + 2 * t + e;
+          if (co < p.Nc) atomicAdd(W + (long long)ci * p.Nc + co, acc[mt][nt][2 * h + e]);
+        }
+      }
+}
+
 }  // namespace
 
 // train_tc5.cu: the tcgen05 kind::tf32 kernels (K-major B only)
@@ -630,7 +731,18 @@ extern "C" int rsg_train_wgrad(void* stream, const float* X, const float* dY, fl
   rows = (rows + WG_PX - 1) / WG_PX * WG_PX;
   p.rows_per_split = rows;
   const int ksplit = ceil_div(M, rows);
-  wgrad_kernel<<<dim3((unsigned)(tiles_m * p.tiles_n), (unsigned)p.taps, (unsigned)ksplit), GM_THREADS, 0, (cudaStream_t)stream>>>(p);
+  const dim3 grid((unsigned)(tiles_m * p.tiles_n), (unsigned)p.taps, (unsigned)ksplit);
+  if (!p.precise && p.vecX && p.vecY && Ca % 4 == 0 && Nc % 4 == 0) {
+    const size_t smem = (size_t)WGA_STAGES * 2 * WG_PX * WG_PITCH * sizeof(float);
+    static DeviceOnce once;
+    if (once.first()) {
+      RSG_CUDA(cudaFuncSetAttribute(wgrad_async_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+      once.done();
+    }
+    wgrad_async_kernel<<<grid, GM_THREADS, smem, (cudaStream_t)stream>>>(p);
+  } else {
+    wgrad_kernel<<<grid, GM_THREADS, 0, (cudaStream_t)stream>>>(p);
+  }
   RSG_LAUNCH_CHECK();
   return RSG_OK;
 }
