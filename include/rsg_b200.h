@@ -318,16 +318,18 @@ int rsg_train_wgrad(void* stream, const float* X, const float* dY, float* dW, in
 
 /* BatchNorm over the rows of x [M, C] with batch statistics (torch batch_norm, training=True): y = (x - mean) * invstd *
  * gamma + beta (+ ReLU); running_mean / running_var (may be NULL) are updated with `momentum`, running_var with the
- * unbiased variance.  save_mean / save_invstd [C] feed the backward pass; ws = 2*C doubles of scratch. */
+ * unbiased variance.  save_mean / save_invstd [C] feed the backward pass.  ws = 3*C + 4 doubles of scratch that must be ZERO on entry and is
+ * left zero (the last reduction block finalizes the statistics and cleans up: no memset / finalize launches). */
 int rsg_train_bn_fwd(void* stream, const float* x, long long M, int C, const float* gamma, const float* beta, float eps,
                      float momentum, float* running_mean, float* running_var, int relu, float* y, float* save_mean,
                      float* save_invstd, double* ws);
 /* dx (may be NULL) = gamma * invstd * (dy' - mean(dy') - xhat * mean(dy' * xhat)), dgamma += sum dy' * xhat, dbeta += sum dy',
- * with dy' = dy * [y > 0] when relu (y = the forward output). */
+ * with dy' = dy * [y > 0] when relu (y = the forward output).  ws as for rsg_train_bn_fwd. */
 int rsg_train_bn_bwd(void* stream, const float* x, const float* y, const float* dy, long long M, int C, const float* gamma,
                      const float* save_mean, const float* save_invstd, int relu, float* dx, float* dgamma, float* dbeta,
                      double* ws);
-/* out[c] (+)= sum over the M rows of x[m][c]  (bias gradients; backward of a batch broadcast).  ws = C doubles. */
+/* out[c] (+)= sum over the M rows of x[m][c]  (bias gradients; backward of a batch broadcast).  ws = C doubles (cleared
+ * before and after use). */
 int rsg_train_colsum(void* stream, const float* x, long long M, int C, float* out, int accumulate, double* ws);
 
 /* GroupNorm(G, C) over x [B, S, C] (association.py:243-246); mean / rstd are [B*G]. */

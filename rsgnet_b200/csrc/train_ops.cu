@@ -150,11 +150,21 @@ struct F4 { float v[4]; };
 __device__ __forceinline__ F4 ld4(const float* p) { const float4 t = *reinterpret_cast<const float4*>(p); return F4{{t.x, t.y, t.z, t.w}}; }
 __device__ __forceinline__ void st4(float* p, const F4& a) { *reinterpret_cast<float4*>(p) = make_float4(a.v[0], a.v[1], a.v[2], a.v[3]); }
 
+// What the LAST block of a channel reduction does with the finished sums (ticket counter at out[2 C]): the BatchNorm
+// finalize step (forward) or the means for the backward apply kernel + the dgamma / dbeta accumulation (backward); it then
+// zeroes the sums and the ticket, so the scratch is zero on entry of the next reduction and no memset / finalize launch is
+// needed (a BN is 2 launches instead of 4 forward and 3 backward: the step has 604 of them, each a dependent ~3 us launch).
+struct BnFin {
+  float eps, momentum;
+  float* mean_out; float* invstd_out; float* running_mean; float* running_var;     // KIND 0
+  float* fsum; float* dgamma; float* dbeta;                                        // KIND 1
+};
+
 template <int KIND>      // 0: sum x, sum x^2;  1: sum dy', sum dy' xhat
 __global__ void __launch_bounds__(EW_THREADS) chan_reduce4_kernel(const float* __restrict__ x, const float* __restrict__ dy,
                                                                   const float* __restrict__ y, const float* __restrict__ mean,
                                                                   const float* __restrict__ invstd, int relu, long long M, int C,
-                                                                  int rows_per_block, double* __restrict__ out) {
+                                                                  int rows_per_block, double* out, const BnFin fin) {
   __shared__ double red[2][4][EW_THREADS];
   const int CQ = C >> 2, CT = CQ < EW_THREADS ? CQ : EW_THREADS, G = EW_THREADS / CT;
   const int tid = threadIdx.x, g = tid / CT, cl = tid - g * CT;
@@ -201,6 +211,39 @@ __global__ void __launch_bounds__(EW_THREADS) chan_reduce4_kernel(const float* _
     }
     __syncthreads();
   }
+  // ---- ticket: the last block to arrive finalizes and cleans the scratch
+  __shared__ int is_last;
+  __threadfence();
+  if (tid == 0) {
+    const unsigned t = atomicAdd(reinterpret_cast<unsigned*>(out + 2 * C), 1u);
+    is_last = t == gridDim.x * gridDim.y - 1;
+  }
+  __syncthreads();
+  if (!is_last) return;
+  __threadfence();
+  for (int c = tid; c < C; c += EW_THREADS) {
+    const double s0 = __ldcg(out + c), s1 = __ldcg(out + C + c);
+    if (KIND == 0) {
+      const double mu = s0 / (double)M;
+      double var = s1 / (double)M - mu * mu;
+      if (var < 0.0) var = 0.0;
+      fin.mean_out[c] = (float)mu;
+      fin.invstd_out[c] = (float)(1.0 / sqrt(var + (double)fin.eps));
+      if (fin.running_mean) fin.running_mean[c] = (1.f - fin.momentum) * fin.running_mean[c] + fin.momentum * (float)mu;
+      if (fin.running_var) {
+        const double unb = M > 1 ? var * (double)M / (double)(M - 1) : var;
+        fin.running_var[c] = (1.f - fin.momentum) * fin.running_var[c] + fin.momentum * (float)unb;
+      }
+    } else {
+      fin.fsum[c] = (float)(s0 / (double)M);
+      fin.fsum[C + c] = (float)(s1 / (double)M);
+      if (fin.dbeta) fin.dbeta[c] += (float)s0;
+      if (fin.dgamma) fin.dgamma[c] += (float)s1;
+    }
+    out[c] = 0.0;
+    out[C + c] = 0.0;
+  }
+  if (tid == 0) *reinterpret_cast<unsigned*>(out + 2 * C) = 0u;
 }
 
 __global__ void __launch_bounds__(EW_THREADS) bn_apply4_kernel(const float* __restrict__ x, const float* __restrict__ mean,
@@ -231,30 +274,22 @@ __global__ void __launch_bounds__(EW_THREADS) bn_apply4_kernel(const float* __re
 __global__ void __launch_bounds__(EW_THREADS) bn_bwd_apply4_kernel(const float* __restrict__ x, const float* __restrict__ dy,
                                                                    const float* __restrict__ y, const float* __restrict__ mean,
                                                                    const float* __restrict__ invstd, const float* __restrict__ gamma,
-                                                                   const double* __restrict__ sums, int relu, long long M, int C,
-                                                                   int rows_per_block, float* __restrict__ dx, float* __restrict__ dgamma,
-                                                                   float* __restrict__ dbeta) {
-  if (blockIdx.x == 0) {
-    for (int c = threadIdx.x; c < C; c += blockDim.x) {
-      if (dbeta) dbeta[c] += (float)sums[c];
-      if (dgamma) dgamma[c] += (float)sums[C + c];
-    }
-  }
-  if (!dx) return;
+                                                                   const float* __restrict__ fsum, int relu, long long M, int C,
+                                                                   int rows_per_block, float* __restrict__ dx) {
   const int CQ = C >> 2, CT = CQ < EW_THREADS ? CQ : EW_THREADS, G = EW_THREADS / CT;
   const int tid = threadIdx.x, g = tid / CT, cl = tid - g * CT;
   if (g >= G) return;
   const long long r0 = (long long)blockIdx.x * rows_per_block;
   long long r1 = r0 + rows_per_block;
   if (r1 > M) r1 = M;
-  const double invM = 1.0 / (double)M;
   for (int cq = cl; cq < CQ; cq += CT) {
     const F4 mu = ld4(mean + 4 * cq), is = ld4(invstd + 4 * cq), ga = ld4(gamma + 4 * cq);
+    const F4 f0 = ld4(fsum + 4 * cq), f1 = ld4(fsum + C + 4 * cq);
     float m0[4], m1[4], sc[4];
 #pragma unroll
     for (int e = 0; e < 4; ++e) {
-      m0[e] = (float)(sums[4 * cq + e] * invM);
-      m1[e] = (float)(sums[C + 4 * cq + e] * invM);
+      m0[e] = f0.v[e];
+      m1[e] = f1.v[e];
       sc[e] = ga.v[e] * is.v[e];
     }
     for (long long r = r0 + g; r < r1; r += G) {
@@ -729,24 +764,31 @@ __global__ void __launch_bounds__(EW_THREADS) adam_kernel(float* __restrict__ p,
 
 // ------------------------------------------------------------------------------------------------------------------
 // C ABI
+// Scratch contract of the BatchNorm entry points: ws holds 3 C + 4 doubles and is ZERO on entry of the float4 path, which leaves
+// it zero (the last reduction block cleans up); the scalar fallback and rsg_train_colsum clear what they use before and after.
 extern "C" int rsg_train_bn_fwd(void* stream, const float* x, long long M, int C, const float* gamma, const float* beta, float eps,
                                 float momentum, float* running_mean, float* running_var, int relu, float* y, float* save_mean,
                                 float* save_invstd, double* ws) {
   RSG_REQUIRE(x && y && gamma && beta && save_mean && save_invstd && ws && M > 0 && C > 0, "bn_fwd: bad arguments");
-  RSG_CUDA(cudaMemsetAsync(ws, 0, 2 * (size_t)C * sizeof(double), ST));
   const bool v4 = (C & 3) == 0 && al16p(x) && al16p(y) && al16p(gamma) && al16p(beta) && al16p(save_mean) && al16p(save_invstd);
   int rpb, blocks;
   const int yt = v4 ? ceil_div(C / 4, EW_THREADS) : ceil_div(C, EW_THREADS);
   chan_reduce_cfg(M, rpb, blocks, yt);
-  if (v4) chan_reduce4_kernel<0><<<dim3(blocks, yt), EW_THREADS, 0, ST>>>(x, nullptr, nullptr, nullptr, nullptr, 0, M, C, rpb, ws);
-  else chan_reduce_kernel<0><<<dim3(blocks, yt), EW_THREADS, 0, ST>>>(x, nullptr, nullptr, nullptr, nullptr, 0, M, C, rpb, ws);
-  bn_finalize_kernel<<<ceil_div(C, 128), 128, 0, ST>>>(ws, M, C, eps, momentum, save_mean, save_invstd, running_mean, running_var);
   const long long n = M * C;
   if (v4) {
+    BnFin fin;
+    memset(&fin, 0, sizeof(fin));
+    fin.eps = eps; fin.momentum = momentum; fin.mean_out = save_mean; fin.invstd_out = save_invstd;
+    fin.running_mean = running_mean; fin.running_var = running_var;
+    chan_reduce4_kernel<0><<<dim3(blocks, yt), EW_THREADS, 0, ST>>>(x, nullptr, nullptr, nullptr, nullptr, 0, M, C, rpb, ws, fin);
     rows_cfg(M, 16, rpb, blocks);
     bn_apply4_kernel<<<blocks, EW_THREADS, 0, ST>>>(x, save_mean, save_invstd, gamma, beta, relu, M, C, rpb, y);
   } else {
+    RSG_CUDA(cudaMemsetAsync(ws, 0, 2 * (size_t)C * sizeof(double), ST));
+    chan_reduce_kernel<0><<<dim3(blocks, yt), EW_THREADS, 0, ST>>>(x, nullptr, nullptr, nullptr, nullptr, 0, M, C, rpb, ws);
+    bn_finalize_kernel<<<ceil_div(C, 128), 128, 0, ST>>>(ws, M, C, eps, momentum, save_mean, save_invstd, running_mean, running_var);
     bn_apply_kernel<<<ew_grid(n, 4), EW_THREADS, 0, ST>>>(x, save_mean, save_invstd, gamma, beta, relu, n, C, y);
+    RSG_CUDA(cudaMemsetAsync(ws, 0, 2 * (size_t)C * sizeof(double), ST));
   }
   RSG_LAUNCH_CHECK();
   return RSG_OK;
@@ -756,20 +798,27 @@ extern "C" int rsg_train_bn_bwd(void* stream, const float* x, const float* y, co
                                 const float* save_mean, const float* save_invstd, int relu, float* dx, float* dgamma, float* dbeta,
                                 double* ws) {
   RSG_REQUIRE(x && dy && gamma && save_mean && save_invstd && ws && M > 0 && C > 0 && (!relu || y), "bn_bwd: bad arguments");
-  RSG_CUDA(cudaMemsetAsync(ws, 0, 2 * (size_t)C * sizeof(double), ST));
   const bool v4 = (C & 3) == 0 && al16p(x) && al16p(dy) && (!relu || al16p(y)) && (!dx || al16p(dx)) && al16p(gamma) &&
                   al16p(save_mean) && al16p(save_invstd);
   int rpb, blocks;
   const int yt = v4 ? ceil_div(C / 4, EW_THREADS) : ceil_div(C, EW_THREADS);
   chan_reduce_cfg(M, rpb, blocks, yt);
-  if (v4) chan_reduce4_kernel<1><<<dim3(blocks, yt), EW_THREADS, 0, ST>>>(x, dy, y, save_mean, save_invstd, relu, M, C, rpb, ws);
-  else chan_reduce_kernel<1><<<dim3(blocks, yt), EW_THREADS, 0, ST>>>(x, dy, y, save_mean, save_invstd, relu, M, C, rpb, ws);
   const long long n = M * C;
   if (v4) {
-    rows_cfg(M, 16, rpb, blocks);
-    bn_bwd_apply4_kernel<<<blocks, EW_THREADS, 0, ST>>>(x, dy, y, save_mean, save_invstd, gamma, ws, relu, M, C, rpb, dx, dgamma, dbeta);
+    BnFin fin;
+    memset(&fin, 0, sizeof(fin));
+    fin.fsum = reinterpret_cast<float*>(ws + 2 * (size_t)C + 2);              // 2 C floats behind the sums and the ticket
+    fin.dgamma = dgamma; fin.dbeta = dbeta;
+    chan_reduce4_kernel<1><<<dim3(blocks, yt), EW_THREADS, 0, ST>>>(x, dy, y, save_mean, save_invstd, relu, M, C, rpb, ws, fin);
+    if (dx) {
+      rows_cfg(M, 16, rpb, blocks);
+      bn_bwd_apply4_kernel<<<blocks, EW_THREADS, 0, ST>>>(x, dy, y, save_mean, save_invstd, gamma, fin.fsum, relu, M, C, rpb, dx);
+    }
   } else {
+    RSG_CUDA(cudaMemsetAsync(ws, 0, 2 * (size_t)C * sizeof(double), ST));
+    chan_reduce_kernel<1><<<dim3(blocks, yt), EW_THREADS, 0, ST>>>(x, dy, y, save_mean, save_invstd, relu, M, C, rpb, ws);
     bn_bwd_apply_kernel<<<ew_grid(n, 4), EW_THREADS, 0, ST>>>(x, dy, y, save_mean, save_invstd, gamma, ws, relu, n, C, M, dx, dgamma, dbeta);
+    RSG_CUDA(cudaMemsetAsync(ws, 0, 2 * (size_t)C * sizeof(double), ST));
   }
   RSG_LAUNCH_CHECK();
   return RSG_OK;
@@ -783,6 +832,7 @@ extern "C" int rsg_train_colsum(void* stream, const float* x, long long M, int C
   chan_reduce_cfg(M, rpb, blocks, yt);
   chan_reduce_kernel<2><<<dim3(blocks, yt), EW_THREADS, 0, ST>>>(x, nullptr, nullptr, nullptr, nullptr, 0, M, C, rpb, ws);
   d2f_kernel<<<ceil_div(C, 128), 128, 0, ST>>>(ws, 1.f, C, accumulate, out);
+  RSG_CUDA(cudaMemsetAsync(ws, 0, (size_t)C * sizeof(double), ST));          // the BatchNorm float4 path expects a zeroed scratch
   RSG_LAUNCH_CHECK();
   return RSG_OK;
 }

@@ -42,7 +42,8 @@ class Tape:
         self.launches = 0
         self.flops = 0.0              # executed multiply-adds * 2 of the matrix kernels (3x in the 3xTF32 mode not counted)
         self.prof = None              # list of (kernel, start event, end event, flops) when profiling
-        self._ws = torch.empty(4096, dtype=torch.float64, device=device)      # reduction scratch (2 * C doubles)
+        self._ws = None                # reduction scratch (doubles), kept ZERO between calls (include/rsg_b200.h, BatchNorm)
+        self.ws(4096)
 
     # ------------------------------------------------------------------ plumbing
     @property
@@ -101,8 +102,9 @@ class Tape:
         return t.g
 
     def ws(self, n):
-        if self._ws.numel() < n:
-            self._ws = torch.empty(n, dtype=torch.float64, device=self.device)
+        if self._ws is None or self._ws.numel() < n:
+            self._ws = torch.empty(max(n, 4096), dtype=torch.float64, device=self.device)
+            self.call('rsg_train_zero', _p(self._ws), C.c_size_t(8 * self._ws.numel()))
         return self._ws
 
     # ------------------------------------------------------------------ matrix ops
@@ -248,7 +250,7 @@ class Tape:
         y = self.new(*x.shape)
         mean, invstd = self.new(Cn), self.new(Cn)
         self.call('rsg_train_bn_fwd', _p(x.v), M, Cn, _p(gamma.v), _p(beta.v), eps, momentum, _p(running_mean),
-                  _p(running_var), 1 if relu else 0, _p(y), _p(mean), _p(invstd), _p(self.ws(2 * Cn)), n=4)
+                  _p(running_var), 1 if relu else 0, _p(y), _p(mean), _p(invstd), _p(self.ws(3 * Cn + 4)), n=2)
         out = T(y)
 
         def bwd():
@@ -258,7 +260,7 @@ class Tape:
             dx = self.new(*x.shape) if x.req else None
             self.call('rsg_train_bn_bwd', _p(x.v), _p(y), _p(dy), M, Cn, _p(gamma.v), _p(mean), _p(invstd),
                       1 if relu else 0, _p(dx), _p(gamma.g) if gamma.req else None, _p(beta.g) if beta.req else None,
-                      _p(self.ws(2 * Cn)), n=3)
+                      _p(self.ws(3 * Cn + 4)), n=2)
             if dx is not None:
                 self.acc(x, dx)
         self.record(bwd)
