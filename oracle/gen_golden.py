@@ -341,6 +341,7 @@ def main():
         train_case('tiny', 2, 0)
         train_case('tiny_cp', 3, 1)
         train_case('tiny_hrnet', 2, 2)
+        train_case('w32_coco', 2, 3)          # BASELINE.json configs[4]'s model at full depth and resolution
 
 
 if __name__ == '__main__':

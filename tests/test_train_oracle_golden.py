@@ -28,7 +28,7 @@ def flat_sub(tensors, names, sub):
     return torch.cat([tensors[k].reshape(-1).float() for k in names])[::sub].numpy()
 
 
-@pytest.mark.parametrize('key', ['tiny', 'tiny_cp', 'tiny_hrnet'])
+@pytest.mark.parametrize('key', ['tiny', 'tiny_cp', 'tiny_hrnet', 'w32_coco'])
 def test_train_oracle_fp64_equals_reference_loop_fp64(key):
     """Logic pin: in double precision the restatement reproduces the reference loop to rounding."""
     g, cfg, net, sd, b = load_case(key)
@@ -52,7 +52,7 @@ def test_train_oracle_fp64_equals_reference_loop_fp64(key):
     np.testing.assert_allclose(bs, g['buf_sub64'], rtol=1e-9, atol=1e-12)
 
 
-@pytest.mark.parametrize('key', ['tiny', 'tiny_cp', 'tiny_hrnet'])
+@pytest.mark.parametrize('key', ['tiny', 'tiny_cp', 'tiny_hrnet', 'w32_coco'])
 def test_train_oracle_fp32_within_reference_fp32_noise(key):
     """In fp32 two correct implementations differ by rounding, amplified by the GroupNorm behind the TRP ('tiny' is the
     ill-conditioned case: the reference's own fp32 gradients are ~1e-3 .. 1e-2 off its fp64 run).  Bar: per parameter

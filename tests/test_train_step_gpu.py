@@ -49,7 +49,7 @@ def grads_of(net, store, names):
     return out
 
 
-@pytest.mark.parametrize('key', ['tiny', 'tiny_cp', 'tiny_hrnet'])
+@pytest.mark.parametrize('key', ['tiny', 'tiny_cp', 'tiny_hrnet', 'w32_coco'])
 def test_train_step_precise_vs_reference_loop(key):
     from rsgnet_b200.train import TrainStep
     g, cfg, net, sd, batch = setup_case(key)
