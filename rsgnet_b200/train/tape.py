@@ -38,6 +38,7 @@ class Tape:
         self.device = device
         self.lib = _lib.lib()
         self.ops = []
+        self.default_precise = int(precise)
         self.precise = int(precise)       # 0 TF32 (tcgen05 kernel where it applies), 1 3xTF32 (fp32-class), 2 TF32 on mma.sync
         self.launches = 0
         self.flops = 0.0              # executed multiply-adds * 2 of the matrix kernels (3x in the 3xTF32 mode not counted)
@@ -466,6 +467,10 @@ class Tape:
         """x [B,S,C] (theta = phi = x), g [B,S,Cg] -> (y [B,S,Cg] = sigmoid(x x^T) g, P [B,S,S] as a node).
         The gradient of a loss on P (the relation MSE) is added by the caller through ``P.g`` or ``rel_hook``."""
         pr = self.precise
+        # dP = dy g^T and dx = (dA + dA^T) x are ordinary gradient GEMMs: they follow the tape's default precision.  dg = P dy
+        # stays with the forward's 3xTF32: the GroupNorm backward makes sum_j dy_j ~ 0 and every row of P is nearly constant,
+        # so dg is what is left of a cancellation (the g weights' gradient moved by 3e-3 with TF32 products)
+        pb = self.default_precise
         B, S, Cx = x.shape
         Cg = g.shape[-1]
         P = self.new(B, S, S)
@@ -486,7 +491,7 @@ class Tape:
                     self._gemm(pr, P, dy, dg, None, S, Cg, S, S, Cg, Cg, batch=B, sA=S * S, sB=S * Cg, sC=S * Cg)
                     self.acc(g, dg)
                 dP = self.new(B, S, S)
-                self._gemm(pr, dy, g.v, dP, None, S, S, Cg, Cg, Cg, S, transB=1, batch=B, sA=S * Cg, sB=S * Cg, sC=S * S)
+                self._gemm(pb, dy, g.v, dP, None, S, S, Cg, Cg, Cg, S, transB=1, batch=B, sA=S * Cg, sB=S * Cg, sC=S * S)
             if Pn.g is not None:                      # a caller differentiated through the returned scores directly
                 if dP is None:
                     dP = Pn.g
@@ -501,8 +506,8 @@ class Tape:
             self.call('rsg_train_trp_dscore', _p(P), _p(dP), _p(rel[0]) if rel else None, _p(rel[1]) if rel else None,
                       _p(rel[2]) if rel else None, B, S, _p(dA))
             dx = self.new(B, S, Cx)                   # A = x x^T: dx = dA x + dA^T x
-            self._gemm(pr, dA, x.v, dx, None, S, Cx, S, S, Cx, Cx, batch=B, sA=S * S, sB=S * Cx, sC=S * Cx)
-            self._gemm(pr, dA, x.v, dx, None, S, Cx, S, S, Cx, Cx, transA=1, beta=1, batch=B, sA=S * S, sB=S * Cx, sC=S * Cx)
+            self._gemm(pb, dA, x.v, dx, None, S, Cx, S, S, Cx, Cx, batch=B, sA=S * S, sB=S * Cx, sC=S * Cx)
+            self._gemm(pb, dA, x.v, dx, None, S, Cx, S, S, Cx, Cx, transA=1, beta=1, batch=B, sA=S * S, sB=S * Cx, sC=S * Cx)
             self.acc(x, dx)
         self.record(bwd)
         return out, Pn, hook
