@@ -605,7 +605,7 @@ def run_train(args):
     ts.profile = False
     agg = collections.defaultdict(lambda: [0.0, 0, 0.0])
     for name, a, b_, fl in ts.tape.prof:
-        r = agg[name]
+        r = agg[name.split(' ')[0]]
         r[0] += a.elapsed_time(b_)
         r[1] += 1
         r[2] += fl

@@ -54,13 +54,13 @@ class Tape:
     def new(self, *shape):
         return torch.empty(shape, dtype=torch.float32, device=self.device)
 
-    def call(self, name, *args, n=1, flops=0.0):
+    def call(self, name, *args, n=1, flops=0.0, tag=''):
         if self.prof is not None:
             e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             e0.record()
             _lib.check(getattr(self.lib, name)(self.st, *args))
             e1.record()
-            self.prof.append((name, e0, e1, flops))
+            self.prof.append((name + tag, e0, e1, flops))
         else:
             _lib.check(getattr(self.lib, name)(self.st, *args))
         self.launches += n
@@ -114,12 +114,14 @@ class Tape:
         g = (C.c_int * 8)(*geom) if geom is not None else None
         taps = geom[4] * geom[5] if geom is not None else 1
         self.call('rsg_train_gemm', _p(A), _p(B), _p(Cm), _p(bias), M, Nc, Ca, lda, ldb, ldc, batch, sA, sB, sC, mode,
-                  transA, transB, beta, g, pr, flops=2.0 * M * Nc * Ca * taps * batch)
+                  transA, transB, beta, g, pr, flops=2.0 * M * Nc * Ca * taps * batch,
+                  tag=f' M{M} N{Nc} K{Ca} taps{taps} mode{mode} s{geom[6] if geom is not None else 1} b{batch} tA{transA} tB{transB} p{pr}' if self.prof is not None else '')
 
     def _wgrad(self, pr, X, dY, dW, M, Ca, Nc, mode=0, geom=None):
         g = (C.c_int * 8)(*geom) if geom is not None else None
         taps = geom[4] * geom[5] if geom is not None else 1
-        self.call('rsg_train_wgrad', _p(X), _p(dY), _p(dW), M, Ca, Nc, Ca, Nc, mode, g, pr, flops=2.0 * M * Ca * Nc * taps)
+        self.call('rsg_train_wgrad', _p(X), _p(dY), _p(dW), M, Ca, Nc, Ca, Nc, mode, g, pr, flops=2.0 * M * Ca * Nc * taps,
+                  tag=f' M{M} ci{Ca} co{Nc} taps{taps} mode{mode} s{geom[6] if geom is not None else 1}' if self.prof is not None else '')
 
     def precision(self, precise):
         """Context manager: matrix ops RECORDED inside use 3xTF32 products (forward and backward), whatever the tape's

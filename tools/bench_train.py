@@ -33,12 +33,18 @@ ts.profile = True
 ts(*args, sync=False)
 torch.cuda.synchronize()
 agg = collections.defaultdict(lambda: [0.0, 0, 0.0])
+shapes = collections.defaultdict(lambda: [0.0, 0, 0.0])
 for name, a, bb, fl in ts.tape.prof:
-    r = agg[name]; r[0] += a.elapsed_time(bb); r[1] += 1; r[2] += fl
+    r = agg[name.split(' ')[0]]; r[0] += a.elapsed_time(bb); r[1] += 1; r[2] += fl
+    if ' ' in name:
+        q = shapes[name]; q[0] += a.elapsed_time(bb); q[1] += 1; q[2] += fl
 tot = sum(r[0] for r in agg.values())
 print('profiled total %.1f ms' % tot)
 for name, r in sorted(agg.items(), key=lambda kv: -kv[1][0]):
     print('%8.2f ms %5.1f%% n=%5d  %7.1f TF/s  %s' % (r[0], 100 * r[0] / tot, r[1], r[2] / r[0] / 1e9 if r[0] else 0, name))
+for name, r in sorted(shapes.items(), key=lambda kv: -kv[1][0])[:28]:
+    print('  %7.2f ms n=%3d %6.1f TF/s %s' % (r[0], r[1], r[2] / r[0] / 1e9, name))
+sys.exit(0)
 # the slowest individual matrix calls
 rows = sorted(((a.elapsed_time(bb), name, fl) for name, a, bb, fl in ts.tape.prof if fl), reverse=True)[:12]
 for ms, name, fl in rows:
