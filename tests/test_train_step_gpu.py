@@ -199,3 +199,48 @@ def test_training_reduces_the_loss_and_eval_follows_the_new_weights():
     ref = model_oracle.forward(new_sd, cfg, batch['input'].cpu())[1]
     err = float((out[1].cpu() - ref).abs().max() / ref.abs().max())
     assert err < 0.05, err
+
+
+def test_train_mode_with_trp_sub_sample_vs_oracle_autograd():
+    """RELATION_SUB_SAMPLE (association.py:221, 252-266: max-pool before the attention, ConvTranspose + BN + ReLU after) has no
+    reference-loop fixture -- the reference's loop cannot train it (its relation target has the full-map size) -- so the
+    train-mode forward and backward of that variant are checked against torch autograd over the oracle in float64: the
+    drop-in route without a relation target, a random linear functional of all four outputs as the loss."""
+    from oracle import model_oracle
+    from rsgnet_b200 import presets, synth
+    from rsgnet_b200.models import _params, pose_rsgnet
+    cfg = presets.preset('tiny_cp_sub')
+    net = pose_rsgnet.get_pose_net(cfg, True)
+    sd = _params.synth_state_dict(net, seed=1)
+    net.load_state_dict(sd)
+    torch.cuda.set_device(0)
+    net = net.cuda().train()
+    x = torch.from_numpy(synth.crops(2, cfg.MODEL.IMAGE_SIZE, seed=12))
+    outs = net(x.cuda())
+    rs = np.random.RandomState(3)
+    R = [torch.from_numpy(rs.standard_normal(tuple(o.shape)).astype(np.float32)) for o in outs]
+    loss = sum((o * r.cuda()).sum() for o, r in zip(outs, R))
+    loss.backward()
+    # oracle: the same graph in float64 with batch-statistics BN
+    params = {k: v.clone().double().requires_grad_(v.is_floating_point() and not k.endswith(('running_mean', 'running_var')))
+              if v.is_floating_point() else v.clone() for k, v in sd.items()}
+    model_oracle.TRAIN, model_oracle.DTYPE = True, torch.float64
+    try:
+        ref = model_oracle.rsgnet_forward(params, cfg, x.double())
+        ref_loss = sum((o * r.double()).sum() for o, r in zip(ref, R))
+        ref_loss.backward()
+    finally:
+        model_oracle.TRAIN, model_oracle.DTYPE = False, torch.float32
+    for o, r in zip(outs, ref):
+        assert float((o.detach().cpu().double() - r.detach()).abs().max()) <= 5e-3 * float(r.abs().max())
+    rel = []
+    for k, p in net.named_parameters():
+        if not p.requires_grad:
+            continue
+        g = params[k].grad
+        assert p.grad is not None and g is not None, k
+        n = float(g.norm())
+        if n > 1e-6 * max(float(q.grad.norm()) for q in params.values() if torch.is_tensor(q) and q.requires_grad and q.grad is not None):
+            rel.append(abs(float(p.grad.detach().cpu().double().norm()) - n) / n)
+    print(f'sub_sample: per-tensor gradient-norm error median {np.median(rel):.2e} max {max(rel):.2e} (TF32 products)')
+    assert np.median(rel) < 0.02 and max(rel) < 0.3
