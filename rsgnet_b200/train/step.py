@@ -385,10 +385,11 @@ class _NetFunction(torch.autograd.Function):
                     P.own = False
             tape.backward()
             st.unpack_grads(tape)
+        snap = st.flat_g.clone()            # ONE copy: the next forward zeroes flat_g, p.grad must survive it
         out = []
         for p in ctx.params:
             off, n = st.offsets[id(p)]
-            out.append(st.flat_g[off:off + n].view(p.shape).clone() if p.requires_grad else None)
+            out.append(snap[off:off + n].view(p.shape) if p.requires_grad else None)
         return (None, None, None, *out)
 
 
