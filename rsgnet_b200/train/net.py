@@ -52,9 +52,13 @@ class Net:
     def hr_module(self, xs, mod):
         nb = len(xs)
         xs = list(xs)
-        for b in range(nb):
+
+        def branch(b):
+            x = xs[b]
             for blk in mod.branches[b]:
-                xs[b] = self.basic(xs[b], blk)
+                x = self.basic(x, blk)
+            return x
+        xs = self.t.parallel([lambda b=b: branch(b) for b in range(nb)])       # independent chains: one stream each
         if nb == 1:
             return xs
         outs = []

@@ -19,7 +19,7 @@ import torch.nn as nn
 from .. import _lib
 from ..config import KIND_RSGNET
 from .net import Net
-from .tape import T, Tape, _p
+from .tape import T, Tape, _p, side_streams
 
 
 def _ceil4(n):
@@ -183,6 +183,8 @@ class TrainStep:
             self.world = torch.distributed.get_world_size(process_group)
         self.last_launches = 0
         self.profile = False          # True: CUDA events around every library call of the next step (see tape.prof)
+        self.concurrent = True        # HRNet branches on side streams (Tape.parallel); False = one stream
+        self.side = side_streams(self.device, 3)
         # frozen parameters (loc_features, kt_machine.real_matrix_limb) keep a zero gradient and are skipped by masking lr:
         # Adam with g = 0, m = v = 0 leaves them unchanged (update = 0 / (0 + eps) = 0)
 
@@ -194,7 +196,7 @@ class TrainStep:
         (function.py:256-269), or the reference's explicit [B,S,S] tensor.  Returns (losses dict after sync, outputs)."""
         mod, dev = self.module, self.device
         with torch.cuda.device(dev):
-            tape = Tape(dev, self.precise)
+            tape = Tape(dev, self.precise, side=self.side if self.concurrent else None)
             if self.profile:
                 tape.prof = []
             self.tape = tape

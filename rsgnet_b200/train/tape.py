@@ -33,8 +33,22 @@ def _p(t):
     return C.c_void_p(t.data_ptr()) if t is not None else None
 
 
+_SIDE_STREAMS = {}
+
+
+def side_streams(device, n=3):
+    """Process-wide side streams of a device for Tape.parallel (created once, outside any graph capture)."""
+    key = (device.index if device.index is not None else torch.cuda.current_device())
+    st = _SIDE_STREAMS.get(key)
+    if st is None or len(st) < n:
+        with torch.cuda.device(device):
+            st = [torch.cuda.Stream(device) for _ in range(n)]
+        _SIDE_STREAMS[key] = st
+    return st
+
+
 class Tape:
-    def __init__(self, device, precise=False):
+    def __init__(self, device, precise=False, side=None):
         self.device = device
         self.lib = _lib.lib()
         self.ops = []
@@ -43,7 +57,8 @@ class Tape:
         self.launches = 0
         self.flops = 0.0              # executed multiply-adds * 2 of the matrix kernels (3x in the 3xTF32 mode not counted)
         self.prof = None              # list of (kernel, start event, end event, flops) when profiling
-        self._ws = None                # reduction scratch (doubles), kept ZERO between calls (include/rsg_b200.h, BatchNorm)
+        self.side = side or []         # side streams for parallel(); empty = everything on the current stream
+        self._ws = {}                  # per-stream reduction scratch (doubles), kept ZERO between calls (rsg_b200.h, BatchNorm)
         self.ws(4096)
 
     # ------------------------------------------------------------------ plumbing
@@ -103,10 +118,64 @@ class Tape:
         return t.g
 
     def ws(self, n):
-        if self._ws is None or self._ws.numel() < n:
-            self._ws = torch.empty(max(n, 4096), dtype=torch.float64, device=self.device)
-            self.call('rsg_train_zero', _p(self._ws), C.c_size_t(8 * self._ws.numel()))
-        return self._ws
+        key = torch.cuda.current_stream(self.device).cuda_stream
+        buf = self._ws.get(key)
+        if buf is None or buf.numel() < n:
+            buf = torch.empty(max(n, 4096), dtype=torch.float64, device=self.device)
+            self.call('rsg_train_zero', _p(buf), C.c_size_t(8 * buf.numel()))
+            self._ws[key] = buf
+        return buf
+
+    def parallel(self, fns):
+        """Run the callables concurrently: fns[0] on the current stream, fns[i] on side stream i - 1 (fork / join with events;
+        captured into a CUDA graph these become parallel branches).  Each callable records its own sub-tape; ONE composite
+        closure on the main tape replays the sub-tapes backwards with the same fork / join, so the backward passes of the
+        branches overlap too.  The HRNet branches of a HighResolutionModule (pose_rsgnet.py:254-260) are independent chains of
+        BasicBlocks, and on the 16x12 and 8x6 maps their kernels fill a fraction of the SMs.
+        Memory safety without record_stream: every tensor that crosses streams is produced before a fork or consumed after a
+        join, and torch's caching allocator reuses a freed block only on the stream it was allocated on."""
+        if not self.side or len(fns) < 2:
+            return [fn() for fn in fns]
+        dev = self.device
+        main = torch.cuda.current_stream(dev)
+        n = min(len(fns), len(self.side) + 1)
+        fork = torch.cuda.Event()
+        fork.record(main)
+        saved = self.ops
+        results, recs = [], []
+        for i, fn in enumerate(fns):
+            st = main if (i == 0 or i >= n) else self.side[i - 1]
+            self.ops = []
+            if st is not main:
+                st.wait_event(fork)
+            with torch.cuda.stream(st):
+                results.append(fn())
+            recs.append((st is not main, st, self.ops))
+        self.ops = saved
+        for on_side, st, _ in recs:
+            if on_side:
+                ev = torch.cuda.Event()
+                ev.record(st)
+                main.wait_event(ev)
+
+        def bwd():
+            cur = torch.cuda.current_stream(dev)
+            fk = torch.cuda.Event()
+            fk.record(cur)
+            for on_side, st, ops in recs:
+                run_on = st if on_side else cur
+                if on_side:
+                    run_on.wait_event(fk)
+                with torch.cuda.stream(run_on):
+                    while ops:
+                        ops.pop()()
+            for on_side, st, _ in recs:
+                if on_side:
+                    ev = torch.cuda.Event()
+                    ev.record(st)
+                    cur.wait_event(ev)
+        self.record(bwd)
+        return results
 
     # ------------------------------------------------------------------ matrix ops
     def _gemm(self, pr, A, B, Cm, bias, M, Nc, Ca, lda, ldb, ldc, mode=0, transA=0, transB=0, beta=0, geom=None, batch=1,
