@@ -61,22 +61,28 @@ class Net:
         xs = self.t.parallel([lambda b=b: branch(b) for b in range(nb)])       # independent chains: one stream each
         if nb == 1:
             return xs
-        outs = []
-        for i, row in enumerate(mod.fuse_layers):
+        # The fused outputs are independent of each other too, but they READ the same branch results: every output gets its
+        # own alias nodes (made before the fork), so that the gradients of a shared input are summed on the main stream,
+        # after the join, by the aliases' link closures -- never by two streams at once.
+        rows = list(mod.fuse_layers)
+        alias = [[self.t.view(xs[j], *xs[j].shape) for j in range(nb)] for _ in rows]
+
+        def fuse(i):
+            row, src = rows[i], alias[i]
             terms = []
             for j in range(nb):
                 if j == i:
-                    terms.append(xs[j])
+                    terms.append(src[j])
                 elif j > i:
-                    terms.append(self.t.upsample_nearest(self.cbr(xs[j], row[j], False), 2 ** (j - i)))
+                    terms.append(self.t.upsample_nearest(self.cbr(src[j], row[j], False), 2 ** (j - i)))
                 else:
-                    t = xs[j]
+                    t = src[j]
                     hops = row[j]
                     for k, hop in enumerate(hops):
                         t = self.cbr(t, hop, relu=(k != len(hops) - 1))
                     terms.append(t)
-            outs.append(self.t.add(terms, relu=True))
-        return outs
+            return self.t.add(terms, relu=True)
+        return self.t.parallel([lambda i=i: fuse(i) for i in range(len(rows))])
 
     def transition(self, prev, layers):
         n_pre = len(prev)
