@@ -506,6 +506,110 @@ __global__ void __launch_bounds__(GM_THREADS, 2) wgrad_async_kernel(const WgradP
       }
 }
 
+
+// Narrow layers, 3x3 stride-1 convs (the C0 = 32 branch at 64x48 and the heads at 128x96): the per-tap CTAs of wgrad32_kernel
+// read X and dY nine times (226 MB of L2 traffic for a 12.6 MB layer: 72 us).  Flat form as in train_tc5.cu: the pixels are one
+// array of pitch P = W + 1 (zero column / zero row per image = padding); a CTA takes 128 consecutive positions of dY and the
+// 128 + 2 P + 2 halo positions of X ONCE into shared memory (cp.async, two stages), and its nine warps each own one tap:
+// warp t multiplies the X rows shifted by dy P + dx with the same dY rows into its own 32 x 32 tile.
+constexpr int WF_THREADS = 288, WF_PX = 128, WF_PITCH = 40;
+
+struct WgradFlatP {
+  const float* X; const float* dY; float* dW;
+  int Nimg, H, W, Ca, Nc, ldx, ldy, P, RPI, NPH;
+  long long total, per_split;
+};
+
+__device__ __forceinline__ int wf_pixel(const WgradFlatP& p, long long gpos) {
+  if (gpos < 0 || gpos >= p.total) return -1;
+  const int R = (int)(gpos / p.P), Xc = (int)(gpos - (long long)R * p.P);
+  const int n = R / p.RPI, yy = R - n * p.RPI;
+  if (Xc == 0 || yy == 0) return -1;
+  return (n * p.H + (yy - 1)) * p.W + (Xc - 1);
+}
+
+__global__ void __launch_bounds__(WF_THREADS, 1) wgrad32_flat_kernel(const WgradFlatP p) {
+  extern __shared__ __align__(16) float wf_smem[];                // [stage][X halo NPH rows | dY 128 rows][WF_PITCH]
+  const int stage_f = (p.NPH + WF_PX) * WF_PITCH;
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, g = lane >> 2, tq = lane & 3;
+  const long long fb = (long long)blockIdx.x * p.per_split;
+  long long fe = fb + p.per_split;
+  if (fe > p.total) fe = p.total;
+  const int nchunk = fe > fb ? (int)((fe - fb + WF_PX - 1) / WF_PX) : 0;
+  const int q4 = (tid & 7) * 4, r0 = tid >> 3;                   // staged: rows r0 + 36 j, channels q4 .. q4+3
+  const bool xok = q4 < p.Ca, yok = q4 < p.Nc;
+  const int dy = warp / 3, dx = warp - 3 * dy, off = dy * p.P + dx;
+  float acc[2][4][4];
+#pragma unroll
+  for (int i = 0; i < 2; ++i)
+#pragma unroll
+    for (int j = 0; j < 4; ++j)
+#pragma unroll
+      for (int k = 0; k < 4; ++k) acc[i][j][k] = 0.f;
+  auto issue = [&](int c) {
+    if (c < nchunk) {
+      float* Xs = wf_smem + (c & 1) * stage_f;
+      float* Ys = Xs + p.NPH * WF_PITCH;
+      const long long f0 = fb + (long long)c * WF_PX;
+      for (int r = r0; r < p.NPH; r += WF_THREADS / 8) {          // halo position r <-> flat position f0 - P - 1 + r
+        const long long gp = f0 - p.P - 1 + r;
+        const int px = gp < fe + p.P + 1 ? wf_pixel(p, gp) : -1;
+        wg_cp16(&Xs[r * WF_PITCH + q4], px >= 0 && xok ? p.X + (long long)px * p.ldx + q4 : p.X, px >= 0 && xok);
+      }
+      for (int r = r0; r < WF_PX; r += WF_THREADS / 8) {
+        const long long gp = f0 + r;
+        const int px = gp < fe ? wf_pixel(p, gp) : -1;
+        wg_cp16(&Ys[r * WF_PITCH + q4], px >= 0 && yok ? p.dY + (long long)px * p.ldy + q4 : p.dY, px >= 0 && yok);
+      }
+    }
+    asm volatile("cp.async.commit_group;" ::: "memory");
+  };
+  issue(0);
+  for (int c = 0; c < nchunk; ++c) {
+    issue(c + 1);
+    asm volatile("cp.async.wait_group 1;" ::: "memory");
+    __syncthreads();
+    const float* Xs = wf_smem + (c & 1) * stage_f + off * WF_PITCH;
+    const float* Ys = wf_smem + (c & 1) * stage_f + p.NPH * WF_PITCH;
+#pragma unroll 4
+    for (int k8 = 0; k8 < WF_PX / 8; ++k8) {
+      uint32_t ah[2][4], bh[4][2];
+#pragma unroll
+      for (int mt = 0; mt < 2; ++mt) {
+        const float* a = &Xs[(k8 * 8 + tq) * WF_PITCH + mt * 16 + g];
+        ah[mt][0] = to_tf32(a[0]);
+        ah[mt][1] = to_tf32(a[8]);
+        ah[mt][2] = to_tf32(a[4 * WF_PITCH]);
+        ah[mt][3] = to_tf32(a[4 * WF_PITCH + 8]);
+      }
+#pragma unroll
+      for (int nt = 0; nt < 4; ++nt) {
+        const float* b = &Ys[(k8 * 8 + tq) * WF_PITCH + nt * 8 + g];
+        bh[nt][0] = to_tf32(b[0]);
+        bh[nt][1] = to_tf32(b[4 * WF_PITCH]);
+      }
+#pragma unroll
+      for (int mt = 0; mt < 2; ++mt)
+#pragma unroll
+        for (int nt = 0; nt < 4; ++nt) mma_tf32(acc[mt][nt], ah[mt], bh[nt]);
+    }
+    __syncthreads();
+  }
+  asm volatile("cp.async.wait_group 0;" ::: "memory");
+  float* Wt = p.dW + (long long)warp * p.Ca * p.Nc;               // tap = warp
+#pragma unroll
+  for (int mt = 0; mt < 2; ++mt)
+#pragma unroll
+    for (int nt = 0; nt < 4; ++nt)
+#pragma unroll
+      for (int h = 0; h < 2; ++h)
+#pragma unroll
+        for (int e = 0; e < 2; ++e) {
+          const int ci = mt * 16 + g + 8 * h, co = nt * 8 + 2 * tq + e;
+          if (ci < p.Ca && co < p.Nc) atomicAdd(Wt + (long long)ci * p.Nc + co, acc[mt][nt][2 * h + e]);
+        }
+}
+
 }  // namespace
 
 // train_tc5.cu: the tcgen05 kind::tf32 kernels (K-major B only)
@@ -707,6 +811,31 @@ extern "C" int rsg_train_wgrad(void* stream, const float* X, const float* dY, fl
   }
   p.vecX = al16(X) && ldx % 4 == 0;
   p.vecY = al16(dY) && ldy % 4 == 0;
+  if (Ca <= 32 && Nc <= 32 && !p.precise && mode == 1 && geom[4] == 3 && geom[5] == 3 && geom[6] == 1 && geom[7] == 1 &&
+      geom[0] == geom[2] && geom[1] == geom[3] && geom[1] <= 110 && Ca % 4 == 0 && Nc % 4 == 0 && p.vecX && p.vecY &&
+      (long long)M * ldx < (1ll << 31) && (long long)M * ldy < (1ll << 31)) {
+    WgradFlatP f;                              // narrow 3x3 stride-1 layers: flat form, X and dY read once
+    memset(&f, 0, sizeof(f));
+    f.X = X; f.dY = dY; f.dW = dW; f.H = geom[0]; f.W = geom[1]; f.Nimg = M / (f.H * f.W); f.Ca = Ca; f.Nc = Nc; f.ldx = ldx; f.ldy = ldy;
+    f.P = f.W + 1; f.RPI = f.H + 1; f.NPH = WF_PX + 2 * f.P + 2;
+    f.total = (long long)f.Nimg * f.RPI * f.P;
+    long long splits = 2ll * rsg_num_sms(), maxsplit = (f.total + 4 * WF_PX - 1) / (4 * WF_PX);
+    if (splits > maxsplit) splits = maxsplit;
+    if (splits < 1) splits = 1;
+    f.per_split = ((f.total + splits - 1) / splits + WF_PX - 1) / WF_PX * WF_PX;
+    splits = (f.total + f.per_split - 1) / f.per_split;
+    const size_t smem = 2 * (size_t)(f.NPH + WF_PX) * WF_PITCH * sizeof(float);
+    static DeviceOnce once_f;
+    if (once_f.first()) {
+      RSG_CUDA(cudaFuncSetAttribute(wgrad32_flat_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+      once_f.done();
+    }
+    if (smem <= 200 * 1024) {
+      wgrad32_flat_kernel<<<dim3((unsigned)splits), WF_THREADS, smem, (cudaStream_t)stream>>>(f);
+      RSG_LAUNCH_CHECK();
+      return RSG_OK;
+    }
+  }
   if (Ca <= 32 && Nc <= 32) {                  // narrow layers: pixel-split warps on one 32 x 32 tile
     long long want = (4ll * rsg_num_sms() + p.taps - 1) / p.taps, maxsplit = (M + 1023) / 1024;
     if (want > maxsplit) want = maxsplit;
