@@ -598,11 +598,11 @@ def run_train(args):
         last['L'], _ = ts.step_graph(*[host[k] for k in keys], sync=True)     # H2D of the batch + D2H of the losses
     ms_e2e, _ = timed(e2e_step, args.steps)
     # eager step with CUDA events around every library call: per-kernel-family time and executed FLOPs
-    ts.profile = True
+    ts.profile, ts.concurrent = True, False          # one stream: with overlapping branches a CUDA-event pair times its neighbours too
     with torch.cuda.stream(stream):
         ts(*batch, sync=False)
     torch.cuda.synchronize()
-    ts.profile = False
+    ts.profile, ts.concurrent = False, True
     agg = collections.defaultdict(lambda: [0.0, 0, 0.0])
     for name, a, b_, fl in ts.tape.prof:
         r = agg[name.split(' ')[0]]
@@ -636,8 +636,8 @@ def run_train(args):
                      'traffic': None, 'peak_source': pk['src'] + ' bf16_tflops_sustained / 2 (TF32 runs at half the bf16 rate)',
                      'algorithmic_flops_per_launch': g[2] / max(g[1], 1), 'us_per_launch': g[0] / max(g[1], 1) * 1e3,
                      'launches_per_step': g[1], 'share_of_step': g[0] / tot, 'families': fam,
-                     'note': 'first-correct kernels of the SURVEY 8f-4 row (mma.sync, register-staged tiles); per-family times from an '
-                             'eager step with CUDA events around every call'},
+                     'note': 'per-family times from an eager single-stream step with CUDA events around every library call; the timed '
+                             'steps replay one CUDA graph whose HRNet branches run concurrently'},
         'executed_gflop_per_step_per_gpu': gflop, 'executed_tflops_per_gpu': gflop / per_ms,
         'parity_checked': bool(parity), 'parity': parity, 'cpu_baseline': cpu,
     }

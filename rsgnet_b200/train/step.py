@@ -50,7 +50,7 @@ class ParamStore:
             view = self.flat_p[off:off + n].view(p.shape)
             view.copy_(p.data)
             p.data = view
-            self.leaf[id(p)] = T(view, req=p.requires_grad, g=self.flat_g[off:off + n].view(p.shape))
+            self.leaf[id(p)] = T(view, req=p.requires_grad, g=self.flat_g[off:off + n].view(p.shape), leaf=True)
             self.offsets[id(p)] = (off, n)
             off += _ceil4(n)
         self.total = total
@@ -83,7 +83,7 @@ class ParamStore:
                 wT = m.weight.data.view(1, co, ci)              # [Cout][Cin] is already the forward operand
             else:
                 wT = self.packed_wT[off:off + n].view(t, co, cip)
-            node = T(wv, req=m.weight.requires_grad, g=gv)
+            node = T(wv, req=m.weight.requires_grad, g=gv, leaf=True)
             self.packed[id(m)] = (node, wT)
             if not tr:      # OIHW: w[tap][ci][co] = W[co*Ci*T + ci*T + tap];  wT[tap][co][ci] likewise
                 pack.append(_lib.PermEntry(src, wv.data_ptr(), t, cip, co, ci, co, 1, t, ci * t, 0))
@@ -184,7 +184,7 @@ class TrainStep:
         self.last_launches = 0
         self.profile = False          # True: CUDA events around every library call of the next step (see tape.prof)
         self.concurrent = True        # HRNet branches on side streams (Tape.parallel); False = one stream
-        self.side = side_streams(self.device, 3)
+        self.side = side_streams(self.device, 4)    # 3 for parallel chains, 1 for the weight gradients
         # frozen parameters (loc_features, kt_machine.real_matrix_limb) keep a zero gradient and are skipped by masking lr:
         # Adam with g = 0, m = v = 0 leaves them unchanged (update = 0 / (0 + eps) = 0)
 
@@ -196,7 +196,8 @@ class TrainStep:
         (function.py:256-269), or the reference's explicit [B,S,S] tensor.  Returns (losses dict after sync, outputs)."""
         mod, dev = self.module, self.device
         with torch.cuda.device(dev):
-            tape = Tape(dev, self.precise, side=self.side if self.concurrent else None)
+            tape = Tape(dev, self.precise, side=self.side[:3] if self.concurrent else None,
+                        wstream=self.side[3] if self.concurrent else None)
             if self.profile:
                 tape.prof = []
             self.tape = tape

@@ -16,12 +16,13 @@ from .. import _lib
 
 class T:
     """A tape value: ``v`` the tensor, ``g`` its gradient (None until something flows back)."""
-    __slots__ = ('v', 'g', 'req', 'own')
+    __slots__ = ('v', 'g', 'req', 'own', 'leaf')
 
-    def __init__(self, v, req=True, g=None):
+    def __init__(self, v, req=True, g=None, leaf=False):
         self.v = v
         self.g = g
         self.req = req
+        self.leaf = leaf              # a parameter: nothing in the backward pass reads its gradient
         self.own = g is not None      # whether g may be updated in place (False when the tensor is shared with another node)
 
     @property
@@ -48,7 +49,7 @@ def side_streams(device, n=3):
 
 
 class Tape:
-    def __init__(self, device, precise=False, side=None):
+    def __init__(self, device, precise=False, side=None, wstream=None):
         self.device = device
         self.lib = _lib.lib()
         self.ops = []
@@ -58,6 +59,8 @@ class Tape:
         self.flops = 0.0              # executed multiply-adds * 2 of the matrix kernels (3x in the 3xTF32 mode not counted)
         self.prof = None              # list of (kernel, start event, end event, flops) when profiling
         self.side = side or []         # side streams for parallel(); empty = everything on the current stream
+        self.wstream = wstream         # weight gradients run here, off the critical path (None = on the current stream)
+        self._w_keep, self._w_event = [], None
         self._ws = {}                  # per-stream reduction scratch (doubles), kept ZERO between calls (rsg_b200.h, BatchNorm)
         self.ws(4096)
 
@@ -87,6 +90,7 @@ class Tape:
     def backward(self):
         while self.ops:
             self.ops.pop()()
+        self.join_wgrad()
 
     def acc(self, t, g, shared=False):
         """Add gradient tensor g into node t.  `shared`: g is also handed to another node (must not be modified)."""
@@ -186,7 +190,32 @@ class Tape:
                   transA, transB, beta, g, pr, flops=2.0 * M * Nc * Ca * taps * batch,
                   tag=f' M{M} N{Nc} K{Ca} taps{taps} mode{mode} s{geom[6] if geom is not None else 1} b{batch} tA{transA} tB{transB} p{pr}' if self.prof is not None else '')
 
-    def _wgrad(self, pr, X, dY, dW, M, Ca, Nc, mode=0, geom=None):
+    def _wgrad(self, pr, X, dY, dW, M, Ca, Nc, mode=0, geom=None, leaf=False):
+        """Weight gradients of PARAMETERS are leaves of the backward pass: nothing waits for them before the step's gradient
+        un-packing, so they go to a dedicated stream that only waits for `dY` and is joined once, at the end of backward().
+        X and dY are kept referenced until that join: the caching allocator must not hand their blocks to the main stream
+        meanwhile.  Gradients of COMPUTED weights (the type vectors, the KTMachine's limb filters) are read by later closures
+        and stay on the current stream."""
+        if leaf and self.wstream is not None and self.prof is None:
+            cur = torch.cuda.current_stream(self.device)
+            ev = torch.cuda.Event()
+            ev.record(cur)
+            self.wstream.wait_event(ev)
+            self._w_keep.append((X, dY))
+            with torch.cuda.stream(self.wstream):
+                self._wgrad_now(pr, X, dY, dW, M, Ca, Nc, mode, geom)
+                self._w_event = torch.cuda.Event()
+                self._w_event.record(self.wstream)
+            return
+        self._wgrad_now(pr, X, dY, dW, M, Ca, Nc, mode, geom)
+
+    def join_wgrad(self):
+        if self._w_event is not None:
+            torch.cuda.current_stream(self.device).wait_event(self._w_event)
+            self._w_event = None
+        self._w_keep = []
+
+    def _wgrad_now(self, pr, X, dY, dW, M, Ca, Nc, mode=0, geom=None):
         g = (C.c_int * 8)(*geom) if geom is not None else None
         taps = geom[4] * geom[5] if geom is not None else 1
         self.call('rsg_train_wgrad', _p(X), _p(dY), _p(dW), M, Ca, Nc, Ca, Nc, mode, g, pr, flops=2.0 * M * Ca * Nc * taps,
@@ -229,7 +258,7 @@ class Tape:
             if dy is None:
                 return
             if wp.req:
-                self._wgrad(pr, x.v, dy, self.grad_buf(wp), M, Ci, Co, mode=0 if plain else 1, geom=fg)
+                self._wgrad(pr, x.v, dy, self.grad_buf(wp), M, Ci, Co, mode=0 if plain else 1, geom=fg, leaf=wp.leaf)
             if bias is not None and bias.req:
                 self.call('rsg_train_colsum', _p(dy), M, Co, _p(self.grad_buf(bias)), 1, _p(self.ws(Co)), n=2)
             if x.req:
@@ -258,7 +287,7 @@ class Tape:
             if dy is None:
                 return
             if wp.req:
-                self._wgrad(pr, x.v, dy, self.grad_buf(wp), M, Ci, Co, mode=2, geom=tg)
+                self._wgrad(pr, x.v, dy, self.grad_buf(wp), M, Ci, Co, mode=2, geom=tg, leaf=wp.leaf)
             if x.req:
                 dx = self.new(N, h, w, Ci)
                 self._gemm(pr, dy, wp.v, dx, None, N * h * w, Ci, Co, Co, Co, Ci, mode=1, transB=1,
@@ -283,7 +312,7 @@ class Tape:
             if dy is None:
                 return
             if w.req:
-                self._wgrad(pr, dy, x.v, self.grad_buf(w), M, O, I)
+                self._wgrad(pr, dy, x.v, self.grad_buf(w), M, O, I, leaf=w.leaf)
             if bias is not None and bias.req:
                 self.call('rsg_train_colsum', _p(dy), M, O, _p(self.grad_buf(bias)), 1, _p(self.ws(O)), n=2)
             if x.req:
@@ -307,7 +336,7 @@ class Tape:
             if dy is None:
                 return
             if b.req:
-                self._wgrad(pr, a.v, dy, self.grad_buf(b), M, K, N)
+                self._wgrad(pr, a.v, dy, self.grad_buf(b), M, K, N, leaf=b.leaf)
             if a.req:
                 da = self.new(M, K)
                 self._gemm(pr, dy, b.v, da, None, M, K, N, N, N, K, transB=1)

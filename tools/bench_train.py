@@ -29,7 +29,7 @@ for i in range(n):
     ts(*args, sync=False)
 e1.record(); torch.cuda.synchronize()
 print('eager: wall %.1f ms/step, device %.1f ms/step' % ((time.perf_counter() - t0) / n * 1e3, e0.elapsed_time(e1) / n))
-ts.profile = True
+ts.profile, ts.concurrent = True, False
 ts(*args, sync=False)
 torch.cuda.synchronize()
 agg = collections.defaultdict(lambda: [0.0, 0, 0.0])
