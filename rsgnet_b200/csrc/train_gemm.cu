@@ -522,7 +522,8 @@ struct WgradFlatP {
 
 __device__ __forceinline__ int wf_pixel(const WgradFlatP& p, long long gpos) {
   if (gpos < 0 || gpos >= p.total) return -1;
-  const int R = (int)(gpos / p.P), Xc = (int)(gpos - (long long)R * p.P);
+  const int gi = (int)gpos;                                       // total < 2^31 (host check): 32-bit divisions
+  const int R = gi / p.P, Xc = gi - R * p.P;
   const int n = R / p.RPI, yy = R - n * p.RPI;
   if (Xc == 0 || yy == 0) return -1;
   return (n * p.H + (yy - 1)) * p.W + (Xc - 1);
@@ -551,16 +552,30 @@ __global__ void __launch_bounds__(WF_THREADS, 1) wgrad32_flat_kernel(const Wgrad
       float* Xs = wf_smem + (c & 1) * stage_f;
       float* Ys = Xs + p.NPH * WF_PITCH;
       const long long f0 = fb + (long long)c * WF_PX;
-      for (int r = r0; r < p.NPH; r += WF_THREADS / 8) {          // halo position r <-> flat position f0 - P - 1 + r
-        const long long gp = f0 - p.P - 1 + r;
-        const int px = gp < fe + p.P + 1 ? wf_pixel(p, gp) : -1;
-        wg_cp16(&Xs[r * WF_PITCH + q4], px >= 0 && xok ? p.X + (long long)px * p.ldx + q4 : p.X, px >= 0 && xok);
-      }
-      for (int r = r0; r < WF_PX; r += WF_THREADS / 8) {
-        const long long gp = f0 + r;
-        const int px = gp < fe ? wf_pixel(p, gp) : -1;
-        wg_cp16(&Ys[r * WF_PITCH + q4], px >= 0 && yok ? p.dY + (long long)px * p.ldy + q4 : p.dY, px >= 0 && yok);
-      }
+      // one division pair per chunk, then incremental (column, row-in-image, image) updates (36 positions per step); the
+      // position is shifted by one image block so that negative halo positions decode with ordinary division
+      auto walk = [&](long long g0, int nrows, long long glimit, auto&& emit) {
+        const int gs = (int)g0 + p.RPI * p.P;
+        int R = gs / p.P, Xc = gs - R * p.P;
+        int n = R / p.RPI, yy = R - n * p.RPI;
+        n -= 1;
+        long long gp = g0;
+        for (int r = r0; r < nrows; r += WF_THREADS / 8, gp += WF_THREADS / 8) {
+          const bool ok = gp < glimit && n >= 0 && n < p.Nimg && Xc != 0 && yy != 0;
+          emit(r, ok, (n * p.H + (yy - 1)) * p.W + (Xc - 1));
+          Xc += WF_THREADS / 8;
+          while (Xc >= p.P) {
+            Xc -= p.P;
+            if (++yy == p.RPI) { yy = 0; ++n; }
+          }
+        }
+      };
+      walk(f0 - p.P - 1 + r0, p.NPH, fe + p.P + 1, [&](int r, bool ok, int px) {
+        wg_cp16(&Xs[r * WF_PITCH + q4], ok && xok ? p.X + (long long)px * p.ldx + q4 : p.X, ok && xok);
+      });
+      walk(f0 + r0, WF_PX, fe, [&](int r, bool ok, int px) {
+        wg_cp16(&Ys[r * WF_PITCH + q4], ok && yok ? p.dY + (long long)px * p.ldy + q4 : p.dY, ok && yok);
+      });
     }
     asm volatile("cp.async.commit_group;" ::: "memory");
   };
@@ -813,7 +828,8 @@ extern "C" int rsg_train_wgrad(void* stream, const float* X, const float* dY, fl
   p.vecY = al16(dY) && ldy % 4 == 0;
   if (Ca <= 32 && Nc <= 32 && !p.precise && mode == 1 && geom[4] == 3 && geom[5] == 3 && geom[6] == 1 && geom[7] == 1 &&
       geom[0] == geom[2] && geom[1] == geom[3] && geom[1] <= 110 && Ca % 4 == 0 && Nc % 4 == 0 && p.vecX && p.vecY &&
-      (long long)M * ldx < (1ll << 31) && (long long)M * ldy < (1ll << 31)) {
+      (long long)M * ldx < (1ll << 31) && (long long)M * ldy < (1ll << 31) &&
+      (long long)(M / (geom[0] * geom[1])) * (geom[0] + 1) * (geom[1] + 1) < (1ll << 31)) {
     WgradFlatP f;                              // narrow 3x3 stride-1 layers: flat form, X and dY read once
     memset(&f, 0, sizeof(f));
     f.X = X; f.dY = dY; f.dW = dW; f.H = geom[0]; f.W = geom[1]; f.Nimg = M / (f.H * f.W); f.Ca = Ca; f.Nc = Nc; f.ldx = ldx; f.ldy = ldy;

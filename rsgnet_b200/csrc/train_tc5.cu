@@ -36,6 +36,13 @@ struct T5P {
 __device__ __forceinline__ void cp_async16(uint32_t dst, const void* src, uint32_t src_bytes) {
   asm volatile("cp.async.ca.shared.global [%0], [%1], 16, %2;" ::"r"(dst), "l"(src), "r"(src_bytes) : "memory");
 }
+// 32-byte store (STG.256): one full sector per lane and instruction.  Row-per-lane epilogues write 128-byte rows; with 16-byte
+// stores every sector is written by two instructions (partial-sector writes in L2).
+__device__ __forceinline__ void stg256(float* p, const float* f) {
+  asm volatile("st.global.v8.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};" ::"l"(p), "r"(__float_as_uint(f[0])), "r"(__float_as_uint(f[1])),
+               "r"(__float_as_uint(f[2])), "r"(__float_as_uint(f[3])), "r"(__float_as_uint(f[4])), "r"(__float_as_uint(f[5])),
+               "r"(__float_as_uint(f[6])), "r"(__float_as_uint(f[7])) : "memory");
+}
 __device__ __forceinline__ void umma_tf32(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
   asm volatile(
       "{\n\t.reg .pred p;\n\t"
@@ -237,9 +244,12 @@ struct T5F {
 };
 constexpr int T5F_MAXJ = 22;       // NP <= 16 * 22 = 352: W <= 110
 
-__device__ __forceinline__ int t5f_pixel(const T5F& p, long long g) {     // flat position -> NHWC pixel index, -1 = padding
-  if (g < 0 || g >= p.total) return -1;
-  const int R = (int)(g / p.P), X = (int)(g - (long long)R * p.P);
+// flat position -> NHWC pixel index, -1 = padding.  32-bit arithmetic on purpose (the host checks total < 2^31): the 64-bit
+// divisions of the first version cost ~100 instructions each, 30 per thread and tile -- more than the MMAs of a 32 -> 32 layer.
+__device__ __forceinline__ int t5f_pixel(const T5F& p, long long g64) {
+  if (g64 < 0 || g64 >= p.total) return -1;
+  const int g = (int)g64;
+  const int R = g / p.P, X = g - R * p.P;
   const int n = R / p.RPI, yy = R - n * p.RPI;
   if (X == 0 || yy == 0) return -1;
   return (n * p.H + (yy - 1)) * p.W + (X - 1);
@@ -394,6 +404,153 @@ __global__ void __launch_bounds__(T5_THREADS) conv3x3_tf32_tc5_kernel(const T5F 
 }
 
 
+
+// The same flat 3x3 form for layers with at most 32 input channels (the C0 = 32 branch at 64x48 and the heads at 128x96: the
+// convs on the critical path of a step): ONE channel chunk, so the halo and the weights of all nine taps (36 KB for 32 -> 32)
+// are fetched in a single cp.async batch -- one barrier round trip instead of nine -- and the 36 MMAs are issued back to back.
+__global__ void __launch_bounds__(T5_THREADS) conv3x3_tf32_small_kernel(const T5F p, const int mtiles) {
+  // persistent: a CTA keeps the weights of all nine taps and its TMEM accumulator, and walks over the 128-position tiles
+  // blockIdx.x, blockIdx.x + gridDim.x, ...; per tile only the halo is fetched (three CTAs per SM cover each other's waits)
+  extern __shared__ __align__(128) unsigned char smem_raw[];
+  __shared__ __align__(8) uint64_t bars[2];                       // operands landed | accumulator full
+  __shared__ uint32_t tmem_base_slot;
+  const uint32_t bar0 = smem_u32(&bars[0]);
+  const uint32_t sbase = (smem_u32(smem_raw) + 127u) & ~127u;
+  const uint32_t sB = sbase + p.a_bytes;                          // weights: [tap][8 k-groups][n_mma + 1][16 B]
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int n0 = blockIdx.y * p.n_mma;
+  if (tid == 0) {
+    mbar_init(bar0, T5_PROD);
+    mbar_init(bar0 + 8u, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 4) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_base_slot)), "r"(p.tmem_cols) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+  const uint32_t tmem_base = tmem_base_slot;
+
+  if (warp < 4) {
+    const int q = tid & 7, rr = tid >> 3, k = q * 4;
+    const bool kok = k < p.Ca;
+    const uint32_t sa = sbase + (uint32_t)q * p.a_plane + (uint32_t)rr * 16u;
+    const int nb = p.n_mma >> 4;
+    for (int tap = 0; tap < 9; ++tap) {                            // the weights: once per CTA, in the first tile's batch
+      const uint32_t sb = sB + (uint32_t)tap * p.b_stage + (uint32_t)q * p.b_plane + (uint32_t)rr * 16u;
+      const float* Bt = p.B + (long long)tap * p.tapB + k;
+      for (int j = 0; j < nb; ++j) {
+        const int n = n0 + rr + 16 * j;
+        const bool ok = kok && n < p.Nc;
+        cp_async16(sb + (uint32_t)j * 256u, ok ? (const void*)(Bt + (long long)n * p.ldb) : (const void*)p.B, ok ? 16u : 0u);
+      }
+    }
+    const bool vec = (p.ldc & 3) == 0 && ((reinterpret_cast<uintptr_t>(p.C) & 15u) == 0);
+    const bool vec32 = (p.ldc & 7) == 0 && ((reinterpret_cast<uintptr_t>(p.C) & 31u) == 0) && (n0 & 7) == 0;
+    const uint32_t taddr = tmem_base + ((uint32_t)(warp * 32) << 16);
+    uint32_t ph = 0;
+    for (int tile = blockIdx.x; tile < mtiles; tile += gridDim.x, ph ^= 1u) {
+      const long long f0 = (long long)tile * T5_BM;
+      {
+        // halo position rr + 16 j <-> flat position f0 - P - 1 + rr + 16 j.  ncu: with two integer divisions per position the
+        // producers' address generation WAS the kernel (38 M of its instructions, IPC 1.15); one division pair per tile and
+        // incremental (column, row-in-image, image) updates instead.  The position is shifted by one image block so that
+        // the first tile's negative positions decode with ordinary division (image index -1 = outside).
+        const int gs = (int)f0 - p.P - 1 + rr + p.RPI * p.P;
+        int R = gs / p.P, X = gs - R * p.P;
+        int n = R / p.RPI, yy = R - n * p.RPI;
+        n -= 1;
+        for (int j = 0; j < p.JH; ++j) {
+          const int hp = rr + 16 * j;
+          if (hp >= p.NP) break;
+          const bool ok = kok && n >= 0 && n < p.Nimg && X != 0 && yy != 0;
+          const int px = (n * p.H + (yy - 1)) * p.W + (X - 1);
+          cp_async16(sa + (uint32_t)j * 256u, ok ? (const void*)(p.A + (long long)px * p.lda + k) : (const void*)p.A, ok ? 16u : 0u);
+          X += 16;
+          while (X >= p.P) {
+            X -= p.P;
+            if (++yy == p.RPI) { yy = 0; ++n; }
+          }
+        }
+      }
+      asm volatile("cp.async.commit_group;" ::: "memory");
+      asm volatile("cp.async.wait_group 0;" ::: "memory");
+      asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+      mbar_arrive(bar0);
+      // epilogue of this tile (the MMAs have also finished reading the halo when the accumulator barrier completes)
+      mbar_wait(bar0 + 8u, ph);
+      asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+      const int m = t5f_pixel(p, f0 + warp * 32 + lane);
+      float* crow = p.C + (long long)(m < 0 ? 0 : m) * p.ldc + n0;
+      for (int c = 0; c < p.n_mma; c += 16) {
+        uint32_t v[16];
+        tmem_ld16(taddr + (uint32_t)c, v);
+        asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+        if (m >= 0) {
+          if (vec32 && n0 + c + 15 < p.Nc) {                       // two full sectors per lane
+            float f[16];
+#pragma unroll
+            for (int e = 0; e < 16; ++e) f[e] = __uint_as_float(v[e]) + (p.bias ? p.bias[n0 + c + e] : 0.f);
+            stg256(crow + c, f);
+            stg256(crow + c + 8, f + 8);
+          } else {
+#pragma unroll
+            for (int g = 0; g < 4; ++g) {
+              const int n = n0 + c + 4 * g;
+              if (n >= p.Nc) break;
+              float f[4];
+#pragma unroll
+              for (int e = 0; e < 4; ++e) {
+                f[e] = __uint_as_float(v[4 * g + e]);
+                if (p.bias && n + e < p.Nc) f[e] += p.bias[n + e];
+              }
+              if (vec && n + 3 < p.Nc) {
+                *reinterpret_cast<float4*>(crow + c + 4 * g) = make_float4(f[0], f[1], f[2], f[3]);
+              } else {
+#pragma unroll
+                for (int e = 0; e < 4; ++e)
+                  if (n + e < p.Nc) crow[c + 4 * g + e] = f[e];
+              }
+            }
+          }
+        }
+      }
+      asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");      // the next tile's MMAs overwrite the accumulator
+    }
+  } else {
+    const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(p.n_mma >> 3) << 17) | ((128u >> 4) << 24);
+    const uint32_t hi = desc_hi(128u);
+    const int kk = (p.Ca + 7) >> 3;                                // K = 8 steps that hold channels
+    uint32_t ph = 0;
+    for (int tile = blockIdx.x; tile < mtiles; tile += gridDim.x, ph ^= 1u) {
+      mbar_wait(bar0, ph);
+      asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+      if (elect_one()) {
+#pragma unroll 1
+        for (int tap = 0; tap < 9; ++tap) {
+          const int dy = tap / 3, dx = tap - 3 * dy;
+          const uint32_t off = p.flip ? (uint32_t)((2 - dy) * p.P + (2 - dx)) : (uint32_t)(dy * p.P + dx);
+          const uint32_t a0 = sbase + off * 16u, b0 = sB + (uint32_t)tap * p.b_stage;
+          for (int k8 = 0; k8 < kk; ++k8) {
+            const uint64_t ad = ((uint64_t)hi << 32) | desc_lo(a0 + 2u * k8 * p.a_plane, p.a_plane);
+            const uint64_t bd = ((uint64_t)hi << 32) | desc_lo(b0 + 2u * k8 * p.b_plane, p.b_plane);
+            umma_tf32(tmem_base, ad, bd, idesc, (tap | k8) ? 1u : 0u);
+          }
+        }
+        umma_commit(bar0 + 8u);
+      }
+      __syncwarp();
+    }
+  }
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  if (warp == 4) {
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(p.tmem_cols) : "memory");
+  }
+}
+
 }  // namespace
 
 // 1 when the tcgen05 kernel covers this call of rsg_train_gemm (else the mma.sync kernel runs)
@@ -418,7 +575,8 @@ int train_tc5_launch(cudaStream_t s, const float* A, const float* B, float* C, c
   }
   // every 3x3 stride-1 pad-1 convolution (forward: mode 1, input gradient: mode 2) takes the flat form
   if (mode != 0 && batch == 1 && !beta && geom[4] == 3 && geom[5] == 3 && geom[6] == 1 && geom[7] == 1 && geom[0] == geom[2] &&
-      geom[1] == geom[3] && geom[1] <= 110 && (long long)M * lda < (1ll << 31)) {
+      geom[1] == geom[3] && geom[1] <= 110 && (long long)M * lda < (1ll << 31) &&
+      (long long)(M / (geom[0] * geom[1])) * (geom[0] + 1) * (geom[1] + 1) < (1ll << 31)) {
     T5F f;
     memset(&f, 0, sizeof(f));
     f.A = A; f.B = B; f.C = C; f.bias = bias; f.H = geom[0]; f.W = geom[1]; f.Nimg = M / (f.H * f.W); f.Ca = Ca; f.Nc = Nc;
@@ -440,12 +598,27 @@ int train_tc5_launch(cudaStream_t s, const float* A, const float* B, float* C, c
     uint32_t cols = 32;
     while (cols < (uint32_t)nm) cols <<= 1;
     f.tmem_cols = cols;
-    const size_t smem = 128 + 2 * (size_t)f.a_bytes + (size_t)T5_STAGES * f.b_stage;
     static DeviceOnce once_f;
     if (once_f.first()) {
       RSG_CUDA(cudaFuncSetAttribute(conv3x3_tf32_tc5_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024));
+      RSG_CUDA(cudaFuncSetAttribute(conv3x3_tf32_small_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
       once_f.done();
     }
+    if (Ca <= 32 && nm <= 64) {                // one channel chunk: everything in one cp.async batch
+      const size_t smem_s = 128 + (size_t)f.a_bytes + 9 * (size_t)f.b_stage;
+      if (smem_s <= 100 * 1024) {
+        int occ = 0;
+        RSG_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, conv3x3_tf32_small_kernel, T5_THREADS, smem_s));
+        if (occ < 1) occ = 1;
+        int gx = occ * rsg_num_sms() / nt;     // persistent: exactly the CTAs that are resident at once
+        if (gx > mtiles) gx = mtiles;
+        if (gx < 1) gx = 1;
+        conv3x3_tf32_small_kernel<<<dim3((unsigned)gx, (unsigned)nt, 1), T5_THREADS, smem_s, s>>>(f, mtiles);
+        RSG_LAUNCH_CHECK();
+        return RSG_OK;
+      }
+    }
+    const size_t smem = 128 + 2 * (size_t)f.a_bytes + (size_t)T5_STAGES * f.b_stage;
     if (smem <= 220 * 1024) {
       conv3x3_tf32_tc5_kernel<<<dim3((unsigned)mtiles, (unsigned)nt, 1), T5_THREADS, smem, s>>>(f);
       RSG_LAUNCH_CHECK();

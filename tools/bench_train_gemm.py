@@ -35,16 +35,25 @@ for idx, (N, H, W, Ci, Co, k, s) in enumerate(SHAPES):
                 dx = torch.empty_like(x)
                 fn = (lambda f=fn: tape._gemm(pr, out.g, wp, dx, None, N * H * W, Ci, Co, Co, Co, Ci, mode=0 if k == 1 else 2, transB=1,
                                               geom=None if k == 1 else (out.shape[1], out.shape[2], H, W, k, k, s, k // 2)))
-            for _ in range(2):
-                fn()
-            torch.cuda.synchronize()
-            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-            e0.record()
-            for _ in range(5):
-                fn()
-            e1.record()
-            torch.cuda.synchronize()
-            res[name] = e0.elapsed_time(e1) / 5
+            # ten launches replayed as a CUDA graph: eager launches from Python cost ~25 us each, more than the small kernels
+            side = torch.cuda.Stream()
+            side.wait_stream(torch.cuda.current_stream())
+            with torch.cuda.stream(side):
+                for _ in range(2):
+                    fn()
+                torch.cuda.synchronize()
+                gph = torch.cuda.CUDAGraph()
+                with torch.cuda.graph(gph, stream=side):
+                    for _ in range(10):
+                        fn()
+                gph.replay()
+                torch.cuda.synchronize()
+                e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                e0.record(side)
+                gph.replay()
+                e1.record(side)
+                torch.cuda.synchronize()
+            res[name] = e0.elapsed_time(e1) / 10
         row.append(res)
     gf = 2.0 * N * (H // s) * (W // s) * Ci * Co * k * k / 1e9
     print(f'{N}x{H}x{W} {Ci}->{Co} k{k} s{s}: {gf:6.1f} GF | tc5 fwd {row[0]["fwd"]*1e3:7.0f} us ({gf/row[0]["fwd"]:6.1f} TF) dgrad {row[0]["dgrad"]*1e3:7.0f} us ({gf/row[0]["dgrad"]:6.1f} TF)'
