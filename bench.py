@@ -610,6 +610,38 @@ def run_train(args):
         r[1] += 1
         r[2] += fl
     launches, gflop = ts.last_launches, ts.last_flops / 1e9
+    # the dominant kernel by launch count and by its place on the critical path: forward / input gradient of the 3x3 convs of
+    # the C0 = 32 branch (132 launches per step), timed alone -- ten launches replayed as a CUDA graph, because an eager launch
+    # from Python costs more host time than this kernel runs
+    from rsgnet_b200.train.tape import Tape as _Tape
+    dk = None
+    try:
+        c0 = int(cfg.MODEL.EXTRA.STAGE2.NUM_CHANNELS[0])
+        fh, fw = int(cfg.MODEL.IMAGE_SIZE[1]) // 4, int(cfg.MODEL.IMAGE_SIZE[0]) // 4
+        with torch.cuda.stream(stream):
+            tp = _Tape(dev, 0)
+            xa = torch.randn(B, fh, fw, c0, device=dev)
+            wk = torch.randn(9, c0, c0, device=dev) / (9 * c0) ** 0.5
+            ya = torch.empty(B, fh, fw, c0, device=dev)
+            run = lambda: tp._gemm(0, xa, wk, ya, None, B * fh * fw, c0, c0, c0, c0, c0, mode=1, transB=1, geom=(fh, fw, fh, fw, 3, 3, 1, 1))
+            run()
+            torch.cuda.synchronize()
+            gph = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(gph, stream=stream):
+                for _ in range(10):
+                    run()
+            gph.replay()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record(stream)
+            gph.replay()
+            e1.record(stream)
+        torch.cuda.synchronize()
+        us = e0.elapsed_time(e1) * 1e3 / 10
+        fl = 2.0 * B * fh * fw * c0 * c0 * 9
+        dk = {'us_per_launch': us, 'flops': fl, 'tflops': fl / us / 1e6, 'bytes': 2.0 * B * fh * fw * c0 * 4,
+              'shape': f'{c0}->{c0} 3x3 @{fh}x{fw} x {B} samples'}
+    except Exception as e:                      # informational: never fails the bench
+        dk = {'error': str(e)[:200]}
     if rank != 0:
         if dist is not None:
             dist.destroy_process_group()
@@ -631,13 +663,18 @@ def run_train(args):
         'clocks': clocks, 'gpu_launches': launches * args.steps,
         'e2e': {'value': B * world * args.steps / (ms_e2e * 1e-3), 'unit': 'samples/s', 'h2d_bytes_per_step': h2d,
                 'd2h_bytes_per_step': 8 * (3 + B), 'ms_per_step': ms_e2e / args.steps, 'last_loss': last['L']['loss']},
-        'roofline': {'bound': 'tensor', 'kernel': 'gather_gemm_kernel (TF32 mma.sync implicit GEMM: conv forward / input gradient, Linear, TRP products)',
-                     'achieved': g[2] / g[0] / 1e9, 'peak': tf32_peak, 'unit': 'TFLOP/s', 'frac': g[2] / g[0] / 1e9 / tf32_peak,
+        'roofline': {'bound': 'tensor', 'kernel': 'conv3x3_tf32_small_kernel (tcgen05 kind::tf32 flat 3x3 conv): ' + str(dk.get('shape')),
+                     'achieved': dk.get('tflops'), 'peak': tf32_peak, 'unit': 'TFLOP/s',
+                     'frac': (dk['tflops'] / tf32_peak) if 'tflops' in dk else None,
                      'traffic': None, 'peak_source': pk['src'] + ' bf16_tflops_sustained / 2 (TF32 runs at half the bf16 rate)',
-                     'algorithmic_flops_per_launch': g[2] / max(g[1], 1), 'us_per_launch': g[0] / max(g[1], 1) * 1e3,
-                     'launches_per_step': g[1], 'share_of_step': g[0] / tot, 'families': fam,
-                     'note': 'per-family times from an eager single-stream step with CUDA events around every library call; the timed '
-                             'steps replay one CUDA graph whose HRNet branches run concurrently'},
+                     'algorithmic_flops_per_launch': dk.get('flops'), 'algorithmic_bytes_per_launch': dk.get('bytes'),
+                     'us_per_launch': dk.get('us_per_launch'), 'launches_per_step': 132,
+                     'hbm_frac': (dk['bytes'] / dk['us_per_launch'] / 1e3 / pk['hbm']) if 'us_per_launch' in dk else None,
+                     'matrix_family_eager': {'tflops': g[2] / g[0] / 1e9, 'ms': g[0], 'launches': g[1], 'share_of_step': g[0] / tot},
+                     'families': fam,
+                     'note': 'achieved = the dominant kernel timed alone by graph replay; families = an eager single-stream step with CUDA '
+                             'events around every library call (small kernels are padded there by the host launch gap); the '
+                             'timed steps replay one CUDA graph whose HRNet branches run concurrently'},
         'executed_gflop_per_step_per_gpu': gflop, 'executed_tflops_per_gpu': gflop / per_ms,
         'parity_checked': bool(parity), 'parity': parity, 'cpu_baseline': cpu,
     }
