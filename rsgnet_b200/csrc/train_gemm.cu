@@ -518,6 +518,7 @@ struct WgradFlatP {
   const float* X; const float* dY; float* dW;
   int Nimg, H, W, Ca, Nc, ldx, ldy, P, RPI, NPH;
   long long total, per_split;
+  uint32_t magicP, magicR;          // ceil(2^32 / P), ceil(2^32 / RPI): exact multiply-high quotients for every flat position
 };
 
 __device__ __forceinline__ int wf_pixel(const WgradFlatP& p, long long gpos) {
@@ -552,22 +553,17 @@ __global__ void __launch_bounds__(WF_THREADS, 1) wgrad32_flat_kernel(const Wgrad
       float* Xs = wf_smem + (c & 1) * stage_f;
       float* Ys = Xs + p.NPH * WF_PITCH;
       const long long f0 = fb + (long long)c * WF_PX;
-      // one division pair per chunk, then incremental (column, row-in-image, image) updates (36 positions per step); the
-      // position is shifted by one image block so that negative halo positions decode with ordinary division
+      // flat position -> pixel by multiply-high division (magic numbers from the host); the position is shifted by one image
+      // block so that negative halo positions decode too (image index -1 = outside)
       auto walk = [&](long long g0, int nrows, long long glimit, auto&& emit) {
-        const int gs = (int)g0 + p.RPI * p.P;
-        int R = gs / p.P, Xc = gs - R * p.P;
-        int n = R / p.RPI, yy = R - n * p.RPI;
-        n -= 1;
         long long gp = g0;
         for (int r = r0; r < nrows; r += WF_THREADS / 8, gp += WF_THREADS / 8) {
+          const uint32_t gs = (uint32_t)((int)gp + p.RPI * p.P);
+          const uint32_t R = __umulhi(gs, p.magicP), Xc = gs - R * (uint32_t)p.P;
+          const uint32_t nn = __umulhi(R, p.magicR), yy = R - nn * (uint32_t)p.RPI;
+          const int n = (int)nn - 1;
           const bool ok = gp < glimit && n >= 0 && n < p.Nimg && Xc != 0 && yy != 0;
-          emit(r, ok, (n * p.H + (yy - 1)) * p.W + (Xc - 1));
-          Xc += WF_THREADS / 8;
-          while (Xc >= p.P) {
-            Xc -= p.P;
-            if (++yy == p.RPI) { yy = 0; ++n; }
-          }
+          emit(r, ok, (n * p.H + ((int)yy - 1)) * p.W + ((int)Xc - 1));
         }
       };
       walk(f0 - p.P - 1 + r0, p.NPH, fe + p.P + 1, [&](int r, bool ok, int px) {
@@ -835,6 +831,8 @@ extern "C" int rsg_train_wgrad(void* stream, const float* X, const float* dY, fl
     f.X = X; f.dY = dY; f.dW = dW; f.H = geom[0]; f.W = geom[1]; f.Nimg = M / (f.H * f.W); f.Ca = Ca; f.Nc = Nc; f.ldx = ldx; f.ldy = ldy;
     f.P = f.W + 1; f.RPI = f.H + 1; f.NPH = WF_PX + 2 * f.P + 2;
     f.total = (long long)f.Nimg * f.RPI * f.P;
+    f.magicP = (uint32_t)(((1ull << 32) + f.P - 1) / f.P);
+    f.magicR = (uint32_t)(((1ull << 32) + f.RPI - 1) / f.RPI);
     long long splits = 2ll * rsg_num_sms(), maxsplit = (f.total + 4 * WF_PX - 1) / (4 * WF_PX);
     if (splits > maxsplit) splits = maxsplit;
     if (splits < 1) splits = 1;

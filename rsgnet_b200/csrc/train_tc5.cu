@@ -241,6 +241,7 @@ struct T5F {
   long long total;                 // Nimg * RPI * P flat positions
   int flip, beta, n_mma;
   uint32_t a_plane, b_plane, a_bytes, b_stage, tmem_cols;
+  uint32_t magicP, magicR;         // ceil(2^32 / P), ceil(2^32 / RPI): exact quotients for every flat position (< 2^32 / P)
 };
 constexpr int T5F_MAXJ = 22;       // NP <= 16 * 22 = 352: W <= 110
 
@@ -248,11 +249,11 @@ constexpr int T5F_MAXJ = 22;       // NP <= 16 * 22 = 352: W <= 110
 // divisions of the first version cost ~100 instructions each, 30 per thread and tile -- more than the MMAs of a 32 -> 32 layer.
 __device__ __forceinline__ int t5f_pixel(const T5F& p, long long g64) {
   if (g64 < 0 || g64 >= p.total) return -1;
-  const int g = (int)g64;
-  const int R = g / p.P, X = g - R * p.P;
-  const int n = R / p.RPI, yy = R - n * p.RPI;
+  const uint32_t g = (uint32_t)g64;
+  const uint32_t R = __umulhi(g, p.magicP), X = g - R * (uint32_t)p.P;          // exact: g < 2^32 / P (host check)
+  const uint32_t n = __umulhi(R, p.magicR), yy = R - n * (uint32_t)p.RPI;
   if (X == 0 || yy == 0) return -1;
-  return (n * p.H + (yy - 1)) * p.W + (X - 1);
+  return ((int)n * p.H + ((int)yy - 1)) * p.W + ((int)X - 1);
 }
 
 __global__ void __launch_bounds__(T5_THREADS) conv3x3_tf32_tc5_kernel(const T5F p) {
@@ -458,21 +459,20 @@ __global__ void __launch_bounds__(T5_THREADS) conv3x3_tf32_small_kernel(const T5
         // producers' address generation WAS the kernel (38 M of its instructions, IPC 1.15); one division pair per tile and
         // incremental (column, row-in-image, image) updates instead.  The position is shifted by one image block so that
         // the first tile's negative positions decode with ordinary division (image index -1 = outside).
-        const int gs = (int)f0 - p.P - 1 + rr + p.RPI * p.P;
-        int R = gs / p.P, X = gs - R * p.P;
-        int n = R / p.RPI, yy = R - n * p.RPI;
-        n -= 1;
+        // multiply-high division by the two constants (magic numbers from the host): ~10 independent instructions per
+        // position instead of two ~35-instruction division sequences or a loop-carried incremental update (clock64 timeline:
+        // the decode was 2450 of the 8500 cycles of a tile)
+        const uint32_t gs0 = (uint32_t)((int)f0 - p.P - 1 + rr + p.RPI * p.P);
         for (int j = 0; j < p.JH; ++j) {
           const int hp = rr + 16 * j;
           if (hp >= p.NP) break;
+          const uint32_t gs = gs0 + 16u * (uint32_t)j;
+          const uint32_t R = __umulhi(gs, p.magicP), X = gs - R * (uint32_t)p.P;
+          const uint32_t nn = __umulhi(R, p.magicR), yy = R - nn * (uint32_t)p.RPI;
+          const int n = (int)nn - 1;
           const bool ok = kok && n >= 0 && n < p.Nimg && X != 0 && yy != 0;
-          const int px = (n * p.H + (yy - 1)) * p.W + (X - 1);
+          const int px = (n * p.H + ((int)yy - 1)) * p.W + ((int)X - 1);
           cp_async16(sa + (uint32_t)j * 256u, ok ? (const void*)(p.A + (long long)px * p.lda + k) : (const void*)p.A, ok ? 16u : 0u);
-          X += 16;
-          while (X >= p.P) {
-            X -= p.P;
-            if (++yy == p.RPI) { yy = 0; ++n; }
-          }
         }
       }
       asm volatile("cp.async.commit_group;" ::: "memory");
@@ -584,6 +584,8 @@ int train_tc5_launch(cudaStream_t s, const float* A, const float* B, float* C, c
     f.NP = T5_BM + 2 * f.P + 2; f.JH = (f.NP + 15) / 16;
     f.total = (long long)f.Nimg * f.RPI * f.P;
     f.flip = mode == 2; f.beta = beta;
+    f.magicP = (uint32_t)(((1ull << 32) + f.P - 1) / f.P);
+    f.magicR = (uint32_t)(((1ull << 32) + f.RPI - 1) / f.RPI);
     const int mtiles = (int)((f.total + T5_BM - 1) / T5_BM);
     int nm = (Nc + 15) / 16 * 16;
     if (nm > 256) nm = 256;
