@@ -11,9 +11,10 @@
 //
 // Math: mma.sync m16n8k8 TF32 with fp32 accumulation (what the reference's cuDNN path does on an Ampere-or-later GPU:
 // torch.backends.cudnn.allow_tf32 defaults to True).  `precise` = 3xTF32 (hi/lo split of both operands: fp32-class
-// products), used by the parity tests to separate logic errors from rounding.  These are first-correct kernels: 128 x 64
-// (or 128 x 32) CTA tiles, register-staged global -> shared copies; the tcgen05 treatment the inference convs got is the
-// next step for this row.
+// products), used by the parity tests to separate logic errors from rounding, and always for the TRP's forward products.
+// In the production TF32 mode rsg_train_gemm routes every call with a K-major B operand to the tcgen05 kind::tf32 kernels of
+// train_tc5.cu; this file keeps the mma.sync implicit GEMM (3xTF32, transposed / odd-shaped products) and the weight-gradient
+// kernels (which cannot use tcgen05 for TF32: both operands are MN-major, see wgrad below).
 #include "common.cuh"
 #include "../../include/rsg_b200.h"
 

@@ -3,7 +3,8 @@
 The reference gets its backward pass from torch autograd over cuDNN / cuBLAS (lib/core/function.py:240-363 calls
 ``loss.backward()``).  Here every operation of the train-mode forward (lib/models/pose_rsgnet.py:955-1021) is one or a few
 calls into librsg_b200.so, and records a closure that issues the matching backward kernels.  torch supplies device memory
-(``torch.empty``) and the current stream only; no torch kernel computes anything on this path.
+(``torch.empty``), streams and events; the only torch kernels on this path are bookkeeping: the ``num_batches_tracked``
+counters (one ``_foreach_add_``), input copies into the graph's static buffers, and the gradient snapshot of the drop-in route.
 
 Activations are fp32 NHWC tensors ``[N, H, W, C]`` (or plain matrices ``[M, C]``).
 """
