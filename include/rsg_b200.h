@@ -328,6 +328,14 @@ int rsg_train_bn_fwd(void* stream, const float* x, long long M, int C, const flo
 int rsg_train_bn_bwd(void* stream, const float* x, const float* y, const float* dy, long long M, int C, const float* gamma,
                      const float* save_mean, const float* save_invstd, int relu, float* dx, float* dgamma, float* dbeta,
                      double* ws);
+/* The same with the residual branch of a BasicBlock / Bottleneck fused in (pose_rsgnet.py:47-52, 88-93): y = relu(bn(x) + res)
+ * (res NULL = plain), and in the backward pass dres = dy * [y > 0], the gradient of the residual input (dres NULL = none). */
+int rsg_train_bn_fwd_res(void* stream, const float* x, long long M, int C, const float* gamma, const float* beta, float eps,
+                         float momentum, float* running_mean, float* running_var, int relu, const float* res, float* y,
+                         float* save_mean, float* save_invstd, double* ws);
+int rsg_train_bn_bwd_res(void* stream, const float* x, const float* y, const float* dy, long long M, int C, const float* gamma,
+                         const float* save_mean, const float* save_invstd, int relu, float* dx, float* dres, float* dgamma,
+                         float* dbeta, double* ws);
 /* out[c] (+)= sum over the M rows of x[m][c]  (bias gradients; backward of a batch broadcast).  ws = C doubles (cleared
  * before and after use). */
 int rsg_train_colsum(void* stream, const float* x, long long M, int C, float* out, int accumulate, double* ws);

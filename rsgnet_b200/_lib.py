@@ -128,6 +128,10 @@ _SIGS = {
                                    C.c_float, C.c_void_p, C.c_void_p, C.c_int] + [C.c_void_p] * 4),
     'rsg_train_bn_bwd': (C.c_int, [C.c_void_p] * 4 + [C.c_longlong, C.c_int] + [C.c_void_p] * 3 + [C.c_int] +
                          [C.c_void_p] * 4),
+    'rsg_train_bn_fwd_res': (C.c_int, [C.c_void_p, C.c_void_p, C.c_longlong, C.c_int, C.c_void_p, C.c_void_p, C.c_float,
+                                       C.c_float, C.c_void_p, C.c_void_p, C.c_int] + [C.c_void_p] * 5),
+    'rsg_train_bn_bwd_res': (C.c_int, [C.c_void_p] * 4 + [C.c_longlong, C.c_int] + [C.c_void_p] * 3 + [C.c_int] +
+                             [C.c_void_p] * 5),
     'rsg_train_colsum': (C.c_int, [C.c_void_p, C.c_void_p, C.c_longlong, C.c_int, C.c_void_p, C.c_int, C.c_void_p]),
     'rsg_train_gn_fwd': (C.c_int, [C.c_void_p, C.c_void_p] + [C.c_int] * 4 + [C.c_void_p] * 2 + [C.c_float] +
                          [C.c_void_p] * 3),

@@ -248,8 +248,8 @@ __global__ void __launch_bounds__(EW_THREADS) chan_reduce4_kernel(const float* _
 
 __global__ void __launch_bounds__(EW_THREADS) bn_apply4_kernel(const float* __restrict__ x, const float* __restrict__ mean,
                                                                const float* __restrict__ invstd, const float* __restrict__ gamma,
-                                                               const float* __restrict__ beta, int relu, long long M, int C,
-                                                               int rows_per_block, float* __restrict__ y) {
+                                                               const float* __restrict__ beta, const float* __restrict__ res, int relu,
+                                                               long long M, int C, int rows_per_block, float* __restrict__ y) {
   const int CQ = C >> 2, CT = CQ < EW_THREADS ? CQ : EW_THREADS, G = EW_THREADS / CT;
   const int tid = threadIdx.x, g = tid / CT, cl = tid - g * CT;
   if (g >= G) return;
@@ -261,9 +261,11 @@ __global__ void __launch_bounds__(EW_THREADS) bn_apply4_kernel(const float* __re
     for (long long r = r0 + g; r < r1; r += G) {
       const long long i = r * C + 4 * cq;
       F4 v = ld4(x + i);
+      F4 rv = {{0.f, 0.f, 0.f, 0.f}};
+      if (res) rv = ld4(res + i);                       // residual branch of a BasicBlock / Bottleneck: relu(bn(x) + res)
 #pragma unroll
       for (int e = 0; e < 4; ++e) {
-        v.v[e] = (v.v[e] - mu.v[e]) * is.v[e] * ga.v[e] + be.v[e];
+        v.v[e] = (v.v[e] - mu.v[e]) * is.v[e] * ga.v[e] + be.v[e] + rv.v[e];
         if (relu) v.v[e] = fmaxf(v.v[e], 0.f);
       }
       st4(y + i, v);
@@ -275,7 +277,7 @@ __global__ void __launch_bounds__(EW_THREADS) bn_bwd_apply4_kernel(const float* 
                                                                    const float* __restrict__ y, const float* __restrict__ mean,
                                                                    const float* __restrict__ invstd, const float* __restrict__ gamma,
                                                                    const float* __restrict__ fsum, int relu, long long M, int C,
-                                                                   int rows_per_block, float* __restrict__ dx) {
+                                                                   int rows_per_block, float* __restrict__ dx, float* __restrict__ dres) {
   const int CQ = C >> 2, CT = CQ < EW_THREADS ? CQ : EW_THREADS, G = EW_THREADS / CT;
   const int tid = threadIdx.x, g = tid / CT, cl = tid - g * CT;
   if (g >= G) return;
@@ -301,10 +303,13 @@ __global__ void __launch_bounds__(EW_THREADS) bn_bwd_apply4_kernel(const float* 
 #pragma unroll
         for (int e = 0; e < 4; ++e) if (!(yv.v[e] > 0.f)) d.v[e] = 0.f;
       }
-      F4 o;
+      if (dres) st4(dres + i, d);                      // gradient of the residual input: the ReLU-masked dy
+      if (dx) {
+        F4 o;
 #pragma unroll
-      for (int e = 0; e < 4; ++e) o.v[e] = sc[e] * (d.v[e] - m0[e] - (xv.v[e] - mu.v[e]) * is.v[e] * m1[e]);
-      st4(dx + i, o);
+        for (int e = 0; e < 4; ++e) o.v[e] = sc[e] * (d.v[e] - m0[e] - (xv.v[e] - mu.v[e]) * is.v[e] * m1[e]);
+        st4(dx + i, o);
+      }
     }
   }
 }
@@ -766,11 +771,13 @@ __global__ void __launch_bounds__(EW_THREADS) adam_kernel(float* __restrict__ p,
 // C ABI
 // Scratch contract of the BatchNorm entry points: ws holds 3 C + 4 doubles and is ZERO on entry of the float4 path, which leaves
 // it zero (the last reduction block cleans up); the scalar fallback and rsg_train_colsum clear what they use before and after.
-extern "C" int rsg_train_bn_fwd(void* stream, const float* x, long long M, int C, const float* gamma, const float* beta, float eps,
-                                float momentum, float* running_mean, float* running_var, int relu, float* y, float* save_mean,
-                                float* save_invstd, double* ws) {
+extern "C" int rsg_train_bn_fwd_res(void* stream, const float* x, long long M, int C, const float* gamma, const float* beta, float eps,
+                                    float momentum, float* running_mean, float* running_var, int relu, const float* res, float* y,
+                                    float* save_mean, float* save_invstd, double* ws) {
   RSG_REQUIRE(x && y && gamma && beta && save_mean && save_invstd && ws && M > 0 && C > 0, "bn_fwd: bad arguments");
-  const bool v4 = (C & 3) == 0 && al16p(x) && al16p(y) && al16p(gamma) && al16p(beta) && al16p(save_mean) && al16p(save_invstd);
+  const bool v4 = (C & 3) == 0 && al16p(x) && al16p(y) && al16p(gamma) && al16p(beta) && al16p(save_mean) && al16p(save_invstd) &&
+                  al16p(res);
+  RSG_REQUIRE(v4 || !res, "bn_fwd: the fused residual needs the float4 path (C %% 4 == 0, 16-byte aligned tensors)");
   int rpb, blocks;
   const int yt = v4 ? ceil_div(C / 4, EW_THREADS) : ceil_div(C, EW_THREADS);
   chan_reduce_cfg(M, rpb, blocks, yt);
@@ -782,7 +789,7 @@ extern "C" int rsg_train_bn_fwd(void* stream, const float* x, long long M, int C
     fin.running_mean = running_mean; fin.running_var = running_var;
     chan_reduce4_kernel<0><<<dim3(blocks, yt), EW_THREADS, 0, ST>>>(x, nullptr, nullptr, nullptr, nullptr, 0, M, C, rpb, ws, fin);
     rows_cfg(M, 16, rpb, blocks);
-    bn_apply4_kernel<<<blocks, EW_THREADS, 0, ST>>>(x, save_mean, save_invstd, gamma, beta, relu, M, C, rpb, y);
+    bn_apply4_kernel<<<blocks, EW_THREADS, 0, ST>>>(x, save_mean, save_invstd, gamma, beta, res, relu, M, C, rpb, y);
   } else {
     RSG_CUDA(cudaMemsetAsync(ws, 0, 2 * (size_t)C * sizeof(double), ST));
     chan_reduce_kernel<0><<<dim3(blocks, yt), EW_THREADS, 0, ST>>>(x, nullptr, nullptr, nullptr, nullptr, 0, M, C, rpb, ws);
@@ -794,12 +801,13 @@ extern "C" int rsg_train_bn_fwd(void* stream, const float* x, long long M, int C
   return RSG_OK;
 }
 
-extern "C" int rsg_train_bn_bwd(void* stream, const float* x, const float* y, const float* dy, long long M, int C, const float* gamma,
-                                const float* save_mean, const float* save_invstd, int relu, float* dx, float* dgamma, float* dbeta,
-                                double* ws) {
+extern "C" int rsg_train_bn_bwd_res(void* stream, const float* x, const float* y, const float* dy, long long M, int C,
+                                    const float* gamma, const float* save_mean, const float* save_invstd, int relu, float* dx,
+                                    float* dres, float* dgamma, float* dbeta, double* ws) {
   RSG_REQUIRE(x && dy && gamma && save_mean && save_invstd && ws && M > 0 && C > 0 && (!relu || y), "bn_bwd: bad arguments");
   const bool v4 = (C & 3) == 0 && al16p(x) && al16p(dy) && (!relu || al16p(y)) && (!dx || al16p(dx)) && al16p(gamma) &&
-                  al16p(save_mean) && al16p(save_invstd);
+                  al16p(save_mean) && al16p(save_invstd) && al16p(dres);
+  RSG_REQUIRE(v4 || !dres, "bn_bwd: the fused residual gradient needs the float4 path");
   int rpb, blocks;
   const int yt = v4 ? ceil_div(C / 4, EW_THREADS) : ceil_div(C, EW_THREADS);
   chan_reduce_cfg(M, rpb, blocks, yt);
@@ -810,9 +818,9 @@ extern "C" int rsg_train_bn_bwd(void* stream, const float* x, const float* y, co
     fin.fsum = reinterpret_cast<float*>(ws + 2 * (size_t)C + 2);              // 2 C floats behind the sums and the ticket
     fin.dgamma = dgamma; fin.dbeta = dbeta;
     chan_reduce4_kernel<1><<<dim3(blocks, yt), EW_THREADS, 0, ST>>>(x, dy, y, save_mean, save_invstd, relu, M, C, rpb, ws, fin);
-    if (dx) {
+    if (dx || dres) {
       rows_cfg(M, 16, rpb, blocks);
-      bn_bwd_apply4_kernel<<<blocks, EW_THREADS, 0, ST>>>(x, dy, y, save_mean, save_invstd, gamma, fin.fsum, relu, M, C, rpb, dx);
+      bn_bwd_apply4_kernel<<<blocks, EW_THREADS, 0, ST>>>(x, dy, y, save_mean, save_invstd, gamma, fin.fsum, relu, M, C, rpb, dx, dres);
     }
   } else {
     RSG_CUDA(cudaMemsetAsync(ws, 0, 2 * (size_t)C * sizeof(double), ST));
@@ -822,6 +830,19 @@ extern "C" int rsg_train_bn_bwd(void* stream, const float* x, const float* y, co
   }
   RSG_LAUNCH_CHECK();
   return RSG_OK;
+}
+
+extern "C" int rsg_train_bn_fwd(void* stream, const float* x, long long M, int C, const float* gamma, const float* beta, float eps,
+                                float momentum, float* running_mean, float* running_var, int relu, float* y, float* save_mean,
+                                float* save_invstd, double* ws) {
+  return rsg_train_bn_fwd_res(stream, x, M, C, gamma, beta, eps, momentum, running_mean, running_var, relu, nullptr, y, save_mean,
+                              save_invstd, ws);
+}
+
+extern "C" int rsg_train_bn_bwd(void* stream, const float* x, const float* y, const float* dy, long long M, int C, const float* gamma,
+                                const float* save_mean, const float* save_invstd, int relu, float* dx, float* dgamma, float* dbeta,
+                                double* ws) {
+  return rsg_train_bn_bwd_res(stream, x, y, dy, M, C, gamma, save_mean, save_invstd, relu, dx, nullptr, dgamma, dbeta, ws);
 }
 
 extern "C" int rsg_train_colsum(void* stream, const float* x, long long M, int C, float* out, int accumulate, double* ws) {

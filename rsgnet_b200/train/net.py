@@ -26,6 +26,10 @@ class Net:
         return self.t.batchnorm(x, self.s.raw(bn.weight), self.s.raw(bn.bias), bn.running_mean, bn.running_var, relu,
                                 bn.eps, bn.momentum)
 
+    def bn_add_relu(self, x, bn, res):
+        return self.t.batchnorm_add_relu(x, self.s.raw(bn.weight), self.s.raw(bn.bias), bn.running_mean, bn.running_var, res,
+                                         bn.eps, bn.momentum)
+
     def cbr(self, x, seq, relu):
         """Sequential(conv, BN[, ReLU]) as built by _params.conv_bn."""
         conv = seq[0]
@@ -40,14 +44,12 @@ class Net:
     def bottleneck(self, x, b):
         y = self.bn(self.conv(x, b.conv1), b.bn1, True)
         y = self.bn(self.conv(y, b.conv2), b.bn2, True)
-        y = self.bn(self.conv(y, b.conv3), b.bn3, False)
         r = self.cbr(x, b.downsample, False) if hasattr(b, 'downsample') else x
-        return self.t.add([y, r], relu=True)
+        return self.bn_add_relu(self.conv(y, b.conv3), b.bn3, r)
 
     def basic(self, x, b):
         y = self.bn(self.conv(x, b.conv1), b.bn1, True)
-        y = self.bn(self.conv(y, b.conv2), b.bn2, False)
-        return self.t.add([y, x], relu=True)
+        return self.bn_add_relu(self.conv(y, b.conv2), b.bn2, x)
 
     def hr_module(self, xs, mod):
         nb = len(xs)

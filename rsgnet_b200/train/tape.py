@@ -368,6 +368,34 @@ class Tape:
         self.record(bwd)
         return out
 
+    def batchnorm_add_relu(self, x, gamma, beta, running_mean, running_var, res, eps=1e-5, momentum=0.1):
+        """relu(bn(x) + res): the tail of a BasicBlock / Bottleneck (pose_rsgnet.py:47-52, 88-93) in the BN's own two launches --
+        the residual add + ReLU and, backward, the ReLU mask are folded into the apply kernels."""
+        Cn = x.shape[-1]
+        if Cn % 4:
+            return self.add([self.batchnorm(x, gamma, beta, running_mean, running_var, False, eps, momentum), res], relu=True)
+        M = x.v.numel() // Cn
+        y = self.new(*x.shape)
+        mean, invstd = self.new(Cn), self.new(Cn)
+        self.call('rsg_train_bn_fwd_res', _p(x.v), M, Cn, _p(gamma.v), _p(beta.v), eps, momentum, _p(running_mean),
+                  _p(running_var), 1, _p(res.v), _p(y), _p(mean), _p(invstd), _p(self.ws(3 * Cn + 4)), n=2)
+        out = T(y)
+
+        def bwd():
+            dy = out.g
+            if dy is None:
+                return
+            dx = self.new(*x.shape) if x.req else None
+            dres = self.new(*x.shape) if res.req else None
+            self.call('rsg_train_bn_bwd_res', _p(x.v), _p(y), _p(dy), M, Cn, _p(gamma.v), _p(mean), _p(invstd), 1, _p(dx), _p(dres),
+                      _p(gamma.g) if gamma.req else None, _p(beta.g) if beta.req else None, _p(self.ws(3 * Cn + 4)), n=2)
+            if dres is not None:
+                self.acc(res, dres)
+            if dx is not None:
+                self.acc(x, dx)
+        self.record(bwd)
+        return out
+
     def groupnorm(self, x, gamma, beta, groups=8, eps=1e-5):
         B = x.shape[0]
         Cn = x.shape[-1]

@@ -391,3 +391,27 @@ def test_losses_person_mask_adam():
         _lib.check(_lib.lib().rsg_train_adam(tape.st, _p(dw), _p(d_g), _p(m), _p(v), n, 1e-3, 0.9, 0.999, 1e-8, step, 0.5))
         torch.cuda.synchronize()
     assert _rel(dw, pw.data) < 1e-6
+
+
+@pytest.mark.parametrize('M,C', [(2 * 24 * 16, 32), (4096, 256), (777, 64)])
+def test_batchnorm_add_relu_fused(M, C):
+    """relu(bn(x) + res) and its backward (BasicBlock / Bottleneck tails, pose_rsgnet.py:47-52, 88-93) in the BN's two launches."""
+    rs = np.random.RandomState(15)
+    x = (rs.standard_normal((M, C)) * rs.uniform(0.5, 2, C) + rs.uniform(-1, 1, C)).astype(np.float32)
+    r = rs.standard_normal((M, C)).astype(np.float32)
+    gam, bet = rs.uniform(0.5, 1.5, C).astype(np.float32), rs.standard_normal(C).astype(np.float32)
+    rm, rv = rs.standard_normal(C).astype(np.float32), rs.uniform(0.5, 1.5, C).astype(np.float32)
+    tape = _tape()
+    xn, rn, gn, bn = _node(x), _node(r), _param(gam), _param(bet)
+    rmd, rvd = torch.from_numpy(rm).to(DEV), torch.from_numpy(rv).to(DEV)
+    out = tape.batchnorm_add_relu(xn, gn, bn, rmd, rvd, rn, 1e-5, 0.1)
+    R = _run(tape, out, rs)
+    xt, rt = torch.from_numpy(x).double().requires_grad_(True), torch.from_numpy(r).double().requires_grad_(True)
+    gt, bt = torch.from_numpy(gam).double().requires_grad_(True), torch.from_numpy(bet).double().requires_grad_(True)
+    rmt, rvt = torch.from_numpy(rm).double(), torch.from_numpy(rv).double()
+    ref = F.relu(F.batch_norm(xt, rmt, rvt, gt, bt, True, 0.1, 1e-5) + rt)
+    (ref * R).sum().backward()
+    assert _rel(out.v, ref) < 1e-5
+    assert _rel(xn.g, xt.grad) < 5e-5 and _rel(rn.g, rt.grad) < 1e-6
+    assert _rel(gn.g, gt.grad) < 2e-5 and _rel(bn.g, bt.grad) < 2e-5
+    assert _rel(rmd, rmt) < 1e-6 and _rel(rvd, rvt) < 1e-5
