@@ -736,6 +736,36 @@ __global__ void __launch_bounds__(EW_THREADS) trp_dscore_kernel(const float* __r
   }
 }
 
+// float4 / row-wise form of the same (S % 4 == 0): no index divisions, v[i] a scalar per row
+__global__ void __launch_bounds__(EW_THREADS) trp_dscore4_kernel(const float* __restrict__ P, const float* __restrict__ dP,
+                                                                 const float* __restrict__ T, const float* __restrict__ v,
+                                                                 const float* __restrict__ coef, int S, int blocks_per_b,
+                                                                 float* __restrict__ dA) {
+  const int b = blockIdx.x / blocks_per_b, part = blockIdx.x % blocks_per_b;
+  const long long base = (long long)b * S * S;
+  const float cb = coef ? coef[b] : 0.f;
+  const float* vb = v ? v + (long long)b * S : nullptr;
+  for (int i = part; i < S; i += blocks_per_b) {
+    const long long ro = base + (long long)i * S;
+    const float4* Pr = reinterpret_cast<const float4*>(P + ro);
+    const float4* Dr = dP ? reinterpret_cast<const float4*>(dP + ro) : nullptr;
+    const float4* Tr = (coef && T) ? reinterpret_cast<const float4*>(T + ro) : nullptr;
+    float4* Ar = reinterpret_cast<float4*>(dA + ro);
+    const float vi = (coef && vb) ? vb[i] : 0.f;
+    for (int j = threadIdx.x; j < S / 4; j += blockDim.x) {
+      const float4 pp = Pr[j];
+      float4 d = Dr ? Dr[j] : make_float4(0.f, 0.f, 0.f, 0.f);
+      if (coef) {
+        float4 tt;
+        if (Tr) tt = Tr[j];
+        else { const float4 vj = reinterpret_cast<const float4*>(vb)[j]; tt = make_float4(vi * vj.x, vi * vj.y, vi * vj.z, vi * vj.w); }
+        d.x += cb * (pp.x - tt.x); d.y += cb * (pp.y - tt.y); d.z += cb * (pp.z - tt.z); d.w += cb * (pp.w - tt.w);
+      }
+      Ar[j] = make_float4(d.x * pp.x * (1.f - pp.x), d.y * pp.y * (1.f - pp.y), d.z * pp.z * (1.f - pp.z), d.w * pp.w * (1.f - pp.w));
+    }
+  }
+}
+
 // lib/core/function.py:261-267: v[b, y, x] = bilinear(align_corners=True, size H/2 x W/2) of max_k target[b, k, :, :]
 __global__ void __launch_bounds__(EW_THREADS) person_mask_kernel(const float* __restrict__ t, int K, int H, int W, long long n,
                                                                  float* __restrict__ v) {
@@ -1036,7 +1066,13 @@ extern "C" int rsg_train_trp_dscore(void* stream, const float* P, const float* d
   const long long per = ((long long)S * S + EW_THREADS - 1) / EW_THREADS;
   if (bpb > per) bpb = (int)per;
   if (bpb < 1) bpb = 1;
-  trp_dscore_kernel<<<B * bpb, EW_THREADS, 0, ST>>>(P, dP, T, v, coef, S, bpb, dA);
+  if ((S & 3) == 0 && al16p(P) && al16p(dP) && al16p(T) && al16p(v) && al16p(dA)) {
+    int rb = ceil_div(16ll * rsg_num_sms(), B);
+    if (rb > S) rb = S;
+    trp_dscore4_kernel<<<B * rb, EW_THREADS, 0, ST>>>(P, dP, T, v, coef, S, rb, dA);
+  } else {
+    trp_dscore_kernel<<<B * bpb, EW_THREADS, 0, ST>>>(P, dP, T, v, coef, S, bpb, dA);
+  }
   RSG_LAUNCH_CHECK();
   return RSG_OK;
 }
