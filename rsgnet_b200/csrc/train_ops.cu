@@ -474,7 +474,7 @@ __global__ void __launch_bounds__(EW_THREADS) copy2d_kernel(const float* __restr
                                                             long long dst_pitch, long long rows, int cols, int accumulate) {
   const long long n = rows * cols;
   GRID_STRIDE(i, n) {
-    const long long r = i / cols;
+    const long long r = (long long)((unsigned)i / (unsigned)cols);
     const int c = (int)(i - r * cols);
     const float v = src[r * src_pitch + c];
     float* d = dst + r * dst_pitch + c;
@@ -493,10 +493,11 @@ struct Perm {
 __device__ __forceinline__ void perm_body(const Perm& q, long long lo, long long stride) {
   const long long n = (long long)q.D0 * q.D1 * q.D2;
   for (long long i = lo; i < n; i += stride) {
-    const int i2 = (int)(i % q.D2);
-    const long long r = i / q.D2;
-    const int i1 = (int)(r % q.D1);
-    const long long i0 = r / q.D1;
+    const unsigned u = (unsigned)i;
+    const int i2 = (int)(u % (unsigned)q.D2);
+    const unsigned r = u / (unsigned)q.D2;
+    const int i1 = (int)(r % (unsigned)q.D1);
+    const long long i0 = r / (unsigned)q.D1;
     float v = 0.f;
     if (i1 < q.V1 && i2 < q.V2) v = q.src[i0 * q.s0 + i1 * q.s1 + i2 * q.s2];
     q.dst[i] = q.accumulate ? q.dst[i] + v : v;
@@ -518,11 +519,12 @@ __global__ void __launch_bounds__(EW_THREADS) nearest_fwd_kernel(const float* __
                                                                  float* __restrict__ y) {
   const int W = w * f, H = h * f;
   GRID_STRIDE(i, n) {
-    const int c = (int)(i % C);
-    long long r = i / C;
-    const int X = (int)(r % W); r /= W;
-    const int Y = (int)(r % H);
-    const long long nb = r / H;
+    const unsigned u = (unsigned)i;                 // 32-bit index arithmetic (n < 2^32, checked on the host): a 64-bit
+    const int c = (int)(u % (unsigned)C);           // division costs ~100 instructions, four of them per element
+    unsigned r = u / (unsigned)C;
+    const int X = (int)(r % (unsigned)W); r /= (unsigned)W;
+    const int Y = (int)(r % (unsigned)H);
+    const long long nb = r / (unsigned)H;
     y[i] = x[((nb * h + Y / f) * w + X / f) * C + c];
   }
 }
@@ -531,11 +533,12 @@ __global__ void __launch_bounds__(EW_THREADS) nearest_bwd_kernel(const float* __
                                                                  float* __restrict__ dx) {
   const int W = w * f, H = h * f;
   GRID_STRIDE(i, n) {                    // n = elements of dx
-    const int c = (int)(i % C);
-    long long r = i / C;
-    const int xx = (int)(r % w); r /= w;
-    const int yy = (int)(r % h);
-    const long long nb = r / h;
+    const unsigned u = (unsigned)i;
+    const int c = (int)(u % (unsigned)C);
+    unsigned r = u / (unsigned)C;
+    const int xx = (int)(r % (unsigned)w); r /= (unsigned)w;
+    const int yy = (int)(r % (unsigned)h);
+    const long long nb = r / (unsigned)h;
     float s = 0.f;
     for (int a = 0; a < f; ++a)
       for (int b2 = 0; b2 < f; ++b2) s += dy[((nb * H + yy * f + a) * W + xx * f + b2) * C + c];
@@ -557,11 +560,12 @@ __global__ void __launch_bounds__(EW_THREADS) bilinear_fwd_kernel(const float* _
                                                                   float* __restrict__ y) {
   const int H = 2 * h, W = 2 * w;
   GRID_STRIDE(i, n) {
-    const int c = (int)(i % C);
-    long long r = i / C;
-    const int X = (int)(r % W); r /= W;
-    const int Y = (int)(r % H);
-    const long long nb = r / H;
+    const unsigned u = (unsigned)i;                 // 32-bit index arithmetic (n < 2^32, checked on the host): a 64-bit
+    const int c = (int)(u % (unsigned)C);           // division costs ~100 instructions, four of them per element
+    unsigned r = u / (unsigned)C;
+    const int X = (int)(r % (unsigned)W); r /= (unsigned)W;
+    const int Y = (int)(r % (unsigned)H);
+    const long long nb = r / (unsigned)H;
     int y0, y1, x0, x1;
     float ly, lx;
     bil_src(Y, h, H, y0, y1, ly);
@@ -578,11 +582,12 @@ __global__ void __launch_bounds__(EW_THREADS) bilinear_bwd_kernel(const float* _
                                                                   float* __restrict__ dx) {   // dx zeroed by the caller
   const int H = 2 * h, W = 2 * w;
   GRID_STRIDE(i, n) {                    // n = elements of dy
-    const int c = (int)(i % C);
-    long long r = i / C;
-    const int X = (int)(r % W); r /= W;
-    const int Y = (int)(r % H);
-    const long long nb = r / H;
+    const unsigned u = (unsigned)i;                 // 32-bit index arithmetic (n < 2^32, checked on the host): a 64-bit
+    const int c = (int)(u % (unsigned)C);           // division costs ~100 instructions, four of them per element
+    unsigned r = u / (unsigned)C;
+    const int X = (int)(r % (unsigned)W); r /= (unsigned)W;
+    const int Y = (int)(r % (unsigned)H);
+    const long long nb = r / (unsigned)H;
     int y0, y1, x0, x1;
     float ly, lx;
     bil_src(Y, h, H, y0, y1, ly);
@@ -601,11 +606,12 @@ __global__ void __launch_bounds__(EW_THREADS) maxpool_fwd_kernel(const float* __
                                                                  float* __restrict__ y, unsigned char* __restrict__ idx) {
   const int h = H / 2, w = W / 2;
   GRID_STRIDE(i, n) {
-    const int c = (int)(i % C);
-    long long r = i / C;
-    const int xx = (int)(r % w); r /= w;
-    const int yy = (int)(r % h);
-    const long long nb = r / h;
+    const unsigned u = (unsigned)i;
+    const int c = (int)(u % (unsigned)C);
+    unsigned r = u / (unsigned)C;
+    const int xx = (int)(r % (unsigned)w); r /= (unsigned)w;
+    const int yy = (int)(r % (unsigned)h);
+    const long long nb = r / (unsigned)h;
     float best = 0.f;
     int bi = 0;
     for (int k = 0; k < 4; ++k) {
@@ -621,11 +627,12 @@ __global__ void __launch_bounds__(EW_THREADS) maxpool_bwd_kernel(const float* __
                                                                  int W, int C, long long n, float* __restrict__ dx) {
   const int h = H / 2, w = W / 2;
   GRID_STRIDE(i, n) {                    // n = elements of dx; odd trailing rows / columns get zero
-    const int c = (int)(i % C);
-    long long r = i / C;
-    const int X = (int)(r % W); r /= W;
-    const int Y = (int)(r % H);
-    const long long nb = r / H;
+    const unsigned u = (unsigned)i;                 // 32-bit index arithmetic (n < 2^32, checked on the host): a 64-bit
+    const int c = (int)(u % (unsigned)C);           // division costs ~100 instructions, four of them per element
+    unsigned r = u / (unsigned)C;
+    const int X = (int)(r % (unsigned)W); r /= (unsigned)W;
+    const int Y = (int)(r % (unsigned)H);
+    const long long nb = r / (unsigned)H;
     float v = 0.f;
     if ((Y >> 1) < h && (X >> 1) < w) {
       const long long o = ((nb * h + (Y >> 1)) * w + (X >> 1)) * C + c;
@@ -971,6 +978,7 @@ extern "C" int rsg_train_ew(void* stream, int op, const float* a, const float* b
 extern "C" int rsg_train_copy2d(void* stream, const float* src, long long src_pitch, float* dst, long long dst_pitch, long long rows,
                                 int cols, int accumulate) {
   RSG_REQUIRE(src && dst && rows >= 0 && cols > 0, "copy2d: bad arguments");
+  RSG_REQUIRE(rows * cols < (1ll << 32), "copy2d: more than 2^32 elements");
   if (rows == 0) return RSG_OK;
   copy2d_kernel<<<ew_grid(rows * cols, 4), EW_THREADS, 0, ST>>>(src, src_pitch, dst, dst_pitch, rows, cols, accumulate);
   RSG_LAUNCH_CHECK();
@@ -980,6 +988,7 @@ extern "C" int rsg_train_copy2d(void* stream, const float* src, long long src_pi
 extern "C" int rsg_train_permute3(void* stream, const float* src, float* dst, int D0, int D1, int D2, long long s0, long long s1,
                                   long long s2, int V1, int V2, int accumulate) {
   RSG_REQUIRE(src && dst && D0 > 0 && D1 > 0 && D2 > 0, "permute3: bad arguments");
+  RSG_REQUIRE((long long)D0 * D1 * D2 < (1ll << 32), "permute3: more than 2^32 elements");
   Perm q;
   q.src = src; q.dst = dst; q.D0 = D0; q.D1 = D1; q.D2 = D2; q.V1 = V1; q.V2 = V2; q.s0 = s0; q.s1 = s1; q.s2 = s2;
   q.accumulate = accumulate;
@@ -1004,6 +1013,7 @@ extern "C" int rsg_train_resample(void* stream, int kind, const float* in, int N
   // 2 bilinear x2 fwd; 3 bilinear x2 bwd (out zeroed here)
   RSG_REQUIRE(in && out && N > 0 && h > 0 && w > 0 && C > 0 && kind >= 0 && kind <= 3, "resample: bad arguments");
   RSG_REQUIRE(kind >= 2 || f >= 1, "resample: factor");
+  RSG_REQUIRE((long long)N * h * w * C * (kind < 2 ? (long long)f * f : 4) < (1ll << 32), "resample: more than 2^32 elements");
   const long long small = (long long)N * h * w * C;
   if (kind == 0) { const long long n = small * f * f; nearest_fwd_kernel<<<ew_grid(n, 4), EW_THREADS, 0, ST>>>(in, h, w, C, f, n, out); }
   else if (kind == 1) nearest_bwd_kernel<<<ew_grid(small, 2), EW_THREADS, 0, ST>>>(in, h, w, C, f, small, out);
@@ -1019,6 +1029,7 @@ extern "C" int rsg_train_resample(void* stream, int kind, const float* in, int N
 
 extern "C" int rsg_train_maxpool(void* stream, int backward, const float* in, unsigned char* idx, int N, int H, int W, int C, float* out) {
   RSG_REQUIRE(in && idx && out && N > 0 && H >= 2 && W >= 2 && C > 0, "maxpool: bad arguments");
+  RSG_REQUIRE((long long)N * H * W * C < (1ll << 32), "maxpool: more than 2^32 elements");
   if (!backward) { const long long n = (long long)N * (H / 2) * (W / 2) * C; maxpool_fwd_kernel<<<ew_grid(n, 2), EW_THREADS, 0, ST>>>(in, H, W, C, n, out, idx); }
   else { const long long n = (long long)N * H * W * C; maxpool_bwd_kernel<<<ew_grid(n, 4), EW_THREADS, 0, ST>>>(in, idx, H, W, C, n, out); }
   RSG_LAUNCH_CHECK();
