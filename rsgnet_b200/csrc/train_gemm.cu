@@ -631,6 +631,10 @@ int train_tc5_launch(cudaStream_t s, const float* A, const float* B, float* C, c
                      int ldb, int ldc, int batch, long long sA, long long sB, long long sC, long long tapB, int mode, int beta,
                      const int* geom);
 
+// train_wgrad5.cu: tcgen05 weight gradients (bf16 hi / lo splits) of the wide 3x3 stride-1 layers; -1 = not covered
+int train_wgrad5_launch(cudaStream_t s, const float* X, const float* dY, float* dW, int M, int Ca, int Nc, int ldx, int ldy,
+                        const int* geom);
+
 namespace {
 
 // wgrad for narrow layers (Ca <= 32 and Nc <= 32: the C0 = 32 branch at 64x48 and the heads at 128x96, 40 % of all weight-
@@ -823,6 +827,10 @@ extern "C" int rsg_train_wgrad(void* stream, const float* X, const float* dY, fl
   }
   p.vecX = al16(X) && ldx % 4 == 0;
   p.vecY = al16(dY) && ldy % 4 == 0;
+  if (precise == 0 && mode == 1) {             // wide 3x3 stride-1 layers: tensor pipe (tcgen05, bf16 hi / lo splits)
+    const int r = train_wgrad5_launch((cudaStream_t)stream, X, dY, dW, M, Ca, Nc, ldx, ldy, geom);
+    if (r >= 0) return r;
+  }
   if (Ca <= 32 && Nc <= 32 && !p.precise && mode == 1 && geom[4] == 3 && geom[5] == 3 && geom[6] == 1 && geom[7] == 1 &&
       geom[0] == geom[2] && geom[1] == geom[3] && geom[1] <= 110 && Ca % 4 == 0 && Nc % 4 == 0 && p.vecX && p.vecY &&
       (long long)M * ldx < (1ll << 31) && (long long)M * ldy < (1ll << 31) &&

@@ -79,6 +79,14 @@ CONV_CASES = [  # N, H, W, Ci, Co, k, stride, bias
     (4, 40, 30, 32, 32, 3, 1, False),       # narrow-layer weight-gradient kernel, several pixel splits
     (3, 33, 21, 16, 24, 3, 2, True),
     (2, 128, 96, 3, 32, 3, 2, False),
+    (2, 16, 12, 128, 128, 3, 1, False),     # tcgen05 weight gradients: 128-row accumulators
+    (3, 8, 6, 256, 256, 3, 1, True),        # ... 2 x 4 tiles, 3 kernel rows, position splits
+    (1, 5, 7, 64, 192, 3, 1, False),        # ... 64-row accumulators (M = 64 TMEM layout), one chunk
+    (5, 32, 24, 128, 64, 3, 1, False),
+    (2, 10, 8, 32, 64, 3, 1, False),        # ... partial tiles: 32 of 64 rows
+    (2, 10, 8, 64, 32, 3, 1, True),         # ... 32 of 64 columns
+    (2, 7, 9, 40, 72, 3, 1, False),         # ... 40 rows, 64 + 8 columns
+    (1, 12, 9, 200, 24, 3, 1, False),       # ... 128 + 72 rows, 24 columns (N = 32 MMAs)
 ]
 
 

@@ -57,4 +57,4 @@ for idx, (N, H, W, Ci, Co, k, s) in enumerate(SHAPES):
         row.append(res)
     gf = 2.0 * N * (H // s) * (W // s) * Ci * Co * k * k / 1e9
     print(f'{N}x{H}x{W} {Ci}->{Co} k{k} s{s}: {gf:6.1f} GF | tc5 fwd {row[0]["fwd"]*1e3:7.0f} us ({gf/row[0]["fwd"]:6.1f} TF) dgrad {row[0]["dgrad"]*1e3:7.0f} us ({gf/row[0]["dgrad"]:6.1f} TF)'
-          f' | mma fwd {row[1]["fwd"]*1e3:7.0f} us ({gf/row[1]["fwd"]:6.1f} TF) dgrad {row[1]["dgrad"]*1e3:7.0f} us | wgrad {row[1]["wgrad"]*1e3:7.0f} us ({gf/row[1]["wgrad"]:6.1f} TF)', flush=True)
+          f' | mma fwd {row[1]["fwd"]*1e3:7.0f} us ({gf/row[1]["fwd"]:6.1f} TF) dgrad {row[1]["dgrad"]*1e3:7.0f} us | wgrad tc5 {row[0]["wgrad"]*1e3:7.0f} us ({gf/row[0]["wgrad"]:6.1f} TF) mma {row[1]["wgrad"]*1e3:7.0f} us ({gf/row[1]["wgrad"]:6.1f} TF)', flush=True)
