@@ -410,19 +410,23 @@ __global__ void __launch_bounds__(T5_THREADS) conv3x3_tf32_tc5_kernel(const T5F 
 // convs on the critical path of a step): ONE channel chunk, so the halo and the weights of all nine taps (36 KB for 32 -> 32)
 // are fetched in a single cp.async batch -- one barrier round trip instead of nine -- and the 36 MMAs are issued back to back.
 __global__ void __launch_bounds__(T5_THREADS) conv3x3_tf32_small_kernel(const T5F p, const int mtiles) {
-  // persistent: a CTA keeps the weights of all nine taps and its TMEM accumulator, and walks over the 128-position tiles
-  // blockIdx.x, blockIdx.x + gridDim.x, ...; per tile only the halo is fetched (three CTAs per SM cover each other's waits)
+  // persistent: a CTA keeps the weights of all nine taps and walks over the 128-position tiles blockIdx.x, blockIdx.x +
+  // gridDim.x, ...; per tile only the halo is fetched.  Two halo buffers and two TMEM accumulators: while the MMAs of tile i
+  // run, the producers fetch the halo of tile i + 1 and write out tile i - 1 (one buffer / one accumulator made the CTA a
+  // serial chain fetch -> MMA -> epilogue: tensor pipe 22 % busy)
   extern __shared__ __align__(128) unsigned char smem_raw[];
-  __shared__ __align__(8) uint64_t bars[2];                       // operands landed | accumulator full
+  __shared__ __align__(8) uint64_t bars[4];                       // operands landed [2] | accumulator full [2]
   __shared__ uint32_t tmem_base_slot;
   const uint32_t bar0 = smem_u32(&bars[0]);
   const uint32_t sbase = (smem_u32(smem_raw) + 127u) & ~127u;
-  const uint32_t sB = sbase + p.a_bytes;                          // weights: [tap][8 k-groups][n_mma + 1][16 B]
+  const uint32_t sB = sbase + 2u * p.a_bytes;                     // weights: [tap][8 k-groups][n_mma + 1][16 B]
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int n0 = blockIdx.y * p.n_mma;
   if (tid == 0) {
     mbar_init(bar0, T5_PROD);
-    mbar_init(bar0 + 8u, 1);
+    mbar_init(bar0 + 8u, T5_PROD);
+    mbar_init(bar0 + 16u, 1);
+    mbar_init(bar0 + 24u, 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == 4) {
@@ -433,6 +437,7 @@ __global__ void __launch_bounds__(T5_THREADS) conv3x3_tf32_small_kernel(const T5
   __syncthreads();
   asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
   const uint32_t tmem_base = tmem_base_slot;
+  const uint32_t acc_cols = p.tmem_cols >> 1;                     // second accumulator
 
   if (warp < 4) {
     const int q = tid & 7, rr = tid >> 3, k = q * 4;
@@ -451,42 +456,33 @@ __global__ void __launch_bounds__(T5_THREADS) conv3x3_tf32_small_kernel(const T5
     const bool vec = (p.ldc & 3) == 0 && ((reinterpret_cast<uintptr_t>(p.C) & 15u) == 0);
     const bool vec32 = (p.ldc & 7) == 0 && ((reinterpret_cast<uintptr_t>(p.C) & 31u) == 0) && (n0 & 7) == 0;
     const uint32_t taddr = tmem_base + ((uint32_t)(warp * 32) << 16);
-    uint32_t ph = 0;
-    for (int tile = blockIdx.x; tile < mtiles; tile += gridDim.x, ph ^= 1u) {
-      const long long f0 = (long long)tile * T5_BM;
-      {
-        // halo position rr + 16 j <-> flat position f0 - P - 1 + rr + 16 j.  ncu: with two integer divisions per position the
-        // producers' address generation WAS the kernel (38 M of its instructions, IPC 1.15); one division pair per tile and
-        // incremental (column, row-in-image, image) updates instead.  The position is shifted by one image block so that
-        // the first tile's negative positions decode with ordinary division (image index -1 = outside).
-        // multiply-high division by the two constants (magic numbers from the host): ~10 independent instructions per
-        // position instead of two ~35-instruction division sequences or a loop-carried incremental update (clock64 timeline:
-        // the decode was 2450 of the 8500 cycles of a tile)
-        const uint32_t gs0 = (uint32_t)((int)f0 - p.P - 1 + rr + p.RPI * p.P);
-        for (int j = 0; j < p.JH; ++j) {
-          const int hp = rr + 16 * j;
-          if (hp >= p.NP) break;
-          const uint32_t gs = gs0 + 16u * (uint32_t)j;
-          const uint32_t R = __umulhi(gs, p.magicP), X = gs - R * (uint32_t)p.P;
-          const uint32_t nn = __umulhi(R, p.magicR), yy = R - nn * (uint32_t)p.RPI;
-          const int n = (int)nn - 1;
-          const bool ok = kok && n >= 0 && n < p.Nimg && X != 0 && yy != 0;
-          const int px = (n * p.H + ((int)yy - 1)) * p.W + ((int)X - 1);
-          cp_async16(sa + (uint32_t)j * 256u, ok ? (const void*)(p.A + (long long)px * p.lda + k) : (const void*)p.A, ok ? 16u : 0u);
-        }
+    // halo position rr + 16 j <-> flat position f0 - P - 1 + rr + 16 j, decoded by multiply-high division with the two
+    // constants (magic numbers from the host; the position is shifted by one image block so that the first tile's negative
+    // positions decode too: image index -1 = outside).  ncu / clock64 history: two integer divisions per position WERE the
+    // kernel (38 M instructions, IPC 1.15); a loop-carried incremental update was 2450 of a tile's 8500 cycles.
+    auto fetch = [&](int tile, uint32_t buf) {
+      const uint32_t gs0 = (uint32_t)(tile * T5_BM - p.P - 1 + rr + p.RPI * p.P);
+      const uint32_t dst = sa + buf * p.a_bytes;
+      for (int j = 0; j < p.JH; ++j) {
+        const int hp = rr + 16 * j;
+        if (hp >= p.NP) break;
+        const uint32_t gs = gs0 + 16u * (uint32_t)j;
+        const uint32_t R = __umulhi(gs, p.magicP), X = gs - R * (uint32_t)p.P;
+        const uint32_t nn = __umulhi(R, p.magicR), yy = R - nn * (uint32_t)p.RPI;
+        const int n = (int)nn - 1;
+        const bool ok = kok && n >= 0 && n < p.Nimg && X != 0 && yy != 0;
+        const int px = (n * p.H + ((int)yy - 1)) * p.W + ((int)X - 1);
+        cp_async16(dst + (uint32_t)j * 256u, ok ? (const void*)(p.A + (long long)px * p.lda + k) : (const void*)p.A, ok ? 16u : 0u);
       }
       asm volatile("cp.async.commit_group;" ::: "memory");
-      asm volatile("cp.async.wait_group 0;" ::: "memory");
-      asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-      mbar_arrive(bar0);
-      // epilogue of this tile (the MMAs have also finished reading the halo when the accumulator barrier completes)
-      mbar_wait(bar0 + 8u, ph);
-      asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-      const int m = t5f_pixel(p, f0 + warp * 32 + lane);
+    };
+    auto epilogue = [&](int tile, uint32_t buf) {
+      const int m = t5f_pixel(p, (long long)tile * T5_BM + warp * 32 + lane);
       float* crow = p.C + (long long)(m < 0 ? 0 : m) * p.ldc + n0;
+      const uint32_t ta = taddr + buf * acc_cols;
       for (int c = 0; c < p.n_mma; c += 16) {
         uint32_t v[16];
-        tmem_ld16(taddr + (uint32_t)c, v);
+        tmem_ld16(ta + (uint32_t)c, v);
         asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
         if (m >= 0) {
           if (vec32 && n0 + c + 15 < p.Nc) {                       // two full sectors per lane
@@ -517,29 +513,54 @@ __global__ void __launch_bounds__(T5_THREADS) conv3x3_tf32_small_kernel(const T5
           }
         }
       }
-      asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");      // the next tile's MMAs overwrite the accumulator
+      asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");      // a later tile's MMAs overwrite this accumulator
+    };
+    fetch(blockIdx.x, 0u);
+    uint32_t it = 0;
+    int prev = -1;
+    for (int tile = blockIdx.x; tile < mtiles; tile += gridDim.x, ++it) {
+      const uint32_t b = it & 1u;
+      asm volatile("cp.async.wait_group 0;" ::: "memory");          // halo of `tile` (and, first time, the weights) landed
+      asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+      mbar_arrive(bar0 + 8u * b);                                   // -> the MMAs of `tile` may start
+      if (prev >= 0) {                                              // MMAs of the previous tile done: its halo buffer is free
+        mbar_wait(bar0 + 16u + 8u * (b ^ 1u), ((it - 1u) >> 1) & 1u);
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+      }
+      const int next = tile + (int)gridDim.x;
+      if (next < mtiles) fetch(next, b ^ 1u);
+      if (prev >= 0) epilogue(prev, b ^ 1u);
+      prev = tile;
+    }
+    if (prev >= 0) {
+      const uint32_t lb = (it - 1u) & 1u;
+      mbar_wait(bar0 + 16u + 8u * lb, ((it - 1u) >> 1) & 1u);
+      asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+      epilogue(prev, lb);
     }
   } else {
     const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(p.n_mma >> 3) << 17) | ((128u >> 4) << 24);
     const uint32_t hi = desc_hi(128u);
     const int kk = (p.Ca + 7) >> 3;                                // K = 8 steps that hold channels
-    uint32_t ph = 0;
-    for (int tile = blockIdx.x; tile < mtiles; tile += gridDim.x, ph ^= 1u) {
-      mbar_wait(bar0, ph);
+    uint32_t it = 0;
+    for (int tile = blockIdx.x; tile < mtiles; tile += gridDim.x, ++it) {
+      const uint32_t b = it & 1u;
+      mbar_wait(bar0 + 8u * b, (it >> 1) & 1u);
       asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
       if (elect_one()) {
+        const uint32_t abase = sbase + b * p.a_bytes, d = tmem_base + b * acc_cols;
 #pragma unroll 1
         for (int tap = 0; tap < 9; ++tap) {
           const int dy = tap / 3, dx = tap - 3 * dy;
           const uint32_t off = p.flip ? (uint32_t)((2 - dy) * p.P + (2 - dx)) : (uint32_t)(dy * p.P + dx);
-          const uint32_t a0 = sbase + off * 16u, b0 = sB + (uint32_t)tap * p.b_stage;
+          const uint32_t a0 = abase + off * 16u, b0 = sB + (uint32_t)tap * p.b_stage;
           for (int k8 = 0; k8 < kk; ++k8) {
             const uint64_t ad = ((uint64_t)hi << 32) | desc_lo(a0 + 2u * k8 * p.a_plane, p.a_plane);
             const uint64_t bd = ((uint64_t)hi << 32) | desc_lo(b0 + 2u * k8 * p.b_plane, p.b_plane);
-            umma_tf32(tmem_base, ad, bd, idesc, (tap | k8) ? 1u : 0u);
+            umma_tf32(d, ad, bd, idesc, (tap | k8) ? 1u : 0u);
           }
         }
-        umma_commit(bar0 + 8u);
+        umma_commit(bar0 + 16u + 8u * b);
       }
       __syncwarp();
     }
@@ -603,19 +624,21 @@ int train_tc5_launch(cudaStream_t s, const float* A, const float* B, float* C, c
     static DeviceOnce once_f;
     if (once_f.first()) {
       RSG_CUDA(cudaFuncSetAttribute(conv3x3_tf32_tc5_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024));
-      RSG_CUDA(cudaFuncSetAttribute(conv3x3_tf32_small_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
+      RSG_CUDA(cudaFuncSetAttribute(conv3x3_tf32_small_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024));
       once_f.done();
     }
     if (Ca <= 32 && nm <= 64) {                // one channel chunk: everything in one cp.async batch
-      const size_t smem_s = 128 + (size_t)f.a_bytes + 9 * (size_t)f.b_stage;
-      if (smem_s <= 100 * 1024) {
+      const size_t smem_s = 128 + 2 * (size_t)f.a_bytes + 9 * (size_t)f.b_stage;      // two halo buffers + the nine taps' weights
+      if (smem_s <= 160 * 1024) {
+        T5F fs = f;
+        fs.tmem_cols = 2 * cols;                 // two accumulators
         int occ = 0;
         RSG_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, conv3x3_tf32_small_kernel, T5_THREADS, smem_s));
         if (occ < 1) occ = 1;
         int gx = occ * rsg_num_sms() / nt;     // persistent: exactly the CTAs that are resident at once
         if (gx > mtiles) gx = mtiles;
         if (gx < 1) gx = 1;
-        conv3x3_tf32_small_kernel<<<dim3((unsigned)gx, (unsigned)nt, 1), T5_THREADS, smem_s, s>>>(f, mtiles);
+        conv3x3_tf32_small_kernel<<<dim3((unsigned)gx, (unsigned)nt, 1), T5_THREADS, smem_s, s>>>(fs, mtiles);
         RSG_LAUNCH_CHECK();
         return RSG_OK;
       }
