@@ -232,6 +232,7 @@ def run_reference(args):
 # dram__bytes_read.sum + dram__bytes_write.sum per launch of the dominant kernel, from the committed
 # `ncu --set full` captures (profiles/r1_conv_bb_ncu_details.txt, r1_conv_tc5_ncu_details.txt,
 # r1_conv_bneck_ncu_details.txt; 512 forwards)
+TRAIN_NCU_TRAFFIC = 12.65e6       # conv3x3_tf32_small_kernel, 32->32 @64x48 x 32 samples (algorithmic: 25.2 MB)
 NCU_TRAFFIC = {('conv_tcgen05', 'conv 32->32 taps9 s1 64x48 +res'): 201.44e6 + 72.35e6,
                ('basic_block_tcgen05', 'bblock'): 100.78e6 + 54.63e6,
                ('bottleneck_tcgen05', 'bneck'): 902.87e6 + 759.45e6}
@@ -610,8 +611,9 @@ def run_train(args):
         r[1] += 1
         r[2] += fl
     launches, gflop = ts.last_launches, ts.last_flops / 1e9
-    # the dominant kernel by launch count and by its place on the critical path: forward / input gradient of the 3x3 convs of
-    # the C0 = 32 branch (132 launches per step), timed alone -- ten launches replayed as a CUDA graph, because an eager launch
+    # the roofline kernel: forward / input gradient of the 3x3 convs of the C0 = 32 branch (135 launches per step, the critical
+    # path of every HRNet module).  The step is flat -- profiles/r2_train_launches.csv: no (kernel, shape) group above 7 % of the
+    # serialised launch time, this one 5.3 % -- so a second kernel (the tcgen05 weight gradients) is timed beside it.  Timed alone -- ten launches replayed as a CUDA graph, because an eager launch
     # from Python costs more host time than this kernel runs
     from rsgnet_b200.train.tape import Tape as _Tape
     dk = None
@@ -640,6 +642,30 @@ def run_train(args):
         fl = 2.0 * B * fh * fw * c0 * c0 * 9
         dk = {'us_per_launch': us, 'flops': fl, 'tflops': fl / us / 1e6, 'bytes': 2.0 * B * fh * fw * c0 * 4,
               'shape': f'{c0}->{c0} 3x3 @{fh}x{fw} x {B} samples'}
+        # second kernel: the tcgen05 weight-gradient kernel on the 2 C0 branch (64 launches per step), same method
+        c1, h1, w1 = 2 * c0, fh // 2, fw // 2
+        with torch.cuda.stream(stream):
+            xb = torch.randn(B, h1, w1, c1, device=dev)
+            gb = torch.randn(B, h1, w1, c1, device=dev)
+            dwb = torch.zeros(9, c1, c1, device=dev)
+            runw = lambda: tp._wgrad(0, xb, gb, dwb, B * h1 * w1, c1, c1, mode=1, geom=(h1, w1, h1, w1, 3, 3, 1, 1))
+            runw()
+            torch.cuda.synchronize()
+            gw = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(gw, stream=stream):
+                for _ in range(10):
+                    runw()
+            gw.replay()
+            e0.record(stream)
+            gw.replay()
+            e1.record(stream)
+        torch.cuda.synchronize()
+        usw = e0.elapsed_time(e1) * 1e3 / 10
+        flw = 2.0 * B * h1 * w1 * c1 * c1 * 9
+        dk['wgrad'] = {'kernel': 'wgrad_tc5_kernel (tcgen05 kind::f16 on bf16 hi/lo splits, 3 MMAs per product)',
+                       'shape': f'{c1}->{c1} 3x3 @{h1}x{w1} x {B} samples', 'us_per_launch': usw, 'algorithmic_flops_per_launch': flw,
+                       'achieved_tflops': flw / usw / 1e6, 'frac_of_tf32_peak': flw / usw / 1e6 / (pk['tf_sus'] / 2.0),
+                       'launches_per_step': 64}
     except Exception as e:                      # informational: never fails the bench
         dk = {'error': str(e)[:200]}
     if rank != 0:
@@ -666,9 +692,14 @@ def run_train(args):
         'roofline': {'bound': 'tensor', 'kernel': 'conv3x3_tf32_small_kernel (tcgen05 kind::tf32 flat 3x3 conv): ' + str(dk.get('shape')),
                      'achieved': dk.get('tflops'), 'peak': tf32_peak, 'unit': 'TFLOP/s',
                      'frac': (dk['tflops'] / tf32_peak) if 'tflops' in dk else None,
-                     'traffic': None, 'peak_source': pk['src'] + ' bf16_tflops_sustained / 2 (TF32 runs at half the bf16 rate)',
+                     'traffic': TRAIN_NCU_TRAFFIC, 'traffic_source': 'constant from the committed ncu --set full capture '
+                     'profiles/r2_train_conv3x3_small_ncu_details.txt (dram__bytes_read.sum + dram__bytes_write.sum of one launch; not '
+                     'measured in this run; the 12.6 MB the kernel writes stay in the 126 MB L2)',
+                     'peak_source': pk['src'] + ' bf16_tflops_sustained / 2 (TF32 runs at half the bf16 rate)',
+                     'second_kernel': dk.get('wgrad'),
                      'algorithmic_flops_per_launch': dk.get('flops'), 'algorithmic_bytes_per_launch': dk.get('bytes'),
-                     'us_per_launch': dk.get('us_per_launch'), 'launches_per_step': 132,
+                     'us_per_launch': dk.get('us_per_launch'), 'launches_per_step': 135,
+                     'share_of_serialised_launch_time': 0.053,
                      'hbm_frac': (dk['bytes'] / dk['us_per_launch'] / 1e3 / pk['hbm']) if 'us_per_launch' in dk else None,
                      'matrix_family_eager': {'tflops': g[2] / g[0] / 1e9, 'ms': g[0], 'launches': g[1], 'share_of_step': g[0] / tot},
                      'families': fam,
