@@ -312,7 +312,9 @@ int rsg_train_gemm(void* stream, const float* A, const float* B, float* C, const
 
 /* Weight gradient: dW[tap][ci][co] += sum over the M pixels m of dY's grid of X[src(m, tap)][ci] * dY[m][co]  (fp32 atomics
  * over pixel splits: dW must hold zeros or the gradient accumulated so far).  mode / geom as for rsg_train_gemm, the
- * gather applies to X.  With mode 0 this is dW[ci][co] += X^T dY (Linear / 1x1 weight gradients, either orientation). */
+ * gather applies to X.  With mode 0 this is dW[ci][co] += X^T dY (Linear / 1x1 weight gradients, either orientation).
+ * precise: 0 = tensor pipe where a kernel covers the shape (3x3 stride-1, channel counts multiples of 8: tcgen05 on bf16
+ * hi / lo splits, ~5e-6 of max; else TF32 mma.sync), 1 = 3xTF32 (~2e-7), 2 = TF32 mma.sync (~3e-4). */
 int rsg_train_wgrad(void* stream, const float* X, const float* dY, float* dW, int M, int Ca, int Nc, int ldx, int ldy,
                     int mode, const int* geom, int precise);
 

@@ -276,10 +276,11 @@ __global__ void __launch_bounds__(GM_THREADS) gather_gemm_kernel(const GemmP p) 
 
 // ---------------------------------------------------------------------------------------------------------------------
 // wgrad: dW[tap][ci][co] += sum_m X[src(m, tap), ci] * dY[m, co]; 64 x 64 output tile, 64-pixel reduction chunks, split
-// over the pixels with fp32 atomics into a zeroed (or accumulating) dW.  This stays on mma.sync: the reduction runs over
-// pixels, so in NHWC memory both operands are MN-major (channels contiguous), and tcgen05.mma kind::tf32 returns ZEROS
-// as soon as either transpose bit of the instruction descriptor is set (measured on B200, profiles/r2_notes.md §9; kind::f16
-// accepts MN-major, attention_tc5.cu uses it) -- a tcgen05 version needs a transposing register-staged producer.
+// over the pixels with fp32 atomics into a zeroed (or accumulating) dW.  The reduction runs over pixels, so in NHWC memory
+// both operands are MN-major (channels contiguous), and tcgen05.mma kind::tf32 returns ZEROS as soon as either transpose bit of
+// the instruction descriptor is set (measured on B200, profiles/r2_notes.md §9).  kind::f16 accepts MN-major operands:
+// train_wgrad5.cu runs the wide 3x3 stride-1 layers on it with bf16 hi / lo splits; the kernels below keep the 1x1 and
+// stride-2 convs, odd channel counts, the narrow layers, and the 3xTF32 mode.
 struct WgradP {
   const float* X; const float* dY; float* dW;
   int M, Ca, Nc, ldx, ldy;
