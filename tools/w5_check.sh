@@ -1,4 +1,4 @@
-# scratch driver: training tests + the eager per-shape profile of one step
+# scratch driver: compute-sanitizer memcheck over the training conv / wgrad parity cases
 cd $GRAFT_REPO_ROOT
-timeout 900 python -m pytest tests/test_train_kernels_gpu.py tests/test_train_step_gpu.py -q -x 2>&1 | tail -3 > gpurun_out/w5.log
-timeout 600 python tools/bench_train.py > gpurun_out/train_shapes.log 2>&1
+timeout 900 compute-sanitizer --tool memcheck --error-exitcode 7 --print-limit 5 python -m pytest tests/test_train_kernels_gpu.py -q -x -k "conv_forward and 0-0.004" > gpurun_out/memcheck.log 2>&1
+echo "rc=$?" >> gpurun_out/memcheck.log
