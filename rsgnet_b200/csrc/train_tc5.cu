@@ -165,11 +165,18 @@ __global__ void __launch_bounds__(T5_THREADS) gemm_tf32_tc5_kernel(const T5P p) 
     const uint32_t taddr = tmem_base + ((uint32_t)(warp * 32) << 16);
     float* crow = Cp + (long long)m * p.ldc + n0;
     const bool vec = (p.ldc & 3) == 0 && ((reinterpret_cast<uintptr_t>(Cp) & 15u) == 0) && (n0 & 3) == 0;
+    const bool vec32 = !p.beta && (p.ldc & 7) == 0 && ((reinterpret_cast<uintptr_t>(Cp) & 31u) == 0) && (n0 & 7) == 0;
     for (int c = 0; c < p.n_mma; c += 16) {
       uint32_t v[16];
       tmem_ld16(taddr + (uint32_t)c, v);
       asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-      if (m < p.M) {
+      if (m < p.M && vec32 && n0 + c + 15 < p.Nc) {               // two full 32-byte sectors per lane and instruction
+        float f[16];
+#pragma unroll
+        for (int e = 0; e < 16; ++e) f[e] = __uint_as_float(v[e]) + (p.bias ? p.bias[n0 + c + e] : 0.f);
+        stg256(crow + c, f);
+        stg256(crow + c + 8, f + 8);
+      } else if (m < p.M) {
 #pragma unroll
         for (int g = 0; g < 4; ++g) {
           const int n = n0 + c + 4 * g;
@@ -338,11 +345,18 @@ __global__ void __launch_bounds__(T5_THREADS) conv3x3_tf32_tc5_kernel(const T5F 
     const uint32_t taddr = tmem_base + ((uint32_t)(warp * 32) << 16);
     float* crow = p.C + (long long)(m < 0 ? 0 : m) * p.ldc + n0;
     const bool vec = (p.ldc & 3) == 0 && ((reinterpret_cast<uintptr_t>(p.C) & 15u) == 0);
+    const bool vec32 = !p.beta && (p.ldc & 7) == 0 && ((reinterpret_cast<uintptr_t>(p.C) & 31u) == 0) && (n0 & 7) == 0;
     for (int c = 0; c < p.n_mma; c += 16) {
       uint32_t v[16];
       tmem_ld16(taddr + (uint32_t)c, v);
       asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-      if (m >= 0) {
+      if (m >= 0 && vec32 && n0 + c + 15 < p.Nc) {                // two full 32-byte sectors per lane and instruction
+        float f[16];
+#pragma unroll
+        for (int e = 0; e < 16; ++e) f[e] = __uint_as_float(v[e]) + (p.bias ? p.bias[n0 + c + e] : 0.f);
+        stg256(crow + c, f);
+        stg256(crow + c + 8, f + 8);
+      } else if (m >= 0) {
 #pragma unroll
         for (int g = 0; g < 4; ++g) {
           const int n = n0 + c + 4 * g;
@@ -662,7 +676,10 @@ int train_tc5_launch(cudaStream_t s, const float* A, const float* B, float* C, c
   uint32_t cols = 32;
   while (cols < (uint32_t)n_mma) cols <<= 1;
   p.tmem_cols = cols;
-  const size_t smem = 128 + (size_t)T5_STAGES * p.stage_bytes;
+  // the ring is walked taps x ceil(Ca / 32) times: a short reduction (the 64 -> 256 1x1 convs of layer1: two iterations of
+  // 49 KB) only touches its first stages, and asking for all four cost the second resident CTA per SM
+  const long long niter = (long long)p.taps * ((Ca + T5_BK - 1) / T5_BK);
+  const size_t smem = 128 + (size_t)(niter < T5_STAGES ? niter : T5_STAGES) * p.stage_bytes;
   static DeviceOnce attr_once;
   if (attr_once.first()) {
     RSG_CUDA(cudaFuncSetAttribute(gemm_tf32_tc5_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));

@@ -1,4 +1,5 @@
 # A/B of two builds of the library on the same box: gpurun_ab/lib_old.so vs gpurun_ab/lib_new.so, alternating
+# (boxes differ by 1-3 %, more than most single changes).  Build both here, then `gpurun -- bash tools/ab_train.sh`.
 cd $GRAFT_REPO_ROOT
 cp rsgnet_b200/librsg_b200.so /tmp/lib_keep.so
 for r in 1 2; do
@@ -9,4 +10,5 @@ import json,sys; d=json.loads(sys.stdin.read()); print('$v', round(d['value'],1)
   done
 done > gpurun_out/ab.log 2>&1
 cp /tmp/lib_keep.so rsgnet_b200/librsg_b200.so
-timeout 600 python -m pytest tests/test_train_step_gpu.py -q -x -k dropin 2>&1 | grep -E "Error|assert|passed|failed" | head -8 >> gpurun_out/ab.log
+timeout 600 python -m pytest tests/test_train_kernels_gpu.py -q -x 2>&1 | tail -1 >> gpurun_out/ab.log
+timeout 300 python tools/bench_train_gemm.py 4 5 2>&1 | tail -2 >> gpurun_out/ab.log
