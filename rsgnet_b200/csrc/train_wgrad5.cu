@@ -65,6 +65,17 @@ __device__ __forceinline__ void split8(const float4& a, const float4& b, uint4& 
   lo = make_uint4(l[0], l[1], l[2], l[3]);
 }
 
+// 8 consecutive floats of a pixel: one 32-byte load (a full sector per lane and instruction) when the row is 32-byte aligned
+__device__ __forceinline__ void ld8(const float* p, bool v32, float4& a, float4& b) {
+  if (v32) {
+    asm volatile("ld.global.nc.v8.f32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+                 : "=f"(a.x), "=f"(a.y), "=f"(a.z), "=f"(a.w), "=f"(b.x), "=f"(b.y), "=f"(b.z), "=f"(b.w) : "l"(p));
+  } else {
+    a = __ldg(reinterpret_cast<const float4*>(p));
+    b = __ldg(reinterpret_cast<const float4*>(p) + 1);
+  }
+}
+
 __device__ __forceinline__ void sts16(uint32_t addr, const uint4& v) {
   asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
 }
@@ -122,6 +133,8 @@ __global__ void __launch_bounds__(W5_THREADS, 2) wgrad_tc5_kernel(const W5P p) {
     // channel groups past the end of a partial tile are neither loaded nor stored: their accumulator rows / columns hold
     // whatever the shared memory held and are never read (rows and columns of a product are independent)
     const bool xg = 8 * gx < mvalid, yg = 8 * gy < nvalid;
+    const bool x32 = (p.ldx & 7) == 0 && (reinterpret_cast<uintptr_t>(p.X) & 31u) == 0;
+    const bool y32 = (p.ldy & 7) == 0 && (reinterpret_cast<uintptr_t>(p.dY) & 31u) == 0;
     uint32_t s = 0, ph = 0;
     for (int c = 0; c < nchunk; ++c) {
       const int f0 = fb + c * W5_KC;
@@ -135,9 +148,7 @@ __global__ void __launch_bounds__(W5_THREADS, 2) wgrad_tc5_kernel(const W5P p) {
         if (h < W5_KC + 2 && xg) {
           const int px = w5_pixel(p, fx + h);
           if (px >= 0) {
-            const float4* src = reinterpret_cast<const float4*>(Xc + (long long)px * p.ldx);
-            xa[j] = __ldg(src);
-            xb[j] = __ldg(src + 1);
+            ld8(Xc + (long long)px * p.ldx, x32, xa[j], xb[j]);
           }
         }
       }
@@ -148,9 +159,7 @@ __global__ void __launch_bounds__(W5_THREADS, 2) wgrad_tc5_kernel(const W5P p) {
         yb[j] = ya[j];
         const int px = yg && f0 + r < fe ? w5_pixel(p, f0 + r) : -1;
         if (px >= 0) {
-          const float4* src = reinterpret_cast<const float4*>(Yc + (long long)px * p.ldy);
-          ya[j] = __ldg(src);
-          yb[j] = __ldg(src + 1);
+          ld8(Yc + (long long)px * p.ldy, y32, ya[j], yb[j]);
         }
       }
       mbar_wait(BAR(W5_STAGES + s), ph ^ 1u);                      // the MMAs that read this stage have completed
