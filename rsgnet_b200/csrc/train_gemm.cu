@@ -835,7 +835,9 @@ extern "C" int rsg_train_wgrad(void* stream, const float* X, const float* dY, fl
   if (Ca <= 32 && Nc <= 32 && !p.precise && mode == 1 && geom[4] == 3 && geom[5] == 3 && geom[6] == 1 && geom[7] == 1 &&
       geom[0] == geom[2] && geom[1] == geom[3] && geom[1] <= 110 && Ca % 4 == 0 && Nc % 4 == 0 && p.vecX && p.vecY &&
       (long long)M * ldx < (1ll << 31) && (long long)M * ldy < (1ll << 31) &&
-      (long long)(M / (geom[0] * geom[1])) * (geom[0] + 1) * (geom[1] + 1) < (1ll << 31)) {
+      (long long)(M / (geom[0] * geom[1])) * (geom[0] + 1) * (geom[1] + 1) < (1ll << 31) &&
+      // the multiply-high position decode is exact for positions below 2^32 / P (two image blocks of slack: shift + halo)
+      ((long long)(M / (geom[0] * geom[1]) + 2) * (geom[0] + 1) * (geom[1] + 1) + 512) * (geom[1] + 1) < (1ll << 32)) {
     WgradFlatP f;                              // narrow 3x3 stride-1 layers: flat form, X and dY read once
     memset(&f, 0, sizeof(f));
     f.X = X; f.dY = dY; f.dW = dW; f.H = geom[0]; f.W = geom[1]; f.Nimg = M / (f.H * f.W); f.Ca = Ca; f.Nc = Nc; f.ldx = ldx; f.ldy = ldy;

@@ -611,7 +611,9 @@ int train_tc5_launch(cudaStream_t s, const float* A, const float* B, float* C, c
   // every 3x3 stride-1 pad-1 convolution (forward: mode 1, input gradient: mode 2) takes the flat form
   if (mode != 0 && batch == 1 && !beta && geom[4] == 3 && geom[5] == 3 && geom[6] == 1 && geom[7] == 1 && geom[0] == geom[2] &&
       geom[1] == geom[3] && geom[1] <= 110 && (long long)M * lda < (1ll << 31) &&
-      (long long)(M / (geom[0] * geom[1])) * (geom[0] + 1) * (geom[1] + 1) < (1ll << 31)) {
+      (long long)(M / (geom[0] * geom[1])) * (geom[0] + 1) * (geom[1] + 1) < (1ll << 31) &&
+      // the multiply-high position decode is exact for positions below 2^32 / P (two image blocks of slack: shift + halo)
+      ((long long)(M / (geom[0] * geom[1]) + 2) * (geom[0] + 1) * (geom[1] + 1) + 512) * (geom[1] + 1) < (1ll << 32)) {
     T5F f;
     memset(&f, 0, sizeof(f));
     f.A = A; f.B = B; f.C = C; f.bias = bias; f.H = geom[0]; f.W = geom[1]; f.Nimg = M / (f.H * f.W); f.Ca = Ca; f.Nc = Nc;

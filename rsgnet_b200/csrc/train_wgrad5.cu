@@ -273,6 +273,8 @@ int train_wgrad5_launch(cudaStream_t s, const float* X, const float* dY, float* 
   if (total + (long long)(H + 1) * (W + 1) + 2 * (W + 1) + 256 >= (1ll << 31) || (long long)M * ldx >= (1ll << 31) ||
       (long long)M * ldy >= (1ll << 31))
     return -1;
+  // the multiply-high position decode is exact for positions below 2^32 / P (two image blocks of slack: shift + halo)
+  if (((nimg + 2) * (H + 1) * (W + 1) + 512) * (W + 1) >= (1ll << 32)) return -1;
   W5P p;
   memset(&p, 0, sizeof(p));
   p.X = X; p.dY = dY; p.dW = dW; p.Nimg = (int)nimg; p.H = H; p.W = W; p.Ca = Ca; p.Nc = Nc; p.ldx = ldx; p.ldy = ldy;
