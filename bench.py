@@ -613,7 +613,7 @@ def run_train(args):
     launches, gflop = ts.last_launches, ts.last_flops / 1e9
     # the roofline kernel: forward / input gradient of the 3x3 convs of the C0 = 32 branch (135 launches per step, the critical
     # path of every HRNet module).  The step is flat -- profiles/r2_train_launches.csv: no (kernel, shape) group above 7 % of the
-    # serialised launch time, this one 5.3 % -- so a second kernel (the tcgen05 weight gradients) is timed beside it.  Timed alone -- ten launches replayed as a CUDA graph, because an eager launch
+    # serialised launch time, this one 5.5 % -- so a second kernel (the tcgen05 weight gradients) is timed beside it.  Timed alone -- ten launches replayed as a CUDA graph, because an eager launch
     # from Python costs more host time than this kernel runs
     from rsgnet_b200.train.tape import Tape as _Tape
     dk = None
@@ -699,7 +699,7 @@ def run_train(args):
                      'second_kernel': dk.get('wgrad'),
                      'algorithmic_flops_per_launch': dk.get('flops'), 'algorithmic_bytes_per_launch': dk.get('bytes'),
                      'us_per_launch': dk.get('us_per_launch'), 'launches_per_step': 135,
-                     'share_of_serialised_launch_time': 0.053,
+                     'share_of_serialised_launch_time': 0.055,
                      'hbm_frac': (dk['bytes'] / dk['us_per_launch'] / 1e3 / pk['hbm']) if 'us_per_launch' in dk else None,
                      'matrix_family_eager': {'tflops': g[2] / g[0] / 1e9, 'ms': g[0], 'launches': g[1], 'share_of_step': g[0] / tot},
                      'families': fam,
